@@ -1,0 +1,528 @@
+"""
+CPU ORACLE -- TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (rlgym_ppo_b200) never imports it and has no CPU fallback.
+
+This is a restatement, in NumPy / torch-CPU tensor math (no autograd, no nn.Module), of the learner-side
+hot path of AechPro/rlgym-ppo v1.3.13.  Every function cites the reference file:line it follows.  The
+reference's own arithmetic lives in two third-party dependencies that are not under /root/reference:
+
+  * PyTorch (requirements.txt:9 `torch>1.13`; 2.11.0+cu128 in this image): nn.Linear / ReLU / Softmax /
+    autograd / torch.optim.Adam / clip_grad_norm_.  Restated here explicitly: Linear is x @ W.T + b, the
+    backward is the analytic chain rule of SURVEY.md Appendix A.3, Adam follows the published algorithm
+    as implemented by torch.optim.Adam (bias-corrected, eps added after the sqrt, no weight decay).
+  * NumPy (requirements.txt:7; 2.3.5 here): np.random.RandomState(seed).permutation -- the legacy MT19937
+    stream, frozen by NumPy's compatibility policy.  The oracle calls NumPy itself for it and, separately,
+    restates the algorithm (mt19937_permutation) so the product's C implementation can be checked.
+
+PARITY PINNING: the reference has no tests or golden vectors.  The oracle is pinned
+against outputs of the reference itself, imported in the authoring container from /root/reference by
+tests/golden/make_golden.py; the resulting fixtures are committed under tests/golden/ and
+tests/test_oracle_vs_golden.py checks every function here against them.
+
+Scalar-promotion note (compute_gae, WelfordRunningStat): the reference mixes np.float32 scalars, Python
+floats and an f64 `truncated` array, so its rounding points depend on the NumPy major version.  The
+functions below reproduce what NumPy >= 2 (NEP 50) executes, which is what the goldens were made with:
+delta is rounded to f32, the A and R accumulations are f64.  `gae_fp64` is the all-f64 statement
+(NumPy 1.x behaviour); the two differ by ~2e-6 abs, inside the 1e-5 tolerance.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# --------------------------------------------------------------------------------------------------
+# GAE  (rlgym_ppo/util/torch_functions.py:36-78)
+# --------------------------------------------------------------------------------------------------
+
+
+def gae_nep50(rews, dones, truncated, values, gamma=0.99, lmbda=0.95, return_std=1.0):
+    """torch_functions.py:50-78 with the exact rounding points NumPy>=2 executes.
+
+    rews, dones: f32 [N]; truncated: f64 (or f32) [N]; values: f32-representable [N+1];
+    return_std: f32 scalar or None.  Returns (value_targets f32, advantages f32, returns f64).
+    """
+    rews = np.asarray(rews, dtype=np.float32)
+    dones = np.asarray(dones, dtype=np.float32)
+    trunc = np.asarray(truncated, dtype=np.float64)
+    vals = np.asarray(values, dtype=np.float64)  # python floats in the reference (learner.py:352)
+    n = rews.shape[0]
+    adv = np.zeros(n, dtype=np.float64)
+    rets = np.zeros(n, dtype=np.float64)
+    f32 = np.float32
+    gl32 = f32(gamma * lmbda)  # python float * np.float32 -> float32 (weak python scalar)
+    last_gae = 0.0
+    last_ret = 0.0
+    for t in range(n - 1, -1, -1):
+        nd = f32(1.0) - dones[t]  # torch_functions.py:59 (f32)
+        nt = 1.0 - trunc[t]  # :60 (f64)
+        if return_std is not None:  # :62-65
+            nr = f32(rews[t] / f32(return_std))
+            nr = f32(min(max(nr, f32(-10)), f32(10)))
+        else:
+            nr = rews[t]
+        gv = f32(gamma * vals[t + 1])  # python-float product, rounded when it meets the f32 nd
+        pred = f32(nr + f32(gv * nd))  # :67
+        delta = f32(pred - f32(vals[t]))  # :68
+        last_ret = float(rews[t]) + last_ret * gamma * float(nd) * nt  # :69 (f64)
+        rets[t] = last_ret
+        last_gae = float(delta) + float(f32(gl32 * nd)) * nt * last_gae  # :72 (f64)
+        adv[t] = last_gae
+    advantages = adv.astype(np.float32)  # :76
+    value_targets = (vals[:-1] + adv).astype(np.float32)  # :77
+    return value_targets, advantages, rets
+
+
+def gae_fp64(rews, dones, truncated, values, gamma=0.99, lmbda=0.95, return_std=1.0):
+    """the all-f64 statement of torch_functions.py:50-78 (NumPy 1.x promotion)."""
+    r = np.asarray(rews, dtype=np.float64)
+    d = np.asarray(dones, dtype=np.float64)
+    tr = np.asarray(truncated, dtype=np.float64)
+    v = np.asarray(values, dtype=np.float64)
+    n = r.shape[0]
+    adv = np.zeros(n)
+    rets = np.zeros(n)
+    la = 0.0
+    lr = 0.0
+    for t in range(n - 1, -1, -1):
+        nd = 1.0 - d[t]
+        nt = 1.0 - tr[t]
+        nr = min(max(r[t] / float(return_std), -10.0), 10.0) if return_std is not None else r[t]
+        delta = nr + gamma * v[t + 1] * nd - v[t]
+        lr = r[t] + lr * gamma * nd * nt
+        rets[t] = lr
+        la = delta + gamma * lmbda * nd * nt * la
+        adv[t] = la
+    return (v[:-1] + adv).astype(np.float32), adv.astype(np.float32), rets
+
+
+_C_LIB = None
+
+
+def _c_lib():
+    """The C restatement (oracle/gae_oracle.c), built by oracle/Makefile into oracle/_build/."""
+    global _C_LIB
+    if _C_LIB is None:
+        path = os.path.join(_HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle` (or __graft_entry__.build())")
+        lib = ctypes.CDLL(path)
+        P = ctypes.c_void_p
+        lib.oracle_gae_nep50.argtypes = [P, P, P, P, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                         ctypes.c_int, ctypes.c_float, P, P, P]
+        lib.oracle_gae_nep50.restype = None
+        lib.oracle_welford_update.argtypes = [P, P, P, P, ctypes.c_int64]
+        lib.oracle_welford_update.restype = None
+        lib.oracle_mt19937_permutation.argtypes = [P, P, ctypes.c_int64, P]
+        lib.oracle_mt19937_permutation.restype = None
+        _C_LIB = lib
+    return _C_LIB
+
+
+def gae_nep50_c(rews, dones, truncated, values, gamma=0.99, lmbda=0.95, return_std=1.0):
+    """Same as gae_nep50, through the plain-C restatement (fast enough for 1e8 steps)."""
+    lib = _c_lib()
+    r = np.ascontiguousarray(rews, dtype=np.float32)
+    d = np.ascontiguousarray(dones, dtype=np.float32)
+    tr = np.ascontiguousarray(truncated, dtype=np.float64)
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    n = r.shape[0]
+    adv = np.empty(n, np.float32)
+    vt = np.empty(n, np.float32)
+    rets = np.empty(n, np.float64)
+    lib.oracle_gae_nep50(r.ctypes.data, d.ctypes.data, tr.ctypes.data, v.ctypes.data, n, gamma, lmbda,
+                         0 if return_std is None else 1, 1.0 if return_std is None else float(return_std),
+                         adv.ctypes.data, vt.ctypes.data, rets.ctypes.data)
+    return vt, adv, rets
+
+
+# --------------------------------------------------------------------------------------------------
+# WelfordRunningStat  (rlgym_ppo/util/running_stats.py:15-98)
+# --------------------------------------------------------------------------------------------------
+
+
+class WelfordOracle:
+    """running_stats.py:21-69.  State f32, intermediates f64 when the sample is f64 (NumPy>=2)."""
+
+    def __init__(self, shape):
+        self.shape = shape
+        self.mean = np.zeros(shape, np.float32)  # :25
+        self.m2 = np.zeros(shape, np.float32)  # :26 ("running_variance" holds M2)
+        self.count = 0
+
+    def update(self, sample):  # :37-46
+        sample = np.asarray(sample)
+        cc = self.count
+        self.count += 1
+        if sample.dtype == np.float64:
+            delta = (sample.astype(np.float64) - self.mean.astype(np.float64)).reshape(self.mean.shape)
+            delta_n = delta / self.count
+            self.mean = (self.mean.astype(np.float64) + delta_n).astype(np.float32)
+            self.m2 = (self.m2.astype(np.float64) + delta * delta_n * cc).astype(np.float32)
+        else:
+            s = sample.astype(np.float32)
+            delta = (s - self.mean).reshape(self.mean.shape)
+            delta_n = (delta / np.float32(self.count)).astype(np.float32)
+            self.mean = self.mean + delta_n
+            self.m2 = self.m2 + delta * delta_n * np.float32(cc)
+
+    def increment(self, samples, num):  # :30-35
+        if num > 1:
+            for i in range(num):
+                self.update(samples[i])
+        else:
+            self.update(samples)
+
+    def get_mean(self):  # :54-58
+        if self.count < 2:
+            return np.zeros(self.shape, np.float32)
+        return self.mean
+
+    def get_std(self):  # :60-69
+        if self.count < 2:
+            return np.ones(self.shape, np.float32)
+        var = self.m2 / np.float32(self.count - 1)
+        var = np.where(var == 0, np.float32(1.0), var)
+        return np.sqrt(var).astype(np.float32)
+
+    def merge(self, other_mean, other_m2, other_count):  # :71-98
+        if other_count == 0:
+            return
+        om = np.asarray(other_mean, np.float32).reshape(self.mean.shape)
+        ov = np.asarray(other_m2, np.float32).reshape(self.m2.shape)
+        count = self.count + other_count
+        d = om - self.mean
+        self.m2 = self.m2 + ov + d * d * self.count * other_count / count
+        self.mean = (self.count * self.mean + other_count * om) / count
+        self.count = count
+
+
+# --------------------------------------------------------------------------------------------------
+# ExperienceBuffer  (rlgym_ppo/ppo/experience_buffer.py:17-102)
+# --------------------------------------------------------------------------------------------------
+
+FIELDS = ("states", "actions", "log_probs", "rewards", "next_states", "dones", "truncated", "values",
+          "advantages")
+
+
+def fifo_cat(old, new, size):
+    """experience_buffer.py:17-37 `_cat`: keep the newest `size` rows of old (+) new."""
+    if len(new) > size:
+        return new[-size:].copy()
+    if len(new) == size:
+        return new
+    if len(old) + len(new) > size:
+        return np.concatenate((old[len(new) - size:], new), 0)
+    return np.concatenate((old, new), 0)
+
+
+class BufferOracle:
+    def __init__(self, max_size, seed):  # :39-52
+        self.max_size = max_size
+        self.rng = np.random.RandomState(seed)
+        self.f = {k: np.zeros((0,), np.float32) for k in FIELDS}
+
+    def submit(self, **fields):  # :54-80
+        for k in FIELDS:
+            new = np.asarray(fields[k], dtype=np.float32)
+            old = self.f[k]
+            if old.shape[0] == 0 and new.ndim > 1:
+                old = np.zeros((0,) + new.shape[1:], np.float32)
+            self.f[k] = fifo_cat(old, new, self.max_size)
+
+    def batches(self, batch_size):  # :89-102 ; yields (indices, 5-tuple) per batch
+        total = self.f["rewards"].shape[0]
+        idx = self.rng.permutation(total)  # :98 one permutation per call (= per epoch)
+        start = 0
+        while start + batch_size <= total:  # :100 remainder dropped
+            ii = idx[start:start + batch_size]
+            yield ii, (self.f["actions"][ii], self.f["log_probs"][ii], self.f["states"][ii],
+                       self.f["values"][ii], self.f["advantages"][ii])  # :82-87 field order
+            start += batch_size
+
+
+# --- legacy MT19937 permutation, restated (numpy/random/mtrand.pyx RandomState.permutation -> shuffle,
+#     numpy/random/src/legacy + mt19937.c: rk_interval masked rejection, Fisher-Yates from the top) -----
+
+
+def mt19937_permutation(key, pos, n):
+    """Pure-Python restatement (small n only).  key: uint32[624], pos: int.  Returns (perm, key, pos)."""
+    mt = [int(x) for x in key]
+
+    def gen():
+        nonlocal pos
+        if pos == 624:
+            for k in range(624):
+                y = (mt[k] & 0x80000000) | (mt[(k + 1) % 624] & 0x7FFFFFFF)
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if (y & 1) else 0)
+            pos = 0
+        y = mt[pos]
+        pos += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+    def interval(mx):
+        if mx == 0:
+            return 0
+        mask = mx
+        for s in (1, 2, 4, 8, 16, 32):
+            mask |= mask >> s
+        if mx <= 0xFFFFFFFF:
+            while True:
+                v = gen() & mask
+                if v <= mx:
+                    return v
+        while True:
+            v = ((gen() << 32) | gen()) & mask
+            if v <= mx:
+                return v
+
+    x = list(range(n))
+    for i in range(n - 1, 0, -1):
+        j = interval(i)
+        x[i], x[j] = x[j], x[i]
+    return np.asarray(x, np.int64), np.asarray(mt, np.uint32), pos
+
+
+def mt19937_permutation_c(key, pos, n):
+    lib = _c_lib()
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    p = np.asarray([pos], dtype=np.int32)
+    out = np.empty(n, np.int64)
+    lib.oracle_mt19937_permutation(key.ctypes.data, p.ctypes.data, n, out.ctypes.data)
+    return out, key, int(p[0])
+
+
+# --------------------------------------------------------------------------------------------------
+# Networks  (discrete_policy.py:22-42, value_estimator.py:19-36): params = [W0,b0,W1,b1,...], W [out,in]
+# --------------------------------------------------------------------------------------------------
+
+
+def mlp_forward(params, x, quant=None):
+    """Linear/ReLU stack; returns (pre-softmax output, list of layer inputs).  `quant` optionally rounds
+    both GEMM operands (e.g. to bf16) so the oracle can mirror the tensor-core kernels' rounding points."""
+    q = quant if quant is not None else (lambda t: t)
+    acts = []
+    h = x
+    nl = len(params) // 2
+    for i in range(nl):
+        acts.append(h)
+        h = q(h) @ q(params[2 * i]).t() + params[2 * i + 1]
+        if i < nl - 1:
+            h = torch.relu(h)
+            if quant is not None:
+                h = q(h)  # the kernels store hidden activations in bf16
+    return h, acts
+
+
+def policy_probs(params, x, quant=None):
+    """discrete_policy.py:35-42 get_output: softmax over the last Linear."""
+    z, _ = mlp_forward(params, x, quant)
+    return torch.softmax(z, dim=-1)
+
+
+def action_logprob(params, x, actions, quant=None):
+    """discrete_policy.py:54,60: clamp(1e-11,1) -> log -> gather."""
+    p = torch.clamp(policy_probs(params, x, quant), 1e-11, 1.0)
+    return torch.log(p).gather(-1, actions.view(-1, 1).long()).flatten()
+
+
+def sample_inverse_cdf(probs, u):
+    """Categorical sample by inverse CDF on the clamped probabilities (the product's K-a kernel contract):
+    action = first j with cumsum(p)[j] > u * sum(p); torch.multinomial's own stream is not reproducible
+    outside torch, so the sampler is pinned on injected uniforms + a chi-square test instead."""
+    p = torch.clamp(probs, 1e-11, 1.0).double()
+    c = torch.cumsum(p, -1)
+    thr = (u.double() * c[:, -1]).unsqueeze(-1)
+    a = (c > thr).float().argmax(-1)
+    return a
+
+
+def mlp_backward(params, acts, dout, quant=None):
+    """Analytic backward of the Linear/ReLU stack.  Returns grads in params order."""
+    q = quant if quant is not None else (lambda t: t)
+    nl = len(params) // 2
+    grads = [None] * len(params)
+    g = dout
+    for i in range(nl - 1, -1, -1):
+        gq = q(g)
+        grads[2 * i] = gq.t() @ q(acts[i])
+        grads[2 * i + 1] = g.sum(0)
+        if i > 0:
+            g = (gq @ q(params[2 * i])) * (acts[i] > 0).to(g.dtype)  # acts[i] = relu output of layer i-1
+    return grads
+
+
+def ppo_minibatch(pol, val, obs, acts, old_logp, targets, adv, clip, ent_coef, batch_size, quant=None):
+    """ppo_learner.py:146-185 + discrete_policy.py:64-80 forward, and the analytic backward of
+    SURVEY.md A.3.  Returns (policy grads, value grads, metrics dict with per-minibatch means)."""
+    mb = obs.shape[0]
+    w = 1.0 / batch_size  # (1/mb) * (mb/B), ppo_learner.py:175-177
+    z, pacts = mlp_forward(pol, obs, quant)
+    s = torch.softmax(z, -1)  # discrete_policy.py:30
+    p = torch.clamp(s, 1e-11, 1.0)  # :74
+    logp_all = torch.log(p)  # :76
+    a = acts.view(-1, 1).long()  # :71
+    logp = logp_all.gather(-1, a).flatten()  # :77
+    ent_b = -(logp_all * p).sum(-1)  # :78
+    entropy = ent_b.mean()  # :80
+    log_ratio = logp - old_logp
+    ratio = torch.exp(log_ratio)  # ppo_learner.py:153
+    clipped = torch.clamp(ratio, 1.0 - clip, 1.0 + clip)  # :154-156
+    kl = ((ratio - 1) - log_ratio).mean()  # :160-162
+    clip_frac = ((ratio - 1).abs() > clip).float().mean()  # :165-169
+    s1 = ratio * adv
+    s2 = clipped * adv
+    policy_loss = -torch.min(s1, s2).mean()  # :172-174
+    v, vacts = mlp_forward(val, obs, quant)
+    v = v.flatten()
+    value_loss = ((v - targets) ** 2).mean()  # :176 (MSELoss), before the minibatch_ratio factor
+
+    # ---- backward (A.3) ----
+    # torch.min(a,b) backward: gradient to `a` where a < b, split 0.5/0.5 where a == b (ATen
+    # min.other derivative: grad.masked_fill(self > other, 0) / (1 + (self == other))) -- the tie is the
+    # common case here: whenever the ratio is inside the clip range, s1 == s2 exactly.
+    in_range = (ratio >= 1.0 - clip) & (ratio <= 1.0 + clip)  # clamp passes gradient inside (inclusive)
+    lt = (s1 < s2).to(z.dtype)
+    eq = (s1 == s2).to(z.dtype)
+    gt = (s1 > s2).to(z.dtype)
+    d_s1 = lt + 0.5 * eq  # dmin/ds1
+    d_s2 = gt + 0.5 * eq  # dmin/ds2
+    d_ratio = -w * adv * (d_s1 + d_s2 * in_range.to(z.dtype))
+    d_logp = d_ratio * ratio
+    g = ent_coef * w * (logp_all + 1.0)  # d/dp of -ent_coef*w*sum(-p log p)  (both factors are the clamped p)
+    g = g.scatter_add(-1, a, (d_logp / p.gather(-1, a).flatten()).unsqueeze(-1))
+    g = g * ((s >= 1e-11) & (s <= 1.0)).to(z.dtype)  # clamp mask on the unclamped softmax
+    dz = s * (g - (g * s).sum(-1, keepdim=True))  # softmax Jacobian
+    pg = mlp_backward(pol, pacts, dz, quant)
+    dv = (2.0 * w * (v - targets)).unsqueeze(-1)
+    vg = mlp_backward(val, vacts, dv, quant)
+    metrics = dict(entropy=float(entropy), kl=float(kl), clip_fraction=float(clip_frac),
+                   value_loss=float(value_loss), policy_loss=float(policy_loss))
+    return pg, vg, metrics
+
+
+def clip_grad_norm(grads, max_norm=0.5):
+    """torch.nn.utils.clip_grad_norm_ (called at ppo_learner.py:187-190): norm of per-tensor norms,
+    coef = max_norm / (total + 1e-6) clamped to 1."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in grads]))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return [g * coef for g in grads], float(total)
+
+
+class AdamOracle:
+    """torch.optim.Adam as configured at ppo_learner.py:56-59 (betas (0.9,0.999), eps 1e-8, wd 0)."""
+
+    def __init__(self, params, lr, b1=0.9, b2=0.999, eps=1e-8):
+        self.lr, self.b1, self.b2, self.eps = lr, b1, b2, eps
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.step_count = 0
+
+    def step(self, params, grads):
+        self.step_count += 1
+        t = self.step_count
+        bc1 = 1.0 - self.b1 ** t
+        bc2 = 1.0 - self.b2 ** t
+        step_size = self.lr / bc1
+        bc2s = math.sqrt(bc2)
+        for i, (p, g) in enumerate(zip(params, grads)):
+            self.m[i] = self.m[i] + (g - self.m[i]) * (1.0 - self.b1)  # lerp_
+            self.v[i] = self.v[i] * self.b2 + (1.0 - self.b2) * g * g
+            denom = self.v[i].sqrt() / bc2s + self.eps
+            params[i] = p - step_size * (self.m[i] / denom)
+        return params
+
+
+class PPOLearnerOracle:
+    """ppo_learner.py:92-238 `learn`, restated around ppo_minibatch/clip_grad_norm/AdamOracle."""
+
+    def __init__(self, pol, val, batch_size, n_epochs, policy_lr, critic_lr, clip_range, ent_coef,
+                 mini_batch_size, quant=None):
+        self.pol = [p.clone() for p in pol]
+        self.val = [p.clone() for p in val]
+        self.batch_size, self.n_epochs = batch_size, n_epochs
+        self.mini_batch_size = mini_batch_size
+        self.clip_range, self.ent_coef = clip_range, ent_coef
+        self.popt = AdamOracle(self.pol, policy_lr)
+        self.vopt = AdamOracle(self.val, critic_lr)
+        self.cumulative_model_updates = 0
+        self.quant = quant
+        self.last_grads = None
+
+    def learn(self, buf: BufferOracle):
+        n_it = n_mb = 0
+        m_ent = m_kl = m_vl = 0.0
+        clips = []
+        pb = torch.cat([p.flatten() for p in self.pol])
+        vb = torch.cat([p.flatten() for p in self.val])
+        for _ in range(self.n_epochs):  # :119
+            for _, (acts, oldp, obs, tgt, adv) in buf.batches(self.batch_size):  # :121-129
+                pg = [torch.zeros_like(p) for p in self.pol]
+                vg = [torch.zeros_like(p) for p in self.val]
+                for s in range(0, self.batch_size, self.mini_batch_size):  # :134
+                    e = s + self.mini_batch_size
+                    g1, g2, mt = ppo_minibatch(self.pol, self.val, torch.from_numpy(obs[s:e]),
+                                               torch.from_numpy(acts[s:e]), torch.from_numpy(oldp[s:e]),
+                                               torch.from_numpy(tgt[s:e]), torch.from_numpy(adv[s:e]),
+                                               self.clip_range, self.ent_coef, self.batch_size, self.quant)
+                    pg = [a + b for a, b in zip(pg, g1)]
+                    vg = [a + b for a, b in zip(vg, g2)]
+                    m_vl += mt["value_loss"]
+                    m_kl += mt["kl"]
+                    m_ent += mt["entropy"]
+                    clips.append(mt["clip_fraction"])
+                    n_mb += 1
+                vg, _ = clip_grad_norm(vg, 0.5)  # :187-189
+                pg, _ = clip_grad_norm(pg, 0.5)  # :190
+                self.last_grads = (pg, vg)
+                self.pol = self.popt.step(self.pol, pg)  # :192
+                self.val = self.vopt.step(self.val, vg)  # :193
+                n_it += 1
+        n_it = max(n_it, 1)
+        n_mb = max(n_mb, 1)
+        pa = torch.cat([p.flatten() for p in self.pol])
+        va = torch.cat([p.flatten() for p in self.val])
+        self.cumulative_model_updates += n_it
+        return {
+            "Cumulative Model Updates": self.cumulative_model_updates,
+            "Policy Entropy": m_ent / n_mb,
+            "Mean KL Divergence": m_kl / n_mb,
+            "Value Function Loss": m_vl / n_mb,
+            "SB3 Clip Fraction": float(np.mean(clips)) if clips else 0,
+            "Policy Update Magnitude": float((pb - pa).norm()),
+            "Value Function Update Magnitude": float((vb - va).norm()),
+        }
+
+
+def add_new_experience(val_params, buf: BufferOracle, stats: WelfordOracle, experience, gamma, lmbda,
+                       standardize_returns=True, max_returns_per_stats_increment=150, quant=None):
+    """learner.py:330-385."""
+    states, actions, log_probs, rewards, next_states, dones, truncated = experience
+    val_inp = np.zeros((states.shape[0] + 1, states.shape[1]))  # :347 (float64 staging)
+    val_inp[:-1] = states
+    val_inp[-1] = next_states[-1]
+    v, _ = mlp_forward(val_params, torch.as_tensor(val_inp, dtype=torch.float32), quant)  # :352
+    val_preds = v.flatten().numpy()
+    ret_std = stats.get_std()[0] if standardize_returns else None  # :356
+    vt, adv, rets = gae_nep50(rewards, dones, truncated, val_preds, gamma, lmbda, ret_std)  # :358
+    if standardize_returns:  # :368-372
+        n_inc = min(max_returns_per_stats_increment, len(rets))
+        stats.increment(rets[:n_inc], n_inc)
+    buf.submit(states=states, actions=actions, log_probs=log_probs, rewards=rewards, next_states=next_states,
+               dones=dones, truncated=truncated, values=vt, advantages=adv)  # :375-385
+    return val_preds, vt, adv, rets
+
+
+def quant_bf16(t):
+    return t.to(torch.bfloat16).to(torch.float32)
