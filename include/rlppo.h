@@ -1,0 +1,183 @@
+/*
+ * rlppo.h -- C-ABI of librlppo_b200.so: the B200-native (sm_100a) learner hot path of rlgym-ppo.
+ *
+ * The reference (AechPro/rlgym-ppo v1.3.13) is pure Python and has no FFI; its boundary for this path is
+ * its Python class surface.  The Python classes in rlgym_ppo_b200/ keep that surface and
+ * bind these entry points with ctypes (INTEGRATION.md shows the stub).  Each entry point cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the name starts with `h_` (host).
+ *   - No allocation, no host synchronisation, no stream creation inside; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).  All calls are CUDA-graph capturable.
+ *   - Return 0 on success, <0 on error; rlppo_last_error() gives the message (thread-local).
+ *   - There is no CPU fallback: every compute entry point fails with RLPPO_ERR_DEVICE when the current
+ *     device is not compute capability 10.x.
+ *   - bf16 buffers are passed as uint16_t*.  "ld" = leading dimension (row stride) in elements.
+ */
+#ifndef RLPPO_H_
+#define RLPPO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLPPO_OK 0
+#define RLPPO_ERR_ARG (-1)
+#define RLPPO_ERR_CUDA (-2)
+#define RLPPO_ERR_DEVICE (-3)
+#define RLPPO_ERR_WORKSPACE (-4)
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int rlppo_version(void);
+const char* rlppo_last_error(void);
+/* 0 if the current CUDA device can run the sm_100a kernels; RLPPO_ERR_DEVICE otherwise. */
+int rlppo_device_check(void);
+
+/* ---- (b-2) GAE: rlgym_ppo/util/torch_functions.py:36-78 compute_gae --------------------------------
+ * One-pass segmented reverse scan (decoupled look-back) over the flat rollout.
+ *   delta_t = clip(r_t/std,-10,10) + gamma*V[t+1]*(1-done_t) - V[t]      (std = *ret_std, NULL: raw r)
+ *   A_t = delta_t + gamma*lambda*(1-done_t)*(1-trunc_t)*A_{t+1};  R_t = r_t + gamma*(1-done_t)*(1-trunc_t)*R_{t+1}
+ * Rounding points follow what NumPy>=2 executes in the reference (delta in f32, A and R carried in f64).
+ *   trunc            f32[n] (trunc_is_f64=0) or f64[n] (=1; the dtype collect_timesteps produces,
+ *                    batched_agent_manager.py:159-168)
+ *   values           f32[n+1] (value net on [states ; next_states[-1]], learner.py:347-352)
+ *   adv, vtarget, ret  f32[n] outputs (advantages, V[:-1]+A, returns)
+ *   ret_head64       optional f64[n_head]: the first n_head returns un-rounded (fed to Welford,
+ *                    learner.py:368-372)
+ *   carry_in         optional f64[2] {A_n, R_n}: values just right of this chunk (sharded scan); NULL = 0
+ *   ws               workspace of rlppo_gae_workspace_bytes(n) bytes (contents ignored; cleared inside)
+ * Algorithmic traffic: 28 B/step (16 read + 12 written). */
+size_t rlppo_gae_workspace_bytes(int64_t n);
+int rlppo_gae_f32(const float* rew, const float* done, const void* trunc, int trunc_is_f64,
+                  const float* values, int64_t n, double gamma, double lambda, const float* ret_std,
+                  float* adv, float* vtarget, float* ret, double* ret_head64, int64_t n_head,
+                  const double* carry_in, void* ws, size_t ws_bytes, void* stream);
+/* Affine summary of a chunk for the sharded scan: out f64[4] = {aA, bA, aR, bR} with
+ * A_first = bA + aA*A_right, R_first = bR + aR*R_right. */
+int rlppo_gae_chunk_summary(const float* rew, const float* done, const void* trunc, int trunc_is_f64,
+                            const float* values, int64_t n, double gamma, double lambda,
+                            const float* ret_std, double* out4, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (b-3) WelfordRunningStat: rlgym_ppo/util/running_stats.py:30-69 ------------------------------
+ * Sequential Welford over n samples of width dim, bit-faithful to update() (:37-46): state mean/m2 f32[dim],
+ * count i64[1]; f64 intermediates for f64 samples (NumPy>=2), f32 for f32 samples.  Afterwards writes
+ * std_out[dim] (:60-69: ones if count<2, zero variance -> 1) and mean_out[dim] (:54-58) if non-NULL. */
+int rlppo_welford_update(float* mean, float* m2, int64_t* count, const void* samples, int samples_are_f64,
+                         int64_t n, int dim, float* std_out, float* mean_out, void* stream);
+
+/* ---- (c-1) ExperienceBuffer store: rlgym_ppo/ppo/experience_buffer.py:17-37,54-80 -----------------
+ * The FIFO `_cat` as a ring: logical row i lives at physical row (start+i) % capacity.  The host keeps
+ * (start,size); these kernels move rows.  rlppo_ring_append copies n_rows rows of `src` (row-major,
+ * src_ld elements apart, element type f32, or f64 when src_is_f64 -> cast to f32 like torch.as_tensor)
+ * to physical rows (phys_first + i) % capacity of `ring` (row width `width`, ld `ring_ld`).
+ * If ring_bf16 != NULL the same rows are also written as bf16 (ld bf16_ld, zero padded to bf16_ld). */
+int rlppo_ring_append(float* ring, int64_t ring_ld, uint16_t* ring_bf16, int64_t bf16_ld, int64_t capacity,
+                      int64_t phys_first, const void* src, int src_is_f64, int64_t src_ld, int64_t n_rows,
+                      int width, void* stream);
+
+/* ---- (c-2) minibatch gather: experience_buffer.py:82-102 _get_samples ------------------------------
+ * idx: int64[B] LOGICAL indices (a slice of RandomState.permutation, generated on the host so the
+ * stream is NumPy's own); physical row = (start + idx) % capacity.  Any output may be NULL.
+ *   out_actions/out_logp/out_values/out_adv  f32[B];  out_states f32[B,obs] (exact copy: the public
+ *   get_all_batches_shuffled contract);  out_states_bf16 [B, bf16_ld] from the bf16 ring (GEMM operand). */
+int rlppo_gather_batch(const float* actions, const float* logp, const float* values, const float* adv,
+                       const float* states, int64_t states_ld, const uint16_t* states_bf16, int64_t bf16_ld,
+                       int obs_dim, int64_t capacity, int64_t start, const int64_t* idx, int64_t B,
+                       float* out_actions, float* out_logp, float* out_values, float* out_adv,
+                       float* out_states, uint16_t* out_states_bf16, void* stream);
+/* Host-side NumPy-legacy permutation (experience_buffer.py:98 `self.rng.permutation(total)`):
+ * MT19937 + masked-rejection Fisher-Yates, bit-exact with np.random.RandomState.  h_key: uint32[624],
+ * h_pos: int32[1] (both updated in place so the caller can set_state() the NumPy object back). */
+int rlppo_host_permutation(uint32_t* h_key, int32_t* h_pos, int64_t n, int64_t* h_out);
+
+/* ---- operand preparation ------------------------------------------------------------------------- */
+/* f32 [n_rows, width] (ld src_ld) -> bf16 [n_rows, dst_ld], zero padded; used for the value-net input
+ * [states ; next_states[-1]] (learner.py:347-349) and policy inference obs. */
+int rlppo_rows_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width, uint16_t* dst,
+                       int64_t dst_ld, void* stream);
+/* Same with obs standardisation fused: clip((x-mean)/std, -5, 5) (batched_agent_manager.py:303-315). */
+int rlppo_rows_standardize_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width,
+                                   const float* mean, const float* std, float clip, uint16_t* dst,
+                                   int64_t dst_ld, void* stream);
+/* fp32 master weight W [out,in] (torch nn.Linear layout) -> bf16 W [out_pad, in_pad] (K-major operand of
+ * the forward GEMM) and, if wt != NULL, bf16 W^T [in_pad, out_pad] (operand of the dgrad GEMM). */
+int rlppo_weight_to_bf16(const float* w, int out_f, int in_f, uint16_t* wq, int64_t wq_ld, int out_pad,
+                         uint16_t* wt, int64_t wt_ld, int in_pad, void* stream);
+
+/* ---- (a-3, d-2) MLP on tcgen05 tensor cores: discrete_policy.py:22-42, value_estimator.py:19-36 ----
+ * All GEMMs: bf16 operands staged by TMA (128B swizzle), fp32 accumulation in TMEM, one elected thread
+ * issuing tcgen05.mma, epilogue warps reading TMEM with tcgen05.ld.  M = rows (timesteps).
+ *
+ * rlppo_linear_fwd:  Y[M,N] = act(X[M,K] * W[N,K]^T + bias)   (nn.Linear + ReLU), Y bf16.
+ *   x ld = ldx (>= K, multiple of 8), w bf16 [>=N rows, ldw], bias f32[N] or NULL, relu 0/1. */
+int rlppo_linear_fwd(const uint16_t* x, int64_t ldx, const uint16_t* w, int64_t ldw, const float* bias,
+                     uint16_t* y, int64_t ldy, int64_t M, int N, int K, int relu, void* stream);
+/* rlppo_linear_dgrad: dX[M,K] = (dY[M,N] * W[N,K]) (.) (Hprev > 0); wt = bf16 W^T [K, ldwt>=N].
+ *   hprev = the ReLU output that was this layer's input (bf16 [M,ldh]) or NULL (no mask). */
+int rlppo_linear_dgrad(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt,
+                       const uint16_t* hprev, int64_t ldh, uint16_t* dx, int64_t lddx, int64_t M, int N,
+                       int K, void* stream);
+/* rlppo_linear_wgrad: dW[N,K] += dY[M,N]^T * X[M,K]  (fp32, torch [out,in] layout with ld = lddw) and
+ *   db[N] += column sums of dY (if db != NULL).  Split over M across the SMs; fp32 atomics. */
+int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int64_t ldx, float* dw,
+                       int64_t lddw, float* db, int64_t M, int N, int K, void* stream);
+
+/* Policy head, sampling (DiscreteFF.get_action, discrete_policy.py:44-62): logits = H*W^T + b over
+ * n_actions <= 256, softmax, clamp(1e-11,1), categorical sample by inverse CDF, log-prob of the sample.
+ *   u_inject   optional f32[M] uniforms in [0,1) (tests); NULL -> Philox4x32-10(seed, offset + row)
+ *   actions_out f32[M] (the manager casts actions to f32, batched_agent_manager.py:204) and/or
+ *   actions_i64_out int64[M]; logp_out f32[M]; probs_out optional f32[M, n_actions] (get_output).
+ *   deterministic != 0: per-row argmax, logp of it (the reference's deterministic branch returns one
+ *   global argmax, discrete_policy.py:56-57; the per-row form is what its batch-of-1 use means). */
+int rlppo_policy_head_sample(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw,
+                             const float* bias, int64_t M, int n_actions, int K, const float* u_inject,
+                             uint64_t seed, uint64_t offset, int deterministic, float* actions_out,
+                             int64_t* actions_i64_out, float* logp_out, float* probs_out, void* stream);
+
+/* Policy head, training (DiscreteFF.get_backprop_data discrete_policy.py:64-80 + ppo_learner.py:153-177
+ * + the analytic backward of SURVEY.md A.3), fused into the head GEMM's epilogue:
+ *   p = clamp(softmax(z),1e-11,1); logp = log p[a]; H = -sum p log p; ratio = exp(logp - old_logp);
+ *   loss terms; dz[M, lddz] (bf16) = d(ppo_loss)/dz with weight inv_batch = 1/batch_size;
+ *   metrics f32[8] accumulated with atomics: [0] sum entropy, [1] sum kl, [2] sum clipped-count,
+ *   [3] sum min(ratio*A, clip(ratio)*A), [4] rows processed; [5..7] reserved.
+ *   logp_out optional f32[M]. */
+int rlppo_policy_head_train(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw,
+                            const float* bias, int64_t M, int n_actions, int K, const float* actions,
+                            const float* old_logp, const float* adv, float inv_batch, float clip,
+                            float ent_coef, uint16_t* dz, int64_t lddz, float* logp_out, float* metrics,
+                            void* stream);
+
+/* Value head (ValueEstimator last Linear(.,1), value_estimator.py:27; MSELoss ppo_learner.py:176),
+ * fused SIMT pass over the last hidden activation H[M,K] (bf16):
+ *   v = H*w + b  -> values_out f32[M] (if non-NULL).
+ *   if targets != NULL: dv = 2*inv_batch*(v - target); dH[M,lddh] (bf16) = dv * w (.) (H > 0);
+ *   dw[K] += sum_m dv*H;  db[1] += sum dv;  metrics[5] += sum (v-target)^2, metrics[6] += rows. */
+int rlppo_value_head(const uint16_t* h, int64_t ldh, const float* w, const float* bias, int64_t M, int K,
+                     float* values_out, const float* targets, float inv_batch, uint16_t* dh, int64_t lddh,
+                     float* dw, float* db, float* metrics, void* stream);
+
+/* ---- (d-6) clip_grad_norm_ + Adam: ppo_learner.py:187-193, torch.optim.Adam ------------------------
+ * Flat fp32 arenas; `seg` describes n_seg contiguous segments (policy params, value params): seg_off
+ * int64[n_seg+1].  rlppo_grad_sqnorm writes per-segment sum of squares to sqnorm f32[n_seg] (zeroed
+ * inside).  rlppo_clip_adam then applies, per segment s: c = min(1, max_norm/(sqrt(sqnorm[s])+1e-6));
+ * g = c*grad; m = lerp(m,g,1-b1); v = b2*v+(1-b2)g*g; step = ++step_count[s] (device i64);
+ * p -= lr[s]/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps).  lr f32[n_seg] on device
+ * (update_learning_rate, learner.py:205-216, rewrites it).  delta_sq (optional f32[n_seg]) accumulates
+ * nothing here; see rlppo_sqdiff. */
+int rlppo_grad_sqnorm(const float* grads, const int64_t* h_seg_off, int n_seg, float* sqnorm, void* stream);
+int rlppo_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off,
+                    int n_seg, const float* sqnorm, const float* lr, int64_t* step_count, double max_norm,
+                    double beta1, double beta2, double eps, void* stream);
+/* out f32[n_seg] = per-segment sum (a-b)^2 (update magnitudes, ppo_learner.py:212-220). */
+int rlppo_sqdiff(const float* a, const float* b, const int64_t* h_seg_off, int n_seg, float* out,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLPPO_H_ */

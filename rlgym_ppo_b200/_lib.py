@@ -1,0 +1,119 @@
+"""ctypes binding of librlppo_b200.so (include/rlppo.h).
+
+There is no CPU fallback: importing this module without the built library raises, and every compute entry
+point returns RLPPO_ERR_DEVICE (raised here as RuntimeError) when no sm_100 device is current.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librlppo_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m rlgym_ppo_b200.build` (nvcc, sm_100a). "
+        "rlgym_ppo_b200 has no CPU or PyTorch fallback for its kernels."
+    )
+
+_lib = ctypes.CDLL(LIB_PATH)
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+_D = ctypes.c_double
+_F = ctypes.c_float
+_U64 = ctypes.c_uint64
+_SZ = ctypes.c_size_t
+
+_SIGS = {
+    "rlppo_version": ([], _I),
+    "rlppo_last_error": ([], ctypes.c_char_p),
+    "rlppo_device_check": ([], _I),
+    "rlppo_gae_workspace_bytes": ([_L], _SZ),
+    "rlppo_gae_f32": ([_P, _P, _P, _I, _P, _L, _D, _D, _P, _P, _P, _P, _P, _L, _P, _P, _SZ, _P], _I),
+    "rlppo_gae_chunk_summary": ([_P, _P, _P, _I, _P, _L, _D, _D, _P, _P, _P, _SZ, _P], _I),
+    "rlppo_welford_update": ([_P, _P, _P, _P, _I, _L, _I, _P, _P, _P], _I),
+    "rlppo_ring_append": ([_P, _L, _P, _L, _L, _L, _P, _I, _L, _L, _I, _P], _I),
+    "rlppo_gather_batch": ([_P, _P, _P, _P, _P, _L, _P, _L, _I, _L, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P], _I),
+    "rlppo_host_permutation": ([_P, _P, _L, _P], _I),
+    "rlppo_rows_to_bf16": ([_P, _L, _L, _I, _P, _L, _P], _I),
+    "rlppo_rows_standardize_to_bf16": ([_P, _L, _L, _I, _P, _P, _F, _P, _L, _P], _I),
+    "rlppo_weight_to_bf16": ([_P, _I, _I, _P, _L, _I, _P, _L, _I, _P], _I),
+    "rlppo_linear_fwd": ([_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _P], _I),
+    "rlppo_linear_dgrad": ([_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P], _I),
+    "rlppo_linear_wgrad": ([_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P], _I),
+    "rlppo_policy_head_sample": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _U64, _U64, _I, _P, _P, _P, _P, _P], _I),
+    "rlppo_policy_head_train": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _P, _P, _F, _F, _F, _P, _L, _P, _P, _P], _I),
+    "rlppo_value_head": ([_P, _L, _P, _P, _L, _I, _P, _P, _F, _P, _L, _P, _P, _P, _P], _I),
+    "rlppo_grad_sqnorm": ([_P, _P, _I, _P, _P], _I),
+    "rlppo_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P], _I),
+    "rlppo_sqdiff": ([_P, _P, _P, _I, _P, _P], _I),
+}
+
+EXPORTED = tuple(_SIGS)
+
+for _name, (_args, _res) in _SIGS.items():
+    _fn = getattr(_lib, _name)  # AttributeError here = header and library disagree
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+
+class RlppoError(RuntimeError):
+    pass
+
+
+def last_error():
+    return _lib.rlppo_last_error().decode("utf-8", "replace")
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise RlppoError(f"{name} failed ({rc}): {last_error()}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a tensor, None -> NULL."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    """The torch current stream as a cudaStream_t (so kernels order with torch ops and graph capture)."""
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    rc = getattr(_lib, name)(*args)
+    _check(rc, name)
+
+
+def require_device():
+    """Raise unless the current CUDA device can run the sm_100a kernels."""
+    if not torch.cuda.is_available():
+        raise RlppoError("rlgym_ppo_b200 needs a CUDA device (B200, sm_100); there is no CPU fallback")
+    _check(_lib.rlppo_device_check(), "rlppo_device_check")
+
+
+def version():
+    return _lib.rlppo_version()
+
+
+def gae_workspace_bytes(n):
+    return int(_lib.rlppo_gae_workspace_bytes(int(n)))
+
+
+def host_permutation(rng, n):
+    """np.random.RandomState.permutation(n), bit-exact, through the C implementation; advances `rng`."""
+    import numpy as np
+
+    st = rng.get_state()
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = np.asarray([st[2]], dtype=np.int32)
+    out = np.empty(int(n), dtype=np.int64)
+    rc = _lib.rlppo_host_permutation(key.ctypes.data_as(_P), pos.ctypes.data_as(_P), int(n), out.ctypes.data_as(_P))
+    _check(rc, "rlppo_host_permutation")
+    rng.set_state((st[0], key, int(pos[0]), st[3], st[4]))
+    return out

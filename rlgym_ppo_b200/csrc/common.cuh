@@ -1,0 +1,71 @@
+// Shared helpers for librlppo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/rlppo.h"
+
+namespace rlppo {
+
+void set_error(const char* fmt, ...);
+int check_device();   // RLPPO_OK or RLPPO_ERR_DEVICE (cached per device)
+int num_sms();
+
+#define RLPPO_CHECK_ARG(cond, ...)                 \
+    do {                                           \
+        if (!(cond)) {                             \
+            rlppo::set_error(__VA_ARGS__);         \
+            return RLPPO_ERR_ARG;                  \
+        }                                          \
+    } while (0)
+
+#define RLPPO_CUDA(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            rlppo::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                       \
+            return RLPPO_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define RLPPO_REQUIRE_DEVICE()                    \
+    do {                                          \
+        int _d = rlppo::check_device();           \
+        if (_d != RLPPO_OK) return _d;            \
+    } while (0)
+
+#define RLPPO_LAUNCH_CHECK() RLPPO_CUDA(cudaGetLastError())
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
+    return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ float bf16_bits_to_f32(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    return (uint32_t)f32_to_bf16_bits(lo) | ((uint32_t)f32_to_bf16_bits(hi) << 16);
+}
+
+}  // namespace rlppo

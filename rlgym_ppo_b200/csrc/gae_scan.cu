@@ -1,0 +1,325 @@
+// GAE + returns as a one-pass segmented reverse scan (replaces the Python loop of
+// rlgym_ppo/util/torch_functions.py:58-73).
+//
+// Each timestep t is a pair of affine maps  A_t = bA + aA * A_{t+1},  R_t = bR + aR * R_{t+1}  with
+//   aA = f32(gamma*lambda)*(1-done)*(1-trunc),  bA = delta_t (f32),  aR = gamma*(1-done)*(1-trunc),  bR = r_t.
+// A done/truncated step has a = 0, which is the segment reset.  Composition (a,b)o(c,d) = (a*c, b + a*d)
+// is associative, so the recurrence is a suffix scan: thread-serial over 4 steps, warp shuffle scan over
+// lanes, one warp over the 16 warp aggregates, and decoupled look-back across tiles (tile 0 is the END of
+// the rollout; tile ids are handed out by an atomic ticket so a tile only ever waits on tiles that are
+// already running).  Carries are f64 (HBM-bound kernel; the fp64 work is free) which also reproduces the
+// reference's f64 accumulation; delta is formed with the reference's f32 rounding points.
+//
+// HBM traffic: reads r, done, trunc, V (16 B/step with f32 flags), writes adv, vtarget, ret (12 B/step).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kItems = 4;
+constexpr int kTile = kThreads * kItems;  // 2048 steps per CTA
+constexpr int kWarps = kThreads / 32;
+
+struct Aff {
+    double aA, bA, aR, bR;
+};
+
+__device__ __forceinline__ Aff aff_identity() { return Aff{1.0, 0.0, 1.0, 0.0}; }
+// l = earlier timesteps, r = later timesteps: (l o r)(x) = l(r(x))
+__device__ __forceinline__ Aff compose(const Aff& l, const Aff& r) {
+    return Aff{l.aA * r.aA, fma(l.aA, r.bA, l.bA), l.aR * r.aR, fma(l.aR, r.bR, l.bR)};
+}
+__device__ __forceinline__ Aff shfl_down(const Aff& x, int off) {
+    return Aff{__shfl_down_sync(0xffffffffu, x.aA, off), __shfl_down_sync(0xffffffffu, x.bA, off),
+               __shfl_down_sync(0xffffffffu, x.aR, off), __shfl_down_sync(0xffffffffu, x.bR, off)};
+}
+__device__ __forceinline__ Aff shfl_idx(const Aff& x, int src) {
+    return Aff{__shfl_sync(0xffffffffu, x.aA, src), __shfl_sync(0xffffffffu, x.bA, src),
+               __shfl_sync(0xffffffffu, x.aR, src), __shfl_sync(0xffffffffu, x.bR, src)};
+}
+// inclusive suffix scan over the lanes of a warp (lane l gets l o l+1 o ... o 31)
+__device__ __forceinline__ Aff warp_suffix_scan(Aff x, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Aff y = shfl_down(x, off);
+        if (lane + off < 32) x = compose(x, y);
+    }
+    return x;
+}
+
+struct Workspace {
+    int* counter;   // ticket
+    int* status;    // per tile: 0 = nothing, 1 = aggregate published, 2 = inclusive published
+    double* agg;    // per tile 4 doubles: map of this tile alone
+    double* incl;   // per tile 4 doubles: map of this tile and every tile to its right
+};
+
+template <bool TRUNC64, bool VEC, bool STORE>
+__global__ void __launch_bounds__(kThreads)
+gae_scan_kernel(const float* __restrict__ rew, const float* __restrict__ done, const void* __restrict__ trunc,
+                const float* __restrict__ val, int64_t n, double gamma, float gl32,
+                const float* __restrict__ ret_std, float* __restrict__ adv, float* __restrict__ vt,
+                float* __restrict__ ret, double* __restrict__ ret_head, int64_t n_head,
+                const double* __restrict__ carry_in, double* __restrict__ summary_out, Workspace ws,
+                int n_tiles) {
+    __shared__ int s_tile;
+    __shared__ double s_warp[kWarps][4];
+    __shared__ double s_carry[2];
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(ws.counter, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const int chunk = n_tiles - 1 - tile;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)chunk * kTile + (int64_t)threadIdx.x * kItems;
+
+    float r[kItems], d[kItems], v[kItems + 1];
+    double tr[kItems];
+    const bool full = base + kItems <= n;
+    if (VEC && full) {
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rew + base));
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(done + base));
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(val + base));
+        r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
+        d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+        v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+        v[4] = __ldg(val + base + 4);
+        if (TRUNC64) {
+            const double2 t0 = __ldg(reinterpret_cast<const double2*>(static_cast<const double*>(trunc) + base));
+            const double2 t1 = __ldg(reinterpret_cast<const double2*>(static_cast<const double*>(trunc) + base + 2));
+            tr[0] = t0.x; tr[1] = t0.y; tr[2] = t1.x; tr[3] = t1.y;
+        } else {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(trunc) + base));
+            tr[0] = t4.x; tr[1] = t4.y; tr[2] = t4.z; tr[3] = t4.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+            const int64_t t = base + i;
+            const bool ok = t < n;
+            r[i] = ok ? __ldg(rew + t) : 0.f;
+            d[i] = ok ? __ldg(done + t) : 0.f;
+            v[i] = ok ? __ldg(val + t) : 0.f;
+            tr[i] = !ok ? 0.0
+                        : (TRUNC64 ? __ldg(static_cast<const double*>(trunc) + t)
+                                   : (double)__ldg(static_cast<const float*>(trunc) + t));
+        }
+        v[kItems] = (base + kItems <= n) ? __ldg(val + base + kItems) : 0.f;
+    }
+    const bool has_std = ret_std != nullptr;
+    const float stdv = has_std ? __ldg(ret_std) : 1.f;
+
+    // per-step maps; steps past the end are identities so the carry passes through them
+    Aff f[kItems];
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        if (base + i < n) {
+            const float nd = __fsub_rn(1.0f, d[i]);                              // torch_functions.py:59
+            const double nt = 1.0 - tr[i];                                       // :60
+            float nr = r[i];
+            if (has_std) {                                                        // :62-65
+                nr = __fdiv_rn(r[i], stdv);
+                nr = fminf(fmaxf(nr, -10.f), 10.f);
+            }
+            const float gv = (float)(gamma * (double)v[i + 1]);
+            const float pred = __fadd_rn(nr, __fmul_rn(gv, nd));                 // :67
+            const float delta = __fsub_rn(pred, v[i]);                           // :68
+            f[i].aA = (double)__fmul_rn(gl32, nd) * nt;                          // :72
+            f[i].bA = (double)delta;
+            f[i].aR = gamma * (double)nd * nt;                                   // :69
+            f[i].bR = (double)r[i];
+        } else {
+            f[i] = aff_identity();
+        }
+    }
+    Aff agg = f[kItems - 1];
+#pragma unroll
+    for (int i = kItems - 2; i >= 0; --i) agg = compose(f[i], agg);
+
+    // warp-level suffix scan of the thread aggregates
+    const Aff incl_w = warp_suffix_scan(agg, lane);
+    Aff excl = shfl_down(incl_w, 1);
+    if (lane == 31) excl = aff_identity();
+    if (lane == 0) {
+        s_warp[warp][0] = incl_w.aA; s_warp[warp][1] = incl_w.bA;
+        s_warp[warp][2] = incl_w.aR; s_warp[warp][3] = incl_w.bR;
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        Aff w = aff_identity();
+        if (lane < kWarps) w = Aff{s_warp[lane][0], s_warp[lane][1], s_warp[lane][2], s_warp[lane][3]};
+        const Aff wi = warp_suffix_scan(w, lane);       // lanes >= kWarps hold identities
+        Aff we = shfl_down(wi, 1);                      // exclusive: warps to the right of `lane`
+        if (lane == 31) we = aff_identity();
+        if (lane < kWarps) {
+            s_warp[lane][0] = we.aA; s_warp[lane][1] = we.bA; s_warp[lane][2] = we.aR; s_warp[lane][3] = we.bR;
+        }
+        const Aff tile_agg = shfl_idx(wi, 0);
+
+        // ---- decoupled look-back: map of everything to the right of this tile ----
+        Aff right = aff_identity();
+        if (tile > 0) {
+            if (lane == 0) {
+                double* a = ws.agg + (size_t)tile * 4;
+                a[0] = tile_agg.aA; a[1] = tile_agg.bA; a[2] = tile_agg.aR; a[3] = tile_agg.bR;
+                __threadfence();
+                rlppo::st_release_s32(ws.status + tile, 1);
+            }
+            int look = tile - 1;
+            bool finished = false;
+            while (!finished) {
+                const int j = look - lane;
+                int st = 2;
+                Aff m = aff_identity();   // j < 0: nothing to the right of tile 0
+                if (j >= 0) {
+                    const long long t0 = clock64();
+                    do {
+                        st = rlppo::ld_acquire_s32(ws.status + j);
+                        if (st == 0 && clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
+                    } while (st == 0);
+                    const double* src = (st == 2 ? ws.incl : ws.agg) + (size_t)j * 4;
+                    m = Aff{__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3)};
+                }
+                const unsigned done_mask = __ballot_sync(0xffffffffu, st == 2);
+                const int upto = done_mask ? (__ffs(done_mask) - 1) : 31;
+                for (int l = 0; l <= upto; ++l) right = compose(right, shfl_idx(m, l));
+                finished = done_mask != 0;
+                look -= 32;
+            }
+        }
+        const Aff incl = compose(tile_agg, right);
+        if (lane == 0) {
+            double* o = ws.incl + (size_t)tile * 4;
+            o[0] = incl.aA; o[1] = incl.bA; o[2] = incl.aR; o[3] = incl.bR;
+            __threadfence();
+            rlppo::st_release_s32(ws.status + tile, 2);
+            const double cA = carry_in ? carry_in[0] : 0.0;
+            const double cR = carry_in ? carry_in[1] : 0.0;
+            s_carry[0] = fma(right.aA, cA, right.bA);
+            s_carry[1] = fma(right.aR, cR, right.bR);
+            if (summary_out != nullptr && tile == n_tiles - 1) {
+                summary_out[0] = incl.aA; summary_out[1] = incl.bA;
+                summary_out[2] = incl.aR; summary_out[3] = incl.bR;
+            }
+        }
+    }
+    if (!STORE) return;
+    __syncthreads();
+
+    // value just right of this thread's 4 steps
+    const Aff wr = Aff{s_warp[warp][0], s_warp[warp][1], s_warp[warp][2], s_warp[warp][3]};
+    const Aff e = compose(excl, wr);
+    double xA = fma(e.aA, s_carry[0], e.bA);
+    double xR = fma(e.aR, s_carry[1], e.bR);
+    float oa[kItems], ov[kItems], orr[kItems];
+    double r64[kItems];
+#pragma unroll
+    for (int i = kItems - 1; i >= 0; --i) {
+        xA = fma(f[i].aA, xA, f[i].bA);
+        xR = fma(f[i].aR, xR, f[i].bR);
+        oa[i] = (float)xA;                       // :76
+        ov[i] = (float)((double)v[i] + xA);      // :77
+        orr[i] = (float)xR;
+        r64[i] = xR;
+    }
+    if (VEC && full) {
+        *reinterpret_cast<float4*>(adv + base) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+        *reinterpret_cast<float4*>(vt + base) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+        *reinterpret_cast<float4*>(ret + base) = make_float4(orr[0], orr[1], orr[2], orr[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kItems; ++i)
+            if (base + i < n) {
+                adv[base + i] = oa[i];
+                vt[base + i] = ov[i];
+                ret[base + i] = orr[i];
+            }
+    }
+    if (ret_head != nullptr && base < n_head) {
+#pragma unroll
+        for (int i = 0; i < kItems; ++i)
+            if (base + i < n_head && base + i < n) ret_head[base + i] = r64[i];
+    }
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+    size_t status_off, agg_off, incl_off, total, clear_bytes;
+};
+WsLayout ws_layout(int64_t n) {
+    const size_t n_tiles = (size_t)((n + kTile - 1) / kTile);
+    WsLayout L;
+    L.status_off = 16;
+    L.clear_bytes = align_up(16 + n_tiles * sizeof(int), 16);
+    L.agg_off = align_up(L.clear_bytes, 256);
+    L.incl_off = L.agg_off + n_tiles * 4 * sizeof(double);
+    L.total = L.incl_off + n_tiles * 4 * sizeof(double);
+    return L;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <bool STORE>
+int launch_gae(const float* rew, const float* done, const void* trunc, int trunc_is_f64, const float* values,
+               int64_t n, double gamma, double lambda, const float* ret_std, float* adv, float* vtarget,
+               float* ret, double* ret_head64, int64_t n_head, const double* carry_in, double* summary_out,
+               void* wsp, size_t ws_bytes, cudaStream_t s) {
+    const WsLayout L = ws_layout(n);
+    if (ws_bytes < L.total || wsp == nullptr) {
+        rlppo::set_error("gae workspace too small: %zu < %zu", ws_bytes, L.total);
+        return RLPPO_ERR_WORKSPACE;
+    }
+    RLPPO_CHECK_ARG(aligned16(wsp), "gae workspace must be 16-byte aligned");
+    const int n_tiles = (int)((n + kTile - 1) / kTile);
+    char* base = static_cast<char*>(wsp);
+    Workspace ws{reinterpret_cast<int*>(base), reinterpret_cast<int*>(base + L.status_off),
+                 reinterpret_cast<double*>(base + L.agg_off), reinterpret_cast<double*>(base + L.incl_off)};
+    RLPPO_CUDA(cudaMemsetAsync(base, 0, L.clear_bytes, s));
+    const float gl32 = (float)(gamma * lambda);
+    bool vec = aligned16(rew) && aligned16(done) && aligned16(trunc) && aligned16(values);
+    if (STORE) vec = vec && aligned16(adv) && aligned16(vtarget) && aligned16(ret);
+#define RLPPO_GAE_LAUNCH(T64, V)                                                                         \
+    gae_scan_kernel<T64, V, STORE><<<n_tiles, kThreads, 0, s>>>(rew, done, trunc, values, n, gamma, gl32, \
+                                                                ret_std, adv, vtarget, ret, ret_head64,  \
+                                                                n_head, carry_in, summary_out, ws, n_tiles)
+    if (trunc_is_f64) {
+        if (vec) RLPPO_GAE_LAUNCH(true, true); else RLPPO_GAE_LAUNCH(true, false);
+    } else {
+        if (vec) RLPPO_GAE_LAUNCH(false, true); else RLPPO_GAE_LAUNCH(false, false);
+    }
+#undef RLPPO_GAE_LAUNCH
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t rlppo_gae_workspace_bytes(int64_t n) { return ws_layout(n < 1 ? 1 : n).total; }
+
+int rlppo_gae_f32(const float* rew, const float* done, const void* trunc, int trunc_is_f64, const float* values,
+                  int64_t n, double gamma, double lambda, const float* ret_std, float* adv, float* vtarget,
+                  float* ret, double* ret_head64, int64_t n_head, const double* carry_in, void* ws,
+                  size_t ws_bytes, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(n >= 0, "n must be >= 0");
+    if (n == 0) return RLPPO_OK;
+    RLPPO_CHECK_ARG(n <= (int64_t)kTile * 0x7fffffff, "n too large");
+    RLPPO_CHECK_ARG(rew && done && trunc && values && adv && vtarget && ret, "null pointer");
+    return launch_gae<true>(rew, done, trunc, trunc_is_f64, values, n, gamma, lambda, ret_std, adv, vtarget, ret,
+                            ret_head64, n_head, carry_in, nullptr, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int rlppo_gae_chunk_summary(const float* rew, const float* done, const void* trunc, int trunc_is_f64,
+                            const float* values, int64_t n, double gamma, double lambda, const float* ret_std,
+                            double* out4, void* ws, size_t ws_bytes, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(n >= 1 && rew && done && trunc && values && out4, "bad argument");
+    return launch_gae<false>(rew, done, trunc, trunc_is_f64, values, n, gamma, lambda, ret_std, nullptr, nullptr,
+                             nullptr, nullptr, 0, nullptr, out4, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,155 @@
+// clip_grad_norm_ + Adam over flat fp32 arenas (ppo_learner.py:187-193; torch.optim.Adam defaults at :56-59).
+// Both nets live in one arena [policy params | value params]; "segments" keep their separate norms, clips,
+// learning rates and step counters -- launches are fused, the mathematics is not.
+// HBM-bound: 16 B read + 12 B written per parameter for the Adam pass, 4 B read for the norm pass.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxSeg = 8;
+struct Segs {
+    int64_t off[kMaxSeg + 1];
+    int n;
+};
+
+__device__ __forceinline__ int seg_of(const Segs& s, int64_t i) {
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxSeg; ++j)
+        if (j < s.n && i >= s.off[j]) k = j;
+    return k;
+}
+
+// out[seg] += sum over the segment of f(a[i], b[i]);  DIFF: (a-b)^2, else a^2
+template <bool DIFF>
+__global__ void seg_sumsq_kernel(const float* __restrict__ a, const float* __restrict__ b, Segs segs,
+                                 float* __restrict__ out) {
+    __shared__ float s_part[kMaxSeg];
+    if (threadIdx.x < kMaxSeg) s_part[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int64_t total = segs.off[segs.n];
+    float acc[kMaxSeg];
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k) acc[k] = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float x = __ldg(a + i);
+        if (DIFF) x -= __ldg(b + i);
+        const int k = seg_of(segs, i);
+#pragma unroll
+        for (int j = 0; j < kMaxSeg; ++j)
+            if (j == k) acc[j] = fmaf(x, x, acc[j]);
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k) {
+        if (k < segs.n) {
+            const float w = rlppo::warp_sum(acc[k]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_part[k], w);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < segs.n) atomicAdd(out + threadIdx.x, s_part[threadIdx.x]);
+}
+
+// step counters are bumped by a one-thread prologue kernel so every Adam thread sees the same value
+__global__ void bump_steps_kernel(int64_t* step_count, int n_seg) {
+    if (threadIdx.x < n_seg) step_count[threadIdx.x] += 1;
+}
+
+__global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, Segs segs, const float* __restrict__ sqnorm,
+                                 const float* __restrict__ lr, const int64_t* __restrict__ step_count, float max_norm,
+                                 double beta1d, double beta2d, float eps) {
+    // the weights torch derives in Python doubles and then casts: (float)(1 - beta)
+    const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
+    __shared__ float s_coef[kMaxSeg], s_step_size[kMaxSeg], s_bc2_sqrt[kMaxSeg];
+    if (threadIdx.x < segs.n) {
+        const int k = threadIdx.x;
+        // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+        const float total_norm = sqrtf(sqnorm[k]);
+        s_coef[k] = fminf(max_norm / (total_norm + 1e-6f), 1.0f);
+        const double t = (double)step_count[k];
+        const double bc1 = 1.0 - pow(beta1d, t);
+        const double bc2 = 1.0 - pow(beta2d, t);
+        s_step_size[k] = (float)((double)lr[k] / bc1);
+        s_bc2_sqrt[k] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const int64_t total = segs.off[segs.n];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = seg_of(segs, i);
+        const float gi = g[i] * s_coef[k];
+        float mi = m[i], vi = v[i];
+        mi = mi + (gi - mi) * omb1;                           // exp_avg.lerp_(grad, 1-beta1)
+        vi = vi * beta2 + omb2 * gi * gi;                      // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+        const float denom = sqrtf(vi) / s_bc2_sqrt[k] + eps;   // (sqrt(v)/sqrt(bc2)).add_(eps)
+        p[i] = p[i] - s_step_size[k] * (mi / denom);           // param.addcdiv_(m, denom, -step_size)
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+int make_segs(const int64_t* h_seg_off, int n_seg, Segs* out) {
+    RLPPO_CHECK_ARG(h_seg_off && n_seg >= 1 && n_seg <= kMaxSeg, "n_seg must be in [1,%d]", kMaxSeg);
+    out->n = n_seg;
+    for (int i = 0; i <= n_seg; ++i) {
+        out->off[i] = h_seg_off[i];
+        RLPPO_CHECK_ARG(i == 0 || h_seg_off[i] >= h_seg_off[i - 1], "segment offsets must be non-decreasing");
+    }
+    for (int i = n_seg + 1; i <= kMaxSeg; ++i) out->off[i] = h_seg_off[n_seg];
+    return RLPPO_OK;
+}
+
+unsigned grid_for(int64_t total) {
+    const int64_t want = (total + 1023) / 1024;
+    const int64_t cap = (int64_t)rlppo::num_sms() * 8;
+    return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace
+
+extern "C" {
+
+int rlppo_grad_sqnorm(const float* grads, const int64_t* h_seg_off, int n_seg, float* sqnorm, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(grads && sqnorm, "null pointer");
+    Segs segs;
+    int rc = make_segs(h_seg_off, n_seg, &segs);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    RLPPO_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(float) * n_seg, s));
+    seg_sumsq_kernel<false><<<grid_for(segs.off[n_seg]), 256, 0, s>>>(grads, nullptr, segs, sqnorm);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_sqdiff(const float* a, const float* b, const int64_t* h_seg_off, int n_seg, float* out, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(a && b && out, "null pointer");
+    Segs segs;
+    int rc = make_segs(h_seg_off, n_seg, &segs);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    RLPPO_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_seg, s));
+    seg_sumsq_kernel<true><<<grid_for(segs.off[n_seg]), 256, 0, s>>>(a, b, segs, out);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off, int n_seg,
+                    const float* sqnorm, const float* lr, int64_t* step_count, double max_norm, double beta1,
+                    double beta2, double eps, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(params && grads && m && v && sqnorm && lr && step_count, "null pointer");
+    Segs segs;
+    int rc = make_segs(h_seg_off, n_seg, &segs);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    bump_steps_kernel<<<1, 32, 0, s>>>(step_count, n_seg);
+    clip_adam_kernel<<<grid_for(segs.off[n_seg]), 256, 0, s>>>(params, grads, m, v, segs, sqnorm, lr, step_count,
+                                                              (float)max_norm, beta1, beta2, (float)eps);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+}

@@ -1,0 +1,271 @@
+// Welford running statistics, the experience ring (append / gather) and bf16 operand preparation.
+// All of these are HBM-bound byte movers: coalesced, vectorised where rows are 16-byte aligned, grids sized
+// from the row count.  Reference semantics: running_stats.py:30-69, experience_buffer.py:17-37,82-102.
+#include "common.cuh"
+
+namespace {
+
+// ---- Welford ------------------------------------------------------------------------------------------
+// One thread per statistic dimension, samples applied strictly in order (running_stats.py:37-46).
+template <bool F64>
+__global__ void welford_kernel(float* mean, float* m2, int64_t* count, const void* samples, int64_t n, int dim,
+                               float* std_out, float* mean_out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    const int64_t c0 = *count;
+    float mu = mean[j], s2 = m2[j];
+    int64_t c = c0;
+    if (F64) {
+        const double* x = static_cast<const double*>(samples);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t cc = c;
+            c += 1;
+            const double delta = x[i * dim + j] - (double)mu;
+            const double delta_n = delta / (double)c;
+            mu = (float)((double)mu + delta_n);
+            s2 = (float)((double)s2 + delta * delta_n * (double)cc);
+        }
+    } else {
+        const float* x = static_cast<const float*>(samples);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t cc = c;
+            c += 1;
+            const float delta = __fsub_rn(x[i * dim + j], mu);
+            const float delta_n = __fdiv_rn(delta, (float)c);
+            mu = __fadd_rn(mu, delta_n);
+            s2 = __fadd_rn(s2, __fmul_rn(__fmul_rn(delta, delta_n), (float)cc));
+        }
+    }
+    mean[j] = mu;
+    m2[j] = s2;
+    if (std_out) {  // running_stats.py:60-69
+        float sd = 1.f;
+        if (c >= 2) {
+            float var = __fdiv_rn(s2, (float)(c - 1));
+            if (var == 0.f) var = 1.f;
+            sd = __fsqrt_rn(var);
+        }
+        std_out[j] = sd;
+    }
+    if (mean_out) mean_out[j] = (c >= 2) ? mu : 0.f;  // :54-58
+    __syncthreads();
+    if (j == 0) *count = c;  // single block when dim <= 1024 (checked on the host)
+}
+
+// ---- ring append ----------------------------------------------------------------------------------------
+template <bool F64>
+__global__ void ring_append_kernel(float* ring, int64_t ring_ld, uint16_t* ring_bf16, int64_t bf16_ld,
+                                   int64_t capacity, int64_t phys_first, const void* src, int64_t src_ld,
+                                   int64_t n_rows, int width) {
+    // one warp per row (rows are 1 or obs_dim wide); scalar rows are handled by the flat variant below
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    int64_t phys = phys_first + row;
+    if (phys >= capacity) phys -= capacity;
+    for (int c = lane; c < (ring_bf16 ? (int)bf16_ld : width); c += 32) {
+        float x = 0.f;
+        if (c < width)
+            x = F64 ? (float)static_cast<const double*>(src)[row * src_ld + c]
+                    : static_cast<const float*>(src)[row * src_ld + c];
+        if (c < width) ring[phys * ring_ld + c] = x;
+        if (ring_bf16) ring_bf16[phys * bf16_ld + c] = rlppo::f32_to_bf16_bits(x);
+    }
+}
+
+template <bool F64>
+__global__ void ring_append_flat_kernel(float* ring, int64_t capacity, int64_t phys_first, const void* src,
+                                        int64_t n_rows) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    int64_t phys = phys_first + i;
+    if (phys >= capacity) phys -= capacity;
+    ring[phys] = F64 ? (float)static_cast<const double*>(src)[i] : static_cast<const float*>(src)[i];
+}
+
+// ---- gather ---------------------------------------------------------------------------------------------
+// One warp per sample: lane 0..3 fetch the four scalars, all lanes stream the observation row(s).
+__global__ void gather_kernel(const float* __restrict__ actions, const float* __restrict__ logp,
+                              const float* __restrict__ values, const float* __restrict__ adv,
+                              const float* __restrict__ states, int64_t states_ld,
+                              const uint16_t* __restrict__ states_bf16, int64_t bf16_ld, int obs_dim,
+                              int64_t capacity, int64_t start, const int64_t* __restrict__ idx, int64_t B,
+                              float* __restrict__ out_actions, float* __restrict__ out_logp,
+                              float* __restrict__ out_values, float* __restrict__ out_adv,
+                              float* __restrict__ out_states, uint16_t* __restrict__ out_states_bf16) {
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int lane = threadIdx.x & 31;
+    int64_t phys = start + __ldg(idx + b);
+    if (phys >= capacity) phys -= capacity;
+    if (lane == 0 && out_actions) out_actions[b] = __ldg(actions + phys);
+    if (lane == 1 && out_logp) out_logp[b] = __ldg(logp + phys);
+    if (lane == 2 && out_values) out_values[b] = __ldg(values + phys);
+    if (lane == 3 && out_adv) out_adv[b] = __ldg(adv + phys);
+    if (out_states) {
+        const float* s = states + phys * states_ld;
+        float* o = out_states + b * (int64_t)obs_dim;
+        for (int c = lane; c < obs_dim; c += 32) o[c] = __ldg(s + c);
+    }
+    if (out_states_bf16) {
+        // rows are bf16_ld*2 bytes, bf16_ld % 8 == 0 -> 16-byte vectors
+        const uint4* s = reinterpret_cast<const uint4*>(states_bf16 + phys * bf16_ld);
+        uint4* o = reinterpret_cast<uint4*>(out_states_bf16 + b * bf16_ld);
+        const int nvec = (int)(bf16_ld >> 3);
+        for (int c = lane; c < nvec; c += 32) o[c] = __ldg(s + c);
+    }
+}
+
+// ---- f32 rows -> padded bf16 rows -------------------------------------------------------------------------
+template <bool STANDARDIZE>
+__global__ void rows_to_bf16_kernel(const float* __restrict__ src, int64_t src_ld, int64_t n_rows, int width,
+                                    const float* __restrict__ mean, const float* __restrict__ stdv, float clip,
+                                    uint16_t* __restrict__ dst, int64_t dst_ld) {
+    const int64_t total = n_rows * dst_ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / dst_ld;
+        const int c = (int)(i - row * dst_ld);
+        float x = 0.f;
+        if (c < width) {
+            x = __ldg(src + row * src_ld + c);
+            if (STANDARDIZE) {  // batched_agent_manager.py:303-315
+                x = __fdiv_rn(__fsub_rn(x, __ldg(mean + c)), __ldg(stdv + c));
+                x = fminf(fmaxf(x, -clip), clip);
+            }
+        }
+        dst[i] = rlppo::f32_to_bf16_bits(x);
+    }
+}
+
+__global__ void weight_to_bf16_kernel(const float* __restrict__ w, int out_f, int in_f, uint16_t* __restrict__ wq,
+                                      int64_t wq_ld, int out_pad, uint16_t* __restrict__ wt, int64_t wt_ld,
+                                      int in_pad) {
+    // tile transpose through shared memory so both outputs are written coalesced
+    __shared__ float tile[32][33];
+    const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int o = o0 + r, i = i0 + threadIdx.x;
+        const float x = (o < out_f && i < in_f) ? w[(int64_t)o * in_f + i] : 0.f;
+        tile[r][threadIdx.x] = x;
+        if (o < out_pad && i < wq_ld) wq[(int64_t)o * wq_ld + i] = rlppo::f32_to_bf16_bits(x);
+    }
+    if (wt == nullptr) return;
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, o = o0 + threadIdx.x;
+        if (i < in_pad && o < wt_ld) wt[(int64_t)i * wt_ld + o] = rlppo::f32_to_bf16_bits(tile[threadIdx.x][r]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rlppo_welford_update(float* mean, float* m2, int64_t* count, const void* samples, int samples_are_f64,
+                         int64_t n, int dim, float* std_out, float* mean_out, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(mean && m2 && count && (samples || n == 0), "null pointer");
+    RLPPO_CHECK_ARG(dim >= 1 && dim <= 1024 && n >= 0, "dim must be in [1,1024]");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int threads = ((dim + 31) / 32) * 32;
+    if (samples_are_f64)
+        welford_kernel<true><<<1, threads, 0, s>>>(mean, m2, count, samples, n, dim, std_out, mean_out);
+    else
+        welford_kernel<false><<<1, threads, 0, s>>>(mean, m2, count, samples, n, dim, std_out, mean_out);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_ring_append(float* ring, int64_t ring_ld, uint16_t* ring_bf16, int64_t bf16_ld, int64_t capacity,
+                      int64_t phys_first, const void* src, int src_is_f64, int64_t src_ld, int64_t n_rows, int width,
+                      void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(ring && src && capacity > 0 && n_rows >= 0 && n_rows <= capacity && width >= 1, "bad argument");
+    RLPPO_CHECK_ARG(phys_first >= 0 && phys_first < capacity, "phys_first out of range");
+    RLPPO_CHECK_ARG(!ring_bf16 || (bf16_ld >= width && bf16_ld % 8 == 0), "bf16_ld must be >= width and %% 8 == 0");
+    if (n_rows == 0) return RLPPO_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (width == 1 && ring_ld == 1 && src_ld == 1 && !ring_bf16) {
+        const int threads = 256;
+        const unsigned blocks = (unsigned)((n_rows + threads - 1) / threads);
+        if (src_is_f64) ring_append_flat_kernel<true><<<blocks, threads, 0, s>>>(ring, capacity, phys_first, src, n_rows);
+        else ring_append_flat_kernel<false><<<blocks, threads, 0, s>>>(ring, capacity, phys_first, src, n_rows);
+    } else {
+        const int threads = 256, rows_per_block = threads / 32;
+        const unsigned blocks = (unsigned)((n_rows + rows_per_block - 1) / rows_per_block);
+        if (src_is_f64)
+            ring_append_kernel<true><<<blocks, threads, 0, s>>>(ring, ring_ld, ring_bf16, bf16_ld, capacity, phys_first,
+                                                                src, src_ld, n_rows, width);
+        else
+            ring_append_kernel<false><<<blocks, threads, 0, s>>>(ring, ring_ld, ring_bf16, bf16_ld, capacity, phys_first,
+                                                                 src, src_ld, n_rows, width);
+    }
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_gather_batch(const float* actions, const float* logp, const float* values, const float* adv,
+                       const float* states, int64_t states_ld, const uint16_t* states_bf16, int64_t bf16_ld,
+                       int obs_dim, int64_t capacity, int64_t start, const int64_t* idx, int64_t B, float* out_actions,
+                       float* out_logp, float* out_values, float* out_adv, float* out_states,
+                       uint16_t* out_states_bf16, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(idx && capacity > 0 && start >= 0 && start < capacity && B >= 0, "bad argument");
+    RLPPO_CHECK_ARG(!out_actions || actions, "actions ring missing");
+    RLPPO_CHECK_ARG(!out_logp || logp, "log_probs ring missing");
+    RLPPO_CHECK_ARG(!out_values || values, "values ring missing");
+    RLPPO_CHECK_ARG(!out_adv || adv, "advantages ring missing");
+    RLPPO_CHECK_ARG(!out_states || states, "states ring missing");
+    RLPPO_CHECK_ARG(!out_states_bf16 || (states_bf16 && bf16_ld % 8 == 0), "bf16 states ring missing / ld %% 8");
+    if (B == 0) return RLPPO_OK;
+    const int threads = 256, per_block = threads / 32;
+    const unsigned blocks = (unsigned)((B + per_block - 1) / per_block);
+    gather_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        actions, logp, values, adv, states, states_ld, states_bf16, bf16_ld, obs_dim, capacity, start, idx, B,
+        out_actions, out_logp, out_values, out_adv, out_states, out_states_bf16);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_rows_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width, uint16_t* dst, int64_t dst_ld,
+                       void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(src && dst && dst_ld >= width && n_rows >= 0, "bad argument");
+    if (n_rows == 0) return RLPPO_OK;
+    const int64_t total = n_rows * dst_ld;
+    const unsigned blocks = (unsigned)min((int64_t)rlppo::num_sms() * 16, (total + 255) / 256);
+    rows_to_bf16_kernel<false><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_ld, n_rows, width, nullptr,
+                                                                                       nullptr, 0.f, dst, dst_ld);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_rows_standardize_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width, const float* mean,
+                                   const float* stdv, float clip, uint16_t* dst, int64_t dst_ld, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(src && dst && mean && stdv && dst_ld >= width && n_rows >= 0, "bad argument");
+    if (n_rows == 0) return RLPPO_OK;
+    const int64_t total = n_rows * dst_ld;
+    const unsigned blocks = (unsigned)min((int64_t)rlppo::num_sms() * 16, (total + 255) / 256);
+    rows_to_bf16_kernel<true><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_ld, n_rows, width, mean,
+                                                                                      stdv, clip, dst, dst_ld);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_weight_to_bf16(const float* w, int out_f, int in_f, uint16_t* wq, int64_t wq_ld, int out_pad, uint16_t* wt,
+                         int64_t wt_ld, int in_pad, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(w && wq && out_f >= 1 && in_f >= 1 && wq_ld >= in_f && out_pad >= out_f, "bad argument");
+    RLPPO_CHECK_ARG(!wt || (wt_ld >= out_f && in_pad >= in_f), "bad transposed operand shape");
+    // cover the padded extents of both outputs
+    const int cols = (int)max((int64_t)max(in_pad, in_f), wq_ld);
+    const int rows = (int)max((int64_t)out_pad, wt ? wt_ld : (int64_t)0);
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    weight_to_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(w, out_f, in_f, wq, wq_ld, out_pad, wt,
+                                                                                 wt_ld, in_pad);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+}

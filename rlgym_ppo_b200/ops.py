@@ -1,0 +1,184 @@
+"""Tensor-level wrappers over the C-ABI (one function per entry point of include/rlppo.h).
+
+torch is used for device memory and streams only; every function enqueues hand-written kernels from
+librlppo_b200.so on the current torch CUDA stream and returns without synchronising.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+
+
+def _cuda(t, dtype=None):
+    assert t.is_cuda, "device tensor expected (no CPU fallback)"
+    if dtype is not None:
+        assert t.dtype == dtype, f"expected {dtype}, got {t.dtype}"
+    return t
+
+
+def pad8(n):
+    return (int(n) + 7) // 8 * 8
+
+
+# ---- GAE ------------------------------------------------------------------------------------------------
+_gae_ws = {}
+
+
+def _workspace(n, device):
+    need = _lib.gae_workspace_bytes(n)
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _gae_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _gae_ws[key] = ws
+    return ws
+
+
+def gae(rew, done, trunc, values, gamma, lmbda, ret_std=None, out=None, ret_head64=None, carry_in=None):
+    """compute_gae on device.  rew/done f32[n], trunc f32|f64[n], values f32[n+1], ret_std f32[1] tensor or
+    None.  Returns (value_targets, advantages, returns) f32[n]."""
+    n = rew.numel()
+    _cuda(rew, torch.float32), _cuda(done, torch.float32), _cuda(values, torch.float32)
+    assert values.numel() == n + 1 and done.numel() == n and trunc.numel() == n
+    assert trunc.dtype in (torch.float32, torch.float64)
+    for t in (rew, done, trunc, values):
+        assert t.is_contiguous()
+    if out is None:
+        adv = torch.empty(n, dtype=torch.float32, device=rew.device)
+        vt = torch.empty_like(adv)
+        ret = torch.empty_like(adv)
+    else:
+        vt, adv, ret = out
+    if n == 0:
+        return vt, adv, ret
+    ws = _workspace(n, rew.device)
+    n_head = 0 if ret_head64 is None else min(ret_head64.numel(), n)
+    call("rlppo_gae_f32", ptr(rew), ptr(done), ptr(trunc), int(trunc.dtype == torch.float64), ptr(values), n,
+         float(gamma), float(lmbda), ptr(ret_std), ptr(adv), ptr(vt), ptr(ret), ptr(ret_head64), n_head,
+         ptr(carry_in), ptr(ws), ws.numel(), stream_ptr())
+    return vt, adv, ret
+
+
+def gae_chunk_summary(rew, done, trunc, values, gamma, lmbda, ret_std=None):
+    n = rew.numel()
+    out = torch.empty(4, dtype=torch.float64, device=rew.device)
+    ws = _workspace(n, rew.device)
+    call("rlppo_gae_chunk_summary", ptr(rew), ptr(done), ptr(trunc), int(trunc.dtype == torch.float64), ptr(values),
+         n, float(gamma), float(lmbda), ptr(ret_std), ptr(out), ptr(ws), ws.numel(), stream_ptr())
+    return out
+
+
+# ---- Welford --------------------------------------------------------------------------------------------
+def welford_update(mean, m2, count, samples, n, std_out=None, mean_out=None):
+    dim = mean.numel()
+    assert samples.dtype in (torch.float32, torch.float64) and count.dtype == torch.int64
+    call("rlppo_welford_update", ptr(mean), ptr(m2), ptr(count), ptr(samples), int(samples.dtype == torch.float64),
+         int(n), dim, ptr(std_out), ptr(mean_out), stream_ptr())
+
+
+# ---- ring / gather --------------------------------------------------------------------------------------
+def ring_append(ring, phys_first, src, n_rows, ring_bf16=None):
+    cap = ring.shape[0]
+    width = 1 if ring.dim() == 1 else ring.shape[1]
+    ring_ld = 1 if ring.dim() == 1 else ring.stride(0)
+    src_ld = 1 if src.dim() == 1 else src.stride(0)
+    assert src.dtype in (torch.float32, torch.float64)
+    call("rlppo_ring_append", ptr(ring), ring_ld, ptr(ring_bf16), 0 if ring_bf16 is None else ring_bf16.stride(0),
+         cap, int(phys_first), ptr(src), int(src.dtype == torch.float64), src_ld, int(n_rows), width, stream_ptr())
+
+
+def gather_batch(buf, idx, out_actions=None, out_logp=None, out_values=None, out_adv=None, out_states=None,
+                 out_states_bf16=None):
+    """buf: object with ring tensors (actions, log_probs, values, advantages, states[, states_bf16]),
+    capacity and start.  idx int64 device tensor of LOGICAL indices."""
+    B = idx.numel()
+    sb = getattr(buf, "states_bf16", None)
+    call("rlppo_gather_batch", ptr(buf.actions), ptr(buf.log_probs), ptr(buf.values), ptr(buf.advantages),
+         ptr(buf.states), buf.states.stride(0) if buf.states is not None and buf.states.dim() == 2 else 1, ptr(sb),
+         0 if sb is None else sb.stride(0), int(buf.obs_dim), int(buf.capacity), int(buf.start), ptr(idx), B,
+         ptr(out_actions), ptr(out_logp), ptr(out_values), ptr(out_adv), ptr(out_states), ptr(out_states_bf16),
+         stream_ptr())
+
+
+# ---- operand preparation ---------------------------------------------------------------------------------
+def rows_to_bf16(src, dst, mean=None, std=None, clip=5.0):
+    n_rows, width = src.shape
+    assert dst.dtype == BF16 and dst.shape[0] >= n_rows
+    if mean is None:
+        call("rlppo_rows_to_bf16", ptr(src), src.stride(0), n_rows, width, ptr(dst), dst.stride(0), stream_ptr())
+    else:
+        call("rlppo_rows_standardize_to_bf16", ptr(src), src.stride(0), n_rows, width, ptr(mean), ptr(std),
+             float(clip), ptr(dst), dst.stride(0), stream_ptr())
+
+
+def weight_to_bf16(w, wq, wt=None):
+    out_f, in_f = w.shape
+    assert w.is_contiguous() and wq.dtype == BF16
+    call("rlppo_weight_to_bf16", ptr(w), out_f, in_f, ptr(wq), wq.stride(0), wq.shape[0], ptr(wt),
+         0 if wt is None else wt.stride(0), 0 if wt is None else wt.shape[0], stream_ptr())
+
+
+# ---- tensor-core layers -------------------------------------------------------------------------------------
+def linear_fwd(x, wq, bias, y, N, K, relu, M=None):
+    M = x.shape[0] if M is None else M
+    call("rlppo_linear_fwd", ptr(x), x.stride(0), ptr(wq), wq.stride(0), ptr(bias), ptr(y), y.stride(0), int(M),
+         int(N), int(K), int(bool(relu)), stream_ptr())
+
+
+def linear_dgrad(dy, wt, hprev, dx, N, K, M=None):
+    M = dy.shape[0] if M is None else M
+    call("rlppo_linear_dgrad", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
+         0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), int(M), int(N), int(K), stream_ptr())
+
+
+def linear_wgrad(dy, x, dw, db, N, K, M=None):
+    M = dy.shape[0] if M is None else M
+    call("rlppo_linear_wgrad", ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(dw), dw.stride(0), ptr(db), int(M),
+         int(N), int(K), stream_ptr())
+
+
+def policy_head_sample(h, wq, bias, n_actions, K, M=None, u=None, seed=0, offset=0, deterministic=False,
+                       actions_out=None, actions_i64_out=None, logp_out=None, probs_out=None):
+    M = h.shape[0] if M is None else M
+    call("rlppo_policy_head_sample", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M), int(n_actions),
+         int(K), ptr(u), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), int(bool(deterministic)),
+         ptr(actions_out), ptr(actions_i64_out), ptr(logp_out), ptr(probs_out), stream_ptr())
+
+
+def policy_head_train(h, wq, bias, n_actions, K, actions, old_logp, adv, inv_batch, clip, ent_coef, dz, metrics,
+                      logp_out=None, M=None):
+    M = h.shape[0] if M is None else M
+    call("rlppo_policy_head_train", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M), int(n_actions),
+         int(K), ptr(actions), ptr(old_logp), ptr(adv), float(inv_batch), float(clip), float(ent_coef), ptr(dz),
+         dz.stride(0), ptr(logp_out), ptr(metrics), stream_ptr())
+
+
+def value_head(h, w, bias, K, values_out=None, targets=None, inv_batch=0.0, dh=None, dw=None, db=None, metrics=None,
+               M=None):
+    M = h.shape[0] if M is None else M
+    call("rlppo_value_head", ptr(h), h.stride(0), ptr(w), ptr(bias), int(M), int(K), ptr(values_out), ptr(targets),
+         float(inv_batch), ptr(dh), 0 if dh is None else dh.stride(0), ptr(dw), ptr(db), ptr(metrics), stream_ptr())
+
+
+# ---- optimiser ------------------------------------------------------------------------------------------------
+def _seg(seg_off):
+    return np.ascontiguousarray(seg_off, dtype=np.int64)
+
+
+def grad_sqnorm(grads, seg_off, sqnorm):
+    so = _seg(seg_off)
+    call("rlppo_grad_sqnorm", ptr(grads), so.ctypes.data, len(so) - 1, ptr(sqnorm), stream_ptr())
+
+
+def clip_adam(params, grads, m, v, seg_off, sqnorm, lr, step_count, max_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-8):
+    so = _seg(seg_off)
+    call("rlppo_clip_adam", ptr(params), ptr(grads), ptr(m), ptr(v), so.ctypes.data, len(so) - 1, ptr(sqnorm), ptr(lr),
+         ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps), stream_ptr())
+
+
+def sqdiff(a, b, seg_off, out):
+    so = _seg(seg_off)
+    call("rlppo_sqdiff", ptr(a), ptr(b), so.ctypes.data, len(so) - 1, ptr(out), stream_ptr())
