@@ -100,7 +100,7 @@ gae_scan_kernel(const float* __restrict__ rew, const float* __restrict__ done, c
             const bool ok = t < n;
             r[i] = ok ? __ldg(rew + t) : 0.f;
             d[i] = ok ? __ldg(done + t) : 0.f;
-            v[i] = ok ? __ldg(val + t) : 0.f;
+            v[i] = (t <= n) ? __ldg(val + t) : 0.f;   // values has n+1 entries
             tr[i] = !ok ? 0.0
                         : (TRUNC64 ? __ldg(static_cast<const double*>(trunc) + t)
                                    : (double)__ldg(static_cast<const float*>(trunc) + t));
