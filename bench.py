@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- learner-side PPO throughput (GAE + normalisation + full update) of rlgym_ppo_b200 on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
+
+One "step" = one learner iteration at steady state on synthetic rollouts of the example shape:
+Learner.add_new_experience on N_new fresh timesteps (value inference on N_new+1 states, GAE + reward
+normalisation, Welford update, ring append) followed by PPOLearner.learn on the full buffer
+(ppo_epochs x floor(buffer/B) optimiser steps: permutation gather, fwd/bwd, clip, Adam).
+
+  value   device-timed (CUDA events per step, L2 flushed between steps), rollout arrays already resident in HBM
+  e2e     the same iteration through the public API with HOST (pinned) rollout arrays: H2D of the 7 arrays and the
+          D2H read of the report scalars inside the timed region (wall clock, synchronised both sides)
+  roofline    per-kernel CUDA-event timing of one more step (rlgym_ppo_b200._lib.timing_begin), dominant kernel
+  cpu_baseline  the CPU oracle (oracle/ref_oracle.py: the reference's algorithm restated, fp32 torch-CPU + the
+          reference's Python GAE loop) on this box's host cores, bounded sample (rank 0, N=1 only)
+
+`--impl reference` times that CPU path alone with all host threads and prints the same JSON line.
+Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank contributes N_new timesteps and takes 1/R of
+every batch; the global batch, rollout and buffer grow with R (config.global_*).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: example.py shape on 1xB200
+    "c2": dict(name="example.py shape (configs[1]): 50k-step rollout, obs 89, 90 actions, 256x3 MLPs, buffer 150k, "
+                    "batch 50k, 1 epoch", n_new=50000, obs=89, act=90, layers=(256, 256, 256), buffer=150000,
+               batch=50000, epochs=1, ent=0.001),
+    # BASELINE.json configs[2] (per-GPU share of it)
+    "c3": dict(name="large nets (configs[2]): 2048-2048-1024-1024 policy/value, buffer 150k, batch 50k, 3 epochs",
+               n_new=50000, obs=89, act=90, layers=(2048, 2048, 1024, 1024), buffer=150000, batch=50000, epochs=3,
+               ent=0.001),
+}
+FLOP_PER_SAMPLE_UPDATE = {"c2": 1894912.0, "c3": 90097664.0}     # SURVEY.md 8(d), fwd+bwd both nets, un-padded
+FLOP_PER_STATE_VALUE = {"c2": 308224.0, "c3": 15046656.0}
+
+
+def synth_rollout(rng, n, obs_dim):
+    """the flat layout collect_timesteps produces (batched_agent_manager.py:159-168)."""
+    states = rng.randn(n, obs_dim).astype(np.float32)
+    next_states = np.roll(states, -1, axis=0).copy()
+    rewards = (rng.randn(n) * 0.1).astype(np.float32)
+    dones = (rng.rand(n) < 1 / 300).astype(np.float32)
+    truncated = ((rng.rand(n) < 1 / 1500) * (1 - dones)).astype(np.float64)
+    truncated[-1] = 1.0 - dones[-1]
+    return states, rewards, next_states, dones, truncated
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        # "under load" = the upper half of the samples (the sampler also sees the idle gaps between steps)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle = checker; here it is what is being timed)
+# ------------------------------------------------------------------------------------------------------------------
+def run_cpu_oracle(wl, steps, warmup, seed=0):
+    import torch
+    from oracle import ref_oracle as O
+    torch.manual_seed(123)
+    import torch.nn as nn
+
+    def mk(out):
+        dims = [wl["obs"], *wl["layers"], out]
+        ps = []
+        for i in range(len(dims) - 1):
+            l = nn.Linear(dims[i], dims[i + 1])
+            ps += [l.weight.detach().clone(), l.bias.detach().clone()]
+        return ps
+
+    pol, val = mk(wl["act"]), mk(1)
+    orc = O.PPOLearnerOracle(pol, val, wl["batch"], wl["epochs"], 3e-4, 3e-4, 0.2, wl["ent"], wl["batch"])
+    buf = O.BufferOracle(wl["buffer"], 123)
+    stats = O.WelfordOracle(1)
+    rng = np.random.RandomState(seed)
+    n = wl["n_new"]
+
+    def rollout():
+        states, rewards, next_states, dones, truncated = synth_rollout(rng, n, wl["obs"])
+        with torch.no_grad():
+            p = torch.clamp(O.policy_probs(orc.pol, torch.from_numpy(states)), 1e-11, 1.0)
+            a = torch.multinomial(p, 1, True)
+            lp = torch.log(p).gather(-1, a).flatten().numpy()
+        return states, a.flatten().numpy().astype(np.float32), lp, rewards, next_states, dones, truncated
+
+    while buf.f["rewards"].shape[0] + n < wl["buffer"]:        # reach steady state without timing
+        O.add_new_experience(orc.val, buf, stats, rollout(), 0.99, 0.95)
+    times = []
+    for it in range(warmup + steps):
+        exp = rollout()
+        t0 = time.perf_counter()
+        O.add_new_experience(orc.val, buf, stats, exp, 0.99, 0.95)
+        orc.learn(buf)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return n / float(np.mean(times)), float(np.mean(times)), torch.get_num_threads()
+
+
+def reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    # bounded: the whole run must end within minutes (one c2 iteration is ~2 s on 8 cores, c3 far more)
+    if args.workload == "c3":
+        steps, warmup = 1, 0
+    else:
+        steps = min(steps, 5)
+    tput, sec, threads = run_cpu_oracle(wl, steps, warmup)
+    sample = f"{steps} steady-state iteration(s) of the full workload after {warmup} warm-up, oracle port of the reference"
+    line = {"impl": "reference", "metric": "learner_timesteps_per_sec", "value": tput, "unit": "timesteps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"]},
+            "cpu_baseline": {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": tput, "unit": "timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def b200_arm(args, wl):
+    import torch
+    from types import SimpleNamespace
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    from rlgym_ppo_b200 import _lib
+    from rlgym_ppo_b200.learner import Learner
+    from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
+    from rlgym_ppo_b200.util import WelfordRunningStat
+    _lib.require_device()
+
+    R = world
+    n_local = wl["n_new"]
+    n_glob, batch, cap = n_local * R, wl["batch"] * R, wl["buffer"] * R
+    torch.manual_seed(123)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ppo = PPOLearner(wl["obs"], wl["act"], 0, wl["layers"], wl["layers"], (0.1, 1.0), batch, wl["epochs"], 3e-4,
+                         3e-4, 0.2, wl["ent"], batch, dev)
+    ns = SimpleNamespace(ppo_learner=ppo, return_stats=WelfordRunningStat(1, device=dev), standardize_returns=True,
+                         gae_gamma=0.99, gae_lambda=0.95, max_returns_per_stats_increment=150,
+                         experience_buffer=ExperienceBuffer(cap, 123, dev))
+
+    # ---- synthetic rollouts: a pool of distinct ones, pinned on the host and resident on the device -------------------
+    # Every rank draws the same global rollout (same seed): the experience is replicated, the update is sharded.
+    rng = np.random.RandomState(0)
+    pool_host, pool_dev = [], []
+    n_pool = 3
+    for _ in range(n_pool):
+        states, rewards, next_states, dones, truncated = synth_rollout(rng, n_glob, wl["obs"])
+        acts, logp = ppo.policy.get_action_device(torch.from_numpy(states).to(dev))
+        host = [torch.from_numpy(a).pin_memory() for a in
+                (states, acts.float().cpu().numpy(), logp.cpu().numpy(), rewards, next_states, dones, truncated)]
+        pool_host.append((tuple(t.numpy() for t in host), host))   # numpy views of pinned memory (+ keep-alive)
+        pool_dev.append(tuple(t.to(dev) for t in host))
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pool_host[0][1])
+    d2h_bytes = ppo._tail_host.numel() * 4
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(exp):
+        Learner.add_new_experience(ns, exp)
+        return ppo.learn(ns.experience_buffer)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # fill to steady state, then warm up
+    it = 0
+    while len(ns.experience_buffer) + n_glob < cap:
+        Learner.add_new_experience(ns, pool_dev[it % n_pool])
+        it += 1
+    for _ in range(max(args.warmup, 3)):
+        step(pool_dev[it % n_pool])
+        it += 1
+
+    # ---- (1) device-resident timing: K steps, one event pair per step, L2 flushed between steps --------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    calls0 = _lib.CALLS
+    barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        report = step(pool_dev[it % n_pool])
+        e1.record()
+        evs.append((e0, e1))
+        it += 1
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    calls = _lib.CALLS - calls0
+
+    # ---- (2) end to end through the public API with host buffers ---------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        report = step(pool_host[it % n_pool][0])
+        _ = report["Policy Entropy"]
+        it += 1
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if sampler else None
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- (3) per-kernel pass for the roofline object (rank 0; not part of the timed numbers) --------------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "measured" if peaks else "fallback"
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+        _lib.timing_begin()
+        step(pool_dev[it % n_pool])
+        per = _lib.timing_end()
+        it += 1
+        total = sum(v["ms"] for v in per.values())
+        kernels = {k.replace("rlppo_", ""): {"calls": v["calls"], "ms": round(v["ms"], 4),
+                                             "share": round(v["ms"] / total, 4),
+                                             **({"TFLOP/s": round(v["flop"] / v["ms"] / 1e9, 2)} if v["flop"] else {}),
+                                             **({"GB/s": round(v["byte"] / v["ms"] / 1e6, 1)} if v["byte"] else {})}
+                   for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])}
+        top_name, top = max(per.items(), key=lambda kv: kv[1]["ms"])
+        if top["flop"]:
+            ach = top["flop"] / top["ms"] / 1e9
+            roofline = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
+                        "frac": ach / tc_peak, "traffic": None, "peak_source": peak_src + " (sustained bf16)",
+                        "launches": top["calls"], "avg_launch_ms": top["ms"] / top["calls"]}
+        else:
+            ach = top["byte"] / top["ms"] / 1e6
+            roofline = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "launches": top["calls"], "avg_launch_ms": top["ms"] / top["calls"]}
+
+    # ---- (4) CPU baseline (rank 0, single-GPU run only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if args.workload == "c2":
+            tput, sec, threads = run_cpu_oracle(wl, 3, 1)
+            cpu = {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": "port",
+                   "sample": "3 steady-state iterations of the full workload after 1 warm-up (oracle/ref_oracle.py: "
+                             "Python GAE loop + fp32 torch-CPU MLPs)", "sec_per_step": sec}
+        else:
+            small = dict(wl, n_new=5000, batch=5000, buffer=15000)
+            tput, sec, threads = run_cpu_oracle(small, 1, 0)
+            cpu = {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": "port",
+                   "sample": "1 iteration at 1/10 of the rows (5k new, batch 5k, buffer 15k), same nets and epochs",
+                   "sec_per_step": sec}
+
+    if rank == 0:
+        K = args.steps
+        n_updates = wl["epochs"] * (cap // batch)
+        flop_step = n_glob * FLOP_PER_STATE_VALUE[args.workload] + n_updates * batch * FLOP_PER_SAMPLE_UPDATE[args.workload]
+        line = {
+            "metric": "learner_timesteps_per_sec", "value": n_glob * K / (dev_ms / 1e3), "unit": "timesteps/s",
+            "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "global_new_timesteps": n_glob, "global_batch": batch,
+                       "global_buffer": cap, "optimizer_steps_per_step": n_updates,
+                       "consumed_samples_per_step": n_updates * batch, "parallelism": f"dp{world}",
+                       "l2": "flushed between timed steps (256 MiB write); working set > L2",
+                       "algorithmic_tflop_per_step": flop_step / 1e12,
+                       "achieved_tflops": flop_step / (dev_ms / K / 1e3) / 1e12},
+            "e2e": {"value": n_glob * K / (e2e_ms / 1e3), "unit": "timesteps/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": calls,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "kernels": kernels,
+            "report": {k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in report.items()},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        reference_arm(args, wl)
+    else:
+        b200_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,10 +100,11 @@ int rlppo_host_permutation(uint32_t* h_key, int32_t* h_pos, int64_t n, int64_t* 
  * [states ; next_states[-1]] (learner.py:347-349) and policy inference obs. */
 int rlppo_rows_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width, uint16_t* dst,
                        int64_t dst_ld, void* stream);
-/* Same with obs standardisation fused: clip((x-mean)/std, -5, 5) (batched_agent_manager.py:303-315). */
+/* Same with obs standardisation fused: clip((x-mean)/std, -5, 5) (batched_agent_manager.py:303-315).
+ * dst_f32 (optional, ld dst_f32_ld): the standardised rows in f32 as well -- what the trajectory stores. */
 int rlppo_rows_standardize_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width,
                                    const float* mean, const float* std, float clip, uint16_t* dst,
-                                   int64_t dst_ld, void* stream);
+                                   int64_t dst_ld, float* dst_f32, int64_t dst_f32_ld, void* stream);
 /* fp32 master weight W [out,in] (torch nn.Linear layout) -> bf16 W [out_pad, in_pad] (K-major operand of
  * the forward GEMM) and, if wt != NULL, bf16 W^T [in_pad, out_pad] (operand of the dgrad GEMM). */
 int rlppo_weight_to_bf16(const float* w, int out_f, int in_f, uint16_t* wq, int64_t wq_ld, int out_pad,
@@ -160,6 +161,52 @@ int rlppo_policy_head_train(const uint16_t* h, int64_t ldh, const uint16_t* w, i
 int rlppo_value_head(const uint16_t* h, int64_t ldh, const float* w, const float* bias, int64_t M, int K,
                      float* values_out, const float* targets, float inv_batch, uint16_t* dh, int64_t lddh,
                      float* dw, float* db, float* metrics, void* stream);
+
+/* ---- whole-network fused kernels (hidden widths 64/128/192/256, <= 4 hidden layers, obs <= 256, <= 128 actions) ----
+ * One persistent tcgen05 kernel runs a 128-row tile of samples through the WHOLE Linear/ReLU stack, the head and
+ * (training) the backward data path without leaving the SM: hidden activations live in shared memory as the next
+ * GEMM's A operand, ReLU masks in registers, bias gradients in registers.  HBM sees x once, and (training) H_l,
+ * d(logits) and dL/dH_l once each -- they are the operands of rlppo_linear_wgrad, which contracts over all rows.
+ * Replaces the per-layer sequence rlppo_linear_fwd x L + head + rlppo_linear_dgrad x L for these shapes.
+ * All pointers device; bf16 as uint16_t; l = 0..n_hidden-1 hidden Linear layers, index n_hidden = the head. */
+typedef struct rlppo_fused_net {
+    int n_hidden;               /* 1..4 */
+    int in_dim;                 /* observation width (<= 256) */
+    int64_t in_ld;              /* row stride of x in elements (multiple of 8) */
+    int hidden[4];              /* hidden widths */
+    const uint16_t* wq[5];      /* forward operands W_l bf16 [out_pad8, ld]; [n_hidden] = policy head (NULL for value) */
+    int64_t wq_ld[5];
+    const uint16_t* wt[5];      /* dgrad operands W_l^T bf16 [in_pad8, ld]; [0] unused; training only */
+    int64_t wt_ld[5];
+    const float* bias[5];       /* f32 biases; [n_hidden] = head bias (policy: n_actions, value: 1) */
+    float* gbias[5];            /* f32 bias gradients, accumulated (training) */
+    uint16_t* h[4];             /* out (training): H_l bf16 [M, hidden_l], ld h_ld */
+    int64_t h_ld[4];
+    uint16_t* dh[4];            /* out (training): dL/dH_l (ReLU-masked) bf16 [M, hidden_l] */
+    int64_t dh_ld[4];
+    uint16_t* dz;               /* out (policy training): d(ppo_loss)/d(logits) bf16 [M, pad8(n_actions)] */
+    int64_t dz_ld;
+} rlppo_fused_net;
+
+/* DiscreteFF.get_backprop_data + PPO loss + backward data path (discrete_policy.py:64-80, ppo_learner.py:153-180,
+ * SURVEY.md A.3).  metrics as rlppo_policy_head_train.  Weight gradients: rlppo_linear_wgrad on (dz, H_L),
+ * (dh[l], H_{l-1}), (dh[0], x); bias gradients are accumulated here. */
+int rlppo_policy_train_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, int n_actions,
+                             const float* actions, const float* old_logp, const float* adv, float inv_batch,
+                             float clip, float ent_coef, float* logp_out, float* metrics, void* stream);
+/* DiscreteFF.get_action (discrete_policy.py:44-62) for all rows: same sampler contract as rlppo_policy_head_sample. */
+int rlppo_policy_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, int n_actions,
+                             const float* u_inject, uint64_t seed, uint64_t offset, int deterministic,
+                             float* actions_out, int64_t* actions_i64_out, float* logp_out, void* stream);
+/* ValueEstimator forward + MSE loss + backward data path (value_estimator.py:30-36, ppo_learner.py:146,176).
+ * w_head f32[hidden_last] (the last Linear's weight row), gw_head f32[hidden_last] accumulated; metrics[5,6] as
+ * rlppo_value_head; values_out optional f32[M]. */
+int rlppo_value_train_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, const float* w_head,
+                            const float* targets, float inv_batch, float* gw_head, float* values_out,
+                            float* metrics, void* stream);
+/* ValueEstimator forward only (learner.py:352): values_out f32[M]. */
+int rlppo_value_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, const float* w_head,
+                            float* values_out, void* stream);
 
 /* ---- (d-6) clip_grad_norm_ + Adam: ppo_learner.py:187-193, torch.optim.Adam ------------------------
  * Flat fp32 arenas; `seg` describes n_seg contiguous segments (policy params, value params): seg_off

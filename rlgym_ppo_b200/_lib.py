@@ -39,7 +39,7 @@ _SIGS = {
     "rlppo_gather_batch": ([_P, _P, _P, _P, _P, _L, _P, _L, _I, _L, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P], _I),
     "rlppo_host_permutation": ([_P, _P, _L, _P], _I),
     "rlppo_rows_to_bf16": ([_P, _L, _L, _I, _P, _L, _P], _I),
-    "rlppo_rows_standardize_to_bf16": ([_P, _L, _L, _I, _P, _P, _F, _P, _L, _P], _I),
+    "rlppo_rows_standardize_to_bf16": ([_P, _L, _L, _I, _P, _P, _F, _P, _L, _P, _L, _P], _I),
     "rlppo_weight_to_bf16": ([_P, _I, _I, _P, _L, _I, _P, _L, _I, _P], _I),
     "rlppo_linear_fwd": ([_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _P], _I),
     "rlppo_linear_dgrad": ([_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P], _I),
@@ -47,12 +47,24 @@ _SIGS = {
     "rlppo_policy_head_sample": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _U64, _U64, _I, _P, _P, _P, _P, _P], _I),
     "rlppo_policy_head_train": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _P, _P, _F, _F, _F, _P, _L, _P, _P, _P], _I),
     "rlppo_value_head": ([_P, _L, _P, _P, _L, _I, _P, _P, _F, _P, _L, _P, _P, _P, _P], _I),
+    "rlppo_policy_train_fused": ([_P, _P, _L, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P], _I),
+    "rlppo_policy_infer_fused": ([_P, _P, _L, _I, _P, _U64, _U64, _I, _P, _P, _P, _P], _I),
+    "rlppo_value_train_fused": ([_P, _P, _L, _P, _P, _F, _P, _P, _P, _P], _I),
+    "rlppo_value_infer_fused": ([_P, _P, _L, _P, _P, _P], _I),
     "rlppo_grad_sqnorm": ([_P, _P, _I, _P, _P], _I),
     "rlppo_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P], _I),
     "rlppo_sqdiff": ([_P, _P, _P, _I, _P, _P], _I),
 }
 
 EXPORTED = tuple(_SIGS)
+
+
+class FusedNet(ctypes.Structure):
+    """struct rlppo_fused_net (include/rlppo.h)."""
+    _fields_ = [("n_hidden", _I), ("in_dim", _I), ("in_ld", _L), ("hidden", _I * 4),
+                ("wq", _P * 5), ("wq_ld", _L * 5), ("wt", _P * 5), ("wt_ld", _L * 5),
+                ("bias", _P * 5), ("gbias", _P * 5), ("h", _P * 4), ("h_ld", _L * 4),
+                ("dh", _P * 4), ("dh_ld", _L * 4), ("dz", _P), ("dz_ld", _L)]
 
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(_lib, _name)  # AttributeError here = header and library disagree
@@ -85,9 +97,45 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name, *args):
+CALLS = 0          # C-ABI compute calls made so far (each enqueues at least one kernel)
+_TIMING = None     # None, or a list of (name, work, start_event, end_event) while per-call timing is on
+
+
+def call(name, *args, work=None):
+    """Invoke a C-ABI entry point.  `work` = (kind, amount): the call's algorithmic flops ("flop") or HBM bytes
+    ("byte"), recorded only while timing_begin() is active (bench.py's roofline pass)."""
+    global CALLS
+    CALLS += 1
+    if _TIMING is None:
+        _check(getattr(_lib, name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     rc = getattr(_lib, name)(*args)
+    e1.record()
     _check(rc, name)
+    _TIMING.append((name, work, e0, e1))
+
+
+def timing_begin():
+    global _TIMING
+    _TIMING = []
+
+
+def timing_end():
+    """Stops per-call timing; returns {name: {"calls", "ms", "flop", "byte"}} measured with CUDA events on the
+    launching stream."""
+    global _TIMING
+    rec, _TIMING = _TIMING, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, work, e0, e1 in rec:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flop": 0.0, "byte": 0.0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        if work is not None:
+            d[work[0]] += float(work[1])
+    return out
 
 
 def require_device():

@@ -120,7 +120,8 @@ __global__ void gather_kernel(const float* __restrict__ actions, const float* __
 template <bool STANDARDIZE>
 __global__ void rows_to_bf16_kernel(const float* __restrict__ src, int64_t src_ld, int64_t n_rows, int width,
                                     const float* __restrict__ mean, const float* __restrict__ stdv, float clip,
-                                    uint16_t* __restrict__ dst, int64_t dst_ld) {
+                                    uint16_t* __restrict__ dst, int64_t dst_ld, float* __restrict__ dst_f32,
+                                    int64_t dst_f32_ld) {
     const int64_t total = n_rows * dst_ld;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -132,6 +133,7 @@ __global__ void rows_to_bf16_kernel(const float* __restrict__ src, int64_t src_l
             if (STANDARDIZE) {  // batched_agent_manager.py:303-315
                 x = __fdiv_rn(__fsub_rn(x, __ldg(mean + c)), __ldg(stdv + c));
                 x = fminf(fmaxf(x, -clip), clip);
+                if (dst_f32 != nullptr) dst_f32[row * dst_f32_ld + c] = x;
             }
         }
         dst[i] = rlppo::f32_to_bf16_bits(x);
@@ -236,20 +238,23 @@ int rlppo_rows_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int wid
     const int64_t total = n_rows * dst_ld;
     const unsigned blocks = (unsigned)min((int64_t)rlppo::num_sms() * 16, (total + 255) / 256);
     rows_to_bf16_kernel<false><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_ld, n_rows, width, nullptr,
-                                                                                       nullptr, 0.f, dst, dst_ld);
+                                                                                       nullptr, 0.f, dst, dst_ld, nullptr, 0);
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }
 
 int rlppo_rows_standardize_to_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width, const float* mean,
-                                   const float* stdv, float clip, uint16_t* dst, int64_t dst_ld, void* stream) {
+                                   const float* stdv, float clip, uint16_t* dst, int64_t dst_ld, float* dst_f32,
+                                   int64_t dst_f32_ld, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(src && dst && mean && stdv && dst_ld >= width && n_rows >= 0, "bad argument");
     if (n_rows == 0) return RLPPO_OK;
     const int64_t total = n_rows * dst_ld;
     const unsigned blocks = (unsigned)min((int64_t)rlppo::num_sms() * 16, (total + 255) / 256);
+    RLPPO_CHECK_ARG(!dst_f32 || dst_f32_ld >= width, "dst_f32_ld must be >= width");
     rows_to_bf16_kernel<true><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_ld, n_rows, width, mean,
-                                                                                      stdv, clip, dst, dst_ld);
+                                                                                      stdv, clip, dst, dst_ld, dst_f32,
+                                                                                      dst_f32_ld);
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }

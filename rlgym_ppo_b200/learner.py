@@ -1,0 +1,473 @@
+"""Learner: the `Learner(env_fn).learn()` surface of rlgym_ppo/learner.py over the B200 learner path.
+
+Constructor keywords, defaults, public attributes, report keys and checkpoint files are the reference's
+(learner.py:29-78, 169-189, 275-296, 387-564).  Environment stepping stays on host processes
+(batched_agents.BatchedAgentManager); everything between "rollout arrays are on the host" and "weights updated"
+runs on the device without a host round trip:
+
+  add_new_experience (learner.py:330-385)
+    7 rollout arrays --one async H2D each--> HBM
+    [states ; next_states[-1]] -> bf16 rows -> value net (tcgen05 GEMMs + fused value head) -> V[N+1]
+    rlppo_gae_f32: segmented reverse scan, reward / return_std clip fused, std read from the device Welford state
+    rlppo_welford_update on the first min(150, N) returns (f64, as the reference's Python floats)
+    rlppo_ring_append x9 into the ExperienceBuffer rings
+  PPOLearner.learn: see ppo/ppo_learner.py
+"""
+import json
+import os
+import random
+import shutil
+import time
+from typing import Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._staging import Stager
+from .ppo import ExperienceBuffer, PPOLearner
+from .util import WelfordRunningStat
+
+_EXP_FIELDS = ("states", "actions", "log_probs", "rewards", "next_states", "dones", "truncated")
+
+
+def _f32(t):
+    return t if t.dtype == torch.float32 else t.to(torch.float32)
+
+
+class Learner(object):
+    def __init__(
+            # fmt: off
+            self,
+            env_create_function,
+            metrics_logger=None,
+            n_proc: int = 8,
+            min_inference_size: int = 80,
+            render: bool = False,
+            render_delay: float = 0,
+            timestep_limit: int = 5_000_000_000,
+            exp_buffer_size: int = 100000,
+            ts_per_iteration: int = 50000,
+            standardize_returns: bool = True,
+            standardize_obs: bool = True,
+            max_returns_per_stats_increment: int = 150,
+            steps_per_obs_stats_increment: int = 5,
+            policy_layer_sizes: Tuple[int, ...] = (256, 256, 256),
+            critic_layer_sizes: Tuple[int, ...] = (256, 256, 256),
+            continuous_var_range: Tuple[float, ...] = (0.1, 1.0),
+            ppo_epochs: int = 10,
+            ppo_batch_size: int = 50000,
+            ppo_minibatch_size: Union[int, None] = None,
+            ppo_ent_coef: float = 0.005,
+            ppo_clip_range: float = 0.2,
+            gae_lambda: float = 0.95,
+            gae_gamma: float = 0.99,
+            policy_lr: float = 3e-4,
+            critic_lr: float = 3e-4,
+            log_to_wandb: bool = False,
+            load_wandb: bool = True,
+            wandb_run=None,
+            wandb_project_name: Union[str, None] = None,
+            wandb_group_name: Union[str, None] = None,
+            wandb_run_name: Union[str, None] = None,
+            checkpoints_save_folder: Union[str, None] = None,
+            add_unix_timestamp: bool = True,
+            checkpoint_load_folder: Union[str, None] = "latest",  # "latest" loads latest checkpoint
+            save_every_ts: int = 1_000_000,
+            instance_launch_delay: Union[float, None] = None,
+            random_seed: int = 123,
+            n_checkpoints_to_keep: int = 5,
+            shm_buffer_size: int = 8192,
+            device: str = "auto"):
+        assert (
+                env_create_function is not None
+        ), "MUST PROVIDE A FUNCTION TO CREATE RLGYM FUNCTIONS TO INITIALIZE RLGYM-PPO"
+
+        if checkpoints_save_folder is None:
+            checkpoints_save_folder = os.path.join("data", "checkpoints", "rlgym-ppo-run")
+        self.add_unix_timestamp = add_unix_timestamp
+        if add_unix_timestamp:
+            checkpoints_save_folder = f"{checkpoints_save_folder}-{time.time_ns()}"
+
+        torch.manual_seed(random_seed)
+        np.random.seed(random_seed)
+        random.seed(random_seed)
+
+        self.n_checkpoints_to_keep = n_checkpoints_to_keep
+        self.checkpoints_save_folder = checkpoints_save_folder
+        self.max_returns_per_stats_increment = max_returns_per_stats_increment
+        self.metrics_logger = metrics_logger
+        self.standardize_returns = standardize_returns
+        self.save_every_ts = save_every_ts
+        self.ts_since_last_save = 0
+
+        # There is no CPU learner here: "auto"/"gpu" pick the current CUDA device, anything else must name one.
+        _lib.require_device()
+        if device in {"auto", "gpu"}:
+            self.device = "cuda:%d" % torch.cuda.current_device()
+        elif "cuda" in str(device):
+            self.device = device
+        else:
+            raise _lib.RlppoError(f"device {device!r}: rlgym_ppo_b200 runs on a B200 only (no CPU fallback)")
+        print(f"Using device {self.device}")
+
+        self.exp_buffer_size = exp_buffer_size
+        self.timestep_limit = timestep_limit
+        self.ts_per_epoch = ts_per_iteration
+        self.gae_lambda = gae_lambda
+        self.gae_gamma = gae_gamma
+        self.return_stats = WelfordRunningStat(1, device=self.device)
+        self.epoch = 0
+
+        self.experience_buffer = ExperienceBuffer(self.exp_buffer_size, seed=random_seed, device=self.device)
+
+        print("Initializing processes...")
+        from .batched_agents import BatchedAgentManager
+        collect_metrics_fn = None if metrics_logger is None else self.metrics_logger.collect_metrics
+        self.agent = BatchedAgentManager(
+            None, min_inference_size=min_inference_size,
+            seed=random_seed,
+            standardize_obs=standardize_obs,
+            steps_per_obs_stats_increment=steps_per_obs_stats_increment,
+            device=self.device,
+        )
+        obs_space_size, act_space_size, action_space_type = self.agent.init_processes(
+            n_processes=n_proc,
+            build_env_fn=env_create_function,
+            collect_metrics_fn=collect_metrics_fn,
+            spawn_delay=instance_launch_delay,
+            render=render,
+            render_delay=render_delay,
+            shm_buffer_size=shm_buffer_size,
+        )
+        obs_space_size = np.prod(obs_space_size)
+        print("Initializing PPO...")
+        if ppo_minibatch_size is None:
+            ppo_minibatch_size = ppo_batch_size
+
+        self.ppo_learner = PPOLearner(
+            obs_space_size,
+            act_space_size,
+            device=self.device,
+            batch_size=ppo_batch_size,
+            mini_batch_size=ppo_minibatch_size,
+            n_epochs=ppo_epochs,
+            continuous_var_range=continuous_var_range,
+            policy_type=action_space_type,
+            policy_layer_sizes=policy_layer_sizes,
+            critic_layer_sizes=critic_layer_sizes,
+            policy_lr=policy_lr,
+            critic_lr=critic_lr,
+            clip_range=ppo_clip_range,
+            ent_coef=ppo_ent_coef,
+        )
+
+        self.agent.policy = self.ppo_learner.policy
+
+        self.config = {
+            "n_proc": n_proc,
+            "min_inference_size": min_inference_size,
+            "timestep_limit": timestep_limit,
+            "exp_buffer_size": exp_buffer_size,
+            "ts_per_iteration": ts_per_iteration,
+            "standardize_returns": standardize_returns,
+            "standardize_obs": standardize_obs,
+            "policy_layer_sizes": policy_layer_sizes,
+            "critic_layer_sizes": critic_layer_sizes,
+            "ppo_epochs": ppo_epochs,
+            "ppo_batch_size": ppo_batch_size,
+            "ppo_minibatch_size": ppo_minibatch_size,
+            "ppo_ent_coef": ppo_ent_coef,
+            "ppo_clip_range": ppo_clip_range,
+            "gae_lambda": gae_lambda,
+            "gae_gamma": gae_gamma,
+            "policy_lr": policy_lr,
+            "critic_lr": critic_lr,
+            "shm_buffer_size": shm_buffer_size,
+        }
+
+        self.wandb_run = wandb_run
+        wandb_loaded = checkpoint_load_folder is not None and self.load(checkpoint_load_folder, load_wandb, policy_lr,
+                                                                        critic_lr)
+
+        if log_to_wandb and self.wandb_run is None and not wandb_loaded:
+            import wandb
+            project = "rlgym-ppo" if wandb_project_name is None else wandb_project_name
+            group = "unnamed-runs" if wandb_group_name is None else wandb_group_name
+            run_name = "rlgym-ppo-run" if wandb_run_name is None else wandb_run_name
+            print("Attempting to create new wandb run...")
+            self.wandb_run = wandb.init(project=project, group=group, config=self.config, name=run_name, reinit=True)
+            print("Created new wandb run!", self.wandb_run.id)
+        print("Learner successfully initialized!")
+
+    def update_learning_rate(self, new_policy_lr=None, new_critic_lr=None):
+        if new_policy_lr is not None:
+            self.policy_lr = new_policy_lr
+            for param_group in self.ppo_learner.policy_optimizer.param_groups:
+                param_group['lr'] = new_policy_lr
+            print(f"New policy learning rate: {new_policy_lr}")
+        if new_critic_lr is not None:
+            self.critic_lr = new_critic_lr
+            for param_group in self.ppo_learner.value_optimizer.param_groups:
+                param_group['lr'] = new_critic_lr
+            print(f"New policy learning rate: {new_policy_lr}")
+
+    def learn(self):
+        """try / save-on-error / always-cleanup wrapper of learner.py:218-238."""
+        try:
+            self._learn()
+        except Exception:
+            import traceback
+            print("\n\nLEARNING LOOP ENCOUNTERED AN ERROR\n")
+            traceback.print_exc()
+            try:
+                self.save(self.agent.cumulative_timesteps)
+            except:  # noqa: E722
+                print("FAILED TO SAVE ON EXIT")
+        finally:
+            self.cleanup()
+
+    def _learn(self):
+        from .util import reporting
+        from .util.kbhit import KBHit
+        kb = KBHit()   # guarded: no-op without a TTY (gpurun / CI)
+        print("Press (p) to pause (c) to checkpoint, (q) to checkpoint and quit (after next iteration)\n")
+
+        while self.agent.cumulative_timesteps < self.timestep_limit:
+            epoch_start = time.perf_counter()
+            report = {}
+
+            experience, collected_metrics, steps_collected, collection_time = self.agent.collect_timesteps(
+                self.ts_per_epoch
+            )
+            if self.metrics_logger is not None:
+                self.metrics_logger.report_metrics(collected_metrics, self.wandb_run, self.agent.cumulative_timesteps)
+
+            self.add_new_experience(experience)
+            ppo_report = self.ppo_learner.learn(self.experience_buffer)
+
+            epoch_stop = time.perf_counter()
+            epoch_time = epoch_stop - epoch_start
+
+            report.update(ppo_report)
+            if self.epoch < 1:
+                report["Value Function Loss"] = np.nan
+            report["Cumulative Timesteps"] = self.agent.cumulative_timesteps
+            report["Total Iteration Time"] = epoch_time
+            report["Timesteps Collected"] = steps_collected
+            report["Timestep Collection Time"] = collection_time
+            report["Timestep Consumption Time"] = epoch_time - collection_time
+            report["Collected Steps per Second"] = steps_collected / collection_time
+            report["Overall Steps per Second"] = steps_collected / epoch_time
+
+            self.ts_since_last_save += steps_collected
+            if self.agent.average_reward is not None:
+                report["Policy Reward"] = self.agent.average_reward
+            else:
+                report["Policy Reward"] = np.nan
+
+            reporting.report_metrics(loggable_metrics=report, debug_metrics=None, wandb_run=self.wandb_run)
+            report.clear()
+            ppo_report.clear()
+
+            if kb.kbhit():
+                c = kb.getch()
+                if c == 'p':
+                    print("Paused, press any key to resume")
+                    while True:
+                        if kb.kbhit():
+                            break
+                if c in ('c', 'q'):
+                    self.save(self.agent.cumulative_timesteps)
+                if c == 'q':
+                    return
+                if c in ('c', 'p'):
+                    print("Resuming...\n")
+
+            if self.ts_since_last_save >= self.save_every_ts:
+                self.save(self.agent.cumulative_timesteps)
+                self.ts_since_last_save = 0
+
+            self.epoch += 1
+
+    # ---- the learner-side hot path, first half (learner.py:330-385) ------------------------------------------------
+    def add_new_experience(self, experience):
+        """
+        Add timesteps to the experience buffer and compute advantages, value targets and returns for them.
+        `experience`: (states, actions, log_probs, rewards, next_states, dones, truncated) as NumPy arrays (any float
+        dtype; pinned memory is copied without a bounce), torch CPU tensors or device tensors.
+        Everything after the H2D copies runs on the device; nothing is read back.  Also callable unbound on any
+        object carrying ppo_learner, return_stats, standardize_returns, gae_gamma, gae_lambda,
+        max_returns_per_stats_increment and experience_buffer.
+        """
+        buf = self.experience_buffer
+        value_net = self.ppo_learner.value_net
+        vst = value_net._stack
+        dev = vst.device
+        stager = getattr(self, "_stager", None)
+        if stager is None:
+            stager = Stager(dev)
+            try:
+                self._stager = stager
+            except AttributeError:
+                pass
+        d = {name: stager.to_device(arr, "exp." + name) for name, arr in zip(_EXP_FIELDS, experience)}
+        states = _f32(d["states"])
+        n = int(states.shape[0])
+        if n == 0:
+            return
+        obs = int(states.shape[1])
+        if buf._rings is None:
+            buf._allocate(obs)
+
+        # value-net input [states ; next_states[-1]] (learner.py:347-349) as bf16 rows, straight from the staged arrays
+        ws = vst.workspace(n + 1)
+        x = ws["x"]
+        ops.rows_to_bf16(states, x)
+        ops.rows_to_bf16(_f32(d["next_states"])[n - 1:n], x[n:n + 1])
+        values = value_net.values_from_bf16(x, n + 1)                      # :352, stays on the device
+
+        ret_std = self.return_stats.device_std() if self.standardize_returns else None     # :356
+        n_inc = min(int(self.max_returns_per_stats_increment), n) if self.standardize_returns else 0
+        head = torch.empty(n_inc, dtype=torch.float64, device=dev) if n_inc else None
+        vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
+                             self.gae_lambda, ret_std, ret_head64=head)    # :358-366
+        if n_inc:
+            self.return_stats.increment_device(head, n_inc)               # :368-372 (after the scan read std)
+        d["values"], d["advantages"] = vt, adv
+        buf.submit_device(d)                                               # :375-385
+
+    def save(self, cumulative_timesteps):
+        """Checkpoint in the reference's layout (learner.py:387-444)."""
+        folder_path = os.path.join(self.checkpoints_save_folder, str(cumulative_timesteps))
+        os.makedirs(folder_path, exist_ok=True)
+
+        print(f"Saving checkpoint {cumulative_timesteps}...")
+        existing_checkpoints = [int(arg) for arg in os.listdir(self.checkpoints_save_folder)]
+        if len(existing_checkpoints) > self.n_checkpoints_to_keep:
+            existing_checkpoints.sort()
+            for checkpoint_name in existing_checkpoints[: -self.n_checkpoints_to_keep]:
+                shutil.rmtree(os.path.join(self.checkpoints_save_folder, str(checkpoint_name)))
+
+        os.makedirs(folder_path, exist_ok=True)
+        self.ppo_learner.save_to(folder_path)
+
+        book_keeping_vars = {
+            "cumulative_timesteps": self.agent.cumulative_timesteps,
+            "cumulative_model_updates": self.ppo_learner.cumulative_model_updates,
+            "policy_average_reward": self.agent.average_reward,
+            "epoch": self.epoch,
+            "ts_since_last_save": self.ts_since_last_save,
+            "reward_running_stats": self.return_stats.to_json(),
+        }
+        if self.agent.standardize_obs:
+            book_keeping_vars["obs_running_stats"] = self.agent.obs_stats.to_json()
+        if self.standardize_returns:
+            book_keeping_vars["reward_running_stats"] = self.return_stats.to_json()
+
+        if self.wandb_run is not None:
+            book_keeping_vars["wandb_run_id"] = self.wandb_run.id
+            book_keeping_vars["wandb_project"] = self.wandb_run.project
+            book_keeping_vars["wandb_entity"] = self.wandb_run.entity
+            book_keeping_vars["wandb_group"] = self.wandb_run.group
+            book_keeping_vars["wandb_config"] = self.wandb_run.config.as_dict()
+
+        book_keeping_table_path = os.path.join(folder_path, "BOOK_KEEPING_VARS.json")
+        with open(book_keeping_table_path, "w") as f:
+            json.dump(book_keeping_vars, f, indent=4)
+        print(f"Checkpoint {cumulative_timesteps} saved!\n")
+
+    def load(self, folder_path, load_wandb, new_policy_lr=None, new_critic_lr=None):
+        """Load a checkpoint written by this implementation or by the reference (learner.py:446-564)."""
+        if folder_path == "latest":
+            save_folder = self.checkpoints_save_folder
+            if save_folder is None:
+                return
+            if self.add_unix_timestamp:
+                base_save_folder = save_folder[:save_folder.rfind('-')]
+                save_path = os.path.dirname(base_save_folder)
+                if not os.path.exists(save_path):
+                    return
+                highest_timestamp = -1
+                best_folder = None
+                for filename in os.listdir(save_path):
+                    full_path = os.path.join(save_path, filename)
+                    if not os.path.isdir(full_path):
+                        continue
+                    if full_path.startswith(base_save_folder):
+                        unix_start_idx = full_path.rfind('-') + 1
+                        if unix_start_idx > 0:
+                            unix_time_str = full_path[unix_start_idx:]
+                            if unix_time_str.isdigit():
+                                timestamp = int(unix_time_str)
+                                if timestamp > highest_timestamp:
+                                    highest_timestamp = timestamp
+                                    best_folder = full_path
+                if best_folder is None:
+                    return
+                load_base_path = best_folder
+            else:
+                if os.path.exists(self.checkpoints_save_folder):
+                    load_base_path = self.checkpoints_save_folder
+                else:
+                    return
+
+            highest_ts = -1
+            for filename in os.listdir(load_base_path):
+                if not os.path.isdir(os.path.join(load_base_path, filename)):
+                    continue
+                if not filename.isdigit():
+                    continue
+                highest_ts = max(highest_ts, int(filename))
+            if highest_ts != -1:
+                folder_path = os.path.join(load_base_path, str(highest_ts))
+                print(f"Auto-load path: {folder_path}")
+            else:
+                return
+
+        assert os.path.exists(folder_path), f"UNABLE TO LOCATE FOLDER {folder_path}"
+        print(f"Loading from checkpoint at {folder_path}")
+
+        self.ppo_learner.load_from(folder_path)
+
+        wandb_loaded = False
+        with open(os.path.join(folder_path, "BOOK_KEEPING_VARS.json"), "r") as f:
+            book_keeping_vars = dict(json.load(f))
+            self.agent.cumulative_timesteps = book_keeping_vars["cumulative_timesteps"]
+            self.agent.average_reward = book_keeping_vars["policy_average_reward"]
+            self.ppo_learner.cumulative_model_updates = book_keeping_vars["cumulative_model_updates"]
+            self.return_stats.from_json(book_keeping_vars["reward_running_stats"])
+            if self.agent.standardize_obs and "obs_running_stats" in book_keeping_vars.keys():
+                self.agent.obs_stats = WelfordRunningStat(1, device=self.device)
+                self.agent.obs_stats.from_json(book_keeping_vars["obs_running_stats"])
+            if self.standardize_returns and "reward_running_stats" in book_keeping_vars.keys():
+                self.return_stats.from_json(book_keeping_vars["reward_running_stats"])
+            self.epoch = book_keeping_vars["epoch"]
+
+            if new_policy_lr is not None or new_critic_lr is not None:
+                self.update_learning_rate(new_policy_lr, new_critic_lr)
+
+            if "wandb_run_id" in book_keeping_vars and load_wandb:
+                import wandb
+                self.wandb_run = wandb.init(
+                    settings=wandb.Settings(start_method="spawn"),
+                    entity=book_keeping_vars["wandb_entity"],
+                    project=book_keeping_vars["wandb_project"],
+                    group=book_keeping_vars["wandb_group"],
+                    id=book_keeping_vars["wandb_run_id"],
+                    config=book_keeping_vars["wandb_config"],
+                    resume="allow",
+                    reinit=True,
+                )
+                wandb_loaded = True
+
+        print("Checkpoint loaded!")
+        return wandb_loaded
+
+    def cleanup(self):
+        if self.wandb_run is not None:
+            self.wandb_run.finish()
+        agent = getattr(self, "agent", None)
+        if agent is not None and hasattr(agent, "cleanup"):
+            agent.cleanup()
+        self.experience_buffer.clear()

@@ -3,6 +3,8 @@
 torch is used for device memory and streams only; every function enqueues hand-written kernels from
 librlppo_b200.so on the current torch CUDA stream and returns without synchronising.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -58,7 +60,7 @@ def gae(rew, done, trunc, values, gamma, lmbda, ret_std=None, out=None, ret_head
     n_head = 0 if ret_head64 is None else min(ret_head64.numel(), n)
     call("rlppo_gae_f32", ptr(rew), ptr(done), ptr(trunc), int(trunc.dtype == torch.float64), ptr(values), n,
          float(gamma), float(lmbda), ptr(ret_std), ptr(adv), ptr(vt), ptr(ret), ptr(ret_head64), n_head,
-         ptr(carry_in), ptr(ws), ws.numel(), stream_ptr())
+         ptr(carry_in), ptr(ws), ws.numel(), stream_ptr(), work=("byte", 28 * n))
     return vt, adv, ret
 
 
@@ -87,7 +89,8 @@ def ring_append(ring, phys_first, src, n_rows, ring_bf16=None):
     src_ld = 1 if src.dim() == 1 else src.stride(0)
     assert src.dtype in (torch.float32, torch.float64)
     call("rlppo_ring_append", ptr(ring), ring_ld, ptr(ring_bf16), 0 if ring_bf16 is None else ring_bf16.stride(0),
-         cap, int(phys_first), ptr(src), int(src.dtype == torch.float64), src_ld, int(n_rows), width, stream_ptr())
+         cap, int(phys_first), ptr(src), int(src.dtype == torch.float64), src_ld, int(n_rows), width, stream_ptr(),
+         work=("byte", int(n_rows) * width * (src.element_size() + 4 + (2 if ring_bf16 is not None else 0))))
 
 
 def gather_batch(buf, idx, out_actions=None, out_logp=None, out_values=None, out_adv=None, out_states=None,
@@ -100,44 +103,51 @@ def gather_batch(buf, idx, out_actions=None, out_logp=None, out_values=None, out
          ptr(buf.states), buf.states.stride(0) if buf.states is not None and buf.states.dim() == 2 else 1, ptr(sb),
          0 if sb is None else sb.stride(0), int(buf.obs_dim), int(buf.capacity), int(buf.start), ptr(idx), B,
          ptr(out_actions), ptr(out_logp), ptr(out_values), ptr(out_adv), ptr(out_states), ptr(out_states_bf16),
-         stream_ptr())
+         stream_ptr(),
+         work=("byte", 8 * B + 2 * B * (4 * sum(o is not None for o in (out_actions, out_logp, out_values, out_adv))
+                                        + (4 * buf.obs_dim if out_states is not None else 0)
+                                        + (2 * sb.stride(0) if out_states_bf16 is not None else 0))))
 
 
 # ---- operand preparation ---------------------------------------------------------------------------------
-def rows_to_bf16(src, dst, mean=None, std=None, clip=5.0):
+def rows_to_bf16(src, dst, mean=None, std=None, clip=5.0, dst_f32=None):
     n_rows, width = src.shape
     assert dst.dtype == BF16 and dst.shape[0] >= n_rows
     if mean is None:
-        call("rlppo_rows_to_bf16", ptr(src), src.stride(0), n_rows, width, ptr(dst), dst.stride(0), stream_ptr())
+        call("rlppo_rows_to_bf16", ptr(src), src.stride(0), n_rows, width, ptr(dst), dst.stride(0), stream_ptr(),
+             work=("byte", n_rows * (4 * width + 2 * dst.stride(0))))
     else:
         call("rlppo_rows_standardize_to_bf16", ptr(src), src.stride(0), n_rows, width, ptr(mean), ptr(std),
-             float(clip), ptr(dst), dst.stride(0), stream_ptr())
+             float(clip), ptr(dst), dst.stride(0), ptr(dst_f32), 0 if dst_f32 is None else dst_f32.stride(0),
+             stream_ptr(), work=("byte", n_rows * (4 * width + 2 * dst.stride(0))))
 
 
 def weight_to_bf16(w, wq, wt=None):
     out_f, in_f = w.shape
     assert w.is_contiguous() and wq.dtype == BF16
     call("rlppo_weight_to_bf16", ptr(w), out_f, in_f, ptr(wq), wq.stride(0), wq.shape[0], ptr(wt),
-         0 if wt is None else wt.stride(0), 0 if wt is None else wt.shape[0], stream_ptr())
+         0 if wt is None else wt.stride(0), 0 if wt is None else wt.shape[0], stream_ptr(),
+         work=("byte", out_f * in_f * (4 + 2 + (2 if wt is not None else 0))))
 
 
 # ---- tensor-core layers -------------------------------------------------------------------------------------
 def linear_fwd(x, wq, bias, y, N, K, relu, M=None):
     M = x.shape[0] if M is None else M
     call("rlppo_linear_fwd", ptr(x), x.stride(0), ptr(wq), wq.stride(0), ptr(bias), ptr(y), y.stride(0), int(M),
-         int(N), int(K), int(bool(relu)), stream_ptr())
+         int(N), int(K), int(bool(relu)), stream_ptr(), work=("flop", 2.0 * M * N * K))
 
 
 def linear_dgrad(dy, wt, hprev, dx, N, K, M=None):
     M = dy.shape[0] if M is None else M
     call("rlppo_linear_dgrad", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
-         0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), int(M), int(N), int(K), stream_ptr())
+         0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), int(M), int(N), int(K), stream_ptr(),
+         work=("flop", 2.0 * M * N * K))
 
 
 def linear_wgrad(dy, x, dw, db, N, K, M=None):
     M = dy.shape[0] if M is None else M
     call("rlppo_linear_wgrad", ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(dw), dw.stride(0), ptr(db), int(M),
-         int(N), int(K), stream_ptr())
+         int(N), int(K), stream_ptr(), work=("flop", 2.0 * M * N * K))
 
 
 def policy_head_sample(h, wq, bias, n_actions, K, M=None, u=None, seed=0, offset=0, deterministic=False,
@@ -145,7 +155,8 @@ def policy_head_sample(h, wq, bias, n_actions, K, M=None, u=None, seed=0, offset
     M = h.shape[0] if M is None else M
     call("rlppo_policy_head_sample", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M), int(n_actions),
          int(K), ptr(u), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), int(bool(deterministic)),
-         ptr(actions_out), ptr(actions_i64_out), ptr(logp_out), ptr(probs_out), stream_ptr())
+         ptr(actions_out), ptr(actions_i64_out), ptr(logp_out), ptr(probs_out), stream_ptr(),
+         work=("flop", 2.0 * M * n_actions * K))
 
 
 def policy_head_train(h, wq, bias, n_actions, K, actions, old_logp, adv, inv_batch, clip, ent_coef, dz, metrics,
@@ -153,14 +164,47 @@ def policy_head_train(h, wq, bias, n_actions, K, actions, old_logp, adv, inv_bat
     M = h.shape[0] if M is None else M
     call("rlppo_policy_head_train", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M), int(n_actions),
          int(K), ptr(actions), ptr(old_logp), ptr(adv), float(inv_batch), float(clip), float(ent_coef), ptr(dz),
-         dz.stride(0), ptr(logp_out), ptr(metrics), stream_ptr())
+         dz.stride(0), ptr(logp_out), ptr(metrics), stream_ptr(), work=("flop", 2.0 * M * n_actions * K))
 
 
 def value_head(h, w, bias, K, values_out=None, targets=None, inv_batch=0.0, dh=None, dw=None, db=None, metrics=None,
                M=None):
     M = h.shape[0] if M is None else M
     call("rlppo_value_head", ptr(h), h.stride(0), ptr(w), ptr(bias), int(M), int(K), ptr(values_out), ptr(targets),
-         float(inv_batch), ptr(dh), 0 if dh is None else dh.stride(0), ptr(dw), ptr(db), ptr(metrics), stream_ptr())
+         float(inv_batch), ptr(dh), 0 if dh is None else dh.stride(0), ptr(dw), ptr(db), ptr(metrics), stream_ptr(),
+         work=("byte", M * K * 2 * (2 if targets is not None else 1) + 4 * M * (2 if targets is not None else 1)))
+
+
+# ---- whole-network fused kernels --------------------------------------------------------------------------------
+def _net_flops(net, M, n_out, train):
+    dims = [net.in_dim] + [net.hidden[i] for i in range(net.n_hidden)]
+    f = sum(2.0 * M * dims[i] * dims[i + 1] for i in range(len(dims) - 1)) + 2.0 * M * dims[-1] * n_out
+    if train:   # + backward data path (all layers but the first)
+        f += sum(2.0 * M * dims[i] * dims[i + 1] for i in range(1, len(dims) - 1)) + 2.0 * M * dims[-1] * n_out
+    return f
+
+
+def policy_train_fused(net, x, M, n_actions, actions, old_logp, adv, inv_batch, clip, ent_coef, metrics, logp_out=None):
+    call("rlppo_policy_train_fused", ctypes.byref(net), ptr(x), int(M), int(n_actions), ptr(actions), ptr(old_logp),
+         ptr(adv), float(inv_batch), float(clip), float(ent_coef), ptr(logp_out), ptr(metrics), stream_ptr(),
+         work=("flop", _net_flops(net, M, n_actions, True)))
+
+
+def policy_infer_fused(net, x, M, n_actions, u=None, seed=0, offset=0, deterministic=False, actions_out=None,
+                       actions_i64_out=None, logp_out=None):
+    call("rlppo_policy_infer_fused", ctypes.byref(net), ptr(x), int(M), int(n_actions), ptr(u), int(seed) & (2 ** 64 - 1),
+         int(offset) & (2 ** 64 - 1), int(bool(deterministic)), ptr(actions_out), ptr(actions_i64_out), ptr(logp_out),
+         stream_ptr(), work=("flop", _net_flops(net, M, n_actions, False)))
+
+
+def value_train_fused(net, x, M, w_head, targets, inv_batch, gw_head, metrics, values_out=None):
+    call("rlppo_value_train_fused", ctypes.byref(net), ptr(x), int(M), ptr(w_head), ptr(targets), float(inv_batch),
+         ptr(gw_head), ptr(values_out), ptr(metrics), stream_ptr(), work=("flop", _net_flops(net, M, 1, True)))
+
+
+def value_infer_fused(net, x, M, w_head, values_out):
+    call("rlppo_value_infer_fused", ctypes.byref(net), ptr(x), int(M), ptr(w_head), ptr(values_out), stream_ptr(),
+         work=("flop", _net_flops(net, M, 1, False)))
 
 
 # ---- optimiser ------------------------------------------------------------------------------------------------
@@ -170,15 +214,18 @@ def _seg(seg_off):
 
 def grad_sqnorm(grads, seg_off, sqnorm):
     so = _seg(seg_off)
-    call("rlppo_grad_sqnorm", ptr(grads), so.ctypes.data, len(so) - 1, ptr(sqnorm), stream_ptr())
+    call("rlppo_grad_sqnorm", ptr(grads), so.ctypes.data, len(so) - 1, ptr(sqnorm), stream_ptr(),
+         work=("byte", 4 * int(so[-1])))
 
 
 def clip_adam(params, grads, m, v, seg_off, sqnorm, lr, step_count, max_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-8):
     so = _seg(seg_off)
     call("rlppo_clip_adam", ptr(params), ptr(grads), ptr(m), ptr(v), so.ctypes.data, len(so) - 1, ptr(sqnorm), ptr(lr),
-         ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps), stream_ptr())
+         ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps), stream_ptr(),
+         work=("byte", 28 * int(so[-1])))
 
 
 def sqdiff(a, b, seg_off, out):
     so = _seg(seg_off)
-    call("rlppo_sqdiff", ptr(a), ptr(b), so.ctypes.data, len(so) - 1, ptr(out), stream_ptr())
+    call("rlppo_sqdiff", ptr(a), ptr(b), so.ctypes.data, len(so) - 1, ptr(out), stream_ptr(),
+         work=("byte", 8 * int(so[-1])))

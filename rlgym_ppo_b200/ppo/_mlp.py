@@ -1,0 +1,181 @@
+"""Linear/ReLU stacks on the tcgen05 kernels: parameter arenas, bf16 operand copies, activation workspaces.
+
+Shared by DiscreteFF (discrete_policy.py) and ValueEstimator (value_estimator.py).  The nn.Module keeps the
+reference's `.model` nn.Sequential so state-dict keys and shapes are the reference's (`model.{2i}.weight` [out,in],
+`model.{2i}.bias`), but its parameters are VIEWS into one flat fp32 arena and their `.grad`s views into a flat
+gradient arena: the fused clip+Adam kernel and the NCCL allreduce see one contiguous buffer per learner.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+
+BF16 = torch.bfloat16
+
+
+def build_sequential(input_shape, layer_sizes, out_features, softmax):
+    """The reference's layer list (discrete_policy.py:22-31, value_estimator.py:19-28), created on the CPU with
+    torch's default initialisation so a given torch.manual_seed yields the reference's initial weights."""
+    assert len(layer_sizes) != 0, "AT LEAST ONE LAYER MUST BE SPECIFIED TO BUILD THE NEURAL NETWORK!"
+    layers = [nn.Linear(int(input_shape), int(layer_sizes[0])), nn.ReLU()]
+    prev = int(layer_sizes[0])
+    for size in layer_sizes[1:]:
+        layers.append(nn.Linear(prev, int(size)))
+        layers.append(nn.ReLU())
+        prev = int(size)
+    layers.append(nn.Linear(prev, int(out_features)))
+    if softmax:
+        layers.append(nn.Softmax(dim=-1))
+    return nn.Sequential(*layers)
+
+
+class Stack:
+    """Kernel-side view of one network: dims, arena views, bf16 operands, workspaces."""
+
+    def __init__(self, model, device):
+        _lib.require_device()
+        self.device = torch.device(device)
+        self.linears = [m for m in model if isinstance(m, nn.Linear)]
+        self.in_dim = self.linears[0].in_features
+        self.hidden = [l.out_features for l in self.linears[:-1]]
+        self.out_dim = self.linears[-1].out_features
+        for h in self.hidden:
+            if h % 8 != 0:
+                raise ValueError(f"hidden layer width {h} is not a multiple of 8 (16-byte rows are required by the "
+                                 "TMA-staged tensor-core kernels)")
+        self.in_pad = ops.pad8(self.in_dim)
+        self.out_pad = ops.pad8(self.out_dim)
+        self.n_params = sum(p.numel() for l in self.linears for p in (l.weight, l.bias))
+        self.params = None
+        self.grads = None
+        self._seen_version = -1
+        self._ws_rows = 0
+        self._ws = None
+        # bf16 operands: wq[i] = W_i [out_pad8, in_pad8] (forward B operand, K-major);
+        #                wt[i] = W_i^T [in_pad8, out_pad8] (dgrad B operand), not needed for the first layer
+        self.wq, self.wt = [], []
+        for i, l in enumerate(self.linears):
+            o8, i8 = ops.pad8(l.out_features), ops.pad8(l.in_features)
+            self.wq.append(torch.zeros((o8, i8), dtype=BF16, device=self.device))
+            self.wt.append(torch.zeros((i8, o8), dtype=BF16, device=self.device) if i > 0 else None)
+
+    # ---- arenas ---------------------------------------------------------------------------------------
+    def bind(self, params_flat, grads_flat):
+        """Move the parameters into `params_flat` (exactly n_params f32 on the device) and re-point every
+        nn.Parameter (and its .grad) at its slice.  Order = nn.Module.parameters() order = parameters_to_vector
+        order (ppo_learner.py:111-116)."""
+        assert params_flat.numel() == self.n_params and grads_flat.numel() == self.n_params
+        off = 0
+        self.w, self.b, self.gw, self.gb = [], [], [], []
+        with torch.no_grad():
+            for l in self.linears:
+                for p, plist, glist in ((l.weight, self.w, self.gw), (l.bias, self.b, self.gb)):
+                    n = p.numel()
+                    pv = params_flat[off:off + n].view(p.shape)
+                    gv = grads_flat[off:off + n].view(p.shape)
+                    pv.copy_(p.data)
+                    p.data = pv
+                    p.grad = gv
+                    plist.append(pv)
+                    glist.append(gv)
+                    off += n
+        self.params, self.grads = params_flat, grads_flat
+        self._seen_version = -1
+        self.__dict__.pop("_net_cache", None)
+
+    def operands_stale(self):
+        return self.params._version != self._seen_version
+
+    def refresh_operands(self, force=False):
+        """fp32 master weights -> bf16 GEMM operands.  Called after every optimiser step (our kernels do not bump
+        torch's version counter) and lazily whenever torch-side code (load_state_dict, user edits) touched the arena."""
+        if not force and not self.operands_stale():
+            return
+        for i in range(len(self.linears)):
+            ops.weight_to_bf16(self.w[i], self.wq[i], self.wt[i])
+        self._seen_version = self.params._version
+
+    # ---- whole-network fused kernels (mlp_fused.cu) ---------------------------------------------------------------
+    @property
+    def fused_ok(self):
+        """Shapes the single-kernel path supports; anything else runs layer by layer (mlp_tcgen05.cu)."""
+        return (1 <= len(self.hidden) <= 4 and all(h % 64 == 0 and 64 <= h <= 256 for h in self.hidden)
+                and self.in_dim <= 256 and self.out_dim <= 128 and not getattr(self, "force_layerwise", False))
+
+    def fused_net(self, x_ld, ws=None, policy_head=False):
+        """struct rlppo_fused_net for this stack; `ws` (a workspace) supplies the training outputs."""
+        key = (x_ld, id(ws), policy_head)
+        cache = self.__dict__.setdefault("_net_cache", {})
+        net = cache.get(key)
+        if net is not None:
+            return net
+        net = _lib.FusedNet()
+        L = len(self.hidden)
+        net.n_hidden, net.in_dim, net.in_ld = L, self.in_dim, x_ld
+        for i, h in enumerate(self.hidden):
+            net.hidden[i] = h
+        n_lin = L + 1 if policy_head else L
+        for i in range(n_lin):
+            net.wq[i], net.wq_ld[i] = self.wq[i].data_ptr(), self.wq[i].stride(0)
+            if i > 0:
+                net.wt[i], net.wt_ld[i] = self.wt[i].data_ptr(), self.wt[i].stride(0)
+        for i in range(L + 1):
+            net.bias[i], net.gbias[i] = self.b[i].data_ptr(), self.gb[i].data_ptr()
+        if ws is not None:
+            for i in range(L):
+                net.h[i], net.h_ld[i] = ws["h"][i].data_ptr(), ws["h"][i].stride(0)
+                net.dh[i], net.dh_ld[i] = ws["dh"][i].data_ptr(), ws["dh"][i].stride(0)
+            net.dz, net.dz_ld = ws["dz"].data_ptr(), ws["dz"].stride(0)
+        cache[key] = net
+        return net
+
+    def fused_wgrads(self, x, M, ws, head_dy=None):
+        """Weight gradients after a fused training pass: dW_l += dH_l^T X_{l-1} (and the policy head's)."""
+        L = len(self.hidden)
+        if head_dy is not None:
+            ops.linear_wgrad(head_dy, ws["h"][L - 1], self.gw[L], None, self.out_dim, self.hidden[L - 1], M=M)
+        for i in range(L - 1, -1, -1):
+            inp = ws["h"][i - 1] if i > 0 else x
+            K = self.hidden[i - 1] if i > 0 else self.in_dim
+            ops.linear_wgrad(ws["dh"][i], inp, self.gw[i], None, self.hidden[i], K, M=M)
+
+    # ---- workspaces -------------------------------------------------------------------------------------
+    def workspace(self, rows):
+        """Activation buffers for `rows` rows (grow-only): h[i] bf16 [rows, hidden_i]; two gradient ping-pong
+        buffers as wide as the widest hidden layer; dz [rows, out_pad]."""
+        if rows > self._ws_rows:
+            cap = max(rows, 1)
+            wmax = max(self.hidden)
+            self._ws = {
+                "h": [torch.empty((cap, h), dtype=BF16, device=self.device) for h in self.hidden],
+                "d": [torch.empty((cap, wmax), dtype=BF16, device=self.device) for _ in range(2)],
+                "dh": [torch.empty((cap, h), dtype=BF16, device=self.device) for h in self.hidden],
+                "dz": torch.zeros((cap, self.out_pad), dtype=BF16, device=self.device),
+                "x": torch.zeros((cap, self.in_pad), dtype=BF16, device=self.device),
+            }
+            self._ws_rows = cap
+            self.__dict__.pop("_net_cache", None)
+        return self._ws
+
+    # ---- forward / backward of the hidden layers ---------------------------------------------------------------
+    def forward_hidden(self, x, M, ws):
+        """x bf16 [>=M, in_pad] -> ws['h'][-1] (last hidden activation, post-ReLU)."""
+        prev, K = x, self.in_dim
+        for i, h in enumerate(self.hidden):
+            ops.linear_fwd(prev, self.wq[i], self.b[i], ws["h"][i], h, K, True, M=M)
+            prev, K = ws["h"][i], h
+        return prev
+
+    def backward_hidden(self, x, M, ws, d_last):
+        """d_last = dL/dH_last (bf16 [>=M, hidden[-1]], already ReLU-masked).  Accumulates dW/db of every hidden
+        layer into the gradient arena (wgrad kernels add) and propagates through the stack."""
+        d = d_last
+        for i in range(len(self.hidden) - 1, -1, -1):
+            inp = ws["h"][i - 1] if i > 0 else x
+            K = self.hidden[i - 1] if i > 0 else self.in_dim
+            ops.linear_wgrad(d, inp, self.gw[i], self.gb[i], self.hidden[i], K, M=M)
+            if i > 0:
+                nxt = ws["d"][0] if d.data_ptr() != ws["d"][0].data_ptr() else ws["d"][1]
+                dx = nxt[:, :K] if nxt.shape[1] != K else nxt
+                ops.linear_dgrad(d, self.wt[i], inp, dx, self.hidden[i], K, M=M)
+                d = dx

@@ -1,0 +1,174 @@
+"""ExperienceBuffer, device resident (replaces rlgym_ppo/ppo/experience_buffer.py).
+
+The reference keeps nine CPU tensors and rebuilds every one of them with torch.cat on each submit
+(experience_buffer.py:17-37, 54-80), then fancy-indexes five of them per batch on the CPU and ships every
+minibatch to the GPU (:82-102, ppo_learner.py:139-143).  Here the nine fields are rings preallocated in HBM:
+logical row i (oldest = 0, the order `_cat` keeps) lives at physical row (start + i) % max_size, submit is one
+append kernel per field, and a batch is one permutation-gather kernel.  The permutation itself is NumPy's
+legacy RandomState stream (bit-exact by construction: produced on the host by the same MT19937/Fisher-Yates
+algorithm, rlppo_host_permutation) so indices and gathered bytes equal the reference's.
+
+A bf16 copy of `states`, zero padded to a multiple of 8 columns, rides along: it is the TMA-legal A operand of
+the first-layer tensor-core GEMMs (row stride 16-byte aligned), so the update never re-converts observations.
+"""
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from .._staging import Stager
+
+FIELDS = ("states", "actions", "log_probs", "rewards", "next_states", "dones", "truncated", "values", "advantages")
+_WIDE = ("states", "next_states")
+
+
+class ExperienceBuffer(object):
+    @staticmethod
+    def _cat(t1, t2, size):
+        """experience_buffer.py:17-37 -- kept for API compatibility (torch tensors on any device)."""
+        if len(t2) > size:
+            t = t2[-size:].clone()
+        elif len(t2) == size:
+            t = t2
+        elif len(t1) + len(t2) > size:
+            t = torch.cat((t1[len(t2) - size:], t2), 0)
+        else:
+            t = torch.cat((t1, t2), 0)
+        return t
+
+    def __init__(self, max_size, seed, device):
+        # The reference's Learner passes device="cpu" here (learner.py:124-126).  The buffer IS the device-side
+        # store in this implementation, so "cpu"/"auto" mean "the current CUDA device".
+        if device in (None, "cpu", "auto", "gpu"):
+            device = "cuda:%d" % torch.cuda.current_device() if torch.cuda.is_available() else "cuda:0"
+        self.device = torch.device(device)
+        self.seed = seed
+        self.max_size = int(max_size)
+        self.rng = np.random.RandomState(seed)
+        self.capacity = self.max_size
+        self.start = 0          # physical row of logical row 0
+        self.size = 0           # number of valid rows
+        self.obs_dim = None
+        self.obs_pad = None
+        self._rings = None
+        self.states_bf16 = None
+        self._stager = None
+        self._idx_dev = None
+
+    # ---- storage -------------------------------------------------------------------------------------
+    def _allocate(self, obs_dim):
+        _lib.require_device()
+        self.obs_dim = int(obs_dim)
+        self.obs_pad = ops.pad8(self.obs_dim)
+        cap = self.capacity
+        self._rings = {}
+        for f in FIELDS:
+            shape = (cap, self.obs_dim) if f in _WIDE else (cap,)
+            self._rings[f] = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        self.states_bf16 = torch.zeros((cap, self.obs_pad), dtype=torch.bfloat16, device=self.device)
+        self._stager = Stager(self.device)
+
+    def ring(self, field):
+        """Physical ring tensor of a field (row i of it is NOT logical row i; see `start`)."""
+        return self._rings[field]
+
+    def _logical(self, field):
+        if self._rings is None:
+            return torch.empty(0, dtype=torch.float32, device=self.device)
+        r = self._rings[field]
+        end = self.start + self.size
+        if end <= self.capacity:
+            return r[self.start:end]
+        return torch.cat((r[self.start:], r[:end - self.capacity]), 0)
+
+    def __len__(self):
+        return self.size
+
+    # ---- submit (experience_buffer.py:54-80) ------------------------------------------------------------
+    def submit_experience(self, states, actions, log_probs, rewards, next_states, dones, truncated, values,
+                          advantages):
+        new = dict(zip(FIELDS, (states, actions, log_probs, rewards, next_states, dones, truncated, values,
+                                advantages)))
+        if self._rings is None:
+            st = states
+            obs_dim = st.shape[1] if hasattr(st, "shape") and len(st.shape) == 2 else np.asarray(st).shape[1]
+            self._allocate(obs_dim)
+        dev = {f: self._stager.to_device(new[f], "sub." + f) for f in FIELDS}
+        self.submit_device(dev)
+
+    def submit_device(self, dev):
+        """Append rows that already live in HBM: dict field -> contiguous f32/f64 device tensor."""
+        n = int(dev["rewards"].shape[0])
+        for f in FIELDS:
+            assert int(dev[f].shape[0]) == n, f"field {f} has {dev[f].shape[0]} rows, expected {n}"
+        if n == 0:
+            return
+        cap = self.capacity
+        skip = max(0, n - cap)          # `_cat`: when the new block alone exceeds max_size keep its tail
+        rows = n - skip
+        if rows == cap:
+            self.start, self.size = 0, 0
+        first = (self.start + self.size) % cap
+        for f in FIELDS:
+            src = dev[f][skip:] if skip else dev[f]
+            ops.ring_append(self._rings[f], first, src, rows,
+                            ring_bf16=self.states_bf16 if f == "states" else None)
+        over = max(0, self.size + rows - cap)
+        self.start = (self.start + over) % cap
+        self.size = min(cap, self.size + rows)
+
+    # ---- sampling (experience_buffer.py:82-102) ------------------------------------------------------------
+    def _index_tensor(self, indices):
+        if isinstance(indices, torch.Tensor):
+            return indices.to(device=self.device, dtype=torch.int64).contiguous()
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        return torch.from_numpy(idx).to(self.device, non_blocking=False)
+
+    def _get_samples(self, indices):
+        idx = self._index_tensor(indices)
+        B = idx.numel()
+        out = [torch.empty(B, dtype=torch.float32, device=self.device) for _ in range(4)]
+        st = torch.empty((B, self.obs_dim), dtype=torch.float32, device=self.device)
+        self.gather(idx, out_actions=out[0], out_logp=out[1], out_values=out[2], out_adv=out[3], out_states=st)
+        return out[0], out[1], st, out[2], out[3]
+
+    def gather(self, idx, **outs):
+        """Device permutation gather of LOGICAL indices into caller-provided outputs (see ops.gather_batch)."""
+        view = _RingView(self)
+        ops.gather_batch(view, idx, **outs)
+
+    def next_permutation(self):
+        """One `self.rng.permutation(total)` (experience_buffer.py:98), NumPy's legacy stream bit for bit."""
+        return _lib.host_permutation(self.rng, self.size)
+
+    def get_all_batches_shuffled(self, batch_size):
+        total_samples = self.size
+        indices = self.next_permutation()
+        idx_dev = torch.from_numpy(indices).to(self.device) if total_samples else None
+        start_idx = 0
+        while start_idx + batch_size <= total_samples:
+            yield self._get_samples(idx_dev[start_idx:start_idx + batch_size])
+            start_idx += batch_size
+
+    def clear(self):
+        self.__init__(self.max_size, self.seed, self.device)
+
+
+class _RingView:
+    """What ops.gather_batch reads: physical rings + (capacity, start)."""
+
+    def __init__(self, buf):
+        r = buf._rings
+        self.actions, self.log_probs = r["actions"], r["log_probs"]
+        self.values, self.advantages = r["values"], r["advantages"]
+        self.states, self.states_bf16 = r["states"], buf.states_bf16
+        self.obs_dim, self.capacity, self.start = buf.obs_dim, buf.capacity, buf.start
+
+
+def _make_field_property(name):
+    def get(self):
+        return self._logical(name)
+    return property(get, doc=f"`{name}` in logical (oldest -> newest) order, as the reference's tensor attribute")
+
+
+for _f in FIELDS:
+    setattr(ExperienceBuffer, _f, _make_field_property(_f))

@@ -1,0 +1,284 @@
+"""PPOLearner on the B200 kernels (replaces rlgym_ppo/ppo/ppo_learner.py).
+
+Same constructor, attributes, `learn(exp) -> report`, `save_to` / `load_from` (same four .pt files) as the
+reference.  What changes is how an optimiser step is executed (ppo_learner.py:119-195):
+
+  reference                                           here
+  ---------                                           ----
+  CPU fancy-index + 5 H2D copies per minibatch        one device permutation-gather kernel (bf16 obs rows)
+  nn.Sequential forward, autograd backward (fp32)     bf16 tcgen05 GEMMs, fp32 TMEM accumulators; the softmax /
+                                                      clamp / log-prob / entropy / ratio / clip / KL / clip-fraction
+                                                      / MSE math and its analytic backward fused
+                                                      into the head kernels
+  4 x .item() per minibatch, 2 x all params D2H       8 metric sums + 2 update norms accumulated on the device,
+                                                      ONE readback per learn()
+  clip_grad_norm_ x2 + Adam.step x2                   one norm kernel + one fused clip+Adam kernel over the flat
+                                                      [policy | value] arena (separate norms, lrs, step counters)
+  single device                                       data parallel: rank r takes slice r of every batch (exactly the
+                                                      reference's minibatch slices), flat-arena NCCL allreduce,
+                                                      identical optimiser step on every rank
+
+Gradient accumulation over minibatches is a memory knob in the reference (sum of (mb/B)-scaled minibatch
+gradients == full-batch gradient).  Here a rank's share of the batch is processed in chunks of at most
+`max_chunk_rows` rows (activations for 131072 rows of the 2048-wide nets are ~3 GB of 180 GB), with the same
+1/batch_size weighting, so `mini_batch_size` keeps its meaning for the result and stops costing launches.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from .discrete_policy import DiscreteFF
+from .fused_adam import FusedAdam
+from .value_estimator import ValueEstimator
+
+
+class PPOLearner(object):
+    def __init__(
+        self,
+        obs_space_size,
+        act_space_size,
+        policy_type,
+        policy_layer_sizes,
+        critic_layer_sizes,
+        continuous_var_range,
+        batch_size,
+        n_epochs,
+        policy_lr,
+        critic_lr,
+        clip_range,
+        ent_coef,
+        mini_batch_size,
+        device,
+        max_chunk_rows=131072,
+        process_group=None,
+    ):
+        _lib.require_device()
+        if device in (None, "auto", "gpu"):
+            device = "cuda:%d" % torch.cuda.current_device()
+        if "cuda" not in str(device):
+            raise _lib.RlppoError(f"PPOLearner device must be a CUDA device (got {device!r}); there is no CPU path")
+        self.device = device
+        dev = torch.device(device)
+
+        assert (
+            batch_size % mini_batch_size == 0
+        ), "MINIBATCH SIZE MUST BE AN INTEGER MULTIPLE OF BATCH SIZE"
+        if policy_type != 0:
+            raise NotImplementedError(
+                "only the discrete head (policy_type 0, DiscreteFF) is implemented on the B200 path; "
+                "MultiDiscreteFF (1) and ContinuousPolicy (2) are out of scope (SURVEY.md section 8f)")
+
+        obs_space_size = int(obs_space_size)
+        self.policy = DiscreteFF(obs_space_size, act_space_size, policy_layer_sizes, device)
+        self.value_net = ValueEstimator(obs_space_size, critic_layer_sizes, device)
+        self.mini_batch_size = mini_batch_size
+
+        # ---- one flat arena [policy | value] for params, grads and both Adam moments -------------------------
+        ps, vs = self.policy._stack, self.value_net._stack
+        n_p, n_v = ps.n_params, vs.n_params
+        self._seg = np.asarray([0, n_p, n_p + n_v], dtype=np.int64)
+        self._params = torch.zeros(n_p + n_v, dtype=torch.float32, device=dev)
+        self._grads = torch.zeros_like(self._params)
+        self._m = torch.zeros_like(self._params)
+        self._v = torch.zeros_like(self._params)
+        self._before = torch.zeros_like(self._params)
+        ps.bind(self._params[:n_p], self._grads[:n_p])
+        vs.bind(self._params[n_p:], self._grads[n_p:])
+        self._steps = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._lr_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._lr_host = None
+        self._sqnorm = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._tail = torch.zeros(12, dtype=torch.float32, device=dev)   # metrics[0:8] | update sq-norms [8:10]
+        self._tail_host = torch.zeros(12, dtype=torch.float32).pin_memory()
+
+        self.policy_optimizer = FusedAdam(ps, policy_lr, self._m[:n_p], self._v[:n_p], self._steps[0:1])
+        self.value_optimizer = FusedAdam(vs, critic_lr, self._m[n_p:], self._v[n_p:], self._steps[1:2])
+
+        policy_params_count, critic_params_count = n_p, n_v
+        total_parameters = policy_params_count + critic_params_count
+        print("Trainable Parameters:")
+        print(f"{'Component':<10} {'Count':<10}")
+        print("-" * 20)
+        print(f"{'Policy':<10} {policy_params_count:<10}")
+        print(f"{'Critic':<10} {critic_params_count:<10}")
+        print("-" * 20)
+        print(f"{'Total':<10} {total_parameters:<10}")
+        print(f"Current Policy Learning Rate: {policy_lr}")
+        print(f"Current Critic Learning Rate: {critic_lr}")
+
+        self.n_epochs = n_epochs
+        self.batch_size = batch_size
+        self.clip_range = clip_range
+        self.ent_coef = ent_coef
+        self.cumulative_model_updates = 0
+        self.max_chunk_rows = int(max_chunk_rows)
+
+        # ---- data parallelism ---------------------------------------------------------------------------------
+        self._pg = process_group
+        self.world_size, self.rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world_size = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        assert batch_size % self.world_size == 0, "batch_size must be a multiple of the number of ranks"
+        self._mb = None
+        self.launches = 0   # kernels enqueued by the last learn() (bench.py reports it)
+
+    # ---- workspaces ----------------------------------------------------------------------------------------
+    def _minibatch_buffers(self, rows):
+        if self._mb is None or self._mb["rows"] < rows:
+            dev = self._params.device
+            f = lambda: torch.empty(rows, dtype=torch.float32, device=dev)  # noqa: E731
+            self._mb = {"rows": rows, "actions": f(), "old_logp": f(), "targets": f(), "adv": f(),
+                        "x": torch.zeros((rows, self.policy._stack.in_pad), dtype=torch.bfloat16, device=dev)}
+        return self._mb
+
+    def _sync_lr(self):
+        lr = (float(self.policy_optimizer.param_groups[0]["lr"]), float(self.value_optimizer.param_groups[0]["lr"]))
+        if lr != self._lr_host:
+            self._lr_dev.copy_(torch.tensor(lr, dtype=torch.float32))
+            self._lr_host = lr
+
+    # ---- one chunk of one batch: gather -> fwd -> fused heads -> bwd (grads accumulate) -------------------------
+    def _train_chunk(self, exp, idx, M):
+        mb = self._minibatch_buffers(M)
+        exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
+                   out_adv=mb["adv"], out_states_bf16=mb["x"])
+        x = mb["x"]
+        inv_b = 1.0 / float(self.batch_size)       # (1/mb) * (mb/B), ppo_learner.py:172-177
+        metrics = self._tail[0:8]
+        n = 1
+        for net, is_policy in ((self.policy, True), (self.value_net, False)):
+            st = net._stack
+            ws = st.workspace(M)
+            if st.fused_ok:
+                # one persistent kernel: forward, fused head, backward data path, bias gradients (mlp_fused.cu)
+                if is_policy:
+                    fnet = st.fused_net(x.stride(0), ws, policy_head=True)
+                    ops.policy_train_fused(fnet, x, M, net.n_actions, mb["actions"], mb["old_logp"], mb["adv"], inv_b,
+                                           float(self.clip_range), float(self.ent_coef), metrics)
+                    st.fused_wgrads(x, M, ws, head_dy=ws["dz"])
+                else:
+                    fnet = st.fused_net(x.stride(0), ws)
+                    ops.value_train_fused(fnet, x, M, st.w[-1], mb["targets"], inv_b, st.gw[-1], metrics)
+                    st.fused_wgrads(x, M, ws)
+                n += 1 + len(st.hidden) + (1 if is_policy else 0)
+                continue
+            h = st.forward_hidden(x, M, ws)
+            hl = st.hidden[-1]
+            d0 = ws["d"][0]
+            dh = d0[:, :hl] if d0.shape[1] != hl else d0
+            if is_policy:
+                A = net.n_actions
+                ops.policy_head_train(h, st.wq[-1], st.b[-1], A, hl, mb["actions"], mb["old_logp"], mb["adv"], inv_b,
+                                      float(self.clip_range), float(self.ent_coef), ws["dz"], metrics, M=M)
+                ops.linear_wgrad(ws["dz"], h, st.gw[-1], st.gb[-1], A, hl, M=M)
+                ops.linear_dgrad(ws["dz"], st.wt[-1], h, dh, st.out_pad, hl, M=M)
+                n += 4      # head GEMM, wgrad, colsum, dgrad
+            else:
+                ops.value_head(h, st.w[-1], st.b[-1], hl, targets=mb["targets"], inv_batch=inv_b, dh=dh,
+                               dw=st.gw[-1], db=st.gb[-1], metrics=metrics, M=M)
+                n += 1
+            st.backward_hidden(x, M, ws, dh)
+            L = len(st.hidden)
+            n += L + 2 * L + (L - 1)   # fwd GEMMs, wgrad + colsum per layer, dgrad for all but the first
+        self.launches += n
+
+    def _optimizer_step(self):
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self._grads, group=self._pg)   # NCCL sum over NVLink; grads carry 1/B
+        ops.grad_sqnorm(self._grads, self._seg, self._sqnorm)           # ppo_learner.py:187-190
+        ops.clip_adam(self._params, self._grads, self._m, self._v, self._seg, self._sqnorm, self._lr_dev,
+                      self._steps, max_norm=0.5)                        # :192-193
+        self.policy._stack.refresh_operands(force=True)
+        self.value_net._stack.refresh_operands(force=True)
+        self.launches += 3 + len(self.policy._stack.linears) + len(self.value_net._stack.linears)
+
+    def learn(self, exp):
+        """
+        Compute PPO updates with an experience buffer (ppo_learner.py:92-238).
+        Returns the reference's report dictionary (same keys).
+        """
+        n_iterations = 0
+        self.launches = 0
+        self.policy._stack.refresh_operands()
+        self.value_net._stack.refresh_operands()
+        self._sync_lr()
+        self._before.copy_(self._params)          # update-magnitude baseline (:110-116), stays on the device
+        self._tail.zero_()
+
+        t1 = time.time()
+        B, R = self.batch_size, self.world_size
+        local = B // R
+        chunk = min(local, self.max_chunk_rows)
+        for epoch in range(self.n_epochs):
+            total = len(exp)
+            perm = exp.next_permutation()                       # experience_buffer.py:98, once per epoch
+            n_batches = total // B                              # :100, remainder dropped
+            if n_batches == 0:
+                continue
+            idx_dev = torch.from_numpy(perm).to(self._params.device, non_blocking=True)
+            for k in range(n_batches):
+                self._grads.zero_()                             # :131-132
+                base = k * B + self.rank * local
+                for c0 in range(0, local, chunk):
+                    rows = min(chunk, local - c0)
+                    self._train_chunk(exp, idx_dev[base + c0:base + c0 + rows], rows)
+                self._optimizer_step()
+                n_iterations += 1
+
+        # ---- report: one device -> host readback for the whole call -------------------------------------------
+        ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
+        if R > 1:
+            torch.distributed.all_reduce(self._tail[0:8], group=self._pg)
+        self._tail_host.copy_(self._tail, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        t = self._tail_host.double().numpy()
+        rows_p = t[4] if t[4] > 0 else 1.0
+        rows_v = t[6] if t[6] > 0 else 1.0
+
+        if n_iterations == 0:
+            n_iterations = 1
+        self.cumulative_model_updates += n_iterations
+
+        report = {
+            "PPO Batch Consumption Time": (time.time() - t1) / n_iterations,
+            "Cumulative Model Updates": self.cumulative_model_updates,
+            "Policy Entropy": float(t[0] / rows_p),
+            "Mean KL Divergence": float(t[1] / rows_p),
+            "Value Function Loss": float(t[5] / rows_v),
+            "SB3 Clip Fraction": float(t[2] / rows_p),
+            "Policy Update Magnitude": float(np.sqrt(t[8])),
+            "Value Function Update Magnitude": float(np.sqrt(t[9])),
+        }
+        return report
+
+    # ---- checkpoints: the reference's four files, stock torch formats (ppo_learner.py:240-271) -------------------
+    def save_to(self, folder_path):
+        os.makedirs(folder_path, exist_ok=True)
+        cpu = lambda sd: {k: v.detach().cpu().clone() for k, v in sd.items()}  # noqa: E731
+        torch.save(cpu(self.policy.state_dict()), os.path.join(folder_path, "PPO_POLICY.pt"))
+        torch.save(cpu(self.value_net.state_dict()), os.path.join(folder_path, "PPO_VALUE_NET.pt"))
+        torch.save(_optim_to_cpu(self.policy_optimizer.state_dict()),
+                   os.path.join(folder_path, "PPO_POLICY_OPTIMIZER.pt"))
+        torch.save(_optim_to_cpu(self.value_optimizer.state_dict()),
+                   os.path.join(folder_path, "PPO_VALUE_NET_OPTIMIZER.pt"))
+
+    def load_from(self, folder_path):
+        assert os.path.exists(folder_path), "PPO LEARNER CANNOT FIND FOLDER {}".format(folder_path)
+        dev = self._params.device
+        self.policy.load_state_dict(torch.load(os.path.join(folder_path, "PPO_POLICY.pt"), map_location=dev))
+        self.value_net.load_state_dict(torch.load(os.path.join(folder_path, "PPO_VALUE_NET.pt"), map_location=dev))
+        self.policy_optimizer.load_state_dict(
+            torch.load(os.path.join(folder_path, "PPO_POLICY_OPTIMIZER.pt"), map_location=dev))
+        self.value_optimizer.load_state_dict(
+            torch.load(os.path.join(folder_path, "PPO_VALUE_NET_OPTIMIZER.pt"), map_location=dev))
+        self._lr_host = None
+
+
+def _optim_to_cpu(sd):
+    state = {i: {k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v) for k, v in s.items()}
+             for i, s in sd["state"].items()}
+    return {"state": state, "param_groups": sd["param_groups"]}
