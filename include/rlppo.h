@@ -80,15 +80,30 @@ int rlppo_ring_append(float* ring, int64_t ring_ld, uint16_t* ring_bf16, int64_t
                       int64_t phys_first, const void* src, int src_is_f64, int64_t src_ld, int64_t n_rows,
                       int width, void* stream);
 
+/* All fields of one submit_experience in ONE launch (nine rings, experience_buffer.py:68-80). */
+typedef struct rlppo_append_field {
+    float* ring;            /* f32 ring [capacity, ring_ld] */
+    int64_t ring_ld;
+    uint16_t* ring_bf16;    /* optional bf16 side copy (zero padded to bf16_ld), else NULL */
+    int64_t bf16_ld;
+    const void* src;        /* new rows, f32 or f64 */
+    int64_t src_ld;
+    int32_t src_is_f64;
+    int32_t width;
+} rlppo_append_field;
+int rlppo_ring_append_fields(const rlppo_append_field* h_fields, int n_fields, int64_t capacity,
+                             int64_t phys_first, int64_t n_rows, void* stream);
+
 /* ---- (c-2) minibatch gather: experience_buffer.py:82-102 _get_samples ------------------------------
  * idx: int64[B] LOGICAL indices (a slice of RandomState.permutation, generated on the host so the
  * stream is NumPy's own); physical row = (start + idx) % capacity.  Any output may be NULL.
+ * d_start: optional device int64[1] overriding `start` (a captured CUDA graph then follows the ring as it wraps).
  *   out_actions/out_logp/out_values/out_adv  f32[B];  out_states f32[B,obs] (exact copy: the public
  *   get_all_batches_shuffled contract);  out_states_bf16 [B, bf16_ld] from the bf16 ring (GEMM operand). */
 int rlppo_gather_batch(const float* actions, const float* logp, const float* values, const float* adv,
                        const float* states, int64_t states_ld, const uint16_t* states_bf16, int64_t bf16_ld,
-                       int obs_dim, int64_t capacity, int64_t start, const int64_t* idx, int64_t B,
-                       float* out_actions, float* out_logp, float* out_values, float* out_adv,
+                       int obs_dim, int64_t capacity, int64_t start, const int64_t* d_start, const int64_t* idx,
+                       int64_t B, float* out_actions, float* out_logp, float* out_values, float* out_adv,
                        float* out_states, uint16_t* out_states_bf16, void* stream);
 /* Host-side NumPy-legacy permutation (experience_buffer.py:98 `self.rng.permutation(total)`):
  * MT19937 + masked-rejection Fisher-Yates, bit-exact with np.random.RandomState.  h_key: uint32[624],
@@ -217,9 +232,20 @@ int rlppo_value_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int64
  * (update_learning_rate, learner.py:205-216, rewrites it).  delta_sq (optional f32[n_seg]) accumulates
  * nothing here; see rlppo_sqdiff. */
 int rlppo_grad_sqnorm(const float* grads, const int64_t* h_seg_off, int n_seg, float* sqnorm, void* stream);
+/* h_views (optional, <= 16): weight matrices inside the arena whose bf16 GEMM operands (W and W^T, see
+ * rlppo_weight_to_bf16) are rewritten by the same launch, so no separate refresh pass is needed after a step. */
+typedef struct rlppo_bf16_view {
+    int64_t offset;         /* element offset of W [out_f, in_f] in the parameter arena */
+    int32_t out_f, in_f;
+    uint16_t* wq;           /* bf16 W, ld wq_ld */
+    int64_t wq_ld;
+    uint16_t* wt;           /* bf16 W^T, ld wt_ld, or NULL */
+    int64_t wt_ld;
+} rlppo_bf16_view;
 int rlppo_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off,
                     int n_seg, const float* sqnorm, const float* lr, int64_t* step_count, double max_norm,
-                    double beta1, double beta2, double eps, void* stream);
+                    double beta1, double beta2, double eps, const rlppo_bf16_view* h_views, int n_views,
+                    void* stream);
 /* out f32[n_seg] = per-segment sum (a-b)^2 (update magnitudes, ppo_learner.py:212-220). */
 int rlppo_sqdiff(const float* a, const float* b, const int64_t* h_seg_off, int n_seg, float* out,
                  void* stream);

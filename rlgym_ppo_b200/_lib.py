@@ -36,7 +36,8 @@ _SIGS = {
     "rlppo_gae_chunk_summary": ([_P, _P, _P, _I, _P, _L, _D, _D, _P, _P, _P, _SZ, _P], _I),
     "rlppo_welford_update": ([_P, _P, _P, _P, _I, _L, _I, _P, _P, _P], _I),
     "rlppo_ring_append": ([_P, _L, _P, _L, _L, _L, _P, _I, _L, _L, _I, _P], _I),
-    "rlppo_gather_batch": ([_P, _P, _P, _P, _P, _L, _P, _L, _I, _L, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P], _I),
+    "rlppo_ring_append_fields": ([_P, _I, _L, _L, _L, _P], _I),
+    "rlppo_gather_batch": ([_P, _P, _P, _P, _P, _L, _P, _L, _I, _L, _L, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P], _I),
     "rlppo_host_permutation": ([_P, _P, _L, _P], _I),
     "rlppo_rows_to_bf16": ([_P, _L, _L, _I, _P, _L, _P], _I),
     "rlppo_rows_standardize_to_bf16": ([_P, _L, _L, _I, _P, _P, _F, _P, _L, _P, _L, _P], _I),
@@ -52,11 +53,23 @@ _SIGS = {
     "rlppo_value_train_fused": ([_P, _P, _L, _P, _P, _F, _P, _P, _P, _P], _I),
     "rlppo_value_infer_fused": ([_P, _P, _L, _P, _P, _P], _I),
     "rlppo_grad_sqnorm": ([_P, _P, _I, _P, _P], _I),
-    "rlppo_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P], _I),
+    "rlppo_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P], _I),
     "rlppo_sqdiff": ([_P, _P, _P, _I, _P, _P], _I),
 }
 
 EXPORTED = tuple(_SIGS)
+
+
+class AppendField(ctypes.Structure):
+    """struct rlppo_append_field."""
+    _fields_ = [("ring", _P), ("ring_ld", _L), ("ring_bf16", _P), ("bf16_ld", _L), ("src", _P), ("src_ld", _L),
+                ("src_is_f64", ctypes.c_int32), ("width", ctypes.c_int32)]
+
+
+class Bf16View(ctypes.Structure):
+    """struct rlppo_bf16_view."""
+    _fields_ = [("offset", _L), ("out_f", ctypes.c_int32), ("in_f", ctypes.c_int32), ("wq", _P), ("wq_ld", _L),
+                ("wt", _P), ("wt_ld", _L)]
 
 
 class FusedNet(ctypes.Structure):
@@ -151,6 +164,20 @@ def version():
 
 def gae_workspace_bytes(n):
     return int(_lib.rlppo_gae_workspace_bytes(int(n)))
+
+
+def host_permutation_raw(key, pos, n, out=None):
+    """The same draw on raw MT19937 state (uint32[624] array, int position): returns (perm, key_after, pos_after).
+    Touches no Python-level RandomState, releases the GIL: safe to run on a worker thread."""
+    import numpy as np
+
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    p = np.asarray([pos], dtype=np.int32)
+    if out is None:
+        out = np.empty(int(n), dtype=np.int64)
+    rc = _lib.rlppo_host_permutation(key.ctypes.data_as(_P), p.ctypes.data_as(_P), int(n), out.ctypes.data_as(_P))
+    _check(rc, "rlppo_host_permutation")
+    return out, key, int(p[0])
 
 
 def host_permutation(rng, n):

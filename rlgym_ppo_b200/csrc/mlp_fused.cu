@@ -40,7 +40,6 @@ constexpr uint32_t ACT_BYTES = 4 * KB_BYTES;       // 64 KB
 constexpr uint32_t WST_BYTES = 256 * KBLK * 2;     // 32 KB: one k-block of a weight operand (<= 256 rows)
 constexpr int NWST = 2;
 constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
 constexpr int MAXPH = 2 * MAXL + 1;
 
 constexpr uint32_t OFF_ACT_A = 0;
@@ -139,6 +138,12 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 }
 
 __device__ __forceinline__ float bf16_round(float x) { return bf16_bits_to_f32(f32_to_bf16_bits(x)); }
+// two floats -> packed bf16x2 in ONE instruction (cvt.rn.bf16x2.f32; `lo` lands in the low half)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 // write 32 consecutive columns [col0, col0+32) of one row into a K-major SWIZZLE_128B activation tile
 __device__ __forceinline__ void store_chunk_sw128(uint8_t* buf, int row, int chunk32, const float (&v)[32]) {
@@ -147,10 +152,10 @@ __device__ __forceinline__ void store_chunk_sw128(uint8_t* buf, int row, int chu
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         uint4 o;
-        o.x = pack_bf16x2(v[t * 8 + 0], v[t * 8 + 1]);
-        o.y = pack_bf16x2(v[t * 8 + 2], v[t * 8 + 3]);
-        o.z = pack_bf16x2(v[t * 8 + 4], v[t * 8 + 5]);
-        o.w = pack_bf16x2(v[t * 8 + 6], v[t * 8 + 7]);
+        o.x = cvt_bf16x2(v[t * 8 + 0], v[t * 8 + 1]);
+        o.y = cvt_bf16x2(v[t * 8 + 2], v[t * 8 + 3]);
+        o.z = cvt_bf16x2(v[t * 8 + 4], v[t * 8 + 5]);
+        o.w = cvt_bf16x2(v[t * 8 + 6], v[t * 8 + 7]);
         *reinterpret_cast<uint4*>(kb + (((base16 + t) ^ (row & 7)) << 4)) = o;
     }
 }
@@ -371,6 +376,35 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         for (int j = 0; j < 4; ++j) dwacc[j] = 0.f;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, mrows = 0.f;   // metric partial sums of this thread's rows
 
+        // The chunk loops below are deliberately NOT unrolled and take the layer as a run-time index (register arrays
+        // are read/written through predicated selects): the first version specialised every (layer, chunk) pair and
+        // grew to 30k instructions (480 KB), and ncu showed the epilogue warps stalled on instruction fetch
+        // (stall_no_inst = half of all samples).
+        auto relu_get = [&](int l, int j) {
+            uint32_t v = 0u;
+#pragma unroll
+            for (int a = 0; a < MAXL; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) v = (a == l && b == j) ? relu[a][b] : v;
+            return v;
+        };
+        auto relu_set = [&](int l, int j, uint32_t v) {
+#pragma unroll
+            for (int a = 0; a < MAXL; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) relu[a][b] = (a == l && b == j) ? v : relu[a][b];
+        };
+        auto db_add = [&](int l, int j, float v) {
+#pragma unroll
+            for (int a = 0; a <= MAXL; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dbacc[a][b] += (a == l && b == j) ? v : 0.f;
+        };
+        auto dw_add = [&](int j, float v) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dwacc[b] += (b == j) ? v : 0.f;
+        };
+
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
@@ -383,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + acc * 256;
                 uint8_t* dst = act[d.src ^ 1];
                 uint8_t* srcb = act[d.src];
+                const int li = d.layer;
 
                 if (d.kind == PH_FWD || d.kind == PH_FWD_VALUE) {
                     const int nc = d.N >> 5;
@@ -390,39 +425,31 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     const bool tail = (d.kind == PH_FWD_VALUE);
                     if (!tail) release_untouched(e, c0, c1);
                     float dot = 0.f;
-#define RLPPO_FWD_LAYER(LI)                                                                                  \
-    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                          \
-        const int c = c0 + j;                                                                                \
-        if (c < c1) {                                                                                        \
-            float v[32];                                                                                     \
-            tmem_ld32(trow + c * 32, v);                                                                     \
-            const float* sb = s_bias + (LI) * 256 + c * 32;                                                  \
-            uint32_t bits = 0u;                                                                              \
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) {                                                 \
-                const float xv = fmaxf(v[i] + sb[i], 0.f);                                                   \
-                bits |= (xv > 0.f ? 1u : 0u) << i;                                                           \
-                v[i] = xv;                                                                                   \
-            }                                                                                                \
-            if (TRAIN) relu[LI][j] = bits;                                                                   \
-            if (tail) {                                                                                      \
-                const float* wv = s_bias + MAXL * 256 + c * 32;                                              \
-                _Pragma("unroll") for (int i = 0; i < 32; ++i) dot = fmaf(bf16_round(v[i]), wv[i], dot);     \
-            }                                                                                                \
-            if (!tail) {                                                                                     \
-                store_chunk_sw128(dst, e.row_in_tile, c, v);                                                 \
-                release_after_chunk(e, c, c1);                                                               \
-            } else if (TRAIN) {                                                                              \
-                store_chunk_sw128(dst, e.row_in_tile, c, v);                                                 \
-            }                                                                                                \
-        }                                                                                                    \
-    }
-                    switch (d.layer) {
-                        case 0: RLPPO_FWD_LAYER(0) break;
-                        case 1: RLPPO_FWD_LAYER(1) break;
-                        case 2: RLPPO_FWD_LAYER(2) break;
-                        default: RLPPO_FWD_LAYER(3) break;
+#pragma unroll 1
+                    for (int c = c0; c < c1; ++c) {
+                        float v[32];
+                        tmem_ld32(trow + c * 32, v);
+                        const float* sb = s_bias + li * 256 + c * 32;
+                        uint32_t bits = 0u;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float xv = fmaxf(v[i] + sb[i], 0.f);
+                            bits |= (xv > 0.f ? 1u : 0u) << i;
+                            v[i] = xv;
+                        }
+                        if (TRAIN) relu_set(li, c - c0, bits);
+                        if (tail) {
+                            const float* wv = s_bias + MAXL * 256 + c * 32;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) dot = fmaf(bf16_round(v[i]), wv[i], dot);
+                        }
+                        if (!tail) {
+                            store_chunk_sw128(dst, e.row_in_tile, c, v);
+                            release_after_chunk(e, c, c1);
+                        } else if (TRAIN) {
+                            store_chunk_sw128(dst, e.row_in_tile, c, v);
+                        }
                     }
-#undef RLPPO_FWD_LAYER
                     if (tail) {
                         // ---- value head: v = H_L . w + b (value_estimator.py:27), MSE loss and its gradient ----
                         e.s_rowx[e.half * 128 + e.row_in_tile] = dot;
@@ -447,65 +474,50 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 }
                             }
                             release_untouched(e, c0, c1);
-#define RLPPO_VALUE_TAIL(LI)                                                                                 \
-    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                          \
-        const int c = c0 + j;                                                                                \
-        if (c < c1) {                                                                                        \
-            float v[32], t[32];                                                                              \
-            tmem_ld32(trow + c * 32, v);                                                                     \
-            const float* sb = s_bias + (LI) * 256 + c * 32;                                                  \
-            const float* wv = s_bias + MAXL * 256 + c * 32;                                                  \
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) {                                                 \
-                const float h = bf16_round(fmaxf(v[i] + sb[i], 0.f));                                        \
-                t[i] = dv * h;                                                                               \
-                v[i] = h > 0.f ? dv * wv[i] : 0.f;                                                           \
-            }                                                                                                \
-            dwacc[j] += warp_colsum32(t, e.lane);                                                            \
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) t[i] = v[i];                                      \
-            dbacc[LI][j] += warp_colsum32(t, e.lane);                                                        \
-            store_chunk_sw128(srcb, e.row_in_tile, c, v);                                                    \
-            release_after_chunk(e, c, c1);                                                                   \
-        }                                                                                                    \
-    }
-                            switch (d.layer) {
-                                case 0: RLPPO_VALUE_TAIL(0) break;
-                                case 1: RLPPO_VALUE_TAIL(1) break;
-                                case 2: RLPPO_VALUE_TAIL(2) break;
-                                default: RLPPO_VALUE_TAIL(3) break;
+#pragma unroll 1
+                            for (int c = c0; c < c1; ++c) {
+                                float v[32], t[32];
+                                tmem_ld32(trow + c * 32, v);
+                                const float* sb = s_bias + li * 256 + c * 32;
+                                const float* wv = s_bias + MAXL * 256 + c * 32;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const float h = bf16_round(fmaxf(v[i] + sb[i], 0.f));
+                                    t[i] = dv * h;
+                                    v[i] = h > 0.f ? dv * wv[i] : 0.f;
+                                }
+                                dw_add(c - c0, warp_colsum32(t, e.lane));
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) t[i] = v[i];
+                                db_add(li, c - c0, warp_colsum32(t, e.lane));
+                                store_chunk_sw128(srcb, e.row_in_tile, c, v);
+                                release_after_chunk(e, c, c1);
                             }
-#undef RLPPO_VALUE_TAIL
                         }
                     }
                 } else if (d.kind == PH_DGRAD) {
                     const int nc = d.N >> 5;
                     const int c0 = e.half * (nc >> 1), c1 = c0 + (nc >> 1);
                     release_untouched(e, c0, c1);
-#define RLPPO_DGRAD_LAYER(LI)                                                                                \
-    _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                                          \
-        const int c = c0 + j;                                                                                \
-        if (c < c1) {                                                                                        \
-            float v[32], t[32];                                                                              \
-            tmem_ld32(trow + c * 32, v);                                                                     \
-            const uint32_t bits = relu[LI][j];                                                               \
-            _Pragma("unroll") for (int i = 0; i < 32; ++i) {                                                 \
-                v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;                                                      \
-                t[i] = v[i];                                                                                 \
-            }                                                                                                \
-            dbacc[LI][j] += warp_colsum32(t, e.lane);                                                        \
-            store_chunk_sw128(dst, e.row_in_tile, c, v);                                                     \
-            release_after_chunk(e, c, c1);                                                                   \
-        }                                                                                                    \
-    }
-                    switch (d.layer) {
-                        case 0: RLPPO_DGRAD_LAYER(0) break;
-                        case 1: RLPPO_DGRAD_LAYER(1) break;
-                        case 2: RLPPO_DGRAD_LAYER(2) break;
-                        default: RLPPO_DGRAD_LAYER(3) break;
+#pragma unroll 1
+                    for (int c = c0; c < c1; ++c) {
+                        float v[32], t[32];
+                        tmem_ld32(trow + c * 32, v);
+                        const uint32_t bits = relu_get(li, c - c0);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
+                            t[i] = v[i];
+                        }
+                        db_add(li, c - c0, warp_colsum32(t, e.lane));
+                        store_chunk_sw128(dst, e.row_in_tile, c, v);
+                        release_after_chunk(e, c, c1);
                     }
-#undef RLPPO_DGRAD_LAYER
                 } else {
                     // ---- policy head (discrete_policy.py:44-80, ppo_learner.py:153-177) ----
-                    // one thread = one row, all logits in registers; the upper-half warps have nothing to do here
+                    // one thread = one row; the logits stay in TMEM and are re-read chunk by chunk in each pass (a TMEM
+                    // load is cheaper than the code size of keeping 128 logits in registers).  The upper-half warps have
+                    // nothing to do in this phase.
                     const int nact = p.n_actions;
                     const int nch = (nact + 31) >> 5;          // <= 4
                     const int nch_out = p.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
@@ -513,34 +525,34 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         release_untouched(e, 0, 0);
                     } else {
                         release_untouched(e, 0, TRAIN ? nch_out : 0);
-                        float z[128];
+                        const float* sb = s_bias + MAXL * 256;
                         float mx = -INFINITY;
                         int argmax = 0;
-                        const float* sb = s_bias + MAXL * 256;
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c) {
+                            float v[32];
+                            tmem_ld32(trow + c * 32, v);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            if (c < nch) {
-                                float v[32];
-                                tmem_ld32(trow + c * 32, v);
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const int col = c * 32 + i;
-                                    const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
-                                    z[col] = zz;
-                                    if (zz > mx) {
-                                        mx = zz;
-                                        argmax = col;
-                                    }
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = c * 32 + i;
+                                const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
+                                if (zz > mx) {
+                                    mx = zz;
+                                    argmax = col;
                                 }
                             }
                         }
                         float S = 0.f;
+#pragma unroll 1
+                        for (int c = 0; c < nch; ++c) {
+                            float v[32];
+                            tmem_ld32(trow + c * 32, v);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (c < nch) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) S += __expf(z[c * 32 + i] - mx);   // exp(-inf) = 0 for padding
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = c * 32 + i;
+                                S += col < nact ? __expf(v[i] + sb[col] - mx) : 0.f;
                             }
+                        }
                         const float logS = logf(S);
                         const float kLogMin = -25.328436022934504f;   // ln(1e-11)
                         if (TRAIN) {
@@ -552,27 +564,29 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 old_lp = __ldg(p.old_logp + row);
                                 advv = __ldg(p.adv + row);
                             }
-                            // pass: log-softmax in place, entropy, sum_j m_j s_j (log p_j + 1), the action's terms
+                            // pass: entropy, sum_j m_j s_j (log p_j + 1), the action's log-softmax
                             float Hent = 0.f, Gs = 0.f, ls_a = 0.f;
+#pragma unroll 1
+                            for (int c = 0; c < nch; ++c) {
+                                float v[32];
+                                tmem_ld32(trow + c * 32, v);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (c < nch) {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
-                                        const int col = c * 32 + i;
-                                        const float ls = (z[col] - mx) - logS;          // log softmax (<= 0)
-                                        z[col] = ls;
+                                for (int i = 0; i < 32; ++i) {
+                                    const int col = c * 32 + i;
+                                    if (col < nact) {
+                                        const float ls = (v[i] + sb[col] - mx) - logS;      // log softmax (<= 0)
                                         const float s = __expf(ls);
-                                        const float lp = fminf(fmaxf(ls, kLogMin), 0.f);  // log clamp(s, 1e-11, 1), :74-76
+                                        const float lp = fminf(fmaxf(ls, kLogMin), 0.f);    // log clamp(s, 1e-11, 1), :74-76
                                         const float pj = fminf(fmaxf(s, 1e-11f), 1.0f);
-                                        Hent -= pj * lp;                                // :78
-                                        if (ls >= kLogMin) Gs += s * (lp + 1.0f);       // clamp passes gradient inside only
-                                        if (col == a) ls_a = ls;
+                                        Hent -= pj * lp;                                    // :78
+                                        Gs += ls >= kLogMin ? s * (lp + 1.0f) : 0.f;        // clamp passes gradient inside only
+                                        ls_a = col == a ? ls : ls_a;
                                     }
                                 }
+                            }
                             const float lp_a = fminf(fmaxf(ls_a, kLogMin), 0.f);
-                            const float p_a = fminf(fmaxf(__expf(ls_a), 1e-11f), 1.0f);
                             const float s_a = __expf(ls_a);
+                            const float p_a = fminf(fmaxf(s_a, 1e-11f), 1.0f);
                             const float log_ratio = lp_a - old_lp;
                             const float ratio = expf(log_ratio);                            // ppo_learner.py:153
                             const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
@@ -595,44 +609,47 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 if (p.logp_out) p.logp_out[row] = lp_a;
                             }
                             // pass: dz_j = s_j (g_j - G) -> bf16 tile (A operand of the first dgrad GEMM) + head bias grads
+#pragma unroll 1
+                            for (int c = 0; c < nch_out; ++c) {
+                                float v[32], t[32];
+                                if (c < nch) {
+                                    tmem_ld32(trow + c * 32, v);
+                                } else {
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (c < nch_out) {
-                                    float v[32], t[32];
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
-                                        const int col = c * 32 + i;
-                                        float o = 0.f;
-                                        if (c < nch && col < nact) {
-                                            const float ls = z[col];
-                                            const float s = __expf(ls);
-                                            const float lp = fminf(fmaxf(ls, kLogMin), 0.f);
-                                            float gj = cw * (lp + 1.0f) + (col == a ? ga : 0.f);
-                                            gj = ls >= kLogMin ? gj : 0.f;
-                                            o = s * (gj - G);
-                                        }
-                                        v[i] = o;
-                                        t[i] = o;
-                                    }
-                                    dbacc[MAXL][c] += warp_colsum32(t, e.lane);
-                                    store_chunk_sw128(dst, e.row_in_tile, c, v);
-                                    release_after_chunk(e, c, nch_out);
+                                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
                                 }
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const int col = c * 32 + i;
+                                    float o = 0.f;
+                                    if (col < nact) {
+                                        const float ls = (v[i] + sb[col] - mx) - logS;
+                                        const float s = __expf(ls);
+                                        const float lp = fminf(fmaxf(ls, kLogMin), 0.f);
+                                        float gj = cw * (lp + 1.0f) + (col == a ? ga : 0.f);
+                                        gj = ls >= kLogMin ? gj : 0.f;
+                                        o = s * (gj - G);
+                                    }
+                                    v[i] = o;
+                                    t[i] = o;
+                                }
+                                db_add(MAXL, c, warp_colsum32(t, e.lane));
+                                store_chunk_sw128(dst, e.row_in_tile, c, v);
+                                release_after_chunk(e, c, nch_out);
+                            }
                         } else {
                             // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62) ----
                             float P = 0.f;
+#pragma unroll 1
+                            for (int c = 0; c < nch; ++c) {
+                                float v[32];
+                                tmem_ld32(trow + c * 32, v);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (c < nch) {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
-                                        const int col = c * 32 + i;
-                                        const float s = __expf((z[col] - mx) - logS);
-                                        const float pj = col < nact ? fminf(fmaxf(s, 1e-11f), 1.0f) : 0.f;
-                                        z[col] = pj;
-                                        P += pj;
-                                    }
+                                for (int i = 0; i < 32; ++i) {
+                                    const int col = c * 32 + i;
+                                    if (col < nact) P += fminf(fmaxf(__expf((v[i] + sb[col] - mx) - logS), 1e-11f), 1.0f);
                                 }
+                            }
                             int actn = nact - 1;
                             float pa = 0.f;
                             if (p.deterministic) {
@@ -653,23 +670,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 const float thr = u * P;   // torch.multinomial normalises what it is given
                                 float run = 0.f, plast = 0.f;
                                 bool found = false;
+#pragma unroll 1
+                                for (int c = 0; c < nch; ++c) {
+                                    float v[32];
+                                    tmem_ld32(trow + c * 32, v);
 #pragma unroll
-                                for (int c = 0; c < 4; ++c)
-                                    if (c < nch) {
-#pragma unroll
-                                        for (int i = 0; i < 32; ++i) {
-                                            const int col = c * 32 + i;
-                                            if (col < nact) {
-                                                run += z[col];
-                                                plast = z[col];
-                                                if (!found && run > thr) {
-                                                    found = true;
-                                                    actn = col;
-                                                    pa = z[col];
-                                                }
+                                    for (int i = 0; i < 32; ++i) {
+                                        const int col = c * 32 + i;
+                                        if (col < nact) {
+                                            const float pj = fminf(fmaxf(__expf((v[i] + sb[col] - mx) - logS), 1e-11f), 1.0f);
+                                            run += pj;
+                                            plast = pj;
+                                            if (!found && run > thr) {
+                                                found = true;
+                                                actn = col;
+                                                pa = pj;
                                             }
                                         }
                                     }
+                                }
                                 if (!found) pa = plast;
                             }
                             if (row_ok) {

@@ -56,10 +56,16 @@ __global__ void bump_steps_kernel(int64_t* step_count, int n_seg) {
     if (threadIdx.x < n_seg) step_count[threadIdx.x] += 1;
 }
 
+constexpr int kMaxViews = 16;
+struct Views {
+    rlppo_bf16_view v[kMaxViews];
+    int n;
+};
+
 __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, Segs segs, const float* __restrict__ sqnorm,
                                  const float* __restrict__ lr, const int64_t* __restrict__ step_count, float max_norm,
-                                 double beta1d, double beta2d, float eps) {
+                                 double beta1d, double beta2d, float eps, Views views) {
     // the weights torch derives in Python doubles and then casts: (float)(1 - beta)
     const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
     __shared__ float s_coef[kMaxSeg], s_step_size[kMaxSeg], s_bc2_sqrt[kMaxSeg];
@@ -84,9 +90,22 @@ __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict_
         mi = mi + (gi - mi) * omb1;                           // exp_avg.lerp_(grad, 1-beta1)
         vi = vi * beta2 + omb2 * gi * gi;                      // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
         const float denom = sqrtf(vi) / s_bc2_sqrt[k] + eps;   // (sqrt(v)/sqrt(bc2)).add_(eps)
-        p[i] = p[i] - s_step_size[k] * (mi / denom);           // param.addcdiv_(m, denom, -step_size)
+        const float pn = p[i] - s_step_size[k] * (mi / denom);   // param.addcdiv_(m, denom, -step_size)
+        p[i] = pn;
         m[i] = mi;
         v[i] = vi;
+        // refresh the bf16 GEMM operands of the weight this element belongs to (W and W^T), same launch
+        for (int q = 0; q < views.n; ++q) {
+            const rlppo_bf16_view& w = views.v[q];
+            const int64_t rel = i - w.offset;
+            if (rel >= 0 && rel < (int64_t)w.out_f * w.in_f) {
+                const int r = (int)(rel / w.in_f), c = (int)(rel - (int64_t)r * w.in_f);
+                const uint16_t b = rlppo::f32_to_bf16_bits(pn);
+                w.wq[(int64_t)r * w.wq_ld + c] = b;
+                if (w.wt != nullptr) w.wt[(int64_t)c * w.wt_ld + r] = b;
+                break;
+            }
+        }
     }
 }
 
@@ -139,16 +158,23 @@ int rlppo_sqdiff(const float* a, const float* b, const int64_t* h_seg_off, int n
 
 int rlppo_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off, int n_seg,
                     const float* sqnorm, const float* lr, int64_t* step_count, double max_norm, double beta1,
-                    double beta2, double eps, void* stream) {
+                    double beta2, double eps, const rlppo_bf16_view* h_views, int n_views, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(params && grads && m && v && sqnorm && lr && step_count, "null pointer");
     Segs segs;
     int rc = make_segs(h_seg_off, n_seg, &segs);
     if (rc) return rc;
+    RLPPO_CHECK_ARG(n_views >= 0 && n_views <= kMaxViews && (n_views == 0 || h_views), "0..%d bf16 views", kMaxViews);
+    Views views;
+    views.n = n_views;
+    for (int i = 0; i < n_views; ++i) {
+        views.v[i] = h_views[i];
+        RLPPO_CHECK_ARG(h_views[i].wq && h_views[i].out_f >= 1 && h_views[i].in_f >= 1, "bad bf16 view %d", i);
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     bump_steps_kernel<<<1, 32, 0, s>>>(step_count, n_seg);
     clip_adam_kernel<<<grid_for(segs.off[n_seg]), 256, 0, s>>>(params, grads, m, v, segs, sqnorm, lr, step_count,
-                                                              (float)max_norm, beta1, beta2, (float)eps);
+                                                              (float)max_norm, beta1, beta2, (float)eps, views);
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }

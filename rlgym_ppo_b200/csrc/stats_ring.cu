@@ -83,19 +83,59 @@ __global__ void ring_append_flat_kernel(float* ring, int64_t capacity, int64_t p
     ring[phys] = F64 ? (float)static_cast<const double*>(src)[i] : static_cast<const float*>(src)[i];
 }
 
+// All fields of one submit in ONE launch: blockIdx.y = field, 64 rows per block (8 warps x 8 rows for wide fields,
+// the first 64 threads for scalar fields).
+constexpr int kMaxAppendFields = 12;
+struct AppendFields {
+    rlppo_append_field f[kMaxAppendFields];
+};
+__global__ void ring_append_fields_kernel(AppendFields fs, int64_t capacity, int64_t phys_first, int64_t n_rows) {
+    const rlppo_append_field& f = fs.f[blockIdx.y];
+    const int64_t row0 = (int64_t)blockIdx.x * 64;
+    if (f.width == 1 && f.ring_bf16 == nullptr) {
+        const int64_t row = row0 + threadIdx.x;
+        if (threadIdx.x < 64 && row < n_rows) {
+            int64_t phys = phys_first + row;
+            if (phys >= capacity) phys -= capacity;
+            f.ring[phys * f.ring_ld] = f.src_is_f64 ? (float)static_cast<const double*>(f.src)[row * f.src_ld]
+                                                    : static_cast<const float*>(f.src)[row * f.src_ld];
+        }
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncol = f.ring_bf16 ? (int)f.bf16_ld : f.width;
+    for (int r = warp; r < 64; r += 8) {
+        const int64_t row = row0 + r;
+        if (row >= n_rows) break;
+        int64_t phys = phys_first + row;
+        if (phys >= capacity) phys -= capacity;
+        for (int c = lane; c < ncol; c += 32) {
+            float x = 0.f;
+            if (c < f.width) {
+                x = f.src_is_f64 ? (float)static_cast<const double*>(f.src)[row * f.src_ld + c]
+                                 : static_cast<const float*>(f.src)[row * f.src_ld + c];
+                f.ring[phys * f.ring_ld + c] = x;
+            }
+            if (f.ring_bf16) f.ring_bf16[phys * f.bf16_ld + c] = rlppo::f32_to_bf16_bits(x);
+        }
+    }
+}
+
 // ---- gather ---------------------------------------------------------------------------------------------
 // One warp per sample: lane 0..3 fetch the four scalars, all lanes stream the observation row(s).
 __global__ void gather_kernel(const float* __restrict__ actions, const float* __restrict__ logp,
                               const float* __restrict__ values, const float* __restrict__ adv,
                               const float* __restrict__ states, int64_t states_ld,
                               const uint16_t* __restrict__ states_bf16, int64_t bf16_ld, int obs_dim,
-                              int64_t capacity, int64_t start, const int64_t* __restrict__ idx, int64_t B,
+                              int64_t capacity, int64_t start, const int64_t* __restrict__ d_start,
+                              const int64_t* __restrict__ idx, int64_t B,
                               float* __restrict__ out_actions, float* __restrict__ out_logp,
                               float* __restrict__ out_values, float* __restrict__ out_adv,
                               float* __restrict__ out_states, uint16_t* __restrict__ out_states_bf16) {
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     const int lane = threadIdx.x & 31;
+    if (d_start != nullptr) start = __ldg(d_start);   // device-resident ring origin: lets a captured graph follow the ring
     int64_t phys = start + __ldg(idx + b);
     if (phys >= capacity) phys -= capacity;
     if (lane == 0 && out_actions) out_actions[b] = __ldg(actions + phys);
@@ -207,11 +247,31 @@ int rlppo_ring_append(float* ring, int64_t ring_ld, uint16_t* ring_bf16, int64_t
     return RLPPO_OK;
 }
 
+int rlppo_ring_append_fields(const rlppo_append_field* h_fields, int n_fields, int64_t capacity, int64_t phys_first,
+                             int64_t n_rows, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(h_fields && n_fields >= 1 && n_fields <= kMaxAppendFields, "1..%d fields", kMaxAppendFields);
+    RLPPO_CHECK_ARG(capacity > 0 && n_rows >= 0 && n_rows <= capacity && phys_first >= 0 && phys_first < capacity,
+                    "bad ring position");
+    if (n_rows == 0) return RLPPO_OK;
+    AppendFields fs;
+    for (int i = 0; i < n_fields; ++i) {
+        const rlppo_append_field& f = h_fields[i];
+        RLPPO_CHECK_ARG(f.ring && f.src && f.width >= 1 && f.ring_ld >= 1 && f.src_ld >= 1, "bad field %d", i);
+        RLPPO_CHECK_ARG(!f.ring_bf16 || (f.bf16_ld >= f.width && f.bf16_ld % 8 == 0), "field %d: bad bf16_ld", i);
+        fs.f[i] = f;
+    }
+    dim3 grid((unsigned)((n_rows + 63) / 64), (unsigned)n_fields);
+    ring_append_fields_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(fs, capacity, phys_first, n_rows);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
 int rlppo_gather_batch(const float* actions, const float* logp, const float* values, const float* adv,
                        const float* states, int64_t states_ld, const uint16_t* states_bf16, int64_t bf16_ld,
-                       int obs_dim, int64_t capacity, int64_t start, const int64_t* idx, int64_t B, float* out_actions,
-                       float* out_logp, float* out_values, float* out_adv, float* out_states,
-                       uint16_t* out_states_bf16, void* stream) {
+                       int obs_dim, int64_t capacity, int64_t start, const int64_t* d_start, const int64_t* idx,
+                       int64_t B, float* out_actions, float* out_logp, float* out_values, float* out_adv,
+                       float* out_states, uint16_t* out_states_bf16, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(idx && capacity > 0 && start >= 0 && start < capacity && B >= 0, "bad argument");
     RLPPO_CHECK_ARG(!out_actions || actions, "actions ring missing");
@@ -224,7 +284,7 @@ int rlppo_gather_batch(const float* actions, const float* logp, const float* val
     const int threads = 256, per_block = threads / 32;
     const unsigned blocks = (unsigned)((B + per_block - 1) / per_block);
     gather_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        actions, logp, values, adv, states, states_ld, states_bf16, bf16_ld, obs_dim, capacity, start, idx, B,
+        actions, logp, values, adv, states, states_ld, states_bf16, bf16_ld, obs_dim, capacity, start, d_start, idx, B,
         out_actions, out_logp, out_values, out_adv, out_states, out_states_bf16);
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;

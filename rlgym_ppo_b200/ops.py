@@ -93,6 +93,22 @@ def ring_append(ring, phys_first, src, n_rows, ring_bf16=None):
          work=("byte", int(n_rows) * width * (src.element_size() + 4 + (2 if ring_bf16 is not None else 0))))
 
 
+def ring_append_fields(fields, capacity, phys_first, n_rows):
+    """fields: list of (ring, src, ring_bf16|None).  One launch for all of them."""
+    arr = (_lib.AppendField * len(fields))()
+    nbytes = 0
+    for a, (ring, src, rb) in zip(arr, fields):
+        assert src.dtype in (torch.float32, torch.float64) and src.is_cuda
+        a.ring, a.ring_ld = ring.data_ptr(), (1 if ring.dim() == 1 else ring.stride(0))
+        a.ring_bf16, a.bf16_ld = (None, 0) if rb is None else (rb.data_ptr(), rb.stride(0))
+        a.src, a.src_ld = src.data_ptr(), (1 if src.dim() == 1 else src.stride(0))
+        a.src_is_f64 = int(src.dtype == torch.float64)
+        a.width = 1 if ring.dim() == 1 else ring.shape[1]
+        nbytes += int(n_rows) * (a.width * (src.element_size() + 4) + (0 if rb is None else 2 * rb.stride(0)))
+    call("rlppo_ring_append_fields", ctypes.cast(arr, ctypes.c_void_p), len(fields), int(capacity), int(phys_first),
+         int(n_rows), stream_ptr(), work=("byte", nbytes))
+
+
 def gather_batch(buf, idx, out_actions=None, out_logp=None, out_values=None, out_adv=None, out_states=None,
                  out_states_bf16=None):
     """buf: object with ring tensors (actions, log_probs, values, advantages, states[, states_bf16]),
@@ -101,7 +117,8 @@ def gather_batch(buf, idx, out_actions=None, out_logp=None, out_values=None, out
     sb = getattr(buf, "states_bf16", None)
     call("rlppo_gather_batch", ptr(buf.actions), ptr(buf.log_probs), ptr(buf.values), ptr(buf.advantages),
          ptr(buf.states), buf.states.stride(0) if buf.states is not None and buf.states.dim() == 2 else 1, ptr(sb),
-         0 if sb is None else sb.stride(0), int(buf.obs_dim), int(buf.capacity), int(buf.start), ptr(idx), B,
+         0 if sb is None else sb.stride(0), int(buf.obs_dim), int(buf.capacity), int(buf.start),
+         ptr(getattr(buf, "start_dev", None)), ptr(idx), B,
          ptr(out_actions), ptr(out_logp), ptr(out_values), ptr(out_adv), ptr(out_states), ptr(out_states_bf16),
          stream_ptr(),
          work=("byte", 8 * B + 2 * B * (4 * sum(o is not None for o in (out_actions, out_logp, out_values, out_adv))
@@ -218,11 +235,14 @@ def grad_sqnorm(grads, seg_off, sqnorm):
          work=("byte", 4 * int(so[-1])))
 
 
-def clip_adam(params, grads, m, v, seg_off, sqnorm, lr, step_count, max_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-8):
+def clip_adam(params, grads, m, v, seg_off, sqnorm, lr, step_count, max_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-8,
+              views=None):
+    """views: optional ctypes array of _lib.Bf16View -- bf16 operands refreshed by the same launch."""
     so = _seg(seg_off)
     call("rlppo_clip_adam", ptr(params), ptr(grads), ptr(m), ptr(v), so.ctypes.data, len(so) - 1, ptr(sqnorm), ptr(lr),
-         ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps), stream_ptr(),
-         work=("byte", 28 * int(so[-1])))
+         ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps),
+         None if views is None else ctypes.cast(views, ctypes.c_void_p), 0 if views is None else len(views),
+         stream_ptr(), work=("byte", 28 * int(so[-1])))
 
 
 def sqdiff(a, b, seg_off, out):

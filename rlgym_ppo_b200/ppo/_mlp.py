@@ -83,6 +83,21 @@ class Stack:
         self._seen_version = -1
         self.__dict__.pop("_net_cache", None)
 
+    def bf16_views(self, arena_offset):
+        """rlppo_bf16_view entries (one per Linear) for the fused clip+Adam kernel's in-launch operand refresh."""
+        out, off = [], int(arena_offset)
+        for i, l in enumerate(self.linears):
+            v = _lib.Bf16View()
+            v.offset, v.out_f, v.in_f = off, l.out_features, l.in_features
+            v.wq, v.wq_ld = self.wq[i].data_ptr(), self.wq[i].stride(0)
+            v.wt, v.wt_ld = (None, 0) if self.wt[i] is None else (self.wt[i].data_ptr(), self.wt[i].stride(0))
+            out.append(v)
+            off += l.weight.numel() + l.bias.numel()
+        return out
+
+    def mark_operands_fresh(self):
+        self._seen_version = self.params._version
+
     def operands_stale(self):
         return self.params._version != self._seen_version
 

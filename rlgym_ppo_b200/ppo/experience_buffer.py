@@ -17,6 +17,7 @@ import torch
 from .. import _lib, ops
 from .._staging import Stager
 
+_PERM_POOL = None
 FIELDS = ("states", "actions", "log_probs", "rewards", "next_states", "dones", "truncated", "values", "advantages")
 _WIDE = ("states", "next_states")
 
@@ -52,7 +53,13 @@ class ExperienceBuffer(object):
         self._rings = None
         self.states_bf16 = None
         self._stager = None
-        self._idx_dev = None
+        self.start_dev = None
+        self._spec = None
+        self._pin = [None, None, None]
+        self._pin_ev = [None, None, None]
+        self._pin_i = 0
+        self._pin_of_last = 0
+        self._last_rows = 0
 
     # ---- storage -------------------------------------------------------------------------------------
     def _allocate(self, obs_dim):
@@ -65,6 +72,7 @@ class ExperienceBuffer(object):
             shape = (cap, self.obs_dim) if f in _WIDE else (cap,)
             self._rings[f] = torch.zeros(shape, dtype=torch.float32, device=self.device)
         self.states_bf16 = torch.zeros((cap, self.obs_pad), dtype=torch.bfloat16, device=self.device)
+        self.start_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._stager = Stager(self.device)
 
     def ring(self, field):
@@ -108,13 +116,14 @@ class ExperienceBuffer(object):
         if rows == cap:
             self.start, self.size = 0, 0
         first = (self.start + self.size) % cap
-        for f in FIELDS:
-            src = dev[f][skip:] if skip else dev[f]
-            ops.ring_append(self._rings[f], first, src, rows,
-                            ring_bf16=self.states_bf16 if f == "states" else None)
+        fields = [(self._rings[f], (dev[f][skip:] if skip else dev[f]),
+                   self.states_bf16 if f == "states" else None) for f in FIELDS]
+        ops.ring_append_fields(fields, cap, first, rows)            # all nine rings, one launch
+        self._last_rows = rows
         over = max(0, self.size + rows - cap)
         self.start = (self.start + over) % cap
         self.size = min(cap, self.size + rows)
+        self.start_dev.fill_(self.start)     # device copy of the ring origin (captured graphs read it)
 
     # ---- sampling (experience_buffer.py:82-102) ------------------------------------------------------------
     def _index_tensor(self, indices):
@@ -137,13 +146,71 @@ class ExperienceBuffer(object):
         ops.gather_batch(view, idx, **outs)
 
     def next_permutation(self):
-        """One `self.rng.permutation(total)` (experience_buffer.py:98), NumPy's legacy stream bit for bit."""
-        return _lib.host_permutation(self.rng, self.size)
+        """One `self.rng.permutation(total)` (experience_buffer.py:98), NumPy's legacy stream bit for bit, returned as
+        a PINNED int64 tensor (async upload).
+
+        The draw is a sequential ~1 ms host computation, comparable to the GPU time of a whole example-size iteration,
+        so the NEXT permutation is always computed speculatively on a worker thread (ctypes releases the GIL) from a
+        copy of the generator state, for the buffer length we expect next.  `self.rng` itself only ever advances here, on
+        the caller's thread, when a permutation is handed out: if the speculation guessed the wrong length it is thrown
+        away and the draw is redone, so the stream is the reference's in every case."""
+        total = int(self.size)
+        spec, self._spec = self._spec, None
+        perm = None
+        if spec is not None:
+            fut, spec_total, spec_state = spec
+            out, key, pos = fut.result()
+            st = self.rng.get_state()
+            if spec_total == total and st[2] == spec_state[1] and np.array_equal(st[1], spec_state[0]):
+                self.rng.set_state((st[0], key, pos, st[3], st[4]))
+                perm, self._pin_of_last = out
+        if perm is None:
+            st = self.rng.get_state()
+            (perm, self._pin_of_last), key, pos = self._draw(st[1], st[2], total)
+            self.rng.set_state((st[0], key, pos, st[3], st[4]))
+        self._speculate(total)
+        return perm
+
+    def next_permutation_device(self):
+        """next_permutation() uploaded to the device (async); the pinned buffer is fenced with an event so the
+        speculative draw two calls later cannot overwrite it before the copy engine has read it."""
+        perm = self.next_permutation()
+        dev = perm.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pin_ev[self._pin_of_last] = ev
+        return dev
+
+    def _draw(self, key, pos, total):
+        self._pin_i = (self._pin_i + 1) % 3
+        ev = self._pin_ev[self._pin_i]
+        if ev is not None:
+            ev.synchronize()
+            self._pin_ev[self._pin_i] = None
+        buf = self._pin[self._pin_i]
+        if buf is None or buf.numel() < total:
+            buf = torch.empty(max(total, 1), dtype=torch.int64).pin_memory() if torch.cuda.is_available() \
+                else torch.empty(max(total, 1), dtype=torch.int64)
+            self._pin[self._pin_i] = buf
+        view = buf[:total]
+        _, key, pos = _lib.host_permutation_raw(key, pos, total, out=view.numpy())
+        return (view, self._pin_i), key, pos
+
+    def _speculate(self, total):
+        if total < 4096:
+            return                      # cheaper to draw on demand
+        global _PERM_POOL
+        if _PERM_POOL is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _PERM_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="rlppo-perm")
+        st = self.rng.get_state()
+        key, pos = st[1].copy(), int(st[2])
+        guess = min(self.capacity, total + self._last_rows) if total < self.capacity else total
+        self._spec = (_PERM_POOL.submit(self._draw, key, pos, guess), guess, (key, pos))
 
     def get_all_batches_shuffled(self, batch_size):
         total_samples = self.size
-        indices = self.next_permutation()
-        idx_dev = torch.from_numpy(indices).to(self.device) if total_samples else None
+        idx_dev = self.next_permutation_device()
         start_idx = 0
         while start_idx + batch_size <= total_samples:
             yield self._get_samples(idx_dev[start_idx:start_idx + batch_size])
@@ -162,6 +229,7 @@ class _RingView:
         self.values, self.advantages = r["values"], r["advantages"]
         self.states, self.states_bf16 = r["states"], buf.states_bf16
         self.obs_dim, self.capacity, self.start = buf.obs_dim, buf.capacity, buf.start
+        self.start_dev = buf.start_dev
 
 
 def _make_field_property(name):

@@ -125,6 +125,14 @@ class PPOLearner(object):
         assert batch_size % self.world_size == 0, "batch_size must be a multiple of the number of ranks"
         self._mb = None
         self.launches = 0   # kernels enqueued by the last learn() (bench.py reports it)
+        views = ps.bf16_views(0) + vs.bf16_views(n_p)
+        self._views = (_lib.Bf16View * len(views))(*views)
+        # CUDA graphs: one optimiser step (gather -> fwd/bwd -> clip+Adam) is ~25 launches of 2-170 us kernels; replaying
+        # a captured graph removes the Python/ctypes/driver launch cost that otherwise dominates the example-size nets
+        self.use_cuda_graph = True
+        self._graphs = {}
+        self._graph_warm = set()
+        self._idx_cur = None
 
     # ---- workspaces ----------------------------------------------------------------------------------------
     def _minibatch_buffers(self, rows):
@@ -191,10 +199,50 @@ class PPOLearner(object):
             torch.distributed.all_reduce(self._grads, group=self._pg)   # NCCL sum over NVLink; grads carry 1/B
         ops.grad_sqnorm(self._grads, self._seg, self._sqnorm)           # ppo_learner.py:187-190
         ops.clip_adam(self._params, self._grads, self._m, self._v, self._seg, self._sqnorm, self._lr_dev,
-                      self._steps, max_norm=0.5)                        # :192-193
-        self.policy._stack.refresh_operands(force=True)
-        self.value_net._stack.refresh_operands(force=True)
-        self.launches += 3 + len(self.policy._stack.linears) + len(self.value_net._stack.linears)
+                      self._steps, max_norm=0.5, views=self._views)     # :192-193, + bf16 operand refresh in-launch
+        self.policy._stack.mark_operands_fresh()
+        self.value_net._stack.mark_operands_fresh()
+        self.launches += 4
+
+    def _batch_body(self, exp, idx, local, chunk):
+        self._grads.zero_()                                     # ppo_learner.py:131-132
+        for c0 in range(0, local, chunk):
+            rows = min(chunk, local - c0)
+            self._train_chunk(exp, idx[c0:c0 + rows], rows)
+        self._optimizer_step()
+
+    def _batch_step(self, exp, idx, local, chunk):
+        """One optimiser step on this rank's share `idx` of a batch: eager, or as a replayed CUDA graph."""
+        if not self.use_cuda_graph or self.world_size > 1 or _lib._TIMING is not None:
+            self._batch_body(exp, idx, local, chunk)
+            return
+        if self._idx_cur is None or self._idx_cur.numel() < local:
+            self._idx_cur = torch.empty(local, dtype=torch.int64, device=self._params.device)
+        cur = self._idx_cur[:local]
+        cur.copy_(idx)      # the graph reads its indices from a fixed buffer; the ring origin from exp.start_dev
+        key = (exp.ring("states").data_ptr(), exp.capacity, local, chunk, float(self.clip_range), float(self.ent_coef),
+               self.batch_size, self.policy._stack.fused_ok, self.value_net._stack.fused_ok)
+        entry = self._graphs.get(key)
+        if entry is None:
+            if key not in self._graph_warm:
+                # first step with this configuration runs eagerly: allocates workspaces, configures kernel attributes
+                self._graph_warm.add(key)
+                self._batch_body(exp, cur, local, chunk)
+                return
+            calls0, launches0 = _lib.CALLS, self.launches
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._batch_body(exp, cur, local, chunk)
+            entry = (graph, _lib.CALLS - calls0, self.launches - launches0)
+            self.launches = launches0
+            _lib.CALLS = calls0
+            self._graphs[key] = entry
+        graph, n_calls, n_launch = entry
+        graph.replay()
+        _lib.CALLS += n_calls
+        self.launches += n_launch
+        self.policy._stack.mark_operands_fresh()
+        self.value_net._stack.mark_operands_fresh()
 
     def learn(self, exp):
         """
@@ -215,18 +263,13 @@ class PPOLearner(object):
         chunk = min(local, self.max_chunk_rows)
         for epoch in range(self.n_epochs):
             total = len(exp)
-            perm = exp.next_permutation()                       # experience_buffer.py:98, once per epoch
+            idx_dev = exp.next_permutation_device()             # experience_buffer.py:98, once per epoch
             n_batches = total // B                              # :100, remainder dropped
             if n_batches == 0:
                 continue
-            idx_dev = torch.from_numpy(perm).to(self._params.device, non_blocking=True)
             for k in range(n_batches):
-                self._grads.zero_()                             # :131-132
                 base = k * B + self.rank * local
-                for c0 in range(0, local, chunk):
-                    rows = min(chunk, local - c0)
-                    self._train_chunk(exp, idx_dev[base + c0:base + c0 + rows], rows)
-                self._optimizer_step()
+                self._batch_step(exp, idx_dev[base:base + local], local, chunk)
                 n_iterations += 1
 
         # ---- report: one device -> host readback for the whole call -------------------------------------------

@@ -144,6 +144,7 @@ def test_ppo_learner_golden(pkg, golden):
         orig()
 
     lr._optimizer_step = step
+    lr.use_cuda_graph = False        # the capturing hook above reads tensors back, which a graph capture forbids
     report = lr.learn(buf)
     assert len(captured) == int(g["n_steps"][0])
 
@@ -191,7 +192,8 @@ def test_ppo_learner_golden(pkg, golden):
     sd = lr.policy_optimizer.state_dict()
     assert float(sd["state"][0]["step"]) == float(g["padam.step"][0])
     for i in sd["state"]:
-        assert rel_l2(sd["state"][i]["exp_avg"].cpu().numpy(), g[f"padam.{i}.m"]) < 2e-2
+        # exp_avg is a running mean of the gradients: it inherits their bf16-forward deviation (see above)
+        assert rel_l2(sd["state"][i]["exp_avg"].cpu().numpy(), g[f"padam.{i}.m"]) < 0.15
 
 
 def test_ppo_learner_vs_bf16_oracle(pkg, golden):
@@ -401,3 +403,47 @@ def test_fused_kernels_match_layerwise(pkg, layers, obs, act, M):
     assert (f["a"] == l["a"]).mean() > 0.995
     same = f["a"] == l["a"]
     assert close(f["lp"][same], l["lp"][same], 1e-3)
+
+
+def test_speculative_permutation_stream_is_numpys(pkg):
+    """The permutation is drawn ahead of time on a worker thread; whatever the speculation guessed, the stream handed
+    out must be np.random.RandomState(seed).permutation(len(buffer)), call after call (experience_buffer.py:98)."""
+    from rlgym_ppo_b200.ppo import ExperienceBuffer
+    rng = np.random.RandomState(0)
+    buf = ExperienceBuffer(20000, 77, DEV)
+    ref = np.random.RandomState(77)
+
+    def submit(n):
+        z = np.zeros(n, np.float32)
+        buf.submit_experience(rng.randn(n, 5).astype(np.float32), z, z, z, np.zeros((n, 5), np.float32), z, z, z, z)
+
+    for n in (6000, 6000, 5000, 1, 9000, 4000):          # grows at a changing rate, then wraps (length pinned at capacity)
+        submit(n)
+        for _ in range(3):
+            got = buf.next_permutation_device().cpu().numpy()
+            assert np.array_equal(got, ref.permutation(len(buf)))
+    assert np.array_equal(buf.rng.permutation(11), ref.permutation(11))      # the live RandomState is where NumPy's is
+    buf.rng.seed(5)                                        # user reseeds: a pending speculation must be discarded
+    ref.seed(5)
+    assert np.array_equal(buf.next_permutation().numpy(), ref.permutation(len(buf)))
+    # and the graph-replayed learner consumes the same indices as the eager one (same weights afterwards)
+    import contextlib
+    import io
+    from rlgym_ppo_b200.ppo import PPOLearner
+    outs = []
+    for use_graph in (True, False):
+        torch.manual_seed(1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            lr = PPOLearner(5, 4, 0, (64,), (64,), (0.1, 1.0), 4096, 3, 3e-4, 3e-4, 0.2, 0.01, 4096, DEV)
+        lr.use_cuda_graph = use_graph
+        b = ExperienceBuffer(20000, 9, DEV)
+        r2 = np.random.RandomState(3)
+        for n in (9000, 9000, 9000):
+            b.submit_experience(r2.randn(n, 5).astype(np.float32), r2.randint(0, 4, n).astype(np.float32),
+                                np.full(n, -1.4, np.float32), np.zeros(n, np.float32), np.zeros((n, 5), np.float32),
+                                np.zeros(n, np.float32), np.zeros(n), r2.randn(n).astype(np.float32),
+                                r2.randn(n).astype(np.float32))
+            rep = lr.learn(b)
+        outs.append((lr._params.clone(), rep))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=0, atol=2e-6)
+    assert abs(outs[0][1]["Mean KL Divergence"] - outs[1][1]["Mean KL Divergence"]) < 1e-6
