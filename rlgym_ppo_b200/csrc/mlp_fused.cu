@@ -21,9 +21,13 @@
 //   warps 2..9  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (rows), warps 2-5 the lower half of the columns,
 //               warps 6-9 the upper half.  A k-block of the next A operand is released to the MMA thread as soon as
 //               its columns are written, so GEMM l+1 starts while epilogue l is still running.
-// Two TMEM accumulators (2 x 256 columns) alternate between consecutive GEMMs; two 64 KB activation buffers
-// alternate between A-operand and epilogue-destination roles.
+// TWO tiles are in flight per CTA ("slots"): slot s owns one 64 KB activation buffer and one 256-column TMEM
+// accumulator, and every epilogue overwrites its tile IN PLACE (the GEMM that read the buffer has completed by then).
+// The MMA thread and the epilogue warps both walk (phase 0, slot 0), (phase 0, slot 1), (phase 1, slot 0), ... so the
+// tensor core (and the L2 latency of the weight stream) works on one tile while the epilogue warps work on the other.
+// ncu on the first, one-tile version showed the epilogue warps waiting on the accumulator barrier ~40 % of the time.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -46,24 +50,23 @@ constexpr uint32_t OFF_ACT_A = 0;
 constexpr uint32_t OFF_ACT_B = ACT_BYTES;
 constexpr uint32_t OFF_WRING = 2 * ACT_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_WRING + NWST * WST_BYTES;          // (MAXL + 1) * 256 floats
-constexpr uint32_t OFF_ROWX = OFF_BIAS + (MAXL + 1) * 256 * 4;      // 2 * 128 floats
-constexpr uint32_t OFF_BARS = OFF_ROWX + 2 * 128 * 4;
+constexpr uint32_t OFF_ROWX = OFF_BIAS + (MAXL + 1) * 256 * 4;      // [slot][half][128] floats
+constexpr uint32_t ROWX_FLOATS = 2048;                               // per slot: row-wise exchange planes
+constexpr uint32_t OFF_DB = OFF_ROWX + 2 * ROWX_FLOATS * 4;          // (MAXL + 1) * 256 floats: column-sum accumulators
+constexpr uint32_t OFF_BARS = OFF_DB + (MAXL + 1) * 256 * 4;   // 2*NWST + 2 + 2 + 8 + 2 mbarriers, TMEM slot
 constexpr uint32_t SMEM_TOTAL = OFF_BARS + 256 + 1024;              // + slack for 1024-byte alignment
 
-enum { PH_FWD = 0, PH_FWD_VALUE = 1, PH_HEAD = 2, PH_DGRAD = 3 };
+enum { PH_FWD = 0, PH_FWD_VALUE = 1, PH_HEAD = 2, PH_DGRAD = 3, PH_VALUE_BWD = 4 };
+constexpr uint8_t NO_STORE = 0xFF;
 
-struct StoreDesc {
-    uint8_t map, buf, n_kb, pad;
-};
 struct PhaseDesc {
-    uint8_t kind;      // PH_*
-    uint8_t layer;     // FWD: hidden index (0-based) of the layer produced; DGRAD: hidden index whose ReLU mask applies
-    uint8_t src;       // A-operand buffer: 0 = A, 1 = B (the epilogue writes the other one)
-    uint8_t n_kb;      // k-blocks of the contraction
-    uint16_t N;        // accumulator columns = rows of the weight box (multiple of 16, <= 256)
-    uint8_t wmap;      // index into Maps::w
-    uint8_t n_store;   // tiles of the PREVIOUS epilogue to store while this phase's MMAs are issued
-    StoreDesc st[2];
+    uint8_t kind;       // PH_*
+    uint8_t layer;      // FWD: hidden index (0-based) of the layer produced; DGRAD/VALUE_BWD: hidden index whose ReLU mask applies
+    uint8_t n_kb;       // k-blocks of the contraction (0: no GEMM, PH_VALUE_BWD)
+    uint8_t wmap;       // index into Maps::w
+    uint16_t N;         // accumulator columns = rows of the weight box (multiple of 16, <= 256)
+    uint8_t store_map;  // tile written by the PREVIOUS epilogue, TMA-stored while this phase's MMAs are issued (or NO_STORE)
+    uint8_t store_kb;   // its k-blocks
 };
 
 struct alignas(64) Maps {
@@ -77,8 +80,7 @@ struct Params {
     int num_tiles, n_ph, L, in_kb;
     int H[MAXL];
     PhaseDesc ph[MAXPH];
-    int n_tail_store;
-    StoreDesc tail[2];
+    int tail_map, tail_kb;   // the last epilogue's tile
     const float* bias[MAXL + 1];
     float* gbias[MAXL + 1];
     // policy head
@@ -97,6 +99,7 @@ struct Params {
     float* gw_head;
     float* values_out;
     float* metrics;
+    unsigned long long* trace;   // debug (RLPPO_FUSED_TRACE=1): clock64 stamps of CTA 0, [role][event]
 };
 
 // ---- small PTX helpers local to this kernel -------------------------------------------------------------------
@@ -137,6 +140,21 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
+// 16-column variant: lanes l and l^16 both return the sum over the 32 lanes of v[l & 15]
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = up ? v[i] : v[i + w];
+            const float keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 __device__ __forceinline__ float bf16_round(float x) { return bf16_bits_to_f32(f32_to_bf16_bits(x)); }
 // two floats -> packed bf16x2 in ONE instruction (cvt.rn.bf16x2.f32; `lo` lands in the low half)
 __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
@@ -160,6 +178,27 @@ __device__ __forceinline__ void store_chunk_sw128(uint8_t* buf, int row, int chu
     }
 }
 
+#define RLPPO_TRACE(role, idx)                                                                  \
+    do {                                                                                        \
+        const int _i = (idx);                                                                   \
+        if (p.trace != nullptr && blockIdx.x == 0 && _i < 512) p.trace[(role) * 512 + _i] = clock64(); \
+    } while (0)
+
+// write 16 consecutive columns [16*chunk16, +16) of one row into a K-major SWIZZLE_128B activation tile
+__device__ __forceinline__ void store_chunk16_sw128(uint8_t* buf, int row, int chunk16, const float (&v)[16]) {
+    uint8_t* kb = buf + (chunk16 >> 2) * KB_BYTES + row * 128;
+    const int base16 = (chunk16 & 3) * 2;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        uint4 o;
+        o.x = cvt_bf16x2(v[t * 8 + 0], v[t * 8 + 1]);
+        o.y = cvt_bf16x2(v[t * 8 + 2], v[t * 8 + 3]);
+        o.z = cvt_bf16x2(v[t * 8 + 4], v[t * 8 + 5]);
+        o.w = cvt_bf16x2(v[t * 8 + 6], v[t * 8 + 7]);
+        *reinterpret_cast<uint4*>(kb + (((base16 + t) ^ (row & 7)) << 4)) = o;
+    }
+}
+
 struct EpiCtx {
     uint8_t* smem;
     float* s_bias;
@@ -169,40 +208,31 @@ struct EpiCtx {
     int lane, quarter, half, row_in_tile;
 };
 
-// arrive on the a_ready barriers of the k-blocks this warp does not write (keeps every barrier at one phase per GEMM)
-__device__ __forceinline__ void release_untouched(const EpiCtx& e, int c0, int c1) {
-    if (e.lane == 0) {
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-            const int lo = max(c0, 2 * kb), hi = min(c1, 2 * kb + 2);
-            if (lo >= hi) mbar_arrive(&e.a_ready[kb]);
-        }
-    }
-}
-// called after chunk c was written: if it is this warp's last chunk inside its k-block, publish the k-block
-__device__ __forceinline__ void release_after_chunk(const EpiCtx& e, int c, int c1) {
-    const int kb = c >> 1;
-    if (c == min(c1, 2 * kb + 2) - 1) {
-        tc_fence_before();
-        fence_proxy_async();
-        __syncwarp();
-        if (e.lane == 0) mbar_arrive(&e.a_ready[kb]);
-    }
+// End of an epilogue phase for this warp: its TMEM reads are done and its part of the tile is written.  One arrival
+// per warp on the slot's a_ready barrier; the MMA thread may then overwrite the accumulator and read the tile.
+// (A per-k-block release that let the next GEMM start early was tried first: with ONE accumulator per slot it lets the
+// next GEMM overwrite accumulator columns this epilogue has not read yet.)
+__device__ __forceinline__ void release_all(const EpiCtx& e) {
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (e.lane == 0) mbar_arrive(e.a_ready);
 }
 
 template <bool POLICY, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_constant__ Maps maps, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* act[2] = {smem + OFF_ACT_A, smem + OFF_ACT_B};
+    uint8_t* act[2] = {smem + OFF_ACT_A, smem + OFF_ACT_B};   // one buffer per slot
     float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     float* s_rowx = reinterpret_cast<float*>(smem + OFF_ROWX);
+    float* s_db = reinterpret_cast<float*>(smem + OFF_DB);
     uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
     uint64_t* wempty = wfull + NWST;
-    uint64_t* x_full = wempty + NWST;
-    uint64_t* x_free = x_full + 1;
-    uint64_t* a_ready = x_free + 1;   // [4]
-    uint64_t* acc_full = a_ready + 4; // [2]
+    uint64_t* x_full = wempty + NWST;   // [2]
+    uint64_t* x_free = x_full + 2;      // [2]
+    uint64_t* a_ready = x_free + 2;     // [2]: one per slot, 8 arrivals (epilogue warps)
+    uint64_t* acc_full = a_ready + 2;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -212,11 +242,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             mbar_init(&wfull[i], 1);
             mbar_init(&wempty[i], 1);
         }
-        mbar_init(x_full, 1);
-        mbar_init(x_free, 1);
-        for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
-        mbar_init(&acc_full[0], 1);
-        mbar_init(&acc_full[1], 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&x_full[s], 1);
+            mbar_init(&x_free[s], 1);
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&a_ready[s], 8);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -234,31 +265,40 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             }
         }
         s_bias[i] = b;
+        s_db[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // tiles of this CTA: blockIdx.x + k * gridDim.x; pair `it` holds k = 2*it (slot 0) and 2*it + 1 (slot 1)
+    const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_pairs = (my_tiles + 1) >> 1;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t ws = 0, wpar = 0, xpar = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                mbar_wait(x_free, xpar ^ 1);
-                mbar_expect_tx(x_full, p.in_kb * KB_BYTES);
-                for (int kb = 0; kb < p.in_kb; ++kb)
-                    tma_load_2d(&maps.x, x_full, act[1] + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                xpar ^= 1;
+            uint32_t ws = 0, wpar = 0;
+            for (int it = 0; it < n_pairs; ++it) {
+                const int ns = (2 * it + 1 < my_tiles) ? 2 : 1;
+                for (int sl = 0; sl < ns; ++sl) {
+                    const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
+                    mbar_wait(&x_free[sl], (it & 1) ^ 1);
+                    mbar_expect_tx(&x_full[sl], p.in_kb * KB_BYTES);
+                    for (int kb = 0; kb < p.in_kb; ++kb)
+                        tma_load_2d(&maps.x, &x_full[sl], act[sl] + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
+                }
                 for (int ph = 0; ph < p.n_ph; ++ph) {
                     const PhaseDesc& d = p.ph[ph];
-                    for (int kb = 0; kb < d.n_kb; ++kb) {
-                        mbar_wait(&wempty[ws], wpar ^ 1);
-                        mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
-                        tma_load_2d(&maps.w[d.wmap], &wfull[ws], smem + OFF_WRING + ws * WST_BYTES, kb * KBLK, 0);
-                        if (++ws == NWST) {
-                            ws = 0;
-                            wpar ^= 1;
+                    for (int sl = 0; sl < ns; ++sl) {
+                        for (int kb = 0; kb < d.n_kb; ++kb) {
+                            mbar_wait(&wempty[ws], wpar ^ 1);
+                            mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
+                            tma_load_2d(&maps.w[d.wmap], &wfull[ws], smem + OFF_WRING + ws * WST_BYTES, kb * KBLK, 0);
+                            if (++ws == NWST) {
+                                ws = 0;
+                                wpar ^= 1;
+                            }
                         }
                     }
                 }
@@ -267,84 +307,75 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer + TMA stores =====================
         if (lane == 0) {
-            uint32_t ws = 0, wpar = 0, xpar = 0, g = 0, acount = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int ph = 0; ph < p.n_ph; ++ph, ++g) {
+            uint32_t ws = 0, wpar = 0;
+            uint32_t gcount[2] = {0, 0};   // GEMM phases issued per slot  -> acc_full parity on the consumer side
+            uint32_t acount[2] = {0, 0};   // epilogue completions consumed per slot -> a_ready parity
+            int tr0 = 0;
+            for (int it = 0; it < n_pairs; ++it) {
+                const int ns = (2 * it + 1 < my_tiles) ? 2 : 1;
+#pragma unroll 1
+                for (int ph = 0; ph < p.n_ph; ++ph) {
                     const PhaseDesc& d = p.ph[ph];
-                    const uint32_t acc = g & 1;
-                    const uint32_t d_tmem = tmem_base + acc * 256;
                     const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, 0);
-                    const uint32_t apar = acount & 1;
-                    if (ph == 0) {
-                        mbar_wait(x_full, xpar);
-                        xpar ^= 1;
+#pragma unroll 1
+                    for (int sl = 0; sl < ns; ++sl) {
+                        const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
+                        const uint32_t d_tmem = tmem_base + sl * 256;
+                        if (ph == 0) {
+                            mbar_wait(&x_full[sl], it & 1);
+                        } else {
+                            mbar_wait(&a_ready[sl], acount[sl] & 1);   // previous epilogue of this slot: tile written,
+                            ++acount[sl];                              // accumulator free
+                        }
                         tc_fence_after();
-                    }
-                    uint32_t waited = 0;
-                    for (int kb = 0; kb < d.n_kb; ++kb) {
-                        if (ph > 0) {
-                            mbar_wait(&a_ready[kb], apar);
-                            waited |= 1u << kb;
-                            tc_fence_after();
-                            if (TRAIN) {
-                                for (int s = 0; s < d.n_store; ++s)
-                                    if (d.st[s].buf == d.src && kb < d.st[s].n_kb)
-                                        tma_store_2d(&maps.out[d.st[s].map], act[d.src] + kb * KB_BYTES, kb * KBLK,
-                                                     tile * TILE_M);
-                            }
-                        }
-                        mbar_wait(&wfull[ws], wpar);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(act[d.src] + kb * KB_BYTES);
-                        const uint32_t b_addr = smem_u32(smem + OFF_WRING + ws * WST_BYTES);
-#pragma unroll
-                        for (int k = 0; k < KBLK / 16; ++k) {
-                            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-                            const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
-                            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                        }
-                        umma_commit(&wempty[ws]);
-                        if (++ws == NWST) {
-                            ws = 0;
-                            wpar ^= 1;
-                        }
-                    }
-                    if (ph > 0) {
-                        if (TRAIN && d.n_store > 0) {
-                            // tiles not covered above: other buffer, or more k-blocks than this GEMM contracts over
-                            for (int s = 0; s < d.n_store; ++s) {
-                                const StoreDesc& sd = d.st[s];
-                                for (int kb = 0; kb < sd.n_kb; ++kb) {
-                                    if (sd.buf == d.src && kb < d.n_kb) continue;
-                                    if (!(waited & (1u << kb))) {
-                                        mbar_wait(&a_ready[kb], apar);
-                                        waited |= 1u << kb;
-                                    }
-                                    tma_store_2d(&maps.out[sd.map], act[sd.buf] + kb * KB_BYTES, kb * KBLK,
-                                                 tile * TILE_M);
-                                }
-                            }
+                        RLPPO_TRACE(0, tr0++);   // MMA: inputs of (ph, slot) ready
+                        const bool storing = TRAIN && ph > 0 && d.store_map != NO_STORE;
+                        if (storing) {
+                            for (int kb = 0; kb < d.store_kb; ++kb)
+                                tma_store_2d(&maps.out[d.store_map], act[sl] + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
                             bulk_commit();
                         }
-                        ++acount;
+                        for (int kb = 0; kb < d.n_kb; ++kb) {
+                            mbar_wait(&wfull[ws], wpar);
+                            tc_fence_after();
+                            const uint32_t a_addr = smem_u32(act[sl] + kb * KB_BYTES);
+                            const uint32_t b_addr = smem_u32(smem + OFF_WRING + ws * WST_BYTES);
+#pragma unroll
+                            for (int k = 0; k < KBLK / 16; ++k) {
+                                const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+                                const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+                                umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&wempty[ws]);
+                            if (++ws == NWST) {
+                                ws = 0;
+                                wpar ^= 1;
+                            }
+                        }
+                        RLPPO_TRACE(0, tr0++);   // MMA: all MMAs of (ph, slot) issued
+                        if (storing) bulk_wait_read_all();   // this phase's epilogue overwrites the tile in place
+                        RLPPO_TRACE(0, tr0++);   // MMA: stores have left shared memory
+                        if (d.n_kb > 0) {
+                            umma_commit(&acc_full[sl]);
+                        } else {
+                            mbar_arrive(&acc_full[sl]);   // GEMM-less phase: the previous accumulator is still in TMEM
+                        }
+                        ++gcount[sl];
                     }
-                    if (TRAIN) bulk_wait_read_all();   // the epilogue of this GEMM may overwrite either buffer
-                    umma_commit(&acc_full[acc]);
                 }
-                // tail: the last epilogue's tiles, then hand buffer B back to the producer for the next x tile
-                {
-                    const uint32_t apar = acount & 1;
-                    for (int kb = 0; kb < 4; ++kb) mbar_wait(&a_ready[kb], apar);
-                    ++acount;
+                // tails: the last epilogue's tile of each slot, then hand the buffer back to the producer
+                for (int sl = 0; sl < ns; ++sl) {
+                    const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
+                    mbar_wait(&a_ready[sl], acount[sl] & 1);
+                    ++acount[sl];
+                    tc_fence_after();
                     if (TRAIN) {
-                        for (int s = 0; s < p.n_tail_store; ++s)
-                            for (int kb = 0; kb < p.tail[s].n_kb; ++kb)
-                                tma_store_2d(&maps.out[p.tail[s].map], act[p.tail[s].buf] + kb * KB_BYTES, kb * KBLK,
-                                             tile * TILE_M);
+                        for (int kb = 0; kb < p.tail_kb; ++kb)
+                            tma_store_2d(&maps.out[p.tail_map], act[sl] + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
                         bulk_commit();
                         bulk_wait_read_all();
                     }
-                    mbar_arrive(x_free);
+                    mbar_arrive(&x_free[sl]);
                 }
             }
         }
@@ -361,107 +392,74 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         e.half = (warp - 2) >> 2;
         e.row_in_tile = e.quarter * 32 + lane;
 
-        uint32_t relu[MAXL][4];
-        float dbacc[MAXL + 1][4];
-        float dwacc[4];
-#pragma unroll
-        for (int l = 0; l < MAXL; ++l)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) relu[l][j] = 0u;
-#pragma unroll
-        for (int l = 0; l <= MAXL; ++l)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dbacc[l][j] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dwacc[j] = 0.f;
+        // ReLU masks of this thread's row (per slot, layer, chunk): a dynamically indexed local array -- one LDL/STL per
+        // chunk.  (Register arrays read through predicated selects cost 32 selects per chunk and 32 registers.)
+        uint32_t relu[2 * MAXL * 4];
+        float dv_keep[2] = {0.f, 0.f};  // value net: d(loss)/dv of this thread's row, kept from the forward tail
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, mrows = 0.f;   // metric partial sums of this thread's rows
+        // column sums (bias gradients, value-head weight gradient) accumulate in shared memory: lane j of a warp holds the
+        // partial sum of column 32c + j over the warp's 32 rows; four warps (row quarters) add into the same word
+        auto db_add = [&](int l, int c, float v) { atomicAdd(&s_db[l * 256 + c * 32 + e.lane], v); };
 
-        // The chunk loops below are deliberately NOT unrolled and take the layer as a run-time index (register arrays
-        // are read/written through predicated selects): the first version specialised every (layer, chunk) pair and
-        // grew to 30k instructions (480 KB), and ncu showed the epilogue warps stalled on instruction fetch
-        // (stall_no_inst = half of all samples).
-        auto relu_get = [&](int l, int j) {
-            uint32_t v = 0u;
-#pragma unroll
-            for (int a = 0; a < MAXL; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) v = (a == l && b == j) ? relu[a][b] : v;
-            return v;
-        };
-        auto relu_set = [&](int l, int j, uint32_t v) {
-#pragma unroll
-            for (int a = 0; a < MAXL; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) relu[a][b] = (a == l && b == j) ? v : relu[a][b];
-        };
-        auto db_add = [&](int l, int j, float v) {
-#pragma unroll
-            for (int a = 0; a <= MAXL; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) dbacc[a][b] += (a == l && b == j) ? v : 0.f;
-        };
-        auto dw_add = [&](int j, float v) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) dwacc[b] += (b == j) ? v : 0.f;
-        };
-
-        uint32_t g = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
-            const bool row_ok = row < p.M;
-            for (int ph = 0; ph < p.n_ph; ++ph, ++g) {
-                const PhaseDesc& d = p.ph[ph];
-                const uint32_t acc = g & 1;
-                mbar_wait(&acc_full[acc], (g >> 1) & 1);
+        uint32_t gcount[2] = {0, 0};
+        int tr1 = 0;
+        for (int it = 0; it < n_pairs; ++it) {
+          const int ns = (2 * it + 1 < my_tiles) ? 2 : 1;
+#pragma unroll 1
+          for (int ph = 0; ph < p.n_ph; ++ph) {
+            const PhaseDesc& d = p.ph[ph];
+#pragma unroll 1
+            for (int sl = 0; sl < ns; ++sl) {
+                const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
+                const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
+                const bool row_ok = row < p.M;
+                mbar_wait(&acc_full[sl], gcount[sl] & 1);
+                ++gcount[sl];
                 tc_fence_after();
-                const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + acc * 256;
-                uint8_t* dst = act[d.src ^ 1];
-                uint8_t* srcb = act[d.src];
+                if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: accumulator of (ph, slot) complete
+                const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + sl * 256;
+                uint8_t* dst = act[sl];      // in place: the GEMM that read this tile has completed
+                e.a_ready = a_ready + sl;
                 const int li = d.layer;
 
                 if (d.kind == PH_FWD || d.kind == PH_FWD_VALUE) {
                     const int nc = d.N >> 5;
                     const int c0 = e.half * (nc >> 1), c1 = c0 + (nc >> 1);
                     const bool tail = (d.kind == PH_FWD_VALUE);
-                    if (!tail) release_untouched(e, c0, c1);
-                    float dot = 0.f;
+                    float dq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
                     for (int c = c0; c < c1; ++c) {
                         float v[32];
                         tmem_ld32(trow + c * 32, v);
                         const float* sb = s_bias + li * 256 + c * 32;
-                        uint32_t bits = 0u;
+                        uint32_t bq[4] = {0u, 0u, 0u, 0u};   // four independent OR chains (one 32-long chain serialises)
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float xv = fmaxf(v[i] + sb[i], 0.f);
-                            bits |= (xv > 0.f ? 1u : 0u) << i;
+                            bq[i & 3] |= (xv > 0.f ? 1u : 0u) << i;
                             v[i] = xv;
                         }
-                        if (TRAIN) relu_set(li, c - c0, bits);
+                        const uint32_t bits = (bq[0] | bq[1]) | (bq[2] | bq[3]);
+                        if (TRAIN) relu[(sl * MAXL + li) * 4 + (c - c0)] = bits;
                         if (tail) {
                             const float* wv = s_bias + MAXL * 256 + c * 32;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) dot = fmaf(bf16_round(v[i]), wv[i], dot);
+                            for (int i = 0; i < 32; ++i) dq[i & 3] = fmaf(bf16_round(v[i]), wv[i], dq[i & 3]);
                         }
                         if (!tail) {
                             store_chunk_sw128(dst, e.row_in_tile, c, v);
-                            release_after_chunk(e, c, c1);
                         } else if (TRAIN) {
                             store_chunk_sw128(dst, e.row_in_tile, c, v);
                         }
                     }
                     if (tail) {
                         // ---- value head: v = H_L . w + b (value_estimator.py:27), MSE loss and its gradient ----
-                        e.s_rowx[e.half * 128 + e.row_in_tile] = dot;
+                        float* rowx = e.s_rowx + sl * ROWX_FLOATS;   // per slot: the other slot's tail may run concurrently
+                        rowx[e.half * 128 + e.row_in_tile] = (dq[0] + dq[1]) + (dq[2] + dq[3]);
                         epi_bar_sync();
                         const float bhead = p.bias[MAXL] != nullptr ? __ldg(p.bias[MAXL]) : 0.f;
-                        const float val = e.s_rowx[e.row_in_tile] + e.s_rowx[128 + e.row_in_tile] + bhead;
+                        const float val = rowx[e.row_in_tile] + rowx[128 + e.row_in_tile] + bhead;
                         if (e.half == 0 && row_ok && p.values_out != nullptr) p.values_out[row] = val;
-                        if (!TRAIN) {
-                            tc_fence_before();
-                            __syncwarp();
-                            release_untouched(e, 0, 0);   // nothing written: hand every k-block barrier back
-                        }
                         if (TRAIN) {
                             float dv = 0.f;
                             if (row_ok) {
@@ -473,99 +471,209 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                     m1 += dv;                                      // head bias gradient
                                 }
                             }
-                            release_untouched(e, c0, c1);
-#pragma unroll 1
-                            for (int c = c0; c < c1; ++c) {
-                                float v[32], t[32];
-                                tmem_ld32(trow + c * 32, v);
-                                const float* sb = s_bias + li * 256 + c * 32;
-                                const float* wv = s_bias + MAXL * 256 + c * 32;
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const float h = bf16_round(fmaxf(v[i] + sb[i], 0.f));
-                                    t[i] = dv * h;
-                                    v[i] = h > 0.f ? dv * wv[i] : 0.f;
-                                }
-                                dw_add(c - c0, warp_colsum32(t, e.lane));
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) t[i] = v[i];
-                                db_add(li, c - c0, warp_colsum32(t, e.lane));
-                                store_chunk_sw128(srcb, e.row_in_tile, c, v);
-                                release_after_chunk(e, c, c1);
-                            }
+                            dv_keep[0] = sl == 0 ? dv : dv_keep[0];
+                            dv_keep[1] = sl == 1 ? dv : dv_keep[1];
+                            // H_L is complete in shared memory: it is TMA-stored by the next, GEMM-less phase, whose
+                            // epilogue then overwrites it with dL/dH_L
                         }
                     }
-                } else if (d.kind == PH_DGRAD) {
+                } else if (d.kind == PH_VALUE_BWD) {
+                    // dL/dH_L = dv * w (.) relu'(H_L), dw_head += dv * H_L, db_L: re-reads the accumulator of the last
+                    // forward GEMM, which is still in this slot's TMEM columns
                     const int nc = d.N >> 5;
                     const int c0 = e.half * (nc >> 1), c1 = c0 + (nc >> 1);
-                    release_untouched(e, c0, c1);
+                    const float dv = sl == 0 ? dv_keep[0] : dv_keep[1];
 #pragma unroll 1
                     for (int c = c0; c < c1; ++c) {
                         float v[32], t[32];
                         tmem_ld32(trow + c * 32, v);
-                        const uint32_t bits = relu_get(li, c - c0);
+                        const float* sb = s_bias + li * 256 + c * 32;
+                        const float* wv = s_bias + MAXL * 256 + c * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float h = bf16_round(fmaxf(v[i] + sb[i], 0.f));
+                            t[i] = dv * h;
+                            v[i] = h > 0.f ? dv * wv[i] : 0.f;
+                        }
+                        db_add(MAXL, c, warp_colsum32(t, e.lane));     // value head weight gradient (slot MAXL)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t[i] = v[i];
+                        db_add(li, c, warp_colsum32(t, e.lane));
+                        store_chunk_sw128(dst, e.row_in_tile, c, v);
+                    }
+                } else if (d.kind == PH_DGRAD) {
+                    const int nc = d.N >> 5;
+                    const int c0 = e.half * (nc >> 1), c1 = c0 + (nc >> 1);
+#pragma unroll 1
+                    for (int c = c0; c < c1; ++c) {
+                        float v[32], t[32];
+                        tmem_ld32(trow + c * 32, v);
+                        const uint32_t bits = relu[(sl * MAXL + li) * 4 + (c - c0)];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
                             t[i] = v[i];
                         }
-                        db_add(li, c - c0, warp_colsum32(t, e.lane));
+                        db_add(li, c, warp_colsum32(t, e.lane));
                         store_chunk_sw128(dst, e.row_in_tile, c, v);
-                        release_after_chunk(e, c, c1);
                     }
                 } else {
                     // ---- policy head (discrete_policy.py:44-80, ppo_learner.py:153-177) ----
-                    // one thread = one row; the logits stay in TMEM and are re-read chunk by chunk in each pass (a TMEM
-                    // load is cheaper than the code size of keeping 128 logits in registers).  The upper-half warps have
-                    // nothing to do in this phase.
+                    // Two threads per row: the warp pair that owns the row's TMEM lanes splits every 32-column chunk into
+                    // its lower / upper 16 columns; the row-wise quantities (max, sum-exp, ...) are combined through shared
+                    // memory.  Three branch-free passes re-read the logits from TMEM.  (History, from the cycle trace of this
+                    // kernel: one thread per row with a data-dependent `if` per element: 42k cycles per tile; branch-free,
+                    // 3 passes: 15.6k; the other epilogues take ~3k.)
                     const int nact = p.n_actions;
                     const int nch = (nact + 31) >> 5;          // <= 4
                     const int nch_out = p.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
-                    if (e.half == 1) {
-                        release_untouched(e, 0, 0);
+                    const int hoff = e.half * 16;              // this thread's 16 columns inside each chunk
+                    const float* sb = s_bias + MAXL * 256;
+                    const float kLogMin = -25.328436022934504f;   // ln(1e-11)
+                    float* xch = e.s_rowx + sl * ROWX_FLOATS;     // per-slot exchange planes: [0,256) max, [512,768) argmax, [1024,1792) S/T/z_a
+                    int a = 0;
+                    float old_lp = 0.f, advv = 0.f;
+                    if (TRAIN && row_ok) {
+                        a = (int)__ldg(p.actions + row);             // acts.long(), discrete_policy.py:71
+                        a = min(max(a, 0), nact - 1);
+                        old_lp = __ldg(p.old_logp + row);
+                        advv = __ldg(p.adv + row);
+                    }
+                    // pass 1: row maximum (+ argmax for the deterministic branch)
+                    float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    int aq[4] = {0, 0, 0, 0};
+#pragma unroll 1
+                    for (int c = 0; c < nch; ++c) {
+                        float v[16];
+                        tmem_ld16(trow + c * 32 + hoff, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int col = c * 32 + hoff + i;
+                            const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
+                            const bool gt = zz > mq[i & 3];
+                            mq[i & 3] = gt ? zz : mq[i & 3];
+                            aq[i & 3] = gt ? col : aq[i & 3];
+                        }
+                    }
+                    float mx = mq[0];
+                    int argmax = aq[0];
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) {
+                        const bool better = mq[q] > mx || (mq[q] == mx && aq[q] < argmax);   // ties: lowest column
+                        mx = better ? mq[q] : mx;
+                        argmax = better ? aq[q] : argmax;
+                    }
+                    xch[e.half * 128 + e.row_in_tile] = mx;
+                    int* xchi = reinterpret_cast<int*>(xch) + 512;   // second plane: argmax (ints), see OFF_ROWX sizing
+                    xchi[e.half * 128 + e.row_in_tile] = argmax;
+                    epi_bar_sync();
+                    {
+                        const float mo = xch[(e.half ^ 1) * 128 + e.row_in_tile];
+                        const int ao = xchi[(e.half ^ 1) * 128 + e.row_in_tile];
+                        const bool better = mo > mx || (mo == mx && ao < argmax);
+                        mx = better ? mo : mx;
+                        argmax = better ? ao : argmax;
+                    }
+                    epi_bar_sync();   // everyone has read the maxima before the plane is reused
+                    // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
+                    float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
+                    float zs_a = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < nch; ++c) {
+                        float v[16];
+                        tmem_ld16(trow + c * 32 + hoff, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int col = c * 32 + hoff + i;
+                            const float zs = col < nact ? v[i] + sb[col] - mx : -INFINITY;
+                            const float ej = __expf(zs);                      // exp(-inf) = 0 for the padding
+                            Sq[i & 3] += ej;
+                            Tq[i & 3] = fmaf(ej, col < nact ? zs : 0.f, Tq[i & 3]);
+                            zs_a += col == a ? zs : 0.f;                      // exactly one of the two threads holds column a
+                        }
+                    }
+                    float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
+                    float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
+                    {
+                        float* x3 = xch + 1024;   // [3][half][row]
+                        x3[0 * 256 + e.half * 128 + e.row_in_tile] = S;
+                        x3[1 * 256 + e.half * 128 + e.row_in_tile] = T;
+                        x3[2 * 256 + e.half * 128 + e.row_in_tile] = zs_a;
+                        epi_bar_sync();
+                        const int o = (e.half ^ 1) * 128 + e.row_in_tile;
+                        // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
+                        const float S0 = e.half == 0 ? S : x3[o], S1 = e.half == 0 ? x3[o] : S;
+                        const float T0 = e.half == 0 ? T : x3[256 + o], T1 = e.half == 0 ? x3[256 + o] : T;
+                        S = S0 + S1;
+                        T = T0 + T1;
+                        zs_a += x3[512 + o];
+                    }
+                    const float logS = logf(S);
+                    const float mxs = mx + logS;
+                    if (TRAIN) {
+                        // Entropy of the CLAMPED probabilities (discrete_policy.py:74-78) from the two sums:
+                        //   -sum s_j log s_j = logS - T/S.  Clamping to [1e-11, 1] changes each term by at most
+                        //   1e-11 * ln(1e11) = 2.5e-10, i.e. below fp32 resolution of the sum; the clamp's effect on the
+                        //   GRADIENT (zero outside the range) is applied exactly in pass 3.
+                        const float Hent = logS - T / S;
+                        const float Gs = 1.0f - Hent;                       // sum_j s_j (log s_j + 1)
+                        const float ls_a = zs_a - logS;
+                        const float lp_a = fminf(fmaxf(ls_a, kLogMin), 0.f);   // log clamp(s_a, 1e-11, 1), :74-77
+                        const float s_a = __expf(ls_a);
+                        const float p_a = fminf(fmaxf(s_a, 1e-11f), 1.0f);
+                        const float log_ratio = lp_a - old_lp;
+                        const float ratio = expf(log_ratio);                            // ppo_learner.py:153
+                        const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
+                        const float clipped = fminf(fmaxf(ratio, lo), hi);              // :154-156
+                        const float s1 = ratio * advv, s2 = clipped * advv;
+                        const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+                        const float d1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);      // torch.min backward, ties 0.5/0.5
+                        const float d2 = s1 > s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
+                        const float okf = row_ok ? 1.f : 0.f;
+                        const float d_logp = -p.inv_batch * advv * (d1 + d2 * in_range) * ratio * okf;
+                        const float ga = (ls_a >= kLogMin) ? d_logp / p_a : 0.f;        // through log(clamp(s_a))
+                        const float cw = p.ent_coef * p.inv_batch * okf;
+                        const float G = cw * Gs + ga * s_a;
+                        if (row_ok && e.half == 0) {
+                            m0 += Hent;
+                            m1 += (ratio - 1.0f) - log_ratio;                           // :161
+                            m2 += fabsf(ratio - 1.0f) > p.clip ? 1.f : 0.f;             // :166
+                            m3 += fminf(s1, s2);
+                            mrows += 1.f;
+                            if (p.logp_out) p.logp_out[row] = lp_a;
+                        }
+                        // pass 3: dz_j = s_j (g_j - G) -> bf16 tile (A operand of the first dgrad GEMM) + head bias grads
+#pragma unroll 1
+                        for (int c = 0; c < nch_out; ++c) {
+                            float v[16], t[16];
+                            if (c < nch) {
+                                tmem_ld16(trow + c * 32 + hoff, v);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int col = c * 32 + hoff + i;
+                                const bool in = col < nact;
+                                const float ls = in ? v[i] + sb[col & 255] - mxs : -INFINITY;   // log softmax (<= 0)
+                                const float sj = __expf(ls);                                    // 0 for the padding
+                                const float lp = fminf(fmaxf(ls, kLogMin), 0.f);
+                                float gj = fmaf(cw, lp + 1.0f, col == a ? ga : 0.f);
+                                gj = ls >= kLogMin ? gj : 0.f;          // clamp passes gradient inside [1e-11, 1] only
+                                const float o = in ? sj * (gj - G) : 0.f;
+                                v[i] = o;
+                                t[i] = o;
+                            }
+                            const float cs = warp_colsum16(t, e.lane);
+                            if (e.lane < 16) atomicAdd(&s_db[MAXL * 256 + c * 32 + hoff + e.lane], cs);
+                            store_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, v);
+                        }
                     } else {
-                        release_untouched(e, 0, TRAIN ? nch_out : 0);
-                        const float* sb = s_bias + MAXL * 256;
-                        float mx = -INFINITY;
-                        int argmax = 0;
-#pragma unroll 1
-                        for (int c = 0; c < nch; ++c) {
-                            float v[32];
-                            tmem_ld32(trow + c * 32, v);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int col = c * 32 + i;
-                                const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
-                                if (zz > mx) {
-                                    mx = zz;
-                                    argmax = col;
-                                }
-                            }
-                        }
-                        float S = 0.f;
-#pragma unroll 1
-                        for (int c = 0; c < nch; ++c) {
-                            float v[32];
-                            tmem_ld32(trow + c * 32, v);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int col = c * 32 + i;
-                                S += col < nact ? __expf(v[i] + sb[col] - mx) : 0.f;
-                            }
-                        }
-                        const float logS = logf(S);
-                        const float kLogMin = -25.328436022934504f;   // ln(1e-11)
-                        if (TRAIN) {
-                            int a = 0;
-                            float old_lp = 0.f, advv = 0.f;
-                            if (row_ok) {
-                                a = (int)__ldg(p.actions + row);             // acts.long(), discrete_policy.py:71
-                                a = min(max(a, 0), nact - 1);
-                                old_lp = __ldg(p.old_logp + row);
-                                advv = __ldg(p.adv + row);
-                            }
-                            // pass: entropy, sum_j m_j s_j (log p_j + 1), the action's log-softmax
-                            float Hent = 0.f, Gs = 0.f, ls_a = 0.f;
+                        // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62): the inverse-CDF scan is
+                        // sequential over the row, so the lower-half thread does it alone over all columns ----
+                        if (e.half == 0) {
+                            float Pq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
                             for (int c = 0; c < nch; ++c) {
                                 float v[32];
@@ -573,83 +681,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     const int col = c * 32 + i;
-                                    if (col < nact) {
-                                        const float ls = (v[i] + sb[col] - mx) - logS;      // log softmax (<= 0)
-                                        const float s = __expf(ls);
-                                        const float lp = fminf(fmaxf(ls, kLogMin), 0.f);    // log clamp(s, 1e-11, 1), :74-76
-                                        const float pj = fminf(fmaxf(s, 1e-11f), 1.0f);
-                                        Hent -= pj * lp;                                    // :78
-                                        Gs += ls >= kLogMin ? s * (lp + 1.0f) : 0.f;        // clamp passes gradient inside only
-                                        ls_a = col == a ? ls : ls_a;
-                                    }
+                                    const float pj = fminf(fmaxf(__expf(v[i] + sb[col & 255] - mxs), 1e-11f), 1.0f);
+                                    Pq[i & 3] += col < nact ? pj : 0.f;
                                 }
                             }
-                            const float lp_a = fminf(fmaxf(ls_a, kLogMin), 0.f);
-                            const float s_a = __expf(ls_a);
-                            const float p_a = fminf(fmaxf(s_a, 1e-11f), 1.0f);
-                            const float log_ratio = lp_a - old_lp;
-                            const float ratio = expf(log_ratio);                            // ppo_learner.py:153
-                            const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
-                            const float clipped = fminf(fmaxf(ratio, lo), hi);              // :154-156
-                            const float s1 = ratio * advv, s2 = clipped * advv;
-                            const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-                            const float d1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);      // torch.min backward, ties 0.5/0.5
-                            const float d2 = s1 > s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
-                            const float okf = row_ok ? 1.f : 0.f;
-                            const float d_logp = -p.inv_batch * advv * (d1 + d2 * in_range) * ratio * okf;
-                            const float ga = (ls_a >= kLogMin) ? d_logp / p_a : 0.f;        // through log(clamp(s_a))
-                            const float cw = p.ent_coef * p.inv_batch * okf;
-                            const float G = cw * Gs + ga * s_a;
-                            if (row_ok) {
-                                m0 += Hent;
-                                m1 += (ratio - 1.0f) - log_ratio;                           // :161
-                                m2 += fabsf(ratio - 1.0f) > p.clip ? 1.f : 0.f;             // :166
-                                m3 += fminf(s1, s2);
-                                mrows += 1.f;
-                                if (p.logp_out) p.logp_out[row] = lp_a;
-                            }
-                            // pass: dz_j = s_j (g_j - G) -> bf16 tile (A operand of the first dgrad GEMM) + head bias grads
-#pragma unroll 1
-                            for (int c = 0; c < nch_out; ++c) {
-                                float v[32], t[32];
-                                if (c < nch) {
-                                    tmem_ld32(trow + c * 32, v);
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
-                                }
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const int col = c * 32 + i;
-                                    float o = 0.f;
-                                    if (col < nact) {
-                                        const float ls = (v[i] + sb[col] - mx) - logS;
-                                        const float s = __expf(ls);
-                                        const float lp = fminf(fmaxf(ls, kLogMin), 0.f);
-                                        float gj = cw * (lp + 1.0f) + (col == a ? ga : 0.f);
-                                        gj = ls >= kLogMin ? gj : 0.f;
-                                        o = s * (gj - G);
-                                    }
-                                    v[i] = o;
-                                    t[i] = o;
-                                }
-                                db_add(MAXL, c, warp_colsum32(t, e.lane));
-                                store_chunk_sw128(dst, e.row_in_tile, c, v);
-                                release_after_chunk(e, c, nch_out);
-                            }
-                        } else {
-                            // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62) ----
-                            float P = 0.f;
-#pragma unroll 1
-                            for (int c = 0; c < nch; ++c) {
-                                float v[32];
-                                tmem_ld32(trow + c * 32, v);
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const int col = c * 32 + i;
-                                    if (col < nact) P += fminf(fmaxf(__expf((v[i] + sb[col] - mx) - logS), 1e-11f), 1.0f);
-                                }
-                            }
+                            const float P = (Pq[0] + Pq[1]) + (Pq[2] + Pq[3]);
                             int actn = nact - 1;
                             float pa = 0.f;
                             if (p.deterministic) {
@@ -669,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 }
                                 const float thr = u * P;   // torch.multinomial normalises what it is given
                                 float run = 0.f, plast = 0.f;
-                                bool found = false;
+                                int found = 0;
 #pragma unroll 1
                                 for (int c = 0; c < nch; ++c) {
                                     float v[32];
@@ -677,19 +713,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #pragma unroll
                                     for (int i = 0; i < 32; ++i) {
                                         const int col = c * 32 + i;
-                                        if (col < nact) {
-                                            const float pj = fminf(fmaxf(__expf((v[i] + sb[col] - mx) - logS), 1e-11f), 1.0f);
-                                            run += pj;
-                                            plast = pj;
-                                            if (!found && run > thr) {
-                                                found = true;
-                                                actn = col;
-                                                pa = pj;
-                                            }
-                                        }
+                                        const bool in = col < nact;
+                                        const float pj = fminf(fmaxf(__expf(v[i] + sb[col & 255] - mxs), 1e-11f), 1.0f);
+                                        run += in ? pj : 0.f;               // the running sum is inherently sequential
+                                        plast = in ? pj : plast;
+                                        const bool hit = in && !found && run > thr;
+                                        actn = hit ? col : actn;
+                                        pa = hit ? pj : pa;
+                                        found |= hit ? 1 : 0;
                                     }
                                 }
-                                if (!found) pa = plast;
+                                pa = found ? pa : plast;
                             }
                             if (row_ok) {
                                 if (p.actions_out) p.actions_out[row] = (float)actn;   // batched_agent_manager.py:204
@@ -699,39 +733,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         }
                     }
                 }
-                if (!TRAIN) {
-                    // inference epilogues that wrote nothing still have to order their TMEM reads before the next MMA
-                    tc_fence_before();
-                }
+                release_all(e);
+                if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (ph, slot) done
             }
+          }
         }
-        // ---- flush the per-thread accumulators: bias gradients, value-head weight gradient, metrics ----
+        // ---- metrics (the column sums are flushed by the whole CTA below) ----
         if (TRAIN) {
-#pragma unroll
-            for (int l = 0; l < MAXL; ++l) {
-                if (l < p.L && p.gbias[l] != nullptr) {
-                    const int nc = p.H[l] >> 5;
-                    const int c0 = e.half * (nc >> 1);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < (nc >> 1)) atomicAdd(p.gbias[l] + (c0 + j) * 32 + e.lane, dbacc[l][j]);
-                }
-            }
-            if (POLICY) {
-                if (e.half == 0 && p.gbias[MAXL] != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int col = c * 32 + e.lane;
-                        if (col < p.n_actions) atomicAdd(p.gbias[MAXL] + col, dbacc[MAXL][c]);
-                    }
-                }
-            } else {
-                const int nc = p.H[p.L - 1] >> 5;
-                const int c0 = e.half * (nc >> 1);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j < (nc >> 1)) atomicAdd(p.gw_head + (c0 + j) * 32 + e.lane, dwacc[j]);
-            }
             if (p.metrics != nullptr && e.half == 0) {
                 const float r0 = warp_sum(m0), r1 = warp_sum(m1), r2 = warp_sum(m2), r3 = warp_sum(m3),
                             rr = warp_sum(mrows);
@@ -756,6 +764,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
+    }
+    if (TRAIN) {
+        // flush the shared-memory column sums: bias gradients of every Linear, value-head weight gradient
+        for (int i = threadIdx.x; i < (MAXL + 1) * 256; i += kThreads) {
+            const int l = i >> 8, c = i & 255;
+            const float v = s_db[i];
+            if (l < p.L) {
+                if (c < p.H[l] && p.gbias[l] != nullptr) atomicAdd(p.gbias[l] + c, v);
+            } else if (l == MAXL) {
+                if (POLICY) {
+                    if (c < p.n_actions && p.gbias[MAXL] != nullptr) atomicAdd(p.gbias[MAXL] + c, v);
+                } else {
+                    if (c < p.H[p.L - 1]) atomicAdd(p.gw_head + c, v);
+                }
+            }
+        }
     }
 }
 
@@ -797,6 +821,7 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     if (rc) return rc;
 
     int nw = 0, nout = 0, nph = 0;
+    for (int i = 0; i < MAXPH; ++i) p.ph[i] = PhaseDesc{};
     auto add_w = [&](const uint16_t* w, int64_t ld, int rows, int cols, int box_rows) -> int {
         RLPPO_CHECK_ARG(w != nullptr && ld % 8 == 0, "missing weight operand");
         int r = make_tmap_bf16_2d(&maps.w[nw], w, (uint64_t)rows, (uint64_t)cols, (uint64_t)ld, (uint32_t)box_rows);
@@ -835,94 +860,62 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         }
     }
     auto kb_of = [](int cols) { return (cols + KBLK - 1) / KBLK; };
+    auto add_phase = [&](int kind, int layer, int n_kb, int N, int wmap, int store_map, int store_kb) {
+        PhaseDesc& d = p.ph[nph++];
+        d.kind = (uint8_t)kind;
+        d.layer = (uint8_t)layer;
+        d.n_kb = (uint8_t)n_kb;
+        d.wmap = (uint8_t)wmap;
+        d.N = (uint16_t)N;
+        d.store_map = (uint8_t)(TRAIN && store_map >= 0 ? store_map : NO_STORE);
+        d.store_kb = (uint8_t)store_kb;
+    };
 
-    // ---- forward phases ----
-    int src = 1;   // x arrives in buffer B
+    // ---- forward phases: the tile is overwritten in place, so each phase stores what the previous epilogue left ----
+    int prev_map = -1, prev_kb = 0;    // the tile currently in the slot buffer, if it has to reach HBM
     for (int l = 0; l < L; ++l) {
-        PhaseDesc& d = p.ph[nph];
-        d = PhaseDesc{};
-        d.kind = (!POLICY && l == L - 1) ? PH_FWD_VALUE : PH_FWD;
-        d.layer = (uint8_t)l;
-        d.src = (uint8_t)src;
         const int K = l == 0 ? net->in_dim : net->hidden[l - 1];
-        d.n_kb = (uint8_t)kb_of(K);
-        d.N = (uint16_t)net->hidden[l];
-        d.wmap = (uint8_t)nw;
+        const int wmap = nw;
         rc = add_w(net->wq[l], net->wq_ld[l], net->hidden[l], K, net->hidden[l]);
         if (rc) return rc;
-        if (TRAIN && l > 0) {
-            d.n_store = 1;
-            d.st[0] = StoreDesc{(uint8_t)map_h[l - 1], (uint8_t)src, (uint8_t)kb_of(net->hidden[l - 1]), 0};
-        }
-        ++nph;
-        src ^= 1;
+        add_phase((!POLICY && l == L - 1) ? PH_FWD_VALUE : PH_FWD, l, kb_of(K), net->hidden[l], wmap, prev_map, prev_kb);
+        prev_map = TRAIN ? map_h[l] : -1;
+        prev_kb = kb_of(net->hidden[l]);
     }
-    // after the loop H_L sits in buffer `src` (the last epilogue's destination)
     if (POLICY) {
-        PhaseDesc& d = p.ph[nph];
-        d = PhaseDesc{};
-        d.kind = PH_HEAD;
-        d.layer = (uint8_t)L;
-        d.src = (uint8_t)src;
-        d.n_kb = (uint8_t)kb_of(net->hidden[L - 1]);
-        d.N = (uint16_t)head_N;
-        d.wmap = (uint8_t)nw;
+        const int wmap = nw;
         rc = add_w(net->wq[L], net->wq_ld[L], out_pad8, net->hidden[L - 1], head_N);
         if (rc) return rc;
-        if (TRAIN) {
-            d.n_store = 1;
-            d.st[0] = StoreDesc{(uint8_t)map_h[L - 1], (uint8_t)src, (uint8_t)kb_of(net->hidden[L - 1]), 0};
-        }
-        ++nph;
-        src ^= 1;   // dz sits in `src`
+        add_phase(PH_HEAD, L, kb_of(net->hidden[L - 1]), head_N, wmap, prev_map, prev_kb);
+        prev_map = TRAIN ? map_dz : -1;
+        prev_kb = p.out_kb;
     }
-    p.n_tail_store = 0;
+    p.tail_map = 0;
+    p.tail_kb = 0;
     if (TRAIN) {
         // ---- backward data phases ----
         if (POLICY) {
-            PhaseDesc& d = p.ph[nph];
-            d = PhaseDesc{};
-            d.kind = PH_DGRAD;
-            d.layer = (uint8_t)(L - 1);
-            d.src = (uint8_t)src;
-            d.n_kb = (uint8_t)p.out_kb;
-            d.N = (uint16_t)net->hidden[L - 1];
-            d.wmap = (uint8_t)nw;
+            const int wmap = nw;
             rc = add_w(net->wt[L], net->wt_ld[L], net->hidden[L - 1], out_pad8, net->hidden[L - 1]);
             if (rc) return rc;
-            d.n_store = 1;
-            d.st[0] = StoreDesc{(uint8_t)map_dz, (uint8_t)src, (uint8_t)p.out_kb, 0};
-            ++nph;
-            src ^= 1;   // dH_L sits in `src`
+            add_phase(PH_DGRAD, L - 1, p.out_kb, net->hidden[L - 1], wmap, prev_map, prev_kb);
         } else {
-            // value tail: H_L went to buffer `src`, dH_L to the other one, which is the next A operand
-            src ^= 1;
+            // GEMM-less phase: H_L (left by the forward tail) is stored, its epilogue writes dL/dH_L in place
+            add_phase(PH_VALUE_BWD, L - 1, 0, net->hidden[L - 1], 0, prev_map, prev_kb);
         }
+        prev_map = map_dh[L - 1];
+        prev_kb = kb_of(net->hidden[L - 1]);
         for (int l = L - 1; l >= 1; --l) {
-            // produce dH_l (hidden index l-1) from dH_{l+1} (hidden index l) with W_{l+1}^T = wt[l]
-            PhaseDesc& d = p.ph[nph];
-            d = PhaseDesc{};
-            d.kind = PH_DGRAD;
-            d.layer = (uint8_t)(l - 1);
-            d.src = (uint8_t)src;
-            d.n_kb = (uint8_t)kb_of(net->hidden[l]);
-            d.N = (uint16_t)net->hidden[l - 1];
-            d.wmap = (uint8_t)nw;
+            // produce dH (hidden index l-1) from dH (hidden index l) with W_l^T = wt[l]
+            const int wmap = nw;
             rc = add_w(net->wt[l], net->wt_ld[l], net->hidden[l - 1], net->hidden[l], net->hidden[l - 1]);
             if (rc) return rc;
-            d.n_store = 1;
-            d.st[0] = StoreDesc{(uint8_t)map_dh[l], (uint8_t)src, (uint8_t)kb_of(net->hidden[l]), 0};
-            if (!POLICY && l == L - 1) {   // first phase after the value tail also stores H_L from the other buffer
-                d.n_store = 2;
-                d.st[1] = StoreDesc{(uint8_t)map_h[L - 1], (uint8_t)(src ^ 1), (uint8_t)kb_of(net->hidden[L - 1]), 0};
-            }
-            ++nph;
-            src ^= 1;
+            add_phase(PH_DGRAD, l - 1, kb_of(net->hidden[l]), net->hidden[l - 1], wmap, prev_map, prev_kb);
+            prev_map = map_dh[l - 1];
+            prev_kb = kb_of(net->hidden[l - 1]);
         }
-        // tail: the gradient tile produced by the last epilogue (dH_1, or dH_L when L == 1)
-        p.tail[p.n_tail_store++] = StoreDesc{(uint8_t)map_dh[0], (uint8_t)src, (uint8_t)kb_of(net->hidden[0]), 0};
-        if (!POLICY && L == 1)
-            p.tail[p.n_tail_store++] = StoreDesc{(uint8_t)map_h[0], (uint8_t)(src ^ 1), (uint8_t)kb_of(net->hidden[0]), 0};
+        p.tail_map = prev_map;
+        p.tail_kb = prev_kb;
     }
     p.n_ph = nph;
 
@@ -933,8 +926,26 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         configured = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    static unsigned long long* d_trace = nullptr;
+    const bool tracing = getenv("RLPPO_FUSED_TRACE") != nullptr && TRAIN && POLICY;
+    if (tracing) {
+        if (d_trace == nullptr) RLPPO_CUDA(cudaMalloc(&d_trace, 1024 * sizeof(unsigned long long)));
+        RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 1024 * sizeof(unsigned long long), s));
+        p.trace = d_trace;
+    }
     kfn<<<grid, kThreads, SMEM_TOTAL, s>>>(maps, p);
     RLPPO_LAUNCH_CHECK();
+    if (tracing) {
+        static unsigned long long h[1024];
+        RLPPO_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
+        RLPPO_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long t0 = h[0];
+        fprintf(stderr, "[fused trace] n_ph=%d tiles=%d\n", p.n_ph, p.num_tiles);
+        for (int i = 0; i + 2 < 512 && h[i] != 0; i += 3)
+            fprintf(stderr, "  mma  #%d ready=%llu issued=+%llu stores=+%llu\n", i / 3, h[i] - t0, h[i + 1] - h[i], h[i + 2] - h[i + 1]);
+        for (int i = 0; i + 1 < 512 && h[512 + i] != 0; i += 2)
+            fprintf(stderr, "  epi  #%d start=%llu dur=%llu\n", i / 2, h[512 + i] - t0, h[512 + i + 1] - h[512 + i]);
+    }
     return RLPPO_OK;
 }
 
