@@ -143,6 +143,21 @@ int rlppo_linear_dgrad(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int
 int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int64_t ldx, float* dw,
                        int64_t lddw, float* db, int64_t M, int N, int K, void* stream);
 
+/* All weight gradients of an optimiser step in ONE persistent launch (<= 8 layers): for every item
+ * dW[N,K] += dY[M,N]^T * X[M,K] as rlppo_linear_wgrad, but dY is read once per 256 k (not once per 128), row
+ * splits are balanced across layers by byte volume, and seven launches become one. */
+typedef struct rlppo_wgrad_item {
+    const uint16_t* dy;     /* bf16 [M, lddy] */
+    int64_t lddy;
+    const uint16_t* x;      /* bf16 [M, ldx] */
+    int64_t ldx;
+    float* dw;              /* f32 [N, lddw], accumulated */
+    int64_t lddw;
+    int64_t M;
+    int32_t N, K;
+} rlppo_wgrad_item;
+int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream);
+
 /* Policy head, sampling (DiscreteFF.get_action, discrete_policy.py:44-62): logits = H*W^T + b over
  * n_actions <= 256, softmax, clamp(1e-11,1), categorical sample by inverse CDF, log-prob of the sample.
  *   u_inject   optional f32[M] uniforms in [0,1) (tests); NULL -> Philox4x32-10(seed, offset + row)

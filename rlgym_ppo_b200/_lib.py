@@ -45,6 +45,7 @@ _SIGS = {
     "rlppo_linear_fwd": ([_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _P], _I),
     "rlppo_linear_dgrad": ([_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P], _I),
     "rlppo_linear_wgrad": ([_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P], _I),
+    "rlppo_wgrad_multi": ([_P, _I, _P], _I),
     "rlppo_policy_head_sample": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _U64, _U64, _I, _P, _P, _P, _P, _P], _I),
     "rlppo_policy_head_train": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _P, _P, _F, _F, _F, _P, _L, _P, _P, _P], _I),
     "rlppo_value_head": ([_P, _L, _P, _P, _L, _I, _P, _P, _F, _P, _L, _P, _P, _P, _P], _I),
@@ -64,6 +65,12 @@ class AppendField(ctypes.Structure):
     """struct rlppo_append_field."""
     _fields_ = [("ring", _P), ("ring_ld", _L), ("ring_bf16", _P), ("bf16_ld", _L), ("src", _P), ("src_ld", _L),
                 ("src_is_f64", ctypes.c_int32), ("width", ctypes.c_int32)]
+
+
+class WgradItem(ctypes.Structure):
+    """struct rlppo_wgrad_item."""
+    _fields_ = [("dy", _P), ("lddy", _L), ("x", _P), ("ldx", _L), ("dw", _P), ("lddw", _L), ("M", _L),
+                ("N", ctypes.c_int32), ("K", ctypes.c_int32)]
 
 
 class Bf16View(ctypes.Structure):

@@ -647,6 +647,177 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// (III) all weight gradients of a learner step in ONE persistent launch.
+// Work item = (layer, 256-wide n tile, 256-wide k pair, row split).  Per 64-row block a CTA stages X [64 x <=256 k]
+// and dY [64 x <=256 n] ONCE and issues up to two M=128 MMAs (the two 128-row k tiles) against the same dY tile, so
+// dY is read once (the per-layer kernel above reads it once per k tile).  Row splits are sized from each layer's
+// byte volume so that the ~148 items finish together.  HBM-bound: reads dY and X exactly once.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MAXW = 8;
+struct alignas(64) WMaps {
+    CUtensorMap x[MAXW];
+    CUtensorMap dy[MAXW];
+};
+struct WLayer {
+    float* dw;
+    int64_t lddw, M, m_per_split;
+    int N, K, n_tiles_n, n_kpairs, splits, first_item;
+};
+struct WMultiParams {
+    WLayer L[MAXW];
+    int n_layers, total_items;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_multi_kernel(const __grid_constant__ WMaps maps, const WMultiParams p) {
+    constexpr uint32_t CHUNK = 64 * BLOCK_K * 2;       // 8 KB: 64 MN-elements x 64 rows
+    constexpr uint32_t STAGE = 8 * CHUNK;              // X: 4 chunks (256 k), dY: 4 chunks (256 n)
+    constexpr int NST = 3;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE);
+    uint64_t* empty = full + NST;
+    uint64_t* tfull = empty + NST;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // decode a work item (identical in every role)
+    struct Item {
+        int layer, n0, k0, nkb, n_x, n_y, bn;
+        int64_t m0;
+    };
+    auto decode = [&](int w) {
+        Item it;
+        int l = 0;
+        while (l + 1 < p.n_layers && w >= p.L[l + 1].first_item) ++l;
+        const WLayer& L = p.L[l];
+        const int local = w - L.first_item;
+        const int split = local % L.splits, tile = local / L.splits;
+        const int kp = tile % L.n_kpairs, nt = tile / L.n_kpairs;
+        it.layer = l;
+        it.n0 = nt * 256;
+        it.k0 = kp * 256;
+        it.m0 = (int64_t)split * L.m_per_split;
+        const int64_t m1 = min(L.M, it.m0 + L.m_per_split);
+        it.nkb = m1 > it.m0 ? (int)((m1 - it.m0 + BLOCK_K - 1) / BLOCK_K) : 0;
+        it.n_x = (min(256, L.K - it.k0) + 63) / 64;            // 64-wide k chunks that hold data
+        it.n_y = (min(256, L.N - it.n0) + 63) / 64;
+        it.bn = (min(256, L.N - it.n0) + 15) / 16 * 16;        // UMMA N
+        return it;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+                const Item it = decode(w);
+                for (int kb = 0; kb < it.nkb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], (uint32_t)(it.n_x + it.n_y) * CHUNK);
+                    uint8_t* sx = smem + stage * STAGE;
+                    const int mrow = (int)(it.m0 + (int64_t)kb * BLOCK_K);
+                    for (int c = 0; c < it.n_x; ++c)
+                        tma_load_2d(&maps.x[it.layer], &full[stage], sx + c * CHUNK, it.k0 + c * 64, mrow);
+                    for (int c = 0; c < it.n_y; ++c)
+                        tma_load_2d(&maps.dy[it.layer], &full[stage], sx + (4 + c) * CHUNK, it.n0 + c * 64, mrow);
+                    if (++stage == NST) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, n_done = 0;
+            for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+                const Item it = decode(w);
+                if (it.nkb == 0) continue;
+                mbar_wait(tempty, (n_done & 1) ^ 1);       // the previous item's accumulators have been drained
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_bf16(128, it.bn, 1, 1);   // both operands MN-major
+                const int n_kt = (it.n_x + 1) / 2;                           // 128-wide k tiles with data
+                for (int kb = 0; kb < it.nkb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(smem + stage * STAGE);
+                    const uint32_t b_addr = x_addr + 4 * CHUNK;
+                    for (int kt = 0; kt < n_kt; ++kt) {
+#pragma unroll
+                        for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+                            const uint64_t ad = umma_smem_desc(x_addr + kt * 2 * CHUNK + ks * (UMMA_K * 128), CHUNK, 1024);
+                            const uint64_t bd = umma_smem_desc(b_addr + ks * (UMMA_K * 128), CHUNK, 1024);
+                            umma_bf16(tmem_base + kt * 256, ad, bd, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == NST) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tfull);
+                ++n_done;
+            }
+        }
+    } else {
+        const int ew = warp & 3;
+        uint32_t n_done = 0;
+        for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+            const Item it = decode(w);
+            if (it.nkb == 0) continue;
+            const WLayer& L = p.L[it.layer];
+            mbar_wait(tfull, n_done & 1);
+            tc_fence_after();
+            const int n_kt = (it.n_x + 1) / 2;
+            const int nch = (min(256, L.N - it.n0) + 31) >> 5;
+            for (int kt = 0; kt < n_kt; ++kt) {
+                const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + kt * 256;
+                const int k = it.k0 + kt * 128 + ew * 32 + lane;
+                for (int c = 0; c < nch; ++c) {
+                    float v[32];
+                    tmem_ld32(trow + c * 32, v);
+                    if (k < L.K) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = it.n0 + c * 32 + j;
+                            if (n < L.N) atomicAdd(L.dw + (int64_t)n * L.lddw + k, v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+            ++n_done;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // column sums of a bf16 matrix: db[n] += sum_m dY[m,n]   (bias gradients)
 __global__ void colsum_kernel(const uint16_t* __restrict__ dy, int64_t ld, int64_t M, int N, int n8,
                               float* __restrict__ db, int64_t rows_per_block) {
@@ -838,6 +1009,58 @@ int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int6
         colsum_kernel<<<blocks, threads, n8 * sizeof(float), s>>>(dy, lddy, M, N, n8, db, rows_per_block);
         RLPPO_LAUNCH_CHECK();
     }
+    return RLPPO_OK;
+}
+
+int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(h_items && n_items >= 1 && n_items <= MAXW, "1..%d weight-gradient items per launch", MAXW);
+    WMaps maps;
+    WMultiParams p{};
+    p.n_layers = n_items;
+    double bytes[MAXW], total_bytes = 0.0;
+    for (int i = 0; i < n_items; ++i) {
+        const rlppo_wgrad_item& it = h_items[i];
+        RLPPO_CHECK_ARG(it.dy && it.x && it.dw && it.M >= 1 && it.N >= 1 && it.K >= 1, "bad item %d", i);
+        RLPPO_CHECK_ARG(it.M < (1ll << 31) && it.lddy % 8 == 0 && it.ldx % 8 == 0, "item %d: ld must be a multiple of 8", i);
+        WLayer& L = p.L[i];
+        L.dw = it.dw; L.lddw = it.lddw; L.M = it.M; L.N = it.N; L.K = it.K;
+        L.n_tiles_n = (it.N + 255) / 256;
+        L.n_kpairs = (it.K + 255) / 256;
+        const uint64_t x_cols = (uint64_t)min((int64_t)((it.K + 7) / 8 * 8), it.ldx);
+        const uint64_t dy_cols = (uint64_t)min((int64_t)((it.N + 7) / 8 * 8), it.lddy);
+        int rc = make_tmap_bf16_2d(&maps.x[i], it.x, (uint64_t)it.M, x_cols, (uint64_t)it.ldx, 64);
+        if (rc) return rc;
+        rc = make_tmap_bf16_2d(&maps.dy[i], it.dy, (uint64_t)it.M, dy_cols, (uint64_t)it.lddy, 64);
+        if (rc) return rc;
+        // bytes one pass over this layer's tiles reads
+        bytes[i] = (double)it.M * 2.0 * ((double)L.n_tiles_n * min(it.K, 256 * L.n_kpairs) + (double)L.n_kpairs * min(it.N, 256 * L.n_tiles_n));
+        total_bytes += bytes[i];
+    }
+    const int ctas = num_sms();
+    int first = 0;
+    for (int i = 0; i < n_items; ++i) {
+        WLayer& L = p.L[i];
+        const int tiles = L.n_tiles_n * L.n_kpairs;
+        const int64_t kblocks = (L.M + BLOCK_K - 1) / BLOCK_K;
+        int64_t splits = (int64_t)(ctas * (bytes[i] / total_bytes) / tiles + 0.5);
+        if (splits < 1) splits = 1;
+        if (splits > kblocks) splits = kblocks;
+        L.m_per_split = ((kblocks + splits - 1) / splits) * BLOCK_K;
+        L.splits = (int)((L.M + L.m_per_split - 1) / L.m_per_split);
+        L.first_item = first;
+        first += tiles * L.splits;
+    }
+    p.total_items = first;
+    constexpr uint32_t SMEM = 3 * 8 * 8192 + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        RLPPO_CUDA(cudaFuncSetAttribute(wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        configured = true;
+    }
+    const int grid = p.total_items < ctas ? p.total_items : ctas;
+    wgrad_multi_kernel<<<grid, kThreads, SMEM, static_cast<cudaStream_t>(stream)>>>(maps, p);
+    RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }
 }

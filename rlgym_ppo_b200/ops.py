@@ -167,6 +167,19 @@ def linear_wgrad(dy, x, dw, db, N, K, M=None):
          int(N), int(K), stream_ptr(), work=("flop", 2.0 * M * N * K))
 
 
+def wgrad_multi(items, M):
+    """items: list of (dy, x, dw, N, K) -- all weight gradients of a step in one launch (<= 8 per call)."""
+    for i0 in range(0, len(items), 8):
+        part = items[i0:i0 + 8]
+        arr = (_lib.WgradItem * len(part))()
+        flop = 0.0
+        for a, (dy, x, dw, N, K) in zip(arr, part):
+            a.dy, a.lddy, a.x, a.ldx = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
+            a.dw, a.lddw, a.M, a.N, a.K = dw.data_ptr(), dw.stride(0), int(M), int(N), int(K)
+            flop += 2.0 * M * N * K
+        call("rlppo_wgrad_multi", ctypes.cast(arr, ctypes.c_void_p), len(part), stream_ptr(), work=("flop", flop))
+
+
 def policy_head_sample(h, wq, bias, n_actions, K, M=None, u=None, seed=0, offset=0, deterministic=False,
                        actions_out=None, actions_i64_out=None, logp_out=None, probs_out=None):
     M = h.shape[0] if M is None else M

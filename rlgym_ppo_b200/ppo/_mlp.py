@@ -144,15 +144,18 @@ class Stack:
         cache[key] = net
         return net
 
-    def fused_wgrads(self, x, M, ws, head_dy=None):
-        """Weight gradients after a fused training pass: dW_l += dH_l^T X_{l-1} (and the policy head's)."""
+    def fused_wgrad_items(self, x, ws, head_dy=None):
+        """(dy, x, dW, N, K) per Linear after a fused training pass: dW_l += dH_l^T X_{l-1} (and the policy head's);
+        fed to ops.wgrad_multi (one launch for both nets)."""
         L = len(self.hidden)
+        items = []
         if head_dy is not None:
-            ops.linear_wgrad(head_dy, ws["h"][L - 1], self.gw[L], None, self.out_dim, self.hidden[L - 1], M=M)
+            items.append((head_dy, ws["h"][L - 1], self.gw[L], self.out_dim, self.hidden[L - 1]))
         for i in range(L - 1, -1, -1):
             inp = ws["h"][i - 1] if i > 0 else x
             K = self.hidden[i - 1] if i > 0 else self.in_dim
-            ops.linear_wgrad(ws["dh"][i], inp, self.gw[i], None, self.hidden[i], K, M=M)
+            items.append((ws["dh"][i], inp, self.gw[i], self.hidden[i], K))
+        return items
 
     # ---- workspaces -------------------------------------------------------------------------------------
     def workspace(self, rows):

@@ -158,6 +158,7 @@ class PPOLearner(object):
         inv_b = 1.0 / float(self.batch_size)       # (1/mb) * (mb/B), ppo_learner.py:172-177
         metrics = self._tail[0:8]
         n = 1
+        wg_items = []
         for net, is_policy in ((self.policy, True), (self.value_net, False)):
             st = net._stack
             ws = st.workspace(M)
@@ -167,12 +168,12 @@ class PPOLearner(object):
                     fnet = st.fused_net(x.stride(0), ws, policy_head=True)
                     ops.policy_train_fused(fnet, x, M, net.n_actions, mb["actions"], mb["old_logp"], mb["adv"], inv_b,
                                            float(self.clip_range), float(self.ent_coef), metrics)
-                    st.fused_wgrads(x, M, ws, head_dy=ws["dz"])
+                    wg_items += st.fused_wgrad_items(x, ws, head_dy=ws["dz"])
                 else:
                     fnet = st.fused_net(x.stride(0), ws)
                     ops.value_train_fused(fnet, x, M, st.w[-1], mb["targets"], inv_b, st.gw[-1], metrics)
-                    st.fused_wgrads(x, M, ws)
-                n += 1 + len(st.hidden) + (1 if is_policy else 0)
+                    wg_items += st.fused_wgrad_items(x, ws)
+                n += 1
                 continue
             h = st.forward_hidden(x, M, ws)
             hl = st.hidden[-1]
@@ -192,6 +193,9 @@ class PPOLearner(object):
             st.backward_hidden(x, M, ws, dh)
             L = len(st.hidden)
             n += L + 2 * L + (L - 1)   # fwd GEMMs, wgrad + colsum per layer, dgrad for all but the first
+        if wg_items:
+            ops.wgrad_multi(wg_items, M)       # every weight gradient of both nets: one persistent launch
+            n += (len(wg_items) + 7) // 8
         self.launches += n
 
     def _optimizer_step(self):

@@ -466,3 +466,29 @@ def test_weight_and_rows_to_bf16(ops):
     ops.rows_to_bf16(dev(x), xb, dev(mean), dev(std), 5.0)
     refx[:, :89] = ((x - mean) / std).clamp(-5, 5)
     assert torch.equal(xb.cpu(), refx.to(torch.bfloat16))
+
+
+def test_wgrad_multi(ops):
+    """All weight gradients in one launch == the per-layer kernel == fp64 reference, incl. n/k tiling and row splits."""
+    M = 7001
+    shapes = [(256, 89, 96), (256, 256, 256), (90, 256, 256), (1024, 2048, 2048), (64, 64, 64), (8, 256, 256)]
+    items, refs, outs = [], [], []
+    for i, (N, K, Kp) in enumerate(shapes):
+        Np = (N + 7) // 8 * 8
+        dy = torch.zeros(M, Np)
+        dy[:, :N] = _mk((M, N), 50 + i)
+        x = torch.zeros(M, Kp)
+        x[:, :K] = _mk((M, K), 60 + i)
+        dw = torch.full((N, K), 0.25, device=DEV)
+        dyd, xd = dev(dy, torch.bfloat16), dev(x, torch.bfloat16)
+        items.append((dyd, xd, dw, N, K))
+        outs.append(dw)
+        refs.append((dy[:, :N].double().t() @ x[:, :K].double()).float() + 0.25)
+    ops.wgrad_multi(items, M)
+    torch.cuda.synchronize()
+    for (N, K, _), got, want in zip(shapes, outs, refs):
+        assert rel_l2(got.cpu(), want) < 1e-4, (N, K, rel_l2(got.cpu(), want))
+    # more than 8 items are split over launches
+    ops.wgrad_multi(items + items[:4], M)
+    torch.cuda.synchronize()
+    assert rel_l2(outs[0].cpu(), 3 * (refs[0] - 0.25) + 0.25) < 1e-4 and rel_l2(outs[5].cpu(), 2 * (refs[5] - 0.25) + 0.25) < 1e-4
