@@ -190,31 +190,32 @@ def b200_arm(args, wl):
 
     R = world
     n_local = wl["n_new"]
+    # Weak scaling, "sharded" data parallelism: every rank owns its rollout (as if fed by its own env workers), its
+    # experience buffer and its shuffle; per-rank batch = the workload's batch, one optimiser step averages over R of them.
     n_glob, batch, cap = n_local * R, wl["batch"] * R, wl["buffer"] * R
-    torch.manual_seed(123)
+    torch.manual_seed(123)        # identical initial weights on every rank
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
-        ppo = PPOLearner(wl["obs"], wl["act"], 0, wl["layers"], wl["layers"], (0.1, 1.0), batch, wl["epochs"], 3e-4,
-                         3e-4, 0.2, wl["ent"], batch, dev)
+        ppo = PPOLearner(wl["obs"], wl["act"], 0, wl["layers"], wl["layers"], (0.1, 1.0), wl["batch"], wl["epochs"], 3e-4,
+                         3e-4, 0.2, wl["ent"], wl["batch"], dev, dp_mode="sharded")
     ns = SimpleNamespace(ppo_learner=ppo, return_stats=WelfordRunningStat(1, device=dev), standardize_returns=True,
                          gae_gamma=0.99, gae_lambda=0.95, max_returns_per_stats_increment=150,
-                         experience_buffer=ExperienceBuffer(cap, 123, dev))
+                         experience_buffer=ExperienceBuffer(wl["buffer"], 123 + rank, dev))
 
-    # ---- synthetic rollouts: a pool of distinct ones, pinned on the host and resident on the device -------------------
-    # Every rank draws the same global rollout (same seed): the experience is replicated, the update is sharded.
-    rng = np.random.RandomState(0)
+    # ---- synthetic rollouts: a pool of distinct ones per rank, pinned on the host and resident on the device -------------
+    rng = np.random.RandomState(rank)
     pool_host, pool_dev = [], []
     n_pool = 3
     for _ in range(n_pool):
-        states, rewards, next_states, dones, truncated = synth_rollout(rng, n_glob, wl["obs"])
+        states, rewards, next_states, dones, truncated = synth_rollout(rng, n_local, wl["obs"])
         acts, logp = ppo.policy.get_action_device(torch.from_numpy(states).to(dev))
         host = [torch.from_numpy(a).pin_memory() for a in
                 (states, acts.float().cpu().numpy(), logp.cpu().numpy(), rewards, next_states, dones, truncated)]
         pool_host.append((tuple(t.numpy() for t in host), host))   # numpy views of pinned memory (+ keep-alive)
         pool_dev.append(tuple(t.to(dev) for t in host))
-    h2d_bytes = sum(t.numel() * t.element_size() for t in pool_host[0][1])
-    d2h_bytes = ppo._tail_host.numel() * 4
+    h2d_bytes = world * sum(t.numel() * t.element_size() for t in pool_host[0][1])     # all ranks
+    d2h_bytes = world * ppo._tail_host.numel() * 4
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -229,7 +230,7 @@ def b200_arm(args, wl):
 
     # fill to steady state, then warm up
     it = 0
-    while len(ns.experience_buffer) + n_glob < cap:
+    while len(ns.experience_buffer) + n_local < wl["buffer"]:
         Learner.add_new_experience(ns, pool_dev[it % n_pool])
         it += 1
     for _ in range(max(args.warmup, 3)):
@@ -332,7 +333,9 @@ def b200_arm(args, wl):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "global_new_timesteps": n_glob, "global_batch": batch,
                        "global_buffer": cap, "optimizer_steps_per_step": n_updates,
-                       "consumed_samples_per_step": n_updates * batch, "parallelism": f"dp{world}",
+                       "consumed_samples_per_step": n_updates * batch,
+                       "parallelism": f"dp{world} (per-rank experience shards; NCCL allreduce of the flat gradient arena "
+                                      f"per optimiser step)" if world > 1 else "dp1",
                        "l2": "flushed between timed steps (256 MiB write); working set > L2",
                        "algorithmic_tflop_per_step": flop_step / 1e12,
                        "achieved_tflops": flop_step / (dev_ms / K / 1e3) / 1e12},

@@ -334,6 +334,10 @@ class Learner(object):
                              self.gae_lambda, ret_std, ret_head64=head)    # :358-366
         if n_inc:
             self.return_stats.increment_device(head, n_inc)               # :368-372 (after the scan read std)
+            ppo = self.ppo_learner
+            if getattr(ppo, "world_size", 1) > 1 and getattr(ppo, "dp_mode", "") == "sharded":
+                # one rollout per rank: the statistics follow rank 0's (the head of the concatenated rollout)
+                self.return_stats.broadcast_(src=0, group=getattr(ppo, "_pg", None))
         d["values"], d["advantages"] = vt, adv
         buf.submit_device(d)                                               # :375-385
 

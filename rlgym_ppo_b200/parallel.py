@@ -1,0 +1,50 @@
+"""Host-side data-parallel bookkeeping (one process per GPU; torch.distributed carries the collectives: NCCL on the
+GPUs, gloo in the CPU tests).  No tensor math here beyond the collectives themselves.
+
+The reference has no distributed mode; the seam is its gradient accumulation over minibatch slices
+(ppo_learner.py:134-193), which sums (mb/B)-scaled minibatch gradients before ONE clip + Adam step.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world(group=None):
+    """(world_size, rank) of the initialised process group, (1, 0) without one."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def rank_rows(k, batch_size, rank, world_size, mode):
+    """Rows of the epoch's permutation that `rank` consumes for optimiser step k: (first, count).
+
+    replicated: every rank holds the same buffer and the same permutation; batch k = perm[k*B : (k+1)*B] is cut into
+                world_size consecutive slices -- the reference's minibatch slices with mini_batch_size = B / world_size.
+    sharded:    every rank holds its own buffer and permutation and consumes a whole per-rank batch."""
+    if mode == "sharded" or world_size == 1:
+        return k * batch_size, batch_size
+    assert batch_size % world_size == 0, "batch_size must be a multiple of the number of ranks"
+    local = batch_size // world_size
+    return k * batch_size + rank * local, local
+
+
+def samples_per_step(batch_size, world_size, mode):
+    """Number of samples one optimiser step averages over (the B of the 1/B gradient weight)."""
+    return batch_size * world_size if (mode == "sharded" and world_size > 1) else batch_size
+
+
+def allreduce_sum_(t, group=None):
+    """In-place sum over ranks (flat gradient arena, metric sums); identity without a process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def report_from_sums(sums):
+    """sums: the 8 metric accumulators of rlppo_policy_head_train / rlppo_value_head summed over ranks and minibatches
+    -> the four averaged report entries of ppo_learner.py:204-210 (equal-size minibatches: mean of means = total mean)."""
+    s = [float(x) for x in sums]
+    rows_p = s[4] if s[4] > 0 else 1.0
+    rows_v = s[6] if s[6] > 0 else 1.0
+    return {"Policy Entropy": s[0] / rows_p, "Mean KL Divergence": s[1] / rows_p, "SB3 Clip Fraction": s[2] / rows_p,
+            "Value Function Loss": s[5] / rows_v}

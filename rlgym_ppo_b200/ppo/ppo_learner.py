@@ -29,7 +29,7 @@ import time
 import numpy as np
 import torch
 
-from .. import _lib, ops
+from .. import _lib, ops, parallel
 from .discrete_policy import DiscreteFF
 from .fused_adam import FusedAdam
 from .value_estimator import ValueEstimator
@@ -54,6 +54,7 @@ class PPOLearner(object):
         device,
         max_chunk_rows=131072,
         process_group=None,
+        dp_mode="replicated",
     ):
         _lib.require_device()
         if device in (None, "auto", "gpu"):
@@ -118,11 +119,18 @@ class PPOLearner(object):
 
         # ---- data parallelism ---------------------------------------------------------------------------------
         self._pg = process_group
-        self.world_size, self.rank = 1, 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.world_size = torch.distributed.get_world_size(process_group)
-            self.rank = torch.distributed.get_rank(process_group)
-        assert batch_size % self.world_size == 0, "batch_size must be a multiple of the number of ranks"
+        self.world_size, self.rank = parallel.world(process_group)
+        # Data-parallel modes (world_size > 1; one process per GPU, NCCL through torch.distributed):
+        #  "replicated": every rank holds the SAME experience buffer and draws the same global permutation; rank r takes
+        #                slice r of every batch -- exactly the reference's minibatch slices (ppo_learner.py:134-143), so the
+        #                result equals the single-process one.  batch_size is the GLOBAL batch.
+        #  "sharded":    every rank holds its OWN experience (its own env workers) and shuffles it with its own stream;
+        #                batch_size is the PER-RANK batch, the optimiser step averages over world_size * batch_size
+        #                samples.  Nothing but gradients (and a few scalars) crosses NVLink: this is the weak-scaling mode.
+        assert dp_mode in ("replicated", "sharded")
+        self.dp_mode = dp_mode
+        if dp_mode == "replicated":
+            assert batch_size % self.world_size == 0, "batch_size must be a multiple of the number of ranks"
         self._mb = None
         self.launches = 0   # kernels enqueued by the last learn() (bench.py reports it)
         views = ps.bf16_views(0) + vs.bf16_views(n_p)
@@ -155,7 +163,8 @@ class PPOLearner(object):
         exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
                    out_adv=mb["adv"], out_states_bf16=mb["x"])
         x = mb["x"]
-        inv_b = 1.0 / float(self.batch_size)       # (1/mb) * (mb/B), ppo_learner.py:172-177
+        # (1/mb) * (mb/B), ppo_learner.py:172-177; B = the number of samples one optimiser step averages over
+        inv_b = 1.0 / float(parallel.samples_per_step(self.batch_size, self.world_size, self.dp_mode))
         metrics = self._tail[0:8]
         n = 1
         wg_items = []
@@ -199,8 +208,10 @@ class PPOLearner(object):
         self.launches += n
 
     def _optimizer_step(self):
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self._grads, group=self._pg)   # NCCL sum over NVLink; grads carry 1/B
+        parallel.allreduce_sum_(self._grads, self._pg)   # NCCL sum over NVLink; the gradients carry the global 1/B
+        self._apply_step()
+
+    def _apply_step(self):
         ops.grad_sqnorm(self._grads, self._seg, self._sqnorm)           # ppo_learner.py:187-190
         ops.clip_adam(self._params, self._grads, self._m, self._v, self._seg, self._sqnorm, self._lr_dev,
                       self._steps, max_norm=0.5, views=self._views)     # :192-193, + bf16 operand refresh in-launch
@@ -208,35 +219,28 @@ class PPOLearner(object):
         self.value_net._stack.mark_operands_fresh()
         self.launches += 4
 
-    def _batch_body(self, exp, idx, local, chunk):
+    def _backward_body(self, exp, idx, local, chunk):
         self._grads.zero_()                                     # ppo_learner.py:131-132
         for c0 in range(0, local, chunk):
             rows = min(chunk, local - c0)
             self._train_chunk(exp, idx[c0:c0 + rows], rows)
+
+    def _batch_body(self, exp, idx, local, chunk):
+        self._backward_body(exp, idx, local, chunk)
         self._optimizer_step()
 
-    def _batch_step(self, exp, idx, local, chunk):
-        """One optimiser step on this rank's share `idx` of a batch: eager, or as a replayed CUDA graph."""
-        if not self.use_cuda_graph or self.world_size > 1 or _lib._TIMING is not None:
-            self._batch_body(exp, idx, local, chunk)
-            return
-        if self._idx_cur is None or self._idx_cur.numel() < local:
-            self._idx_cur = torch.empty(local, dtype=torch.int64, device=self._params.device)
-        cur = self._idx_cur[:local]
-        cur.copy_(idx)      # the graph reads its indices from a fixed buffer; the ring origin from exp.start_dev
-        key = (exp.ring("states").data_ptr(), exp.capacity, local, chunk, float(self.clip_range), float(self.ent_coef),
-               self.batch_size, self.policy._stack.fused_ok, self.value_net._stack.fused_ok)
+    def _captured(self, key, fn):
+        """Replay `fn` as a CUDA graph (captured on its second use: the first run allocates workspaces and configures
+        kernel attributes eagerly).  Returns False when the caller has to run `fn` eagerly itself."""
         entry = self._graphs.get(key)
         if entry is None:
             if key not in self._graph_warm:
-                # first step with this configuration runs eagerly: allocates workspaces, configures kernel attributes
                 self._graph_warm.add(key)
-                self._batch_body(exp, cur, local, chunk)
-                return
+                return False
             calls0, launches0 = _lib.CALLS, self.launches
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._batch_body(exp, cur, local, chunk)
+                fn()
             entry = (graph, _lib.CALLS - calls0, self.launches - launches0)
             self.launches = launches0
             _lib.CALLS = calls0
@@ -245,6 +249,30 @@ class PPOLearner(object):
         graph.replay()
         _lib.CALLS += n_calls
         self.launches += n_launch
+        return True
+
+    def _batch_step(self, exp, idx, local, chunk):
+        """One optimiser step on this rank's share `idx` of a batch: eager, or as replayed CUDA graphs.  With several
+        ranks the step is two graphs (forward/backward, clip+Adam) with the NCCL allreduce between them."""
+        if not self.use_cuda_graph or _lib._TIMING is not None:
+            self._batch_body(exp, idx, local, chunk)
+            return
+        if self._idx_cur is None or self._idx_cur.numel() < local:
+            self._idx_cur = torch.empty(local, dtype=torch.int64, device=self._params.device)
+        cur = self._idx_cur[:local]
+        cur.copy_(idx)      # the graph reads its indices from a fixed buffer; the ring origin from exp.start_dev
+        key = (exp.ring("states").data_ptr(), exp.capacity, local, chunk, float(self.clip_range), float(self.ent_coef),
+               self.batch_size, self.world_size, self.dp_mode, self.policy._stack.fused_ok,
+               self.value_net._stack.fused_ok)
+        if self.world_size == 1:
+            if not self._captured(("step",) + key, lambda: self._batch_body(exp, cur, local, chunk)):
+                self._batch_body(exp, cur, local, chunk)
+        else:
+            if not self._captured(("bwd",) + key, lambda: self._backward_body(exp, cur, local, chunk)):
+                self._backward_body(exp, cur, local, chunk)
+            parallel.allreduce_sum_(self._grads, self._pg)
+            if not self._captured(("opt",) + key, self._apply_step):
+                self._apply_step()
         self.policy._stack.mark_operands_fresh()
         self.value_net._stack.mark_operands_fresh()
 
@@ -263,7 +291,7 @@ class PPOLearner(object):
 
         t1 = time.time()
         B, R = self.batch_size, self.world_size
-        local = B // R
+        local = parallel.rank_rows(0, B, self.rank, R, self.dp_mode)[1]
         chunk = min(local, self.max_chunk_rows)
         for epoch in range(self.n_epochs):
             total = len(exp)
@@ -272,19 +300,17 @@ class PPOLearner(object):
             if n_batches == 0:
                 continue
             for k in range(n_batches):
-                base = k * B + self.rank * local
+                base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
                 self._batch_step(exp, idx_dev[base:base + local], local, chunk)
                 n_iterations += 1
 
         # ---- report: one device -> host readback for the whole call -------------------------------------------
         ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
-        if R > 1:
-            torch.distributed.all_reduce(self._tail[0:8], group=self._pg)
+        parallel.allreduce_sum_(self._tail[0:8], self._pg)
         self._tail_host.copy_(self._tail, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         t = self._tail_host.double().numpy()
-        rows_p = t[4] if t[4] > 0 else 1.0
-        rows_v = t[6] if t[6] > 0 else 1.0
+        avg = parallel.report_from_sums(t[0:8])
 
         if n_iterations == 0:
             n_iterations = 1
@@ -293,10 +319,10 @@ class PPOLearner(object):
         report = {
             "PPO Batch Consumption Time": (time.time() - t1) / n_iterations,
             "Cumulative Model Updates": self.cumulative_model_updates,
-            "Policy Entropy": float(t[0] / rows_p),
-            "Mean KL Divergence": float(t[1] / rows_p),
-            "Value Function Loss": float(t[5] / rows_v),
-            "SB3 Clip Fraction": float(t[2] / rows_p),
+            "Policy Entropy": avg["Policy Entropy"],
+            "Mean KL Divergence": avg["Mean KL Divergence"],
+            "Value Function Loss": avg["Value Function Loss"],
+            "SB3 Clip Fraction": avg["SB3 Clip Fraction"],
             "Policy Update Magnitude": float(np.sqrt(t[8])),
             "Value Function Update Magnitude": float(np.sqrt(t[9])),
         }

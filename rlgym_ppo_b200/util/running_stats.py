@@ -57,6 +57,21 @@ class WelfordRunningStat(object):
             self._h_count = int(d["count"].item())
             self._dev_is_newer = False
 
+    def broadcast_(self, src=0, group=None):
+        """Make every rank's statistics those of rank `src` (device to device over NCCL, no host round trip).  Used by
+        the sharded data-parallel learner: the reference updates its return statistics from the first 150 returns of
+        ONE rollout (learner.py:368-372); with one rollout per rank that is rank 0's, and every rank must normalise
+        rewards with the same scale."""
+        import torch.distributed as dist
+        d = self._push()
+        pack = torch.cat((d["mean"], d["m2"], d["std"], d["mean_out"]))
+        dist.broadcast(pack, src=src, group=group)
+        dist.broadcast(d["count"], src=src, group=group)
+        n = self._dim
+        d["mean"].copy_(pack[0:n]); d["m2"].copy_(pack[n:2 * n]); d["std"].copy_(pack[2 * n:3 * n])
+        d["mean_out"].copy_(pack[3 * n:4 * n])
+        self._dev_is_newer = True
+
     def device_std(self):
         """f32[dim] device tensor holding `std` (running_stats.py:60-69); no host synchronisation."""
         return self._push()["std"]
