@@ -275,6 +275,10 @@ def b200_arm(args, wl):
 
     # ---- (3) per-kernel pass for the roofline object (rank 0; not part of the timed numbers) --------------------------
     roofline, kernels = None, None
+    if rank != 0 and world > 1:
+        flush_buf.zero_()
+        step(pool_dev[it % n_pool])      # the collectives of rank 0's instrumented step need their peers
+        it += 1
     if rank == 0:
         peaks = {}
         try:

@@ -172,6 +172,7 @@ class Stack:
                 "x": torch.zeros((cap, self.in_pad), dtype=BF16, device=self.device),
             }
             self._ws_rows = cap
+            self.ws_gen = getattr(self, "ws_gen", 0) + 1      # captured graphs hold these addresses
             self.__dict__.pop("_net_cache", None)
         return self._ws
 

@@ -18,6 +18,7 @@ from .. import _lib, ops
 from .._staging import Stager
 
 _PERM_POOL = None
+_NEXT_UID = [0]
 FIELDS = ("states", "actions", "log_probs", "rewards", "next_states", "dones", "truncated", "values", "advantages")
 _WIDE = ("states", "next_states")
 
@@ -73,6 +74,8 @@ class ExperienceBuffer(object):
             self._rings[f] = torch.zeros(shape, dtype=torch.float32, device=self.device)
         self.states_bf16 = torch.zeros((cap, self.obs_pad), dtype=torch.bfloat16, device=self.device)
         self.start_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        _NEXT_UID[0] += 1
+        self.uid = _NEXT_UID[0]     # identity of this set of rings (a freed buffer's addresses can be handed out again)
         self._stager = Stager(self.device)
 
     def ring(self, field):

@@ -147,6 +147,7 @@ class PPOLearner(object):
         if self._mb is None or self._mb["rows"] < rows:
             dev = self._params.device
             f = lambda: torch.empty(rows, dtype=torch.float32, device=dev)  # noqa: E731
+            self._mb_gen = getattr(self, "_mb_gen", 0) + 1
             self._mb = {"rows": rows, "actions": f(), "old_logp": f(), "targets": f(), "adv": f(),
                         "x": torch.zeros((rows, self.policy._stack.in_pad), dtype=torch.bfloat16, device=dev)}
         return self._mb
@@ -261,9 +262,11 @@ class PPOLearner(object):
             self._idx_cur = torch.empty(local, dtype=torch.int64, device=self._params.device)
         cur = self._idx_cur[:local]
         cur.copy_(idx)      # the graph reads its indices from a fixed buffer; the ring origin from exp.start_dev
-        key = (exp.ring("states").data_ptr(), exp.capacity, local, chunk, float(self.clip_range), float(self.ent_coef),
-               self.batch_size, self.world_size, self.dp_mode, self.policy._stack.fused_ok,
-               self.value_net._stack.fused_ok)
+        # everything a captured graph bakes in: buffer identity, workspace generations (addresses), scalar arguments
+        key = (exp.uid, local, chunk, float(self.clip_range), float(self.ent_coef), self.batch_size, self.world_size,
+               self.dp_mode, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
+               getattr(self.policy._stack, "ws_gen", 0), getattr(self.value_net._stack, "ws_gen", 0),
+               self._idx_cur.data_ptr())
         if self.world_size == 1:
             if not self._captured(("step",) + key, lambda: self._batch_body(exp, cur, local, chunk)):
                 self._batch_body(exp, cur, local, chunk)
