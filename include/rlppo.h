@@ -93,6 +93,12 @@ typedef struct rlppo_append_field {
 } rlppo_append_field;
 int rlppo_ring_append_fields(const rlppo_append_field* h_fields, int n_fields, int64_t capacity,
                              int64_t phys_first, int64_t n_rows, void* stream);
+/* Same, with the ring position kept ON THE DEVICE: d_state = int64[2] {start, size} (logical row 0 lives at physical row
+ * `start`, `size` valid rows).  Rows go to (start + size + i) % capacity and d_state is advanced afterwards exactly as
+ * `_cat` would (experience_buffer.py:17-37: once full, the oldest rows fall out).  Nothing about the position is baked
+ * into the launch, so a CUDA graph that contains this call keeps following the ring when it is replayed. */
+int rlppo_ring_append_fields_dev(const rlppo_append_field* h_fields, int n_fields, int64_t capacity,
+                                 int64_t* d_state, int64_t n_rows, void* stream);
 
 /* ---- (c-2) minibatch gather: experience_buffer.py:82-102 _get_samples ------------------------------
  * idx: int64[B] LOGICAL indices (a slice of RandomState.permutation, generated on the host so the

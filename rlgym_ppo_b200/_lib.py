@@ -37,6 +37,7 @@ _SIGS = {
     "rlppo_welford_update": ([_P, _P, _P, _P, _I, _L, _I, _P, _P, _P], _I),
     "rlppo_ring_append": ([_P, _L, _P, _L, _L, _L, _P, _I, _L, _L, _I, _P], _I),
     "rlppo_ring_append_fields": ([_P, _I, _L, _L, _L, _P], _I),
+    "rlppo_ring_append_fields_dev": ([_P, _I, _L, _P, _L, _P], _I),
     "rlppo_gather_batch": ([_P, _P, _P, _P, _P, _L, _P, _L, _I, _L, _L, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P], _I),
     "rlppo_host_permutation": ([_P, _P, _L, _P], _I),
     "rlppo_rows_to_bf16": ([_P, _L, _L, _I, _P, _L, _P], _I),

@@ -83,42 +83,77 @@ __global__ void ring_append_flat_kernel(float* ring, int64_t capacity, int64_t p
     ring[phys] = F64 ? (float)static_cast<const double*>(src)[i] : static_cast<const float*>(src)[i];
 }
 
-// All fields of one submit in ONE launch: blockIdx.y = field, 64 rows per block (8 warps x 8 rows for wide fields,
-// the first 64 threads for scalar fields).
+// All fields of one submit in ONE launch: blockIdx.y = field, 64 rows per block.  Wide fields are copied as a flat run
+// of elements (64 rows x width, contiguous in the source and -- away from the wrap -- in the ring): every thread has four
+// independent loads in flight before its first store.  d_state (optional) = device int64[2] {start, size} of the ring:
+// the append position is then (start + size) % capacity, read on the device, so a captured CUDA graph follows the ring.
 constexpr int kMaxAppendFields = 12;
 struct AppendFields {
     rlppo_append_field f[kMaxAppendFields];
 };
-__global__ void ring_append_fields_kernel(AppendFields fs, int64_t capacity, int64_t phys_first, int64_t n_rows) {
+__device__ __forceinline__ float append_load(const rlppo_append_field& f, int64_t row, int c) {
+    return f.src_is_f64 ? (float)__ldg(static_cast<const double*>(f.src) + row * f.src_ld + c)
+                        : __ldg(static_cast<const float*>(f.src) + row * f.src_ld + c);
+}
+__global__ void __launch_bounds__(256)
+ring_append_fields_kernel(AppendFields fs, int64_t capacity, int64_t phys_first, const int64_t* __restrict__ d_state,
+                          int64_t n_rows) {
+    if (d_state != nullptr) phys_first = (__ldg(d_state) + __ldg(d_state + 1)) % capacity;
     const rlppo_append_field& f = fs.f[blockIdx.y];
     const int64_t row0 = (int64_t)blockIdx.x * 64;
+    const int rows = (int)min((int64_t)64, n_rows - row0);
+    if (rows <= 0) return;
+    int64_t phys0 = phys_first + row0;
+    if (phys0 >= capacity) phys0 -= capacity;
+    const int wrap = (int)min((int64_t)rows, capacity - phys0);   // rows [wrap, rows) continue at physical row 0
     if (f.width == 1 && f.ring_bf16 == nullptr) {
-        const int64_t row = row0 + threadIdx.x;
-        if (threadIdx.x < 64 && row < n_rows) {
-            int64_t phys = phys_first + row;
-            if (phys >= capacity) phys -= capacity;
-            f.ring[phys * f.ring_ld] = f.src_is_f64 ? (float)static_cast<const double*>(f.src)[row * f.src_ld]
-                                                    : static_cast<const float*>(f.src)[row * f.src_ld];
+        if ((int)threadIdx.x < rows) {
+            const int r = threadIdx.x;
+            const int64_t phys = r < wrap ? phys0 + r : (int64_t)(r - wrap);
+            f.ring[phys * f.ring_ld] = append_load(f, row0 + r, 0);
         }
         return;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ncol = f.ring_bf16 ? (int)f.bf16_ld : f.width;
-    for (int r = warp; r < 64; r += 8) {
-        const int64_t row = row0 + r;
-        if (row >= n_rows) break;
-        int64_t phys = phys_first + row;
-        if (phys >= capacity) phys -= capacity;
-        for (int c = lane; c < ncol; c += 32) {
-            float x = 0.f;
-            if (c < f.width) {
-                x = f.src_is_f64 ? (float)static_cast<const double*>(f.src)[row * f.src_ld + c]
-                                 : static_cast<const float*>(f.src)[row * f.src_ld + c];
-                f.ring[phys * f.ring_ld + c] = x;
+    const int W = f.width;
+    const int total = rows * W;
+    const float inv_w = 1.0f / (float)W;
+    for (int e0 = threadIdx.x; e0 < total; e0 += 1024) {
+        float x[4];
+        int r[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 256;
+            if (e < total) {
+                r[u] = (int)(((float)e + 0.5f) * inv_w);   // exact: e < 2^18, W <= 4096 (checked on the host)
+                c[u] = e - r[u] * W;
+                x[u] = append_load(f, row0 + r[u], c[u]);
             }
-            if (f.ring_bf16) f.ring_bf16[phys * f.bf16_ld + c] = rlppo::f32_to_bf16_bits(x);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * 256;
+            if (e < total) {
+                const int64_t phys = r[u] < wrap ? phys0 + r[u] : (int64_t)(r[u] - wrap);
+                f.ring[phys * f.ring_ld + c[u]] = x[u];
+                if (f.ring_bf16) f.ring_bf16[phys * f.bf16_ld + c[u]] = rlppo::f32_to_bf16_bits(x[u]);
+            }
         }
     }
+    if (f.ring_bf16 != nullptr && f.bf16_ld > W) {   // zero padding of the bf16 rows
+        const int pad = (int)f.bf16_ld - W;
+        for (int e = threadIdx.x; e < rows * pad; e += 256) {
+            const int r = e / pad, c = W + (e - r * pad);
+            const int64_t phys = r < wrap ? phys0 + r : (int64_t)(r - wrap);
+            f.ring_bf16[phys * f.bf16_ld + c] = 0;
+        }
+    }
+}
+// {start, size} <- state after appending n_rows (the host mirrors the same arithmetic, experience_buffer.py)
+__global__ void ring_advance_kernel(int64_t* state, int64_t n_rows, int64_t capacity) {
+    const int64_t start = state[0], size = state[1];
+    const int64_t over = size + n_rows > capacity ? size + n_rows - capacity : 0;
+    state[0] = (start + over) % capacity;
+    state[1] = size + n_rows > capacity ? capacity : size + n_rows;
 }
 
 // ---- gather ---------------------------------------------------------------------------------------------
@@ -247,9 +282,8 @@ int rlppo_ring_append(float* ring, int64_t ring_ld, uint16_t* ring_bf16, int64_t
     return RLPPO_OK;
 }
 
-int rlppo_ring_append_fields(const rlppo_append_field* h_fields, int n_fields, int64_t capacity, int64_t phys_first,
-                             int64_t n_rows, void* stream) {
-    RLPPO_REQUIRE_DEVICE();
+static int append_fields_impl(const rlppo_append_field* h_fields, int n_fields, int64_t capacity, int64_t phys_first,
+                              int64_t* d_state, int64_t n_rows, cudaStream_t s) {
     RLPPO_CHECK_ARG(h_fields && n_fields >= 1 && n_fields <= kMaxAppendFields, "1..%d fields", kMaxAppendFields);
     RLPPO_CHECK_ARG(capacity > 0 && n_rows >= 0 && n_rows <= capacity && phys_first >= 0 && phys_first < capacity,
                     "bad ring position");
@@ -257,14 +291,32 @@ int rlppo_ring_append_fields(const rlppo_append_field* h_fields, int n_fields, i
     AppendFields fs;
     for (int i = 0; i < n_fields; ++i) {
         const rlppo_append_field& f = h_fields[i];
-        RLPPO_CHECK_ARG(f.ring && f.src && f.width >= 1 && f.ring_ld >= 1 && f.src_ld >= 1, "bad field %d", i);
+        RLPPO_CHECK_ARG(f.ring && f.src && f.width >= 1 && f.width <= 4096 && f.ring_ld >= 1 && f.src_ld >= 1,
+                        "bad field %d", i);
         RLPPO_CHECK_ARG(!f.ring_bf16 || (f.bf16_ld >= f.width && f.bf16_ld % 8 == 0), "field %d: bad bf16_ld", i);
         fs.f[i] = f;
     }
     dim3 grid((unsigned)((n_rows + 63) / 64), (unsigned)n_fields);
-    ring_append_fields_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(fs, capacity, phys_first, n_rows);
+    ring_append_fields_kernel<<<grid, 256, 0, s>>>(fs, capacity, phys_first, d_state, n_rows);
     RLPPO_LAUNCH_CHECK();
+    if (d_state != nullptr) {
+        ring_advance_kernel<<<1, 1, 0, s>>>(d_state, n_rows, capacity);
+        RLPPO_LAUNCH_CHECK();
+    }
     return RLPPO_OK;
+}
+
+int rlppo_ring_append_fields(const rlppo_append_field* h_fields, int n_fields, int64_t capacity, int64_t phys_first,
+                             int64_t n_rows, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    return append_fields_impl(h_fields, n_fields, capacity, phys_first, nullptr, n_rows, static_cast<cudaStream_t>(stream));
+}
+
+int rlppo_ring_append_fields_dev(const rlppo_append_field* h_fields, int n_fields, int64_t capacity, int64_t* d_state,
+                                 int64_t n_rows, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(d_state != nullptr, "null ring state");
+    return append_fields_impl(h_fields, n_fields, capacity, 0, d_state, n_rows, static_cast<cudaStream_t>(stream));
 }
 
 int rlppo_gather_batch(const float* actions, const float* logp, const float* values, const float* adv,

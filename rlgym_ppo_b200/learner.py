@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
+from ._graphs import GraphCache
 from ._staging import Stager
 from .ppo import ExperienceBuffer, PPOLearner
 from .util import WelfordRunningStat
@@ -33,6 +34,15 @@ _EXP_FIELDS = ("states", "actions", "log_probs", "rewards", "next_states", "done
 
 def _f32(t):
     return t if t.dtype == torch.float32 else t.to(torch.float32)
+
+
+def _staged_dtype(x):
+    """dtype a rollout array keeps on the device: f32/f64 as given (the kernels cast f64 like torch.as_tensor(...,
+    dtype=float32) does), anything else is converted to f32 on the host first (see Stager.to_device)."""
+    dt = x.dtype if hasattr(x, "dtype") else np.asarray(x).dtype
+    if dt in (torch.float64, np.float64) or str(dt) in ("float64", "torch.float64"):
+        return torch.float64
+    return torch.float32
 
 
 class Learner(object):
@@ -301,45 +311,69 @@ class Learner(object):
         max_returns_per_stats_increment and experience_buffer.
         """
         buf = self.experience_buffer
-        value_net = self.ppo_learner.value_net
+        ppo = self.ppo_learner
+        value_net = ppo.value_net
         vst = value_net._stack
         dev = vst.device
         stager = getattr(self, "_stager", None)
         if stager is None:
-            stager = Stager(dev)
-            try:
-                self._stager = stager
-            except AttributeError:
-                pass
-        d = {name: stager.to_device(arr, "exp." + name) for name, arr in zip(_EXP_FIELDS, experience)}
-        states = _f32(d["states"])
-        n = int(states.shape[0])
+            stager = self._stager = Stager(dev)
+        n = int(experience[0].shape[0]) if hasattr(experience[0], "shape") else len(experience[0])
         if n == 0:
             return
-        obs = int(states.shape[1])
+        # ---- stage the 7 arrays into persistent device slots (one async copy each; fixed addresses) -------------------
+        shapes = tuple((tuple(np.shape(x)), _staged_dtype(x)) for x in experience)
+        stage = getattr(self, "_exp_stage", None)
+        if stage is None or stage["shapes"] != shapes:
+            stage = {"shapes": shapes, "gen": (0 if stage is None else stage["gen"] + 1)}
+            for name, (shape, dt) in zip(_EXP_FIELDS, shapes):
+                stage[name] = torch.empty(shape, dtype=dt, device=dev)
+            n_inc = min(int(self.max_returns_per_stats_increment), n) if self.standardize_returns else 0
+            stage["values"] = torch.empty(n + 1, dtype=torch.float32, device=dev)
+            stage["out"] = tuple(torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+            stage["head"] = torch.empty(n_inc, dtype=torch.float64, device=dev) if n_inc else None
+            stage["gae_ws"] = ops.gae_workspace(n, dev)
+            self._exp_stage = stage
+        d = {name: stager.to_device(arr, "exp." + name, out=stage[name]) for name, arr in zip(_EXP_FIELDS, experience)}
+        obs = int(d["states"].shape[1])
         if buf._rings is None:
             buf._allocate(obs)
+        vst.workspace(n + 1)
+        vst.refresh_operands()
+        ret_std = self.return_stats.device_std() if self.standardize_returns else None     # learner.py:356
+        n_inc = 0 if stage["head"] is None else stage["head"].numel()
 
-        # value-net input [states ; next_states[-1]] (learner.py:347-349) as bf16 rows, straight from the staged arrays
-        ws = vst.workspace(n + 1)
-        x = ws["x"]
-        ops.rows_to_bf16(states, x)
-        ops.rows_to_bf16(_f32(d["next_states"])[n - 1:n], x[n:n + 1])
-        values = value_net.values_from_bf16(x, n + 1)                      # :352, stays on the device
+        def body():
+            """Device work only (what the CUDA graph captures): value net on [states ; next_states[-1]]
+            (learner.py:347-352), GAE (:358-366), return statistics (:368-372), the nine ring appends (:375-385)."""
+            states = _f32(d["states"])
+            x = vst.workspace(n + 1)["x"]
+            ops.rows_to_bf16(states, x)
+            ops.rows_to_bf16(_f32(d["next_states"])[n - 1:n], x[n:n + 1])
+            values = value_net.values_from_bf16(x, n + 1, out=stage["values"])      # stays on the device
+            vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
+                                 self.gae_lambda, ret_std, out=stage["out"], ret_head64=stage["head"],
+                                 ws=stage["gae_ws"])
+            if n_inc:
+                self.return_stats.increment_device(stage["head"], n_inc)   # after the scan has read std
+            fields = dict(d)
+            fields["values"], fields["advantages"] = vt, adv
+            buf.append_device(fields)
 
-        ret_std = self.return_stats.device_std() if self.standardize_returns else None     # :356
-        n_inc = min(int(self.max_returns_per_stats_increment), n) if self.standardize_returns else 0
-        head = torch.empty(n_inc, dtype=torch.float64, device=dev) if n_inc else None
-        vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
-                             self.gae_lambda, ret_std, ret_head64=head)    # :358-366
+        graphs = getattr(self, "_add_graphs", None)
+        if graphs is None:
+            graphs = self._add_graphs = GraphCache()
+        key = (n, obs, stage["gen"], buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
+               float(self.gae_gamma), float(self.gae_lambda), bool(self.standardize_returns), vst.fused_ok)
+        if not (getattr(ppo, "use_cuda_graph", False) and _lib._TIMING is None and graphs.replay(key, body)):
+            body()
+        # host mirrors of what the device work did
+        buf.advance_host(min(n, buf.capacity))
         if n_inc:
-            self.return_stats.increment_device(head, n_inc)               # :368-372 (after the scan read std)
-            ppo = self.ppo_learner
+            self.return_stats._dev_is_newer = True
             if getattr(ppo, "world_size", 1) > 1 and getattr(ppo, "dp_mode", "") == "sharded":
                 # one rollout per rank: the statistics follow rank 0's (the head of the concatenated rollout)
                 self.return_stats.broadcast_(src=0, group=getattr(ppo, "_pg", None))
-        d["values"], d["advantages"] = vt, adv
-        buf.submit_device(d)                                               # :375-385
 
     def save(self, cumulative_timesteps):
         """Checkpoint in the reference's layout (learner.py:387-444)."""

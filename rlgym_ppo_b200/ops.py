@@ -39,7 +39,13 @@ def _workspace(n, device):
     return ws
 
 
-def gae(rew, done, trunc, values, gamma, lmbda, ret_std=None, out=None, ret_head64=None, carry_in=None):
+def gae_workspace(n, device):
+    """A private scan workspace for n steps (callers that capture CUDA graphs must own theirs: the shared one is
+    re-allocated when a longer rollout arrives)."""
+    return torch.empty(max(_lib.gae_workspace_bytes(n), 1 << 12), dtype=torch.uint8, device=device)
+
+
+def gae(rew, done, trunc, values, gamma, lmbda, ret_std=None, out=None, ret_head64=None, carry_in=None, ws=None):
     """compute_gae on device.  rew/done f32[n], trunc f32|f64[n], values f32[n+1], ret_std f32[1] tensor or
     None.  Returns (value_targets, advantages, returns) f32[n]."""
     n = rew.numel()
@@ -56,7 +62,8 @@ def gae(rew, done, trunc, values, gamma, lmbda, ret_std=None, out=None, ret_head
         vt, adv, ret = out
     if n == 0:
         return vt, adv, ret
-    ws = _workspace(n, rew.device)
+    if ws is None:
+        ws = _workspace(n, rew.device)
     n_head = 0 if ret_head64 is None else min(ret_head64.numel(), n)
     call("rlppo_gae_f32", ptr(rew), ptr(done), ptr(trunc), int(trunc.dtype == torch.float64), ptr(values), n,
          float(gamma), float(lmbda), ptr(ret_std), ptr(adv), ptr(vt), ptr(ret), ptr(ret_head64), n_head,
@@ -93,8 +100,9 @@ def ring_append(ring, phys_first, src, n_rows, ring_bf16=None):
          work=("byte", int(n_rows) * width * (src.element_size() + 4 + (2 if ring_bf16 is not None else 0))))
 
 
-def ring_append_fields(fields, capacity, phys_first, n_rows):
-    """fields: list of (ring, src, ring_bf16|None).  One launch for all of them."""
+def ring_append_fields(fields, capacity, phys_first, n_rows, state_dev=None):
+    """fields: list of (ring, src, ring_bf16|None).  One launch for all of them.  With `state_dev` (int64[2] device
+    tensor {start, size}) the position is read -- and advanced -- on the device and `phys_first` is ignored."""
     arr = (_lib.AppendField * len(fields))()
     nbytes = 0
     for a, (ring, src, rb) in zip(arr, fields):
@@ -105,6 +113,11 @@ def ring_append_fields(fields, capacity, phys_first, n_rows):
         a.src_is_f64 = int(src.dtype == torch.float64)
         a.width = 1 if ring.dim() == 1 else ring.shape[1]
         nbytes += int(n_rows) * (a.width * (src.element_size() + 4) + (0 if rb is None else 2 * rb.stride(0)))
+    if state_dev is not None:
+        assert state_dev.dtype == torch.int64 and state_dev.numel() == 2 and state_dev.is_cuda
+        call("rlppo_ring_append_fields_dev", ctypes.cast(arr, ctypes.c_void_p), len(fields), int(capacity),
+             ptr(state_dev), int(n_rows), stream_ptr(), work=("byte", nbytes))
+        return
     call("rlppo_ring_append_fields", ctypes.cast(arr, ctypes.c_void_p), len(fields), int(capacity), int(phys_first),
          int(n_rows), stream_ptr(), work=("byte", nbytes))
 

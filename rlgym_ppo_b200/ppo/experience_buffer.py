@@ -55,6 +55,7 @@ class ExperienceBuffer(object):
         self.states_bf16 = None
         self._stager = None
         self.start_dev = None
+        self.state_dev = None
         self._spec = None
         self._pin = [None, None, None]
         self._pin_ev = [None, None, None]
@@ -73,7 +74,10 @@ class ExperienceBuffer(object):
             shape = (cap, self.obs_dim) if f in _WIDE else (cap,)
             self._rings[f] = torch.zeros(shape, dtype=torch.float32, device=self.device)
         self.states_bf16 = torch.zeros((cap, self.obs_pad), dtype=torch.bfloat16, device=self.device)
-        self.start_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # {start, size} mirrored on the device: the append and gather kernels read the ring position from here, so a
+        # captured CUDA graph keeps following the ring as it fills and wraps
+        self.state_dev = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.start_dev = self.state_dev[0:1]
         _NEXT_UID[0] += 1
         self.uid = _NEXT_UID[0]     # identity of this set of rings (a freed buffer's addresses can be handed out again)
         self._stager = Stager(self.device)
@@ -108,25 +112,35 @@ class ExperienceBuffer(object):
 
     def submit_device(self, dev):
         """Append rows that already live in HBM: dict field -> contiguous f32/f64 device tensor."""
+        rows = self.append_device(dev)
+        if rows:
+            self.advance_host(rows)
+
+    def append_device(self, dev):
+        """Device half of submit_device (enqueue only, CUDA-graph capturable): all nine rings in one launch, at the
+        position held in state_dev, which the launch also advances.  Returns the number of rows appended; the caller
+        mirrors it on the host with advance_host()."""
         n = int(dev["rewards"].shape[0])
         for f in FIELDS:
             assert int(dev[f].shape[0]) == n, f"field {f} has {dev[f].shape[0]} rows, expected {n}"
         if n == 0:
-            return
+            return 0
         cap = self.capacity
         skip = max(0, n - cap)          # `_cat`: when the new block alone exceeds max_size keep its tail
         rows = n - skip
-        if rows == cap:
-            self.start, self.size = 0, 0
-        first = (self.start + self.size) % cap
         fields = [(self._rings[f], (dev[f][skip:] if skip else dev[f]),
                    self.states_bf16 if f == "states" else None) for f in FIELDS]
-        ops.ring_append_fields(fields, cap, first, rows)            # all nine rings, one launch
+        ops.ring_append_fields(fields, cap, 0, rows, state_dev=self.state_dev)
+        return rows
+
+    def advance_host(self, rows):
+        """Host mirror of the device-side ring advance (the arithmetic of `_cat`, experience_buffer.py:17-37): rows were
+        written at (start + size) % capacity; once full, the oldest rows fall out."""
+        cap = self.capacity
         self._last_rows = rows
         over = max(0, self.size + rows - cap)
         self.start = (self.start + over) % cap
         self.size = min(cap, self.size + rows)
-        self.start_dev.fill_(self.start)     # device copy of the ring origin (captured graphs read it)
 
     # ---- sampling (experience_buffer.py:82-102) ------------------------------------------------------------
     def _index_tensor(self, indices):
@@ -183,6 +197,16 @@ class ExperienceBuffer(object):
         ev.record()
         self._pin_ev[self._pin_of_last] = ev
         return dev
+
+    def next_permutation_into(self, dst):
+        """next_permutation() uploaded (async) into the caller's int64 device buffer `dst` (len == len(self)): a fixed
+        address, so a captured CUDA graph can read its indices from it."""
+        perm = self.next_permutation()
+        assert dst.numel() == perm.numel() and dst.dtype == torch.int64
+        dst.copy_(perm, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pin_ev[self._pin_of_last] = ev
 
     def _draw(self, key, pos, total):
         self._pin_i = (self._pin_i + 1) % 3

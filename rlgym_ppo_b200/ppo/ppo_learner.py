@@ -141,6 +141,10 @@ class PPOLearner(object):
         self._graphs = {}
         self._graph_warm = set()
         self._idx_cur = None
+        self._perm_dev = None
+        # capture the NCCL allreduces inside the whole-call graph when data parallel (torch's NCCL process group is
+        # graph-capturable); off -> two graphs per optimiser step with an eager allreduce between them
+        self.graph_collectives = os.environ.get("RLPPO_GRAPH_COLLECTIVES", "1") != "0"
 
     # ---- workspaces ----------------------------------------------------------------------------------------
     def _minibatch_buffers(self, rows):
@@ -262,11 +266,7 @@ class PPOLearner(object):
             self._idx_cur = torch.empty(local, dtype=torch.int64, device=self._params.device)
         cur = self._idx_cur[:local]
         cur.copy_(idx)      # the graph reads its indices from a fixed buffer; the ring origin from exp.start_dev
-        # everything a captured graph bakes in: buffer identity, workspace generations (addresses), scalar arguments
-        key = (exp.uid, local, chunk, float(self.clip_range), float(self.ent_coef), self.batch_size, self.world_size,
-               self.dp_mode, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
-               getattr(self.policy._stack, "ws_gen", 0), getattr(self.value_net._stack, "ws_gen", 0),
-               self._idx_cur.data_ptr())
+        key = self._graph_key(exp, local, chunk) + (self._idx_cur.data_ptr(),)
         if self.world_size == 1:
             if not self._captured(("step",) + key, lambda: self._batch_body(exp, cur, local, chunk)):
                 self._batch_body(exp, cur, local, chunk)
@@ -279,38 +279,70 @@ class PPOLearner(object):
         self.policy._stack.mark_operands_fresh()
         self.value_net._stack.mark_operands_fresh()
 
+    def _graph_key(self, exp, local, chunk):
+        """Everything a captured graph bakes in: buffer identity, workspace generations (addresses), scalar arguments."""
+        return (exp.uid, local, chunk, float(self.clip_range), float(self.ent_coef), self.batch_size, self.world_size,
+                self.dp_mode, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
+                getattr(self.policy._stack, "ws_gen", 0), getattr(self.value_net._stack, "ws_gen", 0))
+
+    def _learn_body(self, exp, n_batches, local, chunk):
+        """Device work of one learn() call (ppo_learner.py:110-220): update-magnitude baseline, every optimiser step of
+        every epoch (indices from self._perm_dev, one row per epoch), update magnitudes, the report scalars to pinned
+        host memory.  Enqueue only -- this is what the whole-call CUDA graph captures."""
+        B, R = self.batch_size, self.world_size
+        self._before.copy_(self._params)          # update-magnitude baseline (:110-116), stays on the device
+        self._tail.zero_()
+        for epoch in range(self.n_epochs):
+            for k in range(n_batches):
+                base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
+                self._batch_body(exp, self._perm_dev[epoch, base:base + local], local, chunk)
+        ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
+        parallel.allreduce_sum_(self._tail[0:8], self._pg)
+        self._tail_host.copy_(self._tail, non_blocking=True)
+
     def learn(self, exp):
         """
         Compute PPO updates with an experience buffer (ppo_learner.py:92-238).
         Returns the reference's report dictionary (same keys).
         """
-        n_iterations = 0
         self.launches = 0
         self.policy._stack.refresh_operands()
         self.value_net._stack.refresh_operands()
         self._sync_lr()
-        self._before.copy_(self._params)          # update-magnitude baseline (:110-116), stays on the device
-        self._tail.zero_()
 
         t1 = time.time()
-        B, R = self.batch_size, self.world_size
+        B, R, E = self.batch_size, self.world_size, self.n_epochs
         local = parallel.rank_rows(0, B, self.rank, R, self.dp_mode)[1]
         chunk = min(local, self.max_chunk_rows)
-        for epoch in range(self.n_epochs):
-            total = len(exp)
-            idx_dev = exp.next_permutation_device()             # experience_buffer.py:98, once per epoch
-            n_batches = total // B                              # :100, remainder dropped
-            if n_batches == 0:
-                continue
-            for k in range(n_batches):
-                base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
-                self._batch_step(exp, idx_dev[base:base + local], local, chunk)
-                n_iterations += 1
+        total = len(exp)
+        n_batches = total // B                                  # experience_buffer.py:100, remainder dropped
+        # One `rng.permutation(total)` per epoch (experience_buffer.py:98), drawn in the reference's order, uploaded into
+        # one [epochs, total] device buffer before any device work: the whole call is then a single graph replay.
+        if self._perm_dev is None or self._perm_dev.shape[0] != E or self._perm_dev.shape[1] < total:
+            self._perm_dev = torch.empty((E, max(total, 1)), dtype=torch.int64, device=self._params.device)
+        for epoch in range(E):
+            exp.next_permutation_into(self._perm_dev[epoch, :total])
+        n_iterations = E * n_batches
 
-        # ---- report: one device -> host readback for the whole call -------------------------------------------
-        ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
-        parallel.allreduce_sum_(self._tail[0:8], self._pg)
-        self._tail_host.copy_(self._tail, non_blocking=True)
+        whole = (self.use_cuda_graph and _lib._TIMING is None and n_batches > 0
+                 and (R == 1 or self.graph_collectives))
+        if whole:
+            key = ("learn", total, E, n_batches, self._perm_dev.data_ptr()) + self._graph_key(exp, local, chunk)
+            if not self._captured(key, lambda: self._learn_body(exp, n_batches, local, chunk)):
+                self._learn_body(exp, n_batches, local, chunk)
+            self.policy._stack.mark_operands_fresh()
+            self.value_net._stack.mark_operands_fresh()
+        else:
+            self._before.copy_(self._params)
+            self._tail.zero_()
+            for epoch in range(E):
+                for k in range(n_batches):
+                    base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
+                    self._batch_step(exp, self._perm_dev[epoch, base:base + local], local, chunk)
+            # ---- report: one device -> host readback for the whole call ---------------------------------------
+            ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
+            parallel.allreduce_sum_(self._tail[0:8], self._pg)
+            self._tail_host.copy_(self._tail, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         t = self._tail_host.double().numpy()
         avg = parallel.report_from_sums(t[0:8])

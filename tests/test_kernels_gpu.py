@@ -222,6 +222,36 @@ def test_ring_append_and_gather_vs_oracle(ops):
         assert torch.equal(got[:, :obs], want) and float(got[:, obs:].float().abs().max()) == 0.0
 
 
+def test_ring_append_fields_device_state_vs_oracle(ops):
+    """All nine rings in one launch with the ring position kept on the device (rlppo_ring_append_fields_dev): every
+    logical field equals the FIFO oracle (`_cat`, experience_buffer.py:17-37) after appends that fill, wrap inside a
+    64-row block, exactly fill and overfill the ring; f64 sources are cast like torch.as_tensor(..., float32)."""
+    rng = np.random.RandomState(9)
+    cap, obs, pad = 777, 89, 96
+    rings = {k: torch.zeros((cap, obs) if k in ("states", "next_states") else (cap,), device=DEV) for k in O.FIELDS}
+    rings_bf16 = torch.full((cap, pad), 7.0, dtype=torch.bfloat16, device=DEV)   # padding must come out as zeros
+    state = torch.zeros(2, dtype=torch.int64, device=DEV)
+    ob = O.BufferOracle(cap, 123)
+    start = size = 0
+    for n in (300, 100, 450, 777, 70, 5, 776):
+        f = {k: rng.randn(n).astype(np.float32) for k in O.FIELDS}
+        f["states"] = rng.randn(n, obs).astype(np.float32)
+        f["next_states"] = rng.randn(n, obs).astype(np.float32)
+        f["truncated"] = (rng.rand(n) < 0.1).astype(np.float64)
+        ob.submit(**f)
+        fields = [(rings[k], dev(f[k]), rings_bf16 if k == "states" else None) for k in O.FIELDS]
+        ops.ring_append_fields(fields, cap, 0, n, state_dev=state)
+        over = max(0, size + n - cap)
+        start, size = (start + over) % cap, min(cap, size + n)
+        assert state.cpu().tolist() == [start, size]
+        order = (start + np.arange(size)) % cap
+        for k in O.FIELDS:
+            assert np.array_equal(rings[k].cpu().numpy()[order], ob.f[k].astype(np.float32)), k
+        got = rings_bf16.cpu()[order]
+        assert torch.equal(got[:, :obs], torch.from_numpy(ob.f["states"]).to(torch.bfloat16))
+        assert float(got[:, obs:].float().abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------------------------
 # tensor-core layers
 # ------------------------------------------------------------------------------------------------------------

@@ -447,3 +447,55 @@ def test_speculative_permutation_stream_is_numpys(pkg):
         outs.append((lr._params.clone(), rep))
     assert torch.allclose(outs[0][0], outs[1][0], rtol=0, atol=2e-6)
     assert abs(outs[0][1]["Mean KL Divergence"] - outs[1][1]["Mean KL Divergence"]) < 1e-6
+
+
+def test_graph_replayed_iteration_equals_eager(pkg):
+    """add_new_experience + learn replayed as CUDA graphs (second use of a shape onwards) leave the same experience
+    buffer (bit for bit: value predictions, GAE, ring appends are deterministic), the same return statistics and the
+    same weights (fp32 atomics in the weight-gradient reduction: 2e-6) as the launch-by-launch path -- while the ring
+    fills, wraps, and the rollouts arrive as NumPy arrays, pinned tensors and device tensors."""
+    import contextlib
+    import io
+    from rlgym_ppo_b200.learner import Learner
+    from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
+    from rlgym_ppo_b200.util import WelfordRunningStat
+    obs, act, n, B = 21, 6, 3000, 2048
+    sides = []
+    for use_graph in (True, False):
+        torch.manual_seed(3)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ppo = PPOLearner(obs, act, 0, (64, 64), (64, 64), (0.1, 1.0), B, 2, 3e-4, 3e-4, 0.2, 0.01, B, DEV)
+        ppo.use_cuda_graph = use_graph
+        ns = SimpleNamespace(ppo_learner=ppo, return_stats=WelfordRunningStat(1, device=DEV), standardize_returns=True,
+                             gae_gamma=0.99, gae_lambda=0.95, max_returns_per_stats_increment=150,
+                             experience_buffer=ExperienceBuffer(7000, 5, DEV))
+        rng = np.random.RandomState(11)
+        reports = []
+        for it in range(6):
+            states = rng.randn(n, obs).astype(np.float32)
+            exp = [states, rng.randint(0, act, n).astype(np.float32), (-1.8 + 0.2 * rng.randn(n)).astype(np.float32),
+                   rng.randn(n).astype(np.float32), np.roll(states, -1, 0).copy(),
+                   (rng.rand(n) < 0.02).astype(np.float32), (rng.rand(n) < 0.01).astype(np.float64)]
+            if it % 3 == 1:
+                exp = [torch.from_numpy(a).pin_memory() for a in exp]
+            elif it % 3 == 2:
+                exp = [torch.from_numpy(a).to(DEV) for a in exp]
+            Learner.add_new_experience(ns, tuple(exp))
+            reports.append(ppo.learn(ns.experience_buffer))
+        buf = ns.experience_buffer
+        sides.append(({f: getattr(buf, f).cpu().numpy() for f in ("states", "actions", "rewards", "next_states", "dones",
+                                                                   "truncated", "values", "advantages")},
+                      ns.return_stats.serialize(), ppo._params.clone(), reports, len(buf)))
+    (f0, s0, p0, r0, l0), (f1, s1, p1, r1, l1) = sides
+    assert l0 == l1 == 7000
+    for k in f0:
+        if k in ("values", "advantages"):   # depend on the (atomics-ordered) weights of earlier iterations
+            assert np.allclose(f0[k], f1[k], rtol=1e-4, atol=1e-4), k
+        else:
+            assert np.array_equal(f0[k], f1[k]), k
+    assert np.allclose(s0, s1, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(p0, p1, rtol=0, atol=5e-6)
+    for a, b in zip(r0, r1):
+        assert a["Cumulative Model Updates"] == b["Cumulative Model Updates"]
+        for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
+            assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(b[k])), (k, a[k], b[k])
