@@ -15,17 +15,20 @@
 // GEMMs, which contract over ALL rows, read them back in rlppo_linear_wgrad).  Weights stream from L2 through a
 // 2-stage TMA ring.  In inference mode nothing but x, actions/log-probs or values touches HBM.
 //
-// Warp roles (320 threads, 1 CTA/SM, persistent over tiles):
-//   warp 0      TMA producer: x tile + weight k-blocks
-//   warp 1      TMEM owner; one thread issues tcgen05.mma, TMA-stores finished activation tiles, commits barriers
-//   warps 2..9  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (rows), warps 2-5 the lower half of the columns,
-//               warps 6-9 the upper half.  A k-block of the next A operand is released to the MMA thread as soon as
-//               its columns are written, so GEMM l+1 starts while epilogue l is still running.
-// TWO tiles are in flight per CTA ("slots"): slot s owns one 64 KB activation buffer and one 256-column TMEM
-// accumulator, and every epilogue overwrites its tile IN PLACE (the GEMM that read the buffer has completed by then).
-// The MMA thread and the epilogue warps both walk (phase 0, slot 0), (phase 0, slot 1), (phase 1, slot 0), ... so the
-// tensor core (and the L2 latency of the weight stream) works on one tile while the epilogue warps work on the other.
-// ncu on the first, one-tile version showed the epilogue warps waiting on the accumulator barrier ~40 % of the time.
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles, ONE tile in flight per CTA):
+//   warp 0      TMA producer: the x tile of the NEXT tile into its own staging buffer + weight k-blocks (3-stage ring)
+//   warp 1      TMEM owner; one thread issues tcgen05.mma, TMA-stores finished activation k-blocks, commits barriers
+//   warps 2..9  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 (rows); of every 64-column k-block of the output,
+//               warps 2-5 take the lower 32 columns and warps 6-9 the upper 32.
+// The activation tile (128 rows x <=256 columns bf16, 64 KB) is overwritten IN PLACE by every epilogue (the GEMM that
+// read it has completed by then) and there are TWO 256-column TMEM accumulators: the epilogue of layer l releases the
+// tile k-block by k-block (a_ready[kb], 8 warp arrivals each), and GEMM l+1 -- which accumulates into the OTHER
+// accumulator -- starts on k-block 0 while the epilogue is still producing k-blocks 1..3.  The tensor core therefore
+// trails the epilogue warps by one k-block instead of waiting for the whole tile, and the shared memory a second tile
+// would need holds a deeper weight ring instead.
+// History (profiles/README_r01.md): v1 kept two tiles in flight with one accumulator each and a 2-stage weight ring; its
+// cycle trace showed the MMA thread taking ~4.7k cycles to issue 2k cycles of MMAs per layer (waiting for weight
+// k-blocks: 64 KB in flight per SM cannot cover the L2 latency) and the epilogue warps idle 27 % of the time.
 #include <math.h>
 #include <stdlib.h>
 
@@ -42,19 +45,22 @@ constexpr int KBLK = 64;
 constexpr uint32_t KB_BYTES = TILE_M * KBLK * 2;   // 16 KB: one 64-column k-block of an activation tile
 constexpr uint32_t ACT_BYTES = 4 * KB_BYTES;       // 64 KB
 constexpr uint32_t WST_BYTES = 256 * KBLK * 2;     // 32 KB: one k-block of a weight operand (<= 256 rows)
-constexpr int NWST = 2;
+constexpr int MAX_NWST = 3;
 constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
 constexpr int MAXPH = 2 * MAXL + 1;
 
-constexpr uint32_t OFF_ACT_A = 0;
-constexpr uint32_t OFF_ACT_B = ACT_BYTES;
-constexpr uint32_t OFF_WRING = 2 * ACT_BYTES;
-constexpr uint32_t OFF_BIAS = OFF_WRING + NWST * WST_BYTES;          // (MAXL + 1) * 256 floats
-constexpr uint32_t OFF_ROWX = OFF_BIAS + (MAXL + 1) * 256 * 4;      // [slot][half][128] floats
-constexpr uint32_t ROWX_FLOATS = 2048;                               // per slot: row-wise exchange planes
-constexpr uint32_t OFF_DB = OFF_ROWX + 2 * ROWX_FLOATS * 4;          // (MAXL + 1) * 256 floats: column-sum accumulators
-constexpr uint32_t OFF_BARS = OFF_DB + (MAXL + 1) * 256 * 4;   // 2*NWST + 2 + 2 + 8 + 2 mbarriers, TMEM slot
-constexpr uint32_t SMEM_TOTAL = OFF_BARS + 256 + 1024;              // + slack for 1024-byte alignment
+// shared memory (offsets from the 1024-aligned base): [act 64 KB][x stage in_kb*16 KB][weight ring nwst*32 KB][misc]
+constexpr uint32_t OFF_ACT = 0;
+constexpr uint32_t OFF_XST = ACT_BYTES;
+constexpr uint32_t MISC_BIAS = 0;                                  // (MAXL + 1) * 256 floats
+constexpr uint32_t MISC_ROWX = MISC_BIAS + (MAXL + 1) * 256 * 4;   // 1792 floats: row-wise exchange planes
+constexpr uint32_t ROWX_FLOATS = 1792;
+constexpr uint32_t MISC_DB = MISC_ROWX + ROWX_FLOATS * 4;          // (MAXL + 1) * 256 floats: column-sum accumulators
+constexpr uint32_t MISC_MASK = MISC_DB + (MAXL + 1) * 256 * 4;     // ReLU bit masks: [MAXL][4 k-blocks][256 threads] words
+constexpr uint32_t MISC_BARS = MISC_MASK + MAXL * 4 * kEpiThreads * 4;
+constexpr uint32_t MISC_BYTES = MISC_BARS + 256;
+constexpr uint32_t SMEM_LIMIT = 232448;                            // 227 KB
 
 enum { PH_FWD = 0, PH_FWD_VALUE = 1, PH_HEAD = 2, PH_DGRAD = 3, PH_VALUE_BWD = 4 };
 constexpr uint8_t NO_STORE = 0xFF;
@@ -77,10 +83,11 @@ struct alignas(64) Maps {
 
 struct Params {
     int64_t M;
-    int num_tiles, n_ph, L, in_kb;
+    int num_tiles, n_ph, L, in_kb, nwst;
     int H[MAXL];
     PhaseDesc ph[MAXPH];
-    int tail_map, tail_kb;   // the last epilogue's tile
+    int tail_map, tail_kb;   // the last epilogue's tile (training: TMA-stored)
+    int tail_rel_kb;         // k-blocks the last epilogue releases (consumed by the MMA thread at the end of a tile)
     const float* bias[MAXL + 1];
     float* gbias[MAXL + 1];
     // policy head
@@ -200,54 +207,55 @@ __device__ __forceinline__ void store_chunk16_sw128(uint8_t* buf, int row, int c
 }
 
 struct EpiCtx {
-    uint8_t* smem;
+    uint8_t* act;
     float* s_bias;
     float* s_rowx;
-    uint64_t* a_ready;
-    uint32_t tmem_base;
+    uint32_t* s_mask;     // this thread's column of the mask planes: word (layer * 4 + kb) lives at s_mask[(layer*4+kb) * 256]
+    uint64_t* a_ready;    // [4], one per k-block of the activation tile, 8 arrivals (epilogue warps)
     int lane, quarter, half, row_in_tile;
 };
 
-// End of an epilogue phase for this warp: its TMEM reads are done and its part of the tile is written.  One arrival
-// per warp on the slot's a_ready barrier; the MMA thread may then overwrite the accumulator and read the tile.
-// (A per-k-block release that let the next GEMM start early was tried first: with ONE accumulator per slot it lets the
-// next GEMM overwrite accumulator columns this epilogue has not read yet.)
-__device__ __forceinline__ void release_all(const EpiCtx& e) {
+// This warp's part of output k-block `kb` is written and its TMEM reads for it are done: one arrival per warp; the MMA
+// thread may then read that k-block as the next GEMM's A operand (and TMA-store it).
+__device__ __forceinline__ void release_kb(const EpiCtx& e, int kb) {
     tc_fence_before();
     fence_proxy_async();
     __syncwarp();
-    if (e.lane == 0) mbar_arrive(e.a_ready);
+    if (e.lane == 0) mbar_arrive(e.a_ready + kb);
 }
 
 template <bool POLICY, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_constant__ Maps maps, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* act[2] = {smem + OFF_ACT_A, smem + OFF_ACT_B};   // one buffer per slot
-    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-    float* s_rowx = reinterpret_cast<float*>(smem + OFF_ROWX);
-    float* s_db = reinterpret_cast<float*>(smem + OFF_DB);
-    uint64_t* wfull = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
-    uint64_t* wempty = wfull + NWST;
-    uint64_t* x_full = wempty + NWST;   // [2]
-    uint64_t* x_free = x_full + 2;      // [2]
-    uint64_t* a_ready = x_free + 2;     // [2]: one per slot, 8 arrivals (epilogue warps)
-    uint64_t* acc_full = a_ready + 2;   // [2]
+    uint8_t* act = smem + OFF_ACT;
+    uint8_t* xst = smem + OFF_XST;
+    uint8_t* wring = xst + p.in_kb * KB_BYTES;
+    uint8_t* misc = wring + p.nwst * WST_BYTES;
+    float* s_bias = reinterpret_cast<float*>(misc + MISC_BIAS);
+    float* s_rowx = reinterpret_cast<float*>(misc + MISC_ROWX);
+    float* s_db = reinterpret_cast<float*>(misc + MISC_DB);
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(misc + MISC_MASK);
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(misc + MISC_BARS);
+    uint64_t* wempty = wfull + MAX_NWST;
+    uint64_t* x_full = wempty + MAX_NWST;   // [1]
+    uint64_t* x_free = x_full + 1;          // [1]
+    uint64_t* a_ready = x_free + 1;         // [4]
+    uint64_t* acc_full = a_ready + 4;       // [2]: one per accumulator
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&maps.x);
-        for (int i = 0; i < NWST; ++i) {
+        for (int i = 0; i < MAX_NWST; ++i) {
             mbar_init(&wfull[i], 1);
             mbar_init(&wempty[i], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&x_full[s], 1);
-            mbar_init(&x_free[s], 1);
-            mbar_init(&acc_full[s], 1);
-            mbar_init(&a_ready[s], 8);
-        }
+        mbar_init(x_full, 1);
+        mbar_init(x_free, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -271,34 +279,28 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // tiles of this CTA: blockIdx.x + k * gridDim.x; pair `it` holds k = 2*it (slot 0) and 2*it + 1 (slot 1)
+    // tiles of this CTA: blockIdx.x + k * gridDim.x
     const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int n_pairs = (my_tiles + 1) >> 1;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t ws = 0, wpar = 0;
-            for (int it = 0; it < n_pairs; ++it) {
-                const int ns = (2 * it + 1 < my_tiles) ? 2 : 1;
-                for (int sl = 0; sl < ns; ++sl) {
-                    const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
-                    mbar_wait(&x_free[sl], (it & 1) ^ 1);
-                    mbar_expect_tx(&x_full[sl], p.in_kb * KB_BYTES);
-                    for (int kb = 0; kb < p.in_kb; ++kb)
-                        tma_load_2d(&maps.x, &x_full[sl], act[sl] + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                }
+            for (int it = 0; it < my_tiles; ++it) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                mbar_wait(x_free, (it & 1) ^ 1);          // GEMM 0 of the previous tile has read the staging buffer
+                mbar_expect_tx(x_full, p.in_kb * KB_BYTES);
+                for (int kb = 0; kb < p.in_kb; ++kb)
+                    tma_load_2d(&maps.x, x_full, xst + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
                 for (int ph = 0; ph < p.n_ph; ++ph) {
                     const PhaseDesc& d = p.ph[ph];
-                    for (int sl = 0; sl < ns; ++sl) {
-                        for (int kb = 0; kb < d.n_kb; ++kb) {
-                            mbar_wait(&wempty[ws], wpar ^ 1);
-                            mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
-                            tma_load_2d(&maps.w[d.wmap], &wfull[ws], smem + OFF_WRING + ws * WST_BYTES, kb * KBLK, 0);
-                            if (++ws == NWST) {
-                                ws = 0;
-                                wpar ^= 1;
-                            }
+                    for (int kb = 0; kb < d.n_kb; ++kb) {
+                        mbar_wait(&wempty[ws], wpar ^ 1);
+                        mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
+                        tma_load_2d(&maps.w[d.wmap], &wfull[ws], wring + ws * WST_BYTES, kb * KBLK, 0);
+                        if (++ws == (uint32_t)p.nwst) {
+                            ws = 0;
+                            wpar ^= 1;
                         }
                     }
                 }
@@ -308,38 +310,38 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         // ===================== MMA issuer + TMA stores =====================
         if (lane == 0) {
             uint32_t ws = 0, wpar = 0;
-            uint32_t gcount[2] = {0, 0};   // GEMM phases issued per slot  -> acc_full parity on the consumer side
-            uint32_t acount[2] = {0, 0};   // epilogue completions consumed per slot -> a_ready parity
+            uint32_t g = 0;                        // GEMMs issued so far: GEMM g accumulates into accumulator g & 1
+            uint32_t acnt[4] = {0, 0, 0, 0};       // completions consumed per a_ready barrier
             int tr0 = 0;
-            for (int it = 0; it < n_pairs; ++it) {
-                const int ns = (2 * it + 1 < my_tiles) ? 2 : 1;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int tile = blockIdx.x + it * gridDim.x;
 #pragma unroll 1
                 for (int ph = 0; ph < p.n_ph; ++ph) {
                     const PhaseDesc& d = p.ph[ph];
-                    const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, 0);
-#pragma unroll 1
-                    for (int sl = 0; sl < ns; ++sl) {
-                        const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
-                        const uint32_t d_tmem = tmem_base + sl * 256;
-                        if (ph == 0) {
-                            mbar_wait(&x_full[sl], it & 1);
-                        } else {
-                            mbar_wait(&a_ready[sl], acount[sl] & 1);   // previous epilogue of this slot: tile written,
-                            ++acount[sl];                              // accumulator free
-                        }
-                        tc_fence_after();
-                        RLPPO_TRACE(0, tr0++);   // MMA: inputs of (ph, slot) ready
-                        const bool storing = TRAIN && ph > 0 && d.store_map != NO_STORE;
-                        if (storing) {
-                            for (int kb = 0; kb < d.store_kb; ++kb)
-                                tma_store_2d(&maps.out[d.store_map], act[sl] + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                            bulk_commit();
-                        }
+                    const bool storing = TRAIN && ph > 0 && d.store_map != NO_STORE;
+                    if (d.n_kb > 0) {
+                        const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, 0);
+                        const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
+                        RLPPO_TRACE(0, tr0++);   // MMA: start of (tile, ph)
                         for (int kb = 0; kb < d.n_kb; ++kb) {
+                            uint32_t a_addr;
+                            if (ph == 0) {
+                                if (kb == 0) {
+                                    mbar_wait(x_full, it & 1);
+                                    tc_fence_after();
+                                }
+                                a_addr = smem_u32(xst + kb * KB_BYTES);
+                            } else {
+                                mbar_wait(&a_ready[kb], acnt[kb] & 1);   // k-block kb of the previous epilogue's output
+                                ++acnt[kb];
+                                tc_fence_after();
+                                a_addr = smem_u32(act + kb * KB_BYTES);
+                                if (storing && kb < d.store_kb)
+                                    tma_store_2d(&maps.out[d.store_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
+                            }
                             mbar_wait(&wfull[ws], wpar);
                             tc_fence_after();
-                            const uint32_t a_addr = smem_u32(act[sl] + kb * KB_BYTES);
-                            const uint32_t b_addr = smem_u32(smem + OFF_WRING + ws * WST_BYTES);
+                            const uint32_t b_addr = smem_u32(wring + ws * WST_BYTES);
 #pragma unroll
                             for (int k = 0; k < KBLK / 16; ++k) {
                                 const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
@@ -347,90 +349,116 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
                             umma_commit(&wempty[ws]);
-                            if (++ws == NWST) {
+                            if (++ws == (uint32_t)p.nwst) {
                                 ws = 0;
                                 wpar ^= 1;
                             }
                         }
-                        RLPPO_TRACE(0, tr0++);   // MMA: all MMAs of (ph, slot) issued
-                        if (storing) bulk_wait_read_all();   // this phase's epilogue overwrites the tile in place
-                        RLPPO_TRACE(0, tr0++);   // MMA: stores have left shared memory
-                        if (d.n_kb > 0) {
-                            umma_commit(&acc_full[sl]);
-                        } else {
-                            mbar_arrive(&acc_full[sl]);   // GEMM-less phase: the previous accumulator is still in TMEM
+                        if (ph == 0) umma_commit(x_free);      // the staging buffer can take the next tile's x
+                        if (storing) {
+                            // the previous epilogue may have produced more k-blocks than this GEMM consumes
+                            for (int kb = d.n_kb; kb < d.store_kb; ++kb) {
+                                mbar_wait(&a_ready[kb], acnt[kb] & 1);
+                                ++acnt[kb];
+                                tc_fence_after();
+                                tma_store_2d(&maps.out[d.store_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
+                            }
+                            bulk_commit();
+                            bulk_wait_read_all();   // this phase's epilogue overwrites the tile in place
                         }
-                        ++gcount[sl];
+                        RLPPO_TRACE(0, tr0++);   // MMA: all MMAs of (tile, ph) issued, stores have left shared memory
+                        umma_commit(&acc_full[g & 1u]);
+                        ++g;
+                    } else {
+                        // GEMM-less phase (value net: dL/dH_L from the accumulator of the last forward GEMM, still in
+                        // TMEM): store what the previous epilogue left, then hand the SAME accumulator back
+                        RLPPO_TRACE(0, tr0++);
+                        for (int kb = 0; kb < d.store_kb; ++kb) {
+                            mbar_wait(&a_ready[kb], acnt[kb] & 1);
+                            ++acnt[kb];
+                            tc_fence_after();
+                            if (storing) tma_store_2d(&maps.out[d.store_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
+                        }
+                        if (storing) {
+                            bulk_commit();
+                            bulk_wait_read_all();
+                        }
+                        RLPPO_TRACE(0, tr0++);
+                        mbar_arrive(&acc_full[(g - 1u) & 1u]);
                     }
                 }
-                // tails: the last epilogue's tile of each slot, then hand the buffer back to the producer
-                for (int sl = 0; sl < ns; ++sl) {
-                    const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
-                    mbar_wait(&a_ready[sl], acount[sl] & 1);
-                    ++acount[sl];
+                // tail: the last epilogue's output (every k-block it released must be consumed here: barrier parity)
+                for (int kb = 0; kb < p.tail_rel_kb; ++kb) {
+                    mbar_wait(&a_ready[kb], acnt[kb] & 1);
+                    ++acnt[kb];
                     tc_fence_after();
-                    if (TRAIN) {
-                        for (int kb = 0; kb < p.tail_kb; ++kb)
-                            tma_store_2d(&maps.out[p.tail_map], act[sl] + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                        bulk_commit();
-                        bulk_wait_read_all();
-                    }
-                    mbar_arrive(&x_free[sl]);
+                    if (TRAIN && kb < p.tail_kb)
+                        tma_store_2d(&maps.out[p.tail_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
+                }
+                if (TRAIN) {
+                    bulk_commit();
+                    bulk_wait_read_all();
                 }
             }
         }
     } else {
         // ===================== epilogue warps =====================
         EpiCtx e;
-        e.smem = smem;
+        e.act = act;
         e.s_bias = s_bias;
         e.s_rowx = s_rowx;
+        e.s_mask = s_mask + (threadIdx.x - 64);
         e.a_ready = a_ready;
-        e.tmem_base = tmem_base;
         e.lane = lane;
         e.quarter = warp & 3;
         e.half = (warp - 2) >> 2;
         e.row_in_tile = e.quarter * 32 + lane;
 
-        // ReLU masks of this thread's row (per slot, layer, chunk): a dynamically indexed local array -- one LDL/STL per
-        // chunk.  (Register arrays read through predicated selects cost 32 selects per chunk and 32 registers.)
-        uint32_t relu[2 * MAXL * 4];
-        float dv_keep[2] = {0.f, 0.f};  // value net: d(loss)/dv of this thread's row, kept from the forward tail
+        float dv_keep = 0.f;   // value net: d(loss)/dv of this thread's row, kept from the forward tail
         float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, mrows = 0.f;   // metric partial sums of this thread's rows
         // column sums (bias gradients, value-head weight gradient) accumulate in shared memory: lane j of a warp holds the
         // partial sum of column 32c + j over the warp's 32 rows; four warps (row quarters) add into the same word
         auto db_add = [&](int l, int c, float v) { atomicAdd(&s_db[l * 256 + c * 32 + e.lane], v); };
 
-        uint32_t gcount[2] = {0, 0};
+        uint32_t g = 0;                  // mirrors the MMA thread's GEMM counter
+        uint32_t fcnt[2] = {0, 0};       // completions consumed per acc_full barrier
         int tr1 = 0;
-        for (int it = 0; it < n_pairs; ++it) {
-          const int ns = (2 * it + 1 < my_tiles) ? 2 : 1;
+        for (int it = 0; it < my_tiles; ++it) {
+          const int tile = blockIdx.x + it * gridDim.x;
+          const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
+          const bool row_ok = row < p.M;
 #pragma unroll 1
           for (int ph = 0; ph < p.n_ph; ++ph) {
-            const PhaseDesc& d = p.ph[ph];
-#pragma unroll 1
-            for (int sl = 0; sl < ns; ++sl) {
-                const int tile = blockIdx.x + (2 * it + sl) * gridDim.x;
-                const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
-                const bool row_ok = row < p.M;
-                mbar_wait(&acc_full[sl], gcount[sl] & 1);
-                ++gcount[sl];
+                const PhaseDesc& d = p.ph[ph];
+                uint32_t a;
+                if (d.n_kb > 0) {
+                    a = g & 1u;
+                    ++g;
+                } else {
+                    a = (g - 1u) & 1u;
+                }
+                mbar_wait(&acc_full[a], fcnt[a] & 1);
+                ++fcnt[a];
                 tc_fence_after();
-                if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: accumulator of (ph, slot) complete
-                const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + sl * 256;
-                uint8_t* dst = act[sl];      // in place: the GEMM that read this tile has completed
-                e.a_ready = a_ready + sl;
+                if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: accumulator of (tile, ph) complete
+                const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + a * 256u;
+                uint8_t* dst = act;      // in place: the GEMM that read this tile has completed
                 const int li = d.layer;
 
                 if (d.kind == PH_FWD || d.kind == PH_FWD_VALUE) {
-                    const int nc = d.N >> 5;
-                    const int c0 = e.half * (nc >> 1), c1 = c0 + (nc >> 1);
+                    const int nkb = d.N >> 6;
                     const bool tail = (d.kind == PH_FWD_VALUE);
                     float dq[4] = {0.f, 0.f, 0.f, 0.f};
+                    uint32_t rb[32];
+                    tmem_ld32_issue(trow + e.half * 32, rb);
 #pragma unroll 1
-                    for (int c = c0; c < c1; ++c) {
+                    for (int j = 0; j < nkb; ++j) {
+                        const int c = 2 * j + e.half;
                         float v[32];
-                        tmem_ld32(trow + c * 32, v);
+                        tmem_ld32_wait(rb);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
+                        if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);   // next chunk in flight during this one
                         const float* sb = s_bias + li * 256 + c * 32;
                         uint32_t bq[4] = {0u, 0u, 0u, 0u};   // four independent OR chains (one 32-long chain serialises)
 #pragma unroll
@@ -439,22 +467,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             bq[i & 3] |= (xv > 0.f ? 1u : 0u) << i;
                             v[i] = xv;
                         }
-                        const uint32_t bits = (bq[0] | bq[1]) | (bq[2] | bq[3]);
-                        if (TRAIN) relu[(sl * MAXL + li) * 4 + (c - c0)] = bits;
+                        if (TRAIN) e.s_mask[(li * 4 + j) * kEpiThreads] = (bq[0] | bq[1]) | (bq[2] | bq[3]);
                         if (tail) {
                             const float* wv = s_bias + MAXL * 256 + c * 32;
 #pragma unroll
                             for (int i = 0; i < 32; ++i) dq[i & 3] = fmaf(bf16_round(v[i]), wv[i], dq[i & 3]);
                         }
-                        if (!tail) {
-                            store_chunk_sw128(dst, e.row_in_tile, c, v);
-                        } else if (TRAIN) {
-                            store_chunk_sw128(dst, e.row_in_tile, c, v);
-                        }
+                        if (!tail || TRAIN) store_chunk_sw128(dst, e.row_in_tile, c, v);
+                        if (!tail) release_kb(e, j);
                     }
                     if (tail) {
                         // ---- value head: v = H_L . w + b (value_estimator.py:27), MSE loss and its gradient ----
-                        float* rowx = e.s_rowx + sl * ROWX_FLOATS;   // per slot: the other slot's tail may run concurrently
+                        float* rowx = e.s_rowx;
                         rowx[e.half * 128 + e.row_in_tile] = (dq[0] + dq[1]) + (dq[2] + dq[3]);
                         epi_bar_sync();
                         const float bhead = p.bias[MAXL] != nullptr ? __ldg(p.bias[MAXL]) : 0.f;
@@ -471,20 +495,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                     m1 += dv;                                      // head bias gradient
                                 }
                             }
-                            dv_keep[0] = sl == 0 ? dv : dv_keep[0];
-                            dv_keep[1] = sl == 1 ? dv : dv_keep[1];
+                            dv_keep = dv;
                             // H_L is complete in shared memory: it is TMA-stored by the next, GEMM-less phase, whose
                             // epilogue then overwrites it with dL/dH_L
                         }
+                        for (int j = 0; j < nkb; ++j) release_kb(e, j);
                     }
                 } else if (d.kind == PH_VALUE_BWD) {
                     // dL/dH_L = dv * w (.) relu'(H_L), dw_head += dv * H_L, db_L: re-reads the accumulator of the last
-                    // forward GEMM, which is still in this slot's TMEM columns
-                    const int nc = d.N >> 5;
-                    const int c0 = e.half * (nc >> 1), c1 = c0 + (nc >> 1);
-                    const float dv = sl == 0 ? dv_keep[0] : dv_keep[1];
+                    // forward GEMM, which is still in TMEM
+                    const int nkb = d.N >> 6;
+                    const float dv = dv_keep;
 #pragma unroll 1
-                    for (int c = c0; c < c1; ++c) {
+                    for (int j = 0; j < nkb; ++j) {
+                        const int c = 2 * j + e.half;
                         float v[32], t[32];
                         tmem_ld32(trow + c * 32, v);
                         const float* sb = s_bias + li * 256 + c * 32;
@@ -500,180 +524,217 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         for (int i = 0; i < 32; ++i) t[i] = v[i];
                         db_add(li, c, warp_colsum32(t, e.lane));
                         store_chunk_sw128(dst, e.row_in_tile, c, v);
+                        release_kb(e, j);
                     }
                 } else if (d.kind == PH_DGRAD) {
-                    const int nc = d.N >> 5;
-                    const int c0 = e.half * (nc >> 1), c1 = c0 + (nc >> 1);
+                    const int nkb = d.N >> 6;
+                    uint32_t rb[32];
+                    tmem_ld32_issue(trow + e.half * 32, rb);
 #pragma unroll 1
-                    for (int c = c0; c < c1; ++c) {
+                    for (int j = 0; j < nkb; ++j) {
+                        const int c = 2 * j + e.half;
                         float v[32], t[32];
-                        tmem_ld32(trow + c * 32, v);
-                        const uint32_t bits = relu[(sl * MAXL + li) * 4 + (c - c0)];
+                        tmem_ld32_wait(rb);
+                        const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
+                            v[i] = ((bits >> i) & 1u) ? __uint_as_float(rb[i]) : 0.f;
                             t[i] = v[i];
                         }
-                        db_add(li, c, warp_colsum32(t, e.lane));
+                        if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);
                         store_chunk_sw128(dst, e.row_in_tile, c, v);
+                        release_kb(e, j);                                // the next GEMM starts; the column sums follow
+                        db_add(li, c, warp_colsum32(t, e.lane));
                     }
                 } else {
-                    // ---- policy head (discrete_policy.py:44-80, ppo_learner.py:153-177) ----
-                    // Two threads per row: the warp pair that owns the row's TMEM lanes splits every 32-column chunk into
-                    // its lower / upper 16 columns; the row-wise quantities (max, sum-exp, ...) are combined through shared
-                    // memory.  Three branch-free passes re-read the logits from TMEM.  (History, from the cycle trace of this
-                    // kernel: one thread per row with a data-dependent `if` per element: 42k cycles per tile; branch-free,
-                    // 3 passes: 15.6k; the other epilogues take ~3k.)
-                    const int nact = p.n_actions;
-                    const int nch = (nact + 31) >> 5;          // <= 4
-                    const int nch_out = p.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
-                    const int hoff = e.half * 16;              // this thread's 16 columns inside each chunk
-                    const float* sb = s_bias + MAXL * 256;
-                    const float kLogMin = -25.328436022934504f;   // ln(1e-11)
-                    float* xch = e.s_rowx + sl * ROWX_FLOATS;     // per-slot exchange planes: [0,256) max, [512,768) argmax, [1024,1792) S/T/z_a
-                    int a = 0;
-                    float old_lp = 0.f, advv = 0.f;
-                    if (TRAIN && row_ok) {
-                        a = (int)__ldg(p.actions + row);             // acts.long(), discrete_policy.py:71
-                        a = min(max(a, 0), nact - 1);
-                        old_lp = __ldg(p.old_logp + row);
-                        advv = __ldg(p.adv + row);
-                    }
-                    // pass 1: row maximum (+ argmax for the deterministic branch)
-                    float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    int aq[4] = {0, 0, 0, 0};
+                // ---- policy head (discrete_policy.py:44-80, ppo_learner.py:153-177) ----
+                // Two threads per row: the warp pair that owns the row's TMEM lanes splits every 32-column chunk into
+                // its lower / upper 16 columns; the row-wise quantities (max, sum-exp, ...) are combined through shared
+                // memory.  Three branch-free passes re-read the logits from TMEM.  (History, from the cycle trace of this
+                // kernel: one thread per row with a data-dependent `if` per element: 42k cycles per tile; branch-free,
+                // 3 passes: 15.6k; the other epilogues take ~3k.)
+                const int nact = p.n_actions;
+                const int nch = (nact + 31) >> 5;          // <= 4
+                const int nch_out = p.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
+                const int hoff = e.half * 16;              // this thread's 16 columns inside each chunk
+                const float* sb = s_bias + MAXL * 256;
+                const float kLogMin = -25.328436022934504f;   // ln(1e-11)
+                float* xch = e.s_rowx;                        // exchange planes: [0,256) max, [512,768) argmax, [1024,1792) S/T/z_a
+                int a = 0;
+                float old_lp = 0.f, advv = 0.f;
+                if (TRAIN && row_ok) {
+                    a = (int)__ldg(p.actions + row);             // acts.long(), discrete_policy.py:71
+                    a = min(max(a, 0), nact - 1);
+                    old_lp = __ldg(p.old_logp + row);
+                    advv = __ldg(p.adv + row);
+                }
+                // pass 1: row maximum (+ argmax for the deterministic branch)
+                float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                int aq[4] = {0, 0, 0, 0};
 #pragma unroll 1
-                    for (int c = 0; c < nch; ++c) {
-                        float v[16];
-                        tmem_ld16(trow + c * 32 + hoff, v);
+                for (int c = 0; c < nch; ++c) {
+                    float v[16];
+                    tmem_ld16(trow + c * 32 + hoff, v);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int col = c * 32 + hoff + i;
-                            const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
-                            const bool gt = zz > mq[i & 3];
-                            mq[i & 3] = gt ? zz : mq[i & 3];
-                            aq[i & 3] = gt ? col : aq[i & 3];
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        const int col = c * 32 + hoff + i;
+                        const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
+                        const bool gt = zz > mq[i & 3];
+                        mq[i & 3] = gt ? zz : mq[i & 3];
+                        aq[i & 3] = gt ? col : aq[i & 3];
                     }
-                    float mx = mq[0];
-                    int argmax = aq[0];
+                }
+                float mx = mq[0];
+                int argmax = aq[0];
 #pragma unroll
-                    for (int q = 1; q < 4; ++q) {
-                        const bool better = mq[q] > mx || (mq[q] == mx && aq[q] < argmax);   // ties: lowest column
-                        mx = better ? mq[q] : mx;
-                        argmax = better ? aq[q] : argmax;
+                for (int q = 1; q < 4; ++q) {
+                    const bool better = mq[q] > mx || (mq[q] == mx && aq[q] < argmax);   // ties: lowest column
+                    mx = better ? mq[q] : mx;
+                    argmax = better ? aq[q] : argmax;
+                }
+                xch[e.half * 128 + e.row_in_tile] = mx;
+                int* xchi = reinterpret_cast<int*>(xch) + 512;   // second plane: argmax (ints), see OFF_ROWX sizing
+                xchi[e.half * 128 + e.row_in_tile] = argmax;
+                epi_bar_sync();
+                {
+                    const float mo = xch[(e.half ^ 1) * 128 + e.row_in_tile];
+                    const int ao = xchi[(e.half ^ 1) * 128 + e.row_in_tile];
+                    const bool better = mo > mx || (mo == mx && ao < argmax);
+                    mx = better ? mo : mx;
+                    argmax = better ? ao : argmax;
+                }
+                epi_bar_sync();   // everyone has read the maxima before the plane is reused
+                // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
+                float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
+                float zs_a = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < nch; ++c) {
+                    float v[16];
+                    tmem_ld16(trow + c * 32 + hoff, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int col = c * 32 + hoff + i;
+                        const float zs = col < nact ? v[i] + sb[col] - mx : -INFINITY;
+                        const float ej = __expf(zs);                      // exp(-inf) = 0 for the padding
+                        Sq[i & 3] += ej;
+                        Tq[i & 3] = fmaf(ej, col < nact ? zs : 0.f, Tq[i & 3]);
+                        zs_a += col == a ? zs : 0.f;                      // exactly one of the two threads holds column a
                     }
-                    xch[e.half * 128 + e.row_in_tile] = mx;
-                    int* xchi = reinterpret_cast<int*>(xch) + 512;   // second plane: argmax (ints), see OFF_ROWX sizing
-                    xchi[e.half * 128 + e.row_in_tile] = argmax;
+                }
+                float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
+                float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
+                {
+                    float* x3 = xch + 1024;   // [3][half][row]
+                    x3[0 * 256 + e.half * 128 + e.row_in_tile] = S;
+                    x3[1 * 256 + e.half * 128 + e.row_in_tile] = T;
+                    x3[2 * 256 + e.half * 128 + e.row_in_tile] = zs_a;
                     epi_bar_sync();
-                    {
-                        const float mo = xch[(e.half ^ 1) * 128 + e.row_in_tile];
-                        const int ao = xchi[(e.half ^ 1) * 128 + e.row_in_tile];
-                        const bool better = mo > mx || (mo == mx && ao < argmax);
-                        mx = better ? mo : mx;
-                        argmax = better ? ao : argmax;
+                    const int o = (e.half ^ 1) * 128 + e.row_in_tile;
+                    // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
+                    const float S0 = e.half == 0 ? S : x3[o], S1 = e.half == 0 ? x3[o] : S;
+                    const float T0 = e.half == 0 ? T : x3[256 + o], T1 = e.half == 0 ? x3[256 + o] : T;
+                    S = S0 + S1;
+                    T = T0 + T1;
+                    zs_a += x3[512 + o];
+                }
+                const float logS = logf(S);
+                const float mxs = mx + logS;
+                if (TRAIN) {
+                    // Entropy of the CLAMPED probabilities (discrete_policy.py:74-78) from the two sums:
+                    //   -sum s_j log s_j = logS - T/S.  Clamping to [1e-11, 1] changes each term by at most
+                    //   1e-11 * ln(1e11) = 2.5e-10, i.e. below fp32 resolution of the sum; the clamp's effect on the
+                    //   GRADIENT (zero outside the range) is applied exactly in pass 3.
+                    const float Hent = logS - T / S;
+                    const float Gs = 1.0f - Hent;                       // sum_j s_j (log s_j + 1)
+                    const float ls_a = zs_a - logS;
+                    const float lp_a = fminf(fmaxf(ls_a, kLogMin), 0.f);   // log clamp(s_a, 1e-11, 1), :74-77
+                    const float s_a = __expf(ls_a);
+                    const float p_a = fminf(fmaxf(s_a, 1e-11f), 1.0f);
+                    const float log_ratio = lp_a - old_lp;
+                    const float ratio = expf(log_ratio);                            // ppo_learner.py:153
+                    const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
+                    const float clipped = fminf(fmaxf(ratio, lo), hi);              // :154-156
+                    const float s1 = ratio * advv, s2 = clipped * advv;
+                    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+                    const float d1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);      // torch.min backward, ties 0.5/0.5
+                    const float d2 = s1 > s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
+                    const float okf = row_ok ? 1.f : 0.f;
+                    const float d_logp = -p.inv_batch * advv * (d1 + d2 * in_range) * ratio * okf;
+                    const float ga = (ls_a >= kLogMin) ? d_logp / p_a : 0.f;        // through log(clamp(s_a))
+                    const float cw = p.ent_coef * p.inv_batch * okf;
+                    const float G = cw * Gs + ga * s_a;
+                    if (row_ok && e.half == 0) {
+                        m0 += Hent;
+                        m1 += (ratio - 1.0f) - log_ratio;                           // :161
+                        m2 += fabsf(ratio - 1.0f) > p.clip ? 1.f : 0.f;             // :166
+                        m3 += fminf(s1, s2);
+                        mrows += 1.f;
+                        if (p.logp_out) p.logp_out[row] = lp_a;
                     }
-                    epi_bar_sync();   // everyone has read the maxima before the plane is reused
-                    // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
-                    float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
-                    float zs_a = 0.f;
+                    // pass 3: dz_j = s_j (g_j - G) -> bf16 tile (A operand of the first dgrad GEMM) + head bias grads
 #pragma unroll 1
-                    for (int c = 0; c < nch; ++c) {
-                        float v[16];
-                        tmem_ld16(trow + c * 32 + hoff, v);
+                    for (int c = 0; c < nch_out; ++c) {
+                        float v[16], t[16];
+                        if (c < nch) {
+                            tmem_ld16(trow + c * 32 + hoff, v);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int col = c * 32 + hoff + i;
-                            const float zs = col < nact ? v[i] + sb[col] - mx : -INFINITY;
-                            const float ej = __expf(zs);                      // exp(-inf) = 0 for the padding
-                            Sq[i & 3] += ej;
-                            Tq[i & 3] = fmaf(ej, col < nact ? zs : 0.f, Tq[i & 3]);
-                            zs_a += col == a ? zs : 0.f;                      // exactly one of the two threads holds column a
+                            const bool in = col < nact;
+                            const float ls = in ? v[i] + sb[col & 255] - mxs : -INFINITY;   // log softmax (<= 0)
+                            const float sj = __expf(ls);                                    // 0 for the padding
+                            const float lp = fminf(fmaxf(ls, kLogMin), 0.f);
+                            float gj = fmaf(cw, lp + 1.0f, col == a ? ga : 0.f);
+                            gj = ls >= kLogMin ? gj : 0.f;          // clamp passes gradient inside [1e-11, 1] only
+                            const float o = in ? sj * (gj - G) : 0.f;
+                            v[i] = o;
+                            t[i] = o;
                         }
+                        const float cs = warp_colsum16(t, e.lane);
+                        if (e.lane < 16) atomicAdd(&s_db[MAXL * 256 + c * 32 + hoff + e.lane], cs);
+                        store_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, v);
                     }
-                    float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
-                    float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
-                    {
-                        float* x3 = xch + 1024;   // [3][half][row]
-                        x3[0 * 256 + e.half * 128 + e.row_in_tile] = S;
-                        x3[1 * 256 + e.half * 128 + e.row_in_tile] = T;
-                        x3[2 * 256 + e.half * 128 + e.row_in_tile] = zs_a;
-                        epi_bar_sync();
-                        const int o = (e.half ^ 1) * 128 + e.row_in_tile;
-                        // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
-                        const float S0 = e.half == 0 ? S : x3[o], S1 = e.half == 0 ? x3[o] : S;
-                        const float T0 = e.half == 0 ? T : x3[256 + o], T1 = e.half == 0 ? x3[256 + o] : T;
-                        S = S0 + S1;
-                        T = T0 + T1;
-                        zs_a += x3[512 + o];
-                    }
-                    const float logS = logf(S);
-                    const float mxs = mx + logS;
-                    if (TRAIN) {
-                        // Entropy of the CLAMPED probabilities (discrete_policy.py:74-78) from the two sums:
-                        //   -sum s_j log s_j = logS - T/S.  Clamping to [1e-11, 1] changes each term by at most
-                        //   1e-11 * ln(1e11) = 2.5e-10, i.e. below fp32 resolution of the sum; the clamp's effect on the
-                        //   GRADIENT (zero outside the range) is applied exactly in pass 3.
-                        const float Hent = logS - T / S;
-                        const float Gs = 1.0f - Hent;                       // sum_j s_j (log s_j + 1)
-                        const float ls_a = zs_a - logS;
-                        const float lp_a = fminf(fmaxf(ls_a, kLogMin), 0.f);   // log clamp(s_a, 1e-11, 1), :74-77
-                        const float s_a = __expf(ls_a);
-                        const float p_a = fminf(fmaxf(s_a, 1e-11f), 1.0f);
-                        const float log_ratio = lp_a - old_lp;
-                        const float ratio = expf(log_ratio);                            // ppo_learner.py:153
-                        const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
-                        const float clipped = fminf(fmaxf(ratio, lo), hi);              // :154-156
-                        const float s1 = ratio * advv, s2 = clipped * advv;
-                        const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-                        const float d1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);      // torch.min backward, ties 0.5/0.5
-                        const float d2 = s1 > s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
-                        const float okf = row_ok ? 1.f : 0.f;
-                        const float d_logp = -p.inv_batch * advv * (d1 + d2 * in_range) * ratio * okf;
-                        const float ga = (ls_a >= kLogMin) ? d_logp / p_a : 0.f;        // through log(clamp(s_a))
-                        const float cw = p.ent_coef * p.inv_batch * okf;
-                        const float G = cw * Gs + ga * s_a;
-                        if (row_ok && e.half == 0) {
-                            m0 += Hent;
-                            m1 += (ratio - 1.0f) - log_ratio;                           // :161
-                            m2 += fabsf(ratio - 1.0f) > p.clip ? 1.f : 0.f;             // :166
-                            m3 += fminf(s1, s2);
-                            mrows += 1.f;
-                            if (p.logp_out) p.logp_out[row] = lp_a;
-                        }
-                        // pass 3: dz_j = s_j (g_j - G) -> bf16 tile (A operand of the first dgrad GEMM) + head bias grads
+                } else {
+                    // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62): the inverse-CDF scan is
+                    // sequential over the row, so the lower-half thread does it alone over all columns ----
+                    if (e.half == 0) {
+                        float Pq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-                        for (int c = 0; c < nch_out; ++c) {
-                            float v[16], t[16];
-                            if (c < nch) {
-                                tmem_ld16(trow + c * 32 + hoff, v);
-                            } else {
+                        for (int c = 0; c < nch; ++c) {
+                            float v[32];
+                            tmem_ld32(trow + c * 32, v);
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = c * 32 + i;
+                                const float pj = fminf(fmaxf(__expf(v[i] + sb[col & 255] - mxs), 1e-11f), 1.0f);
+                                Pq[i & 3] += col < nact ? pj : 0.f;
                             }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const int col = c * 32 + hoff + i;
-                                const bool in = col < nact;
-                                const float ls = in ? v[i] + sb[col & 255] - mxs : -INFINITY;   // log softmax (<= 0)
-                                const float sj = __expf(ls);                                    // 0 for the padding
-                                const float lp = fminf(fmaxf(ls, kLogMin), 0.f);
-                                float gj = fmaf(cw, lp + 1.0f, col == a ? ga : 0.f);
-                                gj = ls >= kLogMin ? gj : 0.f;          // clamp passes gradient inside [1e-11, 1] only
-                                const float o = in ? sj * (gj - G) : 0.f;
-                                v[i] = o;
-                                t[i] = o;
-                            }
-                            const float cs = warp_colsum16(t, e.lane);
-                            if (e.lane < 16) atomicAdd(&s_db[MAXL * 256 + c * 32 + hoff + e.lane], cs);
-                            store_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, v);
                         }
-                    } else {
-                        // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62): the inverse-CDF scan is
-                        // sequential over the row, so the lower-half thread does it alone over all columns ----
-                        if (e.half == 0) {
-                            float Pq[4] = {0.f, 0.f, 0.f, 0.f};
+                        const float P = (Pq[0] + Pq[1]) + (Pq[2] + Pq[3]);
+                        int actn = nact - 1;
+                        float pa = 0.f;
+                        if (p.deterministic) {
+                            actn = argmax;
+                            pa = fminf(fmaxf(__expf(-logS), 1e-11f), 1.0f);
+                        } else {
+                            float u = 0.f;
+                            if (row_ok) {
+                                if (p.u_inject != nullptr) {
+                                    u = __ldg(p.u_inject + row);
+                                } else {
+                                    const uint64_t ctr = p.offset + (uint64_t)row;
+                                    const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
+                                                                  make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                                    u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+                                }
+                            }
+                            const float thr = u * P;   // torch.multinomial normalises what it is given
+                            float run = 0.f, plast = 0.f;
+                            int found = 0;
 #pragma unroll 1
                             for (int c = 0; c < nch; ++c) {
                                 float v[32];
@@ -681,61 +742,30 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     const int col = c * 32 + i;
+                                    const bool in = col < nact;
                                     const float pj = fminf(fmaxf(__expf(v[i] + sb[col & 255] - mxs), 1e-11f), 1.0f);
-                                    Pq[i & 3] += col < nact ? pj : 0.f;
+                                    run += in ? pj : 0.f;               // the running sum is inherently sequential
+                                    plast = in ? pj : plast;
+                                    const bool hit = in && !found && run > thr;
+                                    actn = hit ? col : actn;
+                                    pa = hit ? pj : pa;
+                                    found |= hit ? 1 : 0;
                                 }
                             }
-                            const float P = (Pq[0] + Pq[1]) + (Pq[2] + Pq[3]);
-                            int actn = nact - 1;
-                            float pa = 0.f;
-                            if (p.deterministic) {
-                                actn = argmax;
-                                pa = fminf(fmaxf(__expf(-logS), 1e-11f), 1.0f);
-                            } else {
-                                float u = 0.f;
-                                if (row_ok) {
-                                    if (p.u_inject != nullptr) {
-                                        u = __ldg(p.u_inject + row);
-                                    } else {
-                                        const uint64_t ctr = p.offset + (uint64_t)row;
-                                        const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                                                                      make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-                                        u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-                                    }
-                                }
-                                const float thr = u * P;   // torch.multinomial normalises what it is given
-                                float run = 0.f, plast = 0.f;
-                                int found = 0;
-#pragma unroll 1
-                                for (int c = 0; c < nch; ++c) {
-                                    float v[32];
-                                    tmem_ld32(trow + c * 32, v);
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i) {
-                                        const int col = c * 32 + i;
-                                        const bool in = col < nact;
-                                        const float pj = fminf(fmaxf(__expf(v[i] + sb[col & 255] - mxs), 1e-11f), 1.0f);
-                                        run += in ? pj : 0.f;               // the running sum is inherently sequential
-                                        plast = in ? pj : plast;
-                                        const bool hit = in && !found && run > thr;
-                                        actn = hit ? col : actn;
-                                        pa = hit ? pj : pa;
-                                        found |= hit ? 1 : 0;
-                                    }
-                                }
-                                pa = found ? pa : plast;
-                            }
-                            if (row_ok) {
-                                if (p.actions_out) p.actions_out[row] = (float)actn;   // batched_agent_manager.py:204
-                                if (p.actions_i64_out) p.actions_i64_out[row] = (int64_t)actn;
-                                if (p.logp_out) p.logp_out[row] = logf(pa);            // :60
-                            }
+                            pa = found ? pa : plast;
+                        }
+                        if (row_ok) {
+                            if (p.actions_out) p.actions_out[row] = (float)actn;   // batched_agent_manager.py:204
+                            if (p.actions_i64_out) p.actions_i64_out[row] = (int64_t)actn;
+                            if (p.logp_out) p.logp_out[row] = logf(pa);            // :60
                         }
                     }
                 }
-                release_all(e);
-                if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (ph, slot) done
-            }
+                    if (TRAIN) {
+                        for (int j = 0; j < p.out_kb; ++j) release_kb(e, j);
+                    }
+                }
+                if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (tile, ph) done
           }
         }
         // ---- metrics (the column sums are flushed by the whole CTA below) ----
@@ -892,6 +922,8 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     }
     p.tail_map = 0;
     p.tail_kb = 0;
+    // inference: the policy head releases nothing, the value tail releases H_L's k-blocks
+    p.tail_rel_kb = POLICY ? 0 : kb_of(net->hidden[L - 1]);
     if (TRAIN) {
         // ---- backward data phases ----
         if (POLICY) {
@@ -916,13 +948,20 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         }
         p.tail_map = prev_map;
         p.tail_kb = prev_kb;
+        p.tail_rel_kb = prev_kb;
     }
     p.n_ph = nph;
 
+    // shared memory: activation tile + x staging (in_kb k-blocks) + as deep a weight ring as fits + misc
+    const uint32_t fixed = ACT_BYTES + (uint32_t)p.in_kb * KB_BYTES + MISC_BYTES + 1024;
+    p.nwst = (int)((SMEM_LIMIT - fixed) / WST_BYTES);
+    if (p.nwst > MAX_NWST) p.nwst = MAX_NWST;
+    RLPPO_CHECK_ARG(p.nwst >= 2, "fused path: shared memory budget");
+    const uint32_t smem_bytes = fixed + (uint32_t)p.nwst * WST_BYTES;
     static bool configured = false;
     auto kfn = fused_mlp_kernel<POLICY, TRAIN>;
     if (!configured) {
-        RLPPO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+        RLPPO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         configured = true;
     }
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
@@ -933,7 +972,7 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 1024 * sizeof(unsigned long long), s));
         p.trace = d_trace;
     }
-    kfn<<<grid, kThreads, SMEM_TOTAL, s>>>(maps, p);
+    kfn<<<grid, kThreads, smem_bytes, s>>>(maps, p);
     RLPPO_LAUNCH_CHECK();
     if (tracing) {
         static unsigned long long h[1024];
@@ -941,8 +980,8 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         RLPPO_CUDA(cudaStreamSynchronize(s));
         const unsigned long long t0 = h[0];
         fprintf(stderr, "[fused trace] n_ph=%d tiles=%d\n", p.n_ph, p.num_tiles);
-        for (int i = 0; i + 2 < 512 && h[i] != 0; i += 3)
-            fprintf(stderr, "  mma  #%d ready=%llu issued=+%llu stores=+%llu\n", i / 3, h[i] - t0, h[i + 1] - h[i], h[i + 2] - h[i + 1]);
+        for (int i = 0; i + 1 < 512 && (i == 0 || h[i] != 0); i += 2)
+            fprintf(stderr, "  mma  #%d start=%llu issued+stored=+%llu\n", i / 2, h[i] - t0, h[i + 1] - h[i]);
         for (int i = 0; i + 1 < 512 && h[512 + i] != 0; i += 2)
             fprintf(stderr, "  epi  #%d start=%llu dur=%llu\n", i / 2, h[512 + i] - t0, h[512 + i + 1] - h[512 + i]);
     }

@@ -321,20 +321,27 @@ class Learner(object):
         n = int(experience[0].shape[0]) if hasattr(experience[0], "shape") else len(experience[0])
         if n == 0:
             return
-        # ---- stage the 7 arrays into persistent device slots (one async copy each; fixed addresses) -------------------
+        # ---- the 7 arrays in HBM at addresses a graph can bake in: host arrays are copied (one async H2D each) into
+        # persistent device slots; arrays that already live on the device are used where they are ---------------------
         shapes = tuple((tuple(np.shape(x)), _staged_dtype(x)) for x in experience)
         stage = getattr(self, "_exp_stage", None)
         if stage is None or stage["shapes"] != shapes:
             stage = {"shapes": shapes, "gen": (0 if stage is None else stage["gen"] + 1)}
-            for name, (shape, dt) in zip(_EXP_FIELDS, shapes):
-                stage[name] = torch.empty(shape, dtype=dt, device=dev)
             n_inc = min(int(self.max_returns_per_stats_increment), n) if self.standardize_returns else 0
             stage["values"] = torch.empty(n + 1, dtype=torch.float32, device=dev)
             stage["out"] = tuple(torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
             stage["head"] = torch.empty(n_inc, dtype=torch.float64, device=dev) if n_inc else None
             stage["gae_ws"] = ops.gae_workspace(n, dev)
             self._exp_stage = stage
-        d = {name: stager.to_device(arr, "exp." + name, out=stage[name]) for name, arr in zip(_EXP_FIELDS, experience)}
+        d, ptrs = {}, []
+        for name, arr, (shape, dt) in zip(_EXP_FIELDS, experience, shapes):
+            if isinstance(arr, torch.Tensor) and arr.is_cuda and arr.dtype == dt and arr.is_contiguous():
+                d[name] = arr
+            else:
+                if name not in stage:
+                    stage[name] = torch.empty(shape, dtype=dt, device=dev)
+                d[name] = stager.to_device(arr, "exp." + name, out=stage[name])
+            ptrs.append(d[name].data_ptr())
         obs = int(d["states"].shape[1])
         if buf._rings is None:
             buf._allocate(obs)
@@ -363,7 +370,7 @@ class Learner(object):
         graphs = getattr(self, "_add_graphs", None)
         if graphs is None:
             graphs = self._add_graphs = GraphCache()
-        key = (n, obs, stage["gen"], buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
+        key = (n, obs, stage["gen"], tuple(ptrs), buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
                float(self.gae_gamma), float(self.gae_lambda), bool(self.standardize_returns), vst.fused_ok)
         if not (getattr(ppo, "use_cuda_graph", False) and _lib._TIMING is None and graphs.replay(key, body)):
             body()

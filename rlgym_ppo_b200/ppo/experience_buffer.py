@@ -57,6 +57,7 @@ class ExperienceBuffer(object):
         self.start_dev = None
         self.state_dev = None
         self._spec = None
+        self._copy_stream = None
         self._pin = [None, None, None]
         self._pin_ev = [None, None, None]
         self._pin_i = 0
@@ -203,10 +204,18 @@ class ExperienceBuffer(object):
         address, so a captured CUDA graph can read its indices from it."""
         perm = self.next_permutation()
         assert dst.numel() == perm.numel() and dst.dtype == torch.int64
-        dst.copy_(perm, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        # on a side stream: the copy engine uploads the indices while the device is still busy with the work enqueued
+        # before (value inference, GAE, ring appends of this iteration); the caller's stream only waits for the event
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        # (readers of dst's previous contents are done: PPOLearner.learn synchronises before it returns)
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            dst.copy_(perm, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
         self._pin_ev[self._pin_of_last] = ev
+        main.wait_event(ev)
 
     def _draw(self, key, pos, total):
         self._pin_i = (self._pin_i + 1) % 3
