@@ -46,7 +46,7 @@ constexpr uint32_t KB_BYTES = TILE_M * KBLK * 2;   // 16 KB: one 64-column k-blo
 constexpr uint32_t ACT_BYTES = 4 * KB_BYTES;       // 64 KB
 constexpr uint32_t WST_BYTES = 256 * KBLK * 2;     // 32 KB: one k-block of a weight operand (<= 256 rows)
 constexpr int MAX_NWST = 3;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;
 constexpr int kEpiThreads = 256;
 constexpr int MAXPH = 2 * MAXL + 1;
 
@@ -71,14 +71,16 @@ struct PhaseDesc {
     uint8_t n_kb;       // k-blocks of the contraction (0: no GEMM, PH_VALUE_BWD)
     uint8_t wmap;       // index into Maps::w
     uint16_t N;         // accumulator columns = rows of the weight box (multiple of 16, <= 256)
-    uint8_t store_map;  // tile written by the PREVIOUS epilogue, TMA-stored while this phase's MMAs are issued (or NO_STORE)
-    uint8_t store_kb;   // its k-blocks
+    uint8_t out;        // index into Params::outp of the HBM copy of this phase's output (weight-gradient operand), or NO_STORE
+    uint8_t smem;       // 1: the epilogue writes the activation tile (it is the next GEMM's A operand)
+    uint8_t wait_kb;    // GEMM-less phase: k-blocks released by the previous epilogue (consumed for barrier parity)
+    uint8_t rel_kb;     // k-blocks this phase's epilogue releases (a_ready arrivals), = k-blocks of its output tile
 };
 
 struct alignas(64) Maps {
     CUtensorMap x;
     CUtensorMap w[MAXPH];
-    CUtensorMap out[MAXPH];
+    CUtensorMap out[MAXPH];   // training: H_l, d(logits), dL/dH_l (weight-gradient operands), TMA-stored per k-block
 };
 
 struct Params {
@@ -86,7 +88,6 @@ struct Params {
     int num_tiles, n_ph, L, in_kb, nwst;
     int H[MAXL];
     PhaseDesc ph[MAXPH];
-    int tail_map, tail_kb;   // the last epilogue's tile (training: TMA-stored)
     int tail_rel_kb;         // k-blocks the last epilogue releases (consumed by the MMA thread at the end of a tile)
     const float* bias[MAXL + 1];
     float* gbias[MAXL + 1];
@@ -106,6 +107,7 @@ struct Params {
     float* gw_head;
     float* values_out;
     float* metrics;
+    int dbg_nostore;             // debug (RLPPO_FUSED_NOSTORE=1): timing experiment, outputs are NOT written
     unsigned long long* trace;   // debug (RLPPO_FUSED_TRACE=1): clock64 stamps of CTA 0, [role][event]
 };
 
@@ -170,19 +172,26 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
     return r;
 }
 
-// write 32 consecutive columns [col0, col0+32) of one row into a K-major SWIZZLE_128B activation tile
-__device__ __forceinline__ void store_chunk_sw128(uint8_t* buf, int row, int chunk32, const float (&v)[32]) {
+// 32 floats -> 16 packed bf16x2 words
+__device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&w)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
+}
+// 32 consecutive columns [32*chunk32, +32) of one row into a K-major SWIZZLE_128B activation tile
+__device__ __forceinline__ void sts_chunk_sw128(uint8_t* buf, int row, int chunk32, const uint32_t (&w)[16]) {
     uint8_t* kb = buf + (chunk32 >> 1) * KB_BYTES + row * 128;
     const int base16 = (chunk32 & 1) * 4;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        uint4 o;
-        o.x = cvt_bf16x2(v[t * 8 + 0], v[t * 8 + 1]);
-        o.y = cvt_bf16x2(v[t * 8 + 2], v[t * 8 + 3]);
-        o.z = cvt_bf16x2(v[t * 8 + 4], v[t * 8 + 5]);
-        o.w = cvt_bf16x2(v[t * 8 + 6], v[t * 8 + 7]);
-        *reinterpret_cast<uint4*>(kb + (((base16 + t) ^ (row & 7)) << 4)) = o;
-    }
+    for (int t = 0; t < 4; ++t)
+        *reinterpret_cast<uint4*>(kb + (((base16 + t) ^ (row & 7)) << 4)) = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
+}
+// 16 consecutive columns [16*chunk16, +16) of one row into a K-major SWIZZLE_128B activation tile
+__device__ __forceinline__ void sts_chunk16_sw128(uint8_t* buf, int row, int chunk16, const uint32_t (&w)[8]) {
+    uint8_t* kb = buf + (chunk16 >> 2) * KB_BYTES + row * 128;
+    const int base16 = (chunk16 & 3) * 2;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+        *reinterpret_cast<uint4*>(kb + (((base16 + t) ^ (row & 7)) << 4)) = make_uint4(w[4 * t], w[4 * t + 1], w[4 * t + 2], w[4 * t + 3]);
 }
 
 #define RLPPO_TRACE(role, idx)                                                                  \
@@ -190,21 +199,6 @@ __device__ __forceinline__ void store_chunk_sw128(uint8_t* buf, int row, int chu
         const int _i = (idx);                                                                   \
         if (p.trace != nullptr && blockIdx.x == 0 && _i < 512) p.trace[(role) * 512 + _i] = clock64(); \
     } while (0)
-
-// write 16 consecutive columns [16*chunk16, +16) of one row into a K-major SWIZZLE_128B activation tile
-__device__ __forceinline__ void store_chunk16_sw128(uint8_t* buf, int row, int chunk16, const float (&v)[16]) {
-    uint8_t* kb = buf + (chunk16 >> 2) * KB_BYTES + row * 128;
-    const int base16 = (chunk16 & 3) * 2;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        uint4 o;
-        o.x = cvt_bf16x2(v[t * 8 + 0], v[t * 8 + 1]);
-        o.y = cvt_bf16x2(v[t * 8 + 2], v[t * 8 + 3]);
-        o.z = cvt_bf16x2(v[t * 8 + 4], v[t * 8 + 5]);
-        o.w = cvt_bf16x2(v[t * 8 + 6], v[t * 8 + 7]);
-        *reinterpret_cast<uint4*>(kb + (((base16 + t) ^ (row & 7)) << 4)) = o;
-    }
-}
 
 struct EpiCtx {
     uint8_t* act;
@@ -242,7 +236,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     uint64_t* x_free = x_full + 1;          // [1]
     uint64_t* a_ready = x_free + 1;         // [4]
     uint64_t* acc_full = a_ready + 4;       // [2]: one per accumulator
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    uint64_t* st_done = acc_full + 2;       // [4]: the TMA store of k-block kb has finished reading shared memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -256,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&st_done[i], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -286,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t ws = 0, wpar = 0;
+            int tr3 = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int tile = blockIdx.x + it * gridDim.x;
                 mbar_wait(x_free, (it & 1) ^ 1);          // GEMM 0 of the previous tile has read the staging buffer
@@ -297,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     for (int kb = 0; kb < d.n_kb; ++kb) {
                         mbar_wait(&wempty[ws], wpar ^ 1);
                         mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
+                        RLPPO_TRACE(3, tr3++);
                         tma_load_2d(&maps.w[d.wmap], &wfull[ws], wring + ws * WST_BYTES, kb * KBLK, 0);
                         if (++ws == (uint32_t)p.nwst) {
                             ws = 0;
@@ -311,14 +309,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         if (lane == 0) {
             uint32_t ws = 0, wpar = 0;
             uint32_t g = 0;                        // GEMMs issued so far: GEMM g accumulates into accumulator g & 1
-            uint32_t acnt[4] = {0, 0, 0, 0};       // completions consumed per a_ready barrier
-            int tr0 = 0;
+            uint32_t apar = 0;                     // bit kb: parity of a_ready[kb] to wait for next (registers, not a local array)
+            int tr0 = 0, tr4 = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const int tile = blockIdx.x + it * gridDim.x;
 #pragma unroll 1
                 for (int ph = 0; ph < p.n_ph; ++ph) {
                     const PhaseDesc& d = p.ph[ph];
-                    const bool storing = TRAIN && ph > 0 && d.store_map != NO_STORE;
                     if (d.n_kb > 0) {
                         const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, 0);
                         const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
@@ -332,15 +329,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 }
                                 a_addr = smem_u32(xst + kb * KB_BYTES);
                             } else {
-                                mbar_wait(&a_ready[kb], acnt[kb] & 1);   // k-block kb of the previous epilogue's output
-                                ++acnt[kb];
+                                mbar_wait(&a_ready[kb], (apar >> kb) & 1u);   // k-block kb of the previous epilogue's output
+                                apar ^= 1u << kb;
                                 tc_fence_after();
                                 a_addr = smem_u32(act + kb * KB_BYTES);
-                                if (storing && kb < d.store_kb)
-                                    tma_store_2d(&maps.out[d.store_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
                             }
                             mbar_wait(&wfull[ws], wpar);
                             tc_fence_after();
+                            RLPPO_TRACE(4, tr4++);
                             const uint32_t b_addr = smem_u32(wring + ws * WST_BYTES);
 #pragma unroll
                             for (int k = 0; k < KBLK / 16; ++k) {
@@ -355,51 +351,68 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             }
                         }
                         if (ph == 0) umma_commit(x_free);      // the staging buffer can take the next tile's x
-                        if (storing) {
-                            // the previous epilogue may have produced more k-blocks than this GEMM consumes
-                            for (int kb = d.n_kb; kb < d.store_kb; ++kb) {
-                                mbar_wait(&a_ready[kb], acnt[kb] & 1);
-                                ++acnt[kb];
-                                tc_fence_after();
-                                tma_store_2d(&maps.out[d.store_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                            }
-                            bulk_commit();
-                            bulk_wait_read_all();   // this phase's epilogue overwrites the tile in place
-                        }
-                        RLPPO_TRACE(0, tr0++);   // MMA: all MMAs of (tile, ph) issued, stores have left shared memory
+                        RLPPO_TRACE(0, tr0++);   // MMA: all MMAs of (tile, ph) issued
                         umma_commit(&acc_full[g & 1u]);
                         ++g;
                     } else {
                         // GEMM-less phase (value net: dL/dH_L from the accumulator of the last forward GEMM, still in
-                        // TMEM): store what the previous epilogue left, then hand the SAME accumulator back
+                        // TMEM): consume the previous epilogue's releases, then hand the SAME accumulator back
                         RLPPO_TRACE(0, tr0++);
-                        for (int kb = 0; kb < d.store_kb; ++kb) {
-                            mbar_wait(&a_ready[kb], acnt[kb] & 1);
-                            ++acnt[kb];
-                            tc_fence_after();
-                            if (storing) tma_store_2d(&maps.out[d.store_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                        }
-                        if (storing) {
-                            bulk_commit();
-                            bulk_wait_read_all();
+                        for (int kb = 0; kb < d.wait_kb; ++kb) {
+                            mbar_wait(&a_ready[kb], (apar >> kb) & 1u);
+                            apar ^= 1u << kb;
                         }
                         RLPPO_TRACE(0, tr0++);
                         mbar_arrive(&acc_full[(g - 1u) & 1u]);
                     }
                 }
-                // tail: the last epilogue's output (every k-block it released must be consumed here: barrier parity)
+                // tail: the last epilogue's releases (barrier parity; also: every epilogue warp is done with both
+                // accumulators and the activation tile before the next tile's first GEMM / epilogue touch them)
                 for (int kb = 0; kb < p.tail_rel_kb; ++kb) {
-                    mbar_wait(&a_ready[kb], acnt[kb] & 1);
-                    ++acnt[kb];
-                    tc_fence_after();
-                    if (TRAIN && kb < p.tail_kb)
-                        tma_store_2d(&maps.out[p.tail_map], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                }
-                if (TRAIN) {
-                    bulk_commit();
-                    bulk_wait_read_all();
+                    mbar_wait(&a_ready[kb], (apar >> kb) & 1u);
+                    apar ^= 1u << kb;
                 }
             }
+        }
+    } else if (warp == 10) {
+        // ===================== store thread (training) =====================
+        // Every k-block an epilogue releases is TMA-stored from the activation tile to its HBM tensor (weight-gradient
+        // operand); st_done[kb] tells the epilogue warps when the store has finished READING shared memory, i.e. when the
+        // next epilogue may overwrite that k-block in place.  The MMA thread never waits for stores.
+        if (TRAIN && lane == 0) {
+            uint32_t apar = 0;
+            int nst = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int tile = blockIdx.x + it * gridDim.x;
+#pragma unroll 1
+                for (int ph = 0; ph < p.n_ph; ++ph) {
+                    const PhaseDesc& d = p.ph[ph];
+                    const bool storing = d.out != NO_STORE;
+                    const bool skip = p.dbg_nostore != 0;
+                    int pending = -1;
+                    for (int kb = 0; kb < d.rel_kb; ++kb) {
+                        mbar_wait(&a_ready[kb], (apar >> kb) & 1u);
+                        apar ^= 1u << kb;
+                        if (!storing) continue;
+                        RLPPO_TRACE(2, 2 * nst);
+                        if (!skip) tma_store_2d(&maps.out[d.out], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
+                        bulk_commit();
+                        if (pending >= 0) {
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            mbar_arrive(&st_done[pending]);
+                            RLPPO_TRACE(2, 2 * (nst - 1) + 1);
+                        }
+                        pending = kb;
+                        ++nst;
+                    }
+                    if (pending >= 0) {
+                        bulk_wait_read_all();
+                        mbar_arrive(&st_done[pending]);
+                        RLPPO_TRACE(2, 2 * (nst - 1) + 1);
+                    }
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
         }
     } else {
         // ===================== epilogue warps =====================
@@ -421,7 +434,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         auto db_add = [&](int l, int c, float v) { atomicAdd(&s_db[l * 256 + c * 32 + e.lane], v); };
 
         uint32_t g = 0;                  // mirrors the MMA thread's GEMM counter
-        uint32_t fcnt[2] = {0, 0};       // completions consumed per acc_full barrier
+        uint32_t fpar = 0;               // bit a: parity of acc_full[a] to wait for next
+        uint32_t pend = 0;               // bit kb: a TMA store of k-block kb was issued since this thread last waited for it
+        uint32_t scnt = 0;               // bit kb: parity of st_done[kb] to wait for next
+        // before overwriting k-block kb of the activation tile: its last TMA store must have read it
+        auto wait_store = [&](int kb) {
+            if ((pend >> kb) & 1u) {
+                mbar_wait(&st_done[kb], (scnt >> kb) & 1u);
+                scnt ^= 1u << kb;
+                pend &= ~(1u << kb);
+            }
+        };
         int tr1 = 0;
         for (int it = 0; it < my_tiles; ++it) {
           const int tile = blockIdx.x + it * gridDim.x;
@@ -430,18 +453,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #pragma unroll 1
           for (int ph = 0; ph < p.n_ph; ++ph) {
                 const PhaseDesc& d = p.ph[ph];
-                uint32_t a;
+                uint32_t acc;
                 if (d.n_kb > 0) {
-                    a = g & 1u;
+                    acc = g & 1u;
                     ++g;
                 } else {
-                    a = (g - 1u) & 1u;
+                    acc = (g - 1u) & 1u;
                 }
-                mbar_wait(&acc_full[a], fcnt[a] & 1);
-                ++fcnt[a];
+                mbar_wait(&acc_full[acc], (fpar >> acc) & 1u);
+                fpar ^= 1u << acc;
                 tc_fence_after();
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: accumulator of (tile, ph) complete
-                const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + a * 256u;
+                const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + acc * 256u;
                 uint8_t* dst = act;      // in place: the GEMM that read this tile has completed
                 const int li = d.layer;
 
@@ -459,22 +482,44 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
                         if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);   // next chunk in flight during this one
-                        const float* sb = s_bias + li * 256 + c * 32;
+                        // biases as 8 x 128-bit shared loads (one wavefront each; the MMA's operand fetch owns most of the
+                        // shared-memory bandwidth while this runs)
+                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias + li * 256 + c * 32);
                         uint32_t bq[4] = {0u, 0u, 0u, 0u};   // four independent OR chains (one 32-long chain serialises)
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float xv = fmaxf(v[i] + sb[i], 0.f);
-                            bq[i & 3] |= (xv > 0.f ? 1u : 0u) << i;
-                            v[i] = xv;
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b4 = sb4[q];
+                            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = q * 4 + u;
+                                const float xv = fmaxf(v[i] + bb[u], 0.f);
+                                bq[u] |= (xv > 0.f ? 1u : 0u) << i;
+                                v[i] = xv;
+                            }
                         }
                         if (TRAIN) e.s_mask[(li * 4 + j) * kEpiThreads] = (bq[0] | bq[1]) | (bq[2] | bq[3]);
                         if (tail) {
-                            const float* wv = s_bias + MAXL * 256 + c * 32;
+                            const float4* wv4 = reinterpret_cast<const float4*>(s_bias + MAXL * 256 + c * 32);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) dq[i & 3] = fmaf(bf16_round(v[i]), wv[i], dq[i & 3]);
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 w4 = wv4[q];
+                                dq[0] = fmaf(bf16_round(v[q * 4 + 0]), w4.x, dq[0]);
+                                dq[1] = fmaf(bf16_round(v[q * 4 + 1]), w4.y, dq[1]);
+                                dq[2] = fmaf(bf16_round(v[q * 4 + 2]), w4.z, dq[2]);
+                                dq[3] = fmaf(bf16_round(v[q * 4 + 3]), w4.w, dq[3]);
+                            }
                         }
-                        if (!tail || TRAIN) store_chunk_sw128(dst, e.row_in_tile, c, v);
-                        if (!tail) release_kb(e, j);
+                        if (d.smem) {
+                            uint32_t w[16];
+                            pack32(v, w);
+                            if (TRAIN) wait_store(j);
+                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
+                        }
+                        if (!tail) {
+                            release_kb(e, j);
+                            if (TRAIN && d.out != NO_STORE) pend |= 1u << j;
+                        }
                     }
                     if (tail) {
                         // ---- value head: v = H_L . w + b (value_estimator.py:27), MSE loss and its gradient ----
@@ -523,8 +568,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #pragma unroll
                         for (int i = 0; i < 32; ++i) t[i] = v[i];
                         db_add(li, c, warp_colsum32(t, e.lane));
-                        store_chunk_sw128(dst, e.row_in_tile, c, v);
+                        if (d.smem) {
+                            uint32_t w[16];
+                            pack32(v, w);
+                            if (TRAIN) wait_store(j);
+                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
+                        }
                         release_kb(e, j);
+                        if (d.out != NO_STORE) pend |= 1u << j;
                     }
                 } else if (d.kind == PH_DGRAD) {
                     const int nkb = d.N >> 6;
@@ -542,8 +593,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             t[i] = v[i];
                         }
                         if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);
-                        store_chunk_sw128(dst, e.row_in_tile, c, v);
+                        if (d.smem) {
+                            uint32_t w[16];
+                            pack32(v, w);
+                            if (TRAIN) wait_store(j);
+                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
+                        }
                         release_kb(e, j);                                // the next GEMM starts; the column sums follow
+                        if (d.out != NO_STORE) pend |= 1u << j;
                         db_add(li, c, warp_colsum32(t, e.lane));
                     }
                 } else {
@@ -696,7 +753,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         }
                         const float cs = warp_colsum16(t, e.lane);
                         if (e.lane < 16) atomicAdd(&s_db[MAXL * 256 + c * 32 + hoff + e.lane], cs);
-                        store_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, v);
+                        {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
+                            wait_store(c >> 1);
+                            sts_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, w);
+                        }
                     }
                 } else {
                     // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62): the inverse-CDF scan is
@@ -762,7 +825,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     }
                 }
                     if (TRAIN) {
-                        for (int j = 0; j < p.out_kb; ++j) release_kb(e, j);
+                        for (int j = 0; j < p.out_kb; ++j) {
+                            release_kb(e, j);
+                            if (d.out != NO_STORE) pend |= 1u << j;
+                        }
                     }
                 }
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (tile, ph) done
@@ -850,7 +916,7 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     rc = make_tmap_bf16_2d(&maps.x, x, (uint64_t)M, (uint64_t)net->in_dim, (uint64_t)net->in_ld, TILE_M);
     if (rc) return rc;
 
-    int nw = 0, nout = 0, nph = 0;
+    int nw = 0, nph = 0;
     for (int i = 0; i < MAXPH; ++i) p.ph[i] = PhaseDesc{};
     auto add_w = [&](const uint16_t* w, int64_t ld, int rows, int cols, int box_rows) -> int {
         RLPPO_CHECK_ARG(w != nullptr && ld % 8 == 0, "missing weight operand");
@@ -859,96 +925,85 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         ++nw;
         return RLPPO_OK;
     };
+    int nout = 0;
     auto add_out = [&](uint16_t* o, int64_t ld, int cols) -> int {
         RLPPO_CHECK_ARG(o != nullptr && ld % 8 == 0 && ld >= cols, "missing activation / gradient output buffer");
         int r = make_tmap_bf16_2d(&maps.out[nout], o, (uint64_t)M, (uint64_t)cols, (uint64_t)ld, TILE_M);
         if (r) return r;
-        ++nout;
-        return RLPPO_OK;
+        return nout++;
     };
     const int out_pad8 = POLICY ? (p.n_actions + 7) / 8 * 8 : 0;
     const int head_N = POLICY ? (p.n_actions + 15) / 16 * 16 : 0;
     p.out_kb = POLICY ? (out_pad8 + KBLK - 1) / KBLK : 0;
-
-    // output maps: [0..L) = H_l ; policy: [L] = dz, [L+1 .. 2L] = dH_L .. dH_1 ; value: [L .. 2L) = dH_L .. dH_1
-    int map_h[MAXL], map_dz = -1, map_dh[MAXL];
-    if (TRAIN) {
-        for (int l = 0; l < L; ++l) {
-            map_h[l] = nout;
-            rc = add_out(net->h[l], net->h_ld[l], net->hidden[l]);
-            if (rc) return rc;
-        }
-        if (POLICY) {
-            map_dz = nout;
-            rc = add_out(net->dz, net->dz_ld, out_pad8);
-            if (rc) return rc;
-        }
-        for (int l = L - 1; l >= 0; --l) {
-            map_dh[l] = nout;
-            rc = add_out(net->dh[l], net->dh_ld[l], net->hidden[l]);
-            if (rc) return rc;
-        }
-    }
     auto kb_of = [](int cols) { return (cols + KBLK - 1) / KBLK; };
-    auto add_phase = [&](int kind, int layer, int n_kb, int N, int wmap, int store_map, int store_kb) {
+    auto add_phase = [&](int kind, int layer, int n_kb, int N, int wmap, int out, int smem_out, int wait_kb, int rel_kb) {
         PhaseDesc& d = p.ph[nph++];
         d.kind = (uint8_t)kind;
         d.layer = (uint8_t)layer;
         d.n_kb = (uint8_t)n_kb;
         d.wmap = (uint8_t)wmap;
         d.N = (uint16_t)N;
-        d.store_map = (uint8_t)(TRAIN && store_map >= 0 ? store_map : NO_STORE);
-        d.store_kb = (uint8_t)store_kb;
+        d.out = (uint8_t)(TRAIN && out >= 0 ? out : NO_STORE);
+        d.smem = (uint8_t)smem_out;
+        d.wait_kb = (uint8_t)wait_kb;
+        d.rel_kb = (uint8_t)rel_kb;
     };
 
-    // ---- forward phases: the tile is overwritten in place, so each phase stores what the previous epilogue left ----
-    int prev_map = -1, prev_kb = 0;    // the tile currently in the slot buffer, if it has to reach HBM
+    // ---- forward phases ----
     for (int l = 0; l < L; ++l) {
         const int K = l == 0 ? net->in_dim : net->hidden[l - 1];
         const int wmap = nw;
         rc = add_w(net->wq[l], net->wq_ld[l], net->hidden[l], K, net->hidden[l]);
         if (rc) return rc;
-        add_phase((!POLICY && l == L - 1) ? PH_FWD_VALUE : PH_FWD, l, kb_of(K), net->hidden[l], wmap, prev_map, prev_kb);
-        prev_map = TRAIN ? map_h[l] : -1;
-        prev_kb = kb_of(net->hidden[l]);
+        const bool value_tail = !POLICY && l == L - 1;
+        // H_l goes to HBM as a weight-gradient operand; the value net's last hidden activation is not one (its head's
+        // weight gradient is formed in-kernel) and is not a GEMM operand either (the head is a register dot product)
+        int out = -1;
+        if (TRAIN && !value_tail) {
+            out = add_out(net->h[l], net->h_ld[l], net->hidden[l]);
+            if (out < 0) return out;
+        }
+        add_phase(value_tail ? PH_FWD_VALUE : PH_FWD, l, kb_of(K), net->hidden[l], wmap, out, value_tail ? 0 : 1, 0,
+                  kb_of(net->hidden[l]));
     }
     if (POLICY) {
         const int wmap = nw;
         rc = add_w(net->wq[L], net->wq_ld[L], out_pad8, net->hidden[L - 1], head_N);
         if (rc) return rc;
-        add_phase(PH_HEAD, L, kb_of(net->hidden[L - 1]), head_N, wmap, prev_map, prev_kb);
-        prev_map = TRAIN ? map_dz : -1;
-        prev_kb = p.out_kb;
+        int out = -1;
+        if (TRAIN) {
+            out = add_out(net->dz, net->dz_ld, out_pad8);
+            if (out < 0) return out;
+        }
+        add_phase(PH_HEAD, L, kb_of(net->hidden[L - 1]), head_N, wmap, out, TRAIN ? 1 : 0, 0, TRAIN ? p.out_kb : 0);
     }
-    p.tail_map = 0;
-    p.tail_kb = 0;
-    // inference: the policy head releases nothing, the value tail releases H_L's k-blocks
+    // k-blocks the last epilogue releases.  inference: the policy head releases nothing, the value tail H_L's k-blocks
     p.tail_rel_kb = POLICY ? 0 : kb_of(net->hidden[L - 1]);
     if (TRAIN) {
-        // ---- backward data phases ----
+        // ---- backward data phases: dL/dH_l is written into the activation tile (the next dgrad GEMM's A operand) and
+        // TMA-stored from there to HBM (weight-gradient operand) ----
+        int out = add_out(net->dh[L - 1], net->dh_ld[L - 1], net->hidden[L - 1]);
+        if (out < 0) return out;
         if (POLICY) {
             const int wmap = nw;
             rc = add_w(net->wt[L], net->wt_ld[L], net->hidden[L - 1], out_pad8, net->hidden[L - 1]);
             if (rc) return rc;
-            add_phase(PH_DGRAD, L - 1, p.out_kb, net->hidden[L - 1], wmap, prev_map, prev_kb);
+            add_phase(PH_DGRAD, L - 1, p.out_kb, net->hidden[L - 1], wmap, out, 1, 0, kb_of(net->hidden[L - 1]));
         } else {
-            // GEMM-less phase: H_L (left by the forward tail) is stored, its epilogue writes dL/dH_L in place
-            add_phase(PH_VALUE_BWD, L - 1, 0, net->hidden[L - 1], 0, prev_map, prev_kb);
+            // GEMM-less phase: dL/dH_L from the accumulator of the last forward GEMM (still in TMEM)
+            add_phase(PH_VALUE_BWD, L - 1, 0, net->hidden[L - 1], 0, out, 1, kb_of(net->hidden[L - 1]),
+                      kb_of(net->hidden[L - 1]));
         }
-        prev_map = map_dh[L - 1];
-        prev_kb = kb_of(net->hidden[L - 1]);
         for (int l = L - 1; l >= 1; --l) {
             // produce dH (hidden index l-1) from dH (hidden index l) with W_l^T = wt[l]
             const int wmap = nw;
             rc = add_w(net->wt[l], net->wt_ld[l], net->hidden[l - 1], net->hidden[l], net->hidden[l - 1]);
             if (rc) return rc;
-            add_phase(PH_DGRAD, l - 1, kb_of(net->hidden[l]), net->hidden[l - 1], wmap, prev_map, prev_kb);
-            prev_map = map_dh[l - 1];
-            prev_kb = kb_of(net->hidden[l - 1]);
+            out = add_out(net->dh[l - 1], net->dh_ld[l - 1], net->hidden[l - 1]);
+            if (out < 0) return out;
+            add_phase(PH_DGRAD, l - 1, kb_of(net->hidden[l]), net->hidden[l - 1], wmap, out, 1, 0, kb_of(net->hidden[l - 1]));
         }
-        p.tail_map = prev_map;
-        p.tail_kb = prev_kb;
-        p.tail_rel_kb = prev_kb;
+        p.tail_rel_kb = kb_of(net->hidden[0]);
     }
     p.n_ph = nph;
 
@@ -967,15 +1022,16 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     static unsigned long long* d_trace = nullptr;
     const bool tracing = getenv("RLPPO_FUSED_TRACE") != nullptr && TRAIN && POLICY;
+    p.dbg_nostore = getenv("RLPPO_FUSED_NOSTORE") != nullptr ? 1 : 0;
     if (tracing) {
-        if (d_trace == nullptr) RLPPO_CUDA(cudaMalloc(&d_trace, 1024 * sizeof(unsigned long long)));
-        RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 1024 * sizeof(unsigned long long), s));
+        if (d_trace == nullptr) RLPPO_CUDA(cudaMalloc(&d_trace, 2560 * sizeof(unsigned long long)));
+        RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 2560 * sizeof(unsigned long long), s));
         p.trace = d_trace;
     }
     kfn<<<grid, kThreads, smem_bytes, s>>>(maps, p);
     RLPPO_LAUNCH_CHECK();
     if (tracing) {
-        static unsigned long long h[1024];
+        static unsigned long long h[2560];
         RLPPO_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
         RLPPO_CUDA(cudaStreamSynchronize(s));
         const unsigned long long t0 = h[0];
@@ -984,6 +1040,12 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
             fprintf(stderr, "  mma  #%d start=%llu issued+stored=+%llu\n", i / 2, h[i] - t0, h[i + 1] - h[i]);
         for (int i = 0; i + 1 < 512 && h[512 + i] != 0; i += 2)
             fprintf(stderr, "  epi  #%d start=%llu dur=%llu\n", i / 2, h[512 + i] - t0, h[512 + i + 1] - h[512 + i]);
+        for (int i = 0; i + 1 < 512 && h[1024 + i] != 0; i += 2)
+            fprintf(stderr, "  store #%d issued=%llu read_done=+%llu\n", i / 2, h[1024 + i] - t0, h[1024 + i + 1] - h[1024 + i]);
+        for (int i = 0; i < 512 && h[1536 + i] != 0; ++i)
+            fprintf(stderr, "  wload #%d issued=%llu\n", i, h[1536 + i] - t0);
+        for (int i = 0; i < 512 && h[2048 + i] != 0; ++i)
+            fprintf(stderr, "  wfull #%d at=%llu\n", i, h[2048 + i] - t0);
     }
     return RLPPO_OK;
 }
