@@ -142,9 +142,11 @@ class PPOLearner(object):
         self._graph_warm = set()
         self._idx_cur = None
         self._perm_dev = None
-        # capture the NCCL allreduces inside the whole-call graph when data parallel (torch's NCCL process group is
-        # graph-capturable); off -> two graphs per optimiser step with an eager allreduce between them
-        self.graph_collectives = os.environ.get("RLPPO_GRAPH_COLLECTIVES", "1") != "0"
+        # RLPPO_GRAPH_COLLECTIVES=1: capture the NCCL allreduces inside the whole-call graph when data parallel.  Off by
+        # default: measured on 2 x B200 it buys 1 % (the step is bound by the collectives' latency, not by their launch)
+        # and process-group teardown hangs with captured NCCL work outstanding.  Default: two graphs per optimiser step
+        # with an eager allreduce between them.
+        self.graph_collectives = os.environ.get("RLPPO_GRAPH_COLLECTIVES", "0") == "1"
 
     # ---- workspaces ----------------------------------------------------------------------------------------
     def _minibatch_buffers(self, rows):

@@ -34,9 +34,13 @@ class WelfordRunningStat(object):
         if self._d is None:
             _lib.require_device()
             dev = torch.device(self._device if self._device is not None else "cuda:%d" % torch.cuda.current_device())
-            z = lambda: torch.zeros(self._dim, dtype=torch.float32, device=dev)  # noqa: E731
-            self._d = {"mean": z(), "m2": z(), "count": torch.zeros(1, dtype=torch.int64, device=dev),
-                       "std": torch.ones(self._dim, dtype=torch.float32, device=dev), "mean_out": z()}
+            # one contiguous allocation [count i64 | mean | m2 | std | mean_out] so the whole state is ONE broadcast
+            n = self._dim
+            raw = torch.zeros(8 + 16 * n, dtype=torch.uint8, device=dev)
+            f = raw[8:].view(torch.float32)
+            self._d = {"raw": raw, "count": raw[0:8].view(torch.int64), "mean": f[0:n], "m2": f[n:2 * n],
+                       "std": f[2 * n:3 * n], "mean_out": f[3 * n:4 * n]}
+            self._d["std"].fill_(1.0)
         return self._d
 
     def _push(self):
@@ -64,12 +68,7 @@ class WelfordRunningStat(object):
         rewards with the same scale."""
         import torch.distributed as dist
         d = self._push()
-        pack = torch.cat((d["mean"], d["m2"], d["std"], d["mean_out"]))
-        dist.broadcast(pack, src=src, group=group)
-        dist.broadcast(d["count"], src=src, group=group)
-        n = self._dim
-        d["mean"].copy_(pack[0:n]); d["m2"].copy_(pack[n:2 * n]); d["std"].copy_(pack[2 * n:3 * n])
-        d["mean_out"].copy_(pack[3 * n:4 * n])
+        dist.broadcast(d["raw"], src=src, group=group)
         self._dev_is_newer = True
 
     def device_std(self):

@@ -48,11 +48,17 @@ def main():
     # ---- replicated: same buffer everywhere; compare with a one-rank learner on the same buffer ----
     dp, alone = learner(None, "replicated"), learner(solo, "replicated")
     assert dp.world_size == world and alone.world_size == 1
+    p_init = dp._params.clone()
     for it in range(3):                                  # eager, captured, replayed
         rep_dp = dp.learn(make_buffer(100 + it, n, dev))
         rep_1 = alone.learn(make_buffer(100 + it, n, dev))
-    err = float((dp._params - alone._params).abs().max())
-    assert err < 5e-6, f"replicated DP differs from the single-rank run: {err}"
+    # Same per-row math, different order of the fp32 sums (tests/test_learner_gpu.py::test_row_partition_invariance shows
+    # the single-GPU version of this statement).  Adam amplifies a 1e-10 wobble on gradient elements of magnitude <= eps,
+    # so compare the update: 1e-3 rel-L2, and no element off by as much as one step (lr) after 18 steps.
+    upd_dp, upd_1 = dp._params - p_init, alone._params - p_init
+    err = float((upd_dp - upd_1).norm() / upd_1.norm())
+    assert err < 1e-3, f"replicated DP differs from the single-rank run: rel-L2 of the update {err}"
+    assert float((upd_dp - upd_1).abs().max()) < 3e-4
     assert float((dp._m - alone._m).abs().max()) < 1e-6
     for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
         assert abs(rep_dp[k] - rep_1[k]) < 1e-5 * max(1.0, abs(rep_1[k])), (k, rep_dp[k], rep_1[k])

@@ -499,3 +499,33 @@ def test_graph_replayed_iteration_equals_eager(pkg):
         assert a["Cumulative Model Updates"] == b["Cumulative Model Updates"]
         for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
             assert abs(a[k] - b[k]) <= 1e-4 * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
+def test_row_partition_invariance(pkg):
+    """Gradient accumulation over chunks of a batch (the reference's minibatches, ppo_learner.py:134-193; also what the
+    data-parallel ranks do) must give the full-batch result: same kernels, same per-row math, only the order of the fp32
+    sums differs (tools/partition_debug.py: gradients agree to 1e-7 rel-L2, the run-to-run noise of the atomics).
+    Adam turns a 1e-10 absolute wobble on a gradient element of magnitude <= eps = 1e-8 into a few % of a step, so the
+    weights are compared the way that makes sense for Adam: the UPDATE (theta - theta_0) agrees to 1e-3 rel-L2 and no
+    element differs by as much as one step (lr) after 18 steps -- whether a 2048-row batch is processed in one chunk,
+    two, or sixteen (128-row tiles: every CTA gets one tile)."""
+    import contextlib
+    import io
+    from tests.dp_check import make_buffer
+    from rlgym_ppo_b200.ppo import PPOLearner
+    B, n, lr_ = 2048, 3 * 2048, 3e-4
+    outs = []
+    for chunk in (2048, 1024, 128):
+        torch.manual_seed(5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            lr = PPOLearner(89, 90, 0, (256, 256), (256, 256), (0.1, 1.0), B, 2, lr_, lr_, 0.2, 0.01, B, DEV,
+                            max_chunk_rows=chunk)
+        p0 = lr._params.clone()
+        reps = [lr.learn(make_buffer(100 + it, n, DEV)) for it in range(3)]
+        outs.append((lr._params - p0, reps[-1]))
+    for upd, rep in outs[1:]:
+        diff = upd - outs[0][0]
+        assert float(diff.norm() / outs[0][0].norm()) < 1e-3, float(diff.norm() / outs[0][0].norm())
+        assert float(diff.abs().max()) < lr_, float(diff.abs().max())
+        for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
+            assert abs(rep[k] - outs[0][1][k]) < 1e-5 * max(1.0, abs(outs[0][1][k])), (k, rep[k], outs[0][1][k])
