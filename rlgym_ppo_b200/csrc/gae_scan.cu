@@ -273,21 +273,56 @@ __device__ __forceinline__ Aff shfl_up(const Aff& x, int off) {
                __shfl_up_sync(0xffffffffu, x.aR, off), __shfl_up_sync(0xffffffffu, x.bR, off)};
 }
 
+// Tile records without flags or fences: a record (aggregate or inclusive map, 4 doubles) is written with two 16-byte
+// relaxed gpu-scope vector stores and polled with two relaxed gpu-scope vector loads.  The workspace is pre-set to
+// all-ones bytes -- a NaN pattern no computation produces -- and a record counts as arrived when none of its four
+// doubles is that pattern (each 8-byte element is single-copy atomic, so nothing torn can pass the test).  The accesses
+// must be STRONG (.relaxed.gpu), not plain .cg: a weak load may be served by the reader's own L2 partition and never
+// observe the other die's store.  (The first version published a status word with __threadfence() + st.release and
+// polled it with ld.acquire: ncu showed 12 % of all stall samples on the CCTL.IVALL the acquire emits, plus a dependent
+// second load per look-back round.)
+__device__ __forceinline__ void rec_store(double* rec, const Aff& m) {
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(rec), "d"(m.aA), "d"(m.bA) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(rec + 2), "d"(m.aR), "d"(m.bR) : "memory");
+}
+__device__ __forceinline__ bool rec_load(const double* rec, Aff& m) {
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(m.aA), "=d"(m.bA) : "l"(rec) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];" : "=d"(m.aR), "=d"(m.bR) : "l"(rec + 2) : "memory");
+    constexpr long long kUnset = -1LL;   // 0xFFFF'FFFF'FFFF'FFFF
+    return __double_as_longlong(m.aA) != kUnset && __double_as_longlong(m.bA) != kUnset &&
+           __double_as_longlong(m.aR) != kUnset && __double_as_longlong(m.bR) != kUnset;
+}
+
 template <bool TRUNC64>
 struct StepMaps {
     const float* r;
     const float* d;
     const float* v;   // kTile2 + 1 entries
     const void* t;
-    double gamma;
+    double gamma, gl64;   // gl64 = (double)gl32
     float gl32, stdv;
     bool has_std;
-    // affine maps of local step j (torch_functions.py:59-72, the reference's NumPy>=2 rounding points)
-    __device__ __forceinline__ Aff at(int j) const {
-        const float dj = d[j], rj = r[j];
+    // multipliers of local step j (torch_functions.py:59-60, 69, 72).  Flags that are exactly 0 or 1 -- what the
+    // collector produces -- take a select instead of three f64 multiplies and two conversions; anything else is
+    // evaluated as written in the reference.
+    __device__ __forceinline__ void mults(int j, double& aA, double& aR) const {
+        const float dj = d[j];
         const double trj = TRUNC64 ? static_cast<const double*>(t)[j] : (double)static_cast<const float*>(t)[j];
-        const float nd = __fsub_rn(1.0f, dj);                                // :59
-        const double nt = 1.0 - trj;                                         // :60
+        if ((dj == 0.f || dj == 1.f) && (trj == 0.0 || trj == 1.0)) {
+            const bool live = dj == 0.f && trj == 0.0;
+            aA = live ? gl64 : 0.0;
+            aR = live ? gamma : 0.0;
+        } else {
+            const float nd = __fsub_rn(1.0f, dj);                            // :59
+            const double nt = 1.0 - trj;                                     // :60
+            aA = (double)__fmul_rn(gl32, nd) * nt;                           // :72
+            aR = gamma * (double)nd * nt;                                    // :69
+        }
+    }
+    // delta_j (f32, the reference's NumPy>=2 rounding points, :62-68)
+    __device__ __forceinline__ float delta(int j) const {
+        const float rj = r[j];
+        const float nd = __fsub_rn(1.0f, d[j]);                              // :59
         float nr = rj;
         if (has_std) {                                                       // :62-65
             nr = __fdiv_rn(rj, stdv);
@@ -295,13 +330,7 @@ struct StepMaps {
         }
         const float gv = (float)(gamma * (double)v[j + 1]);
         const float pred = __fadd_rn(nr, __fmul_rn(gv, nd));                 // :67
-        const float delta = __fsub_rn(pred, v[j]);                           // :68
-        Aff f;
-        f.aA = (double)__fmul_rn(gl32, nd) * nt;                             // :72
-        f.bA = (double)delta;
-        f.aR = gamma * (double)nd * nt;                                      // :69
-        f.bR = (double)rj;
-        return f;
+        return __fsub_rn(pred, v[j]);                                        // :68
     }
 };
 
@@ -316,11 +345,14 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
     float* s_r = reinterpret_cast<float*>(sm2);
     float* s_d = s_r + kTile2;
     float* s_v = s_d + kTile2;                                  // kTile2 + 4 floats (halo + padding to 16 bytes)
-    void* s_t = s_v + kTile2 + 4;
+    float* s_delta = s_v + kTile2 + 4;                          // delta_j, formed once in phase A
+    void* s_t = s_delta + kTile2;
     __shared__ uint64_t s_bar;
     __shared__ int s_tile;
     __shared__ double s_warp[kW2][4];
-    __shared__ double s_carry[2];
+    __shared__ double s_agg[4];
+    __shared__ double s_win[kW2][4];
+    __shared__ int s_winflag[kW2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -372,7 +404,7 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
 
     StepMaps<TRUNC64> sm;
     sm.r = s_r; sm.d = s_d; sm.v = s_v; sm.t = s_t;
-    sm.gamma = gamma; sm.gl32 = gl32;
+    sm.gamma = gamma; sm.gl32 = gl32; sm.gl64 = (double)gl32;
     sm.has_std = ret_std != nullptr;
     sm.stdv = sm.has_std ? __ldg(ret_std) : 1.f;
 
@@ -381,7 +413,15 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
     Aff agg = aff_identity();
 #pragma unroll
     for (int i = kI2 - 1; i >= 0; --i)
-        if (j0 + i < cnt) agg = compose(sm.at(j0 + i), agg);
+        if (j0 + i < cnt) {
+            Aff f;
+            sm.mults(j0 + i, f.aA, f.aR);
+            const float dl = sm.delta(j0 + i);
+            s_delta[j0 + i] = dl;          // read back by this same thread in phase B
+            f.bA = (double)dl;
+            f.bR = (double)s_r[j0 + i];
+            agg = compose(f, agg);
+        }
     const Aff incl_w = warp_suffix_scan(agg, lane);
     Aff excl = shfl_down(incl_w, 1);
     if (lane == 31) excl = aff_identity();
@@ -400,77 +440,94 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
         if (lane < kW2) {
             s_warp[lane][0] = we.aA; s_warp[lane][1] = we.bA; s_warp[lane][2] = we.aR; s_warp[lane][3] = we.bR;
         }
-        const Aff tile_agg = shfl_idx(wi, 0);
-
-        // ---- decoupled look-back: map of everything to the right of this tile ----
-        Aff right = aff_identity();
-        if (tile > 0) {
-            if (lane == 0) {
-                double* a = ws.agg + (size_t)tile * 4;
-                a[0] = tile_agg.aA; a[1] = tile_agg.bA; a[2] = tile_agg.aR; a[3] = tile_agg.bR;
-                __threadfence();
-                rlppo::st_release_s32(ws.status + tile, 1);
-            }
-            int look = tile - 1;
-            for (;;) {
-                const int j = look - lane;      // lane 0 = the nearest tile to the right
-                int st = 2;
-                Aff m = aff_identity();         // j < 0: nothing to the right of tile 0
-                if (j >= 0) {
-                    const long long t0 = clock64();
-                    do {
-                        st = rlppo::ld_acquire_s32(ws.status + j);
-                        if (st == 0 && clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
-                    } while (st == 0);
-                    const double* src = (st == 2 ? ws.incl : ws.agg) + (size_t)j * 4;
-                    m = Aff{__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3)};
-                }
-                const unsigned done_mask = __ballot_sync(0xffffffffu, st == 2);
-                const int upto = done_mask ? (__ffs(done_mask) - 1) : 31;
-                if (lane > upto) m = aff_identity();
-                // inclusive prefix over lanes, lower lane = outer map: lane l ends with m_0 o m_1 o ... o m_l
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const Aff y = shfl_up(m, off);
-                    if (lane >= off) m = compose(y, m);
-                }
-                right = compose(right, shfl_idx(m, 31));
-                if (done_mask != 0) break;
-                look -= 32;
-            }
-        }
-        const Aff incl = compose(tile_agg, right);
         if (lane == 0) {
-            double* o = ws.incl + (size_t)tile * 4;
-            o[0] = incl.aA; o[1] = incl.bA; o[2] = incl.aR; o[3] = incl.bR;
-            __threadfence();
-            rlppo::st_release_s32(ws.status + tile, 2);
-            const double cA = carry_in ? carry_in[0] : 0.0;
-            const double cR = carry_in ? carry_in[1] : 0.0;
-            s_carry[0] = fma(right.aA, cA, right.bA);
-            s_carry[1] = fma(right.aR, cR, right.bR);
-            if (summary_out != nullptr && tile == n_tiles - 1) {
-                summary_out[0] = incl.aA; summary_out[1] = incl.bA;
-                summary_out[2] = incl.aR; summary_out[3] = incl.bR;
+            s_agg[0] = wi.aA; s_agg[1] = wi.bA; s_agg[2] = wi.aR; s_agg[3] = wi.bR;   // the tile's own map
+            if (tile > 0) rec_store(ws.agg + (size_t)tile * 4, wi);
+        }
+    }
+    __syncthreads();
+
+    // ---- decoupled look-back, ALL warps: warp w inspects tiles tile-1-32w-lane (256 tiles per round) ----
+    // The chain of inclusive prefixes advances by one look-back round per (poll + load + scan) latency; with one warp it
+    // moved 32 tiles = 65 k steps per ~1 us, which capped v2's first version at 55 G steps/s whatever the memory system did.
+    Aff right = aff_identity();
+    if (tile > 0) {
+        int look = tile - 1;
+        for (;;) {
+            const int j = look - (warp * 32 + lane);    // lane 0 of warp 0 = the nearest tile to the right
+            int st = 2;
+            Aff m = aff_identity();                     // j < 0: nothing to the right of tile 0
+            if (j >= 0) {
+                const long long t0 = clock64();
+                for (;;) {
+                    if (rec_load(ws.incl + (size_t)j * 4, m)) {
+                        st = 2;
+                        break;
+                    }
+                    if (rec_load(ws.agg + (size_t)j * 4, m)) {
+                        st = 1;
+                        break;
+                    }
+                    if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
+                }
             }
+            const unsigned done_mask = __ballot_sync(0xffffffffu, st == 2);
+            const int upto = done_mask ? (__ffs(done_mask) - 1) : 31;
+            if (lane > upto) m = aff_identity();
+            // inclusive prefix over lanes, lower lane = outer map: lane l ends with m_0 o m_1 o ... o m_l
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const Aff y = shfl_up(m, off);
+                if (lane >= off) m = compose(y, m);
+            }
+            if (lane == 31) {
+                s_win[warp][0] = m.aA; s_win[warp][1] = m.bA; s_win[warp][2] = m.aR; s_win[warp][3] = m.bR;
+                s_winflag[warp] = done_mask != 0 ? 1 : 0;
+            }
+            __syncthreads();
+            bool finished = false;
+#pragma unroll
+            for (int w = 0; w < kW2; ++w) {
+                if (!finished) {
+                    right = compose(right, Aff{s_win[w][0], s_win[w][1], s_win[w][2], s_win[w][3]});
+                    finished = s_winflag[w] != 0;
+                }
+            }
+            __syncthreads();   // s_win is rewritten in the next round
+            if (finished) break;
+            look -= kT2;
+        }
+    }
+    if (tid == 0) {
+        const Aff tile_agg = Aff{s_agg[0], s_agg[1], s_agg[2], s_agg[3]};
+        const Aff incl = compose(tile_agg, right);
+        rec_store(ws.incl + (size_t)tile * 4, incl);
+        if (summary_out != nullptr && tile == n_tiles - 1) {
+            summary_out[0] = incl.aA; summary_out[1] = incl.bA;
+            summary_out[2] = incl.aR; summary_out[3] = incl.bR;
         }
     }
     if (!STORE) return;
-    __syncthreads();
+    // every thread holds `right`: the values just right of this tile
+    const double cA = carry_in ? carry_in[0] : 0.0;
+    const double cR = carry_in ? carry_in[1] : 0.0;
+    const double carryA = fma(right.aA, cA, right.bA);
+    const double carryR = fma(right.aR, cR, right.bR);
 
     // ---- phase B: values just right of this thread's steps, then the per-step maps again (from shared memory) ----
     const Aff wr = Aff{s_warp[warp][0], s_warp[warp][1], s_warp[warp][2], s_warp[warp][3]};
     const Aff e = compose(excl, wr);
-    double xA = fma(e.aA, s_carry[0], e.bA);
-    double xR = fma(e.aR, s_carry[1], e.bR);
+    double xA = fma(e.aA, carryA, e.bA);
+    double xR = fma(e.aR, carryR, e.bR);
     float oa[kI2], ov[kI2], orr[kI2];
     const int64_t gbase = base0 + j0;
 #pragma unroll
     for (int i = kI2 - 1; i >= 0; --i) {
         if (j0 + i < cnt) {
-            const Aff f = sm.at(j0 + i);
-            xA = fma(f.aA, xA, f.bA);
-            xR = fma(f.aR, xR, f.bR);
+            double aA, aR;
+            sm.mults(j0 + i, aA, aR);
+            xA = fma(aA, xA, (double)s_delta[j0 + i]);
+            xR = fma(aR, xR, (double)s_r[j0 + i]);
             if (ret_head != nullptr && gbase + i < n_head) ret_head[gbase + i] = xR;
         }
         oa[i] = (float)xA;                              // :76
@@ -540,10 +597,17 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
                                                                 ret_std, adv, vtarget, ret, ret_head64,  \
                                                                 n_head, carry_in, summary_out, ws, n_tiles)
     if (vec) {
-        // staged kernel: 3 f32 arrays + the truncated flags + the halo slot
-        const size_t smem = (size_t)(3 * kTile2 + 4) * 4 + (size_t)kTile2 * (trunc_is_f64 ? 8 : 4);
-        static_assert((3 * kTile2 + 4) * 4 + kTile2 * 8 <= 48 * 1024, "fits the default dynamic shared memory limit");
+        // staged kernel: r, done, V (+ halo), delta as f32 + the truncated flags; records pre-set to the all-ones sentinel
+        const size_t smem = (size_t)(4 * kTile2 + 4) * 4 + (size_t)kTile2 * (trunc_is_f64 ? 8 : 4);
+        RLPPO_CUDA(cudaMemsetAsync(base + L.agg_off, 0xFF, L.total - L.agg_off, s));
         auto launch2 = [&](auto kfn) -> cudaError_t {
+            static bool configured = false;     // per instantiation (generic lambda): > 48 KB needs the opt-in once
+            if (!configured) {
+                cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)((4 * kTile2 + 4) * 4 + kTile2 * 8));
+                if (e != cudaSuccess) return e;
+                configured = true;
+            }
             kfn<<<n_tiles, kT2, smem, s>>>(rew, done, trunc, values, n, gamma, gl32, ret_std, adv, vtarget, ret, ret_head64,
                                           n_head, carry_in, summary_out, ws, n_tiles);
             return cudaSuccess;
