@@ -600,20 +600,22 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
         // staged kernel: r, done, V (+ halo), delta as f32 + the truncated flags; records pre-set to the all-ones sentinel
         const size_t smem = (size_t)(4 * kTile2 + 4) * 4 + (size_t)kTile2 * (trunc_is_f64 ? 8 : 4);
         RLPPO_CUDA(cudaMemsetAsync(base + L.agg_off, 0xFF, L.total - L.agg_off, s));
-        auto launch2 = [&](auto kfn) -> cudaError_t {
-            static bool configured = false;     // per instantiation (generic lambda): > 48 KB needs the opt-in once
-            if (!configured) {
+        // > 48 KB of dynamic shared memory needs the opt-in once PER KERNEL (both instantiations share one function-pointer
+        // type, so the flag is indexed by the instantiation, not kept in a generic lambda)
+        static bool configured[2] = {false, false};
+        auto launch2 = [&](auto kfn, int which) -> cudaError_t {
+            if (!configured[which]) {
                 cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int)((4 * kTile2 + 4) * 4 + kTile2 * 8));
                 if (e != cudaSuccess) return e;
-                configured = true;
+                configured[which] = true;
             }
             kfn<<<n_tiles, kT2, smem, s>>>(rew, done, trunc, values, n, gamma, gl32, ret_std, adv, vtarget, ret, ret_head64,
                                           n_head, carry_in, summary_out, ws, n_tiles);
             return cudaSuccess;
         };
-        if (trunc_is_f64) RLPPO_CUDA(launch2(gae_scan2_kernel<true, STORE>));
-        else RLPPO_CUDA(launch2(gae_scan2_kernel<false, STORE>));
+        if (trunc_is_f64) RLPPO_CUDA(launch2(gae_scan2_kernel<true, STORE>, 1));
+        else RLPPO_CUDA(launch2(gae_scan2_kernel<false, STORE>, 0));
     } else if (trunc_is_f64) {
         RLPPO_GAE_LAUNCH(true, false);
     } else {

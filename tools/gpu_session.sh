@@ -1,0 +1,52 @@
+#!/bin/bash
+# One GPU-box session: parity tests, bench lines, ncu launch list, ncu --set full captures, GAE sweep.
+# Usage (from the repo root, under gpurun):  bash tools/gpu_session.sh <tag> [what ...]
+#   what: tests bench_c2 bench_c3 launches full_c2 full_c3 sweep     (default: all but full_c3)
+set -u
+TAG=${1:-r01}
+shift || true
+WHAT=${*:-tests bench_c2 launches full_c2 sweep bench_c3}
+O=gpurun_out
+mkdir -p $O
+has() { [[ " $WHAT " == *" $1 "* ]]; }
+
+if has tests; then
+  timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1
+  tail -3 $O/${TAG}_pytest_gpu.log
+fi
+if has bench_c2; then
+  timeout 600 python bench.py --steps 20 --warmup 3 > $O/${TAG}_bench_c2.json 2> $O/${TAG}_bench_c2.err
+  cut -c1-600 $O/${TAG}_bench_c2.json
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_c2_reference.json 2>> $O/${TAG}_bench_c2.err
+fi
+if has launches; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file $O/${TAG}_launches_c2.csv python tools/ncu_step.py --workload c2 > $O/${TAG}_launches_c2.log 2>&1
+  python tools/summarize_launches.py $O/${TAG}_launches_c2.csv > $O/${TAG}_launches_c2.md 2>&1
+  cat $O/${TAG}_launches_c2.md
+fi
+if has full_c2; then
+  timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o $O/${TAG}_full_c2 \
+      python tools/ncu_step.py --workload c2 --gae-log2 26 > $O/${TAG}_full_c2.log 2>&1
+  tail -2 $O/${TAG}_full_c2.log
+fi
+if has sweep; then
+  timeout 900 python tools/gae_sweep.py --max-log2 30 --check > $O/${TAG}_gae_sweep.jsonl 2> $O/${TAG}_gae_sweep.err
+  cat $O/${TAG}_gae_sweep.jsonl | cut -c1-220
+fi
+if has bench_c3; then
+  timeout 900 python bench.py --workload c3 --steps 5 --warmup 3 > $O/${TAG}_bench_c3.json 2> $O/${TAG}_bench_c3.err
+  cut -c1-600 $O/${TAG}_bench_c3.json
+fi
+if has launches_c3; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+      --log-file $O/${TAG}_launches_c3.csv python tools/ncu_step.py --workload c3 > $O/${TAG}_launches_c3.log 2>&1
+  python tools/summarize_launches.py $O/${TAG}_launches_c3.csv > $O/${TAG}_launches_c3.md 2>&1
+  cat $O/${TAG}_launches_c3.md
+fi
+if has full_c3; then
+  timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o $O/${TAG}_full_c3 \
+      -k regex:'rowgemm|wgrad' -c 12 python tools/ncu_step.py --workload c3 > $O/${TAG}_full_c3.log 2>&1
+  tail -2 $O/${TAG}_full_c3.log
+fi
+ls -la $O | tail -20
