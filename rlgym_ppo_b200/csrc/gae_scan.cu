@@ -302,37 +302,44 @@ struct StepMaps {
     double gamma, gl64;   // gl64 = (double)gl32
     float gl32, stdv;
     bool has_std;
-    // multipliers of local step j (torch_functions.py:59-60, 69, 72).  Flags that are exactly 0 or 1 -- what the
-    // collector produces -- take a select instead of three f64 multiplies and two conversions; anything else is
-    // evaluated as written in the reference.
+    // multipliers of local step j exactly as the reference writes them (torch_functions.py:59-60, 69, 72): the generic
+    // path, for flags that are not exactly +0 / 1 and for the ragged tile
     __device__ __forceinline__ void mults(int j, double& aA, double& aR) const {
         const float dj = d[j];
         const double trj = TRUNC64 ? static_cast<const double*>(t)[j] : (double)static_cast<const float*>(t)[j];
-        if ((dj == 0.f || dj == 1.f) && (trj == 0.0 || trj == 1.0)) {
-            const bool live = dj == 0.f && trj == 0.0;
-            aA = live ? gl64 : 0.0;
-            aR = live ? gamma : 0.0;
-        } else {
-            const float nd = __fsub_rn(1.0f, dj);                            // :59
-            const double nt = 1.0 - trj;                                     // :60
-            aA = (double)__fmul_rn(gl32, nd) * nt;                           // :72
-            aR = gamma * (double)nd * nt;                                    // :69
-        }
+        const float nd = __fsub_rn(1.0f, dj);                                // :59
+        const double nt = 1.0 - trj;                                         // :60
+        aA = (double)__fmul_rn(gl32, nd) * nt;                               // :72
+        aR = gamma * (double)nd * nt;                                        // :69
     }
-    // delta_j (f32, the reference's NumPy>=2 rounding points, :62-68)
-    __device__ __forceinline__ float delta(int j) const {
-        const float rj = r[j];
-        const float nd = __fsub_rn(1.0f, d[j]);                              // :59
+    // delta (f32, the reference's NumPy>=2 rounding points, :62-68) from the step's r, done, V and V of the next row
+    __device__ __forceinline__ float delta_of(float rj, float dj, float vj, float vnext) const {
+        const float nd = __fsub_rn(1.0f, dj);                                // :59
         float nr = rj;
         if (has_std) {                                                       // :62-65
             nr = __fdiv_rn(rj, stdv);
             nr = fminf(fmaxf(nr, -10.f), 10.f);
         }
-        const float gv = (float)(gamma * (double)v[j + 1]);
+        const float gv = (float)(gamma * (double)vnext);
         const float pred = __fadd_rn(nr, __fmul_rn(gv, nd));                 // :67
-        return __fsub_rn(pred, v[j]);                                        // :68
+        return __fsub_rn(pred, vj);                                          // :68
     }
+    __device__ __forceinline__ float delta(int j) const { return delta_of(r[j], d[j], v[j], v[j + 1]); }
 };
+
+// 8 consecutive floats of a thread (32 bytes, 16-byte aligned) as two 128-bit shared-memory accesses.  Scalar accesses
+// at this stride put the 32 lanes of a warp on 4 banks (8-way conflict: ncu showed 84 % of v2's shared-memory
+// wavefronts were conflict replays and the L1/shared pipe 96 % busy); 128-bit accesses at a 32-byte stride are 2-way.
+__device__ __forceinline__ void lds8(const float* p, float (&x)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void sts8(float* p, const float (&x)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
 
 template <bool TRUNC64, bool STORE>
 __global__ void __launch_bounds__(kT2, 4)
@@ -365,8 +372,9 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
     const int chunk = n_tiles - 1 - tile;
     const int64_t base0 = (int64_t)chunk * kTile2;
     const int cnt = (int)((n - base0) < (int64_t)kTile2 ? (n - base0) : (int64_t)kTile2);
+    const bool full = cnt == kTile2;
     constexpr uint32_t kTB = TRUNC64 ? 8u : 4u;
-    if (cnt == kTile2) {
+    if (full) {
         if (tid == 0) {
             const uint32_t total = 3u * kTile2 * 4u + kTile2 * kTB;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&s_bar)), "r"(total)
@@ -389,7 +397,7 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
                 : "memory");
         }
     } else {
-        // ragged tile (the left end of the rollout): plain loads, identity maps past the end
+        // ragged tile (the right end of the rollout, tile 0): plain loads; steps past the end are identity maps
         for (int j = tid; j < kTile2; j += kT2) {
             const bool okj = j < cnt;
             s_r[j] = okj ? __ldg(rew + base0 + j) : 0.f;
@@ -410,18 +418,75 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
 
     // ---- phase A: thread aggregate over its 8 consecutive steps, warp scan, block scan ----
     const int j0 = tid * kI2;
-    Aff agg = aff_identity();
+    // Flags first.  `live` bit i: step j0+i has done == +0 and truncated == +0 (the recurrence continues through it);
+    // `fast`: every flag of this thread is exactly +0 or 1 -- what the collector produces -- so a multiplier is either
+    // 0 or the constant gamma*lambda / gamma and needs no arithmetic.  Anything else (and the ragged tile) takes the
+    // generic path, which evaluates the reference's expressions as written.
+    uint32_t live = 0;
+    bool fast = full;
+    float dflt[kI2];
+    lds8(s_d + j0, dflt);
+    {
+        uint32_t dz = 0, bad = 0;
 #pragma unroll
-    for (int i = kI2 - 1; i >= 0; --i)
-        if (j0 + i < cnt) {
-            Aff f;
-            sm.mults(j0 + i, f.aA, f.aR);
-            const float dl = sm.delta(j0 + i);
-            s_delta[j0 + i] = dl;          // read back by this same thread in phase B
-            f.bA = (double)dl;
-            f.bR = (double)s_r[j0 + i];
-            agg = compose(f, agg);
+        for (int i = 0; i < kI2; ++i) {
+            const uint32_t b = __float_as_uint(dflt[i]);
+            dz |= (b == 0u ? 1u : 0u) << i;
+            bad |= (b != 0u && b != 0x3F800000u) ? 1u : 0u;
         }
+        uint32_t tz = 0;
+        if (TRUNC64) {
+            const uint4* tp = reinterpret_cast<const uint4*>(static_cast<const double*>(s_t) + j0);
+#pragma unroll
+            for (int q = 0; q < kI2 / 2; ++q) {
+                const uint4 w = tp[q];   // two doubles: (x = lo0, y = hi0, z = lo1, w = hi1)
+                tz |= ((w.x | w.y) == 0u ? 1u : 0u) << (2 * q);
+                tz |= ((w.z | w.w) == 0u ? 1u : 0u) << (2 * q + 1);
+                bad |= ((w.x | w.y) != 0u && !(w.x == 0u && w.y == 0x3FF00000u)) ? 1u : 0u;
+                bad |= ((w.z | w.w) != 0u && !(w.z == 0u && w.w == 0x3FF00000u)) ? 1u : 0u;
+            }
+        } else {
+            float tf[kI2];
+            lds8(static_cast<const float*>(s_t) + j0, tf);
+#pragma unroll
+            for (int i = 0; i < kI2; ++i) {
+                const uint32_t b = __float_as_uint(tf[i]);
+                tz |= (b == 0u ? 1u : 0u) << i;
+                bad |= (b != 0u && b != 0x3F800000u) ? 1u : 0u;
+            }
+        }
+        live = dz & tz;
+        fast = fast && bad == 0u;
+    }
+    Aff agg = aff_identity();
+    if (fast) {
+        float rr[kI2], vv[kI2], dl[kI2];
+        lds8(s_r + j0, rr);
+        lds8(s_v + j0, vv);
+        float vnext = s_v[j0 + kI2];
+#pragma unroll
+        for (int i = kI2 - 1; i >= 0; --i) {
+            dl[i] = sm.delta_of(rr[i], dflt[i], vv[i], vnext);
+            vnext = vv[i];
+            const bool lv = (live >> i) & 1u;
+            const double aA = lv ? sm.gl64 : 0.0;
+            const double aR = lv ? gamma : 0.0;
+            agg = Aff{aA * agg.aA, fma(aA, agg.bA, (double)dl[i]), aR * agg.aR, fma(aR, agg.bR, (double)rr[i])};
+        }
+        sts8(s_delta + j0, dl);            // read back by this same thread in phase B
+    } else {
+#pragma unroll 1
+        for (int i = kI2 - 1; i >= 0; --i)
+            if (j0 + i < cnt) {
+                Aff f;
+                sm.mults(j0 + i, f.aA, f.aR);
+                const float dl = sm.delta(j0 + i);
+                s_delta[j0 + i] = dl;
+                f.bA = (double)dl;
+                f.bR = (double)s_r[j0 + i];
+                agg = compose(f, agg);
+            }
+    }
     const Aff incl_w = warp_suffix_scan(agg, lane);
     Aff excl = shfl_down(incl_w, 1);
     if (lane == 31) excl = aff_identity();
@@ -514,27 +579,29 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
     const double carryA = fma(right.aA, cA, right.bA);
     const double carryR = fma(right.aR, cR, right.bR);
 
-    // ---- phase B: values just right of this thread's steps, then the per-step maps again (from shared memory) ----
+    // ---- phase B: values just right of this thread's steps, then the per-step maps again ----
     const Aff wr = Aff{s_warp[warp][0], s_warp[warp][1], s_warp[warp][2], s_warp[warp][3]};
     const Aff e = compose(excl, wr);
     double xA = fma(e.aA, carryA, e.bA);
     double xR = fma(e.aR, carryR, e.bR);
-    float oa[kI2], ov[kI2], orr[kI2];
     const int64_t gbase = base0 + j0;
+    if (fast) {
+        float dl[kI2], rr[kI2], vv[kI2];
+        lds8(s_delta + j0, dl);
+        lds8(s_r + j0, rr);
+        lds8(s_v + j0, vv);
+        const bool head = ret_head != nullptr && gbase < n_head;
+        float oa[kI2], ov[kI2], orr[kI2];
 #pragma unroll
-    for (int i = kI2 - 1; i >= 0; --i) {
-        if (j0 + i < cnt) {
-            double aA, aR;
-            sm.mults(j0 + i, aA, aR);
-            xA = fma(aA, xA, (double)s_delta[j0 + i]);
-            xR = fma(aR, xR, (double)s_r[j0 + i]);
-            if (ret_head != nullptr && gbase + i < n_head) ret_head[gbase + i] = xR;
+        for (int i = kI2 - 1; i >= 0; --i) {
+            const bool lv = (live >> i) & 1u;
+            xA = fma(lv ? sm.gl64 : 0.0, xA, (double)dl[i]);
+            xR = fma(lv ? gamma : 0.0, xR, (double)rr[i]);
+            if (head && gbase + i < n_head) ret_head[gbase + i] = xR;
+            oa[i] = (float)xA;                              // :76
+            ov[i] = (float)((double)vv[i] + xA);            // :77
+            orr[i] = (float)xR;
         }
-        oa[i] = (float)xA;                              // :76
-        ov[i] = (float)((double)s_v[j0 + i] + xA);      // :77
-        orr[i] = (float)xR;
-    }
-    if (cnt == kTile2) {
         float4* pa = reinterpret_cast<float4*>(adv + gbase);
         float4* pv = reinterpret_cast<float4*>(vt + gbase);
         float4* pr = reinterpret_cast<float4*>(ret + gbase);
@@ -545,13 +612,19 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
         pr[0] = make_float4(orr[0], orr[1], orr[2], orr[3]);
         pr[1] = make_float4(orr[4], orr[5], orr[6], orr[7]);
     } else {
-#pragma unroll
-        for (int i = 0; i < kI2; ++i)
+#pragma unroll 1
+        for (int i = kI2 - 1; i >= 0; --i) {
             if (j0 + i < cnt) {
-                adv[gbase + i] = oa[i];
-                vt[gbase + i] = ov[i];
-                ret[gbase + i] = orr[i];
+                double aA, aR;
+                sm.mults(j0 + i, aA, aR);
+                xA = fma(aA, xA, (double)s_delta[j0 + i]);
+                xR = fma(aR, xR, (double)s_r[j0 + i]);
+                if (ret_head != nullptr && gbase + i < n_head) ret_head[gbase + i] = xR;
+                adv[gbase + i] = (float)xA;                              // :76
+                vt[gbase + i] = (float)((double)s_v[j0 + i] + xA);       // :77
+                ret[gbase + i] = (float)xR;
             }
+        }
     }
 }
 

@@ -85,6 +85,32 @@ def test_gae_vs_oracle_sizes(ops, n, p_done):
         assert (got != want).mean() < 1e-3, (name, "bit mismatch rate", float((got != want).mean()))
 
 
+@pytest.mark.parametrize("trunc_dtype", [np.float64, np.float32])
+def test_gae_fractional_and_negative_zero_flags(ops, trunc_dtype):
+    """Flags that are not exactly +0 / 1 (fractional, -0.0, 2.0) leave the staged kernel's 0/1 fast path and must be
+    evaluated as the reference writes them (torch_functions.py:59-60): aligned full tiles, mixed with ordinary steps."""
+    rng = np.random.RandomState(11)
+    n = 3 * 2048 + 77
+    rew = (rng.randn(n) * 0.1).astype(np.float32)
+    done = (rng.rand(n) < 0.01).astype(np.float32)
+    trunc = ((rng.rand(n) < 0.005) * (1 - done)).astype(trunc_dtype)
+    odd = rng.choice(n, 64, replace=False)
+    done[odd[:16]] = 0.5
+    done[odd[16:24]] = -0.0
+    done[odd[24:32]] = 2.0
+    trunc[odd[32:48]] = 0.25
+    trunc[odd[48:56]] = -0.0
+    trunc[odd[56:]] = 1.5
+    val = rng.randn(n + 1).astype(np.float32)
+    for std in (np.float32(0.7), None):
+        vt0, adv0, ret0 = O.gae_nep50_c(rew, done, trunc.astype(np.float64), val, 0.99, 0.95, std)
+        vt, adv, ret, _ = _run_gae(ops, rew, done, trunc, val, 0.99, 0.95, std)
+        for name, got, want in (("adv", adv, adv0), ("vt", vt, vt0), ("ret", ret, ret0.astype(np.float32))):
+            err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+            assert err.max() <= 1e-5, (name, float(err.max()))
+            assert (got != want).mean() < 1e-3, (name, "bit mismatch rate", float((got != want).mean()))
+
+
 def test_gae_unaligned_views_and_carry(ops):
     """Misaligned pointers take the scalar path; carry_in + chunk summaries reproduce the unsharded scan."""
     rng = np.random.RandomState(3)

@@ -10,6 +10,15 @@ O=gpurun_out
 mkdir -p $O
 has() { [[ " $WHAT " == *" $1 "* ]]; }
 
+if has gae; then
+  timeout 600 python -m pytest tests -m gpu -x -q -k gae > $O/${TAG}_pytest_gae.log 2>&1
+  tail -3 $O/${TAG}_pytest_gae.log
+  timeout 600 python tools/gae_sweep.py --min-log2 22 --max-log2 28 --check > $O/${TAG}_gae_sweep.jsonl 2> $O/${TAG}_gae_sweep.err
+  cut -c1-200 $O/${TAG}_gae_sweep.jsonl
+  timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o $O/${TAG}_full_gae \
+      python tools/ncu_step.py --no-step --gae-log2 26 > $O/${TAG}_full_gae.log 2>&1
+  tail -2 $O/${TAG}_full_gae.log
+fi
 if has tests; then
   timeout 900 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest_gpu.log 2>&1
   tail -3 $O/${TAG}_pytest_gpu.log
