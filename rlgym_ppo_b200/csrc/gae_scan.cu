@@ -11,6 +11,8 @@
 // reference's f64 accumulation; delta is formed with the reference's f32 rounding points.
 //
 // HBM traffic: reads r, done, trunc, V (16 B/step with f32 flags), writes adv, vtarget, ret (12 B/step).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -628,13 +630,445 @@ gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v3: persistent, software-pipelined scan.
+//
+// ncu on v2 (one tile per CTA, 4 CTAs/SM, 2^26 steps): a tile's lifetime was 11.5 us, of which 22 % waiting for its own
+// ticket + loads, 33 % in the look-back (store -> L2 -> poll round trips, 256-thread shuffle scans, block barriers) and
+// only 37 % in the two compute phases -- latency-bound at 40 % of the DRAM bandwidth however the phases were trimmed.
+// Here a CTA lives for the whole launch and overlaps the three latencies with compute:
+//   * 3 CTAs per SM; CTA b takes tiles b, b+G, b+2G, ... (tile 0 = the END of the rollout, 1024 steps per tile).
+//   * warp 8 (one thread): producer.  Keeps a 3-stage ring of {r, done, V(+halo), truncated} tiles filled with bulk
+//     async copies (mbarrier full/empty per stage), so tile k+1 and k+2 are in flight while tile k is scanned.
+//   * warps 0-7: compute.  A(k): flags -> delta -> thread/warp/block aggregates, everything phase B needs moved to
+//     REGISTERS (r, V, delta, live mask, the thread's exclusive map) and the stage handed back at once.
+//     B(k-1) runs AFTER A(k): by then the look-back of tile k-1 has had a whole A phase to finish.
+//   * warp 9: look-back.  Publishes the tile aggregate, walks the predecessors' records 32 at a time (strong relaxed
+//     vector loads, sentinel-initialised records as in v2), stops at the first inclusive record -- at the latest at this
+//     CTA's own previous tile, G tiles back, whose inclusive map it still holds in registers, so a CTA never depends on
+//     another CTA's look-back, only on aggregates -- publishes the inclusive record and hands the carry to the compute
+//     warps through shared memory.
+// Co-residency: the grid is min(tiles, 3 x SMs) CTAs; a CTA waits only for aggregates of lower-numbered tiles, which
+// lower-numbered CTAs (scheduled first) or earlier iterations produce, so a partially resident grid still progresses.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kC3 = 256;                 // compute threads
+constexpr int kT3 = kC3 + 32;            // + look-back warp
+constexpr int kI3 = 4;
+constexpr int kTile3 = kC3 * kI3;        // 1024 steps
+constexpr int kW3 = kC3 / 32;
+constexpr int kStages3 = 3;
+constexpr int kCtasPerSm3 = 3;
+constexpr uint32_t kVBytes3 = kTile3 * 4u + 16u;            // V tile + 4-float halo (only the first is used)
+constexpr uint32_t kOffD3 = kTile3 * 4u;
+constexpr uint32_t kOffV3 = 2u * kTile3 * 4u;
+constexpr uint32_t kOffT3 = kOffV3 + kVBytes3;
+__host__ __device__ constexpr uint32_t stage_bytes3(bool t64) { return kOffT3 + kTile3 * (t64 ? 8u : 4u); }
+
+__device__ __forceinline__ void mbar_init3(uint64_t* b, uint32_t cnt) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(b)), "r"(cnt) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive3(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx3(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(b)), "r"(bytes) : "memory");
+}
+// Waiters back off with nanosleep: the event trace of the first version showed the look-back warp taking 11 us for a
+// 300-instruction shuffle scan -- the scheduler kept issuing the 24 hot-spinning compute warps of the SM instead.
+__device__ __forceinline__ void mbar_wait3(uint64_t* b, uint32_t parity) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_addr_u32(b)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        __nanosleep(100);
+    }
+}
+
+// what phase B needs of a tile, per thread, in registers
+struct Pending3 {
+    float r[kI3], v[kI3], dl[kI3];
+    Aff e;            // map of everything right of this thread's steps inside the tile
+    uint32_t live;    // bit i: step i continues the recurrence (fast threads)
+    bool fast;        // flags all exactly 0 / 1 and the tile is a full, staged one
+};
+
+template <bool TRUNC64, bool STORE>
+__global__ void __launch_bounds__(kT3, kCtasPerSm3)
+gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, const void* __restrict__ trunc,
+                 const float* __restrict__ val, int64_t n, double gamma, float gl32,
+                 const float* __restrict__ ret_std, float* __restrict__ adv, float* __restrict__ vt,
+                 float* __restrict__ ret, double* __restrict__ ret_head, int64_t n_head,
+                 const double* __restrict__ carry_in, double* __restrict__ summary_out, Workspace ws, int n_tiles,
+                 unsigned long long* __restrict__ trace) {
+    extern __shared__ __align__(128) uint8_t sm3[];
+    __shared__ uint64_t s_full[kStages3], s_aggr[2], s_carr[2];
+    __shared__ double s_wagg[2][kW3][4];
+    __shared__ double s_agg[2][4];
+    __shared__ double s_carry[2][2];
+
+    // debug (RLPPO_GAE_TRACE=<file>): globaltimer stamps of three CTAs, [cta slot][tile k < 128][event]
+    const int tr_slot = trace == nullptr ? -1
+                        : (blockIdx.x == 0 ? 0 : ((int)blockIdx.x == (int)gridDim.x / 2 ? 1 : (blockIdx.x == gridDim.x - 1 ? 2 : -1)));
+    auto stamp = [&](int k, int ev) {
+        if (tr_slot >= 0 && k < 128) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            trace[(tr_slot * 128 + k) * 8 + ev] = now;
+        }
+    };
+    constexpr uint32_t kStage = stage_bytes3(TRUNC64);
+    constexpr uint32_t kTB = TRUNC64 ? 8u : 4u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    const int K = (n_tiles - (int)blockIdx.x + G - 1) / G;      // tiles of this CTA (grid <= n_tiles)
+    if (tid == 0) {
+        for (int i = 0; i < kStages3; ++i) {
+            mbar_init3(&s_full[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init3(&s_aggr[i], 1);
+            mbar_init3(&s_carr[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // a tile is staged by bulk copies iff all of its 1024 steps and the 4-float V halo exist
+    auto base_of = [&](int k) { return (int64_t)(n_tiles - 1 - ((int)blockIdx.x + k * G)) * kTile3; };
+    auto staged = [&](int64_t base0) { return base0 + kTile3 + 4 <= n + 1; };
+
+    // stage s takes tile k: four bulk copies (one thread); a ragged tile is not staged, its barrier completes at once
+    auto produce = [&](int k) {
+        const int s = k % kStages3;
+        const int64_t base0 = base_of(k);
+        if (staged(base0)) {
+            uint8_t* st = sm3 + s * kStage;
+            mbar_expect_tx3(&s_full[s], 2u * kTile3 * 4u + kVBytes3 + kTile3 * kTB);
+            bulk_g2s(st, rew + base0, kTile3 * 4u, &s_full[s]);
+            bulk_g2s(st + kOffD3, done + base0, kTile3 * 4u, &s_full[s]);
+            bulk_g2s(st + kOffV3, val + base0, kVBytes3, &s_full[s]);
+            bulk_g2s(st + kOffT3, static_cast<const uint8_t*>(trunc) + base0 * kTB, kTile3 * kTB, &s_full[s]);
+        } else {
+            mbar_arrive3(&s_full[s]);
+        }
+    };
+    if (warp == kW3) {
+        // ===================== look-back =====================
+        // Two-level, chain-free.  CTAs form groups of 32 consecutive block ids; the last CTA of a group also publishes
+        // the group's aggregate (its own tile's map composed with its 31 peers') in the second record array.  The map of
+        // everything right of tile t = bid + k*G, nearest first:
+        //   S1  aggregates of the lower peers of this iteration          tiles t-1 .. t-l             (l = bid % 32)
+        //   S2  group aggregates of the lower groups of this iteration   groups g-1 .. 0              (g = bid / 32)
+        //   S3  group aggregates of the higher groups of iteration k-1   groups NG-1 .. g+1
+        //   S4  aggregates of the higher peers of iteration k-1          block ids group end .. bid+1
+        //   then this CTA's own previous tile t-G, whose INCLUSIVE map is still in registers.
+        // At most 31 + NG-1 records (<= 64: two per lane), all of them published right after a phase A -- no record
+        // depends on another CTA's look-back, so nothing propagates serially along the rollout.  (The first version
+        // walked 32 predecessors per round until it met an inclusive record: the inclusive frontier advanced 32 tiles
+        // per L2 round trip, 2^26 steps took 2048 round trips = 757 us whatever the memory system did.)
+        const double cA = carry_in ? carry_in[0] : 0.0;
+        const double cR = carry_in ? carry_in[1] : 0.0;
+        const int bid = (int)blockIdx.x;
+        const int NG = (G + 31) >> 5;
+        const int g = bid >> 5, l = bid & 31;
+        const int gend = ((32 * g + 31 < G - 1) ? 32 * g + 31 : G - 1) - 32 * g;   // local index of the group's last CTA
+        const bool group_last = l == gend;
+        double* const gagg = ws.incl;          // second record array: group aggregates, slot = tile id of the group's first tile
+        Aff prev_incl = aff_identity();
+        for (int k = 0; k < K; ++k) {
+            const int t = bid + k * G;
+            mbar_wait3(&s_aggr[k & 1], (k >> 1) & 1);
+            const Aff tile_agg = Aff{s_agg[k & 1][0], s_agg[k & 1][1], s_agg[k & 1][2], s_agg[k & 1][3]};
+            if (lane == 0) stamp(k, 4);
+            // the record at position p of the nearest-first list (nullptr: none)
+            auto rec_at = [&](int p) -> const double* {
+                if (p < l) return ws.agg + (size_t)(t - 1 - p) * 4;
+                p -= l;
+                if (p < g) return gagg + (size_t)(k * G + 32 * (g - 1 - p)) * 4;
+                p -= g;
+                if (k == 0) return nullptr;
+                if (p < NG - 1 - g) return gagg + (size_t)((k - 1) * G + 32 * (NG - 1 - p)) * 4;
+                p -= NG - 1 - g;
+                if (p < gend - l) return ws.agg + (size_t)((k - 1) * G + 32 * g + gend - p) * 4;
+                return nullptr;
+            };
+            // lane i takes positions 2i and 2i+1 (adjacent: one local compose, then ONE 5-round tree over the lanes)
+            const double* pa = rec_at(2 * lane);
+            const double* pb = rec_at(2 * lane + 1);
+            Aff ma = aff_identity(), mb = aff_identity();
+            bool need_a = pa != nullptr, need_b = pb != nullptr;
+            const long long t0 = clock64();
+            if (group_last) {
+                // The group aggregate must not wait for anything but the peers' aggregates (positions 0 .. l-1): publishing
+                // it only after the group records of S2/S3 had arrived chained the groups serially, 14 hops per iteration.
+                // Warp-uniform polling loops (every lane iterates until the last record is in): lanes that leave a
+                // divergent spin loop one by one stayed diverged through the shuffle scans below -- the event trace
+                // showed 11 us from "all records arrived" to "carry handed over" for ~400 instructions.
+                Aff s1 = aff_identity();
+                const double* ps = lane < l ? ws.agg + (size_t)(t - 1 - lane) * 4 : nullptr;
+                bool need_s = ps != nullptr;
+                for (;;) {
+                    if (need_s && rec_load(ps, s1)) need_s = false;
+                    if (!__any_sync(0xffffffffu, need_s)) break;
+                    if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
+                }
+                if (ps == nullptr) s1 = aff_identity();
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {   // adjacent pairs first: the maps do not commute
+                    const Aff y = shfl_down(s1, off);
+                    s1 = compose(s1, y);                       // lanes past the end pull in garbage; lane 0 is exact
+                }
+                if (lane == 0) rec_store(gagg + (size_t)(k * G + 32 * g) * 4, compose(tile_agg, s1));
+            }
+            for (;;) {
+                Aff xa, xb;
+                bool oka = false, okb = false;
+                if (need_a) oka = rec_load(pa, xa);
+                if (need_b) okb = rec_load(pb, xb);
+                if (oka) {
+                    ma = xa;
+                    need_a = false;
+                }
+                if (okb) {
+                    mb = xb;
+                    need_b = false;
+                }
+                if (!__any_sync(0xffffffffu, need_a || need_b)) break;
+                if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
+            }
+            if (lane == 0) stamp(k, 5);
+            Aff right = compose(ma, mb);
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {   // adjacent pairs first: the maps do not commute
+                const Aff y = shfl_down(right, off);
+                right = compose(right, y);                     // exact on lane 0 (shfl_down past the end returns own value)
+            }
+            if (k > 0) right = compose(right, prev_incl);      // lane 0 is the only consumer from here on
+            const Aff incl = compose(tile_agg, right);
+            prev_incl = incl;
+            if (lane == 0) {
+                s_carry[k & 1][0] = fma(right.aA, cA, right.bA);
+                s_carry[k & 1][1] = fma(right.aR, cR, right.bR);
+                if (summary_out != nullptr && t == n_tiles - 1) {
+                    summary_out[0] = incl.aA; summary_out[1] = incl.bA;
+                    summary_out[2] = incl.aR; summary_out[3] = incl.bR;
+                }
+                mbar_arrive3(&s_carr[k & 1]);       // release: the carry stores above are visible to the waiters
+                stamp(k, 6);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ===================== compute warps =====================
+    StepMaps<TRUNC64> sm;
+    sm.gamma = gamma; sm.gl32 = gl32; sm.gl64 = (double)gl32;
+    sm.has_std = ret_std != nullptr;
+    sm.stdv = sm.has_std ? __ldg(ret_std) : 1.f;
+    const double g4A = (sm.gl64 * sm.gl64) * (sm.gl64 * sm.gl64);      // multiplier of 4 live steps
+    const double g4R = (gamma * gamma) * (gamma * gamma);
+    const int j0 = tid * kI3;
+
+    // ---- phase A of tile k: everything up to the tile aggregate; the inputs phase B needs end up in `P` ----
+    auto phaseA = [&](int k, Pending3& P) {
+        const int s = k % kStages3;
+        const int64_t base0 = base_of(k);
+        const bool tile_staged = staged(base0);
+        const uint8_t* st = sm3 + s * kStage;
+        mbar_wait3(&s_full[s], (k / kStages3) & 1);
+        if (tid == 0) stamp(k, 0);
+        Aff agg;
+        P.fast = tile_staged;
+        P.live = 0;
+        if (tile_staged) {
+            const float4 r4 = *reinterpret_cast<const float4*>(st + (size_t)j0 * 4);
+            const float4 d4 = *reinterpret_cast<const float4*>(st + kOffD3 + (size_t)j0 * 4);
+            const float4 v4 = *reinterpret_cast<const float4*>(st + kOffV3 + (size_t)j0 * 4);
+            const float vh = *reinterpret_cast<const float*>(st + kOffV3 + (size_t)(j0 + kI3) * 4);
+            double tt[kI3];
+            if (TRUNC64) {
+                const double2 t0 = *reinterpret_cast<const double2*>(st + kOffT3 + (size_t)j0 * 8);
+                const double2 t1 = *reinterpret_cast<const double2*>(st + kOffT3 + (size_t)j0 * 8 + 16);
+                tt[0] = t0.x; tt[1] = t0.y; tt[2] = t1.x; tt[3] = t1.y;
+            } else {
+                const float4 t4 = *reinterpret_cast<const float4*>(st + kOffT3 + (size_t)j0 * 4);
+                tt[0] = t4.x; tt[1] = t4.y; tt[2] = t4.z; tt[3] = t4.w;
+            }
+            const float dd[kI3] = {d4.x, d4.y, d4.z, d4.w};
+            const float vn[kI3 + 1] = {v4.x, v4.y, v4.z, v4.w, vh};
+            P.r[0] = r4.x; P.r[1] = r4.y; P.r[2] = r4.z; P.r[3] = r4.w;
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < kI3; ++i) {
+                P.v[i] = vn[i];
+                const bool dz = dd[i] == 0.f, tz = tt[i] == 0.0;
+                ok = ok && (dz || dd[i] == 1.f) && (tz || tt[i] == 1.0);
+                P.live |= (dz && tz ? 1u : 0u) << i;
+                P.dl[i] = sm.delta_of(P.r[i], dd[i], vn[i], vn[i + 1]);
+            }
+            P.fast = ok;
+            if (ok) {
+                // multipliers are 0 or a constant: only the additive parts need arithmetic
+                double bA = 0.0, bR = 0.0;
+#pragma unroll
+                for (int i = kI3 - 1; i >= 0; --i) {
+                    const bool lv = (P.live >> i) & 1u;
+                    bA = fma(lv ? sm.gl64 : 0.0, bA, (double)P.dl[i]);
+                    bR = fma(lv ? gamma : 0.0, bR, (double)P.r[i]);
+                }
+                const bool all = P.live == 0xFu;
+                agg = Aff{all ? g4A : 0.0, bA, all ? g4R : 0.0, bR};
+            } else {
+                agg = aff_identity();
+#pragma unroll
+                for (int i = kI3 - 1; i >= 0; --i) {
+                    const float nd = __fsub_rn(1.0f, dd[i]);                              // :59
+                    const double nt = 1.0 - tt[i];                                        // :60
+                    const Aff f = Aff{(double)__fmul_rn(gl32, nd) * nt, (double)P.dl[i],  // :72
+                                      gamma * (double)nd * nt, (double)P.r[i]};           // :69
+                    agg = compose(f, agg);
+                }
+            }
+        } else {
+            // ragged tile: bounds-checked global loads, the reference's expressions as written; steps past the end are
+            // identity maps so that the carry passes through them
+            const int cnt = (int)((n - base0) < (int64_t)kTile3 ? (n - base0) : (int64_t)kTile3);
+            sm.r = rew + base0; sm.d = done + base0; sm.v = val + base0;
+            sm.t = static_cast<const uint8_t*>(trunc) + base0 * kTB;
+            agg = aff_identity();
+#pragma unroll
+            for (int i = 0; i < kI3; ++i) P.r[i] = P.v[i] = P.dl[i] = 0.f;
+#pragma unroll
+            for (int i = kI3 - 1; i >= 0; --i)
+                if (j0 + i < cnt) {
+                    Aff f;
+                    sm.mults(j0 + i, f.aA, f.aR);
+                    P.r[i] = sm.r[j0 + i];
+                    P.v[i] = sm.v[j0 + i];
+                    P.dl[i] = sm.delta(j0 + i);
+                    f.bA = (double)P.dl[i];
+                    f.bR = (double)P.r[i];
+                    agg = compose(f, agg);
+                }
+        }
+        const Aff incl_w = warp_suffix_scan(agg, lane);
+        Aff excl = shfl_down(incl_w, 1);
+        if (lane == 31) excl = aff_identity();
+        double(*wagg)[4] = s_wagg[k & 1];
+        if (lane == 0) {
+            wagg[warp][0] = incl_w.aA; wagg[warp][1] = incl_w.bA;
+            wagg[warp][2] = incl_w.aR; wagg[warp][3] = incl_w.bR;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // every compute warp has read stage s into registers by now: refill it with the tile three ahead
+        if (tid == 0 && k + kStages3 < K) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
+            produce(k + kStages3);
+        }
+        // every warp scans the 8 warp aggregates itself (lanes 0-7): no second barrier
+        Aff w = aff_identity();
+        if (lane < kW3) w = Aff{wagg[lane][0], wagg[lane][1], wagg[lane][2], wagg[lane][3]};
+#pragma unroll
+        for (int off = 1; off < kW3; off <<= 1) {
+            const Aff y = shfl_down(w, off);
+            if (lane + off < kW3) w = compose(w, y);
+        }
+        // lane l < 8 now holds warps l..7; this warp's exclusive = lane warp+1 (identity for the last warp)
+        Aff we = shfl_idx(w, (warp + 1) & 31);
+        if (warp == kW3 - 1) we = aff_identity();
+        if (tid == 0) {
+            // published from here, not by the look-back warp: that one may still be busy with the previous tile
+            rec_store(ws.agg + (size_t)((int)blockIdx.x + k * G) * 4, w);
+            s_agg[k & 1][0] = w.aA; s_agg[k & 1][1] = w.bA; s_agg[k & 1][2] = w.aR; s_agg[k & 1][3] = w.bR;
+            mbar_arrive3(&s_aggr[k & 1]);
+            stamp(k, 1);
+        }
+        P.e = compose(excl, we);
+    };
+
+    // ---- phase B of tile k: apply the carry, write the outputs ----
+    auto phaseB = [&](int k, const Pending3& P) {
+        const int64_t base0 = base_of(k);
+        mbar_wait3(&s_carr[k & 1], (k >> 1) & 1);     // also the flow control that keeps s_agg / s_aggr two tiles deep
+        if (tid == 0) stamp(k, 2);
+        if (!STORE) return;
+        const double carryA = s_carry[k & 1][0], carryR = s_carry[k & 1][1];
+        double xA = fma(P.e.aA, carryA, P.e.bA);
+        double xR = fma(P.e.aR, carryR, P.e.bR);
+        const int64_t gbase = base0 + j0;
+        const bool head = ret_head != nullptr && gbase < n_head;
+        float oa[kI3], ov[kI3], orr[kI3];
+        if (P.fast) {
+#pragma unroll
+            for (int i = kI3 - 1; i >= 0; --i) {
+                const bool lv = (P.live >> i) & 1u;
+                xA = fma(lv ? sm.gl64 : 0.0, xA, (double)P.dl[i]);
+                xR = fma(lv ? gamma : 0.0, xR, (double)P.r[i]);
+                if (head && gbase + i < n_head) ret_head[gbase + i] = xR;
+                oa[i] = (float)xA;                              // :76
+                ov[i] = (float)((double)P.v[i] + xA);           // :77
+                orr[i] = (float)xR;
+            }
+            *reinterpret_cast<float4*>(adv + gbase) = make_float4(oa[0], oa[1], oa[2], oa[3]);
+            *reinterpret_cast<float4*>(vt + gbase) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            *reinterpret_cast<float4*>(ret + gbase) = make_float4(orr[0], orr[1], orr[2], orr[3]);
+        } else {
+            // generic flags / ragged tile: the multipliers again, from global memory (rare)
+            const int cnt = (int)((n - base0) < (int64_t)kTile3 ? (n - base0) : (int64_t)kTile3);
+            StepMaps<TRUNC64> g = sm;
+            g.r = rew + base0; g.d = done + base0; g.v = val + base0;
+            g.t = static_cast<const uint8_t*>(trunc) + base0 * kTB;
+#pragma unroll
+            for (int i = kI3 - 1; i >= 0; --i)
+                if (j0 + i < cnt) {
+                    double aA, aR;
+                    g.mults(j0 + i, aA, aR);
+                    xA = fma(aA, xA, (double)P.dl[i]);
+                    xR = fma(aR, xR, (double)P.r[i]);
+                    if (head && gbase + i < n_head) ret_head[gbase + i] = xR;
+                    adv[gbase + i] = (float)xA;
+                    vt[gbase + i] = (float)((double)P.v[i] + xA);
+                    ret[gbase + i] = (float)xR;
+                }
+        }
+        if (tid == 0) stamp(k, 3);
+    };
+
+    // A(k) runs one tile ahead of B(k-1); two register sets alternate (unrolled by two: no dynamic indexing)
+    if (tid == 0)
+        for (int kk = 0; kk < kStages3 && kk < K; ++kk) produce(kk);
+    Pending3 P0, P1;
+    phaseA(0, P0);
+    int k = 1;
+    for (; k + 1 < K; k += 2) {
+        phaseA(k, P1);
+        phaseB(k - 1, P0);
+        phaseA(k + 1, P0);
+        phaseB(k, P1);
+    }
+    if (k < K) {
+        phaseA(k, P1);
+        phaseB(k - 1, P0);
+        phaseB(k, P1);
+    } else {
+        phaseB(k - 1, P0);
+    }
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
     size_t status_off, agg_off, incl_off, total, clear_bytes;
 };
 WsLayout ws_layout(int64_t n) {
-    const size_t n_tiles = (size_t)((n + kTile - 1) / kTile);
+    const size_t n_tiles = (size_t)((n + kTile3 - 1) / kTile3);   // the finest tiling any of the kernels uses
     WsLayout L;
     L.status_off = 16;
     L.clear_bytes = align_up(16 + n_tiles * sizeof(int), 16);
@@ -669,7 +1103,57 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
     gae_scan_kernel<T64, V, STORE><<<n_tiles, kThreads, 0, s>>>(rew, done, trunc, values, n, gamma, gl32, \
                                                                 ret_std, adv, vtarget, ret, ret_head64,  \
                                                                 n_head, carry_in, summary_out, ws, n_tiles)
-    if (vec) {
+    static const bool use_v2 = getenv("RLPPO_GAE_V2") != nullptr;     // A/B switch for the previous staged kernel
+    if (vec && !use_v2) {
+        // persistent pipelined kernel (v3): 1024-step tiles, records pre-set to the all-ones sentinel
+        const int n_tiles3 = (int)((n + kTile3 - 1) / kTile3);
+        const size_t smem = (size_t)kStages3 * stage_bytes3(trunc_is_f64 != 0);
+        RLPPO_CUDA(cudaMemsetAsync(base + L.agg_off, 0xFF, L.total - L.agg_off, s));
+        // debug trace (see the kernel): RLPPO_GAE_TRACE=<file> dumps the stamps of this launch after a synchronise
+        static const char* trace_env = getenv("RLPPO_GAE_TRACE");
+        static const char* trace_path = (trace_env != nullptr && trace_env[0] != 0) ? trace_env : nullptr;
+        static unsigned long long* trace_dev = nullptr;
+        constexpr size_t kTraceWords = 3 * 128 * 8;
+        if (trace_path != nullptr) {
+            if (trace_dev == nullptr) RLPPO_CUDA(cudaMalloc(&trace_dev, kTraceWords * 8));
+            RLPPO_CUDA(cudaMemsetAsync(trace_dev, 0, kTraceWords * 8, s));
+        }
+        static bool configured3[2] = {false, false};
+        static int resident3[2] = {0, 0};
+        auto launch3 = [&](auto kfn, int which) -> cudaError_t {
+            if (!configured3[which]) {
+                cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)(kStages3 * stage_bytes3(true)));
+                if (e != cudaSuccess) return e;
+                // every CTA of the grid must be able to be resident at once (see the kernel's header comment)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident3[which], kfn, kT3,
+                                                                  kStages3 * stage_bytes3(true));
+                if (e != cudaSuccess) return e;
+                if (resident3[which] < 1) return cudaErrorLaunchOutOfResources;
+                configured3[which] = true;
+            }
+            const int cap = resident3[which] * rlppo::num_sms();
+            const int grid = n_tiles3 < cap ? n_tiles3 : cap;
+            kfn<<<grid, kT3, smem, s>>>(rew, done, trunc, values, n, gamma, gl32, ret_std, adv, vtarget, ret, ret_head64,
+                                       n_head, carry_in, summary_out, ws, n_tiles3, trace_dev);
+            return cudaSuccess;
+        };
+        if (trunc_is_f64) RLPPO_CUDA(launch3(gae_scan3_kernel<true, STORE>, 1));
+        else RLPPO_CUDA(launch3(gae_scan3_kernel<false, STORE>, 0));
+        if (trace_path != nullptr) {
+            static unsigned long long host[kTraceWords];
+            RLPPO_CUDA(cudaStreamSynchronize(s));
+            RLPPO_CUDA(cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost));
+            if (FILE* f = fopen(trace_path, "w")) {
+                for (size_t i = 0; i < kTraceWords; i += 8) {
+                    fprintf(f, "%zu %zu", i / 8 / 128, (i / 8) % 128);
+                    for (int e = 0; e < 8; ++e) fprintf(f, " %llu", host[i + e]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
+    } else if (vec) {
         // staged kernel: r, done, V (+ halo), delta as f32 + the truncated flags; records pre-set to the all-ones sentinel
         const size_t smem = (size_t)(4 * kTile2 + 4) * 4 + (size_t)kTile2 * (trunc_is_f64 ? 8 : 4);
         RLPPO_CUDA(cudaMemsetAsync(base + L.agg_off, 0xFF, L.total - L.agg_off, s));
