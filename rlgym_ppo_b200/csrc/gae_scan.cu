@@ -1132,7 +1132,9 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
                 if (resident3[which] < 1) return cudaErrorLaunchOutOfResources;
                 configured3[which] = true;
             }
-            const int cap = resident3[which] * rlppo::num_sms();
+            int cap = resident3[which] * rlppo::num_sms();
+            static const char* grid_env = getenv("RLPPO_GAE_GRID");      // experiments only: fewer persistent CTAs
+            if (grid_env != nullptr && atoi(grid_env) > 0 && atoi(grid_env) < cap) cap = atoi(grid_env);
             const int grid = n_tiles3 < cap ? n_tiles3 : cap;
             kfn<<<grid, kT3, smem, s>>>(rew, done, trunc, values, n, gamma, gl32, ret_std, adv, vtarget, ret, ret_head64,
                                        n_head, carry_in, summary_out, ws, n_tiles3, trace_dev);
