@@ -166,6 +166,79 @@ def reference_arm(args, wl):
     print(json.dumps(line))
 
 
+
+# C-ABI entry point -> kernel name in the ncu reports (profiles/ncu_traffic.json is keyed by kernel name)
+KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_train_fused": "fused_mlp_kernel<1, 1>",
+             "rlppo_value_train_fused": "fused_mlp_kernel<0, 1>", "rlppo_value_infer_fused": "fused_mlp_kernel<0, 0>",
+             "rlppo_gather_batch": "gather_kernel", "rlppo_gae_f32": "gae_scan3_kernel<1, 1>",
+             "rlppo_linear_wgrad": "wgrad_kernel", "rlppo_linear_fwd": "rowgemm_kernel", "rlppo_linear_dgrad": "rowgemm_kernel",
+             "rlppo_clip_adam": "clip_adam_kernel"}
+
+
+def bound_of(v, hbm_peak, tc_peak):
+    """Which roof bounds a call: the larger of flop / tensor peak and algorithmic bytes / HBM peak."""
+    t_tc = v["flop"] / (tc_peak * 1e12) if v["flop"] else 0.0
+    t_hbm = v["byte"] / (hbm_peak * 1e9) if v["byte"] else 0.0
+    return "tensor" if t_tc > t_hbm else "hbm"
+
+
+def roofline_of(name, v, hbm_peak, tc_peak, peak_src, workload):
+    """roofline object for one C-ABI entry point: achieved = algorithmic work per launch / average CUDA-event time of
+    a launch, against the roof that bounds it; traffic = dram bytes per launch from the committed ncu --set full
+    capture (profiles/ncu_traffic.json), or null."""
+    traffic = None
+    try:
+        tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tbl.get(workload, {}).get(KERNEL_OF.get(name, name))
+    except Exception:
+        pass
+    bound = bound_of(v, hbm_peak, tc_peak)
+    if bound == "tensor":
+        ach, peak, unit, src = v["flop"] / v["ms"] / 1e9, tc_peak, "TFLOP/s", peak_src + " (sustained bf16)"
+    else:
+        ach, peak, unit, src = v["byte"] / v["ms"] / 1e6, hbm_peak, "GB/s", peak_src + " (copy bandwidth)"
+    out = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+           "traffic": traffic, "peak_source": src, "launches": v["calls"], "avg_launch_ms": v["ms"] / v["calls"],
+           "algorithmic_bytes_per_launch": v["byte"] / v["calls"], "algorithmic_flop_per_launch": v["flop"] / v["calls"]}
+    if v["flop"] and v["byte"]:
+        out["other_roof"] = ({"bound": "hbm", "achieved": v["byte"] / v["ms"] / 1e6, "unit": "GB/s",
+                              "frac": v["byte"] / v["ms"] / 1e6 / hbm_peak} if bound == "tensor" else
+                             {"bound": "tensor", "achieved": v["flop"] / v["ms"] / 1e9, "unit": "TFLOP/s",
+                              "frac": v["flop"] / v["ms"] / 1e9 / tc_peak})
+    return out
+
+
+def gae_bandwidth(dev, hbm_peak, peak_src, log2n=26, reps=5):
+    """The metric's second half ("GAE GB/s"): one flat 2^26-step rollout with random done masks (inputs 2 GB > L2),
+    28 algorithmic bytes per step, CUDA events around the C-ABI call, median of `reps`."""
+    import torch
+    from rlgym_ppo_b200 import ops
+    n = 1 << log2n
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    rew = torch.randn(n, device=dev, generator=g) * 0.1
+    done = (torch.rand(n, device=dev, generator=g) < 1 / 300).float()
+    tr = ((torch.rand(n, device=dev, generator=g) < 1 / 1500).float() * (1 - done))
+    tr[-1] = 1 - done[-1]
+    tr = tr.double()
+    val = torch.randn(n + 1, device=dev, generator=g)
+    std = torch.tensor([0.7], device=dev)
+    out = tuple(torch.empty(n, device=dev) for _ in range(3))
+    for _ in range(3):
+        ops.gae(rew, done, tr, val, 0.99, 0.95, std, out=out)
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gae(rew, done, tr, val, 0.99, 0.95, std, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    return {"timesteps": n, "truncated_dtype": "f64", "ms": ms, "algorithmic_GBps": 28 * n / ms / 1e6,
+            "frac_of_hbm_peak": 28 * n / ms / 1e6 / hbm_peak, "actual_bytes_per_step": 32, "peak_source": peak_src,
+            "timesteps_per_sec": n / ms * 1e3}
+
 # ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -278,7 +351,7 @@ def b200_arm(args, wl):
         dev_ms, e2e_ms = float(t[0]), float(t[1])
 
     # ---- (3) per-kernel pass for the roofline object (rank 0; not part of the timed numbers) --------------------------
-    roofline, kernels = None, None
+    roofline, kernels, gae_line = None, None, None
     if rank != 0 and world > 1:
         flush_buf.zero_()
         step(pool_dev[it % n_pool])      # the collectives of rank 0's instrumented step need their peers
@@ -302,19 +375,12 @@ def b200_arm(args, wl):
         kernels = {k.replace("rlppo_", ""): {"calls": v["calls"], "ms": round(v["ms"], 4),
                                              "share": round(v["ms"] / total, 4),
                                              **({"TFLOP/s": round(v["flop"] / v["ms"] / 1e9, 2)} if v["flop"] else {}),
-                                             **({"GB/s": round(v["byte"] / v["ms"] / 1e6, 1)} if v["byte"] else {})}
+                                             **({"GB/s": round(v["byte"] / v["ms"] / 1e6, 1)} if v["byte"] else {}),
+                                             "bound": bound_of(v, hbm_peak, tc_peak)}
                    for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])}
         top_name, top = max(per.items(), key=lambda kv: kv[1]["ms"])
-        if top["flop"]:
-            ach = top["flop"] / top["ms"] / 1e9
-            roofline = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
-                        "frac": ach / tc_peak, "traffic": None, "peak_source": peak_src + " (sustained bf16)",
-                        "launches": top["calls"], "avg_launch_ms": top["ms"] / top["calls"]}
-        else:
-            ach = top["byte"] / top["ms"] / 1e6
-            roofline = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                        "launches": top["calls"], "avg_launch_ms": top["ms"] / top["calls"]}
+        roofline = roofline_of(top_name, top, hbm_peak, tc_peak, peak_src, args.workload)
+        gae_line = gae_bandwidth(dev, hbm_peak, peak_src) if world == 1 else None
 
     # ---- (4) CPU baseline (rank 0, single-GPU run only) ------------------------------------------------------------
     cpu = None
@@ -352,6 +418,7 @@ def b200_arm(args, wl):
             "gpu_launches": calls,
             "clocks": clocks,
             "roofline": roofline,
+            "gae": gae_line,
             "cpu_baseline": cpu,
             "kernels": kernels,
             "report": {k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in report.items()},

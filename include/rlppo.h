@@ -267,6 +267,15 @@ int rlppo_clip_adam(float* params, const float* grads, float* m, float* v, const
                     int n_seg, const float* sqnorm, const float* lr, int64_t* step_count, double max_norm,
                     double beta1, double beta2, double eps, const rlppo_bf16_view* h_views, int n_views,
                     void* stream);
+/* The two calls above as ONE launch (grid barrier between norm and update) with a deterministic, fixed-order norm:
+ * what PPOLearner uses.  sqnorm_out (optional f32[n_seg]) receives the norms.  ws: device workspace of
+ * rlppo_norm_clip_adam_workspace_bytes() bytes, zeroed by the caller once when it is allocated (the kernel leaves its
+ * counters zero again).  Same arithmetic as rlppo_clip_adam; only the summation order of the norm differs. */
+size_t rlppo_norm_clip_adam_workspace_bytes(void);
+int rlppo_norm_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off,
+                         int n_seg, float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm,
+                         double beta1, double beta2, double eps, const rlppo_bf16_view* h_views, int n_views,
+                         void* ws, size_t ws_bytes, void* stream);
 /* out f32[n_seg] = per-segment sum (a-b)^2 (update magnitudes, ppo_learner.py:212-220). */
 int rlppo_sqdiff(const float* a, const float* b, const int64_t* h_seg_off, int n_seg, float* out,
                  void* stream);

@@ -56,6 +56,8 @@ _SIGS = {
     "rlppo_value_infer_fused": ([_P, _P, _L, _P, _P, _P], _I),
     "rlppo_grad_sqnorm": ([_P, _P, _I, _P, _P], _I),
     "rlppo_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P], _I),
+    "rlppo_norm_clip_adam_workspace_bytes": ([], ctypes.c_size_t),
+    "rlppo_norm_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P, ctypes.c_size_t, _P], _I),
     "rlppo_sqdiff": ([_P, _P, _P, _I, _P, _P], _I),
 }
 
@@ -123,8 +125,8 @@ _TIMING = None     # None, or a list of (name, work, start_event, end_event) whi
 
 
 def call(name, *args, work=None):
-    """Invoke a C-ABI entry point.  `work` = (kind, amount): the call's algorithmic flops ("flop") or HBM bytes
-    ("byte"), recorded only while timing_begin() is active (bench.py's roofline pass)."""
+    """Invoke a C-ABI entry point.  `work` = (kind, amount[, kind, amount]): the call's algorithmic flops ("flop") and /
+    or HBM bytes ("byte"), recorded only while timing_begin() is active (bench.py's roofline pass)."""
     global CALLS
     CALLS += 1
     if _TIMING is None:
@@ -155,7 +157,8 @@ def timing_end():
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
         if work is not None:
-            d[work[0]] += float(work[1])
+            for i in range(0, len(work), 2):
+                d[work[i]] += float(work[i + 1])
     return out
 
 

@@ -109,6 +109,138 @@ __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// One launch for the whole optimiser step: per-segment gradient norms -> clip -> Adam (+ bf16 operand refresh),
+// with a grid barrier between the norm and the update.  The norm is summed in a FIXED order (thread-serial by
+// index, xor-shuffle tree, warps in order, blocks in order), so it is bit-identical from run to run and from rank
+// to rank: data-parallel replicas that all-reduced the same gradients stay bit-identical (the separate
+// seg_sumsq_kernel adds its block partials with fp32 atomics in whatever order the blocks finish -- measured on
+// 2 x B200: replicas drifted apart by an ulp of the clip coefficient per step).  It also replaces three launches
+// (memset + norm, step bump, Adam) by one.
+// Workspace: [arrive, depart] counters (zero before the first launch; the last block to leave zeroes them again)
+// followed by gridDim.x * kMaxSeg block partials.  Every block of the grid must be resident (grid <= SMs x occupancy).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+struct FusedWs {
+    unsigned int arrive, depart, pad[2];
+    float partial[1];    // [gridDim.x][kMaxSeg]
+};
+
+__global__ void __launch_bounds__(kFusedThreads)
+norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                      Segs segs, float* __restrict__ sqnorm_out, const float* __restrict__ lr,
+                      int64_t* __restrict__ step_count, float max_norm, double beta1d, double beta2d, float eps,
+                      Views views, FusedWs* __restrict__ ws) {
+    const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
+    __shared__ float s_w[kFusedThreads / 32][kMaxSeg];
+    __shared__ float s_coef[kMaxSeg], s_step_size[kMaxSeg], s_bc2_sqrt[kMaxSeg];
+    __shared__ double s_t[kMaxSeg];
+    const int64_t total = segs.off[segs.n];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < segs.n) s_t[threadIdx.x] = (double)(step_count[threadIdx.x] + 1);   // read BEFORE the barrier
+
+    // ---- phase 1: this block's partial sums of squares, fixed order ----
+    float acc[kMaxSeg];
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k) acc[k] = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = __ldg(g + i);
+        const int k = seg_of(segs, i);
+#pragma unroll
+        for (int j = 0; j < kMaxSeg; ++j)
+            if (j == k) acc[j] = fmaf(x, x, acc[j]);
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k)
+        if (k < segs.n) {
+            const float w = rlppo::warp_sum(acc[k]);
+            if (lane == 0) s_w[warp][k] = w;
+        }
+    __syncthreads();
+    if (threadIdx.x < segs.n) {
+        float t = 0.f;
+        for (int w = 0; w < kFusedThreads / 32; ++w) t += s_w[w][threadIdx.x];
+        __stcg(&ws->partial[(size_t)blockIdx.x * kMaxSeg + threadIdx.x], t);
+    }
+    // ---- grid barrier ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&ws->arrive, 1u);
+        const long long t0 = clock64();
+        while ((unsigned)rlppo::ld_acquire_s32(reinterpret_cast<const int*>(&ws->arrive)) < gridDim.x)
+            if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s): the grid was not co-resident
+    }
+    __syncthreads();
+    // ---- phase 2: every block adds the block partials in block order (identical result everywhere) ----
+    if (warp == 0) {
+        for (int k = 0; k < segs.n; ++k) {
+            float t = 0.f;
+            for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&ws->partial[(size_t)b * kMaxSeg + k]);
+            t = rlppo::warp_sum(t);
+            if (lane == 0) {
+                // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+                s_coef[k] = fminf(max_norm / (sqrtf(t) + 1e-6f), 1.0f);
+                const double st = s_t[k];
+                s_step_size[k] = (float)((double)lr[k] / (1.0 - pow(beta1d, st)));
+                s_bc2_sqrt[k] = (float)sqrt(1.0 - pow(beta2d, st));
+                if (blockIdx.x == 0) {
+                    if (sqnorm_out != nullptr) sqnorm_out[k] = t;
+                    step_count[k] = (int64_t)st;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = seg_of(segs, i);
+        const float gi = g[i] * s_coef[k];
+        float mi = m[i], vi = v[i];
+        mi = mi + (gi - mi) * omb1;                           // exp_avg.lerp_(grad, 1-beta1)
+        vi = vi * beta2 + omb2 * gi * gi;                      // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+        const float denom = sqrtf(vi) / s_bc2_sqrt[k] + eps;   // (sqrt(v)/sqrt(bc2)).add_(eps)
+        const float pn = p[i] - s_step_size[k] * (mi / denom);   // param.addcdiv_(m, denom, -step_size)
+        p[i] = pn;
+        m[i] = mi;
+        v[i] = vi;
+        for (int q = 0; q < views.n; ++q) {
+            const rlppo_bf16_view& w = views.v[q];
+            const int64_t rel = i - w.offset;
+            if (rel >= 0 && rel < (int64_t)w.out_f * w.in_f) {
+                const int r = (int)(rel / w.in_f), c = (int)(rel - (int64_t)r * w.in_f);
+                const uint16_t b = rlppo::f32_to_bf16_bits(pn);
+                w.wq[(int64_t)r * w.wq_ld + c] = b;
+                if (w.wt != nullptr) w.wt[(int64_t)c * w.wt_ld + r] = b;
+                break;
+            }
+        }
+    }
+    // ---- leave: the last block resets the counters for the next launch ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(&ws->depart, 1u);
+        if (old == gridDim.x - 1) {
+            ws->arrive = 0;
+            ws->depart = 0;
+            __threadfence();
+        }
+    }
+}
+
+int fused_grid(int64_t total, int* out) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        RLPPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, norm_clip_adam_kernel, kFusedThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+    }
+    const int64_t want = (total + 2047) / 2048;
+    const int64_t cap = (int64_t)rlppo::num_sms() * per_sm;
+    *out = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    return RLPPO_OK;
+}
+
 int make_segs(const int64_t* h_seg_off, int n_seg, Segs* out) {
     RLPPO_CHECK_ARG(h_seg_off && n_seg >= 1 && n_seg <= kMaxSeg, "n_seg must be in [1,%d]", kMaxSeg);
     out->n = n_seg;
@@ -139,6 +271,37 @@ int rlppo_grad_sqnorm(const float* grads, const int64_t* h_seg_off, int n_seg, f
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     RLPPO_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(float) * n_seg, s));
     seg_sumsq_kernel<false><<<grid_for(segs.off[n_seg]), 256, 0, s>>>(grads, nullptr, segs, sqnorm);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+size_t rlppo_norm_clip_adam_workspace_bytes(void) {
+    return sizeof(FusedWs) + sizeof(float) * kMaxSeg * (size_t)rlppo::num_sms() * 4;
+}
+
+int rlppo_norm_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off, int n_seg,
+                         float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm, double beta1,
+                         double beta2, double eps, const rlppo_bf16_view* h_views, int n_views, void* ws,
+                         size_t ws_bytes, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(params && grads && m && v && lr && step_count && ws, "null pointer");
+    RLPPO_CHECK_ARG(ws_bytes >= rlppo_norm_clip_adam_workspace_bytes(), "workspace too small");
+    Segs segs;
+    int rc = make_segs(h_seg_off, n_seg, &segs);
+    if (rc) return rc;
+    RLPPO_CHECK_ARG(n_views >= 0 && n_views <= kMaxViews && (n_views == 0 || h_views), "0..%d bf16 views", kMaxViews);
+    Views views;
+    views.n = n_views;
+    for (int i = 0; i < n_views; ++i) {
+        views.v[i] = h_views[i];
+        RLPPO_CHECK_ARG(h_views[i].wq && h_views[i].out_f >= 1 && h_views[i].in_f >= 1, "bad bf16 view %d", i);
+    }
+    int grid = 1;
+    rc = fused_grid(segs.off[n_seg], &grid);
+    if (rc) return rc;
+    norm_clip_adam_kernel<<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        params, grads, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
+        static_cast<FusedWs*>(ws));
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }

@@ -164,20 +164,21 @@ def weight_to_bf16(w, wq, wt=None):
 def linear_fwd(x, wq, bias, y, N, K, relu, M=None):
     M = x.shape[0] if M is None else M
     call("rlppo_linear_fwd", ptr(x), x.stride(0), ptr(wq), wq.stride(0), ptr(bias), ptr(y), y.stride(0), int(M),
-         int(N), int(K), int(bool(relu)), stream_ptr(), work=("flop", 2.0 * M * N * K))
+         int(N), int(K), int(bool(relu)), stream_ptr(),
+         work=("flop", 2.0 * M * N * K, "byte", 2.0 * (M * K + N * K + M * N)))
 
 
 def linear_dgrad(dy, wt, hprev, dx, N, K, M=None):
     M = dy.shape[0] if M is None else M
     call("rlppo_linear_dgrad", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
          0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), int(M), int(N), int(K), stream_ptr(),
-         work=("flop", 2.0 * M * N * K))
+         work=("flop", 2.0 * M * N * K, "byte", 2.0 * (M * N + N * K + M * K * (2 if hprev is not None else 1))))
 
 
 def linear_wgrad(dy, x, dw, db, N, K, M=None):
     M = dy.shape[0] if M is None else M
     call("rlppo_linear_wgrad", ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(dw), dw.stride(0), ptr(db), int(M),
-         int(N), int(K), stream_ptr(), work=("flop", 2.0 * M * N * K))
+         int(N), int(K), stream_ptr(), work=("flop", 2.0 * M * N * K, "byte", 2.0 * M * (N + K) + 4.0 * N * K))
 
 
 def wgrad_multi(items, M):
@@ -185,12 +186,14 @@ def wgrad_multi(items, M):
     for i0 in range(0, len(items), 8):
         part = items[i0:i0 + 8]
         arr = (_lib.WgradItem * len(part))()
-        flop = 0.0
+        flop = nbytes = 0.0
         for a, (dy, x, dw, N, K) in zip(arr, part):
             a.dy, a.lddy, a.x, a.ldx = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
             a.dw, a.lddw, a.M, a.N, a.K = dw.data_ptr(), dw.stride(0), int(M), int(N), int(K)
             flop += 2.0 * M * N * K
-        call("rlppo_wgrad_multi", ctypes.cast(arr, ctypes.c_void_p), len(part), stream_ptr(), work=("flop", flop))
+            nbytes += 2.0 * M * (dy.stride(0) + x.stride(0)) + 4.0 * N * K     # both bf16 operands read once, dW written
+        call("rlppo_wgrad_multi", ctypes.cast(arr, ctypes.c_void_p), len(part), stream_ptr(),
+             work=("flop", flop, "byte", nbytes))
 
 
 def policy_head_sample(h, wq, bias, n_actions, K, M=None, u=None, seed=0, offset=0, deterministic=False,
@@ -227,27 +230,41 @@ def _net_flops(net, M, n_out, train):
     return f
 
 
+def _net_bytes(net, M, n_out_pad, train, policy):
+    """HBM bytes a fused launch has to move: x read once; training also writes every hidden activation, the head's
+    d(logits) (policy) and every dL/dH as bf16 -- the operands of the weight-gradient GEMMs, which contract over ALL
+    rows and therefore run as a second launch."""
+    hid = [net.hidden[i] for i in range(net.n_hidden)]
+    b = 2.0 * M * ((net.in_dim + 7) // 8 * 8)
+    if train:
+        b += 2.0 * M * (2 * sum(hid) - (0 if policy else hid[-1])) + (2.0 * M * n_out_pad if policy else 0.0) + 16.0 * M
+    else:
+        b += 8.0 * M
+    return b
+
+
 def policy_train_fused(net, x, M, n_actions, actions, old_logp, adv, inv_batch, clip, ent_coef, metrics, logp_out=None):
     call("rlppo_policy_train_fused", ctypes.byref(net), ptr(x), int(M), int(n_actions), ptr(actions), ptr(old_logp),
          ptr(adv), float(inv_batch), float(clip), float(ent_coef), ptr(logp_out), ptr(metrics), stream_ptr(),
-         work=("flop", _net_flops(net, M, n_actions, True)))
+         work=("flop", _net_flops(net, M, n_actions, True), "byte", _net_bytes(net, M, (n_actions + 7) // 8 * 8, True, True)))
 
 
 def policy_infer_fused(net, x, M, n_actions, u=None, seed=0, offset=0, deterministic=False, actions_out=None,
                        actions_i64_out=None, logp_out=None):
     call("rlppo_policy_infer_fused", ctypes.byref(net), ptr(x), int(M), int(n_actions), ptr(u), int(seed) & (2 ** 64 - 1),
          int(offset) & (2 ** 64 - 1), int(bool(deterministic)), ptr(actions_out), ptr(actions_i64_out), ptr(logp_out),
-         stream_ptr(), work=("flop", _net_flops(net, M, n_actions, False)))
+         stream_ptr(), work=("flop", _net_flops(net, M, n_actions, False), "byte", _net_bytes(net, M, 0, False, True)))
 
 
 def value_train_fused(net, x, M, w_head, targets, inv_batch, gw_head, metrics, values_out=None):
     call("rlppo_value_train_fused", ctypes.byref(net), ptr(x), int(M), ptr(w_head), ptr(targets), float(inv_batch),
-         ptr(gw_head), ptr(values_out), ptr(metrics), stream_ptr(), work=("flop", _net_flops(net, M, 1, True)))
+         ptr(gw_head), ptr(values_out), ptr(metrics), stream_ptr(),
+         work=("flop", _net_flops(net, M, 1, True), "byte", _net_bytes(net, M, 0, True, False)))
 
 
 def value_infer_fused(net, x, M, w_head, values_out):
     call("rlppo_value_infer_fused", ctypes.byref(net), ptr(x), int(M), ptr(w_head), ptr(values_out), stream_ptr(),
-         work=("flop", _net_flops(net, M, 1, False)))
+         work=("flop", _net_flops(net, M, 1, False), "byte", _net_bytes(net, M, 0, False, False)))
 
 
 # ---- optimiser ------------------------------------------------------------------------------------------------
@@ -269,6 +286,23 @@ def clip_adam(params, grads, m, v, seg_off, sqnorm, lr, step_count, max_norm=0.5
          ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps),
          None if views is None else ctypes.cast(views, ctypes.c_void_p), 0 if views is None else len(views),
          stream_ptr(), work=("byte", 28 * int(so[-1])))
+
+
+_nca_ws = {}
+
+
+def norm_clip_adam(params, grads, m, v, seg_off, sqnorm_out, lr, step_count, max_norm=0.5, beta1=0.9, beta2=0.999,
+                   eps=1e-8, views=None):
+    """grad_sqnorm + clip_adam as one launch with a fixed-order (deterministic) norm; see rlppo_norm_clip_adam."""
+    so = _seg(seg_off)
+    ws = _nca_ws.get(params.device)
+    if ws is None:
+        ws = torch.zeros(int(_lib._lib.rlppo_norm_clip_adam_workspace_bytes()), dtype=torch.uint8, device=params.device)
+        _nca_ws[params.device] = ws
+    call("rlppo_norm_clip_adam", ptr(params), ptr(grads), ptr(m), ptr(v), so.ctypes.data, len(so) - 1, ptr(sqnorm_out),
+         ptr(lr), ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps),
+         None if views is None else ctypes.cast(views, ctypes.c_void_p), 0 if views is None else len(views),
+         ptr(ws), ws.numel(), stream_ptr(), work=("byte", 32 * int(so[-1])))
 
 
 def sqdiff(a, b, seg_off, out):

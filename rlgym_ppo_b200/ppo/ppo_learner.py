@@ -219,12 +219,12 @@ class PPOLearner(object):
         self._apply_step()
 
     def _apply_step(self):
-        ops.grad_sqnorm(self._grads, self._seg, self._sqnorm)           # ppo_learner.py:187-190
-        ops.clip_adam(self._params, self._grads, self._m, self._v, self._seg, self._sqnorm, self._lr_dev,
-                      self._steps, max_norm=0.5, views=self._views)     # :192-193, + bf16 operand refresh in-launch
+        # ppo_learner.py:187-193 in one launch: fixed-order (deterministic) norms -> clip -> Adam -> bf16 operand refresh
+        ops.norm_clip_adam(self._params, self._grads, self._m, self._v, self._seg, self._sqnorm, self._lr_dev,
+                           self._steps, max_norm=0.5, views=self._views)
         self.policy._stack.mark_operands_fresh()
         self.value_net._stack.mark_operands_fresh()
-        self.launches += 4
+        self.launches += 1
 
     def _backward_body(self, exp, idx, local, chunk):
         self._grads.zero_()                                     # ppo_learner.py:131-132

@@ -45,24 +45,51 @@ def main():
             return PPOLearner(89, 90, 0, (256, 256), (256, 256), (0.1, 1.0), B, 2, 3e-4, 3e-4, 0.2, 0.01, B, dev,
                               process_group=group, dp_mode=mode)
 
-    # ---- replicated: same buffer everywhere; compare with a one-rank learner on the same buffer ----
+    # ---- replicated, ONE optimiser step: the all-reduced gradient equals the one-rank gradient ----
+    # After the first step Adam's first moment is (1 - beta1) * clipped gradient, so comparing the moment arenas compares
+    # the gradients themselves: same per-row math, a different order of the fp32 sums (rank partials + NCCL sum instead of
+    # one launch; the weight-gradient kernel's atomics are unordered even on one GPU) -> 1e-5 rel-L2.
+    def learner1(group):
+        torch.manual_seed(5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return PPOLearner(89, 90, 0, (256, 256), (256, 256), (0.1, 1.0), B, 1, 3e-4, 3e-4, 0.2, 0.01, B, dev,
+                              process_group=group, dp_mode="replicated")
+    dp1, alone1 = learner1(None), learner1(solo)
+    r_dp1 = dp1.learn(make_buffer(7, B, dev))
+    r_11 = alone1.learn(make_buffer(7, B, dev))
+    g_err = float((dp1._m - alone1._m).norm() / alone1._m.norm())
+    assert r_dp1["Cumulative Model Updates"] == r_11["Cumulative Model Updates"] == 1
+    assert g_err < 1e-5, f"all-reduced gradient differs from the one-rank gradient: rel-L2 {g_err}"
+    for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
+        assert abs(r_dp1[k] - r_11[k]) < 1e-5 * max(1.0, abs(r_11[k])), (k, r_dp1[k], r_11[k])
+
+    # ---- replicated, 3 learn() calls x 6 optimiser steps (eager, captured, replayed), compared call by call ----
+    # bf16 rounding of the forward operands makes the loss piecewise constant in the weights, and Adam turns a 1e-10
+    # wobble on a gradient element whose true value is ~0 into a full +-lr step of either sign: measured on 2 x B200,
+    # two ONE-rank learners fed the same fresh buffers are 3e-6 apart after one call and up to 1e-3 after three (the
+    # weight-gradient kernel's fp32 atomics are unordered).  Equality of trajectories is therefore tested one call at a
+    # time from a COMMON state: after each call the one-rank learner takes over the data-parallel learner's weights and
+    # Adam moments, so every comparison covers 6 optimiser steps of both code paths on identical inputs.
     dp, alone = learner(None, "replicated"), learner(solo, "replicated")
     assert dp.world_size == world and alone.world_size == 1
-    p_init = dp._params.clone()
-    for it in range(3):                                  # eager, captured, replayed
+    errs = []
+    for it in range(3):
+        p_before = dp._params.clone()
         rep_dp = dp.learn(make_buffer(100 + it, n, dev))
         rep_1 = alone.learn(make_buffer(100 + it, n, dev))
-    # Same per-row math, different order of the fp32 sums (tests/test_learner_gpu.py::test_row_partition_invariance shows
-    # the single-GPU version of this statement).  Adam amplifies a 1e-10 wobble on gradient elements of magnitude <= eps,
-    # so compare the update: 1e-3 rel-L2, and no element off by as much as one step (lr) after 18 steps.
-    upd_dp, upd_1 = dp._params - p_init, alone._params - p_init
-    err = float((upd_dp - upd_1).norm() / upd_1.norm())
-    assert err < 1e-3, f"replicated DP differs from the single-rank run: rel-L2 of the update {err}"
-    assert float((upd_dp - upd_1).abs().max()) < 3e-4
-    assert float((dp._m - alone._m).abs().max()) < 1e-6
-    for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
-        assert abs(rep_dp[k] - rep_1[k]) < 1e-5 * max(1.0, abs(rep_1[k])), (k, rep_dp[k], rep_1[k])
+        upd_dp, upd_1 = dp._params - p_before, alone._params - p_before
+        errs.append(float((upd_dp - upd_1).norm() / upd_1.norm()))
+        assert errs[-1] < 2e-4, f"replicated DP differs from the one-rank run in call {it}: rel-L2 of the update {errs[-1]}"
+        assert float((upd_dp - upd_1).abs().max()) < 6 * 2 * 3e-4
+        assert float((dp._v - alone._v).norm() / alone._v.norm()) < 1e-4
+        for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
+            assert abs(rep_dp[k] - rep_1[k]) < 1e-5 * max(1.0, abs(rep_1[k])), (k, rep_dp[k], rep_1[k])
+        for dst, src in ((alone._params, dp._params), (alone._m, dp._m), (alone._v, dp._v)):
+            dst.copy_(src)
+    err = max(errs)
     assert rep_dp["Cumulative Model Updates"] == rep_1["Cumulative Model Updates"] == 3 * 2 * 3
+    if rank == 0:
+        print(f"replicated: one-step gradient rel-L2 {g_err:.2e}; per-call update rel-L2 {errs}")
 
     # ---- sharded: own buffer per rank; replicas must stay identical ----
     sh = learner(None, "sharded")

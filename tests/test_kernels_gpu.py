@@ -506,6 +506,42 @@ def test_clip_adam_vs_torch(ops):
     assert np.allclose(out.sqrt().cpu().numpy(), want, rtol=1e-4)
 
 
+@pytest.mark.parametrize("sizes", [[177754, 154881], [7575083, 7575088], [5, 1]])
+def test_norm_clip_adam_one_launch_vs_torch_and_deterministic(ops, sizes):
+    """rlppo_norm_clip_adam (norm + clip + Adam in one launch, grid barrier, fixed-order norm) against torch's
+    clip_grad_norm_ + Adam, against the two-launch path, and bit-identical from run to run (what keeps data-parallel
+    replicas in step); the workspace counters clean themselves (5 launches on one workspace)."""
+    torch.manual_seed(1)
+    seg = [0, sizes[0], sizes[0] + sizes[1]]
+    p0 = torch.randn(seg[-1]) * 0.05
+    params = [torch.nn.Parameter(p0[seg[i]:seg[i + 1]].clone()) for i in range(2)]
+    opts = [torch.optim.Adam([params[0]], lr=3e-4), torch.optim.Adam([params[1]], lr=1e-4)]
+    lr = dev(torch.tensor([3e-4, 1e-4]))
+    runs = []
+    for rep in range(2):
+        p = dev(p0.clone()); m = torch.zeros_like(p); v = torch.zeros_like(p)
+        sq = torch.zeros(2, device=DEV); steps = torch.zeros(2, dtype=torch.int64, device=DEV)
+        gen = torch.Generator().manual_seed(2)
+        for it in range(5):
+            g = torch.randn(seg[-1], generator=gen) * (0.01 if it % 2 else 1e-4)
+            if rep == 0:
+                for i in range(2):
+                    params[i].grad = g[seg[i]:seg[i + 1]].clone()
+                    torch.nn.utils.clip_grad_norm_([params[i]], 0.5)
+                    opts[i].step()
+            gd = dev(g)
+            ops.norm_clip_adam(p, gd, m, v, seg, sq, lr, steps)
+            want_sq = [float((g[seg[i]:seg[i + 1]].double() ** 2).sum()) for i in range(2)]
+            assert np.allclose(sq.cpu().numpy(), want_sq, rtol=1e-5)
+        torch.cuda.synchronize()
+        assert steps.tolist() == [5, 5]
+        runs.append((p.clone(), m.clone(), v.clone()))
+    ref = torch.cat([q.detach() for q in params])
+    assert float((runs[0][0].cpu() - ref).abs().max()) < 2e-7
+    for a, b in zip(runs[0], runs[1]):
+        assert torch.equal(a, b), "the one-launch optimiser step is not deterministic"
+
+
 def test_weight_and_rows_to_bf16(ops):
     w = torch.randn(90, 89)
     wq = torch.full((96, 96), 9.0, dtype=torch.bfloat16, device=DEV)

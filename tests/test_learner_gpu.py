@@ -504,28 +504,38 @@ def test_graph_replayed_iteration_equals_eager(pkg):
 def test_row_partition_invariance(pkg):
     """Gradient accumulation over chunks of a batch (the reference's minibatches, ppo_learner.py:134-193; also what the
     data-parallel ranks do) must give the full-batch result: same kernels, same per-row math, only the order of the fp32
-    sums differs (tools/partition_debug.py: gradients agree to 1e-7 rel-L2, the run-to-run noise of the atomics).
-    Adam turns a 1e-10 absolute wobble on a gradient element of magnitude <= eps = 1e-8 into a few % of a step, so the
-    weights are compared the way that makes sense for Adam: the UPDATE (theta - theta_0) agrees to 1e-3 rel-L2 and no
-    element differs by as much as one step (lr) after 18 steps -- whether a 2048-row batch is processed in one chunk,
-    two, or sixteen (128-row tiles: every CTA gets one tile)."""
+    sums differs (tools/partition_debug.py: gradients agree to 1e-7 rel-L2, the run-to-run noise of the atomics) --
+    whether a 2048-row batch is processed in one chunk, two, or sixteen (128-row tiles: every CTA gets one tile).
+    bf16 rounding of the forward operands makes the loss piecewise constant in the weights and Adam turns a 1e-10 wobble
+    on a ~0 gradient element into a full +-lr step, so whole trajectories separate chaotically (two identical one-chunk
+    learners end up to 1e-3 rel-L2 apart after 18 steps).  The comparison is therefore made one learn() call (6 optimiser
+    steps) at a time from a COMMON state: after each call the chunked learner takes over the reference learner's weights
+    and Adam moments."""
     import contextlib
     import io
     from tests.dp_check import make_buffer
     from rlgym_ppo_b200.ppo import PPOLearner
     B, n, lr_ = 2048, 3 * 2048, 3e-4
-    outs = []
-    for chunk in (2048, 1024, 128):
+
+    def learner(chunk):
         torch.manual_seed(5)
         with contextlib.redirect_stdout(io.StringIO()):
-            lr = PPOLearner(89, 90, 0, (256, 256), (256, 256), (0.1, 1.0), B, 2, lr_, lr_, 0.2, 0.01, B, DEV,
-                            max_chunk_rows=chunk)
-        p0 = lr._params.clone()
-        reps = [lr.learn(make_buffer(100 + it, n, DEV)) for it in range(3)]
-        outs.append((lr._params - p0, reps[-1]))
-    for upd, rep in outs[1:]:
-        diff = upd - outs[0][0]
-        assert float(diff.norm() / outs[0][0].norm()) < 1e-3, float(diff.norm() / outs[0][0].norm())
-        assert float(diff.abs().max()) < lr_, float(diff.abs().max())
-        for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
-            assert abs(rep[k] - outs[0][1][k]) < 1e-5 * max(1.0, abs(outs[0][1][k])), (k, rep[k], outs[0][1][k])
+            return PPOLearner(89, 90, 0, (256, 256), (256, 256), (0.1, 1.0), B, 2, lr_, lr_, 0.2, 0.01, B, DEV,
+                              max_chunk_rows=chunk)
+
+    for chunk in (1024, 128):
+        full, part = learner(2048), learner(chunk)
+        for it in range(3):
+            p0 = full._params.clone()
+            rep_f = full.learn(make_buffer(100 + it, n, DEV))
+            rep_p = part.learn(make_buffer(100 + it, n, DEV))
+            upd_f, upd_p = full._params - p0, part._params - p0
+            err = float((upd_p - upd_f).norm() / upd_f.norm())
+            assert err < 2e-4, (chunk, it, err)
+            assert float((upd_p - upd_f).abs().max()) < lr_, float((upd_p - upd_f).abs().max())
+            assert float((part._v - full._v).norm() / full._v.norm()) < 1e-4
+            for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
+                assert abs(rep_p[k] - rep_f[k]) < 1e-5 * max(1.0, abs(rep_f[k])), (k, rep_p[k], rep_f[k])
+            for dst, src in ((part._params, full._params), (part._m, full._m), (part._v, full._v)):
+                dst.copy_(src)
+        assert rep_p["Cumulative Model Updates"] == rep_f["Cumulative Model Updates"] == 18
