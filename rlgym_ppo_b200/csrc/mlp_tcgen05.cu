@@ -832,6 +832,7 @@ __global__ void colsum_kernel(const uint16_t* __restrict__ dy, int64_t ld, int64
     const int64_t r1 = min(M, r0 + rows_per_block);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (rlane < rstride) {
+#pragma unroll 4
         for (int64_t r = r0 + rlane; r < r1; r += rstride) {
             const uint4 q = __ldg(reinterpret_cast<const uint4*>(dy + r * ld + g * 8));
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -1002,7 +1003,11 @@ int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int6
         const int n8 = (N + 7) / 8 * 8;
         RLPPO_CHECK_ARG(n8 <= lddy && n8 / 8 <= 256, "bias-gradient pass needs N padded to 8 within lddy");
         // padded columns of dY are zero by construction, so summing n8 columns is safe; only N are written
-        const int64_t rows_per_block = 512;
+        // ~8 blocks per SM: with 512 rows per block a 50 000-row dY gave 98 blocks of 512 dependent 16-byte loads per
+        // thread -- 2 TB/s, and at the wide nets (N = 2048) the pass cost 72 % of the weight-gradient GEMM it follows
+        int64_t rows_per_block = (M + (int64_t)num_sms() * 8 - 1) / ((int64_t)num_sms() * 8);
+        rows_per_block = (rows_per_block + 7) / 8 * 8;
+        if (rows_per_block < 32) rows_per_block = 32;
         const unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
         int threads = 256;
         if (threads < n8 / 8) threads = n8 / 8;

@@ -193,6 +193,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
         }
     }
     __syncthreads();
+    int hint = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = seg_of(segs, i);
         const float gi = g[i] * s_coef[k];
@@ -204,16 +205,25 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
         p[i] = pn;
         m[i] = mi;
         v[i] = vi;
-        for (int q = 0; q < views.n; ++q) {
-            const rlppo_bf16_view& w = views.v[q];
-            const int64_t rel = i - w.offset;
-            if (rel >= 0 && rel < (int64_t)w.out_f * w.in_f) {
-                const int r = (int)(rel / w.in_f), c = (int)(rel - (int64_t)r * w.in_f);
-                const uint16_t b = rlppo::f32_to_bf16_bits(pn);
-                w.wq[(int64_t)r * w.wq_ld + c] = b;
-                if (w.wt != nullptr) w.wt[(int64_t)c * w.wt_ld + r] = b;
-                break;
+        // bf16 operands of the weight this element belongs to (W and W^T).  A thread's elements are gridDim*blockDim apart,
+        // mostly inside one matrix: try the view that matched last time before searching; 32-bit index arithmetic.
+        if (views.n > 0) {
+            int64_t rel = i - views.v[hint].offset;
+            if (rel < 0 || rel >= (int64_t)views.v[hint].out_f * views.v[hint].in_f) {
+                int found = -1;
+                for (int q = 0; q < views.n; ++q) {
+                    const int64_t rq = i - views.v[q].offset;
+                    if (rq >= 0 && rq < (int64_t)views.v[q].out_f * views.v[q].in_f) found = q;
+                }
+                if (found < 0) continue;
+                hint = found;
+                rel = i - views.v[hint].offset;
             }
+            const rlppo_bf16_view& w = views.v[hint];
+            const unsigned r = (unsigned)rel / (unsigned)w.in_f, c = (unsigned)rel - r * (unsigned)w.in_f;
+            const uint16_t b = rlppo::f32_to_bf16_bits(pn);
+            w.wq[(int64_t)r * w.wq_ld + c] = b;
+            if (w.wt != nullptr) w.wt[(int64_t)c * w.wt_ld + r] = b;
         }
     }
     // ---- leave: the last block resets the counters for the next launch ----
