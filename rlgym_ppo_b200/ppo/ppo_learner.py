@@ -147,6 +147,9 @@ class PPOLearner(object):
         # and process-group teardown hangs with captured NCCL work outstanding.  Default: two graphs per optimiser step
         # with an eager allreduce between them.
         self.graph_collectives = os.environ.get("RLPPO_GRAPH_COLLECTIVES", "0") == "1"
+        # RLPPO_TWO_STREAMS=0: policy and value chains of a batch on one stream (see _train_chunk)
+        self.two_streams = os.environ.get("RLPPO_TWO_STREAMS", "1") == "1"
+        self._side_stream = None
 
     # ---- workspaces ----------------------------------------------------------------------------------------
     def _minibatch_buffers(self, rows):
@@ -174,6 +177,34 @@ class PPOLearner(object):
         inv_b = 1.0 / float(parallel.samples_per_step(self.batch_size, self.world_size, self.dp_mode))
         metrics = self._tail[0:8]
         n = 1
+        both_fused = self.policy._stack.fused_ok and self.value_net._stack.fused_ok
+        if both_fused and self.two_streams and _lib._TIMING is None:
+            # The two nets are independent until the optimiser step: the value net's chain (fused kernel, weight
+            # gradients) runs on a second stream -- a parallel branch of the captured graph.  Each kernel is persistent
+            # with one CTA per SM, so the branches do not share SMs; they fill each other's tails (391 tiles over 148 CTAs
+            # leave a third of the SMs idle for the last tile round) and prologue / drain phases.
+            main = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self._params.device)
+            side = self._side_stream
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                st = self.value_net._stack
+                ws = st.workspace(M)
+                ops.value_train_fused(st.fused_net(x.stride(0), ws), x, M, st.w[-1], mb["targets"], inv_b, st.gw[-1], metrics)
+                ops.wgrad_multi(st.fused_wgrad_items(x, ws), M)
+                join.record(side)
+            st = self.policy._stack
+            ws = st.workspace(M)
+            ops.policy_train_fused(st.fused_net(x.stride(0), ws, policy_head=True), x, M, self.policy.n_actions,
+                                   mb["actions"], mb["old_logp"], mb["adv"], inv_b, float(self.clip_range),
+                                   float(self.ent_coef), metrics)
+            ops.wgrad_multi(st.fused_wgrad_items(x, ws, head_dy=ws["dz"]), M)
+            main.wait_event(join)
+            self.launches += 5
+            return
         wg_items = []
         for net, is_policy in ((self.policy, True), (self.value_net, False)):
             st = net._stack

@@ -539,3 +539,61 @@ def test_row_partition_invariance(pkg):
             for dst, src in ((part._params, full._params), (part._m, full._m), (part._v, full._v)):
                 dst.copy_(src)
         assert rep_p["Cumulative Model Updates"] == rep_f["Cumulative Model Updates"] == 18
+
+def test_c4_shape_inference_over_4096_slots_and_slot_major_gae(pkg):
+    """BASELINE.json configs[3]: batched policy inference for 4096 env slots and GAE over a 245 x 4096 = 1 003 520-step
+    iteration.  Inference: the fused kernel on a [4096, 89] observation block with injected uniforms against the oracle
+    with the kernel's bf16 rounding points (actions = inverse CDF of the oracle's probabilities, up to ties at CDF
+    boundaries; log-probs 2e-3).  GAE: the collector's flat layout (slot after slot, every run closed by done or
+    truncated, batched_agent_manager.py:125-172) against the C restatement of the reference loop: 1e-5 scale-aware and a
+    bit-mismatch rate below 1e-3 (the scan re-associates the f64 sums)."""
+    from rlgym_ppo_b200 import ops
+    from rlgym_ppo_b200.ppo import DiscreteFF
+    slots, steps, obs, act = 4096, 245, 89, 90
+    torch.manual_seed(11)
+    pol = DiscreteFF(obs, act, (256, 256, 256), DEV)
+    rng = np.random.RandomState(4)
+    x_np = rng.randn(slots, obs).astype(np.float32)
+    u = torch.rand(slots, generator=torch.Generator().manual_seed(2))
+    st = pol._stack
+    st.refresh_operands()
+    assert st.fused_ok
+    x, n, _ = pol._stage_obs(x_np)
+    a64 = torch.empty(slots, dtype=torch.int64, device=DEV)
+    lp = torch.empty(slots, device=DEV)
+    ops.policy_infer_fused(st.fused_net(x.stride(0), policy_head=True), x, n, act, u=u.to(DEV), actions_i64_out=a64,
+                           logp_out=lp)
+    params = [p.detach().cpu() for p in pol.parameters()]
+    probs = O.policy_probs(params, torch.from_numpy(x_np), quant=O.quant_bf16)
+    want_a = O.sample_inverse_cdf(probs, u).numpy()
+    got_a = a64.cpu().numpy()
+    same = got_a == want_a
+    assert same.mean() > 0.995, same.mean()
+    want_lp = torch.log(torch.clamp(probs, 1e-11, 1.0)).numpy()[np.arange(slots), got_a]
+    assert close(lp.cpu().numpy(), want_lp, 2e-3)
+
+    # slot-major flat rollout: each slot's 245 steps are consecutive; episodes end inside a slot at random, the last
+    # step of every slot is closed (truncated unless done)
+    N = slots * steps
+    rew = (rng.randn(N) * 0.1).astype(np.float32)
+    done = (rng.rand(N) < 1 / 300).astype(np.float32)
+    trunc = np.zeros(N, np.float64)
+    last = np.arange(steps - 1, N, steps)
+    trunc[last] = 1.0 - done[last]
+    val = rng.randn(N + 1).astype(np.float32)
+    std = np.float32(0.8)
+    vt0, adv0, ret0 = O.gae_nep50_c(rew, done, trunc, val, 0.99, 0.95, std)
+    to = lambda a: torch.from_numpy(a).to(DEV)  # noqa: E731
+    vt, adv, ret = ops.gae(to(rew), to(done), to(trunc), to(val), 0.99, 0.95, torch.tensor([std], device=DEV))
+    for name, got, want in (("adv", adv, adv0), ("vt", vt, vt0), ("ret", ret, ret0.astype(np.float32))):
+        got = got.cpu().numpy()
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+        assert err.max() <= 1e-5, (name, float(err.max()))
+        assert (got != want).mean() < 1e-3, (name, float((got != want).mean()))
+    # slots are independent: the scan of one slot alone equals its rows of the whole scan (shard-by-slot, SURVEY 8e)
+    s0 = 1234 * steps
+    sl = slice(s0, s0 + steps)
+    vt1, adv1, ret1 = ops.gae(to(rew[sl]), to(done[sl]), to(trunc[sl]), to(val[s0:s0 + steps + 1]), 0.99, 0.95,
+                              torch.tensor([std], device=DEV))
+    for a, b in ((adv1, adv[sl]), (ret1, ret[sl]), (vt1, vt[sl])):      # same values up to the scan's association
+        assert float(((a - b).abs() / b.abs().clamp(min=1.0)).max()) <= 1e-6
