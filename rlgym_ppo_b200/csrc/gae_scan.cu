@@ -705,7 +705,7 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
                  const float* __restrict__ ret_std, float* __restrict__ adv, float* __restrict__ vt,
                  float* __restrict__ ret, double* __restrict__ ret_head, int64_t n_head,
                  const double* __restrict__ carry_in, double* __restrict__ summary_out, Workspace ws, int n_tiles,
-                 unsigned long long* __restrict__ trace) {
+                 unsigned long long* __restrict__ trace, int early_poll) {
     extern __shared__ __align__(128) uint8_t sm3[];
     __shared__ uint64_t s_full[kStages3], s_aggr[2], s_carr[2];
     __shared__ double s_wagg[2][kW3][4];
@@ -783,9 +783,15 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
         Aff prev_incl = aff_identity();
         for (int k = 0; k < K; ++k) {
             const int t = bid + k * G;
-            mbar_wait3(&s_aggr[k & 1], (k >> 1) & 1);
-            const Aff tile_agg = Aff{s_agg[k & 1][0], s_agg[k & 1][1], s_agg[k & 1][2], s_agg[k & 1][3]};
-            if (lane == 0) stamp(k, 4);
+            // The polls below do not need this tile's own aggregate: they start while the compute warps are still in
+            // phase A, and the aggregate is only waited for where it is consumed.
+            Aff tile_agg;
+            auto wait_own = [&]() {
+                mbar_wait3(&s_aggr[k & 1], (k >> 1) & 1);
+                tile_agg = Aff{s_agg[k & 1][0], s_agg[k & 1][1], s_agg[k & 1][2], s_agg[k & 1][3]};
+                if (lane == 0) stamp(k, 4);
+            };
+            if (!early_poll) wait_own();
             // the record at position p of the nearest-first list (nullptr: none)
             auto rec_at = [&](int p) -> const double* {
                 if (p < l) return ws.agg + (size_t)(t - 1 - p) * 4;
@@ -817,6 +823,7 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
                     if (need_s && rec_load(ps, s1)) need_s = false;
                     if (!__any_sync(0xffffffffu, need_s)) break;
                     if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
+                    __nanosleep(100);                              // back off: 444 warps polling L2 flat out slow everyone down
                 }
                 if (ps == nullptr) s1 = aff_identity();
 #pragma unroll
@@ -824,6 +831,7 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
                     const Aff y = shfl_down(s1, off);
                     s1 = compose(s1, y);                       // lanes past the end pull in garbage; lane 0 is exact
                 }
+                if (early_poll) wait_own();
                 if (lane == 0) rec_store(gagg + (size_t)(k * G + 32 * g) * 4, compose(tile_agg, s1));
             }
             for (;;) {
@@ -841,8 +849,10 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
                 }
                 if (!__any_sync(0xffffffffu, need_a || need_b)) break;
                 if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
+                __nanosleep(100);
             }
             if (lane == 0) stamp(k, 5);
+            if (early_poll && !group_last) wait_own();
             Aff right = compose(ma, mb);
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {   // adjacent pairs first: the maps do not commute
@@ -1118,6 +1128,7 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
             if (trace_dev == nullptr) RLPPO_CUDA(cudaMalloc(&trace_dev, kTraceWords * 8));
             RLPPO_CUDA(cudaMemsetAsync(trace_dev, 0, kTraceWords * 8, s));
         }
+        static const int early_poll = getenv("RLPPO_GAE_EARLY") != nullptr ? atoi(getenv("RLPPO_GAE_EARLY")) : 0;
         static bool configured3[2] = {false, false};
         static int resident3[2] = {0, 0};
         auto launch3 = [&](auto kfn, int which) -> cudaError_t {
@@ -1137,7 +1148,7 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
             if (grid_env != nullptr && atoi(grid_env) > 0 && atoi(grid_env) < cap) cap = atoi(grid_env);
             const int grid = n_tiles3 < cap ? n_tiles3 : cap;
             kfn<<<grid, kT3, smem, s>>>(rew, done, trunc, values, n, gamma, gl32, ret_std, adv, vtarget, ret, ret_head64,
-                                       n_head, carry_in, summary_out, ws, n_tiles3, trace_dev);
+                                       n_head, carry_in, summary_out, ws, n_tiles3, trace_dev, early_poll);
             return cudaSuccess;
         };
         if (trunc_is_f64) RLPPO_CUDA(launch3(gae_scan3_kernel<true, STORE>, 1));
