@@ -105,6 +105,11 @@ class ClockSampler(threading.Thread):
 def run_cpu_oracle(wl, steps, warmup, seed=0):
     import torch
     from oracle import ref_oracle as O
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its ranks: undo that here)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     torch.manual_seed(123)
     import torch.nn as nn
 

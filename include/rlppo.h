@@ -144,6 +144,11 @@ int rlppo_linear_fwd(const uint16_t* x, int64_t ldx, const uint16_t* w, int64_t 
 int rlppo_linear_dgrad(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt,
                        const uint16_t* hprev, int64_t ldh, uint16_t* dx, int64_t lddx, int64_t M, int N,
                        int K, void* stream);
+/* The same, and db_below f32[K] += column sums of the stored dX (= the bias gradient of the layer that produced
+ * Hprev, ppo_learner.py:179-180 autograd): saves that layer's separate column-sum pass over dX. */
+int rlppo_linear_dgrad_db(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt,
+                          const uint16_t* hprev, int64_t ldh, uint16_t* dx, int64_t lddx, float* db_below,
+                          int64_t M, int N, int K, void* stream);
 /* rlppo_linear_wgrad: dW[N,K] += dY[M,N]^T * X[M,K]  (fp32, torch [out,in] layout with ld = lddw) and
  *   db[N] += column sums of dY (if db != NULL).  Split over M across the SMs; fp32 atomics. */
 int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int64_t ldx, float* dw,

@@ -45,6 +45,7 @@ _SIGS = {
     "rlppo_weight_to_bf16": ([_P, _I, _I, _P, _L, _I, _P, _L, _I, _P], _I),
     "rlppo_linear_fwd": ([_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _P], _I),
     "rlppo_linear_dgrad": ([_P, _L, _P, _L, _P, _L, _P, _L, _L, _I, _I, _P], _I),
+    "rlppo_linear_dgrad_db": ([_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P], _I),
     "rlppo_linear_wgrad": ([_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P], _I),
     "rlppo_wgrad_multi": ([_P, _I, _P], _I),
     "rlppo_policy_head_sample": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _U64, _U64, _I, _P, _P, _P, _P, _P], _I),

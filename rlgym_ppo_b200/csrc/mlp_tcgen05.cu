@@ -91,6 +91,7 @@ struct RowGemmParams {
     int relu;
     const uint16_t* mask;
     int64_t ldmask;
+    float* colsum;   // EPI_RELU_MASK: optional f32[N], += column sums of the bf16 output (= bias gradient of the layer below)
     // heads
     int n_actions;
     const float* actions;
@@ -131,22 +132,42 @@ struct SmemLayout {
 // ---------------------------------------------------------------------------------------------------------
 // epilogues (one thread = one output row; `trow` = TMEM address of that row's first accumulator column)
 // ---------------------------------------------------------------------------------------------------------
+// lane j returns sum over the 32 lanes of v[j] (v is destroyed): a 31-shuffle reduce-scatter
+__device__ __forceinline__ float warp_colsum32_rg(float (&v)[32], int lane) {
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = up ? v[i] : v[i + w];
+            const float keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return v[0];
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint32_t trow, int64_t row, int n0,
-                                                    int n_valid) {
+                                                    int n_valid, float* s_colsum, int lane) {
     const int nch = (n_valid + 31) >> 5;
     const bool row_ok = row < p.M;
+    const bool want_sum = EPI == EPI_RELU_MASK && p.colsum != nullptr;
     for (int c = 0; c < nch; ++c) {
         float v[32];
         tmem_ld32(trow + c * 32, v);
-        if (!row_ok) continue;
+        if (!row_ok && !want_sum) continue;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int col = n0 + c * 32 + g * 8;
-            if (col + 8 > p.N) continue;
             float x[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = v[g * 8 + j];
+            if (!row_ok || col + 8 > p.N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] = 0.f;
+                continue;
+            }
             if (EPI == EPI_BIAS_ACT) {
                 if (p.bias != nullptr) {
 #pragma unroll
@@ -174,6 +195,19 @@ __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint
             o.z = pack_bf16x2(x[4], x[5]);
             o.w = pack_bf16x2(x[6], x[7]);
             *reinterpret_cast<uint4*>(p.out + row * p.ldo + col) = o;
+            if (want_sum) {
+                // sum what was STORED (bf16-rounded): the same values the separate column-sum pass used to read back
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[g * 8 + 2 * j] = __uint_as_float(ow[j] << 16);
+                    v[g * 8 + 2 * j + 1] = __uint_as_float(ow[j] & 0xFFFF0000u);
+                }
+            }
+        }
+        if (want_sum) {
+            const float cs = warp_colsum32_rg(v, lane);          // lane j: column c*32+j over this warp's 32 rows
+            atomicAdd(&s_colsum[c * 32 + lane], cs);             // four row-quarter warps add into the same word
         }
     }
 }
@@ -437,6 +471,8 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (EPI == EPI_HEAD_SAMPLE || EPI == EPI_HEAD_TRAIN) {
         for (int i = threadIdx.x; i < BLOCK_N; i += kThreads)
             s_bias[i] = (i < p.n_actions && p.bias != nullptr) ? __ldg(p.bias + i) : 0.f;
+    } else if (EPI == EPI_RELU_MASK) {
+        for (int i = threadIdx.x; i < BLOCK_N; i += kThreads) s_bias[i] = 0.f;     // column-sum accumulators
     }
     tc_fence_before();
     __syncthreads();
@@ -503,7 +539,18 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int64_t row = (int64_t)m_blk * BLOCK_M + ew * 32 + lane;
             if (EPI == EPI_BIAS_ACT || EPI == EPI_RELU_MASK) {
                 const int n0 = n_blk * BLOCK_N;
-                epilogue_store_bf16<EPI>(p, trow, row, n0, min(BLOCK_N, p.N - n0));
+                epilogue_store_bf16<EPI>(p, trow, row, n0, min(BLOCK_N, p.N - n0), s_bias, lane);
+                if (EPI == EPI_RELU_MASK && p.colsum != nullptr) {
+                    // flush this tile's column sums (bias gradient of the layer below) and clear the accumulators
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    const int et = threadIdx.x - 64;                    // 0..127 over the four epilogue warps
+                    for (int j = et; j < BLOCK_N; j += 128) {
+                        const float cs = s_bias[j];
+                        s_bias[j] = 0.f;
+                        if (n0 + j < p.N && cs != 0.f) atomicAdd(p.colsum + n0 + j, cs);
+                    }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                }
             } else if (EPI == EPI_HEAD_SAMPLE) {
                 epilogue_head_sample(p, trow, row, s_bias);
             } else {
@@ -932,6 +979,19 @@ int rlppo_linear_dgrad(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int
     RowGemmParams p{};
     p.M = M; p.N = K; p.K = N;
     p.out = dx; p.ldo = lddx; p.mask = hprev; p.ldmask = ldh;
+    return launch_rowgemm<EPI_RELU_MASK>(dy, lddy, wt, ldwt, K, p, 0, static_cast<cudaStream_t>(stream));
+}
+
+int rlppo_linear_dgrad_db(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt, const uint16_t* hprev,
+                          int64_t ldh, uint16_t* dx, int64_t lddx, float* db_below, int64_t M, int N, int K,
+                          void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(dy && wt && dx, "null pointer");
+    RLPPO_CHECK_ARG(K % 8 == 0 && lddx >= K && lddx % 8 == 0, "K and lddx must be multiples of 8");
+    RLPPO_CHECK_ARG(!hprev || ldh % 8 == 0, "ldh must be a multiple of 8");
+    RowGemmParams p{};
+    p.M = M; p.N = K; p.K = N;
+    p.out = dx; p.ldo = lddx; p.mask = hprev; p.ldmask = ldh; p.colsum = db_below;
     return launch_rowgemm<EPI_RELU_MASK>(dy, lddy, wt, ldwt, K, p, 0, static_cast<cudaStream_t>(stream));
 }
 

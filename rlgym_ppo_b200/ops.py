@@ -168,11 +168,18 @@ def linear_fwd(x, wq, bias, y, N, K, relu, M=None):
          work=("flop", 2.0 * M * N * K, "byte", 2.0 * (M * K + N * K + M * N)))
 
 
-def linear_dgrad(dy, wt, hprev, dx, N, K, M=None):
+def linear_dgrad(dy, wt, hprev, dx, N, K, M=None, db_below=None):
+    """db_below (optional f32[K]): += column sums of dx, the bias gradient of the layer below (fused into the epilogue)."""
     M = dy.shape[0] if M is None else M
-    call("rlppo_linear_dgrad", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
-         0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), int(M), int(N), int(K), stream_ptr(),
-         work=("flop", 2.0 * M * N * K, "byte", 2.0 * (M * N + N * K + M * K * (2 if hprev is not None else 1))))
+    work = ("flop", 2.0 * M * N * K, "byte", 2.0 * (M * N + N * K + M * K * (2 if hprev is not None else 1)))
+    if db_below is None:
+        call("rlppo_linear_dgrad", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
+             0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), int(M), int(N), int(K), stream_ptr(),
+             work=work)
+    else:
+        call("rlppo_linear_dgrad_db", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
+             0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), ptr(db_below), int(M), int(N), int(K),
+             stream_ptr(), work=work)
 
 
 def linear_wgrad(dy, x, dw, db, N, K, M=None):

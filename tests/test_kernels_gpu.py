@@ -320,6 +320,15 @@ def test_linear_dgrad(ops, M, N, K):
     dx2 = torch.empty((M, K), dtype=torch.bfloat16, device=DEV)
     ops.linear_dgrad(dev(dy, torch.bfloat16), wt, None, dx2, N, K)
     assert rel_l2(dx2.float().cpu(), (dy.double() @ w.double()).float()) < 4e-3
+    # fused bias gradient of the layer below: += column sums of the STORED (bf16) dX, twice into the same accumulator
+    db = torch.full((K,), 0.5, device=DEV)
+    dx3 = torch.empty((M, K), dtype=torch.bfloat16, device=DEV)
+    for _ in range(2):
+        ops.linear_dgrad(dev(dy, torch.bfloat16), wt, dev(h, torch.bfloat16), dx3, N, K, db_below=db)
+    torch.cuda.synchronize()
+    assert torch.equal(dx3, dx)
+    want = 0.5 + 2.0 * dx.float().double().sum(0)
+    assert float((db.double() - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
 
 
 @pytest.mark.parametrize("M,N,K,Kp", [(300, 64, 64, 64), (1000, 256, 89, 96), (50000, 256, 256, 256),
