@@ -126,7 +126,8 @@ struct SmemLayout {
     static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
     static constexpr uint32_t BAR_OFF = kStages * STAGE;
     static constexpr uint32_t BIAS_OFF = BAR_OFF + 256;
-    static constexpr uint32_t TOTAL = BIAS_OFF + BLOCK_N * 4 + 1024;  // + slack for 1024-byte alignment
+    static constexpr uint32_t AUX_FLOATS = 4096;   // bias vector of the whole layer (EPI_BIAS_ACT) / per-tile scratch
+    static constexpr uint32_t TOTAL = BIAS_OFF + AUX_FLOATS * 4 + 1024;  // + slack for 1024-byte alignment
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -147,15 +148,43 @@ __device__ __forceinline__ float warp_colsum32_rg(float (&v)[32], int lane) {
     return v[0];
 }
 
+// The accumulator chunk and (dgrad) the ReLU-mask vectors of chunk c+1 are requested before chunk c is processed, and
+// the forward bias comes from shared memory (the whole layer's vector, loaded once per CTA): ncu on the first version
+// showed 52 % of this kernel's stall samples on the FADDs waiting for per-element __ldg(bias) / mask loads, and an
+// epilogue of ~12 us per 128x256 tile -- as long as the MMAs of a K = 1024 tile it is supposed to hide behind.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint32_t trow, int64_t row, int n0,
-                                                    int n_valid, float* s_colsum, int lane) {
+                                                    int n_valid, float* s_aux, int lane) {
     const int nch = (n_valid + 31) >> 5;
     const bool row_ok = row < p.M;
     const bool want_sum = EPI == EPI_RELU_MASK && p.colsum != nullptr;
+    const bool bias_smem = EPI == EPI_BIAS_ACT && p.bias != nullptr && p.N <= 4096;
+    const bool use_mask = EPI == EPI_RELU_MASK && p.mask != nullptr;
+    uint32_t rb[32];
+    uint4 mk_next[4];
+    auto fetch_mask = [&](int c) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int col = n0 + c * 32 + g * 8;
+            mk_next[g] = (use_mask && row_ok && col + 8 <= p.N)
+                             ? __ldg(reinterpret_cast<const uint4*>(p.mask + row * p.ldmask + col))
+                             : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    tmem_ld32_issue(trow, rb);
+    fetch_mask(0);
     for (int c = 0; c < nch; ++c) {
         float v[32];
-        tmem_ld32(trow + c * 32, v);
+        uint4 mk[4];
+        tmem_ld32_wait(rb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) mk[g] = mk_next[g];
+        if (c + 1 < nch) {
+            tmem_ld32_issue(trow + (c + 1) * 32, rb);
+            fetch_mask(c + 1);
+        }
         if (!row_ok && !want_sum) continue;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -169,7 +198,12 @@ __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint
                 continue;
             }
             if (EPI == EPI_BIAS_ACT) {
-                if (p.bias != nullptr) {
+                if (bias_smem) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(s_aux + col);
+                    const float4 b1 = *reinterpret_cast<const float4*>(s_aux + col + 4);
+                    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                } else if (p.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) x[j] += __ldg(p.bias + col + j);
                 }
@@ -178,9 +212,8 @@ __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint
                     for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
                 }
             } else {  // EPI_RELU_MASK
-                if (p.mask != nullptr) {
-                    const uint4 mk = __ldg(reinterpret_cast<const uint4*>(p.mask + row * p.ldmask + col));
-                    const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+                if (use_mask) {
+                    const uint32_t w[4] = {mk[g].x, mk[g].y, mk[g].z, mk[g].w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t bits = (w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
@@ -207,7 +240,7 @@ __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint
         }
         if (want_sum) {
             const float cs = warp_colsum32_rg(v, lane);          // lane j: column c*32+j over this warp's 32 rows
-            atomicAdd(&s_colsum[c * 32 + lane], cs);             // four row-quarter warps add into the same word
+            atomicAdd(&s_aux[c * 32 + lane], cs);                // four row-quarter warps add into the same word
         }
     }
 }
@@ -473,6 +506,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             s_bias[i] = (i < p.n_actions && p.bias != nullptr) ? __ldg(p.bias + i) : 0.f;
     } else if (EPI == EPI_RELU_MASK) {
         for (int i = threadIdx.x; i < BLOCK_N; i += kThreads) s_bias[i] = 0.f;     // column-sum accumulators
+    } else if (EPI == EPI_BIAS_ACT) {
+        if (p.bias != nullptr && p.N <= (int)L::AUX_FLOATS)                        // the whole layer's bias vector
+            for (int i = threadIdx.x; i < (int)L::AUX_FLOATS; i += kThreads) s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();

@@ -193,7 +193,7 @@ class Stack:
         # (rlppo_linear_dgrad_db).  Measured on c3: the weight-gradient calls drop 13.9 -> 11.4 ms per step but the dgrad
         # launches grow 17.5 -> 19.0 ms (their thread-per-row epilogue is not hidden behind the next tile's MMAs): a wash,
         # so it stays off until that epilogue is staged through shared memory.
-        fuse_db = getattr(self, "fuse_bias_grad_into_dgrad", False)
+        fuse_db = getattr(self, "fuse_bias_grad_into_dgrad", os.environ.get("RLPPO_FUSE_DB", "0") == "1")
         db_done = False
         for i in range(len(self.hidden) - 1, -1, -1):
             inp = ws["h"][i - 1] if i > 0 else x
