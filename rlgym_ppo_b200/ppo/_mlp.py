@@ -5,6 +5,8 @@ reference's `.model` nn.Sequential so state-dict keys and shapes are the referen
 `model.{2i}.bias`), but its parameters are VIEWS into one flat fp32 arena and their `.grad`s views into a flat
 gradient arena: the fused clip+Adam kernel and the NCCL allreduce see one contiguous buffer per learner.
 """
+import os
+
 import torch
 import torch.nn as nn
 
