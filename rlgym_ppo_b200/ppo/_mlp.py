@@ -192,10 +192,9 @@ class Stack:
         layer into the gradient arena (wgrad kernels add) and propagates through the stack."""
         d = d_last
         # fuse_db: the bias gradient of layer i-1 comes out of the dgrad epilogue that produces dL/dH_{i-1}
-        # (rlppo_linear_dgrad_db).  Measured on c3: the weight-gradient calls drop 13.9 -> 11.4 ms per step but the dgrad
-        # launches grow 17.5 -> 19.0 ms (their thread-per-row epilogue is not hidden behind the next tile's MMAs): a wash,
-        # so it stays off until that epilogue is staged through shared memory.
-        fuse_db = getattr(self, "fuse_bias_grad_into_dgrad", os.environ.get("RLPPO_FUSE_DB", "0") == "1")
+        # (rlppo_linear_dgrad_db) instead of a separate column-sum pass over that tensor.  Measured on c3 in one box:
+        # 47.3 -> 46.4 ms per step (with the first, unpipelined epilogue it was a wash).  RLPPO_FUSE_DB=0 turns it off.
+        fuse_db = getattr(self, "fuse_bias_grad_into_dgrad", os.environ.get("RLPPO_FUSE_DB", "1") == "1")
         db_done = False
         for i in range(len(self.hidden) - 1, -1, -1):
             inp = ws["h"][i - 1] if i > 0 else x
