@@ -245,7 +245,7 @@ int fused_grid(int64_t total, int* out) {
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;
     }
-    const int64_t want = (total + 2047) / 2048;
+    const int64_t want = (total + 1023) / 1024;      // four elements per thread at the small nets: short serial loops
     const int64_t cap = (int64_t)rlppo::num_sms() * per_sm;
     *out = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     return RLPPO_OK;

@@ -361,11 +361,26 @@ class Learner(object):
             vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
                                  self.gae_lambda, ret_std, out=stage["out"], ret_head64=stage["head"],
                                  ws=stage["gae_ws"])
-            if n_inc:
-                self.return_stats.increment_device(stage["head"], n_inc)   # after the scan has read std
             fields = dict(d)
             fields["values"], fields["advantages"] = vt, adv
-            buf.append_device(fields)
+            if n_inc:
+                # The Welford update (150 strictly sequential f64 steps on one thread: ~22 us of pure latency) only
+                # gates the NEXT call's scan, so it runs beside the ring appends on a second stream -- a parallel branch
+                # of the captured graph -- after the scan has read std.
+                main = torch.cuda.current_stream()
+                side = getattr(self, "_side_stream", None)
+                if side is None:
+                    side = self._side_stream = torch.cuda.Stream(device=dev)
+                fork, join = torch.cuda.Event(), torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    self.return_stats.increment_device(stage["head"], n_inc)
+                    join.record(side)
+                buf.append_device(fields)
+                main.wait_event(join)
+            else:
+                buf.append_device(fields)
 
         graphs = getattr(self, "_add_graphs", None)
         if graphs is None:
