@@ -176,8 +176,9 @@ def reference_arm(args, wl):
 KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_train_fused": "fused_mlp_kernel<1, 1>",
              "rlppo_value_train_fused": "fused_mlp_kernel<0, 1>", "rlppo_value_infer_fused": "fused_mlp_kernel<0, 0>",
              "rlppo_gather_batch": "gather_kernel", "rlppo_gae_f32": "gae_scan3_kernel<1, 1>",
-             "rlppo_linear_wgrad": "wgrad_kernel", "rlppo_linear_fwd": "rowgemm_kernel", "rlppo_linear_dgrad": "rowgemm_kernel",
-             "rlppo_clip_adam": "clip_adam_kernel"}
+             "rlppo_linear_wgrad": "wgrad_kernel<256>", "rlppo_linear_fwd": "rowgemm_kernel<256, 0>",
+             "rlppo_linear_dgrad": "rowgemm_kernel<256, 1>", "rlppo_linear_dgrad_db": "rowgemm_kernel<256, 1>",
+             "rlppo_clip_adam": "clip_adam_kernel", "rlppo_norm_clip_adam": "norm_clip_adam_kernel"}
 
 
 def bound_of(v, hbm_peak, tc_peak):

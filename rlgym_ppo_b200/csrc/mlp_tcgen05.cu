@@ -17,6 +17,8 @@
 //         split over M across all SMs, fp32 accumulation in TMEM, coalesced fp32 atomics into the grad arena.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace rlppo {
@@ -750,6 +752,7 @@ struct WLayer {
 struct WMultiParams {
     WLayer L[MAXW];
     int n_layers, total_items;
+    int dbg_nodrain;   // debug (RLPPO_WGRAD_NODRAIN=1): timing experiment, the accumulators are NOT added to dW
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -882,7 +885,7 @@ wgrad_multi_kernel(const __grid_constant__ WMaps maps, const WMultiParams p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int n = it.n0 + c * 32 + j;
-                            if (n < L.N) atomicAdd(L.dw + (int64_t)n * L.lddw + k, v[j]);
+                            if (n < L.N && !p.dbg_nodrain) atomicAdd(L.dw + (int64_t)n * L.lddw + k, v[j]);
                         }
                     }
                 }
@@ -1153,6 +1156,8 @@ int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream
         first += tiles * L.splits;
     }
     p.total_items = first;
+    static const bool nodrain = getenv("RLPPO_WGRAD_NODRAIN") != nullptr;
+    p.dbg_nodrain = nodrain ? 1 : 0;
     constexpr uint32_t SMEM = 3 * 8 * 8192 + 256 + 1024;
     static bool configured = false;
     if (!configured) {

@@ -53,6 +53,17 @@ if has launches_c3; then
   python tools/summarize_launches.py $O/${TAG}_launches_c3.csv > $O/${TAG}_launches_c3.md 2>&1
   cat $O/${TAG}_launches_c3.md
 fi
+if has traffic_c3; then
+  # DRAM traffic of EVERY GEMM launch of one c3 iteration (light sections only: ~230 launches)
+  timeout 1500 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --clock-control none \
+      --profile-from-start off -f -o $O/${TAG}_traffic_c3 -k regex:'rowgemm|wgrad|colsum|norm_clip' \
+      python tools/ncu_step.py --workload c3 > $O/${TAG}_traffic_c3.log 2>&1
+  tail -2 $O/${TAG}_traffic_c3.log
+fi
+if has gather; then
+  timeout 300 python tools/gather_sweep.py > $O/${TAG}_gather_sweep.jsonl 2> $O/${TAG}_gather_sweep.err
+  cat $O/${TAG}_gather_sweep.jsonl
+fi
 if has full_c3; then
   timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o $O/${TAG}_full_c3 \
       -k regex:'rowgemm|wgrad' -c 12 python tools/ncu_step.py --workload c3 > $O/${TAG}_full_c3.log 2>&1

@@ -14,7 +14,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+SCALE = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
 def main():
@@ -28,8 +28,16 @@ def main():
         name = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("void ", "").replace("<unnamed>::", "")
         name = re.sub(r"\(bool\)|\(int\)", "", name)
         tot = 0.0
-        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += float(r[ix[m]].replace(",", "")) * SCALE[units[ix[m]]]
+        if "dram__bytes_read.sum" in ix:
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[ix[m]].replace(",", "")) * SCALE[units[ix[m]]]
+        else:
+            # light section sets carry the rate only: bytes = dram__bytes.sum.per_second x duration
+            rate_u = units[ix["dram__bytes.sum.per_second"]].split("/")[0]
+            rate = float(r[ix["dram__bytes.sum.per_second"]].replace(",", "")) * SCALE[rate_u]
+            dur_u = units[ix["gpu__time_duration.sum"]]
+            dur = float(r[ix["gpu__time_duration.sum"]].replace(",", "")) * {"s": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9}[dur_u]
+            tot = rate * dur
         grid = r[ix["Grid Size"]]
         a = acc.setdefault(name, [0, 0.0, 0.0])
         # keep the largest-grid launches of a name (the small warm-up launches of the same kernel are not the bench's)
