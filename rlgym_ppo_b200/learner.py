@@ -333,8 +333,24 @@ class Learner(object):
             stage["head"] = torch.empty(n_inc, dtype=torch.float64, device=dev) if n_inc else None
             stage["gae_ws"] = ops.gae_workspace(n, dev)
             self._exp_stage = stage
+        # next_states arriving from the HOST take the late path: nothing on the learner path reads that ring (only its last
+        # row feeds the value net, learner.py:349), so the 17.8 MB block -- half of the PCIe traffic of an example-size
+        # iteration -- is copied and appended on a second stream while this call's device work and the whole of
+        # PPOLearner.learn run; only the last row crosses on the main stream.  Readers (the `next_states` attribute, the
+        # next call) wait for it through ExperienceBuffer.sync_late().
+        ns_in = experience[4]
+        late_ns = (not (isinstance(ns_in, torch.Tensor) and ns_in.is_cuda) and n >= 2
+                   and os.environ.get("RLPPO_LATE_NEXT_STATES", "1") == "1")
+        buf.sync_late()      # the previous call's late block is in its ring (and out of its staging slot) before we go on
         d, ptrs = {}, []
         for name, arr, (shape, dt) in zip(_EXP_FIELDS, experience, shapes):
+            if name == "next_states" and late_ns:
+                if "ns_last" not in stage:
+                    stage["ns_last"] = torch.empty((1, shape[1]), dtype=dt, device=dev)
+                    stage[name] = torch.empty(shape, dtype=dt, device=dev)
+                d["ns_last"] = stager.to_device(arr[n - 1:n], "exp.ns_last", out=stage["ns_last"])
+                ptrs.append(d["ns_last"].data_ptr())
+                continue
             if isinstance(arr, torch.Tensor) and arr.is_cuda and arr.dtype == dt and arr.is_contiguous():
                 d[name] = arr
             else:
@@ -342,6 +358,14 @@ class Learner(object):
                     stage[name] = torch.empty(shape, dtype=dt, device=dev)
                 d[name] = stager.to_device(arr, "exp." + name, out=stage[name])
             ptrs.append(d[name].data_ptr())
+        if late_ns:
+            late = getattr(self, "_late_stream", None)
+            if late is None:
+                late = self._late_stream = torch.cuda.Stream(device=dev)
+            late.wait_stream(torch.cuda.current_stream())     # after whatever the main stream still has queued on these blocks
+            with torch.cuda.stream(late):
+                ns_dev = stager.to_device(ns_in, "exp.next_states", out=stage["next_states"])
+            stage["next_states"].record_stream(late)
         obs = int(d["states"].shape[1])
         if buf._rings is None:
             buf._allocate(obs)
@@ -356,12 +380,12 @@ class Learner(object):
             states = _f32(d["states"])
             x = vst.workspace(n + 1)["x"]
             ops.rows_to_bf16(states, x)
-            ops.rows_to_bf16(_f32(d["next_states"])[n - 1:n], x[n:n + 1])
+            ops.rows_to_bf16(_f32(d["ns_last"]) if late_ns else _f32(d["next_states"])[n - 1:n], x[n:n + 1])
             values = value_net.values_from_bf16(x, n + 1, out=stage["values"])      # stays on the device
             vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
                                  self.gae_lambda, ret_std, out=stage["out"], ret_head64=stage["head"],
                                  ws=stage["gae_ws"])
-            fields = dict(d)
+            fields = {k: v for k, v in d.items() if k != "ns_last"}
             fields["values"], fields["advantages"] = vt, adv
             if n_inc:
                 # The Welford update (150 strictly sequential f64 steps on one thread: ~22 us of pure latency) only
@@ -385,10 +409,12 @@ class Learner(object):
         graphs = getattr(self, "_add_graphs", None)
         if graphs is None:
             graphs = self._add_graphs = GraphCache()
-        key = (n, obs, stage["gen"], tuple(ptrs), buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
+        key = (n, obs, stage["gen"], tuple(ptrs), late_ns, buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
                float(self.gae_gamma), float(self.gae_lambda), bool(self.standardize_returns), vst.fused_ok)
         if not (getattr(ppo, "use_cuda_graph", False) and _lib._TIMING is None and graphs.replay(key, body)):
             body()
+        if late_ns:
+            buf.append_next_states_late(ns_dev, late)      # position from the host mirrors, BEFORE they advance
         # host mirrors of what the device work did
         buf.advance_host(min(n, buf.capacity))
         if n_inc:

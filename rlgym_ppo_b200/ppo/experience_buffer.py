@@ -87,7 +87,17 @@ class ExperienceBuffer(object):
         """Physical ring tensor of a field (row i of it is NOT logical row i; see `start`)."""
         return self._rings[field]
 
+    def sync_late(self):
+        """Make the current stream wait for a `next_states` block that Learner.add_new_experience is still copying /
+        appending on its late stream (nothing on the learner path reads that ring; see learner.py)."""
+        ev = getattr(self, "_late_ev", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._late_ev = None
+
     def _logical(self, field):
+        if field == "next_states":
+            self.sync_late()
         if self._rings is None:
             return torch.empty(0, dtype=torch.float32, device=self.device)
         r = self._rings[field]
@@ -104,6 +114,7 @@ class ExperienceBuffer(object):
                           advantages):
         new = dict(zip(FIELDS, (states, actions, log_probs, rewards, next_states, dones, truncated, values,
                                 advantages)))
+        self.sync_late()
         if self._rings is None:
             st = states
             obs_dim = st.shape[1] if hasattr(st, "shape") and len(st.shape) == 2 else np.asarray(st).shape[1]
@@ -123,6 +134,8 @@ class ExperienceBuffer(object):
         mirrors it on the host with advance_host()."""
         n = int(dev["rewards"].shape[0])
         for f in FIELDS:
+            if f == "next_states" and f not in dev:
+                continue        # appended separately by the caller (append_next_states_late)
             assert int(dev[f].shape[0]) == n, f"field {f} has {dev[f].shape[0]} rows, expected {n}"
         if n == 0:
             return 0
@@ -130,9 +143,23 @@ class ExperienceBuffer(object):
         skip = max(0, n - cap)          # `_cat`: when the new block alone exceeds max_size keep its tail
         rows = n - skip
         fields = [(self._rings[f], (dev[f][skip:] if skip else dev[f]),
-                   self.states_bf16 if f == "states" else None) for f in FIELDS]
+                   self.states_bf16 if f == "states" else None) for f in FIELDS if f in dev]
         ops.ring_append_fields(fields, cap, 0, rows, state_dev=self.state_dev)
         return rows
+
+    def append_next_states_late(self, src, stream):
+        """Append `src` [n, obs] to the next_states ring on `stream`, at the position the NEXT append_device will use --
+        call it BEFORE advance_host.  The position comes from the host mirrors (same arithmetic as the device state)."""
+        n = int(src.shape[0])
+        cap = self.capacity
+        skip = max(0, n - cap)
+        rows = n - skip
+        pos = (self.start + self.size) % cap
+        with torch.cuda.stream(stream):
+            ops.ring_append(self._rings["next_states"], pos, src[skip:] if skip else src, rows)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._late_ev = ev
 
     def advance_host(self, rows):
         """Host mirror of the device-side ring advance (the arithmetic of `_cat`, experience_buffer.py:17-37): rows were

@@ -7,6 +7,7 @@ value predictions; losses, gradients and weights 1e-3 scale-aware -- stated for 
 accumulation: a bf16 operand carries 2^-9 relative rounding, so per-tensor gradient rel-L2 is checked at 1e-2
 against the fp32 reference and at 2e-3 against the oracle evaluated with the same bf16 rounding points.
 """
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -597,3 +598,50 @@ def test_c4_shape_inference_over_4096_slots_and_slot_major_gae(pkg):
                               torch.tensor([std], device=DEV))
     for a, b in ((adv1, adv[sl]), (ret1, ret[sl]), (vt1, vt[sl])):      # same values up to the scan's association
         assert float(((a - b).abs() / b.abs().clamp(min=1.0)).max()) <= 1e-6
+
+
+def test_late_next_states_path_matches_fifo_oracle(pkg):
+    """Host rollouts: next_states crosses PCIe and enters its ring on a second stream while the rest of the iteration
+    runs (learner.py, ExperienceBuffer.append_next_states_late).  Five iterations of 700 steps into a 2048-row buffer
+    (wraps around, numpy / pinned / device inputs mixed, graph capture on the way): every ring -- next_states included --
+    equals the reference's FIFO (`_cat`, experience_buffer.py:17-37) bit for bit, and so does RLPPO_LATE_NEXT_STATES=0."""
+    import contextlib
+    import io
+    from rlgym_ppo_b200.learner import Learner
+    from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
+    from rlgym_ppo_b200.util import WelfordRunningStat
+    obs, act, n, cap = 89, 90, 700, 2048
+    results = []
+    for late in ("1", "0"):
+        os.environ["RLPPO_LATE_NEXT_STATES"] = late
+        try:
+            torch.manual_seed(3)
+            with contextlib.redirect_stdout(io.StringIO()):
+                ppo = PPOLearner(obs, act, 0, (64, 64), (64, 64), (0.1, 1.0), 512, 1, 3e-4, 3e-4, 0.2, 0.01, 512, DEV)
+            ns = SimpleNamespace(ppo_learner=ppo, return_stats=WelfordRunningStat(1, device=DEV), standardize_returns=True,
+                                 gae_gamma=0.99, gae_lambda=0.95, max_returns_per_stats_increment=150,
+                                 experience_buffer=ExperienceBuffer(cap, 123, DEV))
+            rng = np.random.RandomState(9)
+            want = {k: np.zeros((0, obs), np.float32) for k in ("states", "next_states")}
+            want["rewards"] = np.zeros(0, np.float32)
+            for it in range(5):
+                exp = [rng.randn(n, obs).astype(np.float32), rng.randint(0, act, n).astype(np.float32),
+                       (-4.5 + 0.1 * rng.randn(n)).astype(np.float32), rng.randn(n).astype(np.float32),
+                       rng.randn(n, obs).astype(np.float32), (rng.rand(n) < 0.01).astype(np.float32), np.zeros(n, np.float64)]
+                want["states"] = O.fifo_cat(want["states"], exp[0], cap)
+                want["next_states"] = O.fifo_cat(want["next_states"], exp[4], cap)
+                want["rewards"] = O.fifo_cat(want["rewards"], exp[3], cap)
+                if it % 3 == 1:
+                    exp = [torch.from_numpy(a).pin_memory() for a in exp]
+                elif it == 3:
+                    exp = [torch.from_numpy(a).to(DEV) for a in exp]
+                Learner.add_new_experience(ns, tuple(exp))
+                ppo.learn(ns.experience_buffer)
+            buf = ns.experience_buffer
+            got = {k: getattr(buf, k).cpu().numpy() for k in want}
+            for k in want:
+                assert np.array_equal(got[k], np.asarray(want[k])), (late, k)
+            results.append((ppo._params.clone(), got))
+        finally:
+            os.environ.pop("RLPPO_LATE_NEXT_STATES", None)
+    assert np.array_equal(results[0][1]["next_states"], results[1][1]["next_states"])
