@@ -247,22 +247,10 @@ gae_scan_kernel(const float* __restrict__ rew, const float* __restrict__ done, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// v2 (16-byte aligned arrays): the same scan with the tile's inputs staged in shared memory by bulk async copies.
-//
-// ncu on v1 at 2^28 steps: 98 registers x 512 threads = ONE resident CTA per SM; every tile paid ticket -> load ->
-// scan -> look-back -> store back to back: 1.0 TB/s algorithmic (16 % of the measured copy bandwidth).
-// Here one thread issues four cp.async.bulk copies for the tile (2048 steps, 40 KB with f64 truncated flags) the moment
-// the tile is known, nothing input-related lives in registers across the look-back (the per-step maps are recomputed from
-// shared memory when the carry arrives), and 256 threads x <= 64 registers let four CTAs share an SM: their loads,
-// look-backs and stores overlap.  The look-back composes each 32-tile window with a shuffle scan (5 rounds) instead of
-// a serial loop over up to 32 predecessors.
+// History -- v2 (removed; see profiles/README_r01.md): the same scan with the tile's inputs staged in shared memory by bulk
+// async copies, one 2048-step tile per CTA, 4 CTAs/SM: 3.0 TB/s at 2^28 steps, latency-bound (every tile still paid
+// ticket -> loads -> look-back -> stores back to back).  The helpers below are what v3 kept from it.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kT2 = 256;
-constexpr int kI2 = 8;
-constexpr int kTile2 = kT2 * kI2;   // 2048 steps per CTA, = kTile: both kernels share the workspace layout
-constexpr int kW2 = kT2 / 32;
-static_assert(kTile2 == kTile, "workspace layout is shared between the two scan kernels");
-
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -270,11 +258,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  "l"(gsrc), "r"(bytes), "r"(smem_addr_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ Aff shfl_up(const Aff& x, int off) {
-    return Aff{__shfl_up_sync(0xffffffffu, x.aA, off), __shfl_up_sync(0xffffffffu, x.bA, off),
-               __shfl_up_sync(0xffffffffu, x.aR, off), __shfl_up_sync(0xffffffffu, x.bR, off)};
-}
-
 // Tile records without flags or fences: a record (aggregate or inclusive map, 4 doubles) is written with two 16-byte
 // relaxed gpu-scope vector stores and polled with two relaxed gpu-scope vector loads.  The workspace is pre-set to
 // all-ones bytes -- a NaN pattern no computation produces -- and a record counts as arrived when none of its four
@@ -299,7 +282,7 @@ template <bool TRUNC64>
 struct StepMaps {
     const float* r;
     const float* d;
-    const float* v;   // kTile2 + 1 entries
+    const float* v;   // tile + 1 entries (halo = V of the next row)
     const void* t;
     double gamma, gl64;   // gl64 = (double)gl32
     float gl32, stdv;
@@ -328,307 +311,6 @@ struct StepMaps {
     }
     __device__ __forceinline__ float delta(int j) const { return delta_of(r[j], d[j], v[j], v[j + 1]); }
 };
-
-// 8 consecutive floats of a thread (32 bytes, 16-byte aligned) as two 128-bit shared-memory accesses.  Scalar accesses
-// at this stride put the 32 lanes of a warp on 4 banks (8-way conflict: ncu showed 84 % of v2's shared-memory
-// wavefronts were conflict replays and the L1/shared pipe 96 % busy); 128-bit accesses at a 32-byte stride are 2-way.
-__device__ __forceinline__ void lds8(const float* p, float (&x)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *reinterpret_cast<const float4*>(p + 4);
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-}
-__device__ __forceinline__ void sts8(float* p, const float (&x)[8]) {
-    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
-}
-
-template <bool TRUNC64, bool STORE>
-__global__ void __launch_bounds__(kT2, 4)
-gae_scan2_kernel(const float* __restrict__ rew, const float* __restrict__ done, const void* __restrict__ trunc,
-                 const float* __restrict__ val, int64_t n, double gamma, float gl32,
-                 const float* __restrict__ ret_std, float* __restrict__ adv, float* __restrict__ vt,
-                 float* __restrict__ ret, double* __restrict__ ret_head, int64_t n_head,
-                 const double* __restrict__ carry_in, double* __restrict__ summary_out, Workspace ws, int n_tiles) {
-    extern __shared__ __align__(16) uint8_t sm2[];
-    float* s_r = reinterpret_cast<float*>(sm2);
-    float* s_d = s_r + kTile2;
-    float* s_v = s_d + kTile2;                                  // kTile2 + 4 floats (halo + padding to 16 bytes)
-    float* s_delta = s_v + kTile2 + 4;                          // delta_j, formed once in phase A
-    void* s_t = s_delta + kTile2;
-    __shared__ uint64_t s_bar;
-    __shared__ int s_tile;
-    __shared__ double s_warp[kW2][4];
-    __shared__ double s_agg[4];
-    __shared__ double s_win[kW2][4];
-    __shared__ int s_winflag[kW2];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        s_tile = atomicAdd(ws.counter, 1);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&s_bar)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int tile = s_tile;
-    const int chunk = n_tiles - 1 - tile;
-    const int64_t base0 = (int64_t)chunk * kTile2;
-    const int cnt = (int)((n - base0) < (int64_t)kTile2 ? (n - base0) : (int64_t)kTile2);
-    const bool full = cnt == kTile2;
-    constexpr uint32_t kTB = TRUNC64 ? 8u : 4u;
-    if (full) {
-        if (tid == 0) {
-            const uint32_t total = 3u * kTile2 * 4u + kTile2 * kTB;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&s_bar)), "r"(total)
-                         : "memory");
-            bulk_g2s(s_r, rew + base0, kTile2 * 4u, &s_bar);
-            bulk_g2s(s_d, done + base0, kTile2 * 4u, &s_bar);
-            bulk_g2s(s_v, val + base0, kTile2 * 4u, &s_bar);
-            bulk_g2s(s_t, static_cast<const uint8_t*>(trunc) + base0 * kTB, kTile2 * kTB, &s_bar);
-            s_v[kTile2] = __ldg(val + base0 + kTile2);          // values has n + 1 entries
-        }
-        // wait for the four copies (parity 0: the barrier is used once)
-        uint32_t ok = 0;
-        while (!ok) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok)
-                : "r"(smem_addr_u32(&s_bar))
-                : "memory");
-        }
-    } else {
-        // ragged tile (the right end of the rollout, tile 0): plain loads; steps past the end are identity maps
-        for (int j = tid; j < kTile2; j += kT2) {
-            const bool okj = j < cnt;
-            s_r[j] = okj ? __ldg(rew + base0 + j) : 0.f;
-            s_d[j] = okj ? __ldg(done + base0 + j) : 0.f;
-            s_v[j] = (j <= cnt) ? __ldg(val + base0 + j) : 0.f;
-            if (TRUNC64) static_cast<double*>(s_t)[j] = okj ? __ldg(static_cast<const double*>(trunc) + base0 + j) : 0.0;
-            else static_cast<float*>(s_t)[j] = okj ? __ldg(static_cast<const float*>(trunc) + base0 + j) : 0.f;
-        }
-        if (tid == 0) s_v[kTile2] = 0.f;
-    }
-    __syncthreads();
-
-    StepMaps<TRUNC64> sm;
-    sm.r = s_r; sm.d = s_d; sm.v = s_v; sm.t = s_t;
-    sm.gamma = gamma; sm.gl32 = gl32; sm.gl64 = (double)gl32;
-    sm.has_std = ret_std != nullptr;
-    sm.stdv = sm.has_std ? __ldg(ret_std) : 1.f;
-
-    // ---- phase A: thread aggregate over its 8 consecutive steps, warp scan, block scan ----
-    const int j0 = tid * kI2;
-    // Flags first.  `live` bit i: step j0+i has done == +0 and truncated == +0 (the recurrence continues through it);
-    // `fast`: every flag of this thread is exactly +0 or 1 -- what the collector produces -- so a multiplier is either
-    // 0 or the constant gamma*lambda / gamma and needs no arithmetic.  Anything else (and the ragged tile) takes the
-    // generic path, which evaluates the reference's expressions as written.
-    uint32_t live = 0;
-    bool fast = full;
-    float dflt[kI2];
-    lds8(s_d + j0, dflt);
-    {
-        uint32_t dz = 0, bad = 0;
-#pragma unroll
-        for (int i = 0; i < kI2; ++i) {
-            const uint32_t b = __float_as_uint(dflt[i]);
-            dz |= (b == 0u ? 1u : 0u) << i;
-            bad |= (b != 0u && b != 0x3F800000u) ? 1u : 0u;
-        }
-        uint32_t tz = 0;
-        if (TRUNC64) {
-            const uint4* tp = reinterpret_cast<const uint4*>(static_cast<const double*>(s_t) + j0);
-#pragma unroll
-            for (int q = 0; q < kI2 / 2; ++q) {
-                const uint4 w = tp[q];   // two doubles: (x = lo0, y = hi0, z = lo1, w = hi1)
-                tz |= ((w.x | w.y) == 0u ? 1u : 0u) << (2 * q);
-                tz |= ((w.z | w.w) == 0u ? 1u : 0u) << (2 * q + 1);
-                bad |= ((w.x | w.y) != 0u && !(w.x == 0u && w.y == 0x3FF00000u)) ? 1u : 0u;
-                bad |= ((w.z | w.w) != 0u && !(w.z == 0u && w.w == 0x3FF00000u)) ? 1u : 0u;
-            }
-        } else {
-            float tf[kI2];
-            lds8(static_cast<const float*>(s_t) + j0, tf);
-#pragma unroll
-            for (int i = 0; i < kI2; ++i) {
-                const uint32_t b = __float_as_uint(tf[i]);
-                tz |= (b == 0u ? 1u : 0u) << i;
-                bad |= (b != 0u && b != 0x3F800000u) ? 1u : 0u;
-            }
-        }
-        live = dz & tz;
-        fast = fast && bad == 0u;
-    }
-    Aff agg = aff_identity();
-    if (fast) {
-        float rr[kI2], vv[kI2], dl[kI2];
-        lds8(s_r + j0, rr);
-        lds8(s_v + j0, vv);
-        float vnext = s_v[j0 + kI2];
-#pragma unroll
-        for (int i = kI2 - 1; i >= 0; --i) {
-            dl[i] = sm.delta_of(rr[i], dflt[i], vv[i], vnext);
-            vnext = vv[i];
-            const bool lv = (live >> i) & 1u;
-            const double aA = lv ? sm.gl64 : 0.0;
-            const double aR = lv ? gamma : 0.0;
-            agg = Aff{aA * agg.aA, fma(aA, agg.bA, (double)dl[i]), aR * agg.aR, fma(aR, agg.bR, (double)rr[i])};
-        }
-        sts8(s_delta + j0, dl);            // read back by this same thread in phase B
-    } else {
-#pragma unroll 1
-        for (int i = kI2 - 1; i >= 0; --i)
-            if (j0 + i < cnt) {
-                Aff f;
-                sm.mults(j0 + i, f.aA, f.aR);
-                const float dl = sm.delta(j0 + i);
-                s_delta[j0 + i] = dl;
-                f.bA = (double)dl;
-                f.bR = (double)s_r[j0 + i];
-                agg = compose(f, agg);
-            }
-    }
-    const Aff incl_w = warp_suffix_scan(agg, lane);
-    Aff excl = shfl_down(incl_w, 1);
-    if (lane == 31) excl = aff_identity();
-    if (lane == 0) {
-        s_warp[warp][0] = incl_w.aA; s_warp[warp][1] = incl_w.bA;
-        s_warp[warp][2] = incl_w.aR; s_warp[warp][3] = incl_w.bR;
-    }
-    __syncthreads();
-
-    if (warp == 0) {
-        Aff w = aff_identity();
-        if (lane < kW2) w = Aff{s_warp[lane][0], s_warp[lane][1], s_warp[lane][2], s_warp[lane][3]};
-        const Aff wi = warp_suffix_scan(w, lane);       // lanes >= kW2 hold identities
-        Aff we = shfl_down(wi, 1);                      // exclusive: warps to the right of `lane`
-        if (lane == 31) we = aff_identity();
-        if (lane < kW2) {
-            s_warp[lane][0] = we.aA; s_warp[lane][1] = we.bA; s_warp[lane][2] = we.aR; s_warp[lane][3] = we.bR;
-        }
-        if (lane == 0) {
-            s_agg[0] = wi.aA; s_agg[1] = wi.bA; s_agg[2] = wi.aR; s_agg[3] = wi.bR;   // the tile's own map
-            if (tile > 0) rec_store(ws.agg + (size_t)tile * 4, wi);
-        }
-    }
-    __syncthreads();
-
-    // ---- decoupled look-back, ALL warps: warp w inspects tiles tile-1-32w-lane (256 tiles per round) ----
-    // The chain of inclusive prefixes advances by one look-back round per (poll + load + scan) latency; with one warp it
-    // moved 32 tiles = 65 k steps per ~1 us, which capped v2's first version at 55 G steps/s whatever the memory system did.
-    Aff right = aff_identity();
-    if (tile > 0) {
-        int look = tile - 1;
-        for (;;) {
-            const int j = look - (warp * 32 + lane);    // lane 0 of warp 0 = the nearest tile to the right
-            int st = 2;
-            Aff m = aff_identity();                     // j < 0: nothing to the right of tile 0
-            if (j >= 0) {
-                const long long t0 = clock64();
-                for (;;) {
-                    if (rec_load(ws.incl + (size_t)j * 4, m)) {
-                        st = 2;
-                        break;
-                    }
-                    if (rec_load(ws.agg + (size_t)j * 4, m)) {
-                        st = 1;
-                        break;
-                    }
-                    if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s)
-                }
-            }
-            const unsigned done_mask = __ballot_sync(0xffffffffu, st == 2);
-            const int upto = done_mask ? (__ffs(done_mask) - 1) : 31;
-            if (lane > upto) m = aff_identity();
-            // inclusive prefix over lanes, lower lane = outer map: lane l ends with m_0 o m_1 o ... o m_l
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const Aff y = shfl_up(m, off);
-                if (lane >= off) m = compose(y, m);
-            }
-            if (lane == 31) {
-                s_win[warp][0] = m.aA; s_win[warp][1] = m.bA; s_win[warp][2] = m.aR; s_win[warp][3] = m.bR;
-                s_winflag[warp] = done_mask != 0 ? 1 : 0;
-            }
-            __syncthreads();
-            bool finished = false;
-#pragma unroll
-            for (int w = 0; w < kW2; ++w) {
-                if (!finished) {
-                    right = compose(right, Aff{s_win[w][0], s_win[w][1], s_win[w][2], s_win[w][3]});
-                    finished = s_winflag[w] != 0;
-                }
-            }
-            __syncthreads();   // s_win is rewritten in the next round
-            if (finished) break;
-            look -= kT2;
-        }
-    }
-    if (tid == 0) {
-        const Aff tile_agg = Aff{s_agg[0], s_agg[1], s_agg[2], s_agg[3]};
-        const Aff incl = compose(tile_agg, right);
-        rec_store(ws.incl + (size_t)tile * 4, incl);
-        if (summary_out != nullptr && tile == n_tiles - 1) {
-            summary_out[0] = incl.aA; summary_out[1] = incl.bA;
-            summary_out[2] = incl.aR; summary_out[3] = incl.bR;
-        }
-    }
-    if (!STORE) return;
-    // every thread holds `right`: the values just right of this tile
-    const double cA = carry_in ? carry_in[0] : 0.0;
-    const double cR = carry_in ? carry_in[1] : 0.0;
-    const double carryA = fma(right.aA, cA, right.bA);
-    const double carryR = fma(right.aR, cR, right.bR);
-
-    // ---- phase B: values just right of this thread's steps, then the per-step maps again ----
-    const Aff wr = Aff{s_warp[warp][0], s_warp[warp][1], s_warp[warp][2], s_warp[warp][3]};
-    const Aff e = compose(excl, wr);
-    double xA = fma(e.aA, carryA, e.bA);
-    double xR = fma(e.aR, carryR, e.bR);
-    const int64_t gbase = base0 + j0;
-    if (fast) {
-        float dl[kI2], rr[kI2], vv[kI2];
-        lds8(s_delta + j0, dl);
-        lds8(s_r + j0, rr);
-        lds8(s_v + j0, vv);
-        const bool head = ret_head != nullptr && gbase < n_head;
-        float oa[kI2], ov[kI2], orr[kI2];
-#pragma unroll
-        for (int i = kI2 - 1; i >= 0; --i) {
-            const bool lv = (live >> i) & 1u;
-            xA = fma(lv ? sm.gl64 : 0.0, xA, (double)dl[i]);
-            xR = fma(lv ? gamma : 0.0, xR, (double)rr[i]);
-            if (head && gbase + i < n_head) ret_head[gbase + i] = xR;
-            oa[i] = (float)xA;                              // :76
-            ov[i] = (float)((double)vv[i] + xA);            // :77
-            orr[i] = (float)xR;
-        }
-        float4* pa = reinterpret_cast<float4*>(adv + gbase);
-        float4* pv = reinterpret_cast<float4*>(vt + gbase);
-        float4* pr = reinterpret_cast<float4*>(ret + gbase);
-        pa[0] = make_float4(oa[0], oa[1], oa[2], oa[3]);
-        pa[1] = make_float4(oa[4], oa[5], oa[6], oa[7]);
-        pv[0] = make_float4(ov[0], ov[1], ov[2], ov[3]);
-        pv[1] = make_float4(ov[4], ov[5], ov[6], ov[7]);
-        pr[0] = make_float4(orr[0], orr[1], orr[2], orr[3]);
-        pr[1] = make_float4(orr[4], orr[5], orr[6], orr[7]);
-    } else {
-#pragma unroll 1
-        for (int i = kI2 - 1; i >= 0; --i) {
-            if (j0 + i < cnt) {
-                double aA, aR;
-                sm.mults(j0 + i, aA, aR);
-                xA = fma(aA, xA, (double)s_delta[j0 + i]);
-                xR = fma(aR, xR, (double)s_r[j0 + i]);
-                if (ret_head != nullptr && gbase + i < n_head) ret_head[gbase + i] = xR;
-                adv[gbase + i] = (float)xA;                              // :76
-                vt[gbase + i] = (float)((double)s_v[j0 + i] + xA);       // :77
-                ret[gbase + i] = (float)xR;
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // v3: persistent, software-pipelined scan.
@@ -1113,8 +795,7 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
     gae_scan_kernel<T64, V, STORE><<<n_tiles, kThreads, 0, s>>>(rew, done, trunc, values, n, gamma, gl32, \
                                                                 ret_std, adv, vtarget, ret, ret_head64,  \
                                                                 n_head, carry_in, summary_out, ws, n_tiles)
-    static const bool use_v2 = getenv("RLPPO_GAE_V2") != nullptr;     // A/B switch for the previous staged kernel
-    if (vec && !use_v2) {
+    if (vec) {
         // persistent pipelined kernel (v3): 1024-step tiles, records pre-set to the all-ones sentinel
         const int n_tiles3 = (int)((n + kTile3 - 1) / kTile3);
         const size_t smem = (size_t)kStages3 * stage_bytes3(trunc_is_f64 != 0);
@@ -1166,26 +847,6 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
                 fclose(f);
             }
         }
-    } else if (vec) {
-        // staged kernel: r, done, V (+ halo), delta as f32 + the truncated flags; records pre-set to the all-ones sentinel
-        const size_t smem = (size_t)(4 * kTile2 + 4) * 4 + (size_t)kTile2 * (trunc_is_f64 ? 8 : 4);
-        RLPPO_CUDA(cudaMemsetAsync(base + L.agg_off, 0xFF, L.total - L.agg_off, s));
-        // > 48 KB of dynamic shared memory needs the opt-in once PER KERNEL (both instantiations share one function-pointer
-        // type, so the flag is indexed by the instantiation, not kept in a generic lambda)
-        static bool configured[2] = {false, false};
-        auto launch2 = [&](auto kfn, int which) -> cudaError_t {
-            if (!configured[which]) {
-                cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     (int)((4 * kTile2 + 4) * 4 + kTile2 * 8));
-                if (e != cudaSuccess) return e;
-                configured[which] = true;
-            }
-            kfn<<<n_tiles, kT2, smem, s>>>(rew, done, trunc, values, n, gamma, gl32, ret_std, adv, vtarget, ret, ret_head64,
-                                          n_head, carry_in, summary_out, ws, n_tiles);
-            return cudaSuccess;
-        };
-        if (trunc_is_f64) RLPPO_CUDA(launch2(gae_scan2_kernel<true, STORE>, 1));
-        else RLPPO_CUDA(launch2(gae_scan2_kernel<false, STORE>, 0));
     } else if (trunc_is_f64) {
         RLPPO_GAE_LAUNCH(true, false);
     } else {
