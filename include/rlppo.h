@@ -281,6 +281,21 @@ int rlppo_norm_clip_adam(float* params, const float* grads, float* m, float* v, 
                          int n_seg, float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm,
                          double beta1, double beta2, double eps, const rlppo_bf16_view* h_views, int n_views,
                          void* ws, size_t ws_bytes, void* stream);
+/* Data-parallel form of rlppo_norm_clip_adam: the gradient all-reduce of the reference-equivalent accumulation
+ * (ppo_learner.py:134-193 sums (mb/B)-scaled minibatch gradients before ONE clip + Adam step; here the minibatch slices
+ * live on `world` GPUs of one box) is done INSIDE the launch over NVLink peer mappings -- no separate collective.
+ * h_peer_grads[r] / h_peer_flags[r]: rank r's gradient arena (f32[total]) and flag block (rlppo_peer_flag_bytes() bytes,
+ * zeroed once by its owner before the first launch) as mapped into THIS process (e.g. torch symmetric memory
+ * buffer_ptrs); entry `rank` is the local one.  gsum: local f32[total] scratch that receives the summed gradient (rank
+ * order 0..world-1 on every rank: replicas stay bit-identical).  Every rank must make the same sequence of calls; the
+ * launch ends only after all peers have finished reading this rank's arena, so the caller may overwrite it right after.
+ * A peer that never arrives traps the kernel after ~30 s instead of hanging.  world <= 8.  Other arguments as above. */
+size_t rlppo_peer_flag_bytes(void);
+int rlppo_norm_clip_adam_peers(float* params, const float* const* h_peer_grads, void* const* h_peer_flags, int rank,
+                               int world, float* gsum, float* m, float* v, const int64_t* h_seg_off, int n_seg,
+                               float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm, double beta1,
+                               double beta2, double eps, const rlppo_bf16_view* h_views, int n_views, void* ws,
+                               size_t ws_bytes, void* stream);
 /* out f32[n_seg] = per-segment sum (a-b)^2 (update magnitudes, ppo_learner.py:212-220). */
 int rlppo_sqdiff(const float* a, const float* b, const int64_t* h_seg_off, int n_seg, float* out,
                  void* stream);

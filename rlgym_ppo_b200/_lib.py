@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librlppo_b200.so")
+# RLPPO_LIB_PATH: another build of the same library (kernel A/B runs inside one GPU session); never a fallback
+LIB_PATH = os.environ.get("RLPPO_LIB_PATH") or os.path.join(_HERE, "librlppo_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -59,6 +60,9 @@ _SIGS = {
     "rlppo_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P], _I),
     "rlppo_norm_clip_adam_workspace_bytes": ([], ctypes.c_size_t),
     "rlppo_norm_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P, ctypes.c_size_t, _P], _I),
+    "rlppo_peer_flag_bytes": ([], ctypes.c_size_t),
+    "rlppo_norm_clip_adam_peers": ([_P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P,
+                                    ctypes.c_size_t, _P], _I),
     "rlppo_sqdiff": ([_P, _P, _P, _I, _P, _P], _I),
 }
 

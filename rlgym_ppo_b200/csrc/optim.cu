@@ -122,16 +122,49 @@ __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict_
 // followed by gridDim.x * kMaxSeg block partials.  Every block of the grid must be resident (grid <= SMs x occupancy).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kFusedThreads = 256;
+constexpr int kMaxPeers = 8;
+// Data-parallel form (rlppo_norm_clip_adam_peers): the gradient all-reduce is done by this kernel itself over NVLink peer
+// mappings instead of a separate NCCL launch.  Every rank's gradient arena and a small flag block live in symmetric
+// memory that all ranks of the box have mapped; grads[r] / flags[r] are rank r's copies as seen from THIS process.
+//   flag block (uint32): [0, 8) "gradients complete" epoch written by peer r, [32, 40) "done reading yours" epoch
+//   written by peer r, [64] this rank's own epoch counter (= number of completed launches).
+// Flags are monotonic epochs: a stale read only delays, nothing is ever reset.
+struct Peers {
+    const float* grads[kMaxPeers];
+    unsigned int* flags[kMaxPeers];
+    float* gsum;                      // local f32[total]: the summed gradient (read back in the update phase)
+    int rank, world;
+};
+constexpr int kFlagDone = 32, kFlagEpoch = 64;
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until the epoch at p has reached `epoch` (wrap-safe); traps instead of hanging if a peer never shows up
+__device__ __forceinline__ void wait_epoch(const unsigned int* p, unsigned int epoch) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(p) - epoch) < 0) {
+        if (clock64() - t0 > 60000000000LL) __trap();   // ~30 s
+        __nanosleep(200);
+    }
+}
+
 struct FusedWs {
     unsigned int arrive, depart, pad[2];
     float partial[1];    // [gridDim.x][kMaxSeg]
 };
 
+template <bool PEERS>
 __global__ void __launch_bounds__(kFusedThreads)
 norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                       Segs segs, float* __restrict__ sqnorm_out, const float* __restrict__ lr,
                       int64_t* __restrict__ step_count, float max_norm, double beta1d, double beta2d, float eps,
-                      Views views, FusedWs* __restrict__ ws) {
+                      Views views, FusedWs* __restrict__ ws, const Peers pr) {
     const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
     __shared__ float s_w[kFusedThreads / 32][kMaxSeg];
     __shared__ float s_coef[kMaxSeg], s_step_size[kMaxSeg], s_bc2_sqrt[kMaxSeg];
@@ -140,12 +173,35 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < segs.n) s_t[threadIdx.x] = (double)(step_count[threadIdx.x] + 1);   // read BEFORE the barrier
 
+    // ---- phase 0 (PEERS): every rank's gradients are complete ----
+    // This launch is stream-ordered behind the local backward kernels; block 0 tells every peer so, and every block
+    // waits (polling LOCAL memory) until all peers have said the same.
+    unsigned int epoch = 0;
+    if (PEERS) {
+        epoch = *reinterpret_cast<volatile unsigned int*>(pr.flags[pr.rank] + kFlagEpoch) + 1u;
+        if (blockIdx.x == 0 && threadIdx.x < pr.world) {
+            __threadfence_system();
+            st_release_sys(pr.flags[threadIdx.x] + pr.rank, epoch);
+        }
+        if (threadIdx.x < pr.world) wait_epoch(pr.flags[pr.rank] + threadIdx.x, epoch);
+        __syncthreads();
+    }
+
     // ---- phase 1: this block's partial sums of squares, fixed order ----
     float acc[kMaxSeg];
 #pragma unroll
     for (int k = 0; k < kMaxSeg; ++k) acc[k] = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const float x = __ldg(g + i);
+        float x;
+        if (PEERS) {
+            // the all-reduce: peer loads over NVLink (L1 bypassed), summed in rank order on every rank -- the same
+            // bits everywhere, so the replicas stay identical without a broadcast
+            x = __ldcg(pr.grads[0] + i);
+            for (int r = 1; r < pr.world; ++r) x += __ldcg(pr.grads[r] + i);
+            pr.gsum[i] = x;
+        } else {
+            x = __ldg(g + i);
+        }
         const int k = seg_of(segs, i);
 #pragma unroll
         for (int j = 0; j < kMaxSeg; ++j)
@@ -173,6 +229,9 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
             if (clock64() - t0 > 8000000000LL) __trap();   // watchdog (~4 s): the grid was not co-resident
     }
     __syncthreads();
+    // every block of this rank has finished reading the peers' gradients: let them go on (they wait for this before
+    // their launch ends, i.e. before anything can overwrite their arena)
+    if (PEERS && blockIdx.x == 0 && threadIdx.x < pr.world) st_release_sys(pr.flags[threadIdx.x] + kFlagDone + pr.rank, epoch);
     // ---- phase 2: every block adds the block partials in block order (identical result everywhere) ----
     if (warp == 0) {
         for (int k = 0; k < segs.n; ++k) {
@@ -196,7 +255,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     int hint = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = seg_of(segs, i);
-        const float gi = g[i] * s_coef[k];
+        const float gi = (PEERS ? pr.gsum[i] : g[i]) * s_coef[k];
         float mi = m[i], vi = v[i];
         mi = mi + (gi - mi) * omb1;                           // exp_avg.lerp_(grad, 1-beta1)
         vi = vi * beta2 + omb2 * gi * gi;                      // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
@@ -233,6 +292,11 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
         if (old == gridDim.x - 1) {
             ws->arrive = 0;
             ws->depart = 0;
+            if (PEERS) {
+                // the launch may only end once every peer has finished reading this rank's gradients
+                for (int r = 0; r < pr.world; ++r) wait_epoch(pr.flags[pr.rank] + kFlagDone + r, epoch);
+                *reinterpret_cast<volatile unsigned int*>(pr.flags[pr.rank] + kFlagEpoch) = epoch;
+            }
             __threadfence();
         }
     }
@@ -241,7 +305,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
 int fused_grid(int64_t total, int* out) {
     static int per_sm = 0;
     if (per_sm == 0) {
-        RLPPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, norm_clip_adam_kernel, kFusedThreads, 0));
+        RLPPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, norm_clip_adam_kernel<true>, kFusedThreads, 0));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;
     }
@@ -289,12 +353,12 @@ size_t rlppo_norm_clip_adam_workspace_bytes(void) {
     return sizeof(FusedWs) + sizeof(float) * kMaxSeg * (size_t)rlppo::num_sms() * 4;
 }
 
-int rlppo_norm_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off, int n_seg,
-                         float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm, double beta1,
-                         double beta2, double eps, const rlppo_bf16_view* h_views, int n_views, void* ws,
-                         size_t ws_bytes, void* stream) {
+static int launch_norm_clip_adam(float* params, const float* grads, const Peers* peers, float* m, float* v,
+                                 const int64_t* h_seg_off, int n_seg, float* sqnorm_out, const float* lr,
+                                 int64_t* step_count, double max_norm, double beta1, double beta2, double eps,
+                                 const rlppo_bf16_view* h_views, int n_views, void* ws, size_t ws_bytes, void* stream) {
     RLPPO_REQUIRE_DEVICE();
-    RLPPO_CHECK_ARG(params && grads && m && v && lr && step_count && ws, "null pointer");
+    RLPPO_CHECK_ARG(params && (grads || peers) && m && v && lr && step_count && ws, "null pointer");
     RLPPO_CHECK_ARG(ws_bytes >= rlppo_norm_clip_adam_workspace_bytes(), "workspace too small");
     Segs segs;
     int rc = make_segs(h_seg_off, n_seg, &segs);
@@ -309,11 +373,48 @@ int rlppo_norm_clip_adam(float* params, const float* grads, float* m, float* v, 
     int grid = 1;
     rc = fused_grid(segs.off[n_seg], &grid);
     if (rc) return rc;
-    norm_clip_adam_kernel<<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        params, grads, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
-        static_cast<FusedWs*>(ws));
+    if (peers != nullptr)
+        norm_clip_adam_kernel<true><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            params, nullptr, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
+            static_cast<FusedWs*>(ws), *peers);
+    else
+        norm_clip_adam_kernel<false><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            params, grads, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
+            static_cast<FusedWs*>(ws), Peers{});
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
+}
+
+int rlppo_norm_clip_adam(float* params, const float* grads, float* m, float* v, const int64_t* h_seg_off, int n_seg,
+                         float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm, double beta1,
+                         double beta2, double eps, const rlppo_bf16_view* h_views, int n_views, void* ws,
+                         size_t ws_bytes, void* stream) {
+    RLPPO_CHECK_ARG(grads != nullptr, "null pointer");
+    return launch_norm_clip_adam(params, grads, nullptr, m, v, h_seg_off, n_seg, sqnorm_out, lr, step_count, max_norm,
+                                 beta1, beta2, eps, h_views, n_views, ws, ws_bytes, stream);
+}
+
+size_t rlppo_peer_flag_bytes(void) { return 128 * sizeof(unsigned int); }
+
+int rlppo_norm_clip_adam_peers(float* params, const float* const* h_peer_grads, void* const* h_peer_flags, int rank,
+                               int world, float* gsum, float* m, float* v, const int64_t* h_seg_off, int n_seg,
+                               float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm, double beta1,
+                               double beta2, double eps, const rlppo_bf16_view* h_views, int n_views, void* ws,
+                               size_t ws_bytes, void* stream) {
+    RLPPO_CHECK_ARG(h_peer_grads && h_peer_flags && gsum, "null pointer");
+    RLPPO_CHECK_ARG(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "rank %d of %d (at most %d peers)", rank,
+                    world, kMaxPeers);
+    Peers pr{};
+    for (int r = 0; r < world; ++r) {
+        RLPPO_CHECK_ARG(h_peer_grads[r] && h_peer_flags[r], "null peer pointer %d", r);
+        pr.grads[r] = h_peer_grads[r];
+        pr.flags[r] = static_cast<unsigned int*>(h_peer_flags[r]);
+    }
+    pr.gsum = gsum;
+    pr.rank = rank;
+    pr.world = world;
+    return launch_norm_clip_adam(params, nullptr, &pr, m, v, h_seg_off, n_seg, sqnorm_out, lr, step_count, max_norm,
+                                 beta1, beta2, eps, h_views, n_views, ws, ws_bytes, stream);
 }
 
 int rlppo_sqdiff(const float* a, const float* b, const int64_t* h_seg_off, int n_seg, float* out, void* stream) {

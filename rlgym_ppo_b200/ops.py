@@ -312,6 +312,25 @@ def norm_clip_adam(params, grads, m, v, seg_off, sqnorm_out, lr, step_count, max
          ptr(ws), ws.numel(), stream_ptr(), work=("byte", 32 * int(so[-1])))
 
 
+def norm_clip_adam_peers(params, peer_grad_ptrs, peer_flag_ptrs, rank, gsum, m, v, seg_off, sqnorm_out, lr, step_count,
+                         max_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-8, views=None):
+    """norm_clip_adam with the gradient all-reduce inside the launch (NVLink peer loads); see rlppo_norm_clip_adam_peers.
+    peer_grad_ptrs / peer_flag_ptrs: device addresses (ints) of every rank's gradient arena / flag block as mapped here."""
+    so = _seg(seg_off)
+    ws = _nca_ws.get(params.device)
+    if ws is None:
+        ws = torch.zeros(int(_lib._lib.rlppo_norm_clip_adam_workspace_bytes()), dtype=torch.uint8, device=params.device)
+        _nca_ws[params.device] = ws
+    world = len(peer_grad_ptrs)
+    gp = (ctypes.c_void_p * world)(*[int(x) for x in peer_grad_ptrs])
+    fp = (ctypes.c_void_p * world)(*[int(x) for x in peer_flag_ptrs])
+    call("rlppo_norm_clip_adam_peers", ptr(params), ctypes.cast(gp, ctypes.c_void_p), ctypes.cast(fp, ctypes.c_void_p),
+         int(rank), world, ptr(gsum), ptr(m), ptr(v), so.ctypes.data, len(so) - 1, ptr(sqnorm_out), ptr(lr),
+         ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps),
+         None if views is None else ctypes.cast(views, ctypes.c_void_p), 0 if views is None else len(views),
+         ptr(ws), ws.numel(), stream_ptr(), work=("byte", (32 + 4 * world) * int(so[-1])))
+
+
 def sqdiff(a, b, seg_off, out):
     so = _seg(seg_off)
     call("rlppo_sqdiff", ptr(a), ptr(b), so.ctypes.data, len(so) - 1, ptr(out), stream_ptr(),

@@ -55,6 +55,7 @@ class PPOLearner(object):
         max_chunk_rows=131072,
         process_group=None,
         dp_mode="replicated",
+        dp_collective=None,
     ):
         _lib.require_device()
         if device in (None, "auto", "gpu"):
@@ -82,7 +83,25 @@ class PPOLearner(object):
         n_p, n_v = ps.n_params, vs.n_params
         self._seg = np.asarray([0, n_p, n_p + n_v], dtype=np.int64)
         self._params = torch.zeros(n_p + n_v, dtype=torch.float32, device=dev)
-        self._grads = torch.zeros_like(self._params)
+        # Gradient exchange between data-parallel ranks (world_size > 1):
+        #  "p2p"  (default): the gradient arena lives in symmetric memory every GPU of the box has mapped; the optimiser
+        #         kernel itself sums the peers' arenas over NVLink in rank order (rlppo_norm_clip_adam_peers) -- no
+        #         separate collective launch, and nothing NCCL inside the step, so a whole learn() stays ONE CUDA graph.
+        #         `.grad` then holds this rank's own contribution; the summed gradient is `self._gsum`.
+        #  "nccl": torch.distributed all_reduce on the flat arena between the backward and the optimiser launch.
+        self._pg = process_group
+        self.world_size, self.rank = parallel.world(process_group)
+        self.dp_collective = "none"
+        self._grads = None
+        if self.world_size > 1:
+            self.dp_collective = dp_collective or os.environ.get("RLPPO_DP_COLLECTIVE", "p2p")
+            assert self.dp_collective in ("p2p", "nccl")
+            if self.dp_collective == "p2p" and self.world_size > 8:
+                self.dp_collective = "nccl"          # peer mappings are per box (8 GPUs)
+            if self.dp_collective == "p2p":
+                self._setup_peers(dev, n_p + n_v)
+        if self._grads is None:
+            self._grads = torch.zeros_like(self._params)
         self._m = torch.zeros_like(self._params)
         self._v = torch.zeros_like(self._params)
         self._before = torch.zeros_like(self._params)
@@ -118,8 +137,6 @@ class PPOLearner(object):
         self.max_chunk_rows = int(max_chunk_rows)
 
         # ---- data parallelism ---------------------------------------------------------------------------------
-        self._pg = process_group
-        self.world_size, self.rank = parallel.world(process_group)
         # Data-parallel modes (world_size > 1; one process per GPU, NCCL through torch.distributed):
         #  "replicated": every rank holds the SAME experience buffer and draws the same global permutation; rank r takes
         #                slice r of every batch -- exactly the reference's minibatch slices (ppo_learner.py:134-143), so the
@@ -150,6 +167,26 @@ class PPOLearner(object):
         # RLPPO_TWO_STREAMS=0: policy and value chains of a batch on one stream (see _train_chunk)
         self.two_streams = os.environ.get("RLPPO_TWO_STREAMS", "1") == "1"
         self._side_stream = None
+
+    def _setup_peers(self, dev, n):
+        """Gradient arena + flag block in symmetric memory (torch.distributed._symmetric_memory: CUDA peer mappings over
+        NVLink); a collective call -- every rank constructs its learners in the same order."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self._pg if self._pg is not None else dist.group.WORLD
+        grads = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        grads.zero_()
+        gh = symm_mem.rendezvous(grads, group)
+        flags = symm_mem.empty(int(_lib._lib.rlppo_peer_flag_bytes()) // 4, dtype=torch.int32, device=dev)
+        flags.zero_()
+        fh = symm_mem.rendezvous(flags, group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                         # every rank's flag block is zero before anyone launches
+        self._grads = grads
+        self._gsum = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._peer_grad_ptrs = [int(x) for x in gh.buffer_ptrs]
+        self._peer_flag_ptrs = [int(x) for x in fh.buffer_ptrs]
+        self._symm = (grads, gh, flags, fh)         # keep the mappings alive
 
     # ---- workspaces ----------------------------------------------------------------------------------------
     def _minibatch_buffers(self, rows):
@@ -246,6 +283,15 @@ class PPOLearner(object):
         self.launches += n
 
     def _optimizer_step(self):
+        if self.dp_collective == "p2p":
+            # the all-reduce happens inside the optimiser launch (peer loads over NVLink, rank-order sum)
+            ops.norm_clip_adam_peers(self._params, self._peer_grad_ptrs, self._peer_flag_ptrs, self.rank, self._gsum,
+                                     self._m, self._v, self._seg, self._sqnorm, self._lr_dev, self._steps, max_norm=0.5,
+                                     views=self._views)
+            self.policy._stack.mark_operands_fresh()
+            self.value_net._stack.mark_operands_fresh()
+            self.launches += 1
+            return
         parallel.allreduce_sum_(self._grads, self._pg)   # NCCL sum over NVLink; the gradients carry the global 1/B
         self._apply_step()
 
@@ -300,7 +346,7 @@ class PPOLearner(object):
         cur = self._idx_cur[:local]
         cur.copy_(idx)      # the graph reads its indices from a fixed buffer; the ring origin from exp.start_dev
         key = self._graph_key(exp, local, chunk) + (self._idx_cur.data_ptr(),)
-        if self.world_size == 1:
+        if self.world_size == 1 or self.dp_collective == "p2p":
             if not self._captured(("step",) + key, lambda: self._batch_body(exp, cur, local, chunk)):
                 self._batch_body(exp, cur, local, chunk)
         else:
@@ -315,10 +361,10 @@ class PPOLearner(object):
     def _graph_key(self, exp, local, chunk):
         """Everything a captured graph bakes in: buffer identity, workspace generations (addresses), scalar arguments."""
         return (exp.uid, local, chunk, float(self.clip_range), float(self.ent_coef), self.batch_size, self.world_size,
-                self.dp_mode, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
+                self.dp_mode, self.dp_collective, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
                 getattr(self.policy._stack, "ws_gen", 0), getattr(self.value_net._stack, "ws_gen", 0))
 
-    def _learn_body(self, exp, n_batches, local, chunk):
+    def _learn_body(self, exp, n_batches, local, chunk, tail=True):
         """Device work of one learn() call (ppo_learner.py:110-220): update-magnitude baseline, every optimiser step of
         every epoch (indices from self._perm_dev, one row per epoch), update magnitudes, the report scalars to pinned
         host memory.  Enqueue only -- this is what the whole-call CUDA graph captures."""
@@ -330,8 +376,9 @@ class PPOLearner(object):
                 base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
                 self._batch_body(exp, self._perm_dev[epoch, base:base + local], local, chunk)
         ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
-        parallel.allreduce_sum_(self._tail[0:8], self._pg)
-        self._tail_host.copy_(self._tail, non_blocking=True)
+        if tail:
+            parallel.allreduce_sum_(self._tail[0:8], self._pg)
+            self._tail_host.copy_(self._tail, non_blocking=True)
 
     def learn(self, exp):
         """
@@ -357,12 +404,18 @@ class PPOLearner(object):
             exp.next_permutation_into(self._perm_dev[epoch, :total])
         n_iterations = E * n_batches
 
+        p2p = R > 1 and self.dp_collective == "p2p"
         whole = (self.use_cuda_graph and _lib._TIMING is None and n_batches > 0
-                 and (R == 1 or self.graph_collectives))
+                 and (R == 1 or p2p or self.graph_collectives))
         if whole:
-            key = ("learn", total, E, n_batches, self._perm_dev.data_ptr()) + self._graph_key(exp, local, chunk)
-            if not self._captured(key, lambda: self._learn_body(exp, n_batches, local, chunk)):
-                self._learn_body(exp, n_batches, local, chunk)
+            # data parallel over peer memory: the graph holds everything but the one 8-float metric all-reduce
+            tail = not p2p or self.graph_collectives
+            key = ("learn", total, E, n_batches, tail, self._perm_dev.data_ptr()) + self._graph_key(exp, local, chunk)
+            if not self._captured(key, lambda: self._learn_body(exp, n_batches, local, chunk, tail)):
+                self._learn_body(exp, n_batches, local, chunk, tail)
+            if not tail:
+                parallel.allreduce_sum_(self._tail[0:8], self._pg)
+                self._tail_host.copy_(self._tail, non_blocking=True)
             self.policy._stack.mark_operands_fresh()
             self.value_net._stack.mark_operands_fresh()
         else:

@@ -49,19 +49,30 @@ def main():
     # After the first step Adam's first moment is (1 - beta1) * clipped gradient, so comparing the moment arenas compares
     # the gradients themselves: same per-row math, a different order of the fp32 sums (rank partials + NCCL sum instead of
     # one launch; the weight-gradient kernel's atomics are unordered even on one GPU) -> 1e-5 rel-L2.
-    def learner1(group):
+    def learner1(group, collective=None):
         torch.manual_seed(5)
         with contextlib.redirect_stdout(io.StringIO()):
             return PPOLearner(89, 90, 0, (256, 256), (256, 256), (0.1, 1.0), B, 1, 3e-4, 3e-4, 0.2, 0.01, B, dev,
-                              process_group=group, dp_mode="replicated")
-    dp1, alone1 = learner1(None), learner1(solo)
-    r_dp1 = dp1.learn(make_buffer(7, B, dev))
+                              process_group=group, dp_mode="replicated", dp_collective=collective)
+    # both gradient exchanges: "p2p" (the default: peer loads inside the optimiser launch) and "nccl" (all_reduce)
+    alone1 = learner1(solo)
     r_11 = alone1.learn(make_buffer(7, B, dev))
-    g_err = float((dp1._m - alone1._m).norm() / alone1._m.norm())
-    assert r_dp1["Cumulative Model Updates"] == r_11["Cumulative Model Updates"] == 1
-    assert g_err < 1e-5, f"all-reduced gradient differs from the one-rank gradient: rel-L2 {g_err}"
-    for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
-        assert abs(r_dp1[k] - r_11[k]) < 1e-5 * max(1.0, abs(r_11[k])), (k, r_dp1[k], r_11[k])
+    g_errs = {}
+    for collective in ("p2p", "nccl"):
+        dp1 = learner1(None, collective)
+        assert dp1.dp_collective == collective and alone1.dp_collective == "none"
+        r_dp1 = dp1.learn(make_buffer(7, B, dev))
+        g_err = g_errs[collective] = float((dp1._m - alone1._m).norm() / alone1._m.norm())
+        assert r_dp1["Cumulative Model Updates"] == r_11["Cumulative Model Updates"] == 1
+        assert g_err < 1e-5, f"{collective}: all-reduced gradient differs from the one-rank gradient: rel-L2 {g_err}"
+        for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
+            assert abs(r_dp1[k] - r_11[k]) < 1e-5 * max(1.0, abs(r_11[k])), (k, r_dp1[k], r_11[k])
+        if collective == "p2p":
+            # the summed gradient every rank formed from the peers' arenas is the same bits everywhere
+            gathered = [torch.empty_like(dp1._gsum) for _ in range(world)]
+            dist.all_gather(gathered, dp1._gsum)
+            assert all(torch.equal(g, gathered[0]) for g in gathered[1:]), "p2p: summed gradients differ between ranks"
+    g_err = max(g_errs.values())
 
     # ---- replicated, 3 learn() calls x 6 optimiser steps (eager, captured, replayed), compared call by call ----
     # bf16 rounding of the forward operands makes the loss piecewise constant in the weights, and Adam turns a 1e-10
@@ -89,7 +100,7 @@ def main():
     err = max(errs)
     assert rep_dp["Cumulative Model Updates"] == rep_1["Cumulative Model Updates"] == 3 * 2 * 3
     if rank == 0:
-        print(f"replicated: one-step gradient rel-L2 {g_err:.2e}; per-call update rel-L2 {errs}")
+        print(f"replicated: one-step gradient rel-L2 {g_errs}; per-call update rel-L2 {errs} ({dp.dp_collective})")
 
     # ---- sharded: own buffer per rank; replicas must stay identical ----
     sh = learner(None, "sharded")
