@@ -94,12 +94,33 @@ class PPOLearner(object):
         self.dp_collective = "none"
         self._grads = None
         if self.world_size > 1:
-            self.dp_collective = dp_collective or os.environ.get("RLPPO_DP_COLLECTIVE", "p2p")
+            # One-shot exchange: every rank reads all (R-1) peer arenas, (R-1) * 4 * n bytes over NVLink per step.  That is
+            # the latency-optimal form for the example-size nets (1.3 MB arena); for big arenas on many ranks a ring /
+            # tree all-reduce moves ~2 * 4 * n bytes instead, so the default hands those to NCCL (a two-shot
+            # reduce-scatter + all-gather form of the kernel is the next step).
+            auto = "p2p" if (self.world_size - 1) * 4 * (n_p + n_v) <= (16 << 20) else "nccl"
+            self.dp_collective = dp_collective or os.environ.get("RLPPO_DP_COLLECTIVE", auto)
             assert self.dp_collective in ("p2p", "nccl")
             if self.dp_collective == "p2p" and self.world_size > 8:
                 self.dp_collective = "nccl"          # peer mappings are per box (8 GPUs)
             if self.dp_collective == "p2p":
-                self._setup_peers(dev, n_p + n_v)
+                # Peer mappings need NVLink / P2P between all ranks' GPUs.  If the rendezvous fails on ANY rank, every rank
+                # switches to the NCCL exchange (agreed through one all-reduce, so no rank is left waiting on flags).
+                import torch.distributed as dist
+                err = None
+                try:
+                    self._setup_peers(dev, n_p + n_v)
+                except Exception as e:  # noqa: BLE001
+                    err = e
+                ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._pg)
+                if int(ok.item()) == 0:
+                    if dp_collective == "p2p":
+                        raise _lib.RlppoError(f"dp_collective='p2p' requested but peer mappings are unavailable: {err}")
+                    print(f"[rlgym_ppo_b200] rank {self.rank}: symmetric-memory peer mappings unavailable ({err}); "
+                          "gradients go through NCCL all_reduce", flush=True)
+                    self.dp_collective = "nccl"
+                    self._grads = None
         if self._grads is None:
             self._grads = torch.zeros_like(self._params)
         self._m = torch.zeros_like(self._params)
