@@ -333,13 +333,23 @@ struct StepMaps {
 // Co-residency: the grid is min(tiles, 3 x SMs) CTAs; a CTA waits only for aggregates of lower-numbered tiles, which
 // lower-numbered CTAs (scheduled first) or earlier iterations produce, so a partially resident grid still progresses.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kC3 = 256;                 // compute threads
+#ifndef RLPPO_GAE3_STEPS
+#define RLPPO_GAE3_STEPS 4               // steps per thread (4 or 8)
+#endif
+#ifndef RLPPO_GAE3_CTAS
+#define RLPPO_GAE3_CTAS 3                // resident CTAs per SM
+#endif
+#ifndef RLPPO_GAE3_STAGES
+#define RLPPO_GAE3_STAGES 3
+#endif
+constexpr int kI3 = RLPPO_GAE3_STEPS;
+constexpr int kTile3 = 1024;             // steps per tile
+constexpr int kC3 = kTile3 / kI3;        // compute threads
 constexpr int kT3 = kC3 + 32;            // + look-back warp
-constexpr int kI3 = 4;
-constexpr int kTile3 = kC3 * kI3;        // 1024 steps
 constexpr int kW3 = kC3 / 32;
-constexpr int kStages3 = 3;
-constexpr int kCtasPerSm3 = 3;
+constexpr int kStages3 = RLPPO_GAE3_STAGES;
+constexpr int kCtasPerSm3 = RLPPO_GAE3_CTAS;
+static_assert(kI3 == 4 || kI3 == 8, "4 or 8 steps per thread");
 constexpr uint32_t kVBytes3 = kTile3 * 4u + 16u;            // V tile + 4-float halo (only the first is used)
 constexpr uint32_t kOffD3 = kTile3 * 4u;
 constexpr uint32_t kOffV3 = 2u * kTile3 * 4u;
@@ -564,8 +574,13 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
     sm.gamma = gamma; sm.gl32 = gl32; sm.gl64 = (double)gl32;
     sm.has_std = ret_std != nullptr;
     sm.stdv = sm.has_std ? __ldg(ret_std) : 1.f;
-    const double g4A = (sm.gl64 * sm.gl64) * (sm.gl64 * sm.gl64);      // multiplier of 4 live steps
-    const double g4R = (gamma * gamma) * (gamma * gamma);
+    double g4A = (sm.gl64 * sm.gl64) * (sm.gl64 * sm.gl64);            // multiplier of kI3 live steps
+    double g4R = (gamma * gamma) * (gamma * gamma);
+    if (kI3 == 8) {
+        g4A *= g4A;
+        g4R *= g4R;
+    }
+    constexpr uint32_t kAllLive = (1u << kI3) - 1u;
     const int j0 = tid * kI3;
 
     // ---- phase A of tile k: everything up to the tile aggregate; the inputs phase B needs end up in `P` ----
@@ -580,22 +595,28 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
         P.fast = tile_staged;
         P.live = 0;
         if (tile_staged) {
-            const float4 r4 = *reinterpret_cast<const float4*>(st + (size_t)j0 * 4);
-            const float4 d4 = *reinterpret_cast<const float4*>(st + kOffD3 + (size_t)j0 * 4);
-            const float4 v4 = *reinterpret_cast<const float4*>(st + kOffV3 + (size_t)j0 * 4);
-            const float vh = *reinterpret_cast<const float*>(st + kOffV3 + (size_t)(j0 + kI3) * 4);
+            // 16-byte shared-memory accesses, kI3 / 4 per array (at 8 steps per thread the 32-byte thread stride makes them
+            // 2-way bank conflicts: 5 arrays per tile, not what bounds the kernel)
+            float dd[kI3], vn[kI3 + 1];
             double tt[kI3];
-            if (TRUNC64) {
-                const double2 t0 = *reinterpret_cast<const double2*>(st + kOffT3 + (size_t)j0 * 8);
-                const double2 t1 = *reinterpret_cast<const double2*>(st + kOffT3 + (size_t)j0 * 8 + 16);
-                tt[0] = t0.x; tt[1] = t0.y; tt[2] = t1.x; tt[3] = t1.y;
-            } else {
-                const float4 t4 = *reinterpret_cast<const float4*>(st + kOffT3 + (size_t)j0 * 4);
-                tt[0] = t4.x; tt[1] = t4.y; tt[2] = t4.z; tt[3] = t4.w;
+#pragma unroll
+            for (int q = 0; q < kI3 / 4; ++q) {
+                const float4 r4 = *reinterpret_cast<const float4*>(st + (size_t)(j0 + 4 * q) * 4);
+                const float4 d4 = *reinterpret_cast<const float4*>(st + kOffD3 + (size_t)(j0 + 4 * q) * 4);
+                const float4 v4 = *reinterpret_cast<const float4*>(st + kOffV3 + (size_t)(j0 + 4 * q) * 4);
+                P.r[4 * q] = r4.x; P.r[4 * q + 1] = r4.y; P.r[4 * q + 2] = r4.z; P.r[4 * q + 3] = r4.w;
+                dd[4 * q] = d4.x; dd[4 * q + 1] = d4.y; dd[4 * q + 2] = d4.z; dd[4 * q + 3] = d4.w;
+                vn[4 * q] = v4.x; vn[4 * q + 1] = v4.y; vn[4 * q + 2] = v4.z; vn[4 * q + 3] = v4.w;
+                if (TRUNC64) {
+                    const double2 t0 = *reinterpret_cast<const double2*>(st + kOffT3 + (size_t)(j0 + 4 * q) * 8);
+                    const double2 t1 = *reinterpret_cast<const double2*>(st + kOffT3 + (size_t)(j0 + 4 * q) * 8 + 16);
+                    tt[4 * q] = t0.x; tt[4 * q + 1] = t0.y; tt[4 * q + 2] = t1.x; tt[4 * q + 3] = t1.y;
+                } else {
+                    const float4 t4 = *reinterpret_cast<const float4*>(st + kOffT3 + (size_t)(j0 + 4 * q) * 4);
+                    tt[4 * q] = t4.x; tt[4 * q + 1] = t4.y; tt[4 * q + 2] = t4.z; tt[4 * q + 3] = t4.w;
+                }
             }
-            const float dd[kI3] = {d4.x, d4.y, d4.z, d4.w};
-            const float vn[kI3 + 1] = {v4.x, v4.y, v4.z, v4.w, vh};
-            P.r[0] = r4.x; P.r[1] = r4.y; P.r[2] = r4.z; P.r[3] = r4.w;
+            vn[kI3] = *reinterpret_cast<const float*>(st + kOffV3 + (size_t)(j0 + kI3) * 4);
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < kI3; ++i) {
@@ -615,7 +636,7 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
                     bA = fma(lv ? sm.gl64 : 0.0, bA, (double)P.dl[i]);
                     bR = fma(lv ? gamma : 0.0, bR, (double)P.r[i]);
                 }
-                const bool all = P.live == 0xFu;
+                const bool all = P.live == kAllLive;
                 agg = Aff{all ? g4A : 0.0, bA, all ? g4R : 0.0, bR};
             } else {
                 agg = aff_identity();
@@ -658,7 +679,7 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
             wagg[warp][0] = incl_w.aA; wagg[warp][1] = incl_w.bA;
             wagg[warp][2] = incl_w.aR; wagg[warp][3] = incl_w.bR;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kC3) : "memory");
         // every compute warp has read stage s into registers by now: refill it with the tile three ahead
         if (tid == 0 && k + kStages3 < K) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
@@ -708,9 +729,12 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
                 ov[i] = (float)((double)P.v[i] + xA);           // :77
                 orr[i] = (float)xR;
             }
-            *reinterpret_cast<float4*>(adv + gbase) = make_float4(oa[0], oa[1], oa[2], oa[3]);
-            *reinterpret_cast<float4*>(vt + gbase) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-            *reinterpret_cast<float4*>(ret + gbase) = make_float4(orr[0], orr[1], orr[2], orr[3]);
+#pragma unroll
+            for (int q = 0; q < kI3 / 4; ++q) {
+                *reinterpret_cast<float4*>(adv + gbase + 4 * q) = make_float4(oa[4 * q], oa[4 * q + 1], oa[4 * q + 2], oa[4 * q + 3]);
+                *reinterpret_cast<float4*>(vt + gbase + 4 * q) = make_float4(ov[4 * q], ov[4 * q + 1], ov[4 * q + 2], ov[4 * q + 3]);
+                *reinterpret_cast<float4*>(ret + gbase + 4 * q) = make_float4(orr[4 * q], orr[4 * q + 1], orr[4 * q + 2], orr[4 * q + 3]);
+            }
         } else {
             // generic flags / ragged tile: the multipliers again, from global memory (rare)
             const int cnt = (int)((n - base0) < (int64_t)kTile3 ? (n - base0) : (int64_t)kTile3);
