@@ -191,17 +191,40 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     float acc[kMaxSeg];
 #pragma unroll
     for (int k = 0; k < kMaxSeg; ++k) acc[k] = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        float x;
-        if (PEERS) {
-            // the all-reduce: peer loads over NVLink (L1 bypassed), summed in rank order on every rank -- the same
-            // bits everywhere, so the replicas stay identical without a broadcast
-            x = __ldcg(pr.grads[0] + i);
-            for (int r = 1; r < pr.world; ++r) x += __ldcg(pr.grads[r] + i);
-            pr.gsum[i] = x;
-        } else {
-            x = __ldg(g + i);
+    // (PEERS) the all-reduce: peer loads over NVLink (L1 bypassed), summed in rank order on every rank -- the same bits
+    // everywhere, so the replicas stay identical without a broadcast.  Same thread <-> element mapping and accumulation
+    // order as the one-rank kernel; the loads of four elements x all peers are issued before anything is summed: a loop of
+    // dependent loads paid one NVLink round trip per peer and element (measured on 8 GPUs: no faster than NCCL).
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+    if (PEERS) {
+        for (int64_t i0 = gtid; i0 < total; i0 += 4 * gthreads) {
+            float xs[4][kMaxPeers];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * gthreads;
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; ++r)
+                    if (i < total && r < pr.world) xs[e][r] = __ldcg(pr.grads[r] + i);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * gthreads;
+                if (i < total) {
+                    float x = xs[e][0];
+#pragma unroll
+                    for (int r = 1; r < kMaxPeers; ++r)
+                        if (r < pr.world) x += xs[e][r];
+                    pr.gsum[i] = x;
+                    const int k = seg_of(segs, i);
+#pragma unroll
+                    for (int j = 0; j < kMaxSeg; ++j)
+                        if (j == k) acc[j] = fmaf(x, x, acc[j]);
+                }
+            }
         }
+    }
+    for (int64_t i = gtid; !PEERS && i < total; i += gthreads) {
+        const float x = __ldg(g + i);
         const int k = seg_of(segs, i);
 #pragma unroll
         for (int j = 0; j < kMaxSeg; ++j)
