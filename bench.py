@@ -414,8 +414,11 @@ def b200_arm(args, wl):
             "config": {"workload": wl["name"], "global_new_timesteps": n_glob, "global_batch": batch,
                        "global_buffer": cap, "optimizer_steps_per_step": n_updates,
                        "consumed_samples_per_step": n_updates * batch,
-                       "parallelism": f"dp{world} (per-rank experience shards; NCCL allreduce of the flat gradient arena "
-                                      f"per optimiser step)" if world > 1 else "dp1",
+                       "parallelism": (f"dp{world} (per-rank experience shards; gradient exchange per optimiser step: "
+                                       + ("summed inside the optimiser launch from the peers' arenas over NVLink)"
+                                          if ppo.dp_collective == "p2p" else "NCCL allreduce of the flat gradient arena)"))
+                       if world > 1 else "dp1",
+                       "gradient_exchange": ppo.dp_collective,
                        "l2": "flushed between timed steps (256 MiB write); working set > L2",
                        "algorithmic_tflop_per_step": flop_step / 1e12,
                        "achieved_tflops": flop_step / (dev_ms / K / 1e3) / 1e12},

@@ -33,6 +33,28 @@ def samples_per_step(batch_size, world_size, mode):
     return batch_size * world_size if (mode == "sharded" and world_size > 1) else batch_size
 
 
+ONE_SHOT_BYTES = 16 << 20
+
+
+def choose_collective(world_size, n_params, requested=None, env=None):
+    """How data-parallel ranks exchange gradients: "none" (one rank), "p2p" (summed inside the optimiser launch from the
+    peers' symmetric-memory arenas: rlppo_norm_clip_adam_peers) or "nccl" (all_reduce on the flat arena).
+
+    The one-shot peer exchange makes every rank read all (R-1) peer arenas, (R-1) * 4 * n bytes over NVLink per step:
+    latency-optimal for the example-size nets, but a ring / tree all-reduce moves ~2 * 4 * n bytes however many ranks
+    there are, so big arenas default to NCCL.  Peer mappings exist inside one box only (at most 8 ranks).
+    `requested` (constructor argument) wins over `env` (RLPPO_DP_COLLECTIVE) which wins over the size rule."""
+    if world_size <= 1:
+        return "none"
+    auto = "p2p" if (world_size - 1) * 4 * int(n_params) <= ONE_SHOT_BYTES else "nccl"
+    choice = requested or env or auto
+    if choice not in ("p2p", "nccl"):
+        raise ValueError(f"dp_collective must be 'p2p' or 'nccl', got {choice!r}")
+    if choice == "p2p" and world_size > 8:
+        choice = "nccl"
+    return choice
+
+
 def allreduce_sum_(t, group=None):
     """In-place sum over ranks (flat gradient arena, metric sums); identity without a process group."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

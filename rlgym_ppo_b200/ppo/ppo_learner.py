@@ -94,15 +94,8 @@ class PPOLearner(object):
         self.dp_collective = "none"
         self._grads = None
         if self.world_size > 1:
-            # One-shot exchange: every rank reads all (R-1) peer arenas, (R-1) * 4 * n bytes over NVLink per step.  That is
-            # the latency-optimal form for the example-size nets (1.3 MB arena); for big arenas on many ranks a ring /
-            # tree all-reduce moves ~2 * 4 * n bytes instead, so the default hands those to NCCL (a two-shot
-            # reduce-scatter + all-gather form of the kernel is the next step).
-            auto = "p2p" if (self.world_size - 1) * 4 * (n_p + n_v) <= (16 << 20) else "nccl"
-            self.dp_collective = dp_collective or os.environ.get("RLPPO_DP_COLLECTIVE", auto)
-            assert self.dp_collective in ("p2p", "nccl")
-            if self.dp_collective == "p2p" and self.world_size > 8:
-                self.dp_collective = "nccl"          # peer mappings are per box (8 GPUs)
+            self.dp_collective = parallel.choose_collective(self.world_size, n_p + n_v, dp_collective,
+                                                            os.environ.get("RLPPO_DP_COLLECTIVE"))
             if self.dp_collective == "p2p":
                 # Peer mappings need NVLink / P2P between all ranks' GPUs.  If the rendezvous fails on ANY rank, every rank
                 # switches to the NCCL exchange (agreed through one all-reduce, so no rank is left waiting on flags).

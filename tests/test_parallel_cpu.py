@@ -76,3 +76,18 @@ def test_report_from_sums_and_single_process_defaults():
     assert rep == {"Policy Entropy": 2.25, "Mean KL Divergence": 0.125, "SB3 Clip Fraction": 0.5,
                    "Value Function Loss": 4.0}
     assert parallel.report_from_sums([0.0] * 8)["Policy Entropy"] == 0.0      # no minibatches: zeros, as the reference
+
+
+def test_choose_collective():
+    from rlgym_ppo_b200 import parallel
+    small, big = 332_635, 15_150_171                      # parameter counts of the 256x3 and the 2048-2048-1024-1024 nets
+    assert parallel.choose_collective(1, small) == "none"
+    assert [parallel.choose_collective(r, small) for r in (2, 4, 8)] == ["p2p"] * 3      # 9.3 MB of peer reads at 8 ranks
+    assert [parallel.choose_collective(r, big) for r in (2, 4, 8)] == ["nccl"] * 3       # 60 MB arena: ring all-reduce
+    assert parallel.choose_collective(8, big, requested="p2p") == "p2p"                  # explicit request wins
+    assert parallel.choose_collective(2, small, env="nccl") == "nccl"
+    assert parallel.choose_collective(2, small, requested="p2p", env="nccl") == "p2p"
+    assert parallel.choose_collective(16, small, requested="p2p") == "nccl"              # peer mappings stop at the box
+    import pytest
+    with pytest.raises(ValueError):
+        parallel.choose_collective(2, small, requested="ring")
