@@ -313,6 +313,7 @@ def b200_arm(args, wl):
         Learner.add_new_experience(ns, pool_dev[it % n_pool])
         it += 1
     n_warm = max(args.warmup, 3)
+    barrier()                                     # ranks reach their first data-parallel step together
     for _ in range(max(n_warm, 2 * n_pool)):      # every pooled rollout at least twice: its CUDA graph exists before timing
         step(pool_dev[it % n_pool])
         it += 1

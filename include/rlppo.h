@@ -289,7 +289,7 @@ int rlppo_norm_clip_adam(float* params, const float* grads, float* m, float* v, 
  * buffer_ptrs); entry `rank` is the local one.  gsum: local f32[total] scratch that receives the summed gradient (rank
  * order 0..world-1 on every rank: replicas stay bit-identical).  Every rank must make the same sequence of calls; the
  * launch ends only after all peers have finished reading this rank's arena, so the caller may overwrite it right after.
- * A peer that never arrives traps the kernel after ~30 s instead of hanging.  world <= 8.  Other arguments as above. */
+ * A peer that never arrives traps the kernel after ~2 min instead of hanging.  world <= 8.  Other arguments as above. */
 size_t rlppo_peer_flag_bytes(void);
 int rlppo_norm_clip_adam_peers(float* params, const float* const* h_peer_grads, void* const* h_peer_flags, int rank,
                                int world, float* gsum, float* m, float* v, const int64_t* h_seg_off, int n_seg,

@@ -149,7 +149,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 __device__ __forceinline__ void wait_epoch(const unsigned int* p, unsigned int epoch) {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(p) - epoch) < 0) {
-        if (clock64() - t0 > 60000000000LL) __trap();   // ~30 s
+        if (clock64() - t0 > 240000000000LL) __trap();   // ~2 min: ranks may reach their first step seconds apart
         __nanosleep(200);
     }
 }
