@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box session: parity tests, bench lines, ncu launch list, ncu --set full captures, GAE sweep.
 # Usage (from the repo root, under gpurun):  bash tools/gpu_session.sh <tag> [what ...]
-#   what: tests bench_c2 bench_c3 launches full_c2 full_c3 sweep     (default: all but full_c3)
+#   what: tests bench_c2 bench_c3 launches full_c2 full_c3 sweep dp   (default: all but full_c3 and dp)
 set -u
 TAG=${1:-r01}
 shift || true
@@ -68,5 +68,17 @@ if has full_c3; then
   timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o $O/${TAG}_full_c3 \
       -k regex:'rowgemm|wgrad' -c 12 python tools/ncu_step.py --workload c3 > $O/${TAG}_full_c3.log 2>&1
   tail -2 $O/${TAG}_full_c3.log
+fi
+if has dp; then
+  # data-parallel check + bench lines with both gradient exchanges (run under `gpurun --gpus N`; N from the visible GPUs)
+  N=$(nvidia-smi -L | wc -l)
+  T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port"
+  timeout 300 $T 29541 tests/dp_check.py > $O/${TAG}_dp_check_n$N.log 2>&1
+  grep "dp_check\|replicated:" $O/${TAG}_dp_check_n$N.log
+  for c in p2p nccl; do
+    RLPPO_DP_COLLECTIVE=$c timeout 200 $T 29542 bench.py --gpus $N --steps 20 --warmup 3 \
+        > $O/${TAG}_bench_c2_n${N}_$c.json 2> $O/${TAG}_bench_c2_n${N}_$c.err
+    cut -c1-220 $O/${TAG}_bench_c2_n${N}_$c.json
+  done
 fi
 ls -la $O | tail -20
