@@ -24,6 +24,7 @@ gradients == full-batch gradient).  Here a rank's share of the batch is processe
 1/batch_size weighting, so `mini_batch_size` keeps its meaning for the result and stops costing launches.
 """
 import os
+import sys
 import time
 
 import numpy as np
@@ -111,7 +112,7 @@ class PPOLearner(object):
                     if dp_collective == "p2p":
                         raise _lib.RlppoError(f"dp_collective='p2p' requested but peer mappings are unavailable: {err}")
                     print(f"[rlgym_ppo_b200] rank {self.rank}: symmetric-memory peer mappings unavailable ({err}); "
-                          "gradients go through NCCL all_reduce", flush=True)
+                          "gradients go through NCCL all_reduce", file=sys.stderr, flush=True)
                     self.dp_collective = "nccl"
                     self._grads = None
         if self._grads is None:
