@@ -19,7 +19,9 @@ reference's own arithmetic lives in two third-party dependencies that are not un
 PARITY PINNING: the reference has no tests or golden vectors.  The oracle is pinned
 against outputs of the reference itself, imported in the authoring container from /root/reference by
 tests/golden/make_golden.py; the resulting fixtures are committed under tests/golden/ and
-tests/test_oracle_vs_golden.py checks every function here against them.
+tests/test_oracle_vs_golden.py checks every function here against them.  The two action heads that are next on
+the path (MultiDiscreteFF, ContinuousPolicy: SURVEY.md 8(f)-4) are restated and pinned the same way
+(tests/golden/make_golden_heads.py -> heads.npz) ahead of their CUDA epilogues.
 
 Scalar-promotion note (compute_gae, WelfordRunningStat): the reference mixes np.float32 scalars, Python
 floats and an f64 `truncated` array, so its rounding points depend on the NumPy major version.  The
@@ -363,6 +365,111 @@ def mlp_backward(params, acts, dout, quant=None):
     return grads
 
 
+# --------------------------------------------------------------------------------------------------
+# The other two action heads (ppo_learner.py:36-50 selects by policy_type):
+#   1  MultiDiscreteFF   multi_discrete_policy.py:17-89 + torch_functions.MultiDiscreteRolv (:81-122)
+#   2  ContinuousPolicy  continuous_policy.py:21-120   + torch_functions.MapContinuousToAction (:15-33)
+# Each returns (logp [mb], entropy scalar, backward) where backward(d_logp [mb], d_entropy scalar) is the
+# analytic gradient with respect to the last Linear's output.  torch.distributions is restated, not called.
+# --------------------------------------------------------------------------------------------------
+ROLV_BINS = (3, 3, 3, 3, 3, 2, 2, 2)  # multi_discrete_policy.py:21
+
+
+def head_multi_discrete(z, acts):
+    """21 logits -> 8 categoricals (5 triplets, 3 duets; the reference pads the duets with -inf to triplets,
+    which changes nothing: a -inf logit has probability 0 and, with Categorical.entropy's clamp of the
+    logits to finfo.min, contributes 0 * finite = 0).  log_prob and entropy are SUMMED over the 8
+    distributions (:115, :121), the entropy is then averaged over the minibatch
+    (multi_discrete_policy.py:89)."""
+    a = acts.view(z.shape[0], -1).long()
+    logp = torch.zeros(z.shape[0], dtype=z.dtype)
+    ent = torch.zeros(z.shape[0], dtype=z.dtype)
+    groups = []
+    start = 0
+    for gi, nb in enumerate(ROLV_BINS):
+        zg = z[:, start:start + nb]
+        lsm = zg - torch.logsumexp(zg, -1, keepdim=True)  # Categorical(logits=...) normalisation
+        pg = torch.softmax(lsm, -1)  # logits_to_probs
+        hg = -(lsm * pg).sum(-1)
+        logp = logp + lsm.gather(-1, a[:, gi:gi + 1]).flatten()
+        ent = ent + hg
+        groups.append((start, nb, lsm, pg, hg))
+        start += nb
+
+    def backward(d_logp, d_entropy):
+        dz = torch.zeros_like(z)
+        mb = z.shape[0]
+        for gi, (st, nb, lsm, pg, hg) in enumerate(groups):
+            onehot = torch.zeros_like(pg).scatter_(-1, a[:, gi:gi + 1], 1.0)
+            # d logp / dz = onehot - p ;  dH/dz_i = -p_i (log p_i + H) ; entropy.mean() spreads d_entropy / mb
+            dz[:, st:st + nb] = d_logp.unsqueeze(-1) * (onehot - pg) + \
+                (d_entropy / mb) * (-pg * (lsm + hg.unsqueeze(-1)))
+        return dz
+
+    return logp, ent.mean(), backward
+
+
+def head_continuous(u, acts, var_min=0.1, var_max=1.0):
+    """u = output of the last Linear (2N columns).  continuous_policy.py:37 Tanh, torch_functions.py:24-33 affine map of
+    the second half onto [var_min, var_max], :40-59 the four-term log-pdf as the reference writes it (f32), summed over
+    the N actions (:112); entropy = Normal.entropy() = 0.5 + 0.5 log(2 pi) + log(std), averaged over ALL mb * N
+    elements (:117-118)."""
+    t = torch.tanh(u)
+    n = t.shape[-1] // 2
+    m = (var_max - var_min) / 2.0  # torch_functions.py:27-28
+    b = var_min + m
+    mean, std = t[:, :n], t[:, n:] * m + b
+    x = acts.view(u.shape[0], n).to(u.dtype)
+    msq, ssq, xsq = mean * mean, std * std, x * x
+    term1 = -torch.divide(msq, (2 * ssq))
+    term2 = torch.divide(mean * x, ssq)
+    term3 = -torch.divide(xsq, (2 * ssq))
+    term4 = torch.log(1 / torch.sqrt(2 * np.pi * ssq))
+    logp = (term1 + term2 + term3 + term4).sum(dim=1)
+    ent = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(std)).mean()
+
+    def backward(d_logp, d_entropy):
+        d = d_logp.unsqueeze(-1)
+        d_mean = d * (x - mean) / ssq
+        d_std = d * ((x - mean) ** 2 / (ssq * std) - 1.0 / std) + d_entropy / (std.numel() * std)
+        dt = torch.cat([d_mean, d_std * m], dim=-1)
+        return dt * (1.0 - t * t)  # Tanh
+
+    return logp, ent, backward
+
+
+def ppo_minibatch_head(policy_type, pol, val, obs, acts, old_logp, targets, adv, clip, ent_coef, batch_size,
+                       var_range=(0.1, 1.0), quant=None):
+    """ppo_minibatch for policy_type 1 / 2: the same loss block (ppo_learner.py:146-185) around another head."""
+    w = 1.0 / batch_size
+    mb = obs.shape[0]
+    z, pacts = mlp_forward(pol, obs, quant)
+    if policy_type == 1:
+        logp, entropy, head_bwd = head_multi_discrete(z, acts)
+    else:
+        logp, entropy, head_bwd = head_continuous(z, acts, *var_range)
+    log_ratio = logp - old_logp
+    ratio = torch.exp(log_ratio)
+    clipped = torch.clamp(ratio, 1.0 - clip, 1.0 + clip)
+    kl = ((ratio - 1) - log_ratio).mean()
+    clip_frac = ((ratio - 1).abs() > clip).float().mean()
+    s1, s2 = ratio * adv, clipped * adv
+    policy_loss = -torch.min(s1, s2).mean()
+    v, vacts = mlp_forward(val, obs, quant)
+    v = v.flatten()
+    value_loss = ((v - targets) ** 2).mean()
+    in_range = (ratio >= 1.0 - clip) & (ratio <= 1.0 + clip)
+    lt, eq, gt = (s1 < s2).to(z.dtype), (s1 == s2).to(z.dtype), (s1 > s2).to(z.dtype)
+    d_ratio = -w * adv * ((lt + 0.5 * eq) + (gt + 0.5 * eq) * in_range.to(z.dtype))
+    # ppo_loss = (policy_loss - ent_coef * entropy) * (mb / B): d/d entropy = -ent_coef * mb / B
+    dz = head_bwd(d_ratio * ratio, -ent_coef * mb * w)
+    pg = mlp_backward(pol, pacts, dz, quant)
+    vg = mlp_backward(val, vacts, (2.0 * w * (v - targets)).unsqueeze(-1), quant)
+    metrics = dict(entropy=float(entropy), kl=float(kl), clip_fraction=float(clip_frac),
+                   value_loss=float(value_loss), policy_loss=float(policy_loss))
+    return pg, vg, metrics
+
+
 def ppo_minibatch(pol, val, obs, acts, old_logp, targets, adv, clip, ent_coef, batch_size, quant=None):
     """ppo_learner.py:146-185 + discrete_policy.py:64-80 forward, and the analytic backward of
     SURVEY.md A.3.  Returns (policy grads, value grads, metrics dict with per-minibatch means)."""
@@ -448,7 +555,8 @@ class PPOLearnerOracle:
     """ppo_learner.py:92-238 `learn`, restated around ppo_minibatch/clip_grad_norm/AdamOracle."""
 
     def __init__(self, pol, val, batch_size, n_epochs, policy_lr, critic_lr, clip_range, ent_coef,
-                 mini_batch_size, quant=None):
+                 mini_batch_size, quant=None, policy_type=0, var_range=(0.1, 1.0)):
+        self.policy_type, self.var_range = policy_type, var_range
         self.pol = [p.clone() for p in pol]
         self.val = [p.clone() for p in val]
         self.batch_size, self.n_epochs = batch_size, n_epochs
@@ -472,10 +580,13 @@ class PPOLearnerOracle:
                 vg = [torch.zeros_like(p) for p in self.val]
                 for s in range(0, self.batch_size, self.mini_batch_size):  # :134
                     e = s + self.mini_batch_size
-                    g1, g2, mt = ppo_minibatch(self.pol, self.val, torch.from_numpy(obs[s:e]),
-                                               torch.from_numpy(acts[s:e]), torch.from_numpy(oldp[s:e]),
-                                               torch.from_numpy(tgt[s:e]), torch.from_numpy(adv[s:e]),
-                                               self.clip_range, self.ent_coef, self.batch_size, self.quant)
+                    args = (self.pol, self.val, torch.from_numpy(obs[s:e]), torch.from_numpy(acts[s:e]),
+                            torch.from_numpy(oldp[s:e]), torch.from_numpy(tgt[s:e]), torch.from_numpy(adv[s:e]),
+                            self.clip_range, self.ent_coef, self.batch_size)
+                    if self.policy_type == 0:
+                        g1, g2, mt = ppo_minibatch(*args, self.quant)
+                    else:  # ppo_learner.py:131 batch_acts.view(batch_size, -1): one row of actions per sample
+                        g1, g2, mt = ppo_minibatch_head(self.policy_type, *args, self.var_range, self.quant)
                     pg = [a + b for a, b in zip(pg, g1)]
                     vg = [a + b for a, b in zip(vg, g2)]
                     m_vl += mt["value_loss"]

@@ -1,6 +1,7 @@
 """Pins oracle/ (CPU restatement) against the golden vectors produced by the reference itself
 (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import ref_oracle as O
@@ -179,3 +180,50 @@ def test_add_new_experience(golden):
         assert buf.f["rewards"].shape[0] == g[f"it{it}.buf.len"][0]
         assert np.allclose(buf.f["values"], g[f"it{it}.buf.values"], rtol=1e-5, atol=1e-5)
         assert np.allclose(buf.f["advantages"], g[f"it{it}.buf.advantages"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag,ptype", [("md", 1), ("ct", 2)])
+def test_other_heads_match_reference(golden, tag, ptype):
+    """MultiDiscreteFF / ContinuousPolicy (the next rows of the hot path): the restated heads and
+    their analytic backward reproduce the reference's get_backprop_data and a full PPOLearner.learn (autograd)."""
+    g = golden("heads")
+    obs_dim, B, mb, epochs, total, n_cont = [int(x) for x in g["cfg"][:6]]
+    plr, clr, clip, ent, vmin, vmax = g["hyper"]
+    pol0, val0 = _params(g, f"{tag}.pol0"), _params(g, f"{tag}.val0")
+    # get_backprop_data on the first minibatch of the rollout
+    obs = torch.from_numpy(g[f"{tag}.buf.states"][:mb])
+    acts = torch.from_numpy(g[f"{tag}.buf.actions"][:mb])
+    z, _ = O.mlp_forward(pol0, obs)
+    head = O.head_multi_discrete(z, acts) if ptype == 1 else O.head_continuous(z, acts, vmin, vmax)
+    assert torch.allclose(head[0], torch.from_numpy(g[f"{tag}.bp_logp"]), rtol=1e-5, atol=1e-5)
+    assert abs(float(head[1]) - float(g[f"{tag}.bp_entropy"][0])) < 1e-5
+    # PPOLearner.learn
+    buf = O.BufferOracle(1000, 123)
+    buf.submit(**{name: g[f"{tag}.buf.{name}"] for name in O.FIELDS})
+    L = O.PPOLearnerOracle(pol0, val0, B, epochs, plr, clr, clip, ent, mb, policy_type=ptype, var_range=(vmin, vmax))
+    grads_seen = []
+    orig = L.popt.step
+
+    def spy(params, grads):
+        grads_seen.append((L.last_grads[0], L.last_grads[1]))
+        return orig(params, grads)
+
+    L.popt.step = spy
+    rep = L.learn(buf)
+    n_steps = int(g[f"{tag}.n_steps"][0])
+    assert len(grads_seen) == n_steps == epochs * (total // B)
+    for s in range(n_steps):
+        for i, gr in enumerate(grads_seen[s][0]):
+            ref = torch.from_numpy(g[f"{tag}.pgrad{s}.{i}"])
+            assert ((gr - ref).norm() / ref.norm()) < 2e-5, ("pgrad", s, i, float((gr - ref).norm() / ref.norm()))
+        for i, gr in enumerate(grads_seen[s][1]):
+            ref = torch.from_numpy(g[f"{tag}.vgrad{s}.{i}"])
+            assert ((gr - ref).norm() / ref.norm()) < 2e-5, ("vgrad", s, i)
+    for i, p in enumerate(L.pol):
+        assert torch.allclose(p, torch.from_numpy(g[f"{tag}.pol1.{i}"]), rtol=0, atol=2e-6), ("pol", i)
+    for i, p in enumerate(L.val):
+        assert torch.allclose(p, torch.from_numpy(g[f"{tag}.val1.{i}"]), rtol=0, atol=2e-6), ("val", i)
+    ref_rep = dict(zip(g[f"{tag}.report.keys"], g[f"{tag}.report.vals"]))
+    for k, v in rep.items():
+        assert abs(v - ref_rep[k]) <= 1e-4 * max(abs(ref_rep[k]), 1.0), (k, v, ref_rep[k])
+    assert ref_rep["SB3 Clip Fraction"] > 0.2
