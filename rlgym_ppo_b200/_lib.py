@@ -63,6 +63,8 @@ _SIGS = {
     "rlppo_peer_flag_bytes": ([], ctypes.c_size_t),
     "rlppo_norm_clip_adam_peers": ([_P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P,
                                     ctypes.c_size_t, _P], _I),
+    "rlppo_norm_clip_adam_peers2": ([_P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P,
+                                     ctypes.c_size_t, _P], _I),
     "rlppo_sqdiff": ([_P, _P, _P, _I, _P, _P], _I),
 }
 

@@ -134,8 +134,12 @@ struct Peers {
     unsigned int* flags[kMaxPeers];
     float* gsum;                      // local f32[total]: the summed gradient (read back in the update phase)
     int rank, world;
+    // two-shot form only: every rank's `gsum` buffer as mapped here (symmetric memory; red[rank] == gsum)
+    const float* red[kMaxPeers];
 };
-constexpr int kFlagDone = 32, kFlagEpoch = 64;
+constexpr int kFlagDone = 32, kFlagEpoch = 64, kFlagReduced = 96;
+// kernel modes: 0 = one rank (gradients in g), 1 = one-shot peer exchange, 2 = two-shot peer exchange (EXPERIMENTAL)
+constexpr int kModeLocal = 0, kModeOneShot = 1, kModeTwoShot = 2;
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -155,16 +159,17 @@ __device__ __forceinline__ void wait_epoch(const unsigned int* p, unsigned int e
 }
 
 struct FusedWs {
-    unsigned int arrive, depart, pad[2];
+    unsigned int arrive, depart, arrive2, pad;   // arrive2: the two-shot form's extra grid barrier
     float partial[1];    // [gridDim.x][kMaxSeg]
 };
 
-template <bool PEERS>
+template <int MODE>
 __global__ void __launch_bounds__(kFusedThreads)
 norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                       Segs segs, float* __restrict__ sqnorm_out, const float* __restrict__ lr,
                       int64_t* __restrict__ step_count, float max_norm, double beta1d, double beta2d, float eps,
                       Views views, FusedWs* __restrict__ ws, const Peers pr) {
+    constexpr bool PEERS = MODE != kModeLocal;
     const float beta2 = (float)beta2d, omb1 = (float)(1.0 - beta1d), omb2 = (float)(1.0 - beta2d);
     __shared__ float s_w[kFusedThreads / 32][kMaxSeg];
     __shared__ float s_coef[kMaxSeg], s_step_size[kMaxSeg], s_bc2_sqrt[kMaxSeg];
@@ -196,7 +201,77 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     // order as the one-rank kernel; the loads of four elements x all peers are issued before anything is summed: a loop of
     // dependent loads paid one NVLink round trip per peer and element (measured on 8 GPUs: no faster than NCCL).
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
-    if (PEERS) {
+    if (MODE == kModeTwoShot) {
+        // EXPERIMENTAL (not selected by default; see PPOLearner dp_collective="p2p2"): reduce-scatter + all-gather inside
+        // the launch.  (a) this rank sums ITS slice of every peer's arena into its own `gsum` (which the peers have
+        // mapped), (b) grid barrier, "slice reduced" flags, (c) every rank reads all reduced slices from their owners.
+        // 2 * 4n bytes over NVLink per rank instead of (R-1) * 4n: the form for big arenas on many ranks.
+        const int64_t slice = ((total + pr.world - 1) / pr.world + 3) & ~(int64_t)3;
+        const int64_t lo = slice * pr.rank < total ? slice * pr.rank : total;
+        const int64_t hi = lo + slice < total ? lo + slice : total;
+        for (int64_t i0 = lo + gtid; i0 < hi; i0 += 4 * gthreads) {
+            float xs[4][kMaxPeers];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * gthreads;
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; ++r)
+                    if (i < hi && r < pr.world) xs[e][r] = __ldcg(pr.grads[r] + i);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * gthreads;
+                if (i < hi) {
+                    float x = xs[e][0];
+#pragma unroll
+                    for (int r = 1; r < kMaxPeers; ++r)
+                        if (r < pr.world) x += xs[e][r];
+                    __stcg(pr.gsum + i, x);
+                }
+            }
+        }
+        // grid barrier on its own counter, then tell the peers that this rank's slice is reduced and wait for theirs
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&ws->arrive2, 1u);
+            const long long t0 = clock64();
+            while ((unsigned)rlppo::ld_acquire_s32(reinterpret_cast<const int*>(&ws->arrive2)) < gridDim.x)
+                if (clock64() - t0 > 8000000000LL) __trap();
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x < pr.world) {
+            __threadfence_system();
+            st_release_sys(pr.flags[threadIdx.x] + kFlagReduced + pr.rank, epoch);
+        }
+        if (threadIdx.x < pr.world) wait_epoch(pr.flags[pr.rank] + kFlagReduced + threadIdx.x, epoch);
+        __syncthreads();
+        // (c) gather: the one-rank kernel's thread <-> element mapping and accumulation order
+        for (int64_t i0 = gtid; i0 < total; i0 += 4 * gthreads) {
+            float xs[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * gthreads;
+                if (i < total) {
+                    int64_t o = i / slice;
+                    xs[e] = __ldcg(pr.red[o] + i);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * gthreads;
+                if (i < total) {
+                    const float x = xs[e];
+                    if (i < lo || i >= hi) pr.gsum[i] = x;       // own slice is already in place
+                    const int k = seg_of(segs, i);
+#pragma unroll
+                    for (int j = 0; j < kMaxSeg; ++j)
+                        if (j == k) acc[j] = fmaf(x, x, acc[j]);
+                }
+            }
+        }
+    }
+    if (MODE == kModeOneShot) {
         for (int64_t i0 = gtid; i0 < total; i0 += 4 * gthreads) {
             float xs[4][kMaxPeers];
 #pragma unroll
@@ -315,6 +390,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
         if (old == gridDim.x - 1) {
             ws->arrive = 0;
             ws->depart = 0;
+            if (MODE == kModeTwoShot) ws->arrive2 = 0;
             if (PEERS) {
                 // the launch may only end once every peer has finished reading this rank's gradients
                 for (int r = 0; r < pr.world; ++r) wait_epoch(pr.flags[pr.rank] + kFlagDone + r, epoch);
@@ -328,7 +404,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
 int fused_grid(int64_t total, int* out) {
     static int per_sm = 0;
     if (per_sm == 0) {
-        RLPPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, norm_clip_adam_kernel<true>, kFusedThreads, 0));
+        RLPPO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, norm_clip_adam_kernel<kModeOneShot>, kFusedThreads, 0));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;
     }
@@ -396,12 +472,16 @@ static int launch_norm_clip_adam(float* params, const float* grads, const Peers*
     int grid = 1;
     rc = fused_grid(segs.off[n_seg], &grid);
     if (rc) return rc;
-    if (peers != nullptr)
-        norm_clip_adam_kernel<true><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    if (peers != nullptr && peers->red[0] != nullptr)
+        norm_clip_adam_kernel<kModeTwoShot><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            params, nullptr, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
+            static_cast<FusedWs*>(ws), *peers);
+    else if (peers != nullptr)
+        norm_clip_adam_kernel<kModeOneShot><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
             params, nullptr, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
             static_cast<FusedWs*>(ws), *peers);
     else
-        norm_clip_adam_kernel<false><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        norm_clip_adam_kernel<kModeLocal><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
             params, grads, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
             static_cast<FusedWs*>(ws), Peers{});
     RLPPO_LAUNCH_CHECK();
@@ -434,6 +514,28 @@ int rlppo_norm_clip_adam_peers(float* params, const float* const* h_peer_grads, 
         pr.flags[r] = static_cast<unsigned int*>(h_peer_flags[r]);
     }
     pr.gsum = gsum;
+    pr.rank = rank;
+    pr.world = world;
+    return launch_norm_clip_adam(params, nullptr, &pr, m, v, h_seg_off, n_seg, sqnorm_out, lr, step_count, max_norm,
+                                 beta1, beta2, eps, h_views, n_views, ws, ws_bytes, stream);
+}
+
+int rlppo_norm_clip_adam_peers2(float* params, const float* const* h_peer_grads, void* const* h_peer_flags,
+                                const float* const* h_peer_red, int rank, int world, float* m, float* v,
+                                const int64_t* h_seg_off, int n_seg, float* sqnorm_out, const float* lr,
+                                int64_t* step_count, double max_norm, double beta1, double beta2, double eps,
+                                const rlppo_bf16_view* h_views, int n_views, void* ws, size_t ws_bytes, void* stream) {
+    RLPPO_CHECK_ARG(h_peer_grads && h_peer_flags && h_peer_red, "null pointer");
+    RLPPO_CHECK_ARG(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "rank %d of %d (at most %d peers)", rank,
+                    world, kMaxPeers);
+    Peers pr{};
+    for (int r = 0; r < world; ++r) {
+        RLPPO_CHECK_ARG(h_peer_grads[r] && h_peer_flags[r] && h_peer_red[r], "null peer pointer %d", r);
+        pr.grads[r] = h_peer_grads[r];
+        pr.flags[r] = static_cast<unsigned int*>(h_peer_flags[r]);
+        pr.red[r] = h_peer_red[r];
+    }
+    pr.gsum = const_cast<float*>(h_peer_red[rank]);
     pr.rank = rank;
     pr.world = world;
     return launch_norm_clip_adam(params, nullptr, &pr, m, v, h_seg_off, n_seg, sqnorm_out, lr, step_count, max_norm,

@@ -331,6 +331,26 @@ def norm_clip_adam_peers(params, peer_grad_ptrs, peer_flag_ptrs, rank, gsum, m, 
          ptr(ws), ws.numel(), stream_ptr(), work=("byte", (32 + 4 * world) * int(so[-1])))
 
 
+def norm_clip_adam_peers2(params, peer_grad_ptrs, peer_flag_ptrs, peer_red_ptrs, rank, m, v, seg_off, sqnorm_out, lr,
+                          step_count, max_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-8, views=None):
+    """EXPERIMENTAL two-shot form of norm_clip_adam_peers (rlppo_norm_clip_adam_peers2); the summed gradient ends up in
+    this rank's reduced buffer (peer_red_ptrs[rank])."""
+    so = _seg(seg_off)
+    ws = _nca_ws.get(params.device)
+    if ws is None:
+        ws = torch.zeros(int(_lib._lib.rlppo_norm_clip_adam_workspace_bytes()), dtype=torch.uint8, device=params.device)
+        _nca_ws[params.device] = ws
+    world = len(peer_grad_ptrs)
+    gp = (ctypes.c_void_p * world)(*[int(x) for x in peer_grad_ptrs])
+    fp = (ctypes.c_void_p * world)(*[int(x) for x in peer_flag_ptrs])
+    rp = (ctypes.c_void_p * world)(*[int(x) for x in peer_red_ptrs])
+    call("rlppo_norm_clip_adam_peers2", ptr(params), ctypes.cast(gp, ctypes.c_void_p), ctypes.cast(fp, ctypes.c_void_p),
+         ctypes.cast(rp, ctypes.c_void_p), int(rank), world, ptr(m), ptr(v), so.ctypes.data, len(so) - 1, ptr(sqnorm_out),
+         ptr(lr), ptr(step_count), float(max_norm), float(beta1), float(beta2), float(eps),
+         None if views is None else ctypes.cast(views, ctypes.c_void_p), 0 if views is None else len(views),
+         ptr(ws), ws.numel(), stream_ptr(), work=("byte", 48 * int(so[-1])))
+
+
 def sqdiff(a, b, seg_off, out):
     so = _seg(seg_off)
     call("rlppo_sqdiff", ptr(a), ptr(b), so.ctypes.data, len(so) - 1, ptr(out), stream_ptr(),

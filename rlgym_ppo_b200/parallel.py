@@ -43,14 +43,15 @@ def choose_collective(world_size, n_params, requested=None, env=None):
     The one-shot peer exchange makes every rank read all (R-1) peer arenas, (R-1) * 4 * n bytes over NVLink per step:
     latency-optimal for the example-size nets, but a ring / tree all-reduce moves ~2 * 4 * n bytes however many ranks
     there are, so big arenas default to NCCL.  Peer mappings exist inside one box only (at most 8 ranks).
-    `requested` (constructor argument) wins over `env` (RLPPO_DP_COLLECTIVE) which wins over the size rule."""
+    `requested` (constructor argument) wins over `env` (RLPPO_DP_COLLECTIVE) which wins over the size rule.
+    "p2p2" (EXPERIMENTAL, never chosen by the size rule): the two-shot form, rlppo_norm_clip_adam_peers2."""
     if world_size <= 1:
         return "none"
     auto = "p2p" if (world_size - 1) * 4 * int(n_params) <= ONE_SHOT_BYTES else "nccl"
     choice = requested or env or auto
-    if choice not in ("p2p", "nccl"):
-        raise ValueError(f"dp_collective must be 'p2p' or 'nccl', got {choice!r}")
-    if choice == "p2p" and world_size > 8:
+    if choice not in ("p2p", "nccl", "p2p2"):
+        raise ValueError(f"dp_collective must be 'p2p', 'nccl' or 'p2p2', got {choice!r}")
+    if choice in ("p2p", "p2p2") and world_size > 8:
         choice = "nccl"
     return choice
 

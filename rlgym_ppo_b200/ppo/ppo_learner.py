@@ -97,7 +97,7 @@ class PPOLearner(object):
         if self.world_size > 1:
             self.dp_collective = parallel.choose_collective(self.world_size, n_p + n_v, dp_collective,
                                                             os.environ.get("RLPPO_DP_COLLECTIVE"))
-            if self.dp_collective == "p2p":
+            if self.dp_collective in ("p2p", "p2p2"):
                 # Peer mappings need NVLink / P2P between all ranks' GPUs.  If the rendezvous fails on ANY rank, every rank
                 # switches to the NCCL exchange (agreed through one all-reduce, so no rank is left waiting on flags).
                 import torch.distributed as dist
@@ -109,7 +109,7 @@ class PPOLearner(object):
                 ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._pg)
                 if int(ok.item()) == 0:
-                    if dp_collective == "p2p":
+                    if dp_collective in ("p2p", "p2p2"):
                         raise _lib.RlppoError(f"dp_collective='p2p' requested but peer mappings are unavailable: {err}")
                     print(f"[rlgym_ppo_b200] rank {self.rank}: symmetric-memory peer mappings unavailable ({err}); "
                           "gradients go through NCCL all_reduce", file=sys.stderr, flush=True)
@@ -198,10 +198,21 @@ class PPOLearner(object):
         torch.cuda.synchronize(dev)
         dist.barrier(group)                         # every rank's flag block is zero before anyone launches
         self._grads = grads
-        self._gsum = torch.zeros(n, dtype=torch.float32, device=dev)
         self._peer_grad_ptrs = [int(x) for x in gh.buffer_ptrs]
         self._peer_flag_ptrs = [int(x) for x in fh.buffer_ptrs]
         self._symm = (grads, gh, flags, fh)         # keep the mappings alive
+        if self.dp_collective == "p2p2":
+            # two-shot form (experimental): the reduced gradient lives in symmetric memory too, peers read its slices
+            gsum = symm_mem.empty(n, dtype=torch.float32, device=dev)
+            gsum.zero_()
+            rh = symm_mem.rendezvous(gsum, group)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)
+            self._gsum = gsum
+            self._peer_red_ptrs = [int(x) for x in rh.buffer_ptrs]
+            self._symm += (gsum, rh)
+        else:
+            self._gsum = torch.zeros(n, dtype=torch.float32, device=dev)
 
     # ---- workspaces ----------------------------------------------------------------------------------------
     def _minibatch_buffers(self, rows):
@@ -298,6 +309,14 @@ class PPOLearner(object):
         self.launches += n
 
     def _optimizer_step(self):
+        if self.dp_collective == "p2p2":
+            ops.norm_clip_adam_peers2(self._params, self._peer_grad_ptrs, self._peer_flag_ptrs, self._peer_red_ptrs,
+                                      self.rank, self._m, self._v, self._seg, self._sqnorm, self._lr_dev, self._steps,
+                                      max_norm=0.5, views=self._views)
+            self.policy._stack.mark_operands_fresh()
+            self.value_net._stack.mark_operands_fresh()
+            self.launches += 1
+            return
         if self.dp_collective == "p2p":
             # the all-reduce happens inside the optimiser launch (peer loads over NVLink, rank-order sum)
             ops.norm_clip_adam_peers(self._params, self._peer_grad_ptrs, self._peer_flag_ptrs, self.rank, self._gsum,
@@ -361,7 +380,7 @@ class PPOLearner(object):
         cur = self._idx_cur[:local]
         cur.copy_(idx)      # the graph reads its indices from a fixed buffer; the ring origin from exp.start_dev
         key = self._graph_key(exp, local, chunk) + (self._idx_cur.data_ptr(),)
-        if self.world_size == 1 or self.dp_collective == "p2p":
+        if self.world_size == 1 or self.dp_collective in ("p2p", "p2p2"):
             if not self._captured(("step",) + key, lambda: self._batch_body(exp, cur, local, chunk)):
                 self._batch_body(exp, cur, local, chunk)
         else:
@@ -419,7 +438,7 @@ class PPOLearner(object):
             exp.next_permutation_into(self._perm_dev[epoch, :total])
         n_iterations = E * n_batches
 
-        p2p = R > 1 and self.dp_collective == "p2p"
+        p2p = R > 1 and self.dp_collective in ("p2p", "p2p2")
         whole = (self.use_cuda_graph and _lib._TIMING is None and n_batches > 0
                  and (R == 1 or p2p or self.graph_collectives))
         if whole:

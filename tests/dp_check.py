@@ -58,7 +58,8 @@ def main():
     alone1 = learner1(solo)
     r_11 = alone1.learn(make_buffer(7, B, dev))
     g_errs = {}
-    for collective in ("p2p", "nccl"):
+    # RLPPO_TEST_P2P2=1 adds the experimental two-shot exchange (rlppo_norm_clip_adam_peers2) to the comparison
+    for collective in ("p2p", "nccl") + (("p2p2",) if os.environ.get("RLPPO_TEST_P2P2") == "1" else ()):
         dp1 = learner1(None, collective)
         assert dp1.dp_collective == collective and alone1.dp_collective == "none"
         r_dp1 = dp1.learn(make_buffer(7, B, dev))
@@ -67,7 +68,7 @@ def main():
         assert g_err < 1e-5, f"{collective}: all-reduced gradient differs from the one-rank gradient: rel-L2 {g_err}"
         for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
             assert abs(r_dp1[k] - r_11[k]) < 1e-5 * max(1.0, abs(r_11[k])), (k, r_dp1[k], r_11[k])
-        if collective == "p2p":
+        if collective in ("p2p", "p2p2"):
             # the summed gradient every rank formed from the peers' arenas is the same bits everywhere
             gathered = [torch.empty_like(dp1._gsum) for _ in range(world)]
             dist.all_gather(gathered, dp1._gsum)

@@ -88,6 +88,8 @@ def test_choose_collective():
     assert parallel.choose_collective(2, small, env="nccl") == "nccl"
     assert parallel.choose_collective(2, small, requested="p2p", env="nccl") == "p2p"
     assert parallel.choose_collective(16, small, requested="p2p") == "nccl"              # peer mappings stop at the box
+    assert parallel.choose_collective(8, big, requested="p2p2") == "p2p2"                # experimental two-shot: opt-in only
+    assert "p2p2" not in {parallel.choose_collective(r, n) for r in (2, 4, 8) for n in (small, big)}
     import pytest
     with pytest.raises(ValueError):
         parallel.choose_collective(2, small, requested="ring")
