@@ -174,27 +174,13 @@ class Learner(object):
 
         self.agent.policy = self.ppo_learner.policy
 
-        self.config = {
-            "n_proc": n_proc,
-            "min_inference_size": min_inference_size,
-            "timestep_limit": timestep_limit,
-            "exp_buffer_size": exp_buffer_size,
-            "ts_per_iteration": ts_per_iteration,
-            "standardize_returns": standardize_returns,
-            "standardize_obs": standardize_obs,
-            "policy_layer_sizes": policy_layer_sizes,
-            "critic_layer_sizes": critic_layer_sizes,
-            "ppo_epochs": ppo_epochs,
-            "ppo_batch_size": ppo_batch_size,
-            "ppo_minibatch_size": ppo_minibatch_size,
-            "ppo_ent_coef": ppo_ent_coef,
-            "ppo_clip_range": ppo_clip_range,
-            "gae_lambda": gae_lambda,
-            "gae_gamma": gae_gamma,
-            "policy_lr": policy_lr,
-            "critic_lr": critic_lr,
-            "shm_buffer_size": shm_buffer_size,
-        }
+        # hyper-parameters the reference records (and hands to wandb), learner.py:169-189
+        hp = locals()
+        self.config = {k: hp[k] for k in (
+            "n_proc", "min_inference_size", "timestep_limit", "exp_buffer_size", "ts_per_iteration",
+            "standardize_returns", "standardize_obs", "policy_layer_sizes", "critic_layer_sizes", "ppo_epochs",
+            "ppo_batch_size", "ppo_minibatch_size", "ppo_ent_coef", "ppo_clip_range", "gae_lambda", "gae_gamma",
+            "policy_lr", "critic_lr", "shm_buffer_size")}
 
         self.wandb_run = wandb_run
         wandb_loaded = checkpoint_load_folder is not None and self.load(checkpoint_load_folder, load_wandb, policy_lr,
@@ -202,28 +188,29 @@ class Learner(object):
 
         if log_to_wandb and self.wandb_run is None and not wandb_loaded:
             import wandb
-            project = "rlgym-ppo" if wandb_project_name is None else wandb_project_name
-            group = "unnamed-runs" if wandb_group_name is None else wandb_group_name
-            run_name = "rlgym-ppo-run" if wandb_run_name is None else wandb_run_name
             print("Attempting to create new wandb run...")
-            self.wandb_run = wandb.init(project=project, group=group, config=self.config, name=run_name, reinit=True)
+            self.wandb_run = wandb.init(project=wandb_project_name or "rlgym-ppo",
+                                        group=wandb_group_name or "unnamed-runs",
+                                        name=wandb_run_name or "rlgym-ppo-run", config=self.config, reinit=True)
             print("Created new wandb run!", self.wandb_run.id)
         print("Learner successfully initialized!")
 
     def update_learning_rate(self, new_policy_lr=None, new_critic_lr=None):
-        if new_policy_lr is not None:
-            self.policy_lr = new_policy_lr
-            for param_group in self.ppo_learner.policy_optimizer.param_groups:
-                param_group['lr'] = new_policy_lr
-            print(f"New policy learning rate: {new_policy_lr}")
-        if new_critic_lr is not None:
-            self.critic_lr = new_critic_lr
-            for param_group in self.ppo_learner.value_optimizer.param_groups:
-                param_group['lr'] = new_critic_lr
-            print(f"New policy learning rate: {new_policy_lr}")
+        """Set the learning rate of either optimiser (learner.py:205-216).  The device copy of the rates is refreshed by
+        PPOLearner._sync_lr at the next learn()."""
+        targets = (("policy", "policy_lr", new_policy_lr, self.ppo_learner.policy_optimizer),
+                   ("critic", "critic_lr", new_critic_lr, self.ppo_learner.value_optimizer))
+        for label, attr, lr, optimizer in targets:
+            if lr is None:
+                continue
+            setattr(self, attr, lr)
+            for group in optimizer.param_groups:
+                group["lr"] = lr
+            print(f"New {label} learning rate: {lr}")
 
     def learn(self):
-        """try / save-on-error / always-cleanup wrapper of learner.py:218-238."""
+        """Run iterations until the timestep limit; on an exception print it, try to checkpoint, and always release the
+        workers (the contract of learner.py:218-238)."""
         try:
             self._learn()
         except Exception:
@@ -232,72 +219,65 @@ class Learner(object):
             traceback.print_exc()
             try:
                 self.save(self.agent.cumulative_timesteps)
-            except:  # noqa: E722
+            except Exception:  # noqa: BLE001
                 print("FAILED TO SAVE ON EXIT")
         finally:
             self.cleanup()
 
-    def _learn(self):
+    def _iteration(self):
+        """collect -> add_new_experience -> PPOLearner.learn -> report.  Returns the number of steps collected."""
         from .util import reporting
+        t_start = time.perf_counter()
+        experience, env_metrics, n_steps, t_collect = self.agent.collect_timesteps(self.ts_per_epoch)
+        if self.metrics_logger is not None:
+            self.metrics_logger.report_metrics(env_metrics, self.wandb_run, self.agent.cumulative_timesteps)
+        self.add_new_experience(experience)
+        report = dict(self.ppo_learner.learn(self.experience_buffer))
+        t_total = time.perf_counter() - t_start
+        if self.epoch < 1:
+            report["Value Function Loss"] = np.nan      # the first iteration's critic loss is not reported (:273-274)
+        avg_rew = self.agent.average_reward
+        report.update({
+            "Cumulative Timesteps": self.agent.cumulative_timesteps,
+            "Total Iteration Time": t_total,
+            "Timesteps Collected": n_steps,
+            "Timestep Collection Time": t_collect,
+            "Timestep Consumption Time": t_total - t_collect,
+            "Collected Steps per Second": n_steps / t_collect,
+            "Overall Steps per Second": n_steps / t_total,
+            "Policy Reward": np.nan if avg_rew is None else avg_rew,
+        })
+        reporting.report_metrics(loggable_metrics=report, debug_metrics=None, wandb_run=self.wandb_run)
+        return n_steps
+
+    def _poll_keys(self, kb):
+        """p = pause until a key, c = checkpoint, q = checkpoint and stop.  Returns True when the loop should end."""
+        if not kb.kbhit():
+            return False
+        key = kb.getch()
+        if key == "p":
+            print("Paused, press any key to resume")
+            while not kb.kbhit():
+                time.sleep(0.05)
+        if key in ("c", "q"):
+            self.save(self.agent.cumulative_timesteps)
+        if key == "q":
+            return True
+        if key in ("c", "p"):
+            print("Resuming...\n")
+        return False
+
+    def _learn(self):
         from .util.kbhit import KBHit
         kb = KBHit()   # guarded: no-op without a TTY (gpurun / CI)
         print("Press (p) to pause (c) to checkpoint, (q) to checkpoint and quit (after next iteration)\n")
-
         while self.agent.cumulative_timesteps < self.timestep_limit:
-            epoch_start = time.perf_counter()
-            report = {}
-
-            experience, collected_metrics, steps_collected, collection_time = self.agent.collect_timesteps(
-                self.ts_per_epoch
-            )
-            if self.metrics_logger is not None:
-                self.metrics_logger.report_metrics(collected_metrics, self.wandb_run, self.agent.cumulative_timesteps)
-
-            self.add_new_experience(experience)
-            ppo_report = self.ppo_learner.learn(self.experience_buffer)
-
-            epoch_stop = time.perf_counter()
-            epoch_time = epoch_stop - epoch_start
-
-            report.update(ppo_report)
-            if self.epoch < 1:
-                report["Value Function Loss"] = np.nan
-            report["Cumulative Timesteps"] = self.agent.cumulative_timesteps
-            report["Total Iteration Time"] = epoch_time
-            report["Timesteps Collected"] = steps_collected
-            report["Timestep Collection Time"] = collection_time
-            report["Timestep Consumption Time"] = epoch_time - collection_time
-            report["Collected Steps per Second"] = steps_collected / collection_time
-            report["Overall Steps per Second"] = steps_collected / epoch_time
-
-            self.ts_since_last_save += steps_collected
-            if self.agent.average_reward is not None:
-                report["Policy Reward"] = self.agent.average_reward
-            else:
-                report["Policy Reward"] = np.nan
-
-            reporting.report_metrics(loggable_metrics=report, debug_metrics=None, wandb_run=self.wandb_run)
-            report.clear()
-            ppo_report.clear()
-
-            if kb.kbhit():
-                c = kb.getch()
-                if c == 'p':
-                    print("Paused, press any key to resume")
-                    while True:
-                        if kb.kbhit():
-                            break
-                if c in ('c', 'q'):
-                    self.save(self.agent.cumulative_timesteps)
-                if c == 'q':
-                    return
-                if c in ('c', 'p'):
-                    print("Resuming...\n")
-
+            self.ts_since_last_save += self._iteration()
+            if self._poll_keys(kb):
+                return
             if self.ts_since_last_save >= self.save_every_ts:
                 self.save(self.agent.cumulative_timesteps)
                 self.ts_since_last_save = 0
-
             self.epoch += 1
 
     # ---- the learner-side hot path, first half (learner.py:330-385) ------------------------------------------------
@@ -423,22 +403,11 @@ class Learner(object):
                 # one rollout per rank: the statistics follow rank 0's (the head of the concatenated rollout)
                 self.return_stats.broadcast_(src=0, group=getattr(ppo, "_pg", None))
 
-    def save(self, cumulative_timesteps):
-        """Checkpoint in the reference's layout (learner.py:387-444)."""
-        folder_path = os.path.join(self.checkpoints_save_folder, str(cumulative_timesteps))
-        os.makedirs(folder_path, exist_ok=True)
-
-        print(f"Saving checkpoint {cumulative_timesteps}...")
-        existing_checkpoints = [int(arg) for arg in os.listdir(self.checkpoints_save_folder)]
-        if len(existing_checkpoints) > self.n_checkpoints_to_keep:
-            existing_checkpoints.sort()
-            for checkpoint_name in existing_checkpoints[: -self.n_checkpoints_to_keep]:
-                shutil.rmtree(os.path.join(self.checkpoints_save_folder, str(checkpoint_name)))
-
-        os.makedirs(folder_path, exist_ok=True)
-        self.ppo_learner.save_to(folder_path)
-
-        book_keeping_vars = {
+    # ---- checkpoints: the reference's directory layout and file formats (learner.py:387-564) ---------------------
+    # <save folder>/<cumulative timesteps>/{PPO_POLICY.pt, PPO_VALUE_NET.pt, PPO_POLICY_OPTIMIZER.pt,
+    # PPO_VALUE_NET_OPTIMIZER.pt, BOOK_KEEPING_VARS.json}; at most n_checkpoints_to_keep numbered folders are kept.
+    def _book_keeping(self):
+        bk = {
             "cumulative_timesteps": self.agent.cumulative_timesteps,
             "cumulative_model_updates": self.ppo_learner.cumulative_model_updates,
             "policy_average_reward": self.agent.average_reward,
@@ -447,108 +416,87 @@ class Learner(object):
             "reward_running_stats": self.return_stats.to_json(),
         }
         if self.agent.standardize_obs:
-            book_keeping_vars["obs_running_stats"] = self.agent.obs_stats.to_json()
-        if self.standardize_returns:
-            book_keeping_vars["reward_running_stats"] = self.return_stats.to_json()
+            bk["obs_running_stats"] = self.agent.obs_stats.to_json()
+        run = self.wandb_run
+        if run is not None:
+            bk.update(wandb_run_id=run.id, wandb_project=run.project, wandb_entity=run.entity, wandb_group=run.group,
+                      wandb_config=run.config.as_dict())
+        return bk
 
-        if self.wandb_run is not None:
-            book_keeping_vars["wandb_run_id"] = self.wandb_run.id
-            book_keeping_vars["wandb_project"] = self.wandb_run.project
-            book_keeping_vars["wandb_entity"] = self.wandb_run.entity
-            book_keeping_vars["wandb_group"] = self.wandb_run.group
-            book_keeping_vars["wandb_config"] = self.wandb_run.config.as_dict()
-
-        book_keeping_table_path = os.path.join(folder_path, "BOOK_KEEPING_VARS.json")
-        with open(book_keeping_table_path, "w") as f:
-            json.dump(book_keeping_vars, f, indent=4)
+    def save(self, cumulative_timesteps):
+        root = self.checkpoints_save_folder
+        target = os.path.join(root, str(cumulative_timesteps))
+        os.makedirs(target, exist_ok=True)
+        print(f"Saving checkpoint {cumulative_timesteps}...")
+        # prune: the reference compares with ">" after creating the new folder, i.e. keeps the newest n (+ the new one)
+        numbered = sorted(int(name) for name in os.listdir(root) if name.isdigit())
+        if len(numbered) > self.n_checkpoints_to_keep:
+            for stale in numbered[:-self.n_checkpoints_to_keep]:
+                shutil.rmtree(os.path.join(root, str(stale)), ignore_errors=True)
+        os.makedirs(target, exist_ok=True)
+        self.ppo_learner.save_to(target)
+        with open(os.path.join(target, "BOOK_KEEPING_VARS.json"), "w") as f:
+            json.dump(self._book_keeping(), f, indent=4)
         print(f"Checkpoint {cumulative_timesteps} saved!\n")
 
+    def _latest_checkpoint(self):
+        """The numbered folder with the most timesteps inside the newest run folder, or None.  With add_unix_timestamp the
+        run folders are `<base>-<time_ns>` siblings and the newest stamp wins (learner.py:452-499)."""
+        run_dir = self.checkpoints_save_folder
+        if run_dir is None:
+            return None
+        if self.add_unix_timestamp:
+            base = run_dir[:run_dir.rfind("-")]
+            parent = os.path.dirname(base)
+            if not os.path.isdir(parent):
+                return None
+            stamped = []
+            for name in os.listdir(parent):
+                full = os.path.join(parent, name)
+                stamp = full[full.rfind("-") + 1:]
+                if os.path.isdir(full) and full.startswith(base) and stamp.isdigit():
+                    stamped.append((int(stamp), full))
+            if not stamped:
+                return None
+            run_dir = max(stamped)[1]
+        elif not os.path.isdir(run_dir):
+            return None
+        steps = [int(name) for name in os.listdir(run_dir)
+                 if name.isdigit() and os.path.isdir(os.path.join(run_dir, name))]
+        return os.path.join(run_dir, str(max(steps))) if steps else None
+
     def load(self, folder_path, load_wandb, new_policy_lr=None, new_critic_lr=None):
-        """Load a checkpoint written by this implementation or by the reference (learner.py:446-564)."""
+        """Load a checkpoint written by this implementation or by the reference.  Returns True when a wandb run was
+        resumed, None when `folder_path == "latest"` finds nothing."""
         if folder_path == "latest":
-            save_folder = self.checkpoints_save_folder
-            if save_folder is None:
-                return
-            if self.add_unix_timestamp:
-                base_save_folder = save_folder[:save_folder.rfind('-')]
-                save_path = os.path.dirname(base_save_folder)
-                if not os.path.exists(save_path):
-                    return
-                highest_timestamp = -1
-                best_folder = None
-                for filename in os.listdir(save_path):
-                    full_path = os.path.join(save_path, filename)
-                    if not os.path.isdir(full_path):
-                        continue
-                    if full_path.startswith(base_save_folder):
-                        unix_start_idx = full_path.rfind('-') + 1
-                        if unix_start_idx > 0:
-                            unix_time_str = full_path[unix_start_idx:]
-                            if unix_time_str.isdigit():
-                                timestamp = int(unix_time_str)
-                                if timestamp > highest_timestamp:
-                                    highest_timestamp = timestamp
-                                    best_folder = full_path
-                if best_folder is None:
-                    return
-                load_base_path = best_folder
-            else:
-                if os.path.exists(self.checkpoints_save_folder):
-                    load_base_path = self.checkpoints_save_folder
-                else:
-                    return
-
-            highest_ts = -1
-            for filename in os.listdir(load_base_path):
-                if not os.path.isdir(os.path.join(load_base_path, filename)):
-                    continue
-                if not filename.isdigit():
-                    continue
-                highest_ts = max(highest_ts, int(filename))
-            if highest_ts != -1:
-                folder_path = os.path.join(load_base_path, str(highest_ts))
-                print(f"Auto-load path: {folder_path}")
-            else:
-                return
-
+            folder_path = self._latest_checkpoint()
+            if folder_path is None:
+                return None
+            print(f"Auto-load path: {folder_path}")
         assert os.path.exists(folder_path), f"UNABLE TO LOCATE FOLDER {folder_path}"
         print(f"Loading from checkpoint at {folder_path}")
-
         self.ppo_learner.load_from(folder_path)
-
-        wandb_loaded = False
         with open(os.path.join(folder_path, "BOOK_KEEPING_VARS.json"), "r") as f:
-            book_keeping_vars = dict(json.load(f))
-            self.agent.cumulative_timesteps = book_keeping_vars["cumulative_timesteps"]
-            self.agent.average_reward = book_keeping_vars["policy_average_reward"]
-            self.ppo_learner.cumulative_model_updates = book_keeping_vars["cumulative_model_updates"]
-            self.return_stats.from_json(book_keeping_vars["reward_running_stats"])
-            if self.agent.standardize_obs and "obs_running_stats" in book_keeping_vars.keys():
-                self.agent.obs_stats = WelfordRunningStat(1, device=self.device)
-                self.agent.obs_stats.from_json(book_keeping_vars["obs_running_stats"])
-            if self.standardize_returns and "reward_running_stats" in book_keeping_vars.keys():
-                self.return_stats.from_json(book_keeping_vars["reward_running_stats"])
-            self.epoch = book_keeping_vars["epoch"]
-
-            if new_policy_lr is not None or new_critic_lr is not None:
-                self.update_learning_rate(new_policy_lr, new_critic_lr)
-
-            if "wandb_run_id" in book_keeping_vars and load_wandb:
-                import wandb
-                self.wandb_run = wandb.init(
-                    settings=wandb.Settings(start_method="spawn"),
-                    entity=book_keeping_vars["wandb_entity"],
-                    project=book_keeping_vars["wandb_project"],
-                    group=book_keeping_vars["wandb_group"],
-                    id=book_keeping_vars["wandb_run_id"],
-                    config=book_keeping_vars["wandb_config"],
-                    resume="allow",
-                    reinit=True,
-                )
-                wandb_loaded = True
-
+            bk = dict(json.load(f))
+        self.agent.cumulative_timesteps = bk["cumulative_timesteps"]
+        self.agent.average_reward = bk["policy_average_reward"]
+        self.ppo_learner.cumulative_model_updates = bk["cumulative_model_updates"]
+        self.epoch = bk["epoch"]
+        self.return_stats.from_json(bk["reward_running_stats"])
+        if self.agent.standardize_obs and "obs_running_stats" in bk:
+            self.agent.obs_stats = WelfordRunningStat(1, device=self.device)
+            self.agent.obs_stats.from_json(bk["obs_running_stats"])
+        if new_policy_lr is not None or new_critic_lr is not None:
+            self.update_learning_rate(new_policy_lr, new_critic_lr)
+        resumed = False
+        if load_wandb and "wandb_run_id" in bk:
+            import wandb
+            self.wandb_run = wandb.init(settings=wandb.Settings(start_method="spawn"), entity=bk["wandb_entity"],
+                                        project=bk["wandb_project"], group=bk["wandb_group"], id=bk["wandb_run_id"],
+                                        config=bk["wandb_config"], resume="allow", reinit=True)
+            resumed = True
         print("Checkpoint loaded!")
-        return wandb_loaded
+        return resumed
 
     def cleanup(self):
         if self.wandb_run is not None:

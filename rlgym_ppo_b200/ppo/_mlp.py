@@ -97,11 +97,17 @@ class Stack:
             off += l.weight.numel() + l.bias.numel()
         return out
 
+    def _version_sig(self):
+        """torch version counters of the flat arena AND of every nn.Parameter: bind() re-points each parameter with
+        `p.data = view`, which gives the Parameter its own counter, so load_state_dict (param.copy_) moves the
+        Parameter's counter and not the arena's."""
+        return (self.params._version,) + tuple(p._version for l in self.linears for p in (l.weight, l.bias))
+
     def mark_operands_fresh(self):
-        self._seen_version = self.params._version
+        self._seen_version = self._version_sig()
 
     def operands_stale(self):
-        return self.params._version != self._seen_version
+        return self._version_sig() != self._seen_version
 
     def refresh_operands(self, force=False):
         """fp32 master weights -> bf16 GEMM operands.  Called after every optimiser step (our kernels do not bump
@@ -110,7 +116,7 @@ class Stack:
             return
         for i in range(len(self.linears)):
             ops.weight_to_bf16(self.w[i], self.wq[i], self.wt[i])
-        self._seen_version = self.params._version
+        self._seen_version = self._version_sig()
 
     # ---- whole-network fused kernels (mlp_fused.cu) ---------------------------------------------------------------
     @property

@@ -29,6 +29,14 @@ class DiscreteFF(nn.Module):
         self._offset = 0
         self._obs_stats = None  # optional (mean, std, clip) device tensors: standardisation fused into staging
 
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """Stock nn.Module.load_state_dict into the arena views, then the bf16 GEMM operands are rebuilt at once."""
+        if assign:
+            raise RuntimeError("assign=True would detach the parameters from the flat arena the kernels read")
+        out = super().load_state_dict(state_dict, strict=strict)
+        self._stack.refresh_operands(force=True)
+        return out
+
     # nn.Module.to()/cuda()/cpu() would re-allocate parameters and silently break the arena views
     def _apply(self, fn, recurse=True):
         probe = fn(torch.empty(0, device=self._stack.device))

@@ -20,6 +20,14 @@ class ValueEstimator(nn.Module):
         dev = self._stack.device
         self._stack.bind(torch.zeros(self._stack.n_params, device=dev), torch.zeros(self._stack.n_params, device=dev))
 
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        """Stock nn.Module.load_state_dict into the arena views, then the bf16 GEMM operands are rebuilt at once."""
+        if assign:
+            raise RuntimeError("assign=True would detach the parameters from the flat arena the kernels read")
+        out = super().load_state_dict(state_dict, strict=strict)
+        self._stack.refresh_operands(force=True)
+        return out
+
     def _apply(self, fn, recurse=True):
         probe = fn(torch.empty(0, device=self._stack.device))
         if probe.device != self._stack.device or probe.dtype != torch.float32:
