@@ -203,6 +203,99 @@ int rlppo_value_head(const uint16_t* h, int64_t ldh, const float* w, const float
                      float* values_out, const float* targets, float inv_batch, uint16_t* dh, int64_t lddh,
                      float* dw, float* db, float* metrics, void* stream);
 
+/* ---- precision mode "fp32": split bf16 operands on the same tcgen05 kernels ------------------------------
+ * The reference computes its Linear layers in fp32 (torch CPU/GPU SGEMM, discrete_policy.py:22-31,
+ * value_estimator.py:19-28).  With plain bf16 operands the forward pre-activations carry ~1e-3 relative error, which
+ * flips ReLU masks of near-zero units and moves per-tensor gradients by several per cent -- outside the 1e-3 parity bar
+ * (profiles/r02_precision_study.md).  In this mode every f32 matrix is stored as `parts` bf16 matrices side by side
+ * in one buffer (value = part0 + part1 + part2; part q in columns [q*pstride, q*pstride + cols), pstride a multiple of
+ * 64 columns, padding zero) and a GEMM accumulates the products part_i(A) x part_j(B) for i + j < order into the same
+ * fp32 TMEM accumulator, smallest terms first:
+ *   forward / heads: 3 x 3 parts, order 3 -> 6 products, ~2^-24 per product (fp32-equivalent pre-activations);
+ *   dgrad / wgrad:   2 x 2 parts, order 2 -> 3 products, ~2^-16 (no branch points in the backward: linear errors only).
+ * The kernels are the ones above with a longer k loop (a "k schedule" of part pairs) and epilogues that write their
+ * f32 result as out_parts bf16 parts.  sp == NULL is the plain bf16 entry point. */
+typedef struct rlppo_split {
+    int32_t a_parts;        /* parts of the first (row) operand, 1..3 */
+    int32_t b_parts;        /* parts of the second (weight) operand, 1..3 */
+    int32_t order;          /* products kept: i + j < order */
+    int32_t out_parts;      /* parts the result is written as, 1..3 */
+    int64_t a_pstride;      /* column offset between parts of the first operand (elements) */
+    int64_t b_pstride;      /* ... of the second operand */
+    int64_t out_pstride;    /* ... of the output */
+} rlppo_split;
+/* f32 rows -> parts (optionally standardised first, as rlppo_rows_standardize_to_bf16; mean/std NULL: plain). */
+int rlppo_rows_split_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width, const float* mean,
+                          const float* std, float clip, uint16_t* dst, int64_t dst_ld, int parts, int64_t pstride,
+                          void* stream);
+/* fp32 master weight W [out,in] -> split W [out_rows, q_parts*q_pstride] (forward operand) and/or split
+ * W^T [in_rows, t_parts*t_pstride] (dgrad operand); either output may be NULL.  Padding rows/columns are zeroed. */
+int rlppo_weight_split_bf16(const float* w, int out_f, int in_f, uint16_t* wq, int64_t wq_ld, int q_parts,
+                            int64_t q_pstride, int out_rows, uint16_t* wt, int64_t wt_ld, int t_parts,
+                            int64_t t_pstride, int in_rows, void* stream);
+/* rlppo_linear_fwd / _dgrad(_db) / _wgrad / heads over split operands.  a = the row operand (x, dy, h), b = the weight
+ * operand (w, wt; for wgrad: a = dy, b = x).  The dgrad ReLU mask is read from part 0 of hprev (x > 0 <=> bf16(x) > 0);
+ * db_below / db sums take the un-split f32 values / all parts. */
+/* bias_n: entries of `bias` (0 = N): lets a Linear whose width is not a multiple of 8 (21 logits, 2n outputs) run with N
+ * padded to 8 without reading past its bias vector. */
+int rlppo_linear_fwd_split(const uint16_t* x, int64_t ldx, const uint16_t* w, int64_t ldw, const float* bias,
+                           int bias_n, uint16_t* y, int64_t ldy, int64_t M, int N, int K, int relu,
+                           const rlppo_split* sp, void* stream);
+int rlppo_linear_dgrad_split(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt,
+                             const uint16_t* hprev, int64_t ldh, uint16_t* dx, int64_t lddx, float* db_below,
+                             int64_t M, int N, int K, const rlppo_split* sp, void* stream);
+int rlppo_linear_wgrad_split(const uint16_t* dy, int64_t lddy, const uint16_t* x, int64_t ldx, float* dw,
+                             int64_t lddw, float* db, int64_t M, int N, int K, const rlppo_split* sp, void* stream);
+int rlppo_policy_head_sample_split(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw,
+                                   const float* bias, int64_t M, int n_actions, int K, const float* u_inject,
+                                   uint64_t seed, uint64_t offset, int deterministic, float* actions_out,
+                                   int64_t* actions_i64_out, float* logp_out, float* probs_out,
+                                   const rlppo_split* sp, void* stream);
+/* d(logits) is written as sp->out_parts parts of out_pstride columns each (lddz >= out_parts * out_pstride). */
+int rlppo_policy_head_train_split(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw,
+                                  const float* bias, int64_t M, int n_actions, int K, const float* actions,
+                                  const float* old_logp, const float* adv, float inv_batch, float clip,
+                                  float ent_coef, uint16_t* dz, int64_t lddz, float* logp_out, float* metrics,
+                                  const rlppo_split* sp, void* stream);
+/* rlppo_value_head with H given as h_parts parts and dH written as dh_parts parts. */
+int rlppo_value_head_split(const uint16_t* h, int64_t ldh, const float* w, const float* bias, int64_t M, int K,
+                           float* values_out, const float* targets, float inv_batch, uint16_t* dh, int64_t lddh,
+                           float* dw, float* db, float* metrics, int h_parts, int64_t h_pstride, int dh_parts,
+                           int64_t dh_pstride, void* stream);
+
+/* ---- (f-4) the other two action heads: multi_discrete_policy.py:16-89, continuous_policy.py:23-120 ------------
+ * Per-row tails over the output of the policy's last Linear (run it with rlppo_linear_fwd_split, relu = 0, out_parts = 3:
+ * z = the logits as split bf16 parts, fp32-exact).  z view: z [M, ldz], z_parts parts z_pstride columns apart.
+ *
+ * MultiDiscrete (21 logits = 8 categoricals with bins 3,3,3,3,3,2,2,2; torch_functions.py:81-122): log-prob and entropy
+ * are SUMMED over the 8 distributions, the entropy then averaged over the minibatch.
+ *   _train: get_backprop_data (:74-89) + the PPO loss block (ppo_learner.py:153-177) + its backward into the logits:
+ *     actions f32 [M, >= 8] (bin index per distribution, as stored by the buffer), dz written as dz_parts bf16 parts of
+ *     dz_cols columns (columns past 21 zeroed), metrics as rlppo_policy_head_train ([0] = sum of row entropies).
+ *   _sample: get_action (:44-72): inverse-CDF draw per distribution (u_inject f32 [M,8] or Philox(seed, offset + row)),
+ *     deterministic != 0: per-distribution argmax; actions_out f32 [M, ld_aout >= 8], logp_out f32 [M]. */
+int rlppo_head_multi_discrete_train(const uint16_t* z, int64_t ldz, int z_parts, int64_t z_pstride, int64_t M,
+                                    const float* actions, int64_t ld_act, const float* old_logp, const float* adv,
+                                    float inv_batch, float clip, float ent_coef, uint16_t* dz, int64_t lddz,
+                                    int dz_parts, int64_t dz_pstride, int dz_cols, float* logp_out, float* metrics,
+                                    void* stream);
+int rlppo_head_multi_discrete_sample(const uint16_t* z, int64_t ldz, int z_parts, int64_t z_pstride, int64_t M,
+                                     const float* u_inject, uint64_t seed, uint64_t offset, int deterministic,
+                                     float* actions_out, int64_t ld_aout, float* logp_out, void* stream);
+/* Continuous (2n outputs -> Tanh; mean = first n, std = second n mapped onto [var_min, var_max]; diagonal Gaussian):
+ *   _train: the reference's four-term log-pdf summed over the n actions (continuous_policy.py:40-59, :112), entropy =
+ *     mean of Normal.entropy() over all M*n elements (:117-118), PPO block, backward through the affine map and Tanh.
+ *   _sample: action = clamp(mean + std * N(0,1), -1, 1) (:91-92) with Box-Muller normals from Philox (n_inject f32 [M,n]
+ *     overrides them); deterministic != 0: action = mean, log-prob 0 (:87-89). */
+int rlppo_head_continuous_train(const uint16_t* z, int64_t ldz, int z_parts, int64_t z_pstride, int64_t M, int n_act,
+                                float var_min, float var_max, const float* actions, int64_t ld_act,
+                                const float* old_logp, const float* adv, float inv_batch, float clip, float ent_coef,
+                                uint16_t* dz, int64_t lddz, int dz_parts, int64_t dz_pstride, int dz_cols,
+                                float* logp_out, float* metrics, void* stream);
+int rlppo_head_continuous_sample(const uint16_t* z, int64_t ldz, int z_parts, int64_t z_pstride, int64_t M, int n_act,
+                                 float var_min, float var_max, const float* n_inject, uint64_t seed, uint64_t offset,
+                                 int deterministic, float* actions_out, int64_t ld_aout, float* logp_out, void* stream);
+
 /* ---- whole-network fused kernels (hidden widths 64/128/192/256, <= 4 hidden layers, obs <= 256, <= 128 actions) ----
  * One persistent tcgen05 kernel runs a 128-row tile of samples through the WHOLE Linear/ReLU stack, the head and
  * (training) the backward data path without leaving the SM: hidden activations live in shared memory as the next

@@ -52,6 +52,19 @@ _SIGS = {
     "rlppo_policy_head_sample": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _U64, _U64, _I, _P, _P, _P, _P, _P], _I),
     "rlppo_policy_head_train": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _P, _P, _F, _F, _F, _P, _L, _P, _P, _P], _I),
     "rlppo_value_head": ([_P, _L, _P, _P, _L, _I, _P, _P, _F, _P, _L, _P, _P, _P, _P], _I),
+    "rlppo_rows_split_bf16": ([_P, _L, _L, _I, _P, _P, _F, _P, _L, _I, _L, _P], _I),
+    "rlppo_weight_split_bf16": ([_P, _I, _I, _P, _L, _I, _L, _I, _P, _L, _I, _L, _I, _P], _I),
+    "rlppo_linear_fwd_split": ([_P, _L, _P, _L, _P, _I, _P, _L, _L, _I, _I, _I, _P, _P], _I),
+    "rlppo_linear_dgrad_split": ([_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P, _P], _I),
+    "rlppo_linear_wgrad_split": ([_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P, _P], _I),
+    "rlppo_policy_head_sample_split": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _U64, _U64, _I, _P, _P, _P, _P, _P, _P], _I),
+    "rlppo_policy_head_train_split": ([_P, _L, _P, _L, _P, _L, _I, _I, _P, _P, _P, _F, _F, _F, _P, _L, _P, _P, _P, _P], _I),
+    "rlppo_value_head_split": ([_P, _L, _P, _P, _L, _I, _P, _P, _F, _P, _L, _P, _P, _P, _I, _L, _I, _L, _P], _I),
+    "rlppo_head_multi_discrete_train": ([_P, _L, _I, _L, _L, _P, _L, _P, _P, _F, _F, _F, _P, _L, _I, _L, _I, _P, _P, _P], _I),
+    "rlppo_head_multi_discrete_sample": ([_P, _L, _I, _L, _L, _P, _U64, _U64, _I, _P, _L, _P, _P], _I),
+    "rlppo_head_continuous_train": ([_P, _L, _I, _L, _L, _I, _F, _F, _P, _L, _P, _P, _F, _F, _F, _P, _L, _I, _L, _I, _P,
+                                     _P, _P], _I),
+    "rlppo_head_continuous_sample": ([_P, _L, _I, _L, _L, _I, _F, _F, _P, _U64, _U64, _I, _P, _L, _P, _P], _I),
     "rlppo_policy_train_fused": ([_P, _P, _L, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P], _I),
     "rlppo_policy_infer_fused": ([_P, _P, _L, _I, _P, _U64, _U64, _I, _P, _P, _P, _P], _I),
     "rlppo_value_train_fused": ([_P, _P, _L, _P, _P, _F, _P, _P, _P, _P], _I),
@@ -75,6 +88,12 @@ class AppendField(ctypes.Structure):
     """struct rlppo_append_field."""
     _fields_ = [("ring", _P), ("ring_ld", _L), ("ring_bf16", _P), ("bf16_ld", _L), ("src", _P), ("src_ld", _L),
                 ("src_is_f64", ctypes.c_int32), ("width", ctypes.c_int32)]
+
+
+class Split(ctypes.Structure):
+    """struct rlppo_split: split bf16 operands of the "fp32" precision mode."""
+    _fields_ = [("a_parts", ctypes.c_int32), ("b_parts", ctypes.c_int32), ("order", ctypes.c_int32),
+                ("out_parts", ctypes.c_int32), ("a_pstride", _L), ("b_pstride", _L), ("out_pstride", _L)]
 
 
 class WgradItem(ctypes.Structure):
@@ -165,7 +184,7 @@ def timing_end():
         d["ms"] += e0.elapsed_time(e1)
         if work is not None:
             for i in range(0, len(work), 2):
-                d[work[i]] += float(work[i + 1])
+                d[work[i]] = d.get(work[i], 0.0) + float(work[i + 1])
     return out
 
 

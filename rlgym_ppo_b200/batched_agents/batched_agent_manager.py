@@ -92,6 +92,12 @@ class BatchedAgentManager(object):
         return msg
 
     # ---- collection ------------------------------------------------------------------------------------------------
+    def _bf16_scratch(self, rows, width):
+        sc = getattr(self, "_bf16_sc", None)
+        if sc is None or sc.shape[0] < rows or sc.shape[1] < ops.pad8(width):
+            sc = self._bf16_sc = torch.empty((rows, ops.pad8(width)), dtype=torch.bfloat16, device=self.device)
+        return sc
+
     @torch.no_grad()
     def collect_timesteps(self, n):
         """Collect at least n timesteps.  Returns ((states, actions, log_probs, rewards, next_states, dones,
@@ -121,19 +127,23 @@ class BatchedAgentManager(object):
                 # (`self.obs_stats.mean[0]`, `.std[0]`, batched_agent_manager.py:233-235): reproduced as is
                 mean = self.obs_stats.device_mean()[0:1].expand(D).contiguous()
                 std = self.obs_stats.device_std()[0:1].expand(D).contiguous()
-                ops.rows_to_bf16(raw, ws["x"], mean, std, 5.0, dst_f32=obs_slab[t])
+                if st.exact:
+                    # "fp32" mode: standardised f32 rows first (what the trajectory stores), then the split operand
+                    ops.rows_to_bf16(raw, self._bf16_scratch(S, D), mean, std, 5.0, dst_f32=obs_slab[t])
+                    st.stage_rows(obs_slab[t], ws["x"])
+                else:
+                    ops.rows_to_bf16(raw, ws["x"], mean, std, 5.0, dst_f32=obs_slab[t])
             else:
                 obs_slab[t].copy_(self._current_obs, non_blocking=True)
-                ops.rows_to_bf16(obs_slab[t], ws["x"])
+                st.stage_rows(obs_slab[t], ws["x"])
             return ws
 
         for t in range(T):
             ws = stage(t)
             st.refresh_operands()
             h = st.forward_hidden(ws["x"], S, ws)
-            ops.policy_head_sample(h, st.wq[-1], st.b[-1], self.policy.n_actions, st.hidden[-1], M=S,
-                                   seed=self.policy._seed, offset=self.policy._offset, actions_out=act_slab[t],
-                                   logp_out=logp_slab[t])
+            st.policy_head_sample(h, S, self.policy.n_actions, seed=self.policy._seed, offset=self.policy._offset,
+                                  actions_out=act_slab[t], logp_out=logp_slab[t])
             self.policy._offset += S
             act_host.copy_(act_slab[t], non_blocking=True)
             torch.cuda.current_stream().synchronize()

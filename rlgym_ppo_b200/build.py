@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librlppo_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["common.cu", "gae_scan.cu", "stats_ring.cu", "optim.cu", "mlp_tcgen05.cu", "mlp_fused.cu", "value_head.cu", "host_rng.cpp"]
+SOURCES = ["common.cu", "gae_scan.cu", "stats_ring.cu", "optim.cu", "mlp_tcgen05.cu", "mlp_fused.cu", "value_head.cu", "heads.cu", "host_rng.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -82,14 +82,31 @@ constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 
 enum { EPI_BIAS_ACT = 0, EPI_RELU_MASK = 1, EPI_HEAD_SAMPLE = 2, EPI_HEAD_TRAIN = 3 };
 
+// Split ("fp32-exact") operands: a logical f32 matrix is stored as `parts` bf16 matrices side by side in one buffer
+// (part q in columns [q * pstride, q * pstride + cols), value = part0 + part1 + ...; see rlppo_split in rlppo.h).  A GEMM
+// over split operands is the SAME kernel running a longer k loop: schedule entry s pairs part a_off[s] of A with part
+// b_off[s] of B (column offsets in elements); all products land in one fp32 TMEM accumulator, smallest terms first.
+constexpr int MAX_SCHED = 6;
+struct KSched {
+    int n;                  // entries (0 = plain single-part operands)
+    int kpp;                // 64-wide k-blocks per entry
+    int a_off[MAX_SCHED];
+    int b_off[MAX_SCHED];
+};
+
 struct RowGemmParams {
     int64_t M;
     int N, K;
     int num_m_tiles, num_n_tiles, num_k_blocks;
+    KSched sched;
+    int out_parts;          // 1 (plain bf16 output) .. 3: the f32 result is written as hi / mid / lo bf16 parts
+    int64_t out_pstride;    // column offset between consecutive output parts (elements)
+    int out_cols;           // heads: columns of d(logits) to write per part (padding columns are written as zeros)
     // bias/act and relu-mask epilogues
     uint16_t* out;
     int64_t ldo;
     const float* bias;
+    int bias_n;             // entries of `bias` (<= N; columns past it take no bias)
     int relu;
     const uint16_t* mask;
     int64_t ldmask;
@@ -207,7 +224,7 @@ __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint
                     x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
                 } else if (p.bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) x[j] += __ldg(p.bias + col + j);
+                    for (int j = 0; j < 8; ++j) x[j] += col + j < p.bias_n ? __ldg(p.bias + col + j) : 0.f;
                 }
                 if (p.relu) {
 #pragma unroll
@@ -230,7 +247,26 @@ __device__ __forceinline__ void epilogue_store_bf16(const RowGemmParams& p, uint
             o.z = pack_bf16x2(x[4], x[5]);
             o.w = pack_bf16x2(x[6], x[7]);
             *reinterpret_cast<uint4*>(p.out + row * p.ldo + col) = o;
-            if (want_sum) {
+            if (p.out_parts > 1) {
+                // split output: part q = bf16(x - part_0 - ... - part_{q-1}); the column sums take the f32 values
+                if (want_sum) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[g * 8 + j] = x[j];
+                }
+                for (int q = 1; q < p.out_parts; ++q) {
+                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        x[2 * j] -= __uint_as_float(ow[j] << 16);
+                        x[2 * j + 1] -= __uint_as_float(ow[j] & 0xFFFF0000u);
+                    }
+                    o.x = pack_bf16x2(x[0], x[1]);
+                    o.y = pack_bf16x2(x[2], x[3]);
+                    o.z = pack_bf16x2(x[4], x[5]);
+                    o.w = pack_bf16x2(x[6], x[7]);
+                    *reinterpret_cast<uint4*>(p.out + row * p.ldo + q * p.out_pstride + col) = o;
+                }
+            } else if (want_sum) {
                 // sum what was STORED (bf16-rounded): the same values the separate column-sum pass used to read back
                 const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
@@ -422,7 +458,7 @@ __device__ __forceinline__ void epilogue_head_train(const RowGemmParams& p, uint
         }
     }
     // pass: dz_j = s_j (g_j - G) -> bf16 (padding columns up to lddz are written as zeros)
-    const int ncols_out = (int)p.ldo;
+    const int ncols_out = p.out_cols;
     const int nch_out = (ncols_out + 31) >> 5;
     for (int c = 0; c < nch_out; ++c) {
         float v[32];
@@ -452,6 +488,19 @@ __device__ __forceinline__ void epilogue_head_train(const RowGemmParams& p, uint
             o.z = pack_bf16x2(dz[g8 * 8 + 4], dz[g8 * 8 + 5]);
             o.w = pack_bf16x2(dz[g8 * 8 + 6], dz[g8 * 8 + 7]);
             *reinterpret_cast<uint4*>(p.out + row * p.ldo + col) = o;
+            for (int q = 1; q < p.out_parts; ++q) {
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dz[g8 * 8 + 2 * j] -= __uint_as_float(ow[j] << 16);
+                    dz[g8 * 8 + 2 * j + 1] -= __uint_as_float(ow[j] & 0xFFFF0000u);
+                }
+                o.x = pack_bf16x2(dz[g8 * 8 + 0], dz[g8 * 8 + 1]);
+                o.y = pack_bf16x2(dz[g8 * 8 + 2], dz[g8 * 8 + 3]);
+                o.z = pack_bf16x2(dz[g8 * 8 + 4], dz[g8 * 8 + 5]);
+                o.w = pack_bf16x2(dz[g8 * 8 + 6], dz[g8 * 8 + 7]);
+                *reinterpret_cast<uint4*>(p.out + row * p.ldo + q * p.out_pstride + col) = o;
+            }
         }
     }
     if (row_ok && p.logp_out) p.logp_out[row] = logp;
@@ -510,7 +559,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = threadIdx.x; i < BLOCK_N; i += kThreads) s_bias[i] = 0.f;     // column-sum accumulators
     } else if (EPI == EPI_BIAS_ACT) {
         if (p.bias != nullptr && p.N <= (int)L::AUX_FLOATS)                        // the whole layer's bias vector
-            for (int i = threadIdx.x; i < (int)L::AUX_FLOATS; i += kThreads) s_bias[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
+            for (int i = threadIdx.x; i < (int)L::AUX_FLOATS; i += kThreads) s_bias[i] = i < p.bias_n ? __ldg(p.bias + i) : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -523,12 +572,22 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t stage = 0, phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int m_blk = t / p.num_n_tiles, n_blk = t % p.num_n_tiles;
+                int se = 0, sj = 0;       // schedule entry, k-block inside it
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], L::STAGE);
                     uint8_t* sa = smem + stage * L::STAGE;
-                    tma_load_2d(&tmA, &full[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
-                    tma_load_2d(&tmB, &full[stage], sa + A_BYTES, kb * BLOCK_K, n_blk * BLOCK_N);
+                    int ka = kb * BLOCK_K, kbb = kb * BLOCK_K;
+                    if (p.sched.n > 0) {
+                        ka = p.sched.a_off[se] + sj * BLOCK_K;
+                        kbb = p.sched.b_off[se] + sj * BLOCK_K;
+                        if (++sj == p.sched.kpp) {
+                            sj = 0;
+                            ++se;
+                        }
+                    }
+                    tma_load_2d(&tmA, &full[stage], sa, ka, m_blk * BLOCK_M);
+                    tma_load_2d(&tmB, &full[stage], sa + A_BYTES, kbb, n_blk * BLOCK_N);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -618,6 +677,9 @@ struct WgradParams {
     int64_t lddw;
     int64_t m_per_split;  // multiple of BLOCK_K
     int splits, n_tiles_n, n_tiles_k;
+    // split operands: per 64-row block, n_sched (X part, dY part) pairs accumulate into the same tile (0 = plain)
+    int n_sched;
+    int x_off[MAX_SCHED], dy_off[MAX_SCHED];
 };
 
 template <int BN>
@@ -661,30 +723,35 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const int64_t m1 = min(p.M, m0 + p.m_per_split);
     const int nkb = m1 > m0 ? (int)((m1 - m0 + BLOCK_K - 1) / BLOCK_K) : 0;
 
+    const int nsch = p.n_sched > 0 ? p.n_sched : 1;
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int kb = 0; kb < nkb; ++kb) {
+              const int mrow = (int)(m0 + (int64_t)kb * BLOCK_K);
+              for (int se = 0; se < nsch; ++se) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], STAGE);
                 uint8_t* sx = smem + stage * STAGE;
-                const int mrow = (int)(m0 + (int64_t)kb * BLOCK_K);
+                const int xo = p.n_sched > 0 ? p.x_off[se] : 0, yo = p.n_sched > 0 ? p.dy_off[se] : 0;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) tma_load_2d(&tmX, &full[stage], sx + c * CHUNK, k_tile * 128 + c * 64, mrow);
+                for (int c = 0; c < 2; ++c)
+                    tma_load_2d(&tmX, &full[stage], sx + c * CHUNK, xo + k_tile * 128 + c * 64, mrow);
 #pragma unroll
                 for (int c = 0; c < BN / 64; ++c)
-                    tma_load_2d(&tmDY, &full[stage], sx + XA_BYTES + c * CHUNK, n_tile * BN + c * 64, mrow);
+                    tma_load_2d(&tmDY, &full[stage], sx + XA_BYTES + c * CHUNK, yo + n_tile * BN + c * 64, mrow);
                 if (++stage == kStages) {
                     stage = 0;
                     phase ^= 1;
                 }
+              }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);  // both operands MN-major
             uint32_t stage = 0, phase = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb * nsch; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + stage * STAGE);
@@ -949,7 +1016,7 @@ int launch_rowgemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, RowGemmPara
     }
     p.num_m_tiles = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
     p.num_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-    p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    p.num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K * (p.sched.n > 0 ? p.sched.n : 1);
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < num_sms() ? tiles : num_sms();
     kfn<<<grid, kThreads, L::TOTAL, s>>>(tmA, tmB, p);
@@ -957,17 +1024,50 @@ int launch_rowgemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, RowGemmPara
     return RLPPO_OK;
 }
 
+// Fills the k schedule of a GEMM over split operands: every (i, j) with i < a_parts, j < b_parts, i + j < order,
+// ordered by decreasing i + j so that the smallest products are accumulated first.
+int fill_sched(const rlppo_split* sp, int K, int* n, int* a_off, int* b_off) {
+    *n = 0;
+    if (sp == nullptr) return RLPPO_OK;
+    RLPPO_CHECK_ARG(sp->a_parts >= 1 && sp->a_parts <= 3 && sp->b_parts >= 1 && sp->b_parts <= 3 && sp->order >= 1 &&
+                        sp->order <= 3 && sp->out_parts >= 1 && sp->out_parts <= 3,
+                    "split: parts and order must be in [1,3]");
+    const int Kp = (K + 63) / 64 * 64;
+    RLPPO_CHECK_ARG((sp->a_parts == 1 || (sp->a_pstride % 64 == 0 && sp->a_pstride >= Kp)) &&
+                        (sp->b_parts == 1 || (sp->b_pstride % 64 == 0 && sp->b_pstride >= Kp)),
+                    "split: part strides must be multiples of 64 columns and cover the contraction width");
+    for (int sum = sp->order - 1; sum >= 0; --sum)
+        for (int i = 0; i < sp->a_parts; ++i) {
+            const int j = sum - i;
+            if (j < 0 || j >= sp->b_parts) continue;
+            RLPPO_CHECK_ARG(*n < MAX_SCHED, "split: too many products");
+            a_off[*n] = (int)(i * sp->a_pstride);
+            b_off[*n] = (int)(j * sp->b_pstride);
+            ++*n;
+        }
+    return RLPPO_OK;
+}
+
 template <int EPI>
 int launch_rowgemm(const uint16_t* a, int64_t lda, const uint16_t* b, int64_t ldb, int64_t b_rows,
-                   RowGemmParams& p, int min_block_n, cudaStream_t s) {
+                   RowGemmParams& p, int min_block_n, const rlppo_split* sp, cudaStream_t s) {
     RLPPO_CHECK_ARG(p.M >= 1 && p.N >= 1 && p.K >= 1, "empty GEMM");
     RLPPO_CHECK_ARG(p.M < (1ll << 31), "M too large for TMA coordinates");
     int bn = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
     if (bn < min_block_n) bn = min_block_n;
-    CUtensorMap tmA, tmB;
-    int rc = make_tmap_bf16_2d(&tmA, a, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda, BLOCK_M);
+    int rc = fill_sched(sp, p.K, &p.sched.n, p.sched.a_off, p.sched.b_off);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tmB, b, (uint64_t)b_rows, (uint64_t)p.K, (uint64_t)ldb, (uint32_t)bn);
+    p.sched.kpp = (p.K + BLOCK_K - 1) / BLOCK_K;
+    p.out_parts = sp ? sp->out_parts : 1;
+    p.out_pstride = sp ? sp->out_pstride : 0;
+    RLPPO_CHECK_ARG(p.out_parts == 1 || p.out_pstride % 8 == 0, "split: output part stride must be a multiple of 8");
+    // split operands: the tensor maps span all parts (the k schedule addresses them by column offset)
+    const uint64_t a_cols = sp && sp->a_parts > 1 ? (uint64_t)lda : (uint64_t)p.K;
+    const uint64_t b_cols = sp && sp->b_parts > 1 ? (uint64_t)ldb : (uint64_t)p.K;
+    CUtensorMap tmA, tmB;
+    rc = make_tmap_bf16_2d(&tmA, a, (uint64_t)p.M, a_cols, (uint64_t)lda, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmB, b, (uint64_t)b_rows, b_cols, (uint64_t)ldb, (uint32_t)bn);
     if (rc) return rc;
     if (EPI == EPI_HEAD_SAMPLE || EPI == EPI_HEAD_TRAIN) {
         if (bn <= 128) return launch_rowgemm_t<128, EPI>(tmA, tmB, p, s);
@@ -997,19 +1097,27 @@ int launch_wgrad_t(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradP
 
 extern "C" {
 
-int rlppo_linear_fwd(const uint16_t* x, int64_t ldx, const uint16_t* w, int64_t ldw, const float* bias, uint16_t* y,
-                     int64_t ldy, int64_t M, int N, int K, int relu, void* stream) {
+int rlppo_linear_fwd_split(const uint16_t* x, int64_t ldx, const uint16_t* w, int64_t ldw, const float* bias,
+                           int bias_n, uint16_t* y, int64_t ldy, int64_t M, int N, int K, int relu,
+                           const rlppo_split* sp, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(x && w && y, "null pointer");
     RLPPO_CHECK_ARG(N % 8 == 0 && ldy >= N && ldy % 8 == 0, "N and ldy must be multiples of 8");
+    RLPPO_CHECK_ARG(bias_n >= 0 && bias_n <= N, "bias_n must be in [0, N]");
     RowGemmParams p{};
     p.M = M; p.N = N; p.K = K;
-    p.out = y; p.ldo = ldy; p.bias = bias; p.relu = relu;
-    return launch_rowgemm<EPI_BIAS_ACT>(x, ldx, w, ldw, N, p, 0, static_cast<cudaStream_t>(stream));
+    p.out = y; p.ldo = ldy; p.bias = bias; p.bias_n = bias_n > 0 ? bias_n : N; p.relu = relu;
+    return launch_rowgemm<EPI_BIAS_ACT>(x, ldx, w, ldw, N, p, 0, sp, static_cast<cudaStream_t>(stream));
 }
 
-int rlppo_linear_dgrad(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt, const uint16_t* hprev,
-                       int64_t ldh, uint16_t* dx, int64_t lddx, int64_t M, int N, int K, void* stream) {
+int rlppo_linear_fwd(const uint16_t* x, int64_t ldx, const uint16_t* w, int64_t ldw, const float* bias, uint16_t* y,
+                     int64_t ldy, int64_t M, int N, int K, int relu, void* stream) {
+    return rlppo_linear_fwd_split(x, ldx, w, ldw, bias, 0, y, ldy, M, N, K, relu, nullptr, stream);
+}
+
+int rlppo_linear_dgrad_split(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt, const uint16_t* hprev,
+                             int64_t ldh, uint16_t* dx, int64_t lddx, float* db_below, int64_t M, int N, int K,
+                             const rlppo_split* sp, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(dy && wt && dx, "null pointer");
     RLPPO_CHECK_ARG(K % 8 == 0 && lddx >= K && lddx % 8 == 0, "K and lddx must be multiples of 8");
@@ -1017,27 +1125,25 @@ int rlppo_linear_dgrad(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int
     // dX[M,K] = dY[M,N] * (W^T)[K,N]^T : the GEMM's "N" is K (in features), its contraction runs over N
     RowGemmParams p{};
     p.M = M; p.N = K; p.K = N;
-    p.out = dx; p.ldo = lddx; p.mask = hprev; p.ldmask = ldh;
-    return launch_rowgemm<EPI_RELU_MASK>(dy, lddy, wt, ldwt, K, p, 0, static_cast<cudaStream_t>(stream));
+    p.out = dx; p.ldo = lddx; p.mask = hprev; p.ldmask = ldh; p.colsum = db_below;
+    return launch_rowgemm<EPI_RELU_MASK>(dy, lddy, wt, ldwt, K, p, 0, sp, static_cast<cudaStream_t>(stream));
+}
+
+int rlppo_linear_dgrad(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt, const uint16_t* hprev,
+                       int64_t ldh, uint16_t* dx, int64_t lddx, int64_t M, int N, int K, void* stream) {
+    return rlppo_linear_dgrad_split(dy, lddy, wt, ldwt, hprev, ldh, dx, lddx, nullptr, M, N, K, nullptr, stream);
 }
 
 int rlppo_linear_dgrad_db(const uint16_t* dy, int64_t lddy, const uint16_t* wt, int64_t ldwt, const uint16_t* hprev,
                           int64_t ldh, uint16_t* dx, int64_t lddx, float* db_below, int64_t M, int N, int K,
                           void* stream) {
-    RLPPO_REQUIRE_DEVICE();
-    RLPPO_CHECK_ARG(dy && wt && dx, "null pointer");
-    RLPPO_CHECK_ARG(K % 8 == 0 && lddx >= K && lddx % 8 == 0, "K and lddx must be multiples of 8");
-    RLPPO_CHECK_ARG(!hprev || ldh % 8 == 0, "ldh must be a multiple of 8");
-    RowGemmParams p{};
-    p.M = M; p.N = K; p.K = N;
-    p.out = dx; p.ldo = lddx; p.mask = hprev; p.ldmask = ldh; p.colsum = db_below;
-    return launch_rowgemm<EPI_RELU_MASK>(dy, lddy, wt, ldwt, K, p, 0, static_cast<cudaStream_t>(stream));
+    return rlppo_linear_dgrad_split(dy, lddy, wt, ldwt, hprev, ldh, dx, lddx, db_below, M, N, K, nullptr, stream);
 }
 
-int rlppo_policy_head_sample(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw, const float* bias,
-                             int64_t M, int n_actions, int K, const float* u_inject, uint64_t seed, uint64_t offset,
-                             int deterministic, float* actions_out, int64_t* actions_i64_out, float* logp_out,
-                             float* probs_out, void* stream) {
+int rlppo_policy_head_sample_split(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw, const float* bias,
+                                   int64_t M, int n_actions, int K, const float* u_inject, uint64_t seed,
+                                   uint64_t offset, int deterministic, float* actions_out, int64_t* actions_i64_out,
+                                   float* logp_out, float* probs_out, const rlppo_split* sp, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(h && w, "null pointer");
     RLPPO_CHECK_ARG(n_actions >= 1 && n_actions <= 256, "n_actions must be in [1,256]");
@@ -1046,29 +1152,48 @@ int rlppo_policy_head_sample(const uint16_t* h, int64_t ldh, const uint16_t* w, 
     p.bias = bias; p.n_actions = n_actions;
     p.u_inject = u_inject; p.seed = seed; p.offset = offset; p.deterministic = deterministic;
     p.actions_out = actions_out; p.actions_i64_out = actions_i64_out; p.logp_out = logp_out; p.probs_out = probs_out;
-    return launch_rowgemm<EPI_HEAD_SAMPLE>(h, ldh, w, ldw, n_actions, p, 128, static_cast<cudaStream_t>(stream));
+    return launch_rowgemm<EPI_HEAD_SAMPLE>(h, ldh, w, ldw, n_actions, p, 128, sp, static_cast<cudaStream_t>(stream));
+}
+
+int rlppo_policy_head_sample(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw, const float* bias,
+                             int64_t M, int n_actions, int K, const float* u_inject, uint64_t seed, uint64_t offset,
+                             int deterministic, float* actions_out, int64_t* actions_i64_out, float* logp_out,
+                             float* probs_out, void* stream) {
+    return rlppo_policy_head_sample_split(h, ldh, w, ldw, bias, M, n_actions, K, u_inject, seed, offset, deterministic,
+                                          actions_out, actions_i64_out, logp_out, probs_out, nullptr, stream);
+}
+
+int rlppo_policy_head_train_split(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw, const float* bias,
+                                  int64_t M, int n_actions, int K, const float* actions, const float* old_logp,
+                                  const float* adv, float inv_batch, float clip, float ent_coef, uint16_t* dz,
+                                  int64_t lddz, float* logp_out, float* metrics, const rlppo_split* sp, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(h && w && actions && old_logp && adv && dz, "null pointer");
+    RLPPO_CHECK_ARG(n_actions >= 1 && n_actions <= 256, "n_actions must be in [1,256]");
+    // columns written per output part: the whole (padded) row of d(logits)
+    const int64_t cols = sp && sp->out_parts > 1 ? sp->out_pstride : lddz;
+    RLPPO_CHECK_ARG(cols >= n_actions && cols % 8 == 0 && cols <= 256 && lddz >= cols && lddz % 8 == 0,
+                    "d(logits) row width must be a multiple of 8 in [n_actions,256]");
+    RowGemmParams p{};
+    p.M = M; p.N = (n_actions + 7) / 8 * 8; p.K = K;
+    p.bias = bias; p.n_actions = n_actions;
+    p.actions = actions; p.old_logp = old_logp; p.adv = adv;
+    p.inv_batch = inv_batch; p.clip = clip; p.ent_coef = ent_coef;
+    p.out = dz; p.ldo = lddz; p.out_cols = (int)cols; p.logp_out = logp_out; p.metrics = metrics;
+    const int min_bn = cols > 128 ? 256 : 128;
+    return launch_rowgemm<EPI_HEAD_TRAIN>(h, ldh, w, ldw, n_actions, p, min_bn, sp, static_cast<cudaStream_t>(stream));
 }
 
 int rlppo_policy_head_train(const uint16_t* h, int64_t ldh, const uint16_t* w, int64_t ldw, const float* bias,
                             int64_t M, int n_actions, int K, const float* actions, const float* old_logp,
                             const float* adv, float inv_batch, float clip, float ent_coef, uint16_t* dz, int64_t lddz,
                             float* logp_out, float* metrics, void* stream) {
-    RLPPO_REQUIRE_DEVICE();
-    RLPPO_CHECK_ARG(h && w && actions && old_logp && adv && dz, "null pointer");
-    RLPPO_CHECK_ARG(n_actions >= 1 && n_actions <= 256, "n_actions must be in [1,256]");
-    RLPPO_CHECK_ARG(lddz >= n_actions && lddz % 8 == 0 && lddz <= 256, "lddz must be a multiple of 8 in [n_actions,256]");
-    RowGemmParams p{};
-    p.M = M; p.N = (n_actions + 7) / 8 * 8; p.K = K;
-    p.bias = bias; p.n_actions = n_actions;
-    p.actions = actions; p.old_logp = old_logp; p.adv = adv;
-    p.inv_batch = inv_batch; p.clip = clip; p.ent_coef = ent_coef;
-    p.out = dz; p.ldo = lddz; p.logp_out = logp_out; p.metrics = metrics;
-    const int min_bn = lddz > 128 ? 256 : 128;
-    return launch_rowgemm<EPI_HEAD_TRAIN>(h, ldh, w, ldw, n_actions, p, min_bn, static_cast<cudaStream_t>(stream));
+    return rlppo_policy_head_train_split(h, ldh, w, ldw, bias, M, n_actions, K, actions, old_logp, adv, inv_batch, clip,
+                                         ent_coef, dz, lddz, logp_out, metrics, nullptr, stream);
 }
 
-int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int64_t ldx, float* dw, int64_t lddw,
-                       float* db, int64_t M, int N, int K, void* stream) {
+int rlppo_linear_wgrad_split(const uint16_t* dy, int64_t lddy, const uint16_t* x, int64_t ldx, float* dw, int64_t lddw,
+                             float* db, int64_t M, int N, int K, const rlppo_split* sp, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(dy && x && dw && M >= 1 && N >= 1 && K >= 1, "bad argument");
     RLPPO_CHECK_ARG(M < (1ll << 31), "M too large for TMA coordinates");
@@ -1079,6 +1204,16 @@ int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int6
     p.M = M; p.N = N; p.K = K; p.dw = dw; p.lddw = lddw;
     p.n_tiles_n = (N + bn - 1) / bn;
     p.n_tiles_k = (K + 127) / 128;
+    // split operands: a = dY (contraction over rows, so the "width" the parts must cover is N), b = X (width K)
+    if (sp != nullptr) {
+        rlppo_split t = *sp;
+        const int Np = (N + 63) / 64 * 64, Kp = (K + 63) / 64 * 64;
+        RLPPO_CHECK_ARG((t.a_parts == 1 || t.a_pstride >= Np) && (t.b_parts == 1 || t.b_pstride >= Kp),
+                        "split: part strides must cover the operand widths");
+        // fill_sched validates strides against ONE contraction width; here the two operands have different widths
+        int rc0 = fill_sched(&t, 1, &p.n_sched, p.dy_off, p.x_off);
+        if (rc0) return rc0;
+    }
     const int tiles = p.n_tiles_n * p.n_tiles_k;
     const int64_t kblocks = (M + BLOCK_K - 1) / BLOCK_K;
     int64_t splits = num_sms() / tiles;
@@ -1087,8 +1222,9 @@ int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int6
     p.m_per_split = ((kblocks + splits - 1) / splits) * BLOCK_K;
     p.splits = (int)((M + p.m_per_split - 1) / p.m_per_split);
     // the tensor maps expose the padded widths (ld) so 64-wide boxes past N / K read zeros or padding
-    const uint64_t x_cols = (uint64_t)min((int64_t)((K + 7) / 8 * 8), ldx);
-    const uint64_t dy_cols = (uint64_t)min((int64_t)((N + 7) / 8 * 8), lddy);
+    const bool xs = sp && sp->b_parts > 1, ys = sp && sp->a_parts > 1;
+    const uint64_t x_cols = xs ? (uint64_t)ldx : (uint64_t)min((int64_t)((K + 7) / 8 * 8), ldx);
+    const uint64_t dy_cols = ys ? (uint64_t)lddy : (uint64_t)min((int64_t)((N + 7) / 8 * 8), lddy);
     CUtensorMap tmX, tmDY;
     int rc = make_tmap_bf16_2d(&tmX, x, (uint64_t)M, x_cols, (uint64_t)ldx, 64);
     if (rc) return rc;
@@ -1110,10 +1246,19 @@ int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int6
         const unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
         int threads = 256;
         if (threads < n8 / 8) threads = n8 / 8;
-        colsum_kernel<<<blocks, threads, n8 * sizeof(float), s>>>(dy, lddy, M, N, n8, db, rows_per_block);
-        RLPPO_LAUNCH_CHECK();
+        const int dy_parts = sp ? sp->a_parts : 1;
+        for (int q = 0; q < dy_parts; ++q) {     // every part of a split dY contributes to the column sums
+            colsum_kernel<<<blocks, threads, n8 * sizeof(float), s>>>(dy + (sp ? q * sp->a_pstride : 0), lddy, M, N, n8, db,
+                                                                      rows_per_block);
+            RLPPO_LAUNCH_CHECK();
+        }
     }
     return RLPPO_OK;
+}
+
+int rlppo_linear_wgrad(const uint16_t* dy, int64_t lddy, const uint16_t* x, int64_t ldx, float* dw, int64_t lddw,
+                       float* db, int64_t M, int N, int K, void* stream) {
+    return rlppo_linear_wgrad_split(dy, lddy, x, ldx, dw, lddw, db, M, N, K, nullptr, stream);
 }
 
 int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream) {

@@ -247,6 +247,66 @@ __global__ void weight_to_bf16_kernel(const float* __restrict__ w, int out_f, in
     }
 }
 
+
+// ---- split ("fp32-exact") operands: f32 -> hi / mid / lo bf16 parts side by side (rlppo_split in rlppo.h) ----------
+// part 0 = bf16(x), part q = bf16(x - part_0 - ... - part_{q-1}); three parts carry 24 significand bits.
+template <bool STANDARDIZE>
+__global__ void rows_split_kernel(const float* __restrict__ src, int64_t src_ld, int64_t n_rows, int width,
+                                  const float* __restrict__ mean, const float* __restrict__ stdv, float clip,
+                                  uint16_t* __restrict__ dst, int64_t dst_ld, int parts, int64_t pstride) {
+    const int64_t total = n_rows * pstride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / pstride;
+        const int c = (int)(i - row * pstride);
+        float x = 0.f;
+        if (c < width) {
+            x = __ldg(src + row * src_ld + c);
+            if (STANDARDIZE) {  // batched_agent_manager.py:303-315
+                x = __fdiv_rn(__fsub_rn(x, __ldg(mean + c)), __ldg(stdv + c));
+                x = fminf(fmaxf(x, -clip), clip);
+            }
+        }
+        for (int q = 0; q < parts; ++q) {
+            const uint16_t b = rlppo::f32_to_bf16_bits(x);
+            dst[row * dst_ld + q * pstride + c] = b;
+            x -= rlppo::bf16_bits_to_f32(b);
+        }
+    }
+}
+
+__global__ void weight_split_kernel(const float* __restrict__ w, int out_f, int in_f, uint16_t* __restrict__ wq,
+                                    int64_t wq_ld, int q_parts, int64_t q_pstride, int out_rows,
+                                    uint16_t* __restrict__ wt, int64_t wt_ld, int t_parts, int64_t t_pstride, int in_rows) {
+    __shared__ float tile[32][33];
+    const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int o = o0 + r, i = i0 + threadIdx.x;
+        float x = (o < out_f && i < in_f) ? w[(int64_t)o * in_f + i] : 0.f;
+        tile[r][threadIdx.x] = x;
+        if (wq != nullptr && o < out_rows && i < q_pstride) {
+            for (int q = 0; q < q_parts; ++q) {
+                const uint16_t b = rlppo::f32_to_bf16_bits(x);
+                wq[(int64_t)o * wq_ld + q * q_pstride + i] = b;
+                x -= rlppo::bf16_bits_to_f32(b);
+            }
+        }
+    }
+    if (wt == nullptr) return;
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, o = o0 + threadIdx.x;
+        if (i < in_rows && o < t_pstride) {
+            float x = tile[threadIdx.x][r];
+            for (int q = 0; q < t_parts; ++q) {
+                const uint16_t b = rlppo::f32_to_bf16_bits(x);
+                wt[(int64_t)i * wt_ld + q * t_pstride + o] = b;
+                x -= rlppo::bf16_bits_to_f32(b);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -394,6 +454,44 @@ int rlppo_weight_to_bf16(const float* w, int out_f, int in_f, uint16_t* wq, int6
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
     weight_to_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(w, out_f, in_f, wq, wq_ld, out_pad, wt,
                                                                                  wt_ld, in_pad);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_rows_split_bf16(const float* src, int64_t src_ld, int64_t n_rows, int width, const float* mean,
+                          const float* stdv, float clip, uint16_t* dst, int64_t dst_ld, int parts, int64_t pstride,
+                          void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(src && dst && n_rows >= 0 && parts >= 1 && parts <= 3 && pstride >= width &&
+                        dst_ld >= (int64_t)parts * pstride, "bad argument");
+    RLPPO_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "mean and std go together");
+    if (n_rows == 0) return RLPPO_OK;
+    const int64_t total = n_rows * pstride;
+    const unsigned blocks = (unsigned)min((int64_t)rlppo::num_sms() * 16, (total + 255) / 256);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (mean != nullptr)
+        rows_split_kernel<true><<<blocks, 256, 0, s>>>(src, src_ld, n_rows, width, mean, stdv, clip, dst, dst_ld, parts, pstride);
+    else
+        rows_split_kernel<false><<<blocks, 256, 0, s>>>(src, src_ld, n_rows, width, nullptr, nullptr, 0.f, dst, dst_ld, parts,
+                                                        pstride);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
+int rlppo_weight_split_bf16(const float* w, int out_f, int in_f, uint16_t* wq, int64_t wq_ld, int q_parts,
+                            int64_t q_pstride, int out_rows, uint16_t* wt, int64_t wt_ld, int t_parts, int64_t t_pstride,
+                            int in_rows, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(w && out_f >= 1 && in_f >= 1 && (wq || wt), "bad argument");
+    RLPPO_CHECK_ARG(!wq || (q_parts >= 1 && q_parts <= 3 && q_pstride >= in_f && wq_ld >= (int64_t)q_parts * q_pstride &&
+                            out_rows >= out_f), "bad forward operand shape");
+    RLPPO_CHECK_ARG(!wt || (t_parts >= 1 && t_parts <= 3 && t_pstride >= out_f && wt_ld >= (int64_t)t_parts * t_pstride &&
+                            in_rows >= in_f), "bad transposed operand shape");
+    const int cols = (int)max((int64_t)(wt ? in_rows : in_f), wq ? q_pstride : (int64_t)0);
+    const int rows = (int)max((int64_t)(wq ? out_rows : out_f), wt ? t_pstride : (int64_t)0);
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    weight_split_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(w, out_f, in_f, wq, wq_ld, q_parts, q_pstride,
+                                                                               out_rows, wt, wt_ld, t_parts, t_pstride, in_rows);
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }

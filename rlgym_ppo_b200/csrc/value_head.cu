@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(kThreads)
 value_head_kernel(const uint16_t* __restrict__ h, int64_t ldh, const float* __restrict__ w, const float* __restrict__ bias,
                   int64_t M, int K, float* __restrict__ values_out, const float* __restrict__ targets, float inv_batch,
                   uint16_t* __restrict__ dh, int64_t lddh, float* __restrict__ dw, float* __restrict__ db,
-                  float* __restrict__ metrics) {
+                  float* __restrict__ metrics, int h_parts, int64_t h_pstride, int dh_parts, int64_t dh_pstride) {
     extern __shared__ float s_mem[];   // [K] dw partials (TRAIN)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = K >> 3;
@@ -52,6 +52,17 @@ value_head_kernel(const uint16_t* __restrict__ h, int64_t ldh, const float* __re
                 hv[i][2 * j] = __uint_as_float(u[j] << 16);
                 hv[i][2 * j + 1] = __uint_as_float(u[j] & 0xFFFF0000u);
             }
+            // split activations (rlppo_split): H = part0 + part1 + ..., parts h_pstride columns apart
+            for (int pt = 1; pt < h_parts; ++pt) {
+                uint4 q2 = make_uint4(0, 0, 0, 0);
+                if (c < nvec) q2 = __ldg(reinterpret_cast<const uint4*>(h + row * ldh + pt * h_pstride) + c);
+                const uint32_t u2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hv[i][2 * j] += __uint_as_float(u2[j] << 16);
+                    hv[i][2 * j + 1] += __uint_as_float(u2[j] & 0xFFFF0000u);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) dot = fmaf(hv[i][j], wreg[i][j], dot);
         }
@@ -81,6 +92,19 @@ value_head_kernel(const uint16_t* __restrict__ h, int64_t ldh, const float* __re
                     q.z = rlppo::pack_bf16x2(o[4], o[5]);
                     q.w = rlppo::pack_bf16x2(o[6], o[7]);
                     reinterpret_cast<uint4*>(dh + row * lddh)[c] = q;
+                    for (int pt = 1; pt < dh_parts; ++pt) {
+                        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            o[2 * j] -= __uint_as_float(qq[j] << 16);
+                            o[2 * j + 1] -= __uint_as_float(qq[j] & 0xFFFF0000u);
+                        }
+                        q.x = rlppo::pack_bf16x2(o[0], o[1]);
+                        q.y = rlppo::pack_bf16x2(o[2], o[3]);
+                        q.z = rlppo::pack_bf16x2(o[4], o[5]);
+                        q.w = rlppo::pack_bf16x2(o[6], o[7]);
+                        reinterpret_cast<uint4*>(dh + row * lddh + pt * dh_pstride)[c] = q;
+                    }
                 }
             }
         }
@@ -109,36 +133,51 @@ value_head_kernel(const uint16_t* __restrict__ h, int64_t ldh, const float* __re
 template <int NI>
 int launch(const uint16_t* h, int64_t ldh, const float* w, const float* bias, int64_t M, int K, float* values_out,
            const float* targets, float inv_batch, uint16_t* dh, int64_t lddh, float* dw, float* db, float* metrics,
-           cudaStream_t s) {
+           int h_parts, int64_t h_pstride, int dh_parts, int64_t dh_pstride, cudaStream_t s) {
     const int64_t want = (M + kWarps - 1) / kWarps;
     const int64_t cap = (int64_t)rlppo::num_sms() * 8;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     if (targets != nullptr)
         value_head_kernel<NI, true><<<grid, kThreads, K * sizeof(float), s>>>(h, ldh, w, bias, M, K, values_out, targets,
-                                                                             inv_batch, dh, lddh, dw, db, metrics);
+                                                                             inv_batch, dh, lddh, dw, db, metrics,
+                                                                             h_parts, h_pstride, dh_parts, dh_pstride);
     else
         value_head_kernel<NI, false><<<grid, kThreads, 0, s>>>(h, ldh, w, bias, M, K, values_out, nullptr, 0.f, nullptr, 0,
-                                                               nullptr, nullptr, nullptr);
+                                                               nullptr, nullptr, nullptr, h_parts, h_pstride, 1, 0);
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }
 
 }  // namespace
 
-extern "C" int rlppo_value_head(const uint16_t* h, int64_t ldh, const float* w, const float* bias, int64_t M, int K,
-                                float* values_out, const float* targets, float inv_batch, uint16_t* dh, int64_t lddh,
-                                float* dw, float* db, float* metrics, void* stream) {
+extern "C" int rlppo_value_head_split(const uint16_t* h, int64_t ldh, const float* w, const float* bias, int64_t M,
+                                      int K, float* values_out, const float* targets, float inv_batch, uint16_t* dh,
+                                      int64_t lddh, float* dw, float* db, float* metrics, int h_parts, int64_t h_pstride,
+                                      int dh_parts, int64_t dh_pstride, void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(h && w && M >= 1, "bad argument");
     RLPPO_CHECK_ARG(K % 8 == 0 && K >= 8 && K <= 2048 && ldh % 8 == 0, "K must be a multiple of 8 in [8,2048]");
     RLPPO_CHECK_ARG((reinterpret_cast<uintptr_t>(h) & 15) == 0, "H must be 16-byte aligned");
+    RLPPO_CHECK_ARG(h_parts >= 1 && h_parts <= 3 && dh_parts >= 1 && dh_parts <= 3 && h_pstride % 8 == 0 &&
+                        dh_pstride % 8 == 0 && (h_parts == 1 || h_pstride >= K) && (dh_parts == 1 || dh_pstride >= K),
+                    "split: 1..3 parts, strides multiples of 8 covering K");
     if (targets != nullptr) {
         RLPPO_CHECK_ARG(dh && dw && lddh % 8 == 0 && lddh >= K, "training mode needs dh (ld %% 8) and dw");
         RLPPO_CHECK_ARG((reinterpret_cast<uintptr_t>(dh) & 15) == 0, "dH must be 16-byte aligned");
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (K <= 256) return launch<1>(h, ldh, w, bias, M, K, values_out, targets, inv_batch, dh, lddh, dw, db, metrics, s);
-    if (K <= 512) return launch<2>(h, ldh, w, bias, M, K, values_out, targets, inv_batch, dh, lddh, dw, db, metrics, s);
-    if (K <= 1024) return launch<4>(h, ldh, w, bias, M, K, values_out, targets, inv_batch, dh, lddh, dw, db, metrics, s);
-    return launch<8>(h, ldh, w, bias, M, K, values_out, targets, inv_batch, dh, lddh, dw, db, metrics, s);
+#define RLPPO_VH(NI_) launch<NI_>(h, ldh, w, bias, M, K, values_out, targets, inv_batch, dh, lddh, dw, db, metrics, h_parts, \
+                                  h_pstride, dh_parts, dh_pstride, s)
+    if (K <= 256) return RLPPO_VH(1);
+    if (K <= 512) return RLPPO_VH(2);
+    if (K <= 1024) return RLPPO_VH(4);
+    return RLPPO_VH(8);
+#undef RLPPO_VH
+}
+
+extern "C" int rlppo_value_head(const uint16_t* h, int64_t ldh, const float* w, const float* bias, int64_t M, int K,
+                                float* values_out, const float* targets, float inv_batch, uint16_t* dh, int64_t lddh,
+                                float* dw, float* db, float* metrics, void* stream) {
+    return rlppo_value_head_split(h, ldh, w, bias, M, K, values_out, targets, inv_batch, dh, lddh, dw, db, metrics, 1, 0, 1,
+                                  0, stream);
 }

@@ -348,7 +348,8 @@ class Learner(object):
             stage["next_states"].record_stream(late)
         obs = int(d["states"].shape[1])
         if buf._rings is None:
-            buf._allocate(obs)
+            a_shape = tuple(d["actions"].shape)
+            buf._allocate(obs, int(a_shape[1]) if len(a_shape) == 2 else 1)
         vst.workspace(n + 1)
         vst.refresh_operands()
         ret_std = self.return_stats.device_std() if self.standardize_returns else None     # learner.py:356
@@ -359,8 +360,8 @@ class Learner(object):
             (learner.py:347-352), GAE (:358-366), return statistics (:368-372), the nine ring appends (:375-385)."""
             states = _f32(d["states"])
             x = vst.workspace(n + 1)["x"]
-            ops.rows_to_bf16(states, x)
-            ops.rows_to_bf16(_f32(d["ns_last"]) if late_ns else _f32(d["next_states"])[n - 1:n], x[n:n + 1])
+            vst.stage_rows(states, x)
+            vst.stage_rows(_f32(d["ns_last"]) if late_ns else _f32(d["next_states"])[n - 1:n], x[n:n + 1])
             values = value_net.values_from_bf16(x, n + 1, out=stage["values"])      # stays on the device
             vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
                                  self.gae_lambda, ret_std, out=stage["out"], ret_head64=stage["head"],
@@ -390,7 +391,7 @@ class Learner(object):
         if graphs is None:
             graphs = self._add_graphs = GraphCache()
         key = (n, obs, stage["gen"], tuple(ptrs), late_ns, buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
-               float(self.gae_gamma), float(self.gae_lambda), bool(self.standardize_returns), vst.fused_ok)
+               float(self.gae_gamma), float(self.gae_lambda), bool(self.standardize_returns), vst.fused_ok, vst.precision)
         if not (getattr(ppo, "use_cuda_graph", False) and _lib._TIMING is None and graphs.replay(key, body)):
             body()
         if late_ns:

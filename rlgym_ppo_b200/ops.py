@@ -160,18 +160,67 @@ def weight_to_bf16(w, wq, wt=None):
          work=("byte", out_f * in_f * (4 + 2 + (2 if wt is not None else 0))))
 
 
+# ---- split ("fp32" precision mode) operands: value = part0 + part1 + part2, parts `pstride` columns apart ---------
+def pad64(n):
+    return (int(n) + 63) // 64 * 64
+
+
+def make_split(a_parts, b_parts, order, out_parts, a_pstride, b_pstride, out_pstride=0):
+    """struct rlppo_split; kept alive by the caller for the duration of the call (ctypes.byref)."""
+    sp = _lib.Split()
+    sp.a_parts, sp.b_parts, sp.order, sp.out_parts = int(a_parts), int(b_parts), int(order), int(out_parts)
+    sp.a_pstride, sp.b_pstride, sp.out_pstride = int(a_pstride), int(b_pstride), int(out_pstride)
+    return sp
+
+
+def _n_products(sp):
+    return sum(1 for i in range(sp.a_parts) for j in range(sp.b_parts) if i + j < sp.order)
+
+
+def _sp(sp):
+    return None if sp is None else ctypes.byref(sp)
+
+
+def rows_split(src, dst, parts, pstride, mean=None, std=None, clip=5.0):
+    """f32 [n, width] -> `parts` bf16 parts side by side in dst [>= n, >= parts * pstride] (optionally standardised)."""
+    n_rows, width = src.shape
+    assert dst.dtype == BF16 and dst.shape[0] >= n_rows and src.dtype == torch.float32
+    call("rlppo_rows_split_bf16", ptr(src), src.stride(0), n_rows, width, ptr(mean), ptr(std), float(clip), ptr(dst),
+         dst.stride(0), int(parts), int(pstride), stream_ptr(), work=("byte", n_rows * (4 * width + 2 * parts * pstride)))
+
+
+def weight_split(w, wq, q_parts, q_pstride, wt=None, t_parts=0, t_pstride=0):
+    out_f, in_f = w.shape
+    assert w.is_contiguous()
+    call("rlppo_weight_split_bf16", ptr(w), out_f, in_f, ptr(wq), 0 if wq is None else wq.stride(0), int(q_parts),
+         int(q_pstride), 0 if wq is None else wq.shape[0], ptr(wt), 0 if wt is None else wt.stride(0), int(t_parts),
+         int(t_pstride), 0 if wt is None else wt.shape[0], stream_ptr(),
+         work=("byte", out_f * in_f * (4 + 2 * q_parts + 2 * t_parts)))
+
+
 # ---- tensor-core layers -------------------------------------------------------------------------------------
-def linear_fwd(x, wq, bias, y, N, K, relu, M=None):
+def linear_fwd(x, wq, bias, y, N, K, relu, M=None, split=None, bias_n=0):
     M = x.shape[0] if M is None else M
+    if split is not None:
+        call("rlppo_linear_fwd_split", ptr(x), x.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(bias_n), ptr(y),
+             y.stride(0), int(M), int(N), int(K), int(bool(relu)), _sp(split), stream_ptr(),
+             work=("flop", 2.0 * M * N * K, "mma_flop", 2.0 * M * N * K * _n_products(split),
+                   "byte", 2.0 * (M * K * split.a_parts + N * K * split.b_parts + M * N * split.out_parts)))
+        return
     call("rlppo_linear_fwd", ptr(x), x.stride(0), ptr(wq), wq.stride(0), ptr(bias), ptr(y), y.stride(0), int(M),
          int(N), int(K), int(bool(relu)), stream_ptr(),
          work=("flop", 2.0 * M * N * K, "byte", 2.0 * (M * K + N * K + M * N)))
 
 
-def linear_dgrad(dy, wt, hprev, dx, N, K, M=None, db_below=None):
+def linear_dgrad(dy, wt, hprev, dx, N, K, M=None, db_below=None, split=None):
     """db_below (optional f32[K]): += column sums of dx, the bias gradient of the layer below (fused into the epilogue)."""
     M = dy.shape[0] if M is None else M
     work = ("flop", 2.0 * M * N * K, "byte", 2.0 * (M * N + N * K + M * K * (2 if hprev is not None else 1)))
+    if split is not None:
+        call("rlppo_linear_dgrad_split", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
+             0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), ptr(db_below), int(M), int(N), int(K),
+             _sp(split), stream_ptr(), work=work)
+        return
     if db_below is None:
         call("rlppo_linear_dgrad", ptr(dy), dy.stride(0), ptr(wt), wt.stride(0), ptr(hprev),
              0 if hprev is None else hprev.stride(0), ptr(dx), dx.stride(0), int(M), int(N), int(K), stream_ptr(),
@@ -182,8 +231,13 @@ def linear_dgrad(dy, wt, hprev, dx, N, K, M=None, db_below=None):
              stream_ptr(), work=work)
 
 
-def linear_wgrad(dy, x, dw, db, N, K, M=None):
+def linear_wgrad(dy, x, dw, db, N, K, M=None, split=None):
     M = dy.shape[0] if M is None else M
+    if split is not None:
+        call("rlppo_linear_wgrad_split", ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(dw), dw.stride(0), ptr(db),
+             int(M), int(N), int(K), _sp(split), stream_ptr(),
+             work=("flop", 2.0 * M * N * K, "byte", 2.0 * M * (N * split.a_parts + K * split.b_parts) + 4.0 * N * K))
+        return
     call("rlppo_linear_wgrad", ptr(dy), dy.stride(0), ptr(x), x.stride(0), ptr(dw), dw.stride(0), ptr(db), int(M),
          int(N), int(K), stream_ptr(), work=("flop", 2.0 * M * N * K, "byte", 2.0 * M * (N + K) + 4.0 * N * K))
 
@@ -204,8 +258,14 @@ def wgrad_multi(items, M):
 
 
 def policy_head_sample(h, wq, bias, n_actions, K, M=None, u=None, seed=0, offset=0, deterministic=False,
-                       actions_out=None, actions_i64_out=None, logp_out=None, probs_out=None):
+                       actions_out=None, actions_i64_out=None, logp_out=None, probs_out=None, split=None):
     M = h.shape[0] if M is None else M
+    if split is not None:
+        call("rlppo_policy_head_sample_split", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M),
+             int(n_actions), int(K), ptr(u), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
+             int(bool(deterministic)), ptr(actions_out), ptr(actions_i64_out), ptr(logp_out), ptr(probs_out),
+             _sp(split), stream_ptr(), work=("flop", 2.0 * M * n_actions * K))
+        return
     call("rlppo_policy_head_sample", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M), int(n_actions),
          int(K), ptr(u), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), int(bool(deterministic)),
          ptr(actions_out), ptr(actions_i64_out), ptr(logp_out), ptr(probs_out), stream_ptr(),
@@ -213,19 +273,63 @@ def policy_head_sample(h, wq, bias, n_actions, K, M=None, u=None, seed=0, offset
 
 
 def policy_head_train(h, wq, bias, n_actions, K, actions, old_logp, adv, inv_batch, clip, ent_coef, dz, metrics,
-                      logp_out=None, M=None):
+                      logp_out=None, M=None, split=None):
     M = h.shape[0] if M is None else M
+    if split is not None:
+        call("rlppo_policy_head_train_split", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M),
+             int(n_actions), int(K), ptr(actions), ptr(old_logp), ptr(adv), float(inv_batch), float(clip),
+             float(ent_coef), ptr(dz), dz.stride(0), ptr(logp_out), ptr(metrics), _sp(split), stream_ptr(),
+             work=("flop", 2.0 * M * n_actions * K))
+        return
     call("rlppo_policy_head_train", ptr(h), h.stride(0), ptr(wq), wq.stride(0), ptr(bias), int(M), int(n_actions),
          int(K), ptr(actions), ptr(old_logp), ptr(adv), float(inv_batch), float(clip), float(ent_coef), ptr(dz),
          dz.stride(0), ptr(logp_out), ptr(metrics), stream_ptr(), work=("flop", 2.0 * M * n_actions * K))
 
 
 def value_head(h, w, bias, K, values_out=None, targets=None, inv_batch=0.0, dh=None, dw=None, db=None, metrics=None,
-               M=None):
+               M=None, h_parts=1, h_pstride=0, dh_parts=1, dh_pstride=0):
     M = h.shape[0] if M is None else M
+    if h_parts > 1 or dh_parts > 1:
+        call("rlppo_value_head_split", ptr(h), h.stride(0), ptr(w), ptr(bias), int(M), int(K), ptr(values_out),
+             ptr(targets), float(inv_batch), ptr(dh), 0 if dh is None else dh.stride(0), ptr(dw), ptr(db), ptr(metrics),
+             int(h_parts), int(h_pstride), int(dh_parts), int(dh_pstride), stream_ptr(),
+             work=("byte", M * K * 2 * (h_parts + (dh_parts if targets is not None else 0)) + 8 * M))
+        return
     call("rlppo_value_head", ptr(h), h.stride(0), ptr(w), ptr(bias), int(M), int(K), ptr(values_out), ptr(targets),
          float(inv_batch), ptr(dh), 0 if dh is None else dh.stride(0), ptr(dw), ptr(db), ptr(metrics), stream_ptr(),
          work=("byte", M * K * 2 * (2 if targets is not None else 1) + 4 * M * (2 if targets is not None else 1)))
+
+
+# ---- the other two action heads (rlppo_head_*: per-row tails over the split logits of the last Linear) ----------------
+def head_multi_discrete_train(z, z_parts, z_pstride, M, actions, old_logp, adv, inv_batch, clip, ent_coef, dz, dz_parts,
+                              dz_pstride, dz_cols, metrics, logp_out=None):
+    call("rlppo_head_multi_discrete_train", ptr(z), z.stride(0), int(z_parts), int(z_pstride), int(M), ptr(actions),
+         actions.stride(0), ptr(old_logp), ptr(adv), float(inv_batch), float(clip), float(ent_coef), ptr(dz), dz.stride(0),
+         int(dz_parts), int(dz_pstride), int(dz_cols), ptr(logp_out), ptr(metrics), stream_ptr(),
+         work=("byte", M * (2 * 21 * z_parts + 2 * dz_cols * dz_parts + 4 * 11)))
+
+
+def head_multi_discrete_sample(z, z_parts, z_pstride, M, actions_out, logp_out, u=None, seed=0, offset=0,
+                               deterministic=False):
+    call("rlppo_head_multi_discrete_sample", ptr(z), z.stride(0), int(z_parts), int(z_pstride), int(M), ptr(u),
+         int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), int(bool(deterministic)), ptr(actions_out),
+         actions_out.stride(0), ptr(logp_out), stream_ptr(), work=("byte", M * (2 * 21 * z_parts + 4 * 9)))
+
+
+def head_continuous_train(z, z_parts, z_pstride, M, n_act, var_min, var_max, actions, old_logp, adv, inv_batch, clip,
+                          ent_coef, dz, dz_parts, dz_pstride, dz_cols, metrics, logp_out=None):
+    call("rlppo_head_continuous_train", ptr(z), z.stride(0), int(z_parts), int(z_pstride), int(M), int(n_act),
+         float(var_min), float(var_max), ptr(actions), actions.stride(0), ptr(old_logp), ptr(adv), float(inv_batch),
+         float(clip), float(ent_coef), ptr(dz), dz.stride(0), int(dz_parts), int(dz_pstride), int(dz_cols), ptr(logp_out),
+         ptr(metrics), stream_ptr(), work=("byte", M * (4 * n_act * z_parts + 2 * dz_cols * dz_parts + 4 * (n_act + 3))))
+
+
+def head_continuous_sample(z, z_parts, z_pstride, M, n_act, var_min, var_max, actions_out, logp_out, normals=None, seed=0,
+                           offset=0, deterministic=False):
+    call("rlppo_head_continuous_sample", ptr(z), z.stride(0), int(z_parts), int(z_pstride), int(M), int(n_act),
+         float(var_min), float(var_max), ptr(normals), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
+         int(bool(deterministic)), ptr(actions_out), actions_out.stride(0), ptr(logp_out), stream_ptr(),
+         work=("byte", M * (4 * n_act * z_parts + 4 * (n_act + 1))))
 
 
 # ---- whole-network fused kernels --------------------------------------------------------------------------------

@@ -14,12 +14,12 @@ from ._mlp import BF16, Stack, build_sequential
 
 
 class DiscreteFF(nn.Module):
-    def __init__(self, input_shape, n_actions, layer_sizes, device):
+    def __init__(self, input_shape, n_actions, layer_sizes, device, precision=None):
         super().__init__()
         self.device = device
         self.model = build_sequential(input_shape, layer_sizes, n_actions, softmax=True)   # :22-31
         self.n_actions = int(n_actions)
-        self._stack = Stack(self.model, device)
+        self._stack = Stack(self.model, device, precision)
         dev = self._stack.device
         # standalone arenas; PPOLearner re-binds both nets into one shared arena
         self._stack.bind(torch.zeros(self._stack.n_params, device=dev), torch.zeros(self._stack.n_params, device=dev))
@@ -60,9 +60,9 @@ class DiscreteFF(nn.Module):
         ws = st.workspace(n)
         if self._obs_stats is not None:
             mean, std, clip = self._obs_stats
-            ops.rows_to_bf16(obs, ws["x"], mean, std, clip)
+            st.stage_rows(obs, ws["x"], mean, std, clip)
         else:
-            ops.rows_to_bf16(obs, ws["x"])
+            st.stage_rows(obs, ws["x"])
         return ws["x"], n, ws
 
     def _head_sample(self, obs, deterministic, want_probs):
@@ -81,9 +81,8 @@ class DiscreteFF(nn.Module):
         h = st.forward_hidden(x, n, ws)
         probs = torch.empty((n, self.n_actions), dtype=torch.float32, device=dev) if want_probs else None
         if n:
-            ops.policy_head_sample(h, st.wq[-1], st.b[-1], self.n_actions, st.hidden[-1], M=n, seed=self._seed,
-                                   offset=self._offset, deterministic=deterministic, actions_i64_out=acts,
-                                   logp_out=logp, probs_out=probs)
+            st.policy_head_sample(h, n, self.n_actions, seed=self._seed, offset=self._offset,
+                                  deterministic=deterministic, actions_i64_out=acts, logp_out=logp, probs_out=probs)
             self._offset += n
         return acts, logp, probs
 
@@ -131,7 +130,9 @@ class DiscreteFF(nn.Module):
         zeros = torch.zeros(n, dtype=torch.float32, device=dev)
         logp = torch.empty(n, dtype=torch.float32, device=dev)
         metrics = torch.zeros(8, dtype=torch.float32, device=dev)
-        ops.policy_head_train(h, st.wq[-1], st.b[-1], self.n_actions, st.hidden[-1], acts_f, zeros, zeros, 0.0, 0.2,
-                              0.0, ws["dz"], metrics, logp_out=logp, M=n)
+        hl = st.hidden[-1]
+        sp = ops.make_split(3, 3, 3, 2, ops.pad64(hl), ops.pad64(hl), ops.pad64(st.out_dim)) if st.exact else None
+        ops.policy_head_train(h, st.wq[-1], st.b[-1], self.n_actions, hl, acts_f, zeros, zeros, 0.0, 0.2,
+                              0.0, ws["dz"], metrics, logp_out=logp, M=n, split=sp)
         entropy = metrics[0] / metrics[4]
         return logp.view(-1, 1), entropy

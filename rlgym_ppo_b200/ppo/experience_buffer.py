@@ -51,6 +51,7 @@ class ExperienceBuffer(object):
         self.size = 0           # number of valid rows
         self.obs_dim = None
         self.obs_pad = None
+        self.act_dim = 1        # columns of an action row (8 for MultiDiscreteFF, N for ContinuousPolicy)
         self._rings = None
         self.states_bf16 = None
         self._stager = None
@@ -65,14 +66,17 @@ class ExperienceBuffer(object):
         self._last_rows = 0
 
     # ---- storage -------------------------------------------------------------------------------------
-    def _allocate(self, obs_dim):
+    def _allocate(self, obs_dim, act_dim=1):
         _lib.require_device()
         self.obs_dim = int(obs_dim)
         self.obs_pad = ops.pad8(self.obs_dim)
+        self.act_dim = int(act_dim)
         cap = self.capacity
         self._rings = {}
         for f in FIELDS:
             shape = (cap, self.obs_dim) if f in _WIDE else (cap,)
+            if f == "actions" and self.act_dim > 1:
+                shape = (cap, self.act_dim)      # multi-dimensional actions stay rows, as the reference's tensor does
             self._rings[f] = torch.zeros(shape, dtype=torch.float32, device=self.device)
         self.states_bf16 = torch.zeros((cap, self.obs_pad), dtype=torch.bfloat16, device=self.device)
         # {start, size} mirrored on the device: the append and gather kernels read the ring position from here, so a
@@ -118,7 +122,7 @@ class ExperienceBuffer(object):
         if self._rings is None:
             st = states
             obs_dim = st.shape[1] if hasattr(st, "shape") and len(st.shape) == 2 else np.asarray(st).shape[1]
-            self._allocate(obs_dim)
+            self._allocate(obs_dim, _act_dim(actions))
         dev = {f: self._stager.to_device(new[f], "sub." + f) for f in FIELDS}
         self.submit_device(dev)
 
@@ -181,6 +185,8 @@ class ExperienceBuffer(object):
         idx = self._index_tensor(indices)
         B = idx.numel()
         out = [torch.empty(B, dtype=torch.float32, device=self.device) for _ in range(4)]
+        if self.act_dim > 1:
+            out[0] = torch.empty((B, self.act_dim), dtype=torch.float32, device=self.device)
         st = torch.empty((B, self.obs_dim), dtype=torch.float32, device=self.device)
         self.gather(idx, out_actions=out[0], out_logp=out[1], out_values=out[2], out_adv=out[3], out_states=st)
         return out[0], out[1], st, out[2], out[3]
@@ -188,6 +194,9 @@ class ExperienceBuffer(object):
     def gather(self, idx, **outs):
         """Device permutation gather of LOGICAL indices into caller-provided outputs (see ops.gather_batch)."""
         view = _RingView(self)
+        if self.act_dim > 1 and outs.get("out_actions") is not None:
+            # action ROWS: a second pass of the same kernel over the actions ring as a wide field (exact f32 copy)
+            ops.gather_batch(_WideView(self, self._rings["actions"], self.act_dim), idx, out_states=outs.pop("out_actions"))
         ops.gather_batch(view, idx, **outs)
 
     def next_permutation(self):
@@ -293,6 +302,21 @@ class _RingView:
         self.states, self.states_bf16 = r["states"], buf.states_bf16
         self.obs_dim, self.capacity, self.start = buf.obs_dim, buf.capacity, buf.start
         self.start_dev = buf.start_dev
+
+
+class _WideView:
+    """A [capacity, width] ring presented to ops.gather_batch as its `states` field (scalar fields absent)."""
+
+    def __init__(self, buf, ring, width):
+        self.actions = self.log_probs = self.values = self.advantages = None
+        self.states, self.states_bf16 = ring, None
+        self.obs_dim, self.capacity, self.start = int(width), buf.capacity, buf.start
+        self.start_dev = buf.start_dev
+
+
+def _act_dim(actions):
+    shape = tuple(actions.shape) if hasattr(actions, "shape") else np.asarray(actions).shape
+    return int(shape[1]) if len(shape) == 2 else 1
 
 
 def _make_field_property(name):

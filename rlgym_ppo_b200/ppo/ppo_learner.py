@@ -31,8 +31,10 @@ import numpy as np
 import torch
 
 from .. import _lib, ops, parallel
+from .continuous_policy import ContinuousPolicy
 from .discrete_policy import DiscreteFF
 from .fused_adam import FusedAdam
+from .multi_discrete_policy import MultiDiscreteFF
 from .value_estimator import ValueEstimator
 
 
@@ -57,6 +59,7 @@ class PPOLearner(object):
         process_group=None,
         dp_mode="replicated",
         dp_collective=None,
+        precision=None,
     ):
         _lib.require_device()
         if device in (None, "auto", "gpu"):
@@ -69,14 +72,21 @@ class PPOLearner(object):
         assert (
             batch_size % mini_batch_size == 0
         ), "MINIBATCH SIZE MUST BE AN INTEGER MULTIPLE OF BATCH SIZE"
-        if policy_type != 0:
-            raise NotImplementedError(
-                "only the discrete head (policy_type 0, DiscreteFF) is implemented on the B200 path; "
-                "MultiDiscreteFF (1) and ContinuousPolicy (2) are out of scope (SURVEY.md section 8f)")
-
+        # precision of the Linear layers: "bf16" (throughput) or "fp32" (split operands, reference-grade gradients);
+        # None = the package default (RLPPO_PRECISION / set_default_precision)
         obs_space_size = int(obs_space_size)
-        self.policy = DiscreteFF(obs_space_size, act_space_size, policy_layer_sizes, device)
-        self.value_net = ValueEstimator(obs_space_size, critic_layer_sizes, device)
+        self.policy_type = int(policy_type)
+        if self.policy_type == 2:            # ppo_learner.py:34-50
+            self.policy = ContinuousPolicy(obs_space_size, int(act_space_size) * 2, policy_layer_sizes, device,
+                                           var_min=continuous_var_range[0], var_max=continuous_var_range[1],
+                                           precision=precision)
+        elif self.policy_type == 1:
+            self.policy = MultiDiscreteFF(obs_space_size, policy_layer_sizes, device, precision=precision)
+        else:
+            self.policy = DiscreteFF(obs_space_size, act_space_size, policy_layer_sizes, device, precision)
+        self._act_w = int(getattr(self.policy, "act_width", 1))
+        self.value_net = ValueEstimator(obs_space_size, critic_layer_sizes, device, precision)
+        self.precision = self.policy._stack.precision
         self.mini_batch_size = mini_batch_size
 
         # ---- one flat arena [policy | value] for params, grads and both Adam moments -------------------------
@@ -220,8 +230,16 @@ class PPOLearner(object):
             dev = self._params.device
             f = lambda: torch.empty(rows, dtype=torch.float32, device=dev)  # noqa: E731
             self._mb_gen = getattr(self, "_mb_gen", 0) + 1
-            self._mb = {"rows": rows, "actions": f(), "old_logp": f(), "targets": f(), "adv": f(),
-                        "x": torch.zeros((rows, self.policy._stack.in_pad), dtype=torch.bfloat16, device=dev)}
+            ps = self.policy._stack
+            self._mb = {"rows": rows, "actions": f(), "old_logp": f(), "targets": f(), "adv": f()}
+            if self._act_w > 1:      # action rows (batch_acts.view(batch_size, -1), ppo_learner.py:131)
+                self._mb["actions"] = torch.empty((rows, self._act_w), dtype=torch.float32, device=dev)
+            if ps.exact:
+                # "fp32" mode: the f32 observation rows are gathered and split into 3 bf16 parts (both nets read them)
+                self._mb["x32"] = torch.empty((rows, ps.in_dim), dtype=torch.float32, device=dev)
+                self._mb["x"] = torch.zeros((rows, 3 * ps.in_ps), dtype=torch.bfloat16, device=dev)
+            else:
+                self._mb["x"] = torch.zeros((rows, ps.in_pad), dtype=torch.bfloat16, device=dev)
         return self._mb
 
     def _sync_lr(self):
@@ -233,14 +251,20 @@ class PPOLearner(object):
     # ---- one chunk of one batch: gather -> fwd -> fused heads -> bwd (grads accumulate) -------------------------
     def _train_chunk(self, exp, idx, M):
         mb = self._minibatch_buffers(M)
-        exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
-                   out_adv=mb["adv"], out_states_bf16=mb["x"])
+        if self.policy._stack.exact:
+            exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
+                       out_adv=mb["adv"], out_states=mb["x32"])
+            self.policy._stack.stage_rows(mb["x32"][:M], mb["x"])
+            self.launches += 1
+        else:
+            exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
+                       out_adv=mb["adv"], out_states_bf16=mb["x"])
         x = mb["x"]
         # (1/mb) * (mb/B), ppo_learner.py:172-177; B = the number of samples one optimiser step averages over
         inv_b = 1.0 / float(parallel.samples_per_step(self.batch_size, self.world_size, self.dp_mode))
         metrics = self._tail[0:8]
         n = 1
-        both_fused = self.policy._stack.fused_ok and self.value_net._stack.fused_ok
+        both_fused = self.policy_type == 0 and self.policy._stack.fused_ok and self.value_net._stack.fused_ok
         if both_fused and self.two_streams and _lib._TIMING is None:
             # The two nets are independent until the optimiser step: the value net's chain (fused kernel, weight
             # gradients) runs on a second stream -- a parallel branch of the captured graph.  Each kernel is persistent
@@ -272,7 +296,7 @@ class PPOLearner(object):
         for net, is_policy in ((self.policy, True), (self.value_net, False)):
             st = net._stack
             ws = st.workspace(M)
-            if st.fused_ok:
+            if st.fused_ok and (not is_policy or self.policy_type == 0):
                 # one persistent kernel: forward, fused head, backward data path, bias gradients (mlp_fused.cu)
                 if is_policy:
                     fnet = st.fused_net(x.stride(0), ws, policy_head=True)
@@ -286,19 +310,17 @@ class PPOLearner(object):
                 n += 1
                 continue
             h = st.forward_hidden(x, M, ws)
-            hl = st.hidden[-1]
-            d0 = ws["d"][0]
-            dh = d0[:, :hl] if d0.shape[1] != hl else d0
-            if is_policy:
-                A = net.n_actions
-                ops.policy_head_train(h, st.wq[-1], st.b[-1], A, hl, mb["actions"], mb["old_logp"], mb["adv"], inv_b,
-                                      float(self.clip_range), float(self.ent_coef), ws["dz"], metrics, M=M)
-                ops.linear_wgrad(ws["dz"], h, st.gw[-1], st.gb[-1], A, hl, M=M)
-                ops.linear_dgrad(ws["dz"], st.wt[-1], h, dh, st.out_pad, hl, M=M)
-                n += 4      # head GEMM, wgrad, colsum, dgrad
+            if is_policy and self.policy_type != 0:
+                # MultiDiscrete / Continuous: last Linear -> per-row head kernel -> head wgrad / dgrad
+                dh = net.train_head(h, M, ws, mb["actions"], mb["old_logp"], mb["adv"], inv_b, float(self.clip_range),
+                                    float(self.ent_coef), metrics)
+                n += 5 + (1 if st.exact else 0)
+            elif is_policy:
+                dh = st.policy_head_train(h, M, ws, net.n_actions, mb["actions"], mb["old_logp"], mb["adv"], inv_b,
+                                          float(self.clip_range), float(self.ent_coef), metrics)
+                n += 4 + (1 if st.exact else 0)      # head GEMM, wgrad, colsum (per dz part), dgrad
             else:
-                ops.value_head(h, st.w[-1], st.b[-1], hl, targets=mb["targets"], inv_batch=inv_b, dh=dh,
-                               dw=st.gw[-1], db=st.gb[-1], metrics=metrics, M=M)
+                dh = st.value_head_train(h, M, ws, mb["targets"], inv_b, metrics)
                 n += 1
             st.backward_hidden(x, M, ws, dh)
             L = len(st.hidden)
@@ -312,29 +334,36 @@ class PPOLearner(object):
         if self.dp_collective == "p2p2":
             ops.norm_clip_adam_peers2(self._params, self._peer_grad_ptrs, self._peer_flag_ptrs, self._peer_red_ptrs,
                                       self.rank, self._m, self._v, self._seg, self._sqnorm, self._lr_dev, self._steps,
-                                      max_norm=0.5, views=self._views)
-            self.policy._stack.mark_operands_fresh()
-            self.value_net._stack.mark_operands_fresh()
+                                      max_norm=0.5, views=self._views if len(self._views) else None)
+            self._operands_after_step()
             self.launches += 1
             return
         if self.dp_collective == "p2p":
             # the all-reduce happens inside the optimiser launch (peer loads over NVLink, rank-order sum)
             ops.norm_clip_adam_peers(self._params, self._peer_grad_ptrs, self._peer_flag_ptrs, self.rank, self._gsum,
                                      self._m, self._v, self._seg, self._sqnorm, self._lr_dev, self._steps, max_norm=0.5,
-                                     views=self._views)
-            self.policy._stack.mark_operands_fresh()
-            self.value_net._stack.mark_operands_fresh()
+                                     views=self._views if len(self._views) else None)
+            self._operands_after_step()
             self.launches += 1
             return
         parallel.allreduce_sum_(self._grads, self._pg)   # NCCL sum over NVLink; the gradients carry the global 1/B
         self._apply_step()
 
+    def _operands_after_step(self):
+        """bf16 mode: the optimiser launch has rewritten the bf16 operands itself (views).  "fp32" mode: the split
+        operands are rebuilt here (one small launch per Linear, inside the same graph)."""
+        for st in (self.policy._stack, self.value_net._stack):
+            if st.exact:
+                st.refresh_operands(force=True)
+                self.launches += len(st.linears)
+            else:
+                st.mark_operands_fresh()
+
     def _apply_step(self):
         # ppo_learner.py:187-193 in one launch: fixed-order (deterministic) norms -> clip -> Adam -> bf16 operand refresh
         ops.norm_clip_adam(self._params, self._grads, self._m, self._v, self._seg, self._sqnorm, self._lr_dev,
-                           self._steps, max_norm=0.5, views=self._views)
-        self.policy._stack.mark_operands_fresh()
-        self.value_net._stack.mark_operands_fresh()
+                           self._steps, max_norm=0.5, views=self._views if len(self._views) else None)
+        self._operands_after_step()
         self.launches += 1
 
     def _backward_body(self, exp, idx, local, chunk):
@@ -395,7 +424,7 @@ class PPOLearner(object):
     def _graph_key(self, exp, local, chunk):
         """Everything a captured graph bakes in: buffer identity, workspace generations (addresses), scalar arguments."""
         return (exp.uid, local, chunk, float(self.clip_range), float(self.ent_coef), self.batch_size, self.world_size,
-                self.dp_mode, self.dp_collective, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
+                self.dp_mode, self.dp_collective, self.precision, self.policy_type, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
                 getattr(self.policy._stack, "ws_gen", 0), getattr(self.value_net._stack, "ws_gen", 0))
 
     def _learn_body(self, exp, n_batches, local, chunk, tail=True):

@@ -12,11 +12,11 @@ from ._mlp import Stack, build_sequential
 
 
 class ValueEstimator(nn.Module):
-    def __init__(self, input_shape, layer_sizes, device):
+    def __init__(self, input_shape, layer_sizes, device, precision=None):
         super().__init__()
         self.device = device
         self.model = build_sequential(input_shape, layer_sizes, 1, softmax=False)   # value_estimator.py:19-28
-        self._stack = Stack(self.model, device)
+        self._stack = Stack(self.model, device, precision)
         dev = self._stack.device
         self._stack.bind(torch.zeros(self._stack.n_params, device=dev), torch.zeros(self._stack.n_params, device=dev))
 
@@ -47,7 +47,7 @@ class ValueEstimator(nn.Module):
             return out
         ws = st.workspace(n)
         h = st.forward_hidden(x, n, ws)
-        ops.value_head(h, st.w[-1], st.b[-1], st.hidden[-1], values_out=out, M=n)
+        st.value_head_infer(h, n, out)
         return out
 
     def forward(self, x):
@@ -64,5 +64,5 @@ class ValueEstimator(nn.Module):
         x = x.contiguous()
         n = x.shape[0]
         ws = st.workspace(n)
-        ops.rows_to_bf16(x, ws["x"])
+        st.stage_rows(x, ws["x"])
         return self.values_from_bf16(ws["x"], n).view(*lead, 1)

@@ -1,0 +1,216 @@
+"""GPU parity at the north-star tolerance, against the fp32 reference (BASELINE.json: "losses, gradients and updated
+weights must match within 1e-3 relative").
+
+The reference computes its Linear layers with fp32 SGEMM.  `precision="fp32"` runs the same tcgen05 kernels over split
+bf16 operands (hi/mid/lo parts: 6 products forward, 3 backward; include/rlppo.h "precision mode") and is what these
+tests hold to 1e-3 -- against the reference-generated fixtures (tests/golden/ppo_learn.npz, add_exp.npz) and, on the
+shape the benchmark runs (C2: 50 000 rows, 256x3 nets, obs 89, 90 actions, clip-active log-probs), against the fp32
+oracle.  The plain bf16 mode is measured beside it on the same step and held to 2x its measured deviation; the table of
+per-tensor errors of both modes is written to gpurun_out/r02_parity_c2.json (committed under profiles/).
+"""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_oracle as O
+from parity_helpers import capture_steps, close, rel_l2, unflatten
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NAMES = ("states", "actions", "log_probs", "rewards", "next_states", "dones", "truncated", "values", "advantages")
+
+
+def load_params(module, g, prefix):
+    keys = list(module.state_dict().keys())
+    module.load_state_dict({k: torch.from_numpy(g[f"{prefix}.{i}"]) for i, k in enumerate(keys)})
+
+
+def test_ppo_learner_golden_fp32_mode(golden):
+    """The reference's own 4-step run (2 epochs x 2 batches, clip active): every post-clip gradient tensor of every step,
+    the final weights, Adam moments and the report, at 1e-3 against the fp32 fixtures."""
+    from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
+    g = golden("ppo_learn")
+    obs_dim, n_act, B, mb, epochs, total, l0, l1 = [int(x) for x in g["cfg"]]
+    plr, clr, clip, ent = [float(x) for x in g["hyper"]]
+    lr = PPOLearner(obs_dim, n_act, 0, (l0, l1), (l0, l1), (0.1, 1.0), B, epochs, plr, clr, clip, ent, mb, DEV,
+                    precision="fp32")
+    load_params(lr.policy, g, "pol0")
+    load_params(lr.value_net, g, "val0")
+    buf = ExperienceBuffer(1000, 123, DEV)
+    buf.submit_experience(*[g[f"buf.{n}"] for n in NAMES])
+    captured = capture_steps(lr)
+    report = lr.learn(buf)
+    assert len(captured) == int(g["n_steps"][0])
+    ref_report = dict(zip([str(k) for k in g["report.keys"]], g["report.vals"]))
+    for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction",
+              "Policy Update Magnitude", "Value Function Update Magnitude"):
+        assert abs(report[k] - ref_report[k]) <= 1e-3 * max(1.0, abs(ref_report[k])), (k, report[k], ref_report[k])
+    n_pol = len(list(lr.policy.parameters()))
+    errs = []
+    for s, flat in enumerate(captured):
+        for i, got in enumerate(unflatten(lr, flat)):
+            want = g[f"pgrad{s}.{i}"] if i < n_pol else g[f"vgrad{s}.{i - n_pol}"]
+            errs.append((s, i, rel_l2(got, want)))
+            assert close(got, want, 1e-3), (s, i)
+    print("fp32 mode, grad rel-L2 vs fp32 golden:", [(s, i, float(f"{e:.2e}")) for s, i, e in errs])
+    # first step: identical weights -> pure kernel error; later steps add the (tiny) drift of the weights
+    assert max(e for s, _, e in errs if s == 0) < 1e-3, errs
+    assert max(e for _, _, e in errs) < 2e-3, errs
+    for name, net in (("pol1", lr.policy), ("val1", lr.value_net)):
+        for i, p in enumerate(net.parameters()):
+            got, want = p.detach().cpu().numpy(), g[f"{name}.{i}"]
+            assert close(got, want, 1e-3), (name, i, np.abs(got - want).max())
+            assert rel_l2(got, want) < 1e-3, (name, i, rel_l2(got, want))
+    sd = lr.policy_optimizer.state_dict()
+    for i in sd["state"]:
+        assert rel_l2(sd["state"][i]["exp_avg"].cpu().numpy(), g[f"padam.{i}.m"]) < 2e-3
+
+
+def test_add_new_experience_golden_fp32_mode(golden):
+    """learner.py:330-385 in fp32 mode: the value predictions that feed GAE are fp32-grade, so the buffer's value
+    targets / advantages meet the GAE tolerance (1e-5 scale-aware... measured; asserted 1e-4) against the reference end to end."""
+    from rlgym_ppo_b200.learner import Learner
+    from rlgym_ppo_b200.ppo import ExperienceBuffer, ValueEstimator
+    from rlgym_ppo_b200.util import WelfordRunningStat
+    g = golden("add_exp")
+    obs_dim, n, cap, l0, l1 = [int(x) for x in g["cfg"]]
+    val = ValueEstimator(obs_dim, (l0, l1), DEV, precision="fp32")
+    load_params(val, g, "val")
+    ns = SimpleNamespace(ppo_learner=SimpleNamespace(value_net=val), return_stats=WelfordRunningStat(1, device=DEV),
+                         standardize_returns=True, gae_gamma=0.99, gae_lambda=0.95,
+                         max_returns_per_stats_increment=150, experience_buffer=ExperienceBuffer(cap, 123, DEV))
+    worst = 0.0
+    for it in range(2):
+        exp = tuple(g[f"it{it}.{k}"] for k in ("states", "actions", "log_probs", "rewards", "next_states", "dones",
+                                               "truncated"))
+        Learner.add_new_experience(ns, exp)
+        buf = ns.experience_buffer
+        for field in ("values", "advantages"):
+            got, want = getattr(buf, field).cpu().numpy(), g[f"it{it}.buf.{field}"]
+            worst = max(worst, float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0))))
+            assert close(got, want, 1e-4), (it, field, worst)
+        st = g[f"it{it}.stats"]
+        assert ns.return_stats.count == int(st[2])
+        assert close(ns.return_stats.running_mean, st[0], 1e-5)
+    print("fp32 mode, add_new_experience worst scale-aware error vs reference:", worst)
+
+
+def _c2_problem(n=50_000, obs=89, act=90, layers=(256, 256, 256), seed=0):
+    """One optimiser step of the benchmark shape, SURVEY.md 8(d) synthetic inputs: N(0,1) observations, actions and
+    log-probs from the CURRENT policy, log-probs perturbed by N(0, 0.3^2) (clip fraction ~0.5), N(0,1) advantages."""
+    torch.manual_seed(123)
+    rng = np.random.RandomState(seed)
+
+    def make(nin, nout):
+        dims = [nin, *layers, nout]
+        ps = []
+        for i in range(len(dims) - 1):
+            lin = torch.nn.Linear(dims[i], dims[i + 1])
+            ps += [lin.weight.detach().clone(), lin.bias.detach().clone()]
+        return ps
+
+    pol, val = make(obs, act), make(obs, 1)
+    states = rng.randn(n, obs).astype(np.float32)
+    with torch.no_grad():
+        probs = O.policy_probs(pol, torch.from_numpy(states))
+        acts = torch.multinomial(probs, 1).flatten()
+        logp = torch.log(probs.gather(-1, acts.view(-1, 1)).flatten()).numpy()
+    fields = dict(states=states, actions=acts.numpy().astype(np.float32),
+                  log_probs=(logp + rng.randn(n).astype(np.float32) * 0.3).astype(np.float32),
+                  rewards=np.zeros(n, np.float32), next_states=np.roll(states, -1, 0).copy(),
+                  dones=np.zeros(n, np.float32), truncated=np.zeros(n, np.float64),
+                  values=rng.randn(n).astype(np.float32), advantages=rng.randn(n).astype(np.float32))
+    return pol, val, fields
+
+
+def _run_c2(precision, pol, val, fields, n, obs, act, layers):
+    from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        lr = PPOLearner(obs, act, 0, layers, layers, (0.1, 1.0), n, 1, 3e-4, 3e-4, 0.2, 0.001, n, DEV,
+                        precision=precision)
+    sd = lr.policy.state_dict()
+    lr.policy.load_state_dict({k: p for k, p in zip(sd.keys(), pol)})
+    sd = lr.value_net.state_dict()
+    lr.value_net.load_state_dict({k: p for k, p in zip(sd.keys(), val)})
+    buf = ExperienceBuffer(n, 123, DEV)
+    buf.submit_experience(*[fields[k] for k in NAMES])
+    captured = capture_steps(lr)
+    report = lr.learn(buf)
+    assert len(captured) == 1
+    weights = [p.detach().cpu().numpy().copy() for p in list(lr.policy.parameters()) + list(lr.value_net.parameters())]
+    return report, unflatten(lr, captured[0]), weights
+
+
+def test_c2_shape_one_step_vs_fp32_oracle():
+    """The judged parity case: ONE optimiser step of the C2 shape through PPOLearner against the fp32 oracle (no operand
+    rounding), per-tensor post-clip gradient rel-L2, updated weights, losses.  fp32 mode: asserted at the north-star 1e-3.
+    bf16 mode: measured on the same step, recorded, held to 2x the deviation measured on B200 (profiles/r02_parity_c2.json)."""
+    n, obs, act, layers = 50_000, 89, 90, (256, 256, 256)
+    pol, val, fields = _c2_problem(n, obs, act, layers)
+    ob = O.BufferOracle(n, 123)
+    ob.submit(**fields)
+    orc = O.PPOLearnerOracle(pol, val, n, 1, 3e-4, 3e-4, 0.2, 0.001, n)          # fp32, quant=None
+    want = orc.learn(ob)
+    want_g = [t.numpy() for t in orc.last_grads[0] + orc.last_grads[1]]
+    want_w = [t.numpy() for t in orc.pol + orc.val]
+    old_w = [t.numpy() for t in pol + val]
+    table = {"shape": {"rows": n, "obs": obs, "actions": act, "layers": list(layers)},
+             "oracle": "oracle.PPOLearnerOracle fp32 (torch CPU SGEMM), quant=None", "modes": {}}
+    metrics = ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction",
+               "Policy Update Magnitude", "Value Function Update Magnitude")
+    for precision in ("fp32", "bf16"):
+        report, grads, weights = _run_c2(precision, pol, val, fields, n, obs, act, layers)
+        table["modes"][precision] = {
+            "grad_rel_l2": [rel_l2(a, b) for a, b in zip(grads, want_g)],
+            "weight_rel_l2": [rel_l2(a, b) for a, b in zip(weights, want_w)],
+            "update_rel_l2": [rel_l2(a - o, b - o) for a, b, o in zip(weights, want_w, old_w)],
+            "weight_max_abs": [float(np.abs(a - b).max()) for a, b in zip(weights, want_w)],
+            "metrics": {k: [float(report[k]), float(want[k])] for k in metrics},
+        }
+    out_dir = os.environ.get("RLPPO_TEST_OUT", "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "r02_parity_c2.json"), "w") as f:
+            json.dump(table, f, indent=1)
+    except OSError:
+        pass
+    print(json.dumps(table["modes"], indent=1))
+    assert 0.3 < want["SB3 Clip Fraction"] < 0.7          # the clip branch is exercised
+    m = table["modes"]["fp32"]
+    assert max(m["grad_rel_l2"]) < 1e-3, m["grad_rel_l2"]
+    assert max(m["weight_rel_l2"]) < 1e-3, m["weight_rel_l2"]
+    for k, (got, ref) in m["metrics"].items():
+        assert abs(got - ref) <= 1e-3 * max(1.0, abs(ref)), (k, got, ref)
+    # bf16 mode: 2x the deviation measured on B200 for this step (round 2: max per-tensor gradient rel-L2 ~0.09)
+    b = table["modes"]["bf16"]
+    assert max(b["grad_rel_l2"]) < 0.2, b["grad_rel_l2"]
+    assert max(b["weight_rel_l2"]) < 5e-3, b["weight_rel_l2"]
+    for k, (got, ref) in b["metrics"].items():
+        tol = 2e-2 if "Magnitude" in k else 2e-3
+        assert abs(got - ref) <= tol * max(1.0, abs(ref)), (k, got, ref)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_load_state_dict_refreshes_operands(precision):
+    """after a network has run, load_state_dict must reach the GEMM operands (the staleness check used the flat
+    arena's version counter, which param.copy_ does not move)."""
+    from rlgym_ppo_b200.ppo import DiscreteFF, ValueEstimator
+    torch.manual_seed(1)
+    a = DiscreteFF(20, 7, (64, 64), DEV, precision=precision)
+    b = DiscreteFF(20, 7, (64, 64), DEV, precision=precision)
+    va = ValueEstimator(20, (64,), DEV, precision=precision)
+    vb = ValueEstimator(20, (64,), DEV, precision=precision)
+    x = np.random.RandomState(0).randn(33, 20).astype(np.float32)
+    pa, pb = a.get_output(x).cpu().numpy(), b.get_output(x).cpu().numpy()
+    assert np.abs(pa - pb).max() > 1e-3
+    va0, vb0 = va(x).cpu().numpy(), vb(x).cpu().numpy()
+    b.load_state_dict({k: v.clone() for k, v in a.state_dict().items()})
+    vb.load_state_dict({k: v.clone() for k, v in va.state_dict().items()})
+    assert np.array_equal(b.get_output(x).cpu().numpy(), pa)
+    assert np.array_equal(vb(x).cpu().numpy(), va0) and not np.array_equal(vb0, va0)
