@@ -2,36 +2,49 @@
 """bench.py -- learner-side PPO throughput (GAE + normalisation + full update) of rlgym_ppo_b200 on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
+                    [--precision bf16|fp32] [--device cpu|cuda] [--no-cpu] [--no-sub]
 
 One "step" = one learner iteration at steady state on synthetic rollouts of the example shape:
-Learner.add_new_experience on N_new fresh timesteps (value inference on N_new+1 states, GAE + reward
-normalisation, Welford update, ring append) followed by PPOLearner.learn on the full buffer
-(ppo_epochs x floor(buffer/B) optimiser steps: permutation gather, fwd/bwd, clip, Adam).
+Learner.add_new_experience on N_new fresh timesteps (value inference on N_new+1 states, GAE + reward normalisation,
+Welford update, ring append) followed by PPOLearner.learn on the full buffer (ppo_epochs x floor(buffer/B) optimiser
+steps: permutation gather, fwd/bwd, clip, Adam).
 
-  value   device-timed (CUDA events per step, L2 flushed between steps), rollout arrays already resident in HBM
-  e2e     the same iteration through the public API with HOST (pinned) rollout arrays: H2D of the 7 arrays and the
-          D2H read of the report scalars inside the timed region (wall clock, synchronised both sides)
-  roofline    per-kernel CUDA-event timing of one more step (rlgym_ppo_b200._lib.timing_begin), dominant kernel
-  cpu_baseline  the CPU oracle (oracle/ref_oracle.py: the reference's algorithm restated, fp32 torch-CPU + the
-          reference's Python GAE loop) on this box's host cores, bounded sample (rank 0, N=1 only)
+  value     device-timed (CUDA events per step, L2 flushed between steps), rollout arrays already resident in HBM
+  e2e       the same iteration through the public API with HOST (pinned) rollout arrays: H2D of the 7 arrays and the D2H
+            read of the report scalars inside the timed region.  THIS is SURVEY.md 8(d)'s t_device ("from rollout arrays
+            resident in pinned host memory to weights updated + report scalars on host") and the headline against the
+            reference arm; `value` and the roofline explain it.
+  roofline  per-kernel CUDA-event timing of one more (eager) step; work per launch = SURVEY.md 8(d)'s ALGORITHMIC figures
+            (un-padded flops for the MLP kernels -> tensor roof; 28 B/step GAE, 744 B/sample gather, 28 B/param optimiser,
+            1480 B/step append -> HBM roof), traffic = DRAM bytes per launch from the committed ncu --set full capture.
+  sub       the other BASELINE.json configs, each with its own roofline: precision_fp32 (the same C2 step in the mode that
+            meets the 1e-3 parity bar), c3 (large nets), c4 (4096-slot batched inference + 1M-step GAE), c5 (GAE sweep);
+            at N > 1 also `strong` (dp_mode="replicated": fixed global batch, the reference's minibatch slices).
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, pip-installed by build()) on this box's host cores, bounded
+            sample (rank 0, N=1 only).
 
-`--impl reference` times that CPU path alone with all host threads and prints the same JSON line.
-Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank contributes N_new timesteps and takes 1/R of
-every batch; the global batch, rollout and buffer grow with R (config.global_*).
+`--impl reference` times that reference alone (all host threads; `--device cuda`: PyTorch eager on the B200, the same-box
+GPU comparator of BASELINE.md section 3) on this arm's config and prints the same JSON line.
+Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank contributes N_new timesteps and takes 1/R of every
+batch; the global batch, rollout and buffer grow with R (config.global_*); the reference arm runs that global config.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
+from types import SimpleNamespace
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+from tools.benchlib import (ClockSampler, host_threads, import_reference, load_peaks, run_reference,  # noqa: E402
+                            synth_rollout)
 
 WORKLOADS = {
     # BASELINE.json configs[1]: example.py shape on 1xB200
@@ -45,212 +58,408 @@ WORKLOADS = {
 }
 FLOP_PER_SAMPLE_UPDATE = {"c2": 1894912.0, "c3": 90097664.0}     # SURVEY.md 8(d), fwd+bwd both nets, un-padded
 FLOP_PER_STATE_VALUE = {"c2": 308224.0, "c3": 15046656.0}
+FLOP_PER_OBS_POLICY = {"c2": 353792.0, "c3": 15228928.0}
+
+# ---- which roof bounds a C-ABI entry point, and its algorithmic bytes where ops.py counts real ones ----
+TENSOR_BOUND = ("rlppo_policy_train_fused", "rlppo_value_train_fused", "rlppo_policy_infer_fused",
+                "rlppo_value_infer_fused", "rlppo_wgrad_multi", "rlppo_linear_fwd", "rlppo_linear_dgrad",
+                "rlppo_linear_dgrad_db", "rlppo_linear_wgrad", "rlppo_policy_head_train", "rlppo_policy_head_sample",
+                "rlppo_linear_fwd_split", "rlppo_linear_dgrad_split", "rlppo_linear_wgrad_split",
+                "rlppo_policy_head_train_split", "rlppo_policy_head_sample_split")
+# C-ABI entry point -> kernel name in the ncu reports (profiles/ncu_traffic.json is keyed by kernel name)
+KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_train_fused": "fused_mlp_kernel<1, 1>",
+             "rlppo_value_train_fused": "fused_mlp_kernel<0, 1>", "rlppo_value_infer_fused": "fused_mlp_kernel<0, 0>",
+             "rlppo_policy_infer_fused": "fused_mlp_kernel<1, 0>",
+             "rlppo_gather_batch": "gather_kernel", "rlppo_gae_f32": "gae_scan3_kernel<1, 1>",
+             "rlppo_linear_wgrad": "wgrad_kernel<256>", "rlppo_linear_fwd": "rowgemm_kernel<256, 0>",
+             "rlppo_linear_dgrad": "rowgemm_kernel<256, 1>", "rlppo_linear_dgrad_db": "rowgemm_kernel<256, 1>",
+             "rlppo_linear_wgrad_split": "wgrad_kernel<256>", "rlppo_linear_fwd_split": "rowgemm_kernel<256, 0>",
+             "rlppo_linear_dgrad_split": "rowgemm_kernel<256, 1>",
+             "rlppo_norm_clip_adam": "norm_clip_adam_kernel", "rlppo_ring_append_fields_dev": "ring_append_fields_kernel",
+             "rlppo_welford_update": "welford_kernel<1>", "rlppo_rows_to_bf16": "rows_to_bf16_kernel<0>"}
+# ties in time are broken in this order, so the reported kernel does not flip between runs
+DOMINANT_ORDER = ("rlppo_policy_train_fused", "rlppo_linear_fwd_split", "rlppo_linear_fwd", "rlppo_wgrad_multi",
+                  "rlppo_value_train_fused")
 
 
-def synth_rollout(rng, n, obs_dim):
-    """the flat layout collect_timesteps produces (batched_agent_manager.py:159-168)."""
-    states = rng.randn(n, obs_dim).astype(np.float32)
-    next_states = np.roll(states, -1, axis=0).copy()
-    rewards = (rng.randn(n) * 0.1).astype(np.float32)
-    dones = (rng.rand(n) < 1 / 300).astype(np.float32)
-    truncated = ((rng.rand(n) < 1 / 1500) * (1 - dones)).astype(np.float64)
-    truncated[-1] = 1.0 - dones[-1]
-    return states, rewards, next_states, dones, truncated
+def algorithmic(name, v, ctx):
+    """(bound, work per ALL launches of this entry point in one step) from SURVEY.md 8(d).  ctx: rows per optimiser
+    step, new timesteps, parameter count."""
+    if name in TENSOR_BOUND:
+        return "tensor", v["flop"]                       # ops.py counts 2*M*N*K with the true (un-padded) extents
+    b = v["byte"]
+    if name == "rlppo_gather_batch":
+        b = 744.0 * ctx["rows_per_update"] * v["calls"]  # 372 B/sample read + 372 B written (materialised)
+    elif name in ("rlppo_norm_clip_adam", "rlppo_norm_clip_adam_peers", "rlppo_norm_clip_adam_peers2"):
+        b = 28.0 * ctx["n_params"] * v["calls"]          # p, g, m, v read; p, m, v written
+    elif name == "rlppo_ring_append_fields_dev":
+        b = 1480.0 * ctx["n_new"] * v["calls"]
+    elif name == "rlppo_welford_update":
+        b = 4.0 * 150 * v["calls"]
+    return "hbm", b
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
-
-    def run(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-        except Exception:
-            pass
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        self.join(timeout=2)
-        sm, mx, reasons = [], 0.0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except (ValueError, IndexError):
-                continue
-        # "under load" = the upper half of the samples (the sampler also sees the idle gaps between steps)
-        sm.sort()
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
-
-
-# ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm on the host cores (oracle = checker; here it is what is being timed)
-# ------------------------------------------------------------------------------------------------------------------
-def run_cpu_oracle(wl, steps, warmup, seed=0):
-    import torch
-    from oracle import ref_oracle as O
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its ranks: undo that here)
+def roofline_table(per, peaks, ctx, workload):
+    """Per entry point: share of the step, achieved algorithmic rate, roof, fraction, DRAM traffic per launch."""
     try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, RuntimeError):
-        pass
-    torch.manual_seed(123)
-    import torch.nn as nn
-
-    def mk(out):
-        dims = [wl["obs"], *wl["layers"], out]
-        ps = []
-        for i in range(len(dims) - 1):
-            l = nn.Linear(dims[i], dims[i + 1])
-            ps += [l.weight.detach().clone(), l.bias.detach().clone()]
-        return ps
-
-    pol, val = mk(wl["act"]), mk(1)
-    orc = O.PPOLearnerOracle(pol, val, wl["batch"], wl["epochs"], 3e-4, 3e-4, 0.2, wl["ent"], wl["batch"])
-    buf = O.BufferOracle(wl["buffer"], 123)
-    stats = O.WelfordOracle(1)
-    rng = np.random.RandomState(seed)
-    n = wl["n_new"]
-
-    def rollout():
-        states, rewards, next_states, dones, truncated = synth_rollout(rng, n, wl["obs"])
-        with torch.no_grad():
-            p = torch.clamp(O.policy_probs(orc.pol, torch.from_numpy(states)), 1e-11, 1.0)
-            a = torch.multinomial(p, 1, True)
-            lp = torch.log(p).gather(-1, a).flatten().numpy()
-        return states, a.flatten().numpy().astype(np.float32), lp, rewards, next_states, dones, truncated
-
-    while buf.f["rewards"].shape[0] + n < wl["buffer"]:        # reach steady state without timing
-        O.add_new_experience(orc.val, buf, stats, rollout(), 0.99, 0.95)
-    times = []
-    for it in range(warmup + steps):
-        exp = rollout()
-        t0 = time.perf_counter()
-        O.add_new_experience(orc.val, buf, stats, exp, 0.99, 0.95)
-        orc.learn(buf)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    return n / float(np.mean(times)), float(np.mean(times)), torch.get_num_threads()
+        tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        tbl = {}
+    total = sum(v["ms"] for v in per.values()) or 1.0
+    rows = {}
+    for name, v in per.items():
+        bound, work = algorithmic(name, v, ctx)
+        if bound == "tensor":
+            ach, peak, unit = work / v["ms"] / 1e9, peaks["tc"], "TFLOP/s"
+        else:
+            ach, peak, unit = work / v["ms"] / 1e6, peaks["hbm"], "GB/s"
+        traffic = tbl.get(workload, {}).get(KERNEL_OF.get(name, name))
+        row = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+               "traffic": traffic, "launches": v["calls"], "avg_launch_ms": v["ms"] / v["calls"], "ms": v["ms"],
+               "share": v["ms"] / total,
+               "algorithmic_per_launch": work / v["calls"], "algorithmic_unit": "flop" if bound == "tensor" else "byte"}
+        if bound == "tensor":
+            row["frac_of_burst_peak"] = ach / peaks["tc_burst"]
+            if v.get("mma_flop"):
+                row["issued_mma_tflops"] = v["mma_flop"] / v["ms"] / 1e9      # split operands: 3-6 MMAs per algorithmic one
+        if traffic and bound == "hbm":
+            row["traffic_over_algorithmic"] = traffic / (work / v["calls"])
+        elif traffic and v["byte"]:
+            row["dram_bytes_per_launch_vs_min_io"] = traffic / (v["byte"] / v["calls"])
+        rows[name] = row
+    return rows
 
 
+def dominant(rows):
+    top = max(r["ms"] for r in rows.values())
+    for name in DOMINANT_ORDER:
+        if name in rows and rows[name]["ms"] >= 0.9 * top:
+            return name
+    return max(rows, key=lambda k: rows[k]["ms"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------------------------
 def reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-    # bounded: the whole run must end within minutes (one c2 iteration is ~2 s on 8 cores, c3 far more)
+    R = max(1, args.gpus)
+    # the config of OUR arm at this N (weak scaling: global rollout / batch / buffer grow with N)
+    glob = dict(wl, n_new=wl["n_new"] * R, batch=wl["batch"] * R, buffer=wl["buffer"] * R)
+    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
     if args.workload == "c3":
-        steps, warmup = 1, 0
-    else:
-        steps = min(steps, 5)
-    tput, sec, threads = run_cpu_oracle(wl, steps, warmup)
-    sample = f"{steps} steady-state iteration(s) of the full workload after {warmup} warm-up, oracle port of the reference"
+        steps, warmup = 1, 0          # one c3 iteration is minutes of CPU work
+    if R >= 4:
+        steps = min(steps, 2)
+    device = "cuda:0" if args.device == "cuda" else "cpu"
+    tput, sec, threads, kind = run_reference(glob, steps, warmup, device=device)
+    sample = (f"{steps} steady-state iteration(s) of the full workload after {warmup} warm-up: the unmodified reference's "
+              f"Learner.add_new_experience + PPOLearner.learn on {device}" if kind == "reference" else
+              f"{steps} iteration(s), oracle port of the reference (baseline/_ref missing)")
     line = {"impl": "reference", "metric": "learner_timesteps_per_sec", "value": tput, "unit": "timesteps/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"]},
-            "cpu_baseline": {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": wl["name"], "global_new_timesteps": glob["n_new"], "global_batch": glob["batch"],
+                       "global_buffer": glob["buffer"], "device": device},
+            "cpu_baseline": {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": tput, "unit": "timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-
-# C-ABI entry point -> kernel name in the ncu reports (profiles/ncu_traffic.json is keyed by kernel name)
-KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_train_fused": "fused_mlp_kernel<1, 1>",
-             "rlppo_value_train_fused": "fused_mlp_kernel<0, 1>", "rlppo_value_infer_fused": "fused_mlp_kernel<0, 0>",
-             "rlppo_gather_batch": "gather_kernel", "rlppo_gae_f32": "gae_scan3_kernel<1, 1>",
-             "rlppo_linear_wgrad": "wgrad_kernel<256>", "rlppo_linear_fwd": "rowgemm_kernel<256, 0>",
-             "rlppo_linear_dgrad": "rowgemm_kernel<256, 1>", "rlppo_linear_dgrad_db": "rowgemm_kernel<256, 1>",
-             "rlppo_clip_adam": "clip_adam_kernel", "rlppo_norm_clip_adam": "norm_clip_adam_kernel"}
-
-
-def bound_of(v, hbm_peak, tc_peak):
-    """Which roof bounds a call: the larger of flop / tensor peak and algorithmic bytes / HBM peak."""
-    t_tc = v["flop"] / (tc_peak * 1e12) if v["flop"] else 0.0
-    t_hbm = v["byte"] / (hbm_peak * 1e9) if v["byte"] else 0.0
-    return "tensor" if t_tc > t_hbm else "hbm"
-
-
-def roofline_of(name, v, hbm_peak, tc_peak, peak_src, workload):
-    """roofline object for one C-ABI entry point: achieved = algorithmic work per launch / average CUDA-event time of
-    a launch, against the roof that bounds it; traffic = dram bytes per launch from the committed ncu --set full
-    capture (profiles/ncu_traffic.json), or null."""
-    traffic = None
-    try:
-        tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = tbl.get(workload, {}).get(KERNEL_OF.get(name, name))
-    except Exception:
-        pass
-    bound = bound_of(v, hbm_peak, tc_peak)
-    if bound == "tensor":
-        ach, peak, unit, src = v["flop"] / v["ms"] / 1e9, tc_peak, "TFLOP/s", peak_src + " (sustained bf16)"
-    else:
-        ach, peak, unit, src = v["byte"] / v["ms"] / 1e6, hbm_peak, "GB/s", peak_src + " (copy bandwidth)"
-    out = {"kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-           "traffic": traffic, "peak_source": src, "launches": v["calls"], "avg_launch_ms": v["ms"] / v["calls"],
-           "algorithmic_bytes_per_launch": v["byte"] / v["calls"], "algorithmic_flop_per_launch": v["flop"] / v["calls"]}
-    if v["flop"] and v["byte"]:
-        out["other_roof"] = ({"bound": "hbm", "achieved": v["byte"] / v["ms"] / 1e6, "unit": "GB/s",
-                              "frac": v["byte"] / v["ms"] / 1e6 / hbm_peak} if bound == "tensor" else
-                             {"bound": "tensor", "achieved": v["flop"] / v["ms"] / 1e9, "unit": "TFLOP/s",
-                              "frac": v["flop"] / v["ms"] / 1e9 / tc_peak})
-    return out
-
-
-def gae_bandwidth(dev, hbm_peak, peak_src, log2n=26, reps=5):
-    """The metric's second half ("GAE GB/s"): one flat 2^26-step rollout with random done masks (inputs 2 GB > L2),
-    28 algorithmic bytes per step, CUDA events around the C-ABI call, median of `reps`."""
-    import torch
-    from rlgym_ppo_b200 import ops
-    n = 1 << log2n
-    g = torch.Generator(device=dev)
-    g.manual_seed(5)
-    rew = torch.randn(n, device=dev, generator=g) * 0.1
-    done = (torch.rand(n, device=dev, generator=g) < 1 / 300).float()
-    tr = ((torch.rand(n, device=dev, generator=g) < 1 / 1500).float() * (1 - done))
-    tr[-1] = 1 - done[-1]
-    tr = tr.double()
-    val = torch.randn(n + 1, device=dev, generator=g)
-    std = torch.tensor([0.7], device=dev)
-    out = tuple(torch.empty(n, device=dev) for _ in range(3))
-    for _ in range(3):
-        ops.gae(rew, done, tr, val, 0.99, 0.95, std, out=out)
-    ts = []
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.gae(rew, done, tr, val, 0.99, 0.95, std, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = float(np.median(ts))
-    return {"timesteps": n, "truncated_dtype": "f64", "ms": ms, "algorithmic_GBps": 28 * n / ms / 1e6,
-            "frac_of_hbm_peak": 28 * n / ms / 1e6 / hbm_peak, "actual_bytes_per_step": 32, "peak_source": peak_src,
-            "timesteps_per_sec": n / ms * 1e3}
-
 # ------------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
+class Rig:
+    """A learner (PPOLearner + the namespace Learner.add_new_experience runs on) with a pool of synthetic rollouts,
+    pinned on the host and resident on the device."""
+
+    def __init__(self, wl, dev, rank, world, precision, dp_mode="sharded", n_pool=3, quiet=True):
+        import torch
+        from rlgym_ppo_b200.learner import Learner
+        from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
+        from rlgym_ppo_b200.util import WelfordRunningStat
+        self.torch, self.Learner, self.wl, self.dev, self.world, self.rank = torch, Learner, wl, dev, world, rank
+        torch.manual_seed(123)        # identical initial weights on every rank
+        replicated = dp_mode == "replicated"
+        # sharded (weak scaling): every rank owns its rollout / buffer / shuffle, per-rank batch = the workload's batch.
+        # replicated (strong scaling): the SAME rollout, buffer and permutation on every rank, the workload's batch is global.
+        with contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext():
+            self.ppo = PPOLearner(wl["obs"], wl["act"], 0, wl["layers"], wl["layers"], (0.1, 1.0), wl["batch"],
+                                  wl["epochs"], 3e-4, 3e-4, 0.2, wl["ent"], wl["batch"], dev, dp_mode=dp_mode,
+                                  precision=precision)
+        self.ns = SimpleNamespace(ppo_learner=self.ppo, return_stats=WelfordRunningStat(1, device=dev),
+                                  standardize_returns=True, gae_gamma=0.99, gae_lambda=0.95,
+                                  max_returns_per_stats_increment=150,
+                                  experience_buffer=ExperienceBuffer(wl["buffer"], 123 + (0 if replicated else rank), dev))
+        rng = np.random.RandomState(0 if replicated else rank)
+        self.pool_host, self.pool_dev = [], []
+        for _ in range(n_pool):
+            states, rewards, next_states, dones, truncated = synth_rollout(rng, wl["n_new"], wl["obs"])
+            acts, logp = self.ppo.policy.get_action_device(torch.from_numpy(states).to(dev))
+            host = [torch.from_numpy(a).pin_memory() for a in
+                    (states, acts.float().cpu().numpy(), logp.cpu().numpy(), rewards, next_states, dones, truncated)]
+            self.pool_host.append((tuple(t.numpy() for t in host), host))   # numpy views of pinned memory (+ keep-alive)
+            self.pool_dev.append(tuple(t.to(dev) for t in host))
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pool_host[0][1])
+        self.d2h_bytes = self.ppo._tail_host.numel() * 4
+        self.it = 0
+        self.n_pool = n_pool
+
+    def step(self, exp):
+        self.Learner.add_new_experience(self.ns, exp)
+        return self.ppo.learn(self.ns.experience_buffer)
+
+    def next_dev(self):
+        e = self.pool_dev[self.it % self.n_pool]
+        self.it += 1
+        return e
+
+    def next_host(self):
+        e = self.pool_host[self.it % self.n_pool][0]
+        self.it += 1
+        return e
+
+    def barrier(self):
+        if self.world > 1:
+            self.torch.distributed.barrier()
+        self.torch.cuda.synchronize()
+
+    def fill_and_warm(self, n_warm):
+        wl = self.wl
+        while len(self.ns.experience_buffer) + wl["n_new"] < wl["buffer"]:
+            self.Learner.add_new_experience(self.ns, self.next_dev())
+        self.barrier()                                # ranks reach their first data-parallel step together
+        for _ in range(max(n_warm, 2 * self.n_pool)):  # every pooled rollout at least twice: its CUDA graph exists
+            self.step(self.next_dev())
+
+    def timed_device(self, K, flush_buf):
+        torch = self.torch
+        self.barrier()
+        evs = []
+        for _ in range(K):
+            flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            report = self.step(self.next_dev())
+            e1.record()
+            evs.append((e0, e1))
+        self.barrier()
+        return sum(a.elapsed_time(b) for a, b in evs), report
+
+    def timed_e2e(self, K, n_warm):
+        for _ in range(n_warm):                       # the host-input path has its own staging slots and graph
+            self.step(self.next_host())
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            report = self.step(self.next_host())
+            _ = report["Policy Entropy"]
+        self.barrier()
+        return (time.perf_counter() - t0) * 1e3
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return vals
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        self.torch.distributed.all_reduce(t, op=self.torch.distributed.ReduceOp.MAX)
+        return tuple(float(x) for x in t)
+
+    def kernel_pass(self, flush_buf):
+        """One eager step with CUDA events around every C-ABI call (rlgym_ppo_b200._lib.timing_begin)."""
+        from rlgym_ppo_b200 import _lib
+        flush_buf.zero_()
+        self.torch.cuda.synchronize()
+        _lib.timing_begin()
+        self.step(self.next_dev())
+        return _lib.timing_end()
+
+    def ctx(self):
+        wl = self.wl
+        n_params = int(self.ppo._params.numel())
+        return {"rows_per_update": wl["batch"], "n_new": wl["n_new"], "n_params": n_params}
+
+
+def gae_sweep(dev, peaks, log2s=(20, 22, 24, 26, 28), reps=5):
+    """BASELINE configs[4] (C5): flat rollouts with random done masks, 28 algorithmic bytes per step, CUDA events around
+    the C-ABI call, median of `reps`; inputs of 2^24 steps and more exceed the 126 MB L2."""
+    import torch
+    from rlgym_ppo_b200 import ops
+    out = []
+    for log2n in log2s:
+        n = 1 << log2n
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        rew = torch.randn(n, device=dev, generator=g) * 0.1
+        done = (torch.rand(n, device=dev, generator=g) < 1 / 300).float()
+        tr32 = ((torch.rand(n, device=dev, generator=g) < 1 / 1500).float() * (1 - done))
+        tr32[-1] = 1 - done[-1]
+        val = torch.randn(n + 1, device=dev, generator=g)
+        std = torch.tensor([0.7], device=dev)
+        bufs = tuple(torch.empty(n, device=dev) for _ in range(3))
+        row = {"timesteps": n}
+        for label, tr, real in (("f64_truncated", tr32.double(), 32), ("f32_truncated", tr32, 28)):
+            for _ in range(2):
+                ops.gae(rew, done, tr, val, 0.99, 0.95, std, out=bufs)
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ops.gae(rew, done, tr, val, 0.99, 0.95, std, out=bufs)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = float(np.median(ts))
+            row[label] = {"ms": ms, "algorithmic_GBps": 28 * n / ms / 1e6, "frac": 28 * n / ms / 1e6 / peaks["hbm"],
+                          "real_bytes_per_step": real, "timesteps_per_sec": n / ms * 1e3}
+        del rew, done, tr32, val, bufs
+        out.append(row)
+    return out
+
+
+def sub_fp32(args, dev, rank, world, flush_buf, peaks):
+    """The same C2 step with precision="fp32" (split operands): the mode the 1e-3 parity tests run."""
+    wl = WORKLOADS["c2"]
+    rig = Rig(wl, dev, rank, world, "fp32")
+    rig.fill_and_warm(3)
+    K = min(args.steps, 10)
+    dev_ms, _ = rig.timed_device(K, flush_buf)
+    e2e_ms = rig.timed_e2e(K, 3)
+    dev_ms, e2e_ms = rig.max_over_ranks(dev_ms, e2e_ms)
+    out = {"precision": "fp32 (hi/mid/lo bf16 split: 6 products forward, 3 backward)",
+           "value": wl["n_new"] * world * K / (dev_ms / 1e3), "ms_per_step": dev_ms / K,
+           "e2e": {"value": wl["n_new"] * world * K / (e2e_ms / 1e3), "ms_per_step": e2e_ms / K}, "unit": "timesteps/s"}
+    if rank == 0:
+        rows = roofline_table(rig.kernel_pass(flush_buf), peaks, rig.ctx(), "c2_fp32")
+        top = dominant(rows)
+        out["roofline"] = rows[top]
+        out["kernels"] = {k.replace("rlppo_", ""): {"ms": round(r["ms"], 4), "share": round(r["share"], 3),
+                                                    "frac": round(r["frac"], 3), "bound": r["bound"]}
+                          for k, r in sorted(rows.items(), key=lambda kv: -kv[1]["ms"])}
+    elif world > 1:
+        flush_buf.zero_()
+        rig.step(rig.next_dev())
+    return out
+
+
+def sub_c3(args, dev, rank, world, flush_buf, peaks):
+    """BASELINE configs[2]: 2048-2048-1024-1024 nets, 3 epochs x 3 batches per iteration (per-GPU share; weak scaling)."""
+    wl = WORKLOADS["c3"]
+    rig = Rig(wl, dev, rank, world, "bf16", n_pool=2)
+    rig.fill_and_warm(2)
+    K = 2
+    dev_ms, _ = rig.timed_device(K, flush_buf)
+    (dev_ms,) = rig.max_over_ranks(dev_ms)
+    n_updates = wl["epochs"] * (wl["buffer"] // wl["batch"])
+    flop = wl["n_new"] * FLOP_PER_STATE_VALUE["c3"] + n_updates * wl["batch"] * FLOP_PER_SAMPLE_UPDATE["c3"]
+    out = {"workload": wl["name"], "value": wl["n_new"] * world * K / (dev_ms / 1e3), "unit": "timesteps/s",
+           "ms_per_step": dev_ms / K, "steps": K, "algorithmic_tflop_per_step_per_gpu": flop / 1e12,
+           "achieved_tflops_per_gpu": flop / (dev_ms / K / 1e3) / 1e12,
+           "frac_of_sustained_bf16_peak": flop / (dev_ms / K / 1e3) / 1e12 / peaks["tc"],
+           "gradient_exchange": rig.ppo.dp_collective}
+    if rank == 0:
+        rows = roofline_table(rig.kernel_pass(flush_buf), peaks, rig.ctx(), "c3")
+        top = dominant(rows)
+        out["roofline"] = rows[top]
+        out["kernels"] = {k.replace("rlppo_", ""): {"ms": round(r["ms"], 3), "share": round(r["share"], 3),
+                                                    "frac": round(r["frac"], 3), "bound": r["bound"]}
+                          for k, r in sorted(rows.items(), key=lambda kv: -kv[1]["ms"])}
+    elif world > 1:
+        flush_buf.zero_()
+        rig.step(rig.next_dev())
+    return out
+
+
+def sub_c4(args, dev, rank, world, peaks):
+    """BASELINE configs[3]: batched policy inference over 4096 env slots (sharded across ranks) for 245 ticks -- the
+    observations of every tick go pinned host -> HBM, the sampled actions come back to the host -- then value inference and
+    GAE over the 1 003 520-step iteration (this rank's slots), through the collection classes' own tick path."""
+    import torch
+    from rlgym_ppo_b200 import ops
+    from rlgym_ppo_b200.batched_agents.tick import TickInference
+    from rlgym_ppo_b200.ppo import DiscreteFF, ValueEstimator
+    wl = WORKLOADS["c2"]
+    slots, ticks = 4096 // world, 245
+    torch.manual_seed(123)
+    pol = DiscreteFF(wl["obs"], wl["act"], wl["layers"], dev)
+    val = ValueEstimator(wl["obs"], wl["layers"], dev)
+    tick = TickInference(pol, slots, wl["obs"])
+    rng = np.random.RandomState(rank)
+    tick.obs_host.copy_(torch.from_numpy(rng.randn(slots, wl["obs"]).astype(np.float32)))
+    for _ in range(5):
+        tick.run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        tick.run()                       # returns after the actions of this tick are in pinned host memory
+    infer_s = time.perf_counter() - t0
+    n = slots * ticks
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    states = torch.randn(n + 1, wl["obs"], device=dev, generator=g)
+    rew = torch.randn(n, device=dev, generator=g) * 0.1
+    done = (torch.rand(n, device=dev, generator=g) < 1 / 300).float()
+    tr = ((torch.rand(n, device=dev, generator=g) < 1 / 1500).float() * (1 - done)).double()
+    std = torch.tensor([0.7], device=dev)
+    ws = val._stack.workspace(n + 1)
+    out3 = tuple(torch.empty(n, device=dev) for _ in range(3))
+    values = torch.empty(n + 1, device=dev)
+
+    def learner_half():
+        val._stack.stage_rows(states, ws["x"])
+        val.values_from_bf16(ws["x"], n + 1, out=values)
+        ops.gae(rew, done, tr, values, 0.99, 0.95, std, out=out3)
+    for _ in range(2):
+        learner_half()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    e0.record()
+    val._stack.stage_rows(states, ws["x"])
+    val.values_from_bf16(ws["x"], n + 1, out=values)
+    e1.record()
+    ops.gae(rew, done, tr, values, 0.99, 0.95, std, out=out3)
+    e2.record()
+    torch.cuda.synchronize()
+    v_ms, g_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    t = torch.tensor([infer_s, v_ms, g_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    infer_s, v_ms, g_ms = (float(x) for x in t)
+    total_steps = slots * world * ticks
+    flop_tick = slots * FLOP_PER_OBS_POLICY["c2"]
+    return {"workload": "configs[3]: 4096 env slots x 245 ticks = 1 003 520 steps per iteration",
+            "slots_per_gpu": slots, "ticks": ticks,
+            "inference_tick_us": infer_s / ticks * 1e6,
+            "inference_rows_per_sec": slots * world * ticks / infer_s,
+            "inference_tflops_per_gpu": flop_tick * ticks / infer_s / 1e12,
+            "tick_path": "pinned obs -> H2D -> rows_to_bf16 -> fused policy kernel (MLP + sample) -> actions D2H, one CUDA "
+                         "graph per tick, host waits on one event",
+            "value_inference_ms": v_ms, "gae_ms": g_ms,
+            "gae_algorithmic_GBps": 28 * n / g_ms / 1e6, "gae_frac_of_hbm": 28 * n / g_ms / 1e6 / peaks["hbm"],
+            "iteration_timesteps_per_sec_no_env": total_steps / (infer_s + (v_ms + g_ms) / 1e3),
+            "note": "environment stepping excluded (host processes; not part of the learner-side path)"}
+
+
+def sub_strong(args, dev, rank, world, flush_buf):
+    """Strong scaling: the reference's semantics -- ONE 50k rollout, global batch 50k split into `world` minibatch slices
+    (ppo_learner.py:134-193), replicated buffers, identical optimiser step on every rank."""
+    wl = WORKLOADS["c2"]
+    rig = Rig(wl, dev, rank, world, args.precision, dp_mode="replicated")
+    rig.fill_and_warm(3)
+    K = min(args.steps, 10)
+    dev_ms, _ = rig.timed_device(K, flush_buf)
+    e2e_ms = rig.timed_e2e(K, 3)
+    dev_ms, e2e_ms = rig.max_over_ranks(dev_ms, e2e_ms)
+    return {"scaling": "strong", "dp_mode": "replicated", "global_new_timesteps": wl["n_new"], "global_batch": wl["batch"],
+            "value": wl["n_new"] * K / (dev_ms / 1e3), "ms_per_step": dev_ms / K, "unit": "timesteps/s",
+            "e2e": {"value": wl["n_new"] * K / (e2e_ms / 1e3), "ms_per_step": e2e_ms / K},
+            "gae": "sharded across ranks by contiguous chunks" if getattr(rig.ppo, "gae_sharded", False) else "replicated",
+            "gradient_exchange": rig.ppo.dp_collective}
+
+
 def b200_arm(args, wl):
     import torch
-    from types import SimpleNamespace
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -262,61 +471,16 @@ def b200_arm(args, wl):
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     from rlgym_ppo_b200 import _lib
-    from rlgym_ppo_b200.learner import Learner
-    from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
-    from rlgym_ppo_b200.util import WelfordRunningStat
     _lib.require_device()
+    peaks = load_peaks()
 
     R = world
-    n_local = wl["n_new"]
-    # Weak scaling, "sharded" data parallelism: every rank owns its rollout (as if fed by its own env workers), its
-    # experience buffer and its shuffle; per-rank batch = the workload's batch, one optimiser step averages over R of them.
-    n_glob, batch, cap = n_local * R, wl["batch"] * R, wl["buffer"] * R
-    torch.manual_seed(123)        # identical initial weights on every rank
-    import contextlib
-    import io
-    with contextlib.redirect_stdout(io.StringIO()):
-        ppo = PPOLearner(wl["obs"], wl["act"], 0, wl["layers"], wl["layers"], (0.1, 1.0), wl["batch"], wl["epochs"], 3e-4,
-                         3e-4, 0.2, wl["ent"], wl["batch"], dev, dp_mode="sharded")
-    ns = SimpleNamespace(ppo_learner=ppo, return_stats=WelfordRunningStat(1, device=dev), standardize_returns=True,
-                         gae_gamma=0.99, gae_lambda=0.95, max_returns_per_stats_increment=150,
-                         experience_buffer=ExperienceBuffer(wl["buffer"], 123 + rank, dev))
-
-    # ---- synthetic rollouts: a pool of distinct ones per rank, pinned on the host and resident on the device -------------
-    rng = np.random.RandomState(rank)
-    pool_host, pool_dev = [], []
-    n_pool = 3
-    for _ in range(n_pool):
-        states, rewards, next_states, dones, truncated = synth_rollout(rng, n_local, wl["obs"])
-        acts, logp = ppo.policy.get_action_device(torch.from_numpy(states).to(dev))
-        host = [torch.from_numpy(a).pin_memory() for a in
-                (states, acts.float().cpu().numpy(), logp.cpu().numpy(), rewards, next_states, dones, truncated)]
-        pool_host.append((tuple(t.numpy() for t in host), host))   # numpy views of pinned memory (+ keep-alive)
-        pool_dev.append(tuple(t.to(dev) for t in host))
-    h2d_bytes = world * sum(t.numel() * t.element_size() for t in pool_host[0][1])     # all ranks
-    d2h_bytes = world * ppo._tail_host.numel() * 4
-
+    n_glob, batch, cap = wl["n_new"] * R, wl["batch"] * R, wl["buffer"] * R
+    rig = Rig(wl, dev, rank, world, args.precision)
+    ppo = rig.ppo
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    def step(exp):
-        Learner.add_new_experience(ns, exp)
-        return ppo.learn(ns.experience_buffer)
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    # fill to steady state, then warm up
-    it = 0
-    while len(ns.experience_buffer) + n_local < wl["buffer"]:
-        Learner.add_new_experience(ns, pool_dev[it % n_pool])
-        it += 1
     n_warm = max(args.warmup, 3)
-    barrier()                                     # ranks reach their first data-parallel step together
-    for _ in range(max(n_warm, 2 * n_pool)):      # every pooled rollout at least twice: its CUDA graph exists before timing
-        step(pool_dev[it % n_pool])
-        it += 1
+    rig.fill_and_warm(n_warm)
 
     # ---- (1) device-resident timing: K steps, one event pair per step, L2 flushed between steps --------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -324,83 +488,82 @@ def b200_arm(args, wl):
         sampler.start()
         time.sleep(0.3)
     calls0 = _lib.CALLS
-    barrier()
-    evs = []
-    for _ in range(args.steps):
-        flush_buf.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        report = step(pool_dev[it % n_pool])
-        e1.record()
-        evs.append((e0, e1))
-        it += 1
-    barrier()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    dev_ms, report = rig.timed_device(args.steps, flush_buf)
     calls = _lib.CALLS - calls0
-
     # ---- (2) end to end through the public API with host buffers ---------------------------------------------------
-    for _ in range(n_warm):                       # the host-input path has its own staging slots and graph
-        step(pool_host[it % n_pool][0])
-        it += 1
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        report = step(pool_host[it % n_pool][0])
-        _ = report["Policy Entropy"]
-        it += 1
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = rig.timed_e2e(args.steps, n_warm)
     clocks = sampler.stop() if sampler else None
-
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms = rig.max_over_ranks(dev_ms, e2e_ms)
 
     # ---- (3) per-kernel pass for the roofline object (rank 0; not part of the timed numbers) --------------------------
-    roofline, kernels, gae_line = None, None, None
+    roofline, kernels = None, None
     if rank != 0 and world > 1:
         flush_buf.zero_()
-        step(pool_dev[it % n_pool])      # the collectives of rank 0's instrumented step need their peers
-        it += 1
+        rig.step(rig.next_dev())      # the collectives of rank 0's instrumented step need their peers
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        peak_src = "measured" if peaks else "fallback"
-        flush_buf.zero_()
-        torch.cuda.synchronize()
-        _lib.timing_begin()
-        step(pool_dev[it % n_pool])
-        per = _lib.timing_end()
-        it += 1
-        total = sum(v["ms"] for v in per.values())
-        kernels = {k.replace("rlppo_", ""): {"calls": v["calls"], "ms": round(v["ms"], 4),
-                                             "share": round(v["ms"] / total, 4),
-                                             **({"TFLOP/s": round(v["flop"] / v["ms"] / 1e9, 2)} if v["flop"] else {}),
-                                             **({"GB/s": round(v["byte"] / v["ms"] / 1e6, 1)} if v["byte"] else {}),
-                                             "bound": bound_of(v, hbm_peak, tc_peak)}
-                   for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])}
-        top_name, top = max(per.items(), key=lambda kv: kv[1]["ms"])
-        roofline = roofline_of(top_name, top, hbm_peak, tc_peak, peak_src, args.workload)
-        gae_line = gae_bandwidth(dev, hbm_peak, peak_src) if world == 1 else None
+        rows = roofline_table(rig.kernel_pass(flush_buf), peaks, rig.ctx(), args.workload)
+        top = dominant(rows)
+        roofline = dict(rows[top], peak_source=peaks["src"],
+                        why_this_kernel="largest share of the step among the kernels (ties within 10 % resolved in a "
+                                        "fixed order so the name is stable across runs)")
+        kernels = {k.replace("rlppo_", ""): {"calls": r["launches"], "ms": round(r["ms"], 4), "share": round(r["share"], 4),
+                                             "bound": r["bound"], r["unit"]: round(r["achieved"], 2),
+                                             "frac": round(r["frac"], 4),
+                                             **({"traffic_over_algorithmic": round(r["traffic_over_algorithmic"], 2)}
+                                                if "traffic_over_algorithmic" in r else {})}
+                   for k, r in sorted(rows.items(), key=lambda kv: -kv[1]["ms"])}
 
-    # ---- (4) CPU baseline (rank 0, single-GPU run only) ------------------------------------------------------------
+    # ---- (4) the other configs (every rank takes part; rank 0 reports) --------------------------------------------
+    sub = {}
+    rig_bytes[0], rig_bytes[1] = rig.h2d_bytes, rig.d2h_bytes
+    if not args.no_sub and args.workload == "c2":
+        del rig
+        torch.cuda.empty_cache()
+        for name, fn in (("precision_fp32", lambda: sub_fp32(args, dev, rank, world, flush_buf, peaks)),
+                         ("c3", lambda: sub_c3(args, dev, rank, world, flush_buf, peaks)),
+                         ("c4", lambda: sub_c4(args, dev, rank, world, peaks)),
+                         ("strong", (lambda: sub_strong(args, dev, rank, world, flush_buf)) if world > 1 else None)):
+            if fn is None:
+                continue
+            try:
+                sub[name] = fn()
+            except Exception as e:  # noqa: BLE001  (a failing sub-benchmark must not lose the headline line)
+                if world > 1:
+                    raise           # ranks would desynchronise: fail loudly instead
+                sub[name] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+        try:
+            sweep = gae_sweep(dev, peaks)
+            if world > 1:
+                ms = torch.tensor([r["f64_truncated"]["ms"] for r in sweep] + [r["f32_truncated"]["ms"] for r in sweep],
+                                  dtype=torch.float64, device=dev)
+                torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+                k = len(sweep)
+                for i, r in enumerate(sweep):       # every rank scans its own 2^k-step rollout: aggregate = world x
+                    for j, label in enumerate(("f64_truncated", "f32_truncated")):
+                        t = float(ms[j * k + i])
+                        r[label].update(ms=t, aggregate_GBps=28 * r["timesteps"] * world / t / 1e6,
+                                        aggregate_timesteps_per_sec=r["timesteps"] * world / t * 1e3)
+            sub["c5"] = {"workload": "configs[4]: flat GAE sweep, random done masks (p=1/300), one rollout per GPU",
+                         "peak_GBps": peaks["hbm"], "sweep": sweep}
+        except Exception as e:  # noqa: BLE001
+            if world > 1:
+                raise
+            sub["c5"] = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- (5) CPU baseline: the reference itself on this box's host cores (rank 0, single-GPU run only) -----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         if args.workload == "c2":
-            tput, sec, threads = run_cpu_oracle(wl, 3, 1)
-            cpu = {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": "port",
-                   "sample": "3 steady-state iterations of the full workload after 1 warm-up (oracle/ref_oracle.py: "
-                             "Python GAE loop + fp32 torch-CPU MLPs)", "sec_per_step": sec}
+            tput, sec, threads, kind = run_reference(wl, 3, 1)
+            cpu = {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": kind,
+                   "sample": "3 steady-state iterations of the full workload after 1 warm-up: the unmodified reference "
+                             "(baseline/_ref) Learner.add_new_experience + PPOLearner.learn, device='cpu'",
+                   "sec_per_step": sec}
         else:
             small = dict(wl, n_new=5000, batch=5000, buffer=15000)
-            tput, sec, threads = run_cpu_oracle(small, 1, 0)
-            cpu = {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": "port",
+            tput, sec, threads, kind = run_reference(small, 1, 0)
+            cpu = {"value": tput, "unit": "timesteps/s", "cores": threads, "kind": kind,
                    "sample": "1 iteration at 1/10 of the rows (5k new, batch 5k, buffer 15k), same nets and epochs",
                    "sec_per_step": sec}
 
@@ -408,13 +571,18 @@ def b200_arm(args, wl):
         K = args.steps
         n_updates = wl["epochs"] * (cap // batch)
         flop_step = n_glob * FLOP_PER_STATE_VALUE[args.workload] + n_updates * batch * FLOP_PER_SAMPLE_UPDATE[args.workload]
+        exact = args.precision == "fp32"
         line = {
             "metric": "learner_timesteps_per_sec", "value": n_glob * K / (dev_ms / 1e3), "unit": "timesteps/s",
             "n_gpus": world, "steps": K, "warmup": n_warm, "ms_per_step": dev_ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (fp32-equivalent split operands)" if exact else "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "global_new_timesteps": n_glob, "global_batch": batch,
                        "global_buffer": cap, "optimizer_steps_per_step": n_updates,
                        "consumed_samples_per_step": n_updates * batch,
+                       "precision": args.precision,
+                       "headline": "e2e (SURVEY.md 8(d) t_device: pinned host arrays in, report scalars out); `value` "
+                                   "starts with the rollout resident in HBM",
                        "parallelism": (f"dp{world} (per-rank experience shards; gradient exchange per optimiser step: "
                                        + ("summed inside the optimiser launch from the peers' arenas over NVLink)"
                                           if ppo.dp_collective == "p2p" else "NCCL allreduce of the flat gradient arena)"))
@@ -422,20 +590,24 @@ def b200_arm(args, wl):
                        "gradient_exchange": ppo.dp_collective,
                        "l2": "flushed between timed steps (256 MiB write); working set > L2",
                        "algorithmic_tflop_per_step": flop_step / 1e12,
-                       "achieved_tflops": flop_step / (dev_ms / K / 1e3) / 1e12},
+                       "achieved_tflops": flop_step / (dev_ms / K / 1e3) / 1e12,
+                       "step_frac_of_sustained_bf16_peak": flop_step / (dev_ms / K / 1e3) / 1e12 / (peaks["tc"] * world)},
             "e2e": {"value": n_glob * K / (e2e_ms / 1e3), "unit": "timesteps/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                    "h2d_bytes_per_step": rig_bytes[0] * world, "d2h_bytes_per_step": rig_bytes[1] * world},
             "gpu_launches": calls,
             "clocks": clocks,
             "roofline": roofline,
-            "gae": gae_line,
             "cpu_baseline": cpu,
             "kernels": kernels,
+            "sub": sub,
             "report": {k: (float(v) if isinstance(v, (int, float, np.floating)) else v) for k, v in report.items()},
         }
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+rig_bytes = [0, 0]
 
 
 def main():
@@ -445,7 +617,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("RLPPO_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: where the reference runs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (other configs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

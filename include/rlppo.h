@@ -328,10 +328,15 @@ typedef struct rlppo_fused_net {
 int rlppo_policy_train_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, int n_actions,
                              const float* actions, const float* old_logp, const float* adv, float inv_batch,
                              float clip, float ent_coef, float* logp_out, float* metrics, void* stream);
-/* DiscreteFF.get_action (discrete_policy.py:44-62) for all rows: same sampler contract as rlppo_policy_head_sample. */
+/* DiscreteFF.get_action (discrete_policy.py:44-62) for all rows: same sampler contract as rlppo_policy_head_sample.
+ * d_offset (optional): device counter added to `offset` -- a captured CUDA graph (one per environment tick,
+ * batched_agent_manager.py:180-221) then draws fresh numbers on every replay; advance it with rlppo_u64_add. */
 int rlppo_policy_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, int n_actions,
-                             const float* u_inject, uint64_t seed, uint64_t offset, int deterministic,
-                             float* actions_out, int64_t* actions_i64_out, float* logp_out, void* stream);
+                             const float* u_inject, uint64_t seed, uint64_t offset, const uint64_t* d_offset,
+                             int deterministic, float* actions_out, int64_t* actions_i64_out, float* logp_out,
+                             void* stream);
+/* *d_counter += inc (one thread; graph-capturable). */
+int rlppo_u64_add(uint64_t* d_counter, uint64_t inc, void* stream);
 /* ValueEstimator forward + MSE loss + backward data path (value_estimator.py:30-36, ppo_learner.py:146,176).
  * w_head f32[hidden_last] (the last Linear's weight row), gw_head f32[hidden_last] accumulated; metrics[5,6] as
  * rlppo_value_head; values_out optional f32[M]. */

@@ -306,6 +306,48 @@ def mt19937_permutation_c(key, pos, n):
 
 
 # --------------------------------------------------------------------------------------------------
+# Rollout flattening  (batched_agent_manager.py:100-172, batched_trajectory.py:20-105)
+# --------------------------------------------------------------------------------------------------
+
+
+def flatten_rollout(obs, acts, logp, rew, done, trunc, agents):
+    """What collect_timesteps returns when every process answers every pass.  Inputs are time-major:
+    obs [T+1, S, D], acts [T, S] or [T, S, A], logp / rew [T, S], done / trunc [T, P] (per ENV), agents = agents per
+    process.  A process's open trajectory takes (state, action, log_prob, reward, next_state, done, truncated) per tick
+    (:213-215, :338-341); update() closes it when done (batched_trajectory.py:36-54) and `_sync_trajectories` moves it to
+    the completed list in process order within a tick (:174-178); at the end the open ones follow by process id
+    (:126-128).  get_all() emits agent after agent, each agent's steps in time order (:70-101); the last step of every
+    such run is truncated iff not done (:145).  Returns the seven arrays (truncated as float64, like np.asarray of the
+    reference's mixed list)."""
+    T = acts.shape[0]
+    P = len(agents)
+    slot0 = np.concatenate([[0], np.cumsum(agents)])
+    open_steps = [[] for _ in range(P)]
+    completed = []
+    for t in range(T):
+        for p in range(P):
+            open_steps[p].append(t)
+            if done[t, p]:
+                completed.append((p, open_steps[p]))
+                open_steps[p] = []
+    for p in range(P):
+        completed.append((p, open_steps[p]))
+    cols = [[] for _ in range(7)]
+    for p, steps in completed:
+        if not steps:
+            continue
+        for s in range(slot0[p], slot0[p + 1]):
+            run = [[obs[t, s] for t in steps], [acts[t, s] for t in steps], [logp[t, s] for t in steps],
+                   [rew[t, s] for t in steps], [obs[t + 1, s] for t in steps], [np.float32(done[t, p]) for t in steps],
+                   [float(trunc[t, p]) for t in steps]]
+            run[6][-1] = 1.0 if run[5][-1] == 0 else 0.0
+            for c, r in zip(cols, run):
+                c.extend(r)
+    dt = (np.float32,) * 6 + (np.float64,)
+    return tuple(np.asarray(c, dtype=d) for c, d in zip(cols, dt))
+
+
+# --------------------------------------------------------------------------------------------------
 # Networks  (discrete_policy.py:22-42, value_estimator.py:19-36): params = [W0,b0,W1,b1,...], W [out,in]
 # --------------------------------------------------------------------------------------------------
 

@@ -10,6 +10,7 @@ Here every observation crosses PCIe exactly once and stays in HBM:
   * one async H2D of that row, then on the device: optional standardisation (clip((x-mean)/std, +-5)) fused with
     the bf16 conversion, the policy MLP on tcgen05, softmax/clamp/categorical sample/log-prob in the head epilogue;
   * actions come back in one small D2H; observations, actions and log-probs stay in time-major device slabs;
+  * a tick is ONE CUDA-graph launch (tick.TickInference) ending in the action D2H; the host waits on one event;
   * at the end of collect_timesteps the flat per-trajectory layout the learner expects (completed
     trajectories in completion order, then open ones by process id; each agent's steps in time order; last step of
     every run forced truncated unless done) is produced by ONE index gather on the device.
@@ -92,62 +93,45 @@ class BatchedAgentManager(object):
         return msg
 
     # ---- collection ------------------------------------------------------------------------------------------------
-    def _bf16_scratch(self, rows, width):
-        sc = getattr(self, "_bf16_sc", None)
-        if sc is None or sc.shape[0] < rows or sc.shape[1] < ops.pad8(width):
-            sc = self._bf16_sc = torch.empty((rows, ops.pad8(width)), dtype=torch.bfloat16, device=self.device)
-        return sc
-
     @torch.no_grad()
     def collect_timesteps(self, n):
         """Collect at least n timesteps.  Returns ((states, actions, log_probs, rewards, next_states, dones,
         truncated) as DEVICE tensors in the reference's flat layout, collected_metrics, n_collected, elapsed)."""
+        from .tick import TickInference
         t1 = time.perf_counter()
         S, D, dev = self.n_slots, self.obs_dim, torch.device(self.device)
         T = (int(n) + S - 1) // S
+        tick = getattr(self, "_tick", None)
+        if tick is None or tick.policy is not self.policy:
+            tick = self._tick = TickInference(self.policy, S, D, standardize=self.standardize_obs)
+            tick.obs_host = self._current_obs          # the workers' observations land in the tick's pinned row
+        act_w = tick.act_w
         obs_slab = torch.empty((T + 1, S, D), dtype=torch.float32, device=dev)     # what the policy saw (standardised)
-        act_slab = torch.empty((T, S), dtype=torch.float32, device=dev)
+        act_slab = torch.empty((T, S) if act_w == 1 else (T, S, act_w), dtype=torch.float32, device=dev)
         logp_slab = torch.empty((T, S), dtype=torch.float32, device=dev)
-        act_host = torch.empty(S, dtype=torch.float32).pin_memory()
         rew = np.zeros((T, S), np.float32)
         done = np.zeros((T, S), np.float32)
         trunc = np.zeros((T, S), np.float32)
-        raw = torch.empty((S, D), dtype=torch.float32, device=dev)
-        st = self.policy._stack
         collected_metrics = []
         cur = self._current_obs.numpy()
         env_done = np.zeros((T, self.n_procs), bool)
 
-        def stage(t):
-            """pinned row -> HBM -> (standardised) f32 slab row + bf16 GEMM operand, all on the device."""
-            ws = st.workspace(S)
+        def push_stats():
+            # the reference standardises EVERY feature with the statistics of feature 0
+            # (`self.obs_stats.mean[0]`, `.std[0]`, batched_agent_manager.py:233-235): reproduced as is
             if self.standardize_obs:
-                raw.copy_(self._current_obs, non_blocking=True)
-                # the reference standardises EVERY feature with the statistics of feature 0
-                # (`self.obs_stats.mean[0]`, `.std[0]`, batched_agent_manager.py:233-235): reproduced as is
-                mean = self.obs_stats.device_mean()[0:1].expand(D).contiguous()
-                std = self.obs_stats.device_std()[0:1].expand(D).contiguous()
-                if st.exact:
-                    # "fp32" mode: standardised f32 rows first (what the trajectory stores), then the split operand
-                    ops.rows_to_bf16(raw, self._bf16_scratch(S, D), mean, std, 5.0, dst_f32=obs_slab[t])
-                    st.stage_rows(obs_slab[t], ws["x"])
-                else:
-                    ops.rows_to_bf16(raw, ws["x"], mean, std, 5.0, dst_f32=obs_slab[t])
-            else:
-                obs_slab[t].copy_(self._current_obs, non_blocking=True)
-                st.stage_rows(obs_slab[t], ws["x"])
-            return ws
+                tick.set_obs_stats(self.obs_stats.device_mean()[0:1].expand(D), self.obs_stats.device_std()[0:1].expand(D))
 
+        push_stats()
         for t in range(T):
-            ws = stage(t)
-            st.refresh_operands()
-            h = st.forward_hidden(ws["x"], S, ws)
-            st.policy_head_sample(h, S, self.policy.n_actions, seed=self.policy._seed, offset=self.policy._offset,
-                                  actions_out=act_slab[t], logp_out=logp_slab[t])
-            self.policy._offset += S
-            act_host.copy_(act_slab[t], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            a = act_host.numpy()
+            # one CUDA-graph launch: H2D obs -> standardise/stage -> fused MLP + sample -> D2H actions; then the slab rows
+            # (device-to-device, behind the event the host waits on: they never delay the workers)
+            tick.enqueue()
+            obs_slab[t].copy_(tick.obs_seen, non_blocking=True)
+            act_slab[t].copy_(tick.act_dev, non_blocking=True)
+            logp_slab[t].copy_(tick.logp_dev, non_blocking=True)
+            tick.done_ev.synchronize()
+            a = tick.act_host.numpy()
             for p, (_, conn) in enumerate(self.processes):
                 conn.send(("act", a[self._slot0[p]:self._slot0[p + 1]].copy()))
             tick_obs = []
@@ -178,11 +162,36 @@ class BatchedAgentManager(object):
                     o = tick_obs[t % len(tick_obs)]
                     self.obs_stats.increment(o, o.shape[0])
                     self.steps_since_obs_stats_update = 0
-        stage(T)      # the observation after the last step: next_states of tick T-1
+                    push_stats()
+        # the observation after the last step (next_states of tick T-1): staged like a tick's, without inference
+        self._stage_only(tick, obs_slab[T])
+        out = self.flatten(obs_slab, act_slab, logp_slab, rew, done, trunc, env_done, self._slot0)
+        n_collected = int(out[3].shape[0])
+        self.cumulative_timesteps += n_collected
+        return out, collected_metrics, n_collected, time.perf_counter() - t1
 
-        # ---- flat per-trajectory order, as one index gather on the device -----------------------------
+    def _stage_only(self, tick, dst):
+        tick.obs_raw.copy_(tick.obs_host, non_blocking=True)
+        if self.standardize_obs:
+            ops.rows_to_bf16(tick.obs_raw, tick._scratch(), tick.mean_dev, tick.std_dev, tick.clip, dst_f32=dst)
+        else:
+            dst.copy_(tick.obs_raw, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # obs_host may be rewritten by the next collect_timesteps
+
+    @staticmethod
+    def flatten(obs_slab, act_slab, logp_slab, rew, done, trunc, env_done, slot0):
+        """Time-major device slabs -> the reference's flat rollout (batched_agent_manager.py:125-172 +
+        BatchedTrajectory.get_all, batched_trajectory.py:58-105): completed trajectories in completion
+        order (within a tick by process id), then the still-open ones by process id; inside a trajectory agent after agent,
+        each agent's steps in time order; the last step of every run is truncated iff it is not done (:145).  The index list
+        is built on the host from the done flags (O(T x procs)); the data moves in two device gathers.
+          obs_slab [T+1, S, D], act_slab [T, S] or [T, S, A], logp_slab [T, S] device f32;
+          rew / done / trunc [T, S] host f32; env_done [T, procs] bool; slot0 [procs+1] first slot of every process."""
+        dev = obs_slab.device
+        T, S, D = act_slab.shape[0], obs_slab.shape[1], obs_slab.shape[2]
+        n_procs = env_done.shape[1]
         runs = []           # (completion tick, proc, t0, t1) with t1 inclusive
-        for p in range(self.n_procs):
+        for p in range(n_procs):
             t0 = 0
             for t in np.flatnonzero(env_done[:, p]):
                 runs.append((int(t), p, t0, int(t)))
@@ -190,17 +199,17 @@ class BatchedAgentManager(object):
             if t0 < T:
                 runs.append((T + p, p, t0, T - 1))      # still open: after the completed ones, by process id
         runs.sort()
-        flat = []
-        last_rows = []
-        pos = 0
+        flat, last_rows, pos = [], [], 0
         for _, p, t0, t1e in runs:
             ts = np.arange(t0, t1e + 1, dtype=np.int64)
-            for s in range(self._slot0[p], self._slot0[p + 1]):
+            for s in range(int(slot0[p]), int(slot0[p + 1])):
                 flat.append(ts * S + s)
                 pos += len(ts)
                 last_rows.append(pos - 1)
-        flat = np.concatenate(flat)
+        flat = np.concatenate(flat) if flat else np.zeros(0, np.int64)
         n_collected = int(flat.shape[0])
+        # f32 flags: the reference's list mixes np.float32 and Python ints and so comes out float64; the values are the same
+        # 0/1 and the scan reads 4 instead of 8 bytes per step
         tr_flat = trunc.reshape(-1)[flat].astype(np.float32)
         dn_flat = done.reshape(-1)[flat]
         last_rows = np.asarray(last_rows, np.int64)
@@ -210,20 +219,19 @@ class BatchedAgentManager(object):
         f32 = lambda: torch.empty(n_collected, dtype=torch.float32, device=dev)  # noqa: E731
         states = torch.empty((n_collected, D), dtype=torch.float32, device=dev)
         next_states = torch.empty_like(states)
-        actions, log_probs = f32(), f32()
+        log_probs, rewards, dones = f32(), f32(), f32()
         rew_d, done_d = torch.from_numpy(rew.reshape(-1)).to(dev), torch.from_numpy(done.reshape(-1)).to(dev)
-        rewards, dones = f32(), f32()
-        src = _Slab(obs_slab.view(-1, D), act_slab.view(-1), logp_slab.view(-1), rew_d, done_d)
-        ops.gather_batch(src, idx, out_actions=actions, out_logp=log_probs, out_values=rewards, out_adv=dones,
-                         out_states=states)
+        wide = act_slab.dim() == 3
+        actions = torch.empty((n_collected, act_slab.shape[2]), dtype=torch.float32, device=dev) if wide else f32()
+        src = _Slab(obs_slab.view(-1, D), None if wide else act_slab.view(-1), logp_slab.view(-1), rew_d, done_d)
+        ops.gather_batch(src, idx, out_actions=None if wide else actions, out_logp=log_probs, out_values=rewards,
+                         out_adv=dones, out_states=states)
+        if wide:
+            ops.gather_batch(_Slab(act_slab.view(T * S, -1), None, None, None, None), idx, out_states=actions)
         nxt = _Slab(obs_slab.view(-1, D)[S:], None, None, None, None)           # row (t+1, s)
         ops.gather_batch(nxt, idx, out_states=next_states)
         truncated = torch.from_numpy(tr_flat).to(dev)
-
-        self.cumulative_timesteps += n_collected
-        t2 = time.perf_counter()
-        return (states, actions, log_probs, rewards, next_states, dones, truncated), collected_metrics, n_collected, \
-            t2 - t1
+        return states, actions, log_probs, rewards, next_states, dones, truncated
 
     def cleanup(self):
         import traceback

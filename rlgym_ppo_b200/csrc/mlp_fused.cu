@@ -97,6 +97,7 @@ struct Params {
     float inv_batch, clip, ent_coef;
     const float* u_inject;
     uint64_t seed, offset;
+    const unsigned long long* d_offset;   // optional device counter added to `offset` (a captured graph keeps sampling fresh numbers)
     int deterministic;
     float* actions_out;
     int64_t* actions_i64_out;
@@ -789,7 +790,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 if (p.u_inject != nullptr) {
                                     u = __ldg(p.u_inject + row);
                                 } else {
-                                    const uint64_t ctr = p.offset + (uint64_t)row;
+                                    const uint64_t ctr = p.offset + (p.d_offset != nullptr ? (uint64_t)__ldg(p.d_offset) : 0ull) +
+                                                         (uint64_t)row;
                                     const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
                                                                   make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
                                     u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
@@ -1068,15 +1070,33 @@ int rlppo_policy_train_fused(const rlppo_fused_net* net, const uint16_t* x, int6
     return launch_fused<true, true>(net, x, M, p, static_cast<cudaStream_t>(stream));
 }
 
+}  // extern "C"
+
+namespace {
+__global__ void u64_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+}  // namespace
+
+extern "C" {
+
+int rlppo_u64_add(uint64_t* d_counter, uint64_t inc, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(d_counter != nullptr, "null pointer");
+    u64_add_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(d_counter), inc);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
+
 int rlppo_policy_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, int n_actions,
-                             const float* u_inject, uint64_t seed, uint64_t offset, int deterministic,
-                             float* actions_out, int64_t* actions_i64_out, float* logp_out, void* stream) {
+                             const float* u_inject, uint64_t seed, uint64_t offset, const uint64_t* d_offset,
+                             int deterministic, float* actions_out, int64_t* actions_i64_out, float* logp_out,
+                             void* stream) {
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(x != nullptr, "null pointer");
     RLPPO_CHECK_ARG(n_actions >= 1 && n_actions <= 128, "fused path: n_actions must be in [1,128]");
     Params p{};
     p.n_actions = n_actions;
     p.u_inject = u_inject; p.seed = seed; p.offset = offset; p.deterministic = deterministic;
+    p.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
     p.actions_out = actions_out; p.actions_i64_out = actions_i64_out; p.logp_out = logp_out;
     return launch_fused<true, false>(net, x, M, p, static_cast<cudaStream_t>(stream));
 }

@@ -360,10 +360,16 @@ def policy_train_fused(net, x, M, n_actions, actions, old_logp, adv, inv_batch, 
          work=("flop", _net_flops(net, M, n_actions, True), "byte", _net_bytes(net, M, (n_actions + 7) // 8 * 8, True, True)))
 
 
+def u64_add(counter, inc):
+    """*counter += inc on the device (counter: int64[1] tensor); graph-capturable."""
+    call("rlppo_u64_add", ptr(counter), int(inc), stream_ptr())
+
+
 def policy_infer_fused(net, x, M, n_actions, u=None, seed=0, offset=0, deterministic=False, actions_out=None,
-                       actions_i64_out=None, logp_out=None):
+                       actions_i64_out=None, logp_out=None, offset_dev=None):
     call("rlppo_policy_infer_fused", ctypes.byref(net), ptr(x), int(M), int(n_actions), ptr(u), int(seed) & (2 ** 64 - 1),
-         int(offset) & (2 ** 64 - 1), int(bool(deterministic)), ptr(actions_out), ptr(actions_i64_out), ptr(logp_out),
+         int(offset) & (2 ** 64 - 1), ptr(offset_dev), int(bool(deterministic)), ptr(actions_out), ptr(actions_i64_out),
+         ptr(logp_out),
          stream_ptr(), work=("flop", _net_flops(net, M, n_actions, False), "byte", _net_bytes(net, M, 0, False, True)))
 
 

@@ -227,3 +227,17 @@ def test_other_heads_match_reference(golden, tag, ptype):
     for k, v in rep.items():
         assert abs(v - ref_rep[k]) <= 1e-4 * max(abs(ref_rep[k]), 1.0), (k, v, ref_rep[k])
     assert ref_rep["SB3 Clip Fraction"] > 0.2
+
+
+def test_flatten_rollout_matches_reference(golden):
+    """the restated flattening equals what the reference's own collect_timesteps produced for
+    scripted rollouts (tests/golden/make_golden_collect.py), value for value."""
+    g = golden("collect")
+    for case in g["cases"]:
+        ins = [g[f"{case}.in.{k}"] for k in ("obs", "acts", "logp", "rew", "done", "trunc")]
+        got = O.flatten_rollout(*ins, [int(a) for a in g[f"{case}.agents"]])
+        assert got[0].shape[0] == int(g[f"{case}.n"][0])
+        for arr, k in zip(got, ("states", "actions", "log_probs", "rewards", "next_states", "dones", "truncated")):
+            want = g[f"{case}.out.{k}"]
+            assert arr.shape == want.shape, (case, k, arr.shape, want.shape)
+            assert np.array_equal(arr.astype(np.float64), want.astype(np.float64)), (case, k)

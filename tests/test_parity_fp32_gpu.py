@@ -160,14 +160,30 @@ def test_c2_shape_one_step_vs_fp32_oracle():
     want_g = [t.numpy() for t in orc.last_grads[0] + orc.last_grads[1]]
     want_w = [t.numpy() for t in orc.pol + orc.val]
     old_w = [t.numpy() for t in pol + val]
+    # The same step in fp64 (exact to ~1e-16): how far the REFERENCE'S OWN fp32 evaluation is from the exact gradient.
+    # fp32 SGEMM rounding flips ReLU masks of pre-activations within ~1e-7 of zero; on this step that alone moves the
+    # policy-net gradients by ~1.2e-3 rel-L2 -- any two fp32 evaluations with different summation orders (CPU vs GPU,
+    # other thread counts) differ by that much, so 1e-3 against ONE fp32 evaluation is not a well-posed bar here.
+    ob64 = O.BufferOracle(n, 123)
+    ob64.submit(**fields)
+    orc64 = O.PPOLearnerOracle([t.double() for t in pol], [t.double() for t in val], n, 1, 3e-4, 3e-4, 0.2, 0.001, n)
+    for _, (b_acts, b_old, b_obs, b_tgt, b_adv) in ob64.batches(n):
+        pg64, vg64, _ = O.ppo_minibatch(orc64.pol, orc64.val, torch.from_numpy(b_obs).double(), torch.from_numpy(b_acts),
+                                        torch.from_numpy(b_old).double(), torch.from_numpy(b_tgt).double(),
+                                        torch.from_numpy(b_adv).double(), 0.2, 0.001, n)
+    true_g = [t.numpy() for t in O.clip_grad_norm(pg64, 0.5)[0] + O.clip_grad_norm(vg64, 0.5)[0]]
+    floor = [rel_l2(a, b) for a, b in zip(want_g, true_g)]
     table = {"shape": {"rows": n, "obs": obs, "actions": act, "layers": list(layers)},
-             "oracle": "oracle.PPOLearnerOracle fp32 (torch CPU SGEMM), quant=None", "modes": {}}
+             "oracle": "oracle.PPOLearnerOracle fp32 (torch CPU SGEMM), quant=None",
+             "truth": "the same step in fp64 (oracle.ppo_minibatch on float64 tensors)",
+             "reference_fp32_vs_fp64_grad_rel_l2": floor, "modes": {}}
     metrics = ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction",
                "Policy Update Magnitude", "Value Function Update Magnitude")
     for precision in ("fp32", "bf16"):
         report, grads, weights = _run_c2(precision, pol, val, fields, n, obs, act, layers)
         table["modes"][precision] = {
             "grad_rel_l2": [rel_l2(a, b) for a, b in zip(grads, want_g)],
+            "grad_rel_l2_vs_fp64": [rel_l2(a, b) for a, b in zip(grads, true_g)],
             "weight_rel_l2": [rel_l2(a, b) for a, b in zip(weights, want_w)],
             "update_rel_l2": [rel_l2(a - o, b - o) for a, b, o in zip(weights, want_w, old_w)],
             "weight_max_abs": [float(np.abs(a - b).max()) for a, b in zip(weights, want_w)],
@@ -183,7 +199,11 @@ def test_c2_shape_one_step_vs_fp32_oracle():
     print(json.dumps(table["modes"], indent=1))
     assert 0.3 < want["SB3 Clip Fraction"] < 0.7          # the clip branch is exercised
     m = table["modes"]["fp32"]
-    assert max(m["grad_rel_l2"]) < 1e-3, m["grad_rel_l2"]
+    # (1) against the exact gradient: the north-star 1e-3 with two orders of magnitude to spare (measured ~1e-5)
+    assert max(m["grad_rel_l2_vs_fp64"]) < 1e-4, m["grad_rel_l2_vs_fp64"]
+    # (2) against the fp32 oracle: bounded by that evaluation's own distance from the exact gradient (+ ours)
+    for got_e, fl in zip(m["grad_rel_l2"], floor):
+        assert got_e < max(1e-3, 1.25 * fl + 1e-4), (m["grad_rel_l2"], floor)
     assert max(m["weight_rel_l2"]) < 1e-3, m["weight_rel_l2"]
     for k, (got, ref) in m["metrics"].items():
         assert abs(got - ref) <= 1e-3 * max(1.0, abs(ref)), (k, got, ref)
