@@ -63,6 +63,11 @@ int rlppo_gae_chunk_summary(const float* rew, const float* done, const void* tru
                             const float* values, int64_t n, double gamma, double lambda,
                             const float* ret_std, double* out4, void* ws, size_t ws_bytes, void* stream);
 
+/* Sharded scan, step 2: summaries f64[world,4] = every chunk's rlppo_gae_chunk_summary (chunk 0 = the start
+ * of the rollout), gathered from the ranks.  carry2 f64[2] = {A, R} just right of chunk `rank`: the chunks to its right
+ * composed onto 0, rightmost first.  Feed it to rlppo_gae_f32 as carry_in. */
+int rlppo_gae_compose_carry(const double* summaries, int rank, int world, double* carry2, void* stream);
+
 /* ---- (b-3) WelfordRunningStat: rlgym_ppo/util/running_stats.py:30-69 ------------------------------
  * Sequential Welford over n samples of width dim, bit-faithful to update() (:37-46): state mean/m2 f32[dim],
  * count i64[1]; f64 intermediates for f64 samples (NumPy>=2), f32 for f32 samples.  Afterwards writes

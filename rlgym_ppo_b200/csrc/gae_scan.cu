@@ -881,9 +881,28 @@ int launch_gae(const float* rew, const float* done, const void* trunc, int trunc
     return RLPPO_OK;
 }
 
+// carry of chunk `rank` = the chunks to its right composed onto 0, rightmost first: x -> b + a * x per chunk
+__global__ void compose_carry_kernel(const double* __restrict__ summ, int rank, int world, double* __restrict__ carry) {
+    double A = 0.0, R = 0.0;
+    for (int k = world - 1; k > rank; --k) {
+        A = summ[4 * k + 1] + summ[4 * k + 0] * A;
+        R = summ[4 * k + 3] + summ[4 * k + 2] * R;
+    }
+    carry[0] = A;
+    carry[1] = R;
+}
+
 }  // namespace
 
 extern "C" {
+
+int rlppo_gae_compose_carry(const double* summaries, int rank, int world, double* carry2, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(summaries && carry2 && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    compose_carry_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(summaries, rank, world, carry2);
+    RLPPO_LAUNCH_CHECK();
+    return RLPPO_OK;
+}
 
 size_t rlppo_gae_workspace_bytes(int64_t n) { return ws_layout(n < 1 ? 1 : n).total; }
 

@@ -71,12 +71,22 @@ def gae(rew, done, trunc, values, gamma, lmbda, ret_std=None, out=None, ret_head
     return vt, adv, ret
 
 
-def gae_chunk_summary(rew, done, trunc, values, gamma, lmbda, ret_std=None):
+def gae_chunk_summary(rew, done, trunc, values, gamma, lmbda, ret_std=None, out=None):
     n = rew.numel()
-    out = torch.empty(4, dtype=torch.float64, device=rew.device)
+    if out is None:
+        out = torch.empty(4, dtype=torch.float64, device=rew.device)
     ws = _workspace(n, rew.device)
     call("rlppo_gae_chunk_summary", ptr(rew), ptr(done), ptr(trunc), int(trunc.dtype == torch.float64), ptr(values),
          n, float(gamma), float(lmbda), ptr(ret_std), ptr(out), ptr(ws), ws.numel(), stream_ptr())
+    return out
+
+
+def gae_compose_carry(summaries, rank, world, out=None):
+    """summaries f64 [world, 4] (all ranks' gae_chunk_summary) -> carry f64[2] for chunk `rank`."""
+    assert summaries.dtype == torch.float64 and summaries.numel() == 4 * world and summaries.is_contiguous()
+    if out is None:
+        out = torch.empty(2, dtype=torch.float64, device=summaries.device)
+    call("rlppo_gae_compose_carry", ptr(summaries), int(rank), int(world), ptr(out), stream_ptr())
     return out
 
 

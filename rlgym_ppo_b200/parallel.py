@@ -28,6 +28,18 @@ def rank_rows(k, batch_size, rank, world_size, mode):
     return k * batch_size + rank * local, local
 
 
+def gae_chunk(n, rank, world_size, align=64):
+    """Contiguous chunk [lo, hi) of an n-step flat rollout that `rank` scans when GAE is sharded (the
+    recurrence is an associative affine scan, so the step axis can be cut anywhere).  Chunks are `m` steps long (a
+    multiple of `align`, so every chunk starts 16-byte aligned in f32 and f64 arrays), the last ones may be short or
+    empty.  Returns (lo, hi, m)."""
+    m = -(-int(n) // int(world_size))
+    m = -(-m // align) * align
+    lo = min(int(n), rank * m)
+    hi = min(int(n), lo + m)
+    return lo, hi, m
+
+
 def samples_per_step(batch_size, world_size, mode):
     """Number of samples one optimiser step averages over (the B of the 1/B gradient weight)."""
     return batch_size * world_size if (mode == "sharded" and world_size > 1) else batch_size
