@@ -355,17 +355,73 @@ class Learner(object):
         ret_std = self.return_stats.device_std() if self.standardize_returns else None     # learner.py:356
         n_inc = 0 if stage["head"] is None else stage["head"].numel()
 
+        # GAE shards by trajectory (BASELINE north_star): when every rank holds the SAME rollout
+        # (dp_mode="replicated"), rank r runs the value net and the scan on its contiguous chunk only.
+        world, rank = getattr(ppo, "world_size", 1), getattr(ppo, "rank", 0)
+        shard = (world > 1 and getattr(ppo, "dp_mode", "") == "replicated" and n >= 2048 * world
+                 and os.environ.get("RLPPO_GAE_SHARD", "1") == "1")
+        if hasattr(ppo, "world_size"):
+            ppo.gae_sharded = shard
+
+        def values_and_gae_sharded():
+            """Chunk [lo, hi) of the flat step axis: value net on its rows + 1 halo row, the chunk's affine summary
+            (rlppo_gae_chunk_summary), all-gather of the 4-double summaries, carry = the chunks to the right composed onto 0
+            (rlppo_gae_compose_carry), the scan with that carry, all-gather of advantages / value targets; the first
+            returns (Welford input, learner.py:368-372) come from rank 0's chunk.  Exact: composition of affine maps."""
+            import torch.distributed as dist
+            from . import parallel
+            group = getattr(ppo, "_pg", None)
+            lo, hi, m = parallel.gae_chunk(n, rank, world)
+            cnt = hi - lo
+            sh = stage.get("shard")
+            if sh is None or sh["m"] != m:
+                f64 = lambda k: torch.zeros(k, dtype=torch.float64, device=dev)  # noqa: E731
+                sh = stage["shard"] = {"m": m, "summ": f64(4), "all": f64(4 * world), "carry": f64(2),
+                                       "loc": torch.zeros((2, m), dtype=torch.float32, device=dev),
+                                       "ret": torch.empty(m, dtype=torch.float32, device=dev),
+                                       "full": [torch.empty(world * m, dtype=torch.float32, device=dev) for _ in range(2)],
+                                       "values": torch.empty(m + 1, dtype=torch.float32, device=dev),
+                                       "ws": ops.gae_workspace(m, dev)}
+            states = _f32(d["states"])
+            x = vst.workspace(n + 1)["x"]
+            sh["summ"].zero_()
+            sh["summ"][0] = 1.0       # an empty chunk is the identity map (a = 1, b = 0)
+            sh["summ"][2] = 1.0
+            if cnt > 0:
+                vst.stage_rows(states[lo:hi], x)
+                halo = states[hi:hi + 1] if hi < n else (_f32(d["ns_last"]) if late_ns else _f32(d["next_states"])[n - 1:n])
+                vst.stage_rows(halo, x[cnt:cnt + 1])
+                values = value_net.values_from_bf16(x, cnt + 1, out=sh["values"][:cnt + 1])
+                rew, done, trunc = _f32(d["rewards"])[lo:hi], _f32(d["dones"])[lo:hi], d["truncated"][lo:hi]
+                ops.gae_chunk_summary(rew, done, trunc, values, self.gae_gamma, self.gae_lambda, ret_std, out=sh["summ"])
+            dist.all_gather_into_tensor(sh["all"], sh["summ"], group=group)
+            ops.gae_compose_carry(sh["all"], rank, world, out=sh["carry"])
+            if cnt > 0:
+                head = stage["head"] if (rank == 0 and n_inc) else None
+                ops.gae(rew, done, trunc, values, self.gae_gamma, self.gae_lambda, ret_std,
+                        out=(sh["loc"][0, :cnt], sh["loc"][1, :cnt], sh["ret"][:cnt]), ret_head64=head,
+                        carry_in=sh["carry"], ws=sh["ws"])
+            dist.all_gather_into_tensor(sh["full"][0], sh["loc"][0], group=group)
+            dist.all_gather_into_tensor(sh["full"][1], sh["loc"][1], group=group)
+            if n_inc:
+                assert n_inc <= m, "the returns that feed the running statistics must lie in rank 0's chunk"
+                dist.broadcast(stage["head"], src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            return sh["full"][0][:n], sh["full"][1][:n]
+
         def body():
             """Device work only (what the CUDA graph captures): value net on [states ; next_states[-1]]
             (learner.py:347-352), GAE (:358-366), return statistics (:368-372), the nine ring appends (:375-385)."""
-            states = _f32(d["states"])
-            x = vst.workspace(n + 1)["x"]
-            vst.stage_rows(states, x)
-            vst.stage_rows(_f32(d["ns_last"]) if late_ns else _f32(d["next_states"])[n - 1:n], x[n:n + 1])
-            values = value_net.values_from_bf16(x, n + 1, out=stage["values"])      # stays on the device
-            vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
-                                 self.gae_lambda, ret_std, out=stage["out"], ret_head64=stage["head"],
-                                 ws=stage["gae_ws"])
+            if shard:
+                vt, adv = values_and_gae_sharded()
+            else:
+                states = _f32(d["states"])
+                x = vst.workspace(n + 1)["x"]
+                vst.stage_rows(states, x)
+                vst.stage_rows(_f32(d["ns_last"]) if late_ns else _f32(d["next_states"])[n - 1:n], x[n:n + 1])
+                values = value_net.values_from_bf16(x, n + 1, out=stage["values"])      # stays on the device
+                vt, adv, _ = ops.gae(_f32(d["rewards"]), _f32(d["dones"]), d["truncated"], values, self.gae_gamma,
+                                     self.gae_lambda, ret_std, out=stage["out"], ret_head64=stage["head"],
+                                     ws=stage["gae_ws"])
             fields = {k: v for k, v in d.items() if k != "ns_last"}
             fields["values"], fields["advantages"] = vt, adv
             if n_inc:
@@ -392,7 +448,8 @@ class Learner(object):
             graphs = self._add_graphs = GraphCache()
         key = (n, obs, stage["gen"], tuple(ptrs), late_ns, buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
                float(self.gae_gamma), float(self.gae_lambda), bool(self.standardize_returns), vst.fused_ok, vst.precision)
-        if not (getattr(ppo, "use_cuda_graph", False) and _lib._TIMING is None and graphs.replay(key, body)):
+        # (the sharded scan has NCCL exchanges in it and runs eagerly; everything else replays as one graph)
+        if shard or not (getattr(ppo, "use_cuda_graph", False) and _lib._TIMING is None and graphs.replay(key, body)):
             body()
         if late_ns:
             buf.append_next_states_late(ns_dev, late)      # position from the host mirrors, BEFORE they advance

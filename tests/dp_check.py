@@ -113,6 +113,38 @@ def main():
         assert torch.equal(g, gathered[0]), "sharded replicas diverged"
     assert np.isfinite(rep["Policy Entropy"]) and rep["Cumulative Model Updates"] == 18
 
+    # ---- GAE sharded across ranks (replicated mode): == the one-rank scan on the same rollout -------------------------
+    # Learner.add_new_experience on `world` ranks (each runs the value net + scan on its contiguous chunk, 4-double chunk
+    # summaries all-gathered, carries composed, results all-gathered) against the same call on a one-rank learner.
+    from types import SimpleNamespace
+    from rlgym_ppo_b200.learner import Learner
+    from rlgym_ppo_b200.ppo import ExperienceBuffer
+    rng = np.random.RandomState(77)
+    n_roll = 20000 + 37
+    states = rng.randn(n_roll, 89).astype(np.float32)
+    d_ = (rng.rand(n_roll) < 1 / 300).astype(np.float32)
+    tr_ = ((rng.rand(n_roll) < 1 / 1500) * (1 - d_)).astype(np.float64)
+    tr_[-1] = 1 - d_[-1]
+    exp = (states, rng.randint(0, 90, n_roll).astype(np.float32), (-4.5 + 0.1 * rng.randn(n_roll)).astype(np.float32),
+           (rng.randn(n_roll) * 0.1).astype(np.float32), np.roll(states, -1, 0).copy(), d_, tr_)
+    outs = []
+    for lrn in (dp, alone):
+        ns = SimpleNamespace(ppo_learner=lrn, return_stats=WelfordRunningStat(1, device=dev), standardize_returns=True,
+                             gae_gamma=0.99, gae_lambda=0.95, max_returns_per_stats_increment=150,
+                             experience_buffer=ExperienceBuffer(3 * n_roll, 5, dev))
+        for _ in range(2):      # the second call scans with a learned return_std
+            Learner.add_new_experience(ns, exp)
+        outs.append((ns.experience_buffer.values.clone(), ns.experience_buffer.advantages.clone(),
+                     np.asarray(ns.return_stats.std).copy(), ns.return_stats.count))
+    assert dp.gae_sharded and not alone.gae_sharded
+    (v_s, a_s, std_s, c_s), (v_1, a_1, std_1, c_1) = outs
+    assert c_s == c_1 == 300 and np.array_equal(std_s, std_1), (std_s, std_1)
+    gae_err = max(float((v_s - v_1).abs().max()), float((a_s - a_1).abs().max()))
+    assert gae_err <= 2e-6, f"sharded GAE differs from the one-rank scan: max abs {gae_err}"
+    if rank == 0:
+        print(f"sharded GAE: {world} chunks of a {n_roll}-step rollout vs one launch: max abs diff {gae_err:.2e}, "
+              f"bit-identical fraction {float((a_s == a_1).float().mean()):.6f}")
+
     # ---- return statistics follow rank 0 ----
     st = WelfordRunningStat(1, device=dev)
     st.increment((np.arange(150, dtype=np.float64) + 10.0 * rank), 150)

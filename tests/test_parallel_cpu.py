@@ -93,3 +93,71 @@ def test_choose_collective():
     import pytest
     with pytest.raises(ValueError):
         parallel.choose_collective(2, small, requested="ring")
+
+
+def _gae_worker(rank, world, port, out_dir):
+    """The sharded-GAE protocol of Learner.add_new_experience (replicated mode) with the fp64 oracle standing in for the
+    kernels: chunk bounds from parallel.gae_chunk, 4-double summaries all-gathered, carry composed rightmost first, chunk
+    scanned with its carry, padded chunks all-gathered."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rlgym_ppo_b200 import parallel
+        n, g, lam = 1000, 0.99, 0.95
+        rng = np.random.RandomState(3)                       # the same rollout on every rank
+        rew, val = rng.randn(n), rng.randn(n + 1)
+        done = (rng.rand(n) < 0.02).astype(np.float64)
+        trunc = ((rng.rand(n) < 0.01) * (1 - done)).astype(np.float64)
+        lo, hi, m = parallel.gae_chunk(n, rank, world, align=64)
+        assert m % 64 == 0 and lo == min(n, rank * m) and hi == min(n, lo + m)
+
+        def scan(lo, hi, cA, cR):
+            adv, ret = np.zeros(hi - lo), np.zeros(hi - lo)
+            aA = aR = 1.0
+            for t in range(hi - 1, lo - 1, -1):
+                nd, nt = 1 - done[t], 1 - trunc[t]
+                delta = rew[t] + g * val[t + 1] * nd - val[t]
+                cA = delta + g * lam * nd * nt * cA
+                cR = rew[t] + g * nd * nt * cR
+                aA *= g * lam * nd * nt
+                aR *= g * nd * nt
+                adv[t - lo], ret[t - lo] = cA, cR
+            return adv, ret, aA, aR
+
+        adv0, ret0, aA, aR = scan(lo, hi, 0.0, 0.0)           # summary: x -> b + a x with b = the carry-0 result
+        summ = torch.tensor([aA, adv0[0] if hi > lo else 0.0, aR, ret0[0] if hi > lo else 0.0], dtype=torch.float64)
+        if hi == lo:
+            summ = torch.tensor([1.0, 0.0, 1.0, 0.0], dtype=torch.float64)
+        allsum = torch.zeros(4 * world, dtype=torch.float64)
+        dist.all_gather_into_tensor(allsum, summ)
+        A = R = 0.0
+        for k in range(world - 1, rank, -1):                  # rlppo_gae_compose_carry
+            A = float(allsum[4 * k + 1] + allsum[4 * k] * A)
+            R = float(allsum[4 * k + 3] + allsum[4 * k + 2] * R)
+        adv, ret, _, _ = scan(lo, hi, A, R)
+        loc = torch.zeros(m, dtype=torch.float64)
+        loc[:hi - lo] = torch.from_numpy(adv)
+        full = torch.zeros(world * m, dtype=torch.float64)
+        dist.all_gather_into_tensor(full, loc)
+        want, _, _, _ = scan(0, n, 0.0, 0.0)
+        np.save(os.path.join(out_dir, f"gae{rank}.npy"), np.abs(full[:n].numpy() - want).max())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_gae_protocol(tmp_path, world):
+    mp.spawn(_gae_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert float(np.load(tmp_path / f"gae{r}.npy")) < 1e-12
+
+
+def test_gae_chunk_bounds():
+    from rlgym_ppo_b200 import parallel
+    for n in (1, 63, 64, 1000, 50000, 1003520):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.gae_chunk(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))        # contiguous, ordered, disjoint
+            assert all(s[2] == spans[0][2] and s[2] % 64 == 0 for s in spans)
+            assert all(s[0] % 64 == 0 or s[0] == n for s in spans)            # chunk starts are 16-byte aligned
