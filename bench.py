@@ -259,6 +259,26 @@ class Rig:
         self.barrier()
         return (time.perf_counter() - t0) * 1e3
 
+    def phase_pass(self, K, flush_buf):
+        """Device time of the two halves of a step (events around each), K steps: where a multi-GPU step waits."""
+        torch = self.torch
+        self.barrier()
+        a = b = 0.0
+        for _ in range(K):
+            flush_buf.zero_()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            exp = self.next_dev()
+            e0.record()
+            self.Learner.add_new_experience(self.ns, exp)
+            e1.record()
+            self.ppo.learn(self.ns.experience_buffer)
+            e2.record()
+            torch.cuda.synchronize()
+            a += e0.elapsed_time(e1)
+            b += e1.elapsed_time(e2)
+        self.barrier()
+        return a / K, b / K
+
     def max_over_ranks(self, *vals):
         if self.world == 1:
             return vals
@@ -494,6 +514,7 @@ def b200_arm(args, wl):
     e2e_ms = rig.timed_e2e(args.steps, n_warm)
     clocks = sampler.stop() if sampler else None
     dev_ms, e2e_ms = rig.max_over_ranks(dev_ms, e2e_ms)
+    phases = rig.max_over_ranks(*rig.phase_pass(5, flush_buf))
 
     # ---- (3) per-kernel pass for the roofline object (rank 0; not part of the timed numbers) --------------------------
     roofline, kernels = None, None
@@ -595,6 +616,8 @@ def b200_arm(args, wl):
             "e2e": {"value": n_glob * K / (e2e_ms / 1e3), "unit": "timesteps/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": rig_bytes[0] * world, "d2h_bytes_per_step": rig_bytes[1] * world},
             "gpu_launches": calls,
+            "phases_ms": {"add_new_experience": phases[0], "learn": phases[1],
+                          "note": "device time of the two halves of a step, max over ranks (5 extra steps)"},
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,

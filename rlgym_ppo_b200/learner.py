@@ -304,10 +304,17 @@ class Learner(object):
         # ---- the 7 arrays in HBM at addresses a graph can bake in: host arrays are copied (one async H2D each) into
         # persistent device slots; arrays that already live on the device are used where they are ---------------------
         shapes = tuple((tuple(np.shape(x)), _staged_dtype(x)) for x in experience)
+        # "sharded" data parallelism over peer memory: one rollout per rank, the return statistics are rank 0's (the
+        # reference updates them from the head of ONE rollout, learner.py:368-372).  Rank 0 publishes its std in a
+        # symmetric-memory slot (double buffered by iteration parity) and every rank's scan reads that slot directly over
+        # NVLink: no broadcast, no NCCL call in the iteration.
+        peer_std = (getattr(ppo, "world_size", 1) > 1 and getattr(ppo, "dp_mode", "") == "sharded"
+                    and getattr(ppo, "_std_slots_rank0", None) is not None and self.standardize_returns)
+        stats_here = (not peer_std) or ppo.rank == 0
         stage = getattr(self, "_exp_stage", None)
         if stage is None or stage["shapes"] != shapes:
             stage = {"shapes": shapes, "gen": (0 if stage is None else stage["gen"] + 1)}
-            n_inc = min(int(self.max_returns_per_stats_increment), n) if self.standardize_returns else 0
+            n_inc = min(int(self.max_returns_per_stats_increment), n) if (self.standardize_returns and stats_here) else 0
             stage["values"] = torch.empty(n + 1, dtype=torch.float32, device=dev)
             stage["out"] = tuple(torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
             stage["head"] = torch.empty(n_inc, dtype=torch.float64, device=dev) if n_inc else None
@@ -354,6 +361,19 @@ class Learner(object):
         vst.refresh_operands()
         ret_std = self.return_stats.device_std() if self.standardize_returns else None     # learner.py:356
         n_inc = 0 if stage["head"] is None else stage["head"].numel()
+        par = 0
+        if peer_std:
+            par = getattr(self, "_std_parity", None)
+            if par is None:
+                # first call: rank 0's current std (1, or whatever a loaded checkpoint holds) into slot 0, once, for everyone
+                import torch.distributed as dist
+                par = 0
+                if ppo.rank == 0:
+                    ppo._std_slots_local[0:1].copy_(ret_std)
+                torch.cuda.synchronize(dev)
+                dist.barrier(getattr(ppo, "_pg", None))
+            ret_std = ppo._std_slots_rank0[par:par + 1]
+            self._std_parity = 1 - par
 
         # GAE shards by trajectory (BASELINE north_star): when every rank holds the SAME rollout
         # (dp_mode="replicated"), rank r runs the value net and the scan on its contiguous chunk only.
@@ -437,6 +457,8 @@ class Learner(object):
                 side.wait_event(fork)
                 with torch.cuda.stream(side):
                     self.return_stats.increment_device(stage["head"], n_inc)
+                    if peer_std:     # the scale the NEXT iteration's scans read (every rank, out of this rank's memory)
+                        ppo._std_slots_local[1 - par:2 - par].copy_(self.return_stats.device_std())
                     join.record(side)
                 buf.append_device(fields)
                 main.wait_event(join)
@@ -447,6 +469,7 @@ class Learner(object):
         if graphs is None:
             graphs = self._add_graphs = GraphCache()
         key = (n, obs, stage["gen"], tuple(ptrs), late_ns, buf.uid, getattr(vst, "ws_gen", 0), id(self.return_stats._d), n_inc,
+               peer_std, par,
                float(self.gae_gamma), float(self.gae_lambda), bool(self.standardize_returns), vst.fused_ok, vst.precision)
         # (the sharded scan has NCCL exchanges in it and runs eagerly; everything else replays as one graph)
         if shard or not (getattr(ppo, "use_cuda_graph", False) and _lib._TIMING is None and graphs.replay(key, body)):
@@ -457,8 +480,8 @@ class Learner(object):
         buf.advance_host(min(n, buf.capacity))
         if n_inc:
             self.return_stats._dev_is_newer = True
-            if getattr(ppo, "world_size", 1) > 1 and getattr(ppo, "dp_mode", "") == "sharded":
-                # one rollout per rank: the statistics follow rank 0's (the head of the concatenated rollout)
+            if getattr(ppo, "world_size", 1) > 1 and getattr(ppo, "dp_mode", "") == "sharded" and not peer_std:
+                # one rollout per rank (NCCL gradient exchange: no peer mappings): the statistics follow rank 0's
                 self.return_stats.broadcast_(src=0, group=getattr(ppo, "_pg", None))
 
     # ---- checkpoints: the reference's directory layout and file formats (learner.py:387-564) ---------------------

@@ -92,16 +92,22 @@ class PPOLearner(object):
         # ---- one flat arena [policy | value] for params, grads and both Adam moments -------------------------
         ps, vs = self.policy._stack, self.value_net._stack
         n_p, n_v = ps.n_params, vs.n_params
-        self._seg = np.asarray([0, n_p, n_p + n_v], dtype=np.int64)
-        self._params = torch.zeros(n_p + n_v, dtype=torch.float32, device=dev)
+        self._pg = process_group
+        self.world_size, self.rank = parallel.world(process_group)
+        # Data parallel: the 8 metric sums of an optimiser step ride at the end of the gradient arena as a third segment
+        # with learning rate 0, so the gradient exchange (peer loads inside the optimiser launch, or the NCCL all-reduce)
+        # sums them over the ranks too -- no separate metric collective, nothing NCCL inside an iteration on the p2p path.
+        n_x = 8 if self.world_size > 1 else 0
+        self._n_net = n_p + n_v
+        self._seg = np.asarray([0, n_p, n_p + n_v] + ([n_p + n_v + n_x] if n_x else []), dtype=np.int64)
+        n_seg = len(self._seg) - 1
+        self._params = torch.zeros(n_p + n_v + n_x, dtype=torch.float32, device=dev)
         # Gradient exchange between data-parallel ranks (world_size > 1):
         #  "p2p"  (default): the gradient arena lives in symmetric memory every GPU of the box has mapped; the optimiser
         #         kernel itself sums the peers' arenas over NVLink in rank order (rlppo_norm_clip_adam_peers) -- no
         #         separate collective launch, and nothing NCCL inside the step, so a whole learn() stays ONE CUDA graph.
         #         `.grad` then holds this rank's own contribution; the summed gradient is `self._gsum`.
         #  "nccl": torch.distributed all_reduce on the flat arena between the backward and the optimiser launch.
-        self._pg = process_group
-        self.world_size, self.rank = parallel.world(process_group)
         self.dp_collective = "none"
         self._grads = None
         if self.world_size > 1:
@@ -113,7 +119,7 @@ class PPOLearner(object):
                 import torch.distributed as dist
                 err = None
                 try:
-                    self._setup_peers(dev, n_p + n_v)
+                    self._setup_peers(dev, n_p + n_v + n_x)
                 except Exception as e:  # noqa: BLE001
                     err = e
                 ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
@@ -131,16 +137,16 @@ class PPOLearner(object):
         self._v = torch.zeros_like(self._params)
         self._before = torch.zeros_like(self._params)
         ps.bind(self._params[:n_p], self._grads[:n_p])
-        vs.bind(self._params[n_p:], self._grads[n_p:])
-        self._steps = torch.zeros(2, dtype=torch.int64, device=dev)
-        self._lr_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+        vs.bind(self._params[n_p:n_p + n_v], self._grads[n_p:n_p + n_v])
+        self._steps = torch.zeros(n_seg, dtype=torch.int64, device=dev)
+        self._lr_dev = torch.zeros(n_seg, dtype=torch.float32, device=dev)
         self._lr_host = None
-        self._sqnorm = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._sqnorm = torch.zeros(n_seg, dtype=torch.float32, device=dev)
         self._tail = torch.zeros(12, dtype=torch.float32, device=dev)   # metrics[0:8] | update sq-norms [8:10]
         self._tail_host = torch.zeros(12, dtype=torch.float32).pin_memory()
 
         self.policy_optimizer = FusedAdam(ps, policy_lr, self._m[:n_p], self._v[:n_p], self._steps[0:1])
-        self.value_optimizer = FusedAdam(vs, critic_lr, self._m[n_p:], self._v[n_p:], self._steps[1:2])
+        self.value_optimizer = FusedAdam(vs, critic_lr, self._m[n_p:n_p + n_v], self._v[n_p:n_p + n_v], self._steps[1:2])
 
         policy_params_count, critic_params_count = n_p, n_v
         total_parameters = policy_params_count + critic_params_count
@@ -211,6 +217,17 @@ class PPOLearner(object):
         self._peer_grad_ptrs = [int(x) for x in gh.buffer_ptrs]
         self._peer_flag_ptrs = [int(x) for x in fh.buffer_ptrs]
         self._symm = (grads, gh, flags, fh)         # keep the mappings alive
+        # Return-normalisation scale of rank 0, double buffered by iteration parity: in "sharded" mode every rank's GAE
+        # kernel reads it straight out of rank 0's memory (a peer load), so the per-iteration Welford broadcast disappears
+        # (Learner.add_new_experience).  Both slots start at 1 (the std of an empty WelfordRunningStat).
+        slots = symm_mem.empty(4, dtype=torch.float32, device=dev)
+        slots.fill_(1.0)
+        sh = symm_mem.rendezvous(slots, group)
+        self._std_slots_local = slots
+        self._std_slots_rank0 = sh.get_buffer(0, (4,), torch.float32) if self.rank != 0 else slots
+        self._symm += (slots, sh)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
         if self.dp_collective == "p2p2":
             # two-shot form (experimental): the reduced gradient lives in symmetric memory too, peers read its slices
             gsum = symm_mem.empty(n, dtype=torch.float32, device=dev)
@@ -245,7 +262,8 @@ class PPOLearner(object):
     def _sync_lr(self):
         lr = (float(self.policy_optimizer.param_groups[0]["lr"]), float(self.value_optimizer.param_groups[0]["lr"]))
         if lr != self._lr_host:
-            self._lr_dev.copy_(torch.tensor(lr, dtype=torch.float32))
+            pad = (0.0,) * (self._lr_dev.numel() - 2)          # the metric segment never moves
+            self._lr_dev.copy_(torch.tensor(lr + pad, dtype=torch.float32))
             self._lr_host = lr
 
     # ---- one chunk of one batch: gather -> fwd -> fused heads -> bwd (grads accumulate) -------------------------
@@ -262,7 +280,7 @@ class PPOLearner(object):
         x = mb["x"]
         # (1/mb) * (mb/B), ppo_learner.py:172-177; B = the number of samples one optimiser step averages over
         inv_b = 1.0 / float(parallel.samples_per_step(self.batch_size, self.world_size, self.dp_mode))
-        metrics = self._tail[0:8]
+        metrics = self._step_metrics()
         n = 1
         both_fused = self.policy_type == 0 and self.policy._stack.fused_ok and self.value_net._stack.fused_ok
         if both_fused and self.two_streams and _lib._TIMING is None:
@@ -330,11 +348,24 @@ class PPOLearner(object):
             n += (len(wg_items) + 7) // 8
         self.launches += n
 
+    def _step_metrics(self):
+        """Where the kernels of the current optimiser step accumulate their 8 metric sums: the running totals directly
+        (one rank), or the tail of the gradient arena (data parallel: summed over ranks with the gradients, then added to
+        the totals by _collect_step_metrics)."""
+        if self.world_size > 1:
+            return self._grads[self._n_net:self._n_net + 8]
+        return self._tail[0:8]
+
+    def _collect_step_metrics(self, summed):
+        if self.world_size > 1:
+            self._tail[0:8].add_(summed[self._n_net:self._n_net + 8])
+
     def _optimizer_step(self):
         if self.dp_collective == "p2p2":
             ops.norm_clip_adam_peers2(self._params, self._peer_grad_ptrs, self._peer_flag_ptrs, self._peer_red_ptrs,
                                       self.rank, self._m, self._v, self._seg, self._sqnorm, self._lr_dev, self._steps,
                                       max_norm=0.5, views=self._views if len(self._views) else None)
+            self._collect_step_metrics(self._gsum)
             self._operands_after_step()
             self.launches += 1
             return
@@ -343,6 +374,7 @@ class PPOLearner(object):
             ops.norm_clip_adam_peers(self._params, self._peer_grad_ptrs, self._peer_flag_ptrs, self.rank, self._gsum,
                                      self._m, self._v, self._seg, self._sqnorm, self._lr_dev, self._steps, max_norm=0.5,
                                      views=self._views if len(self._views) else None)
+            self._collect_step_metrics(self._gsum)
             self._operands_after_step()
             self.launches += 1
             return
@@ -363,6 +395,7 @@ class PPOLearner(object):
         # ppo_learner.py:187-193 in one launch: fixed-order (deterministic) norms -> clip -> Adam -> bf16 operand refresh
         ops.norm_clip_adam(self._params, self._grads, self._m, self._v, self._seg, self._sqnorm, self._lr_dev,
                            self._steps, max_norm=0.5, views=self._views if len(self._views) else None)
+        self._collect_step_metrics(self._grads)
         self._operands_after_step()
         self.launches += 1
 
@@ -438,10 +471,9 @@ class PPOLearner(object):
             for k in range(n_batches):
                 base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
                 self._batch_body(exp, self._perm_dev[epoch, base:base + local], local, chunk)
-        ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
+        ops.sqdiff(self._before, self._params, self._seg, self._tail[8:8 + len(self._seg) - 1])
         if tail:
-            parallel.allreduce_sum_(self._tail[0:8], self._pg)
-            self._tail_host.copy_(self._tail, non_blocking=True)
+            self._tail_host.copy_(self._tail, non_blocking=True)      # metric sums are global already (see __init__)
 
     def learn(self, exp):
         """
@@ -471,14 +503,11 @@ class PPOLearner(object):
         whole = (self.use_cuda_graph and _lib._TIMING is None and n_batches > 0
                  and (R == 1 or p2p or self.graph_collectives))
         if whole:
-            # data parallel over peer memory: the graph holds everything but the one 8-float metric all-reduce
-            tail = not p2p or self.graph_collectives
+            # data parallel over peer memory: the graph holds the WHOLE call, the report readback included
+            tail = True
             key = ("learn", total, E, n_batches, tail, self._perm_dev.data_ptr()) + self._graph_key(exp, local, chunk)
             if not self._captured(key, lambda: self._learn_body(exp, n_batches, local, chunk, tail)):
                 self._learn_body(exp, n_batches, local, chunk, tail)
-            if not tail:
-                parallel.allreduce_sum_(self._tail[0:8], self._pg)
-                self._tail_host.copy_(self._tail, non_blocking=True)
             self.policy._stack.mark_operands_fresh()
             self.value_net._stack.mark_operands_fresh()
         else:
@@ -489,8 +518,7 @@ class PPOLearner(object):
                     base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
                     self._batch_step(exp, self._perm_dev[epoch, base:base + local], local, chunk)
             # ---- report: one device -> host readback for the whole call ---------------------------------------
-            ops.sqdiff(self._before, self._params, self._seg, self._tail[8:10])
-            parallel.allreduce_sum_(self._tail[0:8], self._pg)
+            ops.sqdiff(self._before, self._params, self._seg, self._tail[8:8 + len(self._seg) - 1])
             self._tail_host.copy_(self._tail, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         t = self._tail_host.double().numpy()
