@@ -165,7 +165,8 @@ class PPOLearner(object):
         self.clip_range = clip_range
         self.ent_coef = ent_coef
         self.cumulative_model_updates = 0
-        self.max_chunk_rows = int(max_chunk_rows)
+        # RLPPO_MAX_CHUNK_ROWS: experiment knob (rows of a batch processed per fused-kernel launch; see profiles/README_r02.md)
+        self.max_chunk_rows = int(os.environ.get("RLPPO_MAX_CHUNK_ROWS", max_chunk_rows))
 
         # ---- data parallelism ---------------------------------------------------------------------------------
         # Data-parallel modes (world_size > 1; one process per GPU, NCCL through torch.distributed):

@@ -116,6 +116,41 @@ def main():
         assert torch.equal(g, gathered[0]), "sharded replicas diverged"
     assert np.isfinite(rep["Policy Entropy"]) and rep["Cumulative Model Updates"] == 18
 
+    # ---- stress test of the REAL in-kernel gradient exchange (rlppo_norm_clip_adam_peers[2]) ---------------------------
+    # Thousands of back-to-back launches with a random device-side delay in front of each one on every rank (so the ranks
+    # arrive at the flag rendezvous in every possible order, early and late), fresh random gradients per launch, no host
+    # synchronisation in between.  After every launch the summed gradient must be the same bits on every rank and equal the
+    # NCCL all-reduce of the same arenas; a lost or reordered flag update shows up as a stale sum (or as the kernel's
+    # watchdog trap).  Replaces the round-1 Python-thread model of the flag protocol.
+    n_stress = int(os.environ.get("RLPPO_STRESS_LAUNCHES", "3000"))
+    for collective in ("p2p",) + (("p2p2",) if os.environ.get("RLPPO_TEST_P2P2", "1") == "1" else ()):
+        st_l = learner1(None, collective)
+        nn_all = st_l._grads.numel()
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        delay_rng = np.random.RandomState(99 + 7 * rank)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        ref = torch.empty(nn_all, dtype=torch.float32, device=dev)
+        for it in range(n_stress):
+            st_l._grads.copy_(torch.randn(nn_all, device=dev, generator=gen) * 1e-3)
+            ref.copy_(st_l._grads)
+            if delay_rng.rand() < 0.7:
+                torch.cuda._sleep(int(delay_rng.randint(0, 400000)))          # up to ~0.2 ms of skew, per rank, per launch
+            st_l._optimizer_step()
+            if it % 50 == 0:                      # check (and, through NCCL, loosely re-align) every 50 launches
+                dist.all_reduce(ref)
+                gs = st_l._gsum[:nn_all]
+                # rank-order fp32 sum vs NCCL's tree/ring order: equal to rounding; across ranks: the same bits
+                bad += ((gs - ref).abs().max() > 1e-6).int()
+                gathered = [torch.empty_like(gs) for _ in range(world)]
+                dist.all_gather(gathered, gs.contiguous())
+                bad += int(not all(torch.equal(t, gathered[0]) for t in gathered[1:]))
+        torch.cuda.synchronize()
+        assert int(bad.item()) == 0, f"{collective}: stale or diverging gradient sums under skew ({int(bad.item())} checks failed)"
+        if rank == 0:
+            print(f"peer-exchange stress ({collective}): {n_stress} launches with random per-rank skew, sums identical on all "
+                  f"ranks and equal to the NCCL all-reduce")
+
     # ---- GAE sharded across ranks (replicated mode): == the one-rank scan on the same rollout -------------------------
     # Learner.add_new_experience on `world` ranks (each runs the value net + scan on its contiguous chunk, 4-double chunk
     # summaries all-gathered, carries composed, results all-gathered) against the same call on a one-rank learner.
