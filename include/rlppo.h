@@ -399,10 +399,11 @@ int rlppo_norm_clip_adam_peers(float* params, const float* const* h_peer_grads, 
                                float* sqnorm_out, const float* lr, int64_t* step_count, double max_norm, double beta1,
                                double beta2, double eps, const rlppo_bf16_view* h_views, int n_views, void* ws,
                                size_t ws_bytes, void* stream);
-/* EXPERIMENTAL two-shot form of the call above (reduce-scatter + all-gather inside the launch: 2 * 4n bytes over NVLink
- * per rank instead of (world-1) * 4n; for big arenas on many ranks).  h_peer_red[r]: rank r's f32[total] buffer for the
- * reduced gradient in symmetric memory, as mapped here (entry `rank` receives the full sum).  Not selected by default and
- * not yet validated on hardware: PPOLearner(dp_collective="p2p2") / tests/dp_check.py with RLPPO_TEST_P2P2=1. */
+/* Two-shot form of the call above (reduce-scatter + all-gather inside the launch: 2 * 4n bytes over NVLink per rank
+ * instead of (world-1) * 4n; what PPOLearner picks for arenas too big for the one-shot form).  h_peer_red[r]: rank r's
+ * f32[total] buffer for the reduced gradient in symmetric memory, as mapped here (entry `rank` receives the full sum).
+ * Validated on 2 and 8 x B200 (tests/dp_check.py: equal to the NCCL all-reduce to rounding, same bits on every rank,
+ * thousands of launches under random per-rank skew). */
 int rlppo_norm_clip_adam_peers2(float* params, const float* const* h_peer_grads, void* const* h_peer_flags,
                                 const float* const* h_peer_red, int rank, int world, float* m, float* v,
                                 const int64_t* h_seg_off, int n_seg, float* sqnorm_out, const float* lr,

@@ -453,7 +453,7 @@ def norm_clip_adam_peers(params, peer_grad_ptrs, peer_flag_ptrs, rank, gsum, m, 
 
 def norm_clip_adam_peers2(params, peer_grad_ptrs, peer_flag_ptrs, peer_red_ptrs, rank, m, v, seg_off, sqnorm_out, lr,
                           step_count, max_norm=0.5, beta1=0.9, beta2=0.999, eps=1e-8, views=None):
-    """EXPERIMENTAL two-shot form of norm_clip_adam_peers (rlppo_norm_clip_adam_peers2); the summed gradient ends up in
+    """Two-shot form of norm_clip_adam_peers (rlppo_norm_clip_adam_peers2); the summed gradient ends up in
     this rank's reduced buffer (peer_red_ptrs[rank])."""
     so = _seg(seg_off)
     ws = _nca_ws.get(params.device)

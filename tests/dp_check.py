@@ -58,8 +58,8 @@ def main():
     alone1 = learner1(solo)
     r_11 = alone1.learn(make_buffer(7, B, dev))
     g_errs = {}
-    # RLPPO_TEST_P2P2=1 adds the experimental two-shot exchange (rlppo_norm_clip_adam_peers2) to the comparison
-    for collective in ("p2p", "nccl") + (("p2p2",) if os.environ.get("RLPPO_TEST_P2P2") == "1" else ()):
+    # "p2p2" = the two-shot exchange (rlppo_norm_clip_adam_peers2), the default for big arenas
+    for collective in ("p2p", "nccl", "p2p2"):
         dp1 = learner1(None, collective)
         assert dp1.dp_collective == collective and alone1.dp_collective == "none"
         r_dp1 = dp1.learn(make_buffer(7, B, dev))

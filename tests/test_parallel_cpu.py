@@ -83,13 +83,13 @@ def test_choose_collective():
     small, big = 332_635, 15_150_171                      # parameter counts of the 256x3 and the 2048-2048-1024-1024 nets
     assert parallel.choose_collective(1, small) == "none"
     assert [parallel.choose_collective(r, small) for r in (2, 4, 8)] == ["p2p"] * 3      # 9.3 MB of peer reads at 8 ranks
-    assert [parallel.choose_collective(r, big) for r in (2, 4, 8)] == ["nccl"] * 3       # 60 MB arena: ring all-reduce
+    assert [parallel.choose_collective(r, big) for r in (2, 4, 8)] == ["p2p2"] * 3       # 60 MB arena: two-shot peer exchange
     assert parallel.choose_collective(8, big, requested="p2p") == "p2p"                  # explicit request wins
     assert parallel.choose_collective(2, small, env="nccl") == "nccl"
     assert parallel.choose_collective(2, small, requested="p2p", env="nccl") == "p2p"
     assert parallel.choose_collective(16, small, requested="p2p") == "nccl"              # peer mappings stop at the box
-    assert parallel.choose_collective(8, big, requested="p2p2") == "p2p2"                # experimental two-shot: opt-in only
-    assert "p2p2" not in {parallel.choose_collective(r, n) for r in (2, 4, 8) for n in (small, big)}
+    assert parallel.choose_collective(8, big, requested="nccl") == "nccl"
+    assert parallel.choose_collective(16, big) == "nccl"                                 # no peer mappings across boxes
     import pytest
     with pytest.raises(ValueError):
         parallel.choose_collective(2, small, requested="ring")
