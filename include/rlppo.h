@@ -171,6 +171,7 @@ typedef struct rlppo_wgrad_item {
     int64_t lddw;
     int64_t M;
     int32_t N, K;
+    float* db;              /* optional f32 [N], accumulated: column sums of dy (the Linear's bias gradient) */
 } rlppo_wgrad_item;
 int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream);
 

@@ -401,7 +401,7 @@ def mlp_backward(params, acts, dout, quant=None):
     for i in range(nl - 1, -1, -1):
         gq = q(g)
         grads[2 * i] = gq.t() @ q(acts[i])
-        grads[2 * i + 1] = g.sum(0)
+        grads[2 * i + 1] = gq.sum(0)   # quant: the kernels sum the rounded tile the weight-gradient GEMM reads
         if i > 0:
             g = (gq @ q(params[2 * i])) * (acts[i] > 0).to(g.dtype)  # acts[i] = relu output of layer i-1
     return grads

@@ -101,7 +101,7 @@ class Split(ctypes.Structure):
 class WgradItem(ctypes.Structure):
     """struct rlppo_wgrad_item."""
     _fields_ = [("dy", _P), ("lddy", _L), ("x", _P), ("ldx", _L), ("dw", _P), ("lddw", _L), ("M", _L),
-                ("N", ctypes.c_int32), ("K", ctypes.c_int32)]
+                ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("db", _P)]
 
 
 class Bf16View(ctypes.Structure):

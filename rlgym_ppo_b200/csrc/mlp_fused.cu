@@ -173,11 +173,37 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
     return r;
 }
 
+// max(x, 0) of two floats -> packed bf16x2 in ONE instruction (F2FP.RELU: the ReLU costs nothing)
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // 32 floats -> 16 packed bf16x2 words
 __device__ __forceinline__ void pack32(const float (&v)[32], uint32_t (&w)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
 }
+__device__ __forceinline__ void pack32_relu(const float (&v)[32], uint32_t (&w)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = cvt_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+}
+// ReLU mask of 32 post-ReLU bf16 values (16 packed words, all halves >= +0) as ONE word, one instruction per element:
+// the high bytes (sign + exponent[7:1]) of four values are gathered with a byte permute, "+0x7F" carries a non-zero byte
+// into its top bit, and eight such groups are interleaved by shifting group q right by q.  Element 4q+e lands in bit
+// 8e + 7 - q (relu_mask_bit).  A value counts as positive when its exponent field is >= 2, i.e. h >= 2^-125: activations
+// below 2.4e-38 are treated as zero (the reference tests H > 0 on fp32; nothing in between survives bf16 anyway).
+__device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&w)[16]) {
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t t = __byte_perm(w[2 * q], w[2 * q + 1], 0x7531) + 0x7F7F7F7Fu;
+        m[q & 3] |= (t >> q) & (0x80808080u >> q);
+    }
+    return (m[0] | m[1]) | (m[2] | m[3]);
+}
+__device__ __forceinline__ constexpr int relu_mask_bit(int i) { return 8 * (i & 3) + 7 - (i >> 2); }
 // 32 consecutive columns [32*chunk32, +32) of one row into a K-major SWIZZLE_128B activation tile
 __device__ __forceinline__ void sts_chunk_sw128(uint8_t* buf, int row, int chunk32, const uint32_t (&w)[16]) {
     uint8_t* kb = buf + (chunk32 >> 1) * KB_BYTES + row * 128;
@@ -200,6 +226,16 @@ __device__ __forceinline__ void sts_chunk16_sw128(uint8_t* buf, int row, int chu
         const int _i = (idx);                                                                   \
         if (p.trace != nullptr && blockIdx.x == 0 && _i < 512) p.trace[(role) * 512 + _i] = clock64(); \
     } while (0)
+
+// -DRLPPO_FINE_TRACE (experiments): clock stamps inside the epilogue loops of CTA 0's first tile, epilogue warp 2
+#ifdef RLPPO_FINE_TRACE
+#define EPI_T()                                                                                  \
+    do {                                                                                         \
+        if (p.trace != nullptr && blockIdx.x == 0 && it == 0 && warp == 2 && lane == 0 && tr5 < 500) p.trace[5 * 512 + tr5++] = clock64(); \
+    } while (0)
+#else
+#define EPI_T() do { } while (0)
+#endif
 
 struct EpiCtx {
     uint8_t* act;
@@ -241,6 +277,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef RLPPO_FINE_TRACE
+#define STAMP(slot) do { if (p.trace != nullptr && blockIdx.x == 0) p.trace[5 * 512 + (slot)] = clock64(); } while (0)
+#else
+#define STAMP(slot) do { } while (0)
+#endif
+    if (threadIdx.x == 0) STAMP(500);
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&maps.x);
         for (int i = 0; i < MAX_NWST; ++i) {
@@ -264,7 +306,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             if (c < p.H[l]) b = __ldg(p.bias[l] + c);
         } else if (l == MAXL) {
             if (POLICY) {
-                if (c < p.n_actions && p.bias[MAXL] != nullptr) b = __ldg(p.bias[MAXL] + c);
+                // padding columns of the logits: a large negative bias, so exp() of them is exactly 0
+                b = c < p.n_actions ? (p.bias[MAXL] != nullptr ? __ldg(p.bias[MAXL] + c) : 0.f) : -1e30f;
             } else {
                 if (c < p.H[p.L - 1]) b = __ldg(p.w_head + c);
             }
@@ -276,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) STAMP(501);
     // tiles of this CTA: blockIdx.x + k * gridDim.x
     const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -327,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                                 if (kb == 0) {
                                     mbar_wait(x_full, it & 1);
                                     tc_fence_after();
+                                    if (it == 0) STAMP(502);
                                 }
                                 a_addr = smem_u32(xst + kb * KB_BYTES);
                             } else {
@@ -447,6 +492,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             }
         };
         int tr1 = 0;
+        int tr5 = 0;
+        (void)tr5;
         for (int it = 0; it < my_tiles; ++it) {
           const int tile = blockIdx.x + it * gridDim.x;
           const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
@@ -479,46 +526,48 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     for (int j = 0; j < nkb; ++j) {
                         const int c = 2 * j + e.half;
                         float v[32];
+                        EPI_T();
                         tmem_ld32_wait(rb);
+                        EPI_T();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
                         if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);   // next chunk in flight during this one
                         // biases as 8 x 128-bit shared loads (one wavefront each; the MMA's operand fetch owns most of the
-                        // shared-memory bandwidth while this runs)
+                        // shared-memory bandwidth while this runs); bias add in fp32, ReLU inside the bf16 pack
                         const float4* sb4 = reinterpret_cast<const float4*>(s_bias + li * 256 + c * 32);
-                        uint32_t bq[4] = {0u, 0u, 0u, 0u};   // four independent OR chains (one 32-long chain serialises)
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 b4 = sb4[q];
-                            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = q * 4 + u;
-                                const float xv = fmaxf(v[i] + bb[u], 0.f);
-                                bq[u] |= (xv > 0.f ? 1u : 0u) << i;
-                                v[i] = xv;
-                            }
+                            v[q * 4 + 0] += b4.x;
+                            v[q * 4 + 1] += b4.y;
+                            v[q * 4 + 2] += b4.z;
+                            v[q * 4 + 3] += b4.w;
                         }
-                        if (TRAIN) e.s_mask[(li * 4 + j) * kEpiThreads] = (bq[0] | bq[1]) | (bq[2] | bq[3]);
+                        uint32_t w[16];
+                        pack32_relu(v, w);
+                        if (TRAIN) e.s_mask[(li * 4 + j) * kEpiThreads] = relu_mask32(w);
                         if (tail) {
+                            // value head dot product on the bf16-rounded activations (what a GEMM would read)
                             const float4* wv4 = reinterpret_cast<const float4*>(s_bias + MAXL * 256 + c * 32);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 const float4 w4 = wv4[q];
-                                dq[0] = fmaf(bf16_round(v[q * 4 + 0]), w4.x, dq[0]);
-                                dq[1] = fmaf(bf16_round(v[q * 4 + 1]), w4.y, dq[1]);
-                                dq[2] = fmaf(bf16_round(v[q * 4 + 2]), w4.z, dq[2]);
-                                dq[3] = fmaf(bf16_round(v[q * 4 + 3]), w4.w, dq[3]);
+                                dq[0] = fmaf(__uint_as_float(w[2 * q] << 16), w4.x, dq[0]);
+                                dq[1] = fmaf(__uint_as_float(w[2 * q] & 0xFFFF0000u), w4.y, dq[1]);
+                                dq[2] = fmaf(__uint_as_float(w[2 * q + 1] << 16), w4.z, dq[2]);
+                                dq[3] = fmaf(__uint_as_float(w[2 * q + 1] & 0xFFFF0000u), w4.w, dq[3]);
                             }
                         }
+                        EPI_T();
                         if (d.smem) {
-                            uint32_t w[16];
-                            pack32(v, w);
                             if (TRAIN) wait_store(j);
+                            EPI_T();
                             sts_chunk_sw128(dst, e.row_in_tile, c, w);
                         }
+                        EPI_T();
                         if (!tail) {
                             release_kb(e, j);
+                            EPI_T();
                             if (TRAIN && d.out != NO_STORE) pend |= 1u << j;
                         }
                     }
@@ -548,8 +597,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         for (int j = 0; j < nkb; ++j) release_kb(e, j);
                     }
                 } else if (d.kind == PH_VALUE_BWD) {
-                    // dL/dH_L = dv * w (.) relu'(H_L), dw_head += dv * H_L, db_L: re-reads the accumulator of the last
-                    // forward GEMM, which is still in TMEM
+                    // dL/dH_L = dv * w (.) relu'(H_L), dw_head += dv * H_L: re-reads the accumulator of the last forward
+                    // GEMM, which is still in TMEM; the ReLU mask is the one the forward epilogue kept
                     const int nkb = d.N >> 6;
                     const float dv = dv_keep;
 #pragma unroll 1
@@ -557,18 +606,58 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         const int c = 2 * j + e.half;
                         float v[32], t[32];
                         tmem_ld32(trow + c * 32, v);
-                        const float* sb = s_bias + li * 256 + c * 32;
-                        const float* wv = s_bias + MAXL * 256 + c * 32;
+                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias + li * 256 + c * 32);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float h = bf16_round(fmaxf(v[i] + sb[i], 0.f));
-                            t[i] = dv * h;
-                            v[i] = h > 0.f ? dv * wv[i] : 0.f;
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b4 = sb4[q];
+                            v[q * 4 + 0] += b4.x;
+                            v[q * 4 + 1] += b4.y;
+                            v[q * 4 + 2] += b4.z;
+                            v[q * 4 + 3] += b4.w;
+                        }
+                        uint32_t w[16];
+                        pack32_relu(v, w);                               // H_L as the forward pass rounded it
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            t[2 * i] = dv * __uint_as_float(w[i] << 16);
+                            t[2 * i + 1] = dv * __uint_as_float(w[i] & 0xFFFF0000u);
                         }
                         db_add(MAXL, c, warp_colsum32(t, e.lane));     // value head weight gradient (slot MAXL)
+                        const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
+                        const float4* wv4 = reinterpret_cast<const float4*>(s_bias + MAXL * 256 + c * 32);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) t[i] = v[i];
-                        db_add(li, c, warp_colsum32(t, e.lane));
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 w4 = wv4[q];
+                            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = q * 4 + u;
+                                v[i] = ((bits >> relu_mask_bit(i)) & 1u) ? dv * ww[u] : 0.f;
+                            }
+                        }
+                        if (d.smem) {
+                            pack32(v, w);
+                            if (TRAIN) wait_store(j);
+                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
+                        }
+                        release_kb(e, j);
+                        if (d.out != NO_STORE) pend |= 1u << j;
+                    }
+                } else if (d.kind == PH_DGRAD) {
+                    // dL/dH_l = (dL/dH_{l+1} W_{l+1}) (.) relu'(H_l).  The bias gradients (column sums of this tile) are
+                    // formed by the weight-gradient kernel from the bf16 tile it reads anyway (rlppo_wgrad_multi)
+                    const int nkb = d.N >> 6;
+                    uint32_t rb[32];
+                    tmem_ld32_issue(trow + e.half * 32, rb);
+#pragma unroll 1
+                    for (int j = 0; j < nkb; ++j) {
+                        const int c = 2 * j + e.half;
+                        float v[32];
+                        tmem_ld32_wait(rb);
+                        const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = ((bits >> relu_mask_bit(i)) & 1u) ? __uint_as_float(rb[i]) : 0.f;
+                        if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);
                         if (d.smem) {
                             uint32_t w[16];
                             pack32(v, w);
@@ -578,130 +667,94 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         release_kb(e, j);
                         if (d.out != NO_STORE) pend |= 1u << j;
                     }
-                } else if (d.kind == PH_DGRAD) {
-                    const int nkb = d.N >> 6;
-                    uint32_t rb[32];
-                    tmem_ld32_issue(trow + e.half * 32, rb);
-#pragma unroll 1
-                    for (int j = 0; j < nkb; ++j) {
-                        const int c = 2 * j + e.half;
-                        float v[32], t[32];
-                        tmem_ld32_wait(rb);
-                        const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            v[i] = ((bits >> i) & 1u) ? __uint_as_float(rb[i]) : 0.f;
-                            t[i] = v[i];
-                        }
-                        if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);
-                        if (d.smem) {
-                            uint32_t w[16];
-                            pack32(v, w);
-                            if (TRAIN) wait_store(j);
-                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
-                        }
-                        release_kb(e, j);                                // the next GEMM starts; the column sums follow
-                        if (d.out != NO_STORE) pend |= 1u << j;
-                        db_add(li, c, warp_colsum32(t, e.lane));
-                    }
                 } else {
                 // ---- policy head (discrete_policy.py:44-80, ppo_learner.py:153-177) ----
                 // Two threads per row: the warp pair that owns the row's TMEM lanes splits every 32-column chunk into
                 // its lower / upper 16 columns; the row-wise quantities (max, sum-exp, ...) are combined through shared
-                // memory.  Three branch-free passes re-read the logits from TMEM.  (History, from the cycle trace of this
-                // kernel: one thread per row with a data-dependent `if` per element: 42k cycles per tile; branch-free,
-                // 3 passes: 15.6k; the other epilogues take ~3k.)
+                // memory behind a 64-thread named barrier per warp pair.  Three branch-free passes re-read the logits from
+                // TMEM.  The bias slots of the padding columns hold -1e30, so a padding column's exp() is 0 and its
+                // d(logit) is 0 without a bounds test per element.
                 const int nact = p.n_actions;
                 const int nch = (nact + 31) >> 5;          // <= 4
-                const int nch_out = p.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
                 const int hoff = e.half * 16;              // this thread's 16 columns inside each chunk
                 const float* sb = s_bias + MAXL * 256;
                 const float kLogMin = -25.328436022934504f;   // ln(1e-11)
                 float* xch = e.s_rowx;                        // exchange planes: [0,256) max, [512,768) argmax, [1024,1792) S/T/z_a
-                int a = 0;
-                float old_lp = 0.f, advv = 0.f;
-                if (TRAIN && row_ok) {
-                    a = (int)__ldg(p.actions + row);             // acts.long(), discrete_policy.py:71
-                    a = min(max(a, 0), nact - 1);
-                    old_lp = __ldg(p.old_logp + row);
-                    advv = __ldg(p.adv + row);
-                }
-                // pass 1: row maximum (+ argmax for the deterministic branch)
-                float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                int aq[4] = {0, 0, 0, 0};
-#pragma unroll 1
-                for (int c = 0; c < nch; ++c) {
-                    float v[16];
-                    tmem_ld16(trow + c * 32 + hoff, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int col = c * 32 + hoff + i;
-                        const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
-                        const bool gt = zz > mq[i & 3];
-                        mq[i & 3] = gt ? zz : mq[i & 3];
-                        aq[i & 3] = gt ? col : aq[i & 3];
-                    }
-                }
-                float mx = mq[0];
-                int argmax = aq[0];
-#pragma unroll
-                for (int q = 1; q < 4; ++q) {
-                    const bool better = mq[q] > mx || (mq[q] == mx && aq[q] < argmax);   // ties: lowest column
-                    mx = better ? mq[q] : mx;
-                    argmax = better ? aq[q] : argmax;
-                }
-                xch[e.half * 128 + e.row_in_tile] = mx;
-                int* xchi = reinterpret_cast<int*>(xch) + 512;   // second plane: argmax (ints), see OFF_ROWX sizing
-                xchi[e.half * 128 + e.row_in_tile] = argmax;
-                epi_bar_sync();
-                {
-                    const float mo = xch[(e.half ^ 1) * 128 + e.row_in_tile];
-                    const int ao = xchi[(e.half ^ 1) * 128 + e.row_in_tile];
-                    const bool better = mo > mx || (mo == mx && ao < argmax);
-                    mx = better ? mo : mx;
-                    argmax = better ? ao : argmax;
-                }
-                epi_bar_sync();   // everyone has read the maxima before the plane is reused
-                // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
-                float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
-                float zs_a = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < nch; ++c) {
-                    float v[16];
-                    tmem_ld16(trow + c * 32 + hoff, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int col = c * 32 + hoff + i;
-                        const float zs = col < nact ? v[i] + sb[col] - mx : -INFINITY;
-                        const float ej = __expf(zs);                      // exp(-inf) = 0 for the padding
-                        Sq[i & 3] += ej;
-                        Tq[i & 3] = fmaf(ej, col < nact ? zs : 0.f, Tq[i & 3]);
-                        zs_a += col == a ? zs : 0.f;                      // exactly one of the two threads holds column a
-                    }
-                }
-                float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
-                float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
-                {
-                    float* x3 = xch + 1024;   // [3][half][row]
-                    x3[0 * 256 + e.half * 128 + e.row_in_tile] = S;
-                    x3[1 * 256 + e.half * 128 + e.row_in_tile] = T;
-                    x3[2 * 256 + e.half * 128 + e.row_in_tile] = zs_a;
-                    epi_bar_sync();
-                    const int o = (e.half ^ 1) * 128 + e.row_in_tile;
-                    // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
-                    const float S0 = e.half == 0 ? S : x3[o], S1 = e.half == 0 ? x3[o] : S;
-                    const float T0 = e.half == 0 ? T : x3[256 + o], T1 = e.half == 0 ? x3[256 + o] : T;
-                    S = S0 + S1;
-                    T = T0 + T1;
-                    zs_a += x3[512 + o];
-                }
-                const float logS = logf(S);
-                const float mxs = mx + logS;
                 if (TRAIN) {
+                    const int nch_out = p.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
+                    const int prow = e.half * 128 + e.row_in_tile, orow = (e.half ^ 1) * 128 + e.row_in_tile;
+                    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + e.quarter) : "memory"); };
+                    int a = 0;
+                    float old_lp = 0.f, advv = 0.f;
+                    if (row_ok) {
+                        a = (int)__ldg(p.actions + row);             // acts.long(), discrete_policy.py:71
+                        a = min(max(a, 0), nact - 1);
+                        old_lp = __ldg(p.old_logp + row);
+                        advv = __ldg(p.adv + row);
+                    }
+                    // pass 1: row maximum
+                    float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+                    for (int c = 0; c < nch; ++c) {
+                        float v[16];
+                        tmem_ld16(trow + c * 32 + hoff, v);
+                        const float4* b4p = reinterpret_cast<const float4*>(sb + c * 32 + hoff);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b4 = b4p[q];
+                            mq[0] = fmaxf(mq[0], v[4 * q + 0] + b4.x);
+                            mq[1] = fmaxf(mq[1], v[4 * q + 1] + b4.y);
+                            mq[2] = fmaxf(mq[2], v[4 * q + 2] + b4.z);
+                            mq[3] = fmaxf(mq[3], v[4 * q + 3] + b4.w);
+                        }
+                    }
+                    float mx = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+                    xch[prow] = mx;
+                    pair_sync();
+                    mx = fmaxf(mx, xch[orow]);
+                    // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
+                    float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
+                    float zs_a = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < nch; ++c) {
+                        float v[16];
+                        tmem_ld16(trow + c * 32 + hoff, v);
+                        const float4* b4p = reinterpret_cast<const float4*>(sb + c * 32 + hoff);
+                        const int arel = a - (c * 32 + hoff);             // this row's action column relative to the chunk
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b4 = b4p[q];
+                            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = 4 * q + u;
+                                const float zs = (v[i] + bb[u]) - mx;
+                                const float ej = __expf(zs);              // 0 for the padding (zs ~ -1e30)
+                                Sq[u] += ej;
+                                Tq[u] = fmaf(ej, zs, Tq[u]);
+                                if (i == arel) zs_a = zs;                 // exactly one of the two threads holds column a
+                            }
+                        }
+                    }
+                    float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
+                    float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
+                    {
+                        float* x3 = xch + 1024;   // [3][half][row]
+                        x3[prow] = S;
+                        x3[256 + prow] = T;
+                        x3[512 + prow] = zs_a;
+                        pair_sync();
+                        // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
+                        const float So = x3[orow], To = x3[256 + orow];
+                        S = e.half == 0 ? S + So : So + S;
+                        T = e.half == 0 ? T + To : To + T;
+                        zs_a += x3[512 + orow];
+                    }
+                    const float logS = logf(S);
+                    const float mxs = mx + logS;
                     // Entropy of the CLAMPED probabilities (discrete_policy.py:74-78) from the two sums:
                     //   -sum s_j log s_j = logS - T/S.  Clamping to [1e-11, 1] changes each term by at most
-                    //   1e-11 * ln(1e11) = 2.5e-10, i.e. below fp32 resolution of the sum; the clamp's effect on the
-                    //   GRADIENT (zero outside the range) is applied exactly in pass 3.
+                    //   1e-11 * ln(1e11) = 2.5e-10, i.e. below fp32 resolution of the sum.
                     const float Hent = logS - T / S;
                     const float Gs = 1.0f - Hent;                       // sum_j s_j (log s_j + 1)
                     const float ls_a = zs_a - logS;
@@ -729,40 +782,119 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         mrows += 1.f;
                         if (p.logp_out) p.logp_out[row] = lp_a;
                     }
-                    // pass 3: dz_j = s_j (g_j - G) -> bf16 tile (A operand of the first dgrad GEMM) + head bias grads
+                    // pass 3: dz_j = s_j (g_j - G), g_j = cw (log s_j + 1) + [j = a] ga  -> bf16 tile (A operand of the
+                    // first dgrad GEMM and of the head's weight-gradient GEMM, which also forms the head's bias gradient).
+                    // The reference's clamp stops the entropy term's gradient where s_j < 1e-11; that term is then below
+                    // 1e-11 * 25 * cw and is kept (|difference| < 2.5e-10 * ent_coef / B per logit).
+                    const float cwG = cw - G;
 #pragma unroll 1
                     for (int c = 0; c < nch_out; ++c) {
-                        float v[16], t[16];
+                        float v[16];
                         if (c < nch) {
                             tmem_ld16(trow + c * 32 + hoff, v);
+                            const float4* b4p = reinterpret_cast<const float4*>(sb + c * 32 + hoff);
+                            const int arel = a - (c * 32 + hoff);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 b4 = b4p[q];
+                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int i = 4 * q + u;
+                                    const float ls = (v[i] + bb[u]) - mxs;          // log softmax (<= 0); ~ -1e30 for the padding
+                                    const float sj = __expf(ls);
+                                    float o = sj * fmaf(cw, fmaxf(ls, kLogMin), cwG);
+                                    if (i == arel) o = fmaf(sj, ga, o);
+                                    v[i] = o;
+                                }
+                            }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = 0.f;
                         }
+                        uint32_t w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) w[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
+                        wait_store(c >> 1);
+                        sts_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, w);
+                    }
+                    for (int j = 0; j < p.out_kb; ++j) {
+                        release_kb(e, j);
+                        if (d.out != NO_STORE) pend |= 1u << j;
+                    }
+                } else {
+                    // pass 1: row maximum (+ argmax for the deterministic branch)
+                    const int a = -1;
+                    float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    int aq[4] = {0, 0, 0, 0};
+#pragma unroll 1
+                    for (int c = 0; c < nch; ++c) {
+                        float v[16];
+                        tmem_ld16(trow + c * 32 + hoff, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int col = c * 32 + hoff + i;
-                            const bool in = col < nact;
-                            const float ls = in ? v[i] + sb[col & 255] - mxs : -INFINITY;   // log softmax (<= 0)
-                            const float sj = __expf(ls);                                    // 0 for the padding
-                            const float lp = fminf(fmaxf(ls, kLogMin), 0.f);
-                            float gj = fmaf(cw, lp + 1.0f, col == a ? ga : 0.f);
-                            gj = ls >= kLogMin ? gj : 0.f;          // clamp passes gradient inside [1e-11, 1] only
-                            const float o = in ? sj * (gj - G) : 0.f;
-                            v[i] = o;
-                            t[i] = o;
-                        }
-                        const float cs = warp_colsum16(t, e.lane);
-                        if (e.lane < 16) atomicAdd(&s_db[MAXL * 256 + c * 32 + hoff + e.lane], cs);
-                        {
-                            uint32_t w[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) w[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
-                            wait_store(c >> 1);
-                            sts_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, w);
+                            const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
+                            const bool gt = zz > mq[i & 3];
+                            mq[i & 3] = gt ? zz : mq[i & 3];
+                            aq[i & 3] = gt ? col : aq[i & 3];
                         }
                     }
-                } else {
+                    float mx = mq[0];
+                    int argmax = aq[0];
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) {
+                        const bool better = mq[q] > mx || (mq[q] == mx && aq[q] < argmax);   // ties: lowest column
+                        mx = better ? mq[q] : mx;
+                        argmax = better ? aq[q] : argmax;
+                    }
+                    xch[e.half * 128 + e.row_in_tile] = mx;
+                    int* xchi = reinterpret_cast<int*>(xch) + 512;   // second plane: argmax (ints), see OFF_ROWX sizing
+                    xchi[e.half * 128 + e.row_in_tile] = argmax;
+                    epi_bar_sync();
+                    {
+                        const float mo = xch[(e.half ^ 1) * 128 + e.row_in_tile];
+                        const int ao = xchi[(e.half ^ 1) * 128 + e.row_in_tile];
+                        const bool better = mo > mx || (mo == mx && ao < argmax);
+                        mx = better ? mo : mx;
+                        argmax = better ? ao : argmax;
+                    }
+                    epi_bar_sync();   // everyone has read the maxima before the plane is reused
+                    // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
+                    float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
+                    float zs_a = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < nch; ++c) {
+                        float v[16];
+                        tmem_ld16(trow + c * 32 + hoff, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int col = c * 32 + hoff + i;
+                            const float zs = col < nact ? v[i] + sb[col] - mx : -INFINITY;
+                            const float ej = __expf(zs);                      // exp(-inf) = 0 for the padding
+                            Sq[i & 3] += ej;
+                            Tq[i & 3] = fmaf(ej, col < nact ? zs : 0.f, Tq[i & 3]);
+                            zs_a += col == a ? zs : 0.f;                      // exactly one of the two threads holds column a
+                        }
+                    }
+                    float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
+                    float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
+                    {
+                        float* x3 = xch + 1024;   // [3][half][row]
+                        x3[0 * 256 + e.half * 128 + e.row_in_tile] = S;
+                        x3[1 * 256 + e.half * 128 + e.row_in_tile] = T;
+                        x3[2 * 256 + e.half * 128 + e.row_in_tile] = zs_a;
+                        epi_bar_sync();
+                        const int o = (e.half ^ 1) * 128 + e.row_in_tile;
+                        // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
+                        const float S0 = e.half == 0 ? S : x3[o], S1 = e.half == 0 ? x3[o] : S;
+                        const float T0 = e.half == 0 ? T : x3[256 + o], T1 = e.half == 0 ? x3[256 + o] : T;
+                        S = S0 + S1;
+                        T = T0 + T1;
+                        zs_a += x3[512 + o];
+                    }
+                    const float logS = logf(S);
+                    const float mxs = mx + logS;
                     // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62): the inverse-CDF scan is
                     // sequential over the row, so the lower-half thread does it alone over all columns ----
                     if (e.half == 0) {
@@ -826,12 +958,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         }
                     }
                 }
-                    if (TRAIN) {
-                        for (int j = 0; j < p.out_kb; ++j) {
-                            release_kb(e, j);
-                            if (d.out != NO_STORE) pend |= 1u << j;
-                        }
-                    }
                 }
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (tile, ph) done
           }
@@ -859,25 +985,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) STAMP(503);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
-    if (TRAIN) {
-        // flush the shared-memory column sums: bias gradients of every Linear, value-head weight gradient
-        for (int i = threadIdx.x; i < (MAXL + 1) * 256; i += kThreads) {
-            const int l = i >> 8, c = i & 255;
-            const float v = s_db[i];
-            if (l < p.L) {
-                if (c < p.H[l] && p.gbias[l] != nullptr) atomicAdd(p.gbias[l] + c, v);
-            } else if (l == MAXL) {
-                if (POLICY) {
-                    if (c < p.n_actions && p.gbias[MAXL] != nullptr) atomicAdd(p.gbias[MAXL] + c, v);
-                } else {
-                    if (c < p.H[p.L - 1]) atomicAdd(p.gw_head + c, v);
-                }
-            }
-        }
+    if (TRAIN && !POLICY) {
+        // flush the shared-memory column sums of the value head's weight gradient (slot MAXL); the bias gradients of every
+        // Linear are column sums of tiles the weight-gradient kernel reads anyway and are formed there (rlppo_wgrad_multi)
+        for (int c = threadIdx.x; c < p.H[p.L - 1]; c += kThreads) atomicAdd(p.gw_head + c, s_db[MAXL * 256 + c]);
     }
 }
 
@@ -1026,14 +1142,14 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     const bool tracing = getenv("RLPPO_FUSED_TRACE") != nullptr && TRAIN && POLICY;
     p.dbg_nostore = getenv("RLPPO_FUSED_NOSTORE") != nullptr ? 1 : 0;
     if (tracing) {
-        if (d_trace == nullptr) RLPPO_CUDA(cudaMalloc(&d_trace, 2560 * sizeof(unsigned long long)));
-        RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 2560 * sizeof(unsigned long long), s));
+        if (d_trace == nullptr) RLPPO_CUDA(cudaMalloc(&d_trace, 3072 * sizeof(unsigned long long)));
+        RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 3072 * sizeof(unsigned long long), s));
         p.trace = d_trace;
     }
     kfn<<<grid, kThreads, smem_bytes, s>>>(maps, p);
     RLPPO_LAUNCH_CHECK();
     if (tracing) {
-        static unsigned long long h[2560];
+        static unsigned long long h[3072];
         RLPPO_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
         RLPPO_CUDA(cudaStreamSynchronize(s));
         const unsigned long long t0 = h[0];
@@ -1048,6 +1164,11 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
             fprintf(stderr, "  wload #%d issued=%llu\n", i, h[1536 + i] - t0);
         for (int i = 0; i < 512 && h[2048 + i] != 0; ++i)
             fprintf(stderr, "  wfull #%d at=%llu\n", i, h[2048 + i] - t0);
+        fprintf(stderr, "  stamps: entry=%lld prologue_done=%lld first_x=%lld exit=%lld (cycles rel. to first MMA start)\n",
+                (long long)(h[2560 + 500] - t0), (long long)(h[2560 + 501] - t0), (long long)(h[2560 + 502] - t0),
+                (long long)(h[2560 + 503] - t0));
+        for (int i = 0; i < 500 && h[2560 + i] != 0; ++i)
+            fprintf(stderr, "  fine #%d at=%llu (+%llu)\n", i, h[2560 + i] - t0, i ? h[2560 + i] - h[2560 + i - 1] : 0ull);
     }
     return RLPPO_OK;
 }

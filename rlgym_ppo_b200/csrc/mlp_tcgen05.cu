@@ -805,6 +805,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 // and dY [64 x <=256 n] ONCE and issues up to two M=128 MMAs (the two 128-row k tiles) against the same dY tile, so
 // dY is read once (the per-layer kernel above reads it once per k tile).  Row splits are sized from each layer's
 // byte volume so that the ~148 items finish together.  HBM-bound: reads dY and X exactly once.
+// Bias gradients ride along: while the MMA thread works on a stage, the four drain warps (idle until the item ends) add
+// the staged dY tile's columns into registers (warp w: 64-column chunk w, lane: one bf16x2 column pair, conflict-free
+// reads of the swizzled rows), so db_l = colsum(dY_l) costs no extra HBM traffic and no epilogue work in the fused
+// kernel that produced dY.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int MAXW = 8;
 struct alignas(64) WMaps {
@@ -813,6 +817,7 @@ struct alignas(64) WMaps {
 };
 struct WLayer {
     float* dw;
+    float* db;      // optional: += column sums of dY (bias gradient), formed by the drain warps from the staged dY tiles
     int64_t lddw, M, m_per_split;
     int N, K, n_tiles_n, n_kpairs, splits, first_item;
 };
@@ -820,6 +825,7 @@ struct WMultiParams {
     WLayer L[MAXW];
     int n_layers, total_items;
     int dbg_nodrain;   // debug (RLPPO_WGRAD_NODRAIN=1): timing experiment, the accumulators are NOT added to dW
+    int dbg_nomma;     // debug (RLPPO_WGRAD_NOMMA=1): timing experiment, stages are released without issuing MMAs
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -840,7 +846,7 @@ wgrad_multi_kernel(const __grid_constant__ WMaps maps, const WMultiParams p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], 1 + 4);      // the MMA commit + the four drain warps (column sums read the dY tile)
         }
         mbar_init(tfull, 1);
         mbar_init(tempty, 4);
@@ -913,7 +919,7 @@ wgrad_multi_kernel(const __grid_constant__ WMaps maps, const WMultiParams p) {
                     tc_fence_after();
                     const uint32_t x_addr = smem_u32(smem + stage * STAGE);
                     const uint32_t b_addr = x_addr + 4 * CHUNK;
-                    for (int kt = 0; kt < n_kt; ++kt) {
+                    for (int kt = 0; kt < (p.dbg_nomma ? 0 : n_kt); ++kt) {
 #pragma unroll
                         for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
                             const uint64_t ad = umma_smem_desc(x_addr + kt * 2 * CHUNK + ks * (UMMA_K * 128), CHUNK, 1024);
@@ -933,11 +939,41 @@ wgrad_multi_kernel(const __grid_constant__ WMaps maps, const WMultiParams p) {
         }
     } else {
         const int ew = warp & 3;
-        uint32_t n_done = 0;
+        uint32_t n_done = 0, stage = 0, phase = 0;
         for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
             const Item it = decode(w);
             if (it.nkb == 0) continue;
             const WLayer& L = p.L[it.layer];
+            // ---- column sums of the staged dY tiles (bias gradient), one stage behind the TMA like the MMA thread ----
+            const bool want_db = L.db != nullptr && it.k0 == 0 && ew < it.n_y;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int kb = 0; kb < it.nkb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                if (want_db) {
+                    const uint8_t* tile = smem + stage * STAGE + (4 + ew) * CHUNK;
+                    const uint32_t sub = (uint32_t)(lane & 3) * 4u, c16 = (uint32_t)lane >> 2;
+#pragma unroll 8
+                    for (int r = 0; r < BLOCK_K; r += 2) {
+                        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(tile + r * 128 + ((c16 ^ (uint32_t)(r & 7)) << 4) + sub);
+                        const uint32_t w1 = *reinterpret_cast<const uint32_t*>(tile + (r + 1) * 128 + ((c16 ^ (uint32_t)((r + 1) & 7)) << 4) + sub);
+                        s0 += __uint_as_float(w0 << 16);
+                        s1 += __uint_as_float(w0 & 0xFFFF0000u);
+                        s2 += __uint_as_float(w1 << 16);
+                        s3 += __uint_as_float(w1 & 0xFFFF0000u);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == NST) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (want_db && !p.dbg_nodrain) {
+                const int n = it.n0 + ew * 64 + 2 * lane;
+                if (n < L.N) atomicAdd(L.db + n, s0 + s2);
+                if (n + 1 < L.N) atomicAdd(L.db + n + 1, s1 + s3);
+            }
             mbar_wait(tfull, n_done & 1);
             tc_fence_after();
             const int n_kt = (it.n_x + 1) / 2;
@@ -1273,7 +1309,7 @@ int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream
         RLPPO_CHECK_ARG(it.dy && it.x && it.dw && it.M >= 1 && it.N >= 1 && it.K >= 1, "bad item %d", i);
         RLPPO_CHECK_ARG(it.M < (1ll << 31) && it.lddy % 8 == 0 && it.ldx % 8 == 0, "item %d: ld must be a multiple of 8", i);
         WLayer& L = p.L[i];
-        L.dw = it.dw; L.lddw = it.lddw; L.M = it.M; L.N = it.N; L.K = it.K;
+        L.dw = it.dw; L.db = it.db; L.lddw = it.lddw; L.M = it.M; L.N = it.N; L.K = it.K;
         L.n_tiles_n = (it.N + 255) / 256;
         L.n_kpairs = (it.K + 255) / 256;
         const uint64_t x_cols = (uint64_t)min((int64_t)((it.K + 7) / 8 * 8), it.ldx);
@@ -1303,6 +1339,8 @@ int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream
     p.total_items = first;
     static const bool nodrain = getenv("RLPPO_WGRAD_NODRAIN") != nullptr;
     p.dbg_nodrain = nodrain ? 1 : 0;
+    static const bool nomma = getenv("RLPPO_WGRAD_NOMMA") != nullptr;
+    p.dbg_nomma = nomma ? 1 : 0;
     constexpr uint32_t SMEM = 3 * 8 * 8192 + 256 + 1024;
     static bool configured = false;
     if (!configured) {

@@ -253,14 +253,18 @@ def linear_wgrad(dy, x, dw, db, N, K, M=None, split=None):
 
 
 def wgrad_multi(items, M):
-    """items: list of (dy, x, dw, N, K) -- all weight gradients of a step in one launch (<= 8 per call)."""
+    """items: list of (dy, x, dw, N, K[, db]) -- all weight gradients of a step in one launch (<= 8 per call); db (optional)
+    receives the column sums of dy, i.e. the Linear's bias gradient."""
     for i0 in range(0, len(items), 8):
         part = items[i0:i0 + 8]
         arr = (_lib.WgradItem * len(part))()
         flop = nbytes = 0.0
-        for a, (dy, x, dw, N, K) in zip(arr, part):
+        for a, item in zip(arr, part):
+            dy, x, dw, N, K = item[:5]
+            db = item[5] if len(item) > 5 else None
             a.dy, a.lddy, a.x, a.ldx = dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0)
             a.dw, a.lddw, a.M, a.N, a.K = dw.data_ptr(), dw.stride(0), int(M), int(N), int(K)
+            a.db = db.data_ptr() if db is not None else None
             flop += 2.0 * M * N * K
             nbytes += 2.0 * M * (dy.stride(0) + x.stride(0)) + 4.0 * N * K     # both bf16 operands read once, dW written
         call("rlppo_wgrad_multi", ctypes.cast(arr, ctypes.c_void_p), len(part), stream_ptr(),

@@ -190,16 +190,17 @@ class Stack:
         return net
 
     def fused_wgrad_items(self, x, ws, head_dy=None):
-        """(dy, x, dW, N, K) per Linear after a fused training pass: dW_l += dH_l^T X_{l-1} (and the policy head's);
-        fed to ops.wgrad_multi (one launch for both nets)."""
+        """(dy, x, dW, N, K, db) per Linear after a fused training pass: dW_l += dH_l^T X_{l-1}, db_l += colsum(dH_l) (and
+        the policy head's); fed to ops.wgrad_multi.  The fused kernels leave every bias gradient to this launch (the value
+        head's scalar one excepted)."""
         L = len(self.hidden)
         items = []
         if head_dy is not None:
-            items.append((head_dy, ws["h"][L - 1], self.gw[L], self.out_dim, self.hidden[L - 1]))
+            items.append((head_dy, ws["h"][L - 1], self.gw[L], self.out_dim, self.hidden[L - 1], self.gb[L]))
         for i in range(L - 1, -1, -1):
             inp = ws["h"][i - 1] if i > 0 else x
             K = self.hidden[i - 1] if i > 0 else self.in_dim
-            items.append((ws["dh"][i], inp, self.gw[i], self.hidden[i], K))
+            items.append((ws["dh"][i], inp, self.gw[i], self.hidden[i], K, self.gb[i]))
         return items
 
     # ---- workspaces -------------------------------------------------------------------------------------

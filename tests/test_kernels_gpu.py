@@ -570,10 +570,12 @@ def test_weight_and_rows_to_bf16(ops):
 
 
 def test_wgrad_multi(ops):
-    """All weight gradients in one launch == the per-layer kernel == fp64 reference, incl. n/k tiling and row splits."""
+    """All weight gradients in one launch == the per-layer kernel == fp64 reference, incl. n/k tiling and row splits;
+    the optional db output (column sums of dY = bias gradient, formed from the staged tiles) against fp64 sums."""
     M = 7001
     shapes = [(256, 89, 96), (256, 256, 256), (90, 256, 256), (1024, 2048, 2048), (64, 64, 64), (8, 256, 256)]
     items, refs, outs = [], [], []
+    dbs, db_refs = [], []
     for i, (N, K, Kp) in enumerate(shapes):
         Np = (N + 7) // 8 * 8
         dy = torch.zeros(M, Np)
@@ -582,13 +584,19 @@ def test_wgrad_multi(ops):
         x[:, :K] = _mk((M, K), 60 + i)
         dw = torch.full((N, K), 0.25, device=DEV)
         dyd, xd = dev(dy, torch.bfloat16), dev(x, torch.bfloat16)
-        items.append((dyd, xd, dw, N, K))
+        db = torch.full((N,), -0.5, device=DEV) if i != 4 else None      # one item without a bias gradient
+        items.append((dyd, xd, dw, N, K, db))
         outs.append(dw)
+        dbs.append(db)
         refs.append((dy[:, :N].double().t() @ x[:, :K].double()).float() + 0.25)
+        db_refs.append((dyd[:, :N].double().sum(0) - 0.5).float().cpu())
     ops.wgrad_multi(items, M)
     torch.cuda.synchronize()
     for (N, K, _), got, want in zip(shapes, outs, refs):
         assert rel_l2(got.cpu(), want) < 1e-4, (N, K, rel_l2(got.cpu(), want))
+    for (N, K, _), got, want in zip(shapes, dbs, db_refs):
+        if got is not None:
+            assert (got.cpu() - want).abs().max() < 2e-4 * (1 + want.abs().max()), (N, K, (got.cpu() - want).abs().max())
     # more than 8 items are split over launches
     ops.wgrad_multi(items + items[:4], M)
     torch.cuda.synchronize()
