@@ -305,8 +305,9 @@ int rlppo_head_continuous_sample(const uint16_t* z, int64_t ldz, int z_parts, in
 /* ---- whole-network fused kernels (hidden widths 64/128/192/256, <= 4 hidden layers, obs <= 256, <= 128 actions) ----
  * One persistent tcgen05 kernel runs a 128-row tile of samples through the WHOLE Linear/ReLU stack, the head and
  * (training) the backward data path without leaving the SM: hidden activations live in shared memory as the next
- * GEMM's A operand, ReLU masks in registers, bias gradients in registers.  HBM sees x once, and (training) H_l,
- * d(logits) and dL/dH_l once each -- they are the operands of rlppo_linear_wgrad, which contracts over all rows.
+ * GEMM's A operand, ReLU masks as bit words in shared memory.  HBM sees x once, and (training) H_l, d(logits) and
+ * dL/dH_l once each -- they are the operands of rlppo_wgrad_multi, which contracts over all rows and also forms the
+ * bias gradients (column sums of the dL/dH_l tiles it stages; rlppo_wgrad_item.db).
  * Replaces the per-layer sequence rlppo_linear_fwd x L + head + rlppo_linear_dgrad x L for these shapes.
  * All pointers device; bf16 as uint16_t; l = 0..n_hidden-1 hidden Linear layers, index n_hidden = the head. */
 typedef struct rlppo_fused_net {
@@ -316,10 +317,11 @@ typedef struct rlppo_fused_net {
     int hidden[4];              /* hidden widths */
     const uint16_t* wq[5];      /* forward operands W_l bf16 [out_pad8, ld]; [n_hidden] = policy head (NULL for value) */
     int64_t wq_ld[5];
-    const uint16_t* wt[5];      /* dgrad operands W_l^T bf16 [in_pad8, ld]; [0] unused; training only */
+    const uint16_t* wt[5];      /* unused (kept for layout): the backward data GEMMs read wq[l] as an MN-major operand */
     int64_t wt_ld[5];
     const float* bias[5];       /* f32 biases; [n_hidden] = head bias (policy: n_actions, value: 1) */
-    float* gbias[5];            /* f32 bias gradients, accumulated (training) */
+    float* gbias[5];            /* only [n_hidden] of the value net (its head's scalar bias gradient) is written here;
+                                   every other bias gradient comes from rlppo_wgrad_multi (item.db) */
     uint16_t* h[4];             /* out (training): H_l bf16 [M, hidden_l], ld h_ld */
     int64_t h_ld[4];
     uint16_t* dh[4];            /* out (training): dL/dH_l (ReLU-masked) bf16 [M, hidden_l] */
@@ -329,8 +331,8 @@ typedef struct rlppo_fused_net {
 } rlppo_fused_net;
 
 /* DiscreteFF.get_backprop_data + PPO loss + backward data path (discrete_policy.py:64-80, ppo_learner.py:153-180,
- * SURVEY.md A.3).  metrics as rlppo_policy_head_train.  Weight gradients: rlppo_linear_wgrad on (dz, H_L),
- * (dh[l], H_{l-1}), (dh[0], x); bias gradients are accumulated here. */
+ * SURVEY.md A.3).  metrics as rlppo_policy_head_train.  Weight and bias gradients: rlppo_wgrad_multi on (dz, H_L),
+ * (dh[l], H_{l-1}), (dh[0], x) with item.db set. */
 int rlppo_policy_train_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, int n_actions,
                              const float* actions, const float* old_logp, const float* adv, float inv_batch,
                              float clip, float ent_coef, float* logp_out, float* metrics, void* stream);

@@ -1,5 +1,7 @@
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rlppo {
@@ -40,6 +42,15 @@ int check_device() {
         return RLPPO_ERR_DEVICE;
     }
     return RLPPO_OK;
+}
+
+int pdl_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("RLPPO_PDL");
+        mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return mode;
 }
 
 int num_sms() {

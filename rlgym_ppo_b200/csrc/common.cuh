@@ -40,6 +40,31 @@ int num_sms();
 
 #define RLPPO_LAUNCH_CHECK() RLPPO_CUDA(cudaGetLastError())
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// Kernels of the update chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs
+// may be scheduled while this one drains, run their prologue (barrier init, TMEM allocation, tensor-map prefetch) and
+// then block in pdl_wait() until the previous grid has completed and its writes are visible.  A kernel launched without
+// the attribute treats both instructions as no-ops.  pdl_trigger() early in a kernel whose CTAs are all resident lets the
+// dependent grid be scheduled as soon as SMs free up instead of when the last CTA exits.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int pdl_mode();   // 0 off, 1 on (RLPPO_PDL), cached
+
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_mode() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ int ld_acquire_s32(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -45,6 +45,7 @@ constexpr int KBLK = 64;
 constexpr uint32_t KB_BYTES = TILE_M * KBLK * 2;   // 16 KB: one 64-column k-block of an activation tile
 constexpr uint32_t ACT_BYTES = 4 * KB_BYTES;       // 64 KB
 constexpr uint32_t WST_BYTES = 256 * KBLK * 2;     // 32 KB: one k-block of a weight operand (<= 256 rows)
+constexpr uint32_t MN_CHUNK = 64 * KBLK * 2;       // 8 KB: 64 k-rows x 64 n-columns of an MN-major weight operand
 constexpr int MAX_NWST = 3;
 constexpr int kThreads = 352;
 constexpr int kEpiThreads = 256;
@@ -75,6 +76,8 @@ struct PhaseDesc {
     uint8_t smem;       // 1: the epilogue writes the activation tile (it is the next GEMM's A operand)
     uint8_t wait_kb;    // GEMM-less phase: k-blocks released by the previous epilogue (consumed for barrier parity)
     uint8_t rel_kb;     // k-blocks this phase's epilogue releases (a_ready arrivals), = k-blocks of its output tile
+    uint8_t b_mn;       // 1: the weight operand is MN-major (dgrad reads W [out, in] itself: k = out rows, n = in columns,
+                        // staged as N/64 chunks of 64 k-rows x 64 n-columns) -- no transposed copy of W exists
 };
 
 struct alignas(64) Maps {
@@ -298,6 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    // PDL: everything above ran while the previous kernel of the stream was still draining; its outputs (x, parameters)
+    // are read from here on.  All CTAs of this grid are resident, so the next kernel may be scheduled as SMs free up.
+    pdl_wait();
+    pdl_trigger();
     // biases (and the value head's weights) into shared memory: slot l < L hidden biases, slot MAXL the head
     for (int i = threadIdx.x; i < (MAXL + 1) * 256; i += kThreads) {
         const int l = i >> 8, c = i & 255;
@@ -340,7 +347,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         mbar_wait(&wempty[ws], wpar ^ 1);
                         mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
                         RLPPO_TRACE(3, tr3++);
-                        tma_load_2d(&maps.w[d.wmap], &wfull[ws], wring + ws * WST_BYTES, kb * KBLK, 0);
+                        if (d.b_mn) {
+                            for (int c = 0; c < (d.N >> 6); ++c)
+                                tma_load_2d(&maps.w[d.wmap], &wfull[ws], wring + ws * WST_BYTES + c * MN_CHUNK, c * 64, kb * KBLK);
+                        } else {
+                            tma_load_2d(&maps.w[d.wmap], &wfull[ws], wring + ws * WST_BYTES, kb * KBLK, 0);
+                        }
                         if (++ws == (uint32_t)p.nwst) {
                             ws = 0;
                             wpar ^= 1;
@@ -362,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 for (int ph = 0; ph < p.n_ph; ++ph) {
                     const PhaseDesc& d = p.ph[ph];
                     if (d.n_kb > 0) {
-                        const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, 0);
+                        const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, d.b_mn);
                         const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
                         RLPPO_TRACE(0, tr0++);   // MMA: start of (tile, ph)
                         for (int kb = 0; kb < d.n_kb; ++kb) {
@@ -387,7 +399,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 #pragma unroll
                             for (int k = 0; k < KBLK / 16; ++k) {
                                 const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-                                const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+                                const uint64_t bd = d.b_mn ? umma_smem_desc(b_addr + k * (16 * 128), MN_CHUNK, 1024)
+                                                           : umma_smem_desc(b_addr + k * 32, 16, 1024);
                                 umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
                             umma_commit(&wempty[ws]);
@@ -1054,7 +1067,8 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     const int head_N = POLICY ? (p.n_actions + 15) / 16 * 16 : 0;
     p.out_kb = POLICY ? (out_pad8 + KBLK - 1) / KBLK : 0;
     auto kb_of = [](int cols) { return (cols + KBLK - 1) / KBLK; };
-    auto add_phase = [&](int kind, int layer, int n_kb, int N, int wmap, int out, int smem_out, int wait_kb, int rel_kb) {
+    auto add_phase = [&](int kind, int layer, int n_kb, int N, int wmap, int out, int smem_out, int wait_kb, int rel_kb,
+                         int b_mn = 0) {
         PhaseDesc& d = p.ph[nph++];
         d.kind = (uint8_t)kind;
         d.layer = (uint8_t)layer;
@@ -1065,6 +1079,7 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         d.smem = (uint8_t)smem_out;
         d.wait_kb = (uint8_t)wait_kb;
         d.rel_kb = (uint8_t)rel_kb;
+        d.b_mn = (uint8_t)b_mn;
     };
 
     // ---- forward phases ----
@@ -1104,22 +1119,24 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         if (out < 0) return out;
         if (POLICY) {
             const int wmap = nw;
-            rc = add_w(net->wt[L], net->wt_ld[L], net->hidden[L - 1], out_pad8, net->hidden[L - 1]);
+            // dL/dH_L = dz W_head: W_head [out_pad8, hidden] itself as the MN-major operand (k = its rows)
+            rc = add_w(net->wq[L], net->wq_ld[L], out_pad8, net->hidden[L - 1], 64);
             if (rc) return rc;
-            add_phase(PH_DGRAD, L - 1, p.out_kb, net->hidden[L - 1], wmap, out, 1, 0, kb_of(net->hidden[L - 1]));
+            add_phase(PH_DGRAD, L - 1, p.out_kb, net->hidden[L - 1], wmap, out, 1, 0, kb_of(net->hidden[L - 1]), 1);
         } else {
             // GEMM-less phase: dL/dH_L from the accumulator of the last forward GEMM (still in TMEM)
             add_phase(PH_VALUE_BWD, L - 1, 0, net->hidden[L - 1], 0, out, 1, kb_of(net->hidden[L - 1]),
                       kb_of(net->hidden[L - 1]));
         }
         for (int l = L - 1; l >= 1; --l) {
-            // produce dH (hidden index l-1) from dH (hidden index l) with W_l^T = wt[l]
+            // produce dH (hidden index l-1) from dH (hidden index l): dH_l W_l with W_l [hidden_l, hidden_{l-1}] read as the
+            // MN-major operand (the forward pass reads the same array K-major)
             const int wmap = nw;
-            rc = add_w(net->wt[l], net->wt_ld[l], net->hidden[l - 1], net->hidden[l], net->hidden[l - 1]);
+            rc = add_w(net->wq[l], net->wq_ld[l], net->hidden[l], net->hidden[l - 1], 64);
             if (rc) return rc;
             out = add_out(net->dh[l - 1], net->dh_ld[l - 1], net->hidden[l - 1]);
             if (out < 0) return out;
-            add_phase(PH_DGRAD, l - 1, kb_of(net->hidden[l]), net->hidden[l - 1], wmap, out, 1, 0, kb_of(net->hidden[l - 1]));
+            add_phase(PH_DGRAD, l - 1, kb_of(net->hidden[l]), net->hidden[l - 1], wmap, out, 1, 0, kb_of(net->hidden[l - 1]), 1);
         }
         p.tail_rel_kb = kb_of(net->hidden[0]);
     }
@@ -1146,8 +1163,7 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 3072 * sizeof(unsigned long long), s));
         p.trace = d_trace;
     }
-    kfn<<<grid, kThreads, smem_bytes, s>>>(maps, p);
-    RLPPO_LAUNCH_CHECK();
+    RLPPO_CUDA(launch_pdl(kfn, dim3(grid), dim3(kThreads), smem_bytes, s, maps, p));
     if (tracing) {
         static unsigned long long h[3072];
         RLPPO_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));

@@ -857,6 +857,8 @@ wgrad_multi_kernel(const __grid_constant__ WMaps maps, const WMultiParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();       // the operands are the previous kernel's outputs
+    pdl_trigger();    // one item per CTA, all resident: the optimiser launch may be scheduled as items finish
 
     // decode a work item (identical in every role)
     struct Item {
@@ -1348,8 +1350,7 @@ int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream
         configured = true;
     }
     const int grid = p.total_items < ctas ? p.total_items : ctas;
-    wgrad_multi_kernel<<<grid, kThreads, SMEM, static_cast<cudaStream_t>(stream)>>>(maps, p);
-    RLPPO_LAUNCH_CHECK();
+    RLPPO_CUDA(launch_pdl(wgrad_multi_kernel, dim3(grid), dim3(kThreads), SMEM, static_cast<cudaStream_t>(stream), maps, p));
     return RLPPO_OK;
 }
 }

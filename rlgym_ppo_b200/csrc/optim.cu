@@ -176,7 +176,16 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     __shared__ double s_t[kMaxSeg];
     const int64_t total = segs.off[segs.n];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < segs.n) s_t[threadIdx.x] = (double)(step_count[threadIdx.x] + 1);   // read BEFORE the barrier
+    rlppo::pdl_wait();      // gradients come from the previous kernel of the stream
+    rlppo::pdl_trigger();   // every block of this grid is resident (grid barrier below): the next kernel may queue up
+    if (threadIdx.x < segs.n) {
+        // step count read BEFORE the barrier (block 0 writes it after); the double-precision bias corrections are formed
+        // here too, off the critical path between the barrier and the update
+        const double st = (double)(step_count[threadIdx.x] + 1);
+        s_t[threadIdx.x] = st;
+        s_step_size[threadIdx.x] = (float)((double)lr[threadIdx.x] / (1.0 - pow(beta1d, st)));
+        s_bc2_sqrt[threadIdx.x] = (float)sqrt(1.0 - pow(beta2d, st));
+    }
 
     // ---- phase 0 (PEERS): every rank's gradients are complete ----
     // This launch is stream-ordered behind the local backward kernels; block 0 tells every peer so, and every block
@@ -201,6 +210,21 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     // order as the one-rank kernel; the loads of four elements x all peers are issued before anything is summed: a loop of
     // dependent loads paid one NVLink round trip per peer and element (measured on 8 GPUs: no faster than NCCL).
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+    // The first kPre elements of every thread (all of them at the example nets: 332k parameters over 83k threads) stay in
+    // registers across the grid barrier: the summed gradient is not re-read, and p, m, v are fetched BEFORE the barrier,
+    // so the update phase starts without a DRAM round trip.
+    constexpr int kPre = 4;
+    float g_pre[kPre], p_pre[kPre], m_pre[kPre], v_pre[kPre];
+#pragma unroll
+    for (int e = 0; e < kPre; ++e) {
+        const int64_t i = gtid + e * gthreads;
+        g_pre[e] = 0.f;
+        if (i < total) {
+            p_pre[e] = __ldcs(p + i);
+            m_pre[e] = __ldcs(m + i);
+            v_pre[e] = __ldcs(v + i);
+        }
+    }
     if (MODE == kModeTwoShot) {
         // EXPERIMENTAL (not selected by default; see PPOLearner dp_collective="p2p2"): reduce-scatter + all-gather inside
         // the launch.  (a) this rank sums ITS slice of every peer's arena into its own `gsum` (which the peers have
@@ -262,6 +286,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
                 const int64_t i = i0 + e * gthreads;
                 if (i < total) {
                     const float x = xs[e];
+                    if (i0 == gtid) g_pre[e] = x;
                     if (i < lo || i >= hi) pr.gsum[i] = x;       // own slice is already in place
                     const int k = seg_of(segs, i);
 #pragma unroll
@@ -289,6 +314,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
 #pragma unroll
                     for (int r = 1; r < kMaxPeers; ++r)
                         if (r < pr.world) x += xs[e][r];
+                    if (i0 == gtid) g_pre[e] = x;
                     pr.gsum[i] = x;
                     const int k = seg_of(segs, i);
 #pragma unroll
@@ -298,12 +324,29 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
             }
         }
     }
-    for (int64_t i = gtid; !PEERS && i < total; i += gthreads) {
-        const float x = __ldg(g + i);
-        const int k = seg_of(segs, i);
+    if (!PEERS) {
 #pragma unroll
-        for (int j = 0; j < kMaxSeg; ++j)
-            if (j == k) acc[j] = fmaf(x, x, acc[j]);
+        for (int e = 0; e < kPre; ++e) {
+            const int64_t i = gtid + e * gthreads;
+            if (i < total) g_pre[e] = __ldg(g + i);
+        }
+#pragma unroll
+        for (int e = 0; e < kPre; ++e) {                  // same thread-serial order as the plain loop below
+            const int64_t i = gtid + e * gthreads;
+            if (i < total) {
+                const int k = seg_of(segs, i);
+#pragma unroll
+                for (int j = 0; j < kMaxSeg; ++j)
+                    if (j == k) acc[j] = fmaf(g_pre[e], g_pre[e], acc[j]);
+            }
+        }
+        for (int64_t i = gtid + kPre * gthreads; i < total; i += gthreads) {
+            const float x = __ldg(g + i);
+            const int k = seg_of(segs, i);
+#pragma unroll
+            for (int j = 0; j < kMaxSeg; ++j)
+                if (j == k) acc[j] = fmaf(x, x, acc[j]);
+        }
     }
 #pragma unroll
     for (int k = 0; k < kMaxSeg; ++k)
@@ -339,26 +382,22 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
             if (lane == 0) {
                 // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
                 s_coef[k] = fminf(max_norm / (sqrtf(t) + 1e-6f), 1.0f);
-                const double st = s_t[k];
-                s_step_size[k] = (float)((double)lr[k] / (1.0 - pow(beta1d, st)));
-                s_bc2_sqrt[k] = (float)sqrt(1.0 - pow(beta2d, st));
                 if (blockIdx.x == 0) {
                     if (sqnorm_out != nullptr) sqnorm_out[k] = t;
-                    step_count[k] = (int64_t)st;
+                    step_count[k] = (int64_t)s_t[k];
                 }
             }
         }
     }
     __syncthreads();
     int hint = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    auto update = [&](int64_t i, float graw, float mi, float vi, float pi) {
         const int k = seg_of(segs, i);
-        const float gi = (PEERS ? pr.gsum[i] : g[i]) * s_coef[k];
-        float mi = m[i], vi = v[i];
+        const float gi = graw * s_coef[k];
         mi = mi + (gi - mi) * omb1;                           // exp_avg.lerp_(grad, 1-beta1)
         vi = vi * beta2 + omb2 * gi * gi;                      // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
         const float denom = sqrtf(vi) / s_bc2_sqrt[k] + eps;   // (sqrt(v)/sqrt(bc2)).add_(eps)
-        const float pn = p[i] - s_step_size[k] * (mi / denom);   // param.addcdiv_(m, denom, -step_size)
+        const float pn = pi - s_step_size[k] * (mi / denom);   // param.addcdiv_(m, denom, -step_size)
         p[i] = pn;
         m[i] = mi;
         v[i] = vi;
@@ -372,7 +411,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
                     const int64_t rq = i - views.v[q].offset;
                     if (rq >= 0 && rq < (int64_t)views.v[q].out_f * views.v[q].in_f) found = q;
                 }
-                if (found < 0) continue;
+                if (found < 0) return;
                 hint = found;
                 rel = i - views.v[hint].offset;
             }
@@ -382,7 +421,14 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
             w.wq[(int64_t)r * w.wq_ld + c] = b;
             if (w.wt != nullptr) w.wt[(int64_t)c * w.wt_ld + r] = b;
         }
+    };
+#pragma unroll
+    for (int e = 0; e < kPre; ++e) {
+        const int64_t i = gtid + e * gthreads;
+        if (i < total) update(i, g_pre[e], m_pre[e], v_pre[e], p_pre[e]);
     }
+    for (int64_t i = gtid + kPre * gthreads; i < total; i += gthreads)
+        update(i, PEERS ? pr.gsum[i] : g[i], m[i], v[i], p[i]);
     // ---- leave: the last block resets the counters for the next launch ----
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -473,17 +519,20 @@ static int launch_norm_clip_adam(float* params, const float* grads, const Peers*
     rc = fused_grid(segs.off[n_seg], &grid);
     if (rc) return rc;
     if (peers != nullptr && peers->red[0] != nullptr)
-        norm_clip_adam_kernel<kModeTwoShot><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            params, nullptr, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
-            static_cast<FusedWs*>(ws), *peers);
+        RLPPO_CUDA(rlppo::launch_pdl(norm_clip_adam_kernel<kModeTwoShot>, dim3(grid), dim3(kFusedThreads), 0,
+                                     static_cast<cudaStream_t>(stream), params, (const float*)nullptr, m, v, segs, sqnorm_out, lr,
+                                     step_count, (float)max_norm, beta1, beta2, (float)eps, views, static_cast<FusedWs*>(ws),
+                                     *peers));
     else if (peers != nullptr)
-        norm_clip_adam_kernel<kModeOneShot><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            params, nullptr, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
-            static_cast<FusedWs*>(ws), *peers);
+        RLPPO_CUDA(rlppo::launch_pdl(norm_clip_adam_kernel<kModeOneShot>, dim3(grid), dim3(kFusedThreads), 0,
+                                     static_cast<cudaStream_t>(stream), params, (const float*)nullptr, m, v, segs, sqnorm_out, lr,
+                                     step_count, (float)max_norm, beta1, beta2, (float)eps, views, static_cast<FusedWs*>(ws),
+                                     *peers));
     else
-        norm_clip_adam_kernel<kModeLocal><<<grid, kFusedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            params, grads, m, v, segs, sqnorm_out, lr, step_count, (float)max_norm, beta1, beta2, (float)eps, views,
-            static_cast<FusedWs*>(ws), Peers{});
+        RLPPO_CUDA(rlppo::launch_pdl(norm_clip_adam_kernel<kModeLocal>, dim3(grid), dim3(kFusedThreads), 0,
+                                     static_cast<cudaStream_t>(stream), params, (const float*)grads, m, v, segs, sqnorm_out, lr,
+                                     step_count, (float)max_norm, beta1, beta2, (float)eps, views, static_cast<FusedWs*>(ws),
+                                     Peers{}));
     RLPPO_LAUNCH_CHECK();
     return RLPPO_OK;
 }

@@ -173,6 +173,7 @@ __global__ void gather_kernel(const float* __restrict__ actions, const float* __
     const int lane = threadIdx.x & 31;
     const int q = lane & 3;
     const int64_t b = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + (lane >> 2);
+    rlppo::pdl_wait();   // launched with the PDL attribute: the rings / the permutation may come from the previous kernel
     if (b >= B) return;
     if (d_start != nullptr) start = __ldg(d_start);   // device-resident ring origin: lets a captured graph follow the ring
     int64_t phys = start + __ldg(idx + b);
@@ -422,10 +423,9 @@ int rlppo_gather_batch(const float* actions, const float* logp, const float* val
     if (B == 0) return RLPPO_OK;
     const int threads = 256, per_block = threads / 32 * 8;      // eight samples per warp
     const unsigned blocks = (unsigned)((B + per_block - 1) / per_block);
-    gather_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        actions, logp, values, adv, states, states_ld, states_bf16, bf16_ld, obs_dim, capacity, start, d_start, idx, B,
-        out_actions, out_logp, out_values, out_adv, out_states, out_states_bf16);
-    RLPPO_LAUNCH_CHECK();
+    RLPPO_CUDA(rlppo::launch_pdl(gather_kernel, dim3(blocks), dim3(threads), 0, static_cast<cudaStream_t>(stream), actions,
+                                 logp, values, adv, states, states_ld, states_bf16, bf16_ld, obs_dim, capacity, start,
+                                 d_start, idx, B, out_actions, out_logp, out_values, out_adv, out_states, out_states_bf16));
     return RLPPO_OK;
 }
 

@@ -76,8 +76,12 @@ class Stack:
         self._seen_version = -1
         self._ws_rows = 0
         self._ws = None
-        # bf16 operands: wq[i] = W_i [out_pad8, in_pad8] (forward B operand, K-major);
-        #                wt[i] = W_i^T [in_pad8, out_pad8] (dgrad B operand), not needed for the first layer
+        # bf16 operands: wq[i] = W_i [out_pad8, in_pad8] (forward B operand, K-major; the fused kernels also read it as
+        #                the MN-major B operand of the backward data GEMMs);
+        #                wt[i] = W_i^T [in_pad8, out_pad8] (dgrad B operand of the LAYER-WISE kernels only; not needed for
+        #                the first layer).  `need_wt` says whether anything reads wt: while the stack runs on the fused
+        #                kernels it is neither refreshed by the optimiser launch nor by refresh_operands().
+        self.need_wt = True
         # "fp32" mode: wq[i] holds 3 parts (hi|mid|lo, each pad64(in) columns), wt[i] 2 parts of pad64(out) columns
         self.wq, self.wt = [], []
         self.in_ps = ops.pad64(self.in_dim)           # part stride of the split input rows
@@ -124,7 +128,8 @@ class Stack:
             v = _lib.Bf16View()
             v.offset, v.out_f, v.in_f = off, l.out_features, l.in_features
             v.wq, v.wq_ld = self.wq[i].data_ptr(), self.wq[i].stride(0)
-            v.wt, v.wt_ld = (None, 0) if self.wt[i] is None else (self.wt[i].data_ptr(), self.wt[i].stride(0))
+            v.wt, v.wt_ld = ((None, 0) if self.wt[i] is None or not self.need_wt
+                             else (self.wt[i].data_ptr(), self.wt[i].stride(0)))
             out.append(v)
             off += l.weight.numel() + l.bias.numel()
         return out
@@ -151,7 +156,7 @@ class Stack:
                 ops.weight_split(self.w[i], self.wq[i], 3, ops.pad64(l.in_features), self.wt[i], 2,
                                  ops.pad64(l.out_features))
             else:
-                ops.weight_to_bf16(self.w[i], self.wq[i], self.wt[i])
+                ops.weight_to_bf16(self.w[i], self.wq[i], self.wt[i] if self.need_wt else None)
         self._seen_version = self._version_sig()
 
     # ---- whole-network fused kernels (mlp_fused.cu) ---------------------------------------------------------------
@@ -177,8 +182,6 @@ class Stack:
         n_lin = L + 1 if policy_head else L
         for i in range(n_lin):
             net.wq[i], net.wq_ld[i] = self.wq[i].data_ptr(), self.wq[i].stride(0)
-            if i > 0:
-                net.wt[i], net.wt_ld[i] = self.wt[i].data_ptr(), self.wt[i].stride(0)
         for i in range(L + 1):
             net.bias[i], net.gbias[i] = self.b[i].data_ptr(), self.gb[i].data_ptr()
         if ws is not None:

@@ -182,8 +182,8 @@ class PPOLearner(object):
             assert batch_size % self.world_size == 0, "batch_size must be a multiple of the number of ranks"
         self._mb = None
         self.launches = 0   # kernels enqueued by the last learn() (bench.py reports it)
-        views = ps.bf16_views(0) + vs.bf16_views(n_p)
-        self._views = (_lib.Bf16View * len(views))(*views)
+        self._views_sig = None
+        self._sync_operand_views()
         # CUDA graphs: one optimiser step (gather -> fwd/bwd -> clip+Adam) is ~25 launches of 2-170 us kernels; replaying
         # a captured graph removes the Python/ctypes/driver launch cost that otherwise dominates the example-size nets
         self.use_cuda_graph = True
@@ -267,8 +267,26 @@ class PPOLearner(object):
             self._lr_dev.copy_(torch.tensor(lr + pad, dtype=torch.float32))
             self._lr_host = lr
 
+    def _sync_operand_views(self):
+        """Which bf16 operands the optimiser launch refreshes.  A stack that runs on the fused kernels needs no transposed
+        weight copies (its backward data GEMMs read W itself as an MN-major operand); the layer-wise kernels do.  Re-checked
+        before every batch: tests and experiments switch paths on a live learner (force_layerwise)."""
+        ps, vs = self.policy._stack, self.value_net._stack
+        sig = (ps.fused_ok and self.policy_type == 0, vs.fused_ok)
+        if sig == self._views_sig:
+            return
+        for st, fused in zip((ps, vs), sig):
+            was = st.need_wt
+            st.need_wt = not fused
+            if st.need_wt and not was and st.params is not None:
+                st.refresh_operands(force=True)
+        views = ps.bf16_views(0) + vs.bf16_views(ps.n_params)
+        self._views = (_lib.Bf16View * len(views))(*views)
+        self._views_sig = sig
+
     # ---- one chunk of one batch: gather -> fwd -> fused heads -> bwd (grads accumulate) -------------------------
     def _train_chunk(self, exp, idx, M):
+        self._sync_operand_views()
         mb = self._minibatch_buffers(M)
         if self.policy._stack.exact:
             exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
