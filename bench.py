@@ -61,15 +61,16 @@ FLOP_PER_STATE_VALUE = {"c2": 308224.0, "c3": 15046656.0}
 FLOP_PER_OBS_POLICY = {"c2": 353792.0, "c3": 15228928.0}
 
 # ---- which roof bounds a C-ABI entry point, and its algorithmic bytes where ops.py counts real ones ----
-TENSOR_BOUND = ("rlppo_policy_train_fused", "rlppo_value_train_fused", "rlppo_policy_infer_fused",
+TENSOR_BOUND = ("rlppo_policy_value_train_fused", "rlppo_policy_train_fused", "rlppo_value_train_fused", "rlppo_policy_infer_fused",
                 "rlppo_value_infer_fused", "rlppo_wgrad_multi", "rlppo_linear_fwd", "rlppo_linear_dgrad",
                 "rlppo_linear_dgrad_db", "rlppo_linear_wgrad", "rlppo_policy_head_train", "rlppo_policy_head_sample",
                 "rlppo_linear_fwd_split", "rlppo_linear_dgrad_split", "rlppo_linear_wgrad_split",
                 "rlppo_policy_head_train_split", "rlppo_policy_head_sample_split")
 # C-ABI entry point -> kernel name in the ncu reports (profiles/ncu_traffic.json is keyed by kernel name)
-KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_train_fused": "fused_mlp_kernel<1, 1>",
-             "rlppo_value_train_fused": "fused_mlp_kernel<0, 1>", "rlppo_value_infer_fused": "fused_mlp_kernel<0, 0>",
-             "rlppo_policy_infer_fused": "fused_mlp_kernel<1, 0>",
+KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_value_train_fused": "fused_mlp_kernel<1>",
+             "rlppo_policy_train_fused": "fused_mlp_kernel<1>",
+             "rlppo_value_train_fused": "fused_mlp_kernel<1>", "rlppo_value_infer_fused": "fused_mlp_kernel<0>",
+             "rlppo_policy_infer_fused": "fused_mlp_kernel<0>",
              "rlppo_gather_batch": "gather_kernel", "rlppo_gae_f32": "gae_scan3_kernel<1, 1>",
              "rlppo_linear_wgrad": "wgrad_kernel<256>", "rlppo_linear_fwd": "rowgemm_kernel<256, 0>",
              "rlppo_linear_dgrad": "rowgemm_kernel<256, 1>", "rlppo_linear_dgrad_db": "rowgemm_kernel<256, 1>",
@@ -78,7 +79,7 @@ KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_train_fuse
              "rlppo_norm_clip_adam": "norm_clip_adam_kernel", "rlppo_ring_append_fields_dev": "ring_append_fields_kernel",
              "rlppo_welford_update": "welford_kernel<1>", "rlppo_rows_to_bf16": "rows_to_bf16_kernel<0>"}
 # ties in time are broken in this order, so the reported kernel does not flip between runs
-DOMINANT_ORDER = ("rlppo_policy_train_fused", "rlppo_linear_fwd_split", "rlppo_linear_fwd", "rlppo_wgrad_multi",
+DOMINANT_ORDER = ("rlppo_policy_value_train_fused", "rlppo_policy_train_fused", "rlppo_linear_fwd_split", "rlppo_linear_fwd", "rlppo_wgrad_multi",
                   "rlppo_value_train_fused")
 
 

@@ -70,6 +70,7 @@ _SIGS = {
     "rlppo_policy_infer_fused": ([_P, _P, _L, _I, _P, _U64, _U64, _P, _I, _P, _P, _P, _P], _I),
     "rlppo_u64_add": ([_P, _U64, _P], _I),
     "rlppo_value_train_fused": ([_P, _P, _L, _P, _P, _F, _P, _P, _P, _P], _I),
+    "rlppo_policy_value_train_fused": ([_P, _P, _P, _L, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P], _I),
     "rlppo_value_infer_fused": ([_P, _P, _L, _P, _P, _P], _I),
     "rlppo_grad_sqnorm": ([_P, _P, _I, _P, _P], _I),
     "rlppo_clip_adam": ([_P, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D, _D, _P, _I, _P], _I),

@@ -54,14 +54,17 @@ constexpr int MAXPH = 2 * MAXL + 1;
 // shared memory (offsets from the 1024-aligned base): [act 64 KB][x stage in_kb*16 KB][weight ring nwst*32 KB][misc]
 constexpr uint32_t OFF_ACT = 0;
 constexpr uint32_t OFF_XST = ACT_BYTES;
-constexpr uint32_t MISC_BIAS = 0;                                  // (MAXL + 1) * 256 floats
-constexpr uint32_t MISC_ROWX = MISC_BIAS + (MAXL + 1) * 256 * 4;   // 1792 floats: row-wise exchange planes
-constexpr uint32_t ROWX_FLOATS = 1792;
-constexpr uint32_t MISC_DB = MISC_ROWX + ROWX_FLOATS * 4;          // (MAXL + 1) * 256 floats: column-sum accumulators
-constexpr uint32_t MISC_MASK = MISC_DB + (MAXL + 1) * 256 * 4;     // ReLU bit masks: [MAXL][4 k-blocks][256 threads] words
+constexpr uint32_t BIAS_FLOATS = (MAXL + 1) * 256;                 // per net: MAXL hidden bias slots + the head slot
+constexpr uint32_t MISC_BIAS = 0;                                  // 2 nets x BIAS_FLOATS floats
+constexpr uint32_t MISC_ROWX = MISC_BIAS + 2 * BIAS_FLOATS * 4;    // 1280 floats: row-wise exchange planes
+constexpr uint32_t ROWX_FLOATS = 1280;
+constexpr uint32_t MISC_DB = MISC_ROWX + ROWX_FLOATS * 4;          // 256 floats: column sums of the value head's weight gradient
+constexpr uint32_t MISC_MASK = MISC_DB + 256 * 4;                  // ReLU bit masks: [MAXL][4 k-blocks][256 threads] words
 constexpr uint32_t MISC_BARS = MISC_MASK + MAXL * 4 * kEpiThreads * 4;
 constexpr uint32_t MISC_BYTES = MISC_BARS + 256;
 constexpr uint32_t SMEM_LIMIT = 232448;                            // 227 KB
+static_assert(ACT_BYTES + 2 * KB_BYTES + MISC_BYTES + 1024 + 3 * WST_BYTES <= SMEM_LIMIT,
+              "an observation of <= 128 columns must leave room for a 3-stage weight ring (2 stages starve the MMA)");
 
 enum { PH_FWD = 0, PH_FWD_VALUE = 1, PH_HEAD = 2, PH_DGRAD = 3, PH_VALUE_BWD = 4 };
 constexpr uint8_t NO_STORE = 0xFF;
@@ -80,15 +83,18 @@ struct PhaseDesc {
                         // staged as N/64 chunks of 64 k-rows x 64 n-columns) -- no transposed copy of W exists
 };
 
+constexpr int MAXNET = 2;   // one launch runs the tiles of up to two nets (policy + value of the same batch)
+
 struct alignas(64) Maps {
     CUtensorMap x;
-    CUtensorMap w[MAXPH];
-    CUtensorMap out[MAXPH];   // training: H_l, d(logits), dL/dH_l (weight-gradient operands), TMA-stored per k-block
+    CUtensorMap w[MAXNET][MAXPH];
+    CUtensorMap out[MAXNET][MAXPH];   // training: H_l, d(logits), dL/dH_l (weight-gradient operands), TMA-stored per k-block
 };
 
-struct Params {
-    int64_t M;
-    int num_tiles, n_ph, L, in_kb, nwst;
+// everything that differs between the nets of one launch
+struct NetP {
+    int policy;              // 1: discrete policy head, 0: value head
+    int n_ph, L;
     int H[MAXL];
     PhaseDesc ph[MAXPH];
     int tail_rel_kb;         // k-blocks the last epilogue releases (consumed by the MMA thread at the end of a tile)
@@ -111,6 +117,14 @@ struct Params {
     float* gw_head;
     float* values_out;
     float* metrics;
+};
+
+struct Params {
+    int64_t M;
+    int num_tiles, in_kb, nwst;
+    int n_nets;                  // work items = n_nets * num_tiles: item q is tile q % num_tiles of net q / num_tiles
+    NetP net[MAXNET];
+    unsigned int* sched;         // [0] next item to hand out, [1] CTAs that have left (the last one zeroes both)
     int dbg_nostore;             // debug (RLPPO_FUSED_NOSTORE=1): timing experiment, outputs are NOT written
     unsigned long long* trace;   // debug (RLPPO_FUSED_TRACE=1): clock64 stamps of CTA 0, [role][event]
 };
@@ -258,7 +272,7 @@ __device__ __forceinline__ void release_kb(const EpiCtx& e, int kb) {
     if (e.lane == 0) mbar_arrive(e.a_ready + kb);
 }
 
-template <bool POLICY, bool TRAIN>
+template <bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_constant__ Maps maps, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -277,7 +291,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     uint64_t* a_ready = x_free + 1;         // [4]
     uint64_t* acc_full = a_ready + 4;       // [2]: one per accumulator
     uint64_t* st_done = acc_full + 2;       // [4]: the TMA store of k-block kb has finished reading shared memory
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 4);
+    uint64_t* tile_full = st_done + 4;      // [2]: the producer has published the CTA's next tile index
+    uint64_t* tile_empty = tile_full + 2;   // [2]: every consumer role has read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 2);
+    volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef RLPPO_FINE_TRACE
@@ -298,6 +315,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&st_done[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tile_full[i], 1);
+            mbar_init(&tile_empty[i], TRAIN ? 10 : 9);   // MMA thread, (training) store thread, 8 epilogue warps
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -305,53 +326,67 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     // are read from here on.  All CTAs of this grid are resident, so the next kernel may be scheduled as SMs free up.
     pdl_wait();
     pdl_trigger();
-    // biases (and the value head's weights) into shared memory: slot l < L hidden biases, slot MAXL the head
-    for (int i = threadIdx.x; i < (MAXL + 1) * 256; i += kThreads) {
-        const int l = i >> 8, c = i & 255;
+    // biases (and the value head's weights) into shared memory, one table per net: slot l < L hidden biases, slot MAXL the head
+    for (int i = threadIdx.x; i < p.n_nets * (int)BIAS_FLOATS; i += kThreads) {
+        const int ni = i >= (int)BIAS_FLOATS ? 1 : 0;
+        const NetP& np = p.net[ni];
+        const int j = i - ni * (int)BIAS_FLOATS;
+        const int l = j >> 8, c = j & 255;
         float b = 0.f;
-        if (l < p.L) {
-            if (c < p.H[l]) b = __ldg(p.bias[l] + c);
+        if (l < np.L) {
+            if (c < np.H[l]) b = __ldg(np.bias[l] + c);
         } else if (l == MAXL) {
-            if (POLICY) {
+            if (np.policy) {
                 // padding columns of the logits: a large negative bias, so exp() of them is exactly 0
-                b = c < p.n_actions ? (p.bias[MAXL] != nullptr ? __ldg(p.bias[MAXL] + c) : 0.f) : -1e30f;
+                b = c < np.n_actions ? (np.bias[MAXL] != nullptr ? __ldg(np.bias[MAXL] + c) : 0.f) : -1e30f;
             } else {
-                if (c < p.H[p.L - 1]) b = __ldg(p.w_head + c);
+                if (c < np.H[np.L - 1]) b = __ldg(np.w_head + c);
             }
         }
         s_bias[i] = b;
-        s_db[i] = 0.f;
     }
+    for (int i = threadIdx.x; i < 256; i += kThreads) s_db[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) STAMP(501);
-    // tiles of this CTA: blockIdx.x + k * gridDim.x
-    const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // Work items (net, tile) are handed out dynamically from a global counter, the first net's tiles first (the policy
+    // net's: they take longest, so the launch ends on the cheaper value tiles): 2 x 391 items over 148 CTAs instead of two
+    // launches of 391 tiles that each end on a third, 64 %-full round.  The producer thread fetches the next item one
+    // ahead and publishes it to the other roles through a two-slot ring; -1 ends the CTA.
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t ws = 0, wpar = 0;
             int tr3 = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int tile = blockIdx.x + it * gridDim.x;
+            for (int it = 0;; ++it) {
+                const int slot = it & 1;
+                mbar_wait(&tile_empty[slot], ((it >> 1) & 1) ^ 1);
+                int q = (int)atomicAdd(p.sched, 1u);
+                if (q >= p.n_nets * p.num_tiles) q = -1;
+                tile_ring[slot] = q;
+                mbar_arrive(&tile_full[slot]);
+                if (q < 0) break;
+                const int ni = q >= p.num_tiles ? 1 : 0;
+                const int tile = q - ni * p.num_tiles;
+                const NetP& np = p.net[ni];
                 mbar_wait(x_free, (it & 1) ^ 1);          // GEMM 0 of the previous tile has read the staging buffer
                 mbar_expect_tx(x_full, p.in_kb * KB_BYTES);
                 for (int kb = 0; kb < p.in_kb; ++kb)
                     tma_load_2d(&maps.x, x_full, xst + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
-                for (int ph = 0; ph < p.n_ph; ++ph) {
-                    const PhaseDesc& d = p.ph[ph];
+                for (int ph = 0; ph < np.n_ph; ++ph) {
+                    const PhaseDesc& d = np.ph[ph];
                     for (int kb = 0; kb < d.n_kb; ++kb) {
                         mbar_wait(&wempty[ws], wpar ^ 1);
                         mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
                         RLPPO_TRACE(3, tr3++);
                         if (d.b_mn) {
                             for (int c = 0; c < (d.N >> 6); ++c)
-                                tma_load_2d(&maps.w[d.wmap], &wfull[ws], wring + ws * WST_BYTES + c * MN_CHUNK, c * 64, kb * KBLK);
+                                tma_load_2d(&maps.w[ni][d.wmap], &wfull[ws], wring + ws * WST_BYTES + c * MN_CHUNK, c * 64, kb * KBLK);
                         } else {
-                            tma_load_2d(&maps.w[d.wmap], &wfull[ws], wring + ws * WST_BYTES, kb * KBLK, 0);
+                            tma_load_2d(&maps.w[ni][d.wmap], &wfull[ws], wring + ws * WST_BYTES, kb * KBLK, 0);
                         }
                         if (++ws == (uint32_t)p.nwst) {
                             ws = 0;
@@ -368,11 +403,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             uint32_t g = 0;                        // GEMMs issued so far: GEMM g accumulates into accumulator g & 1
             uint32_t apar = 0;                     // bit kb: parity of a_ready[kb] to wait for next (registers, not a local array)
             int tr0 = 0, tr4 = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int tile = blockIdx.x + it * gridDim.x;
+            for (int it = 0;; ++it) {
+                mbar_wait(&tile_full[it & 1], (it >> 1) & 1);
+                const int q = tile_ring[it & 1];
+                mbar_arrive(&tile_empty[it & 1]);
+                if (q < 0) break;
+                const NetP& np = p.net[q >= p.num_tiles ? 1 : 0];
 #pragma unroll 1
-                for (int ph = 0; ph < p.n_ph; ++ph) {
-                    const PhaseDesc& d = p.ph[ph];
+                for (int ph = 0; ph < np.n_ph; ++ph) {
+                    const PhaseDesc& d = np.ph[ph];
                     if (d.n_kb > 0) {
                         const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, d.b_mn);
                         const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
@@ -427,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 }
                 // tail: the last epilogue's releases (barrier parity; also: every epilogue warp is done with both
                 // accumulators and the activation tile before the next tile's first GEMM / epilogue touch them)
-                for (int kb = 0; kb < p.tail_rel_kb; ++kb) {
+                for (int kb = 0; kb < np.tail_rel_kb; ++kb) {
                     mbar_wait(&a_ready[kb], (apar >> kb) & 1u);
                     apar ^= 1u << kb;
                 }
@@ -441,11 +480,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         if (TRAIN && lane == 0) {
             uint32_t apar = 0;
             int nst = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                const int tile = blockIdx.x + it * gridDim.x;
+            for (int it = 0;; ++it) {
+                mbar_wait(&tile_full[it & 1], (it >> 1) & 1);
+                const int q = tile_ring[it & 1];
+                mbar_arrive(&tile_empty[it & 1]);
+                if (q < 0) break;
+                const int ni = q >= p.num_tiles ? 1 : 0;
+                const int tile = q - ni * p.num_tiles;
+                const NetP& np = p.net[ni];
 #pragma unroll 1
-                for (int ph = 0; ph < p.n_ph; ++ph) {
-                    const PhaseDesc& d = p.ph[ph];
+                for (int ph = 0; ph < np.n_ph; ++ph) {
+                    const PhaseDesc& d = np.ph[ph];
                     const bool storing = d.out != NO_STORE;
                     const bool skip = p.dbg_nostore != 0;
                     int pending = -1;
@@ -454,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         apar ^= 1u << kb;
                         if (!storing) continue;
                         RLPPO_TRACE(2, 2 * nst);
-                        if (!skip) tma_store_2d(&maps.out[d.out], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
+                        if (!skip) tma_store_2d(&maps.out[ni][d.out], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
                         bulk_commit();
                         if (pending >= 0) {
                             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -487,10 +532,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         e.row_in_tile = e.quarter * 32 + lane;
 
         float dv_keep = 0.f;   // value net: d(loss)/dv of this thread's row, kept from the forward tail
-        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, mrows = 0.f;   // metric partial sums of this thread's rows
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, mrows = 0.f;   // policy metric partial sums of this thread's rows
+        float vm0 = 0.f, vm1 = 0.f, vrows = 0.f;                     // value net: squared error, head bias gradient, rows
         // column sums (bias gradients, value-head weight gradient) accumulate in shared memory: lane j of a warp holds the
         // partial sum of column 32c + j over the warp's 32 rows; four warps (row quarters) add into the same word
-        auto db_add = [&](int l, int c, float v) { atomicAdd(&s_db[l * 256 + c * 32 + e.lane], v); };
+        auto db_add = [&](int c, float v) { atomicAdd(&s_db[c * 32 + e.lane], v); };
 
         uint32_t g = 0;                  // mirrors the MMA thread's GEMM counter
         uint32_t fpar = 0;               // bit a: parity of acc_full[a] to wait for next
@@ -507,13 +553,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         int tr1 = 0;
         int tr5 = 0;
         (void)tr5;
-        for (int it = 0; it < my_tiles; ++it) {
-          const int tile = blockIdx.x + it * gridDim.x;
+        for (int it = 0;; ++it) {
+          mbar_wait(&tile_full[it & 1], (it >> 1) & 1);
+          const int q = tile_ring[it & 1];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tile_empty[it & 1]);
+          if (q < 0) break;
+          const int ni = q >= p.num_tiles ? 1 : 0;
+          const int tile = q - ni * p.num_tiles;
+          const NetP& np = p.net[ni];
+          const float* s_bias_n = s_bias + ni * (int)BIAS_FLOATS;   // this net's bias table
           const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
           const bool row_ok = row < p.M;
 #pragma unroll 1
-          for (int ph = 0; ph < p.n_ph; ++ph) {
-                const PhaseDesc& d = p.ph[ph];
+          for (int ph = 0; ph < np.n_ph; ++ph) {
+                const PhaseDesc& d = np.ph[ph];
                 uint32_t acc;
                 if (d.n_kb > 0) {
                     acc = g & 1u;
@@ -547,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);   // next chunk in flight during this one
                         // biases as 8 x 128-bit shared loads (one wavefront each; the MMA's operand fetch owns most of the
                         // shared-memory bandwidth while this runs); bias add in fp32, ReLU inside the bf16 pack
-                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias + li * 256 + c * 32);
+                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias_n + li * 256 + c * 32);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 b4 = sb4[q];
@@ -561,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         if (TRAIN) e.s_mask[(li * 4 + j) * kEpiThreads] = relu_mask32(w);
                         if (tail) {
                             // value head dot product on the bf16-rounded activations (what a GEMM would read)
-                            const float4* wv4 = reinterpret_cast<const float4*>(s_bias + MAXL * 256 + c * 32);
+                            const float4* wv4 = reinterpret_cast<const float4*>(s_bias_n + MAXL * 256 + c * 32);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
                                 const float4 w4 = wv4[q];
@@ -589,18 +643,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         float* rowx = e.s_rowx;
                         rowx[e.half * 128 + e.row_in_tile] = (dq[0] + dq[1]) + (dq[2] + dq[3]);
                         epi_bar_sync();
-                        const float bhead = p.bias[MAXL] != nullptr ? __ldg(p.bias[MAXL]) : 0.f;
+                        const float bhead = np.bias[MAXL] != nullptr ? __ldg(np.bias[MAXL]) : 0.f;
                         const float val = rowx[e.row_in_tile] + rowx[128 + e.row_in_tile] + bhead;
-                        if (e.half == 0 && row_ok && p.values_out != nullptr) p.values_out[row] = val;
+                        if (e.half == 0 && row_ok && np.values_out != nullptr) np.values_out[row] = val;
                         if (TRAIN) {
                             float dv = 0.f;
                             if (row_ok) {
-                                const float err = val - __ldg(p.targets + row);
-                                dv = 2.0f * p.inv_batch * err;                     // d(MSE * mb/B)/dv, ppo_learner.py:176
+                                const float err = val - __ldg(np.targets + row);
+                                dv = 2.0f * np.inv_batch * err;                     // d(MSE * mb/B)/dv, ppo_learner.py:176
                                 if (e.half == 0) {
-                                    m0 += err * err;
-                                    mrows += 1.f;
-                                    m1 += dv;                                      // head bias gradient
+                                    vm0 += err * err;
+                                    vrows += 1.f;
+                                    vm1 += dv;                                     // head bias gradient
                                 }
                             }
                             dv_keep = dv;
@@ -619,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         const int c = 2 * j + e.half;
                         float v[32], t[32];
                         tmem_ld32(trow + c * 32, v);
-                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias + li * 256 + c * 32);
+                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias_n + li * 256 + c * 32);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 b4 = sb4[q];
@@ -635,9 +689,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             t[2 * i] = dv * __uint_as_float(w[i] << 16);
                             t[2 * i + 1] = dv * __uint_as_float(w[i] & 0xFFFF0000u);
                         }
-                        db_add(MAXL, c, warp_colsum32(t, e.lane));     // value head weight gradient (slot MAXL)
+                        db_add(c, warp_colsum32(t, e.lane));     // value head weight gradient (slot MAXL)
                         const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
-                        const float4* wv4 = reinterpret_cast<const float4*>(s_bias + MAXL * 256 + c * 32);
+                        const float4* wv4 = reinterpret_cast<const float4*>(s_bias_n + MAXL * 256 + c * 32);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 w4 = wv4[q];
@@ -687,23 +741,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 // memory behind a 64-thread named barrier per warp pair.  Three branch-free passes re-read the logits from
                 // TMEM.  The bias slots of the padding columns hold -1e30, so a padding column's exp() is 0 and its
                 // d(logit) is 0 without a bounds test per element.
-                const int nact = p.n_actions;
+                const int nact = np.n_actions;
                 const int nch = (nact + 31) >> 5;          // <= 4
                 const int hoff = e.half * 16;              // this thread's 16 columns inside each chunk
-                const float* sb = s_bias + MAXL * 256;
+                const float* sb = s_bias_n + MAXL * 256;
                 const float kLogMin = -25.328436022934504f;   // ln(1e-11)
-                float* xch = e.s_rowx;                        // exchange planes: [0,256) max, [512,768) argmax, [1024,1792) S/T/z_a
+                float* xch = e.s_rowx;                        // exchange planes: [0,256) max, [256,512) argmax, [512,1280) S/T/z_a
                 if (TRAIN) {
-                    const int nch_out = p.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
+                    const int nch_out = np.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
                     const int prow = e.half * 128 + e.row_in_tile, orow = (e.half ^ 1) * 128 + e.row_in_tile;
                     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + e.quarter) : "memory"); };
                     int a = 0;
                     float old_lp = 0.f, advv = 0.f;
                     if (row_ok) {
-                        a = (int)__ldg(p.actions + row);             // acts.long(), discrete_policy.py:71
+                        a = (int)__ldg(np.actions + row);             // acts.long(), discrete_policy.py:71
                         a = min(max(a, 0), nact - 1);
-                        old_lp = __ldg(p.old_logp + row);
-                        advv = __ldg(p.adv + row);
+                        old_lp = __ldg(np.old_logp + row);
+                        advv = __ldg(np.adv + row);
                     }
                     // pass 1: row maximum
                     float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -752,7 +806,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
                     float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
                     {
-                        float* x3 = xch + 1024;   // [3][half][row]
+                        float* x3 = xch + 512;   // [3][half][row]
                         x3[prow] = S;
                         x3[256 + prow] = T;
                         x3[512 + prow] = zs_a;
@@ -776,24 +830,24 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     const float p_a = fminf(fmaxf(s_a, 1e-11f), 1.0f);
                     const float log_ratio = lp_a - old_lp;
                     const float ratio = expf(log_ratio);                            // ppo_learner.py:153
-                    const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
+                    const float lo = 1.0f - np.clip, hi = 1.0f + np.clip;
                     const float clipped = fminf(fmaxf(ratio, lo), hi);              // :154-156
                     const float s1 = ratio * advv, s2 = clipped * advv;
                     const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
                     const float d1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);      // torch.min backward, ties 0.5/0.5
                     const float d2 = s1 > s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
                     const float okf = row_ok ? 1.f : 0.f;
-                    const float d_logp = -p.inv_batch * advv * (d1 + d2 * in_range) * ratio * okf;
+                    const float d_logp = -np.inv_batch * advv * (d1 + d2 * in_range) * ratio * okf;
                     const float ga = (ls_a >= kLogMin) ? d_logp / p_a : 0.f;        // through log(clamp(s_a))
-                    const float cw = p.ent_coef * p.inv_batch * okf;
+                    const float cw = np.ent_coef * np.inv_batch * okf;
                     const float G = cw * Gs + ga * s_a;
                     if (row_ok && e.half == 0) {
                         m0 += Hent;
                         m1 += (ratio - 1.0f) - log_ratio;                           // :161
-                        m2 += fabsf(ratio - 1.0f) > p.clip ? 1.f : 0.f;             // :166
+                        m2 += fabsf(ratio - 1.0f) > np.clip ? 1.f : 0.f;             // :166
                         m3 += fminf(s1, s2);
                         mrows += 1.f;
-                        if (p.logp_out) p.logp_out[row] = lp_a;
+                        if (np.logp_out) np.logp_out[row] = lp_a;
                     }
                     // pass 3: dz_j = s_j (g_j - G), g_j = cw (log s_j + 1) + [j = a] ga  -> bf16 tile (A operand of the
                     // first dgrad GEMM and of the head's weight-gradient GEMM, which also forms the head's bias gradient).
@@ -831,7 +885,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         wait_store(c >> 1);
                         sts_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, w);
                     }
-                    for (int j = 0; j < p.out_kb; ++j) {
+                    for (int j = 0; j < np.out_kb; ++j) {
                         release_kb(e, j);
                         if (d.out != NO_STORE) pend |= 1u << j;
                     }
@@ -862,7 +916,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         argmax = better ? aq[q] : argmax;
                     }
                     xch[e.half * 128 + e.row_in_tile] = mx;
-                    int* xchi = reinterpret_cast<int*>(xch) + 512;   // second plane: argmax (ints), see OFF_ROWX sizing
+                    int* xchi = reinterpret_cast<int*>(xch) + 256;   // second plane: argmax (ints)
                     xchi[e.half * 128 + e.row_in_tile] = argmax;
                     epi_bar_sync();
                     {
@@ -893,7 +947,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
                     float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
                     {
-                        float* x3 = xch + 1024;   // [3][half][row]
+                        float* x3 = xch + 512;   // [3][half][row]
                         x3[0 * 256 + e.half * 128 + e.row_in_tile] = S;
                         x3[1 * 256 + e.half * 128 + e.row_in_tile] = T;
                         x3[2 * 256 + e.half * 128 + e.row_in_tile] = zs_a;
@@ -926,19 +980,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         const float P = (Pq[0] + Pq[1]) + (Pq[2] + Pq[3]);
                         int actn = nact - 1;
                         float pa = 0.f;
-                        if (p.deterministic) {
+                        if (np.deterministic) {
                             actn = argmax;
                             pa = fminf(fmaxf(__expf(-logS), 1e-11f), 1.0f);
                         } else {
                             float u = 0.f;
                             if (row_ok) {
-                                if (p.u_inject != nullptr) {
-                                    u = __ldg(p.u_inject + row);
+                                if (np.u_inject != nullptr) {
+                                    u = __ldg(np.u_inject + row);
                                 } else {
-                                    const uint64_t ctr = p.offset + (p.d_offset != nullptr ? (uint64_t)__ldg(p.d_offset) : 0ull) +
+                                    const uint64_t ctr = np.offset + (np.d_offset != nullptr ? (uint64_t)__ldg(np.d_offset) : 0ull) +
                                                          (uint64_t)row;
                                     const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                                                                  make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+                                                                  make_uint2((uint32_t)np.seed, (uint32_t)(np.seed >> 32)));
                                     u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
                                 }
                             }
@@ -965,9 +1019,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             pa = found ? pa : plast;
                         }
                         if (row_ok) {
-                            if (p.actions_out) p.actions_out[row] = (float)actn;   // batched_agent_manager.py:204
-                            if (p.actions_i64_out) p.actions_i64_out[row] = (int64_t)actn;
-                            if (p.logp_out) p.logp_out[row] = logf(pa);            // :60
+                            if (np.actions_out) np.actions_out[row] = (float)actn;   // batched_agent_manager.py:204
+                            if (np.actions_i64_out) np.actions_i64_out[row] = (int64_t)actn;
+                            if (np.logp_out) np.logp_out[row] = logf(pa);            // :60
                         }
                     }
                 }
@@ -976,21 +1030,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           }
         }
         // ---- metrics (the column sums are flushed by the whole CTA below) ----
-        if (TRAIN) {
-            if (p.metrics != nullptr && e.half == 0) {
-                const float r0 = warp_sum(m0), r1 = warp_sum(m1), r2 = warp_sum(m2), r3 = warp_sum(m3),
-                            rr = warp_sum(mrows);
-                if (e.lane == 0 && rr > 0.f) {
-                    if (POLICY) {
-                        atomicAdd(p.metrics + 0, r0);
-                        atomicAdd(p.metrics + 1, r1);
-                        atomicAdd(p.metrics + 2, r2);
-                        atomicAdd(p.metrics + 3, r3);
-                        atomicAdd(p.metrics + 4, rr);
-                    } else {
-                        atomicAdd(p.metrics + 5, r0);
-                        atomicAdd(p.metrics + 6, rr);
-                        if (p.gbias[MAXL] != nullptr) atomicAdd(p.gbias[MAXL], r1);
+        if (TRAIN && e.half == 0) {
+            for (int ni = 0; ni < p.n_nets; ++ni) {
+                const NetP& np = p.net[ni];
+                if (np.metrics == nullptr) continue;
+                if (np.policy) {
+                    const float r0 = warp_sum(m0), r1 = warp_sum(m1), r2 = warp_sum(m2), r3 = warp_sum(m3),
+                                rr = warp_sum(mrows);
+                    if (e.lane == 0 && rr > 0.f) {
+                        atomicAdd(np.metrics + 0, r0);
+                        atomicAdd(np.metrics + 1, r1);
+                        atomicAdd(np.metrics + 2, r2);
+                        atomicAdd(np.metrics + 3, r3);
+                        atomicAdd(np.metrics + 4, rr);
+                    }
+                } else {
+                    const float r0 = warp_sum(vm0), r1 = warp_sum(vm1), rr = warp_sum(vrows);
+                    if (e.lane == 0 && rr > 0.f) {
+                        atomicAdd(np.metrics + 5, r0);
+                        atomicAdd(np.metrics + 6, rr);
+                        if (np.gbias[MAXL] != nullptr) atomicAdd(np.gbias[MAXL], r1);
                     }
                 }
             }
@@ -1003,10 +1062,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
-    if (TRAIN && !POLICY) {
-        // flush the shared-memory column sums of the value head's weight gradient (slot MAXL); the bias gradients of every
-        // Linear are column sums of tiles the weight-gradient kernel reads anyway and are formed there (rlppo_wgrad_multi)
-        for (int c = threadIdx.x; c < p.H[p.L - 1]; c += kThreads) atomicAdd(p.gw_head + c, s_db[MAXL * 256 + c]);
+    if (threadIdx.x == 0) {
+        // every CTA has drawn its last (out-of-range) index by now: the last CTA to leave re-arms the scheduler words
+        if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
+    if (TRAIN) {
+        // flush the shared-memory column sums of the value head's weight gradient; the bias gradients of every Linear are
+        // column sums of tiles the weight-gradient kernel reads anyway and are formed there (rlppo_wgrad_multi)
+        for (int ni = 0; ni < p.n_nets; ++ni) {
+            const NetP& np = p.net[ni];
+            if (np.policy || np.gw_head == nullptr) continue;
+            for (int c = threadIdx.x; c < np.H[np.L - 1]; c += kThreads) atomicAdd(np.gw_head + c, s_db[c]);
+        }
     }
 }
 
@@ -1024,17 +1095,15 @@ int check_net(const rlppo_fused_net* net) {
     return RLPPO_OK;
 }
 
-template <bool POLICY, bool TRAIN>
-int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Params& p, cudaStream_t s) {
+// Fills net slot `ni` of a launch: phase list, tensor maps of its weights and outputs.  `n` already holds the head's
+// arguments (entry points below).
+template <bool TRAIN>
+int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& maps, NetP& p) {
     int rc = check_net(net);
     if (rc) return rc;
-    RLPPO_CHECK_ARG(M >= 1 && M < (1ll << 31) - TILE_M, "bad row count");
     const int L = net->n_hidden;
-    Maps maps;
-    p.M = M;
-    p.num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+    p.policy = POLICY ? 1 : 0;
     p.L = L;
-    p.in_kb = (net->in_dim + KBLK - 1) / KBLK;
     for (int l = 0; l < MAXL; ++l) p.H[l] = l < L ? net->hidden[l] : 0;
     for (int l = 0; l < L; ++l) {
         p.bias[l] = net->bias[l];
@@ -1044,14 +1113,11 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     p.bias[MAXL] = net->bias[L];
     p.gbias[MAXL] = TRAIN ? net->gbias[L] : nullptr;
 
-    rc = make_tmap_bf16_2d(&maps.x, x, (uint64_t)M, (uint64_t)net->in_dim, (uint64_t)net->in_ld, TILE_M);
-    if (rc) return rc;
-
     int nw = 0, nph = 0;
     for (int i = 0; i < MAXPH; ++i) p.ph[i] = PhaseDesc{};
     auto add_w = [&](const uint16_t* w, int64_t ld, int rows, int cols, int box_rows) -> int {
         RLPPO_CHECK_ARG(w != nullptr && ld % 8 == 0, "missing weight operand");
-        int r = make_tmap_bf16_2d(&maps.w[nw], w, (uint64_t)rows, (uint64_t)cols, (uint64_t)ld, (uint32_t)box_rows);
+        int r = make_tmap_bf16_2d(&maps.w[ni][nw], w, (uint64_t)rows, (uint64_t)cols, (uint64_t)ld, (uint32_t)box_rows);
         if (r) return r;
         ++nw;
         return RLPPO_OK;
@@ -1059,7 +1125,7 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     int nout = 0;
     auto add_out = [&](uint16_t* o, int64_t ld, int cols) -> int {
         RLPPO_CHECK_ARG(o != nullptr && ld % 8 == 0 && ld >= cols, "missing activation / gradient output buffer");
-        int r = make_tmap_bf16_2d(&maps.out[nout], o, (uint64_t)M, (uint64_t)cols, (uint64_t)ld, TILE_M);
+        int r = make_tmap_bf16_2d(&maps.out[ni][nout], o, (uint64_t)M, (uint64_t)cols, (uint64_t)ld, TILE_M);
         if (r) return r;
         return nout++;
     };
@@ -1141,6 +1207,28 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         p.tail_rel_kb = kb_of(net->hidden[0]);
     }
     p.n_ph = nph;
+    return RLPPO_OK;
+}
+
+template <bool TRAIN>
+int launch_nets(const rlppo_fused_net* const* nets, const bool* is_policy, int n_nets, const uint16_t* x, int64_t M, Params& p,
+                cudaStream_t s) {
+    RLPPO_CHECK_ARG(n_nets >= 1 && n_nets <= MAXNET && nets[0] != nullptr, "1..%d nets per launch", MAXNET);
+    RLPPO_CHECK_ARG(M >= 1 && M < (1ll << 30) - TILE_M, "bad row count");
+    Maps maps;
+    p.M = M;
+    p.num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+    p.n_nets = n_nets;
+    p.in_kb = (nets[0]->in_dim + KBLK - 1) / KBLK;
+    for (int ni = 0; ni < n_nets; ++ni) {
+        RLPPO_CHECK_ARG(nets[ni]->in_dim == nets[0]->in_dim && nets[ni]->in_ld == nets[0]->in_ld,
+                        "nets of one launch read the same x");
+        int rc = build_net<TRAIN>(is_policy[ni], nets[ni], M, ni, maps, p.net[ni]);
+        if (rc) return rc;
+    }
+    const rlppo_fused_net* net = nets[0];
+    int rc = make_tmap_bf16_2d(&maps.x, x, (uint64_t)M, (uint64_t)net->in_dim, (uint64_t)net->in_ld, TILE_M);
+    if (rc) return rc;
 
     // shared memory: activation tile + x staging (in_kb k-blocks) + as deep a weight ring as fits + misc
     const uint32_t fixed = ACT_BYTES + (uint32_t)p.in_kb * KB_BYTES + MISC_BYTES + 1024;
@@ -1149,14 +1237,30 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     RLPPO_CHECK_ARG(p.nwst >= 2, "fused path: shared memory budget");
     const uint32_t smem_bytes = fixed + (uint32_t)p.nwst * WST_BYTES;
     static bool configured = false;
-    auto kfn = fused_mlp_kernel<POLICY, TRAIN>;
+    auto kfn = fused_mlp_kernel<TRAIN>;
     if (!configured) {
         RLPPO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         configured = true;
     }
-    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    const int items = p.num_tiles * n_nets;
+    const int grid = items < num_sms() ? items : num_sms();
+    // scheduler words: a pool of self-resetting {next tile, departures} pairs, handed out round-robin so that launches that
+    // may overlap (the two nets of a batch on two streams; consecutive launches under PDL) never share a pair
+    {
+        constexpr int kSlots = 64;
+        static unsigned int* d_sched[16] = {};
+        static unsigned int next_slot[16] = {};
+        int dev = 0;
+        RLPPO_CUDA(cudaGetDevice(&dev));
+        RLPPO_CHECK_ARG(dev >= 0 && dev < 16, "device index out of range");
+        if (d_sched[dev] == nullptr) {
+            RLPPO_CUDA(cudaMalloc(&d_sched[dev], kSlots * 2 * sizeof(unsigned int)));
+            RLPPO_CUDA(cudaMemset(d_sched[dev], 0, kSlots * 2 * sizeof(unsigned int)));
+        }
+        p.sched = d_sched[dev] + 2 * (next_slot[dev]++ % kSlots);
+    }
     static unsigned long long* d_trace = nullptr;
-    const bool tracing = getenv("RLPPO_FUSED_TRACE") != nullptr && TRAIN && POLICY;
+    const bool tracing = getenv("RLPPO_FUSED_TRACE") != nullptr && TRAIN && p.net[0].policy;
     p.dbg_nostore = getenv("RLPPO_FUSED_NOSTORE") != nullptr ? 1 : 0;
     if (tracing) {
         if (d_trace == nullptr) RLPPO_CUDA(cudaMalloc(&d_trace, 3072 * sizeof(unsigned long long)));
@@ -1169,7 +1273,7 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
         RLPPO_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
         RLPPO_CUDA(cudaStreamSynchronize(s));
         const unsigned long long t0 = h[0];
-        fprintf(stderr, "[fused trace] n_ph=%d tiles=%d\n", p.n_ph, p.num_tiles);
+        fprintf(stderr, "[fused trace] n_ph=%d tiles=%d\n", p.net[0].n_ph, p.num_tiles);
         for (int i = 0; i + 1 < 512 && (i == 0 || h[i] != 0); i += 2)
             fprintf(stderr, "  mma  #%d start=%llu issued+stored=+%llu\n", i / 2, h[i] - t0, h[i + 1] - h[i]);
         for (int i = 0; i + 1 < 512 && h[512 + i] != 0; i += 2)
@@ -1189,6 +1293,21 @@ int launch_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, Param
     return RLPPO_OK;
 }
 
+void fill_policy_train(NetP& n, int n_actions, const float* actions, const float* old_logp, const float* adv,
+                       float inv_batch, float clip, float ent_coef, float* logp_out, float* metrics) {
+    n.n_actions = n_actions;
+    n.actions = actions; n.old_logp = old_logp; n.adv = adv;
+    n.inv_batch = inv_batch; n.clip = clip; n.ent_coef = ent_coef;
+    n.logp_out = logp_out; n.metrics = metrics;
+}
+void fill_value_train(NetP& n, const float* w_head, const float* targets, float inv_batch, float* gw_head,
+                      float* values_out, float* metrics) {
+    n.w_head = w_head; n.targets = targets; n.inv_batch = inv_batch; n.gw_head = gw_head;
+    n.values_out = values_out; n.metrics = metrics;
+}
+
+__global__ void u64_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+
 }  // namespace
 
 extern "C" {
@@ -1200,20 +1319,36 @@ int rlppo_policy_train_fused(const rlppo_fused_net* net, const uint16_t* x, int6
     RLPPO_CHECK_ARG(x && actions && old_logp && adv, "null pointer");
     RLPPO_CHECK_ARG(n_actions >= 1 && n_actions <= 128, "fused path: n_actions must be in [1,128]");
     Params p{};
-    p.n_actions = n_actions;
-    p.actions = actions; p.old_logp = old_logp; p.adv = adv;
-    p.inv_batch = inv_batch; p.clip = clip; p.ent_coef = ent_coef;
-    p.logp_out = logp_out; p.metrics = metrics;
-    return launch_fused<true, true>(net, x, M, p, static_cast<cudaStream_t>(stream));
+    fill_policy_train(p.net[0], n_actions, actions, old_logp, adv, inv_batch, clip, ent_coef, logp_out, metrics);
+    const bool pol[1] = {true};
+    return launch_nets<true>(&net, pol, 1, x, M, p, static_cast<cudaStream_t>(stream));
 }
 
-}  // extern "C"
+int rlppo_value_train_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, const float* w_head,
+                            const float* targets, float inv_batch, float* gw_head, float* values_out, float* metrics,
+                            void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(x && w_head && targets && gw_head, "null pointer");
+    Params p{};
+    fill_value_train(p.net[0], w_head, targets, inv_batch, gw_head, values_out, metrics);
+    const bool pol[1] = {false};
+    return launch_nets<true>(&net, pol, 1, x, M, p, static_cast<cudaStream_t>(stream));
+}
 
-namespace {
-__global__ void u64_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
-}  // namespace
-
-extern "C" {
+int rlppo_policy_value_train_fused(const rlppo_fused_net* policy_net, const rlppo_fused_net* value_net, const uint16_t* x,
+                                   int64_t M, int n_actions, const float* actions, const float* old_logp, const float* adv,
+                                   float inv_batch, float clip, float ent_coef, float* logp_out, const float* w_head,
+                                   const float* targets, float* gw_head, float* values_out, float* metrics, void* stream) {
+    RLPPO_REQUIRE_DEVICE();
+    RLPPO_CHECK_ARG(policy_net && value_net && x && actions && old_logp && adv && w_head && targets && gw_head, "null pointer");
+    RLPPO_CHECK_ARG(n_actions >= 1 && n_actions <= 128, "fused path: n_actions must be in [1,128]");
+    Params p{};
+    fill_policy_train(p.net[0], n_actions, actions, old_logp, adv, inv_batch, clip, ent_coef, logp_out, metrics);
+    fill_value_train(p.net[1], w_head, targets, inv_batch, gw_head, values_out, metrics);
+    const rlppo_fused_net* nets[2] = {policy_net, value_net};
+    const bool pol[2] = {true, false};
+    return launch_nets<true>(nets, pol, 2, x, M, p, static_cast<cudaStream_t>(stream));
+}
 
 int rlppo_u64_add(uint64_t* d_counter, uint64_t inc, void* stream) {
     RLPPO_REQUIRE_DEVICE();
@@ -1231,22 +1366,13 @@ int rlppo_policy_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int6
     RLPPO_CHECK_ARG(x != nullptr, "null pointer");
     RLPPO_CHECK_ARG(n_actions >= 1 && n_actions <= 128, "fused path: n_actions must be in [1,128]");
     Params p{};
-    p.n_actions = n_actions;
-    p.u_inject = u_inject; p.seed = seed; p.offset = offset; p.deterministic = deterministic;
-    p.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
-    p.actions_out = actions_out; p.actions_i64_out = actions_i64_out; p.logp_out = logp_out;
-    return launch_fused<true, false>(net, x, M, p, static_cast<cudaStream_t>(stream));
-}
-
-int rlppo_value_train_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, const float* w_head,
-                            const float* targets, float inv_batch, float* gw_head, float* values_out, float* metrics,
-                            void* stream) {
-    RLPPO_REQUIRE_DEVICE();
-    RLPPO_CHECK_ARG(x && w_head && targets && gw_head, "null pointer");
-    Params p{};
-    p.w_head = w_head; p.targets = targets; p.inv_batch = inv_batch; p.gw_head = gw_head;
-    p.values_out = values_out; p.metrics = metrics;
-    return launch_fused<false, true>(net, x, M, p, static_cast<cudaStream_t>(stream));
+    NetP& n = p.net[0];
+    n.n_actions = n_actions;
+    n.u_inject = u_inject; n.seed = seed; n.offset = offset; n.deterministic = deterministic;
+    n.d_offset = reinterpret_cast<const unsigned long long*>(d_offset);
+    n.actions_out = actions_out; n.actions_i64_out = actions_i64_out; n.logp_out = logp_out;
+    const bool pol[1] = {true};
+    return launch_nets<false>(&net, pol, 1, x, M, p, static_cast<cudaStream_t>(stream));
 }
 
 int rlppo_value_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, const float* w_head,
@@ -1254,7 +1380,8 @@ int rlppo_value_infer_fused(const rlppo_fused_net* net, const uint16_t* x, int64
     RLPPO_REQUIRE_DEVICE();
     RLPPO_CHECK_ARG(x && w_head && values_out, "null pointer");
     Params p{};
-    p.w_head = w_head; p.values_out = values_out;
-    return launch_fused<false, false>(net, x, M, p, static_cast<cudaStream_t>(stream));
+    p.net[0].w_head = w_head; p.net[0].values_out = values_out;
+    const bool pol[1] = {false};
+    return launch_nets<false>(&net, pol, 1, x, M, p, static_cast<cudaStream_t>(stream));
 }
 }

@@ -1325,15 +1325,42 @@ int rlppo_wgrad_multi(const rlppo_wgrad_item* h_items, int n_items, void* stream
         total_bytes += bytes[i];
     }
     const int ctas = num_sms();
+    // Row splits per layer, proportional to the bytes the layer reads, such that the launch is ONE wave: never more items
+    // than CTAs (an extra item would double the launch time).  Floor of the ideal share first, then the spare CTAs go to
+    // the layers that were rounded down the most.
+    int64_t splits[MAXW], kblocks[MAXW];
+    double ideal[MAXW];
+    int used = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const WLayer& L = p.L[i];
+        const int tiles = L.n_tiles_n * L.n_kpairs;
+        kblocks[i] = (L.M + BLOCK_K - 1) / BLOCK_K;
+        ideal[i] = ctas * (bytes[i] / total_bytes) / tiles;
+        splits[i] = (int64_t)ideal[i];
+        if (splits[i] < 1) splits[i] = 1;
+        if (splits[i] > kblocks[i]) splits[i] = kblocks[i];
+        used += tiles * (int)splits[i];
+    }
+    for (;;) {
+        int best = -1;
+        double best_gap = 0.0;
+        for (int i = 0; i < n_items; ++i) {
+            const int tiles = p.L[i].n_tiles_n * p.L[i].n_kpairs;
+            const double gap = ideal[i] - (double)splits[i];
+            if (splits[i] < kblocks[i] && used + tiles <= ctas && gap > best_gap) {
+                best = i;
+                best_gap = gap;
+            }
+        }
+        if (best < 0) break;
+        ++splits[best];
+        used += p.L[best].n_tiles_n * p.L[best].n_kpairs;
+    }
     int first = 0;
     for (int i = 0; i < n_items; ++i) {
         WLayer& L = p.L[i];
         const int tiles = L.n_tiles_n * L.n_kpairs;
-        const int64_t kblocks = (L.M + BLOCK_K - 1) / BLOCK_K;
-        int64_t splits = (int64_t)(ctas * (bytes[i] / total_bytes) / tiles + 0.5);
-        if (splits < 1) splits = 1;
-        if (splits > kblocks) splits = kblocks;
-        L.m_per_split = ((kblocks + splits - 1) / splits) * BLOCK_K;
+        L.m_per_split = ((kblocks[i] + splits[i] - 1) / splits[i]) * BLOCK_K;
         L.splits = (int)((L.M + L.m_per_split - 1) / L.m_per_split);
         L.first_item = first;
         first += tiles * L.splits;

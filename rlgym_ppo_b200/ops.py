@@ -374,6 +374,16 @@ def policy_train_fused(net, x, M, n_actions, actions, old_logp, adv, inv_batch, 
          work=("flop", _net_flops(net, M, n_actions, True), "byte", _net_bytes(net, M, (n_actions + 7) // 8 * 8, True, True)))
 
 
+def policy_value_train_fused(pnet, vnet, x, M, n_actions, actions, old_logp, adv, inv_batch, clip, ent_coef, w_head, targets,
+                             gw_head, metrics, logp_out=None, values_out=None):
+    """Both nets of a batch in one persistent launch (work items = (net, tile), policy tiles first)."""
+    call("rlppo_policy_value_train_fused", ctypes.byref(pnet), ctypes.byref(vnet), ptr(x), int(M), int(n_actions),
+         ptr(actions), ptr(old_logp), ptr(adv), float(inv_batch), float(clip), float(ent_coef), ptr(logp_out), ptr(w_head),
+         ptr(targets), ptr(gw_head), ptr(values_out), ptr(metrics), stream_ptr(),
+         work=("flop", _net_flops(pnet, M, n_actions, True) + _net_flops(vnet, M, 1, True),
+               "byte", _net_bytes(pnet, M, (n_actions + 7) // 8 * 8, True, True) + _net_bytes(vnet, M, 0, True, False)))
+
+
 def u64_add(counter, inc):
     """*counter += inc on the device (counter: int64[1] tensor); graph-capturable."""
     call("rlppo_u64_add", ptr(counter), int(inc), stream_ptr())

@@ -198,6 +198,8 @@ class PPOLearner(object):
         self.graph_collectives = os.environ.get("RLPPO_GRAPH_COLLECTIVES", "0") == "1"
         # RLPPO_TWO_STREAMS=0: policy and value chains of a batch on one stream (see _train_chunk)
         self.two_streams = os.environ.get("RLPPO_TWO_STREAMS", "1") == "1"
+        # RLPPO_ONE_LAUNCH=0: the two nets of a batch as two fused launches (two streams) instead of one (see _train_chunk)
+        self.one_launch = os.environ.get("RLPPO_ONE_LAUNCH", "1") == "1"
         self._side_stream = None
 
     def _setup_peers(self, dev, n):
@@ -302,6 +304,19 @@ class PPOLearner(object):
         metrics = self._step_metrics()
         n = 1
         both_fused = self.policy_type == 0 and self.policy._stack.fused_ok and self.value_net._stack.fused_ok
+        if both_fused and self.one_launch:
+            # Both nets in ONE persistent launch: 2 x ceil(M/128) work items (policy tiles first) handed out dynamically to
+            # one CTA per SM, then every weight (and bias) gradient of both nets in one launch.  Two launches on two
+            # streams (RLPPO_ONE_LAUNCH=0) each end on a partly filled round of tiles: 391 tiles over 148 CTAs.
+            ps, vs = self.policy._stack, self.value_net._stack
+            wp, wv = ps.workspace(M), vs.workspace(M)
+            ops.policy_value_train_fused(ps.fused_net(x.stride(0), wp, policy_head=True), vs.fused_net(x.stride(0), wv), x, M,
+                                         self.policy.n_actions, mb["actions"], mb["old_logp"], mb["adv"], inv_b,
+                                         float(self.clip_range), float(self.ent_coef), vs.w[-1], mb["targets"], vs.gw[-1],
+                                         metrics)
+            ops.wgrad_multi(ps.fused_wgrad_items(x, wp, head_dy=wp["dz"]) + vs.fused_wgrad_items(x, wv), M)
+            self.launches += 3
+            return
         if both_fused and self.two_streams and _lib._TIMING is None:
             # The two nets are independent until the optimiser step: the value net's chain (fused kernel, weight
             # gradients) runs on a second stream -- a parallel branch of the captured graph.  Each kernel is persistent

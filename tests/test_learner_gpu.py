@@ -524,6 +524,26 @@ def test_row_partition_invariance(pkg):
             return PPOLearner(89, 90, 0, (256, 256), (256, 256), (0.1, 1.0), B, 2, lr_, lr_, 0.2, 0.01, B, DEV,
                               max_chunk_rows=chunk)
 
+    # (1) the accumulated gradients themselves: one chunk vs two vs sixteen, same batch, same weights
+    lr0 = learner(2048)
+    lr0.use_cuda_graph = False
+    lr0.policy._stack.refresh_operands()
+    lr0.value_net._stack.refresh_operands()
+    lr0._sync_lr()
+    buf0 = make_buffer(100, n, DEV)
+    idx0 = buf0.next_permutation_device()[:B].contiguous()
+    grads = {}
+    for chunk in (2048, 1024, 128):
+        lr0._grads.zero_()
+        lr0._tail.zero_()
+        lr0._backward_body(buf0, idx0, B, chunk)
+        torch.cuda.synchronize()
+        grads[chunk] = lr0._grads.clone()
+    for chunk in (1024, 128):
+        d = (grads[chunk] - grads[2048]).abs().max()
+        assert float(d) < 1e-6 * float(grads[2048].abs().max()) + 2e-7, (chunk, float(d))
+    # (2) whole learn() calls.  An element whose gradient is ~0 takes a +-lr Adam step whose sign follows the 1e-8 noise
+    # of the fp32 atomics; ONE such element out of 332k moves the update's rel-L2 by ~1e-3 (2 lr / (lr sqrt(n) ~2.5)).
     for chunk in (1024, 128):
         full, part = learner(2048), learner(chunk)
         for it in range(3):
@@ -532,8 +552,8 @@ def test_row_partition_invariance(pkg):
             rep_p = part.learn(make_buffer(100 + it, n, DEV))
             upd_f, upd_p = full._params - p0, part._params - p0
             err = float((upd_p - upd_f).norm() / upd_f.norm())
-            assert err < 2e-4, (chunk, it, err)
-            assert float((upd_p - upd_f).abs().max()) < lr_, float((upd_p - upd_f).abs().max())
+            assert err < 3e-3, (chunk, it, err)
+            assert float((upd_p - upd_f).abs().max()) < 2 * lr_, float((upd_p - upd_f).abs().max())
             assert float((part._v - full._v).norm() / full._v.norm()) < 1e-4
             for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
                 assert abs(rep_p[k] - rep_f[k]) < 1e-5 * max(1.0, abs(rep_f[k])), (k, rep_p[k], rep_f[k])
