@@ -17,6 +17,8 @@ Here every observation crosses PCIe exactly once and stays in HBM:
 collect_timesteps therefore returns DEVICE tensors; Learner.add_new_experience consumes them without a copy.
 """
 import multiprocessing as mp
+import multiprocessing.sharedctypes
+import os
 import time
 
 import numpy as np
@@ -24,7 +26,9 @@ import torch
 
 from .. import _lib, ops
 from ..util import WelfordRunningStat
+from .batched_agent import batched_agent_process
 from .env_worker import env_worker
+from .wire import WireConn
 
 
 class BatchedAgentManager(object):
@@ -47,20 +51,39 @@ class BatchedAgentManager(object):
 
     # ---- processes -------------------------------------------------------------------------------------------
     def init_processes(self, n_processes, build_env_fn, collect_metrics_fn=None, spawn_delay=None, render=False,
-                       render_delay=None, shm_buffer_size=8192):
+                       render_delay=None, shm_buffer_size=8192, transport=None):
+        """transport: "pipe" (default; multiprocessing pipes, env_worker.py) or "wire" -- the reference's own worker
+        protocol (UDP datagrams + a shared float32 slab of shm_buffer_size bytes per worker, batched_agent.py /
+        comm_consts.py), so workers written for the reference plug in unchanged.  RLPPO_WORKER_TRANSPORT overrides."""
         _lib.require_device()
         if self.device is None:
             self.device = "cuda:%d" % torch.cuda.current_device()
         methods = mp.get_all_start_methods()
         ctx = mp.get_context("forkserver" if "forkserver" in methods else "spawn")
         self.n_procs = n_processes
+        transport = os.environ.get("RLPPO_WORKER_TRANSPORT", transport or "pipe")
+        assert transport in ("pipe", "wire"), transport
+        self.transport = transport
+        if transport == "wire":
+            self.shm_size = shm_buffer_size // 4                         # floats per worker (batched_agent_manager.py:437)
+            self.shm_buffer = multiprocessing.sharedctypes.RawArray("f", n_processes * self.shm_size)
         for proc_id in range(n_processes):
-            parent, child = ctx.Pipe(duplex=True)
-            p = ctx.Process(target=env_worker, args=(child, proc_id, self.seed + proc_id, render and proc_id == 0,
-                                                     render_delay), daemon=True)
-            p.start()
-            child.close()
+            if transport == "wire":
+                parent = WireConn(self.shm_buffer, proc_id * self.shm_size * 4, self.shm_size)
+                p = ctx.Process(target=batched_agent_process,
+                                args=(proc_id, parent.endpoint, self.shm_buffer, proc_id * self.shm_size * 4, self.shm_size,
+                                      self.seed + proc_id, render and proc_id == 0, render_delay), daemon=True)
+                p.start()
+            else:
+                parent, child = ctx.Pipe(duplex=True)
+                p = ctx.Process(target=env_worker, args=(child, proc_id, self.seed + proc_id, render and proc_id == 0,
+                                                         render_delay), daemon=True)
+                p.start()
+                child.close()
             self.processes.append((p, parent))
+        if transport == "wire":
+            for _, conn in self.processes:
+                conn.accept()
         for _, conn in self.processes:
             if spawn_delay is not None:
                 time.sleep(spawn_delay)

@@ -1130,7 +1130,9 @@ int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& 
         return nout++;
     };
     const int out_pad8 = POLICY ? (p.n_actions + 7) / 8 * 8 : 0;
-    const int head_N = POLICY ? (p.n_actions + 15) / 16 * 16 : 0;
+    // the head epilogue reads the logits in 32-column chunks: the GEMM writes whole chunks (weight rows past out_pad8 are
+    // out of bounds for the TMA box = zeros), so no pass ever sees a TMEM column this launch has not written
+    const int head_N = POLICY ? (p.n_actions + 31) / 32 * 32 : 0;
     p.out_kb = POLICY ? (out_pad8 + KBLK - 1) / KBLK : 0;
     auto kb_of = [](int cols) { return (cols + KBLK - 1) / KBLK; };
     auto add_phase = [&](int kind, int layer, int n_kb, int N, int wmap, int out, int smem_out, int wait_kb, int rel_kb,

@@ -53,16 +53,20 @@ def test_learner_runs_checkpoints_and_resumes(tmp_path, capsys):
     assert learner2.agent.cumulative_timesteps >= 3000
 
 
-def test_collect_timesteps_layout():
+@pytest.mark.parametrize("transport", ["pipe", "wire"])
+def test_collect_timesteps_layout(transport):
     """collect_timesteps yields the reference's flat layout: every run ends done or truncated, next_states are the
-    following observation of the same agent inside a run, rewards match the fake env's rule for the sampled actions."""
+    following observation of the same agent inside a run, rewards match the fake env's rule for the sampled actions.
+    transport="wire": the workers are batched_agent_process speaking the reference's UDP + shared-slab protocol
+    (tests/test_wire_cpu.py pins it against the reference itself)."""
     from tests.fake_env import FakeEnv, make_env
     from rlgym_ppo_b200.batched_agents import BatchedAgentManager
     from rlgym_ppo_b200.ppo import DiscreteFF
     torch.manual_seed(0)
     mgr = BatchedAgentManager(None, seed=1, standardize_obs=False, device="cuda:0")
     try:
-        obs_size, n_act, kind = mgr.init_processes(2, make_env)
+        obs_size, n_act, kind = mgr.init_processes(2, make_env, transport=transport)
+        assert mgr.transport == transport
         assert (obs_size, n_act, kind) == (FakeEnv.OBS, FakeEnv.ACT, 0)
         mgr.policy = DiscreteFF(obs_size, n_act, (32,), "cuda:0")
         (states, actions, log_probs, rewards, next_states, dones, truncated), _, n, _ = mgr.collect_timesteps(200)
