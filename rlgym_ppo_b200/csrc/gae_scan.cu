@@ -13,6 +13,8 @@
 // HBM traffic: reads r, done, trunc, V (16 B/step with f32 flags), writes adv, vtarget, ret (12 B/step).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -597,8 +599,11 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
         if (tile_staged) {
             // 16-byte shared-memory accesses, kI3 / 4 per array (at 8 steps per thread the 32-byte thread stride makes them
             // 2-way bank conflicts: 5 arrays per tile, not what bounds the kernel)
+            // flags stay in their storage type: the 0/1 fast path only compares them, and an f32 -> f64 conversion per step
+            // (quarter-rate pipe) made the f32-flag scan SLOWER than the f64-flag one although it reads 4 bytes less
+            using TFlag = typename std::conditional<TRUNC64, double, float>::type;
             float dd[kI3], vn[kI3 + 1];
-            double tt[kI3];
+            TFlag tt[kI3];
 #pragma unroll
             for (int q = 0; q < kI3 / 4; ++q) {
                 const float4 r4 = *reinterpret_cast<const float4*>(st + (size_t)(j0 + 4 * q) * 4);
@@ -621,8 +626,8 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
 #pragma unroll
             for (int i = 0; i < kI3; ++i) {
                 P.v[i] = vn[i];
-                const bool dz = dd[i] == 0.f, tz = tt[i] == 0.0;
-                ok = ok && (dz || dd[i] == 1.f) && (tz || tt[i] == 1.0);
+                const bool dz = dd[i] == 0.f, tz = tt[i] == (TFlag)0;
+                ok = ok && (dz || dd[i] == 1.f) && (tz || tt[i] == (TFlag)1);
                 P.live |= (dz && tz ? 1u : 0u) << i;
                 P.dl[i] = sm.delta_of(P.r[i], dd[i], vn[i], vn[i + 1]);
             }
@@ -643,7 +648,7 @@ gae_scan3_kernel(const float* __restrict__ rew, const float* __restrict__ done, 
 #pragma unroll
                 for (int i = kI3 - 1; i >= 0; --i) {
                     const float nd = __fsub_rn(1.0f, dd[i]);                              // :59
-                    const double nt = 1.0 - tt[i];                                        // :60
+                    const double nt = 1.0 - (double)tt[i];                                // :60
                     const Aff f = Aff{(double)__fmul_rn(gl32, nd) * nt, (double)P.dl[i],  // :72
                                       gamma * (double)nd * nt, (double)P.r[i]};           // :69
                     agg = compose(f, agg);
