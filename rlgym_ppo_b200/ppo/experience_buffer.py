@@ -246,10 +246,14 @@ class ExperienceBuffer(object):
             self._copy_stream = torch.cuda.Stream(device=self.device)
         # (readers of dst's previous contents are done: PPOLearner.learn synchronises before it returns)
         main = torch.cuda.current_stream()
+        # `dst` may be a block the caching allocator just recycled from main-stream temporaries whose kernels are still in
+        # flight: the side-stream copy must not start before them, and the allocator must know the side stream used it
+        self._copy_stream.wait_stream(main)
         with torch.cuda.stream(self._copy_stream):
             dst.copy_(perm, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
+        dst.record_stream(self._copy_stream)
         self._pin_ev[self._pin_of_last] = ev
         main.wait_event(ev)
 

@@ -187,7 +187,9 @@ class PPOLearner(object):
         # CUDA graphs: one optimiser step (gather -> fwd/bwd -> clip+Adam) is ~25 launches of 2-170 us kernels; replaying
         # a captured graph removes the Python/ctypes/driver launch cost that otherwise dominates the example-size nets
         self.use_cuda_graph = True
+        self._nb_final = None
         self._graphs = {}
+        self.max_graphs = 16        # captured graphs kept (each owns a private memory pool); the oldest is dropped beyond
         self._graph_warm = set()
         self._idx_cur = None
         self._perm_dev = None
@@ -458,6 +460,10 @@ class PPOLearner(object):
             entry = (graph, _lib.CALLS - calls0, self.launches - launches0)
             self.launches = launches0
             _lib.CALLS = calls0
+            while len(self._graphs) >= self.max_graphs:      # oldest first: dicts keep insertion order
+                old = next(iter(self._graphs))
+                del self._graphs[old]
+                self._graph_warm.discard(old)
             self._graphs[key] = entry
         graph, n_calls, n_launch = entry
         graph.replay()
@@ -525,6 +531,19 @@ class PPOLearner(object):
         chunk = min(local, self.max_chunk_rows)
         total = len(exp)
         n_batches = total // B                                  # experience_buffer.py:100, remainder dropped
+        if R > 1 and self.dp_mode == "sharded":
+            # Every rank must run the same number of optimiser steps (each one is a rendezvous): agree on the minimum over
+            # the ranks' own buffers -- a host collective outside the iteration's graph, needed only while buffers are still
+            # filling: once EVERY rank reports a full ring (its length can no longer change) the agreed count is final and
+            # the steady state has no collective outside the optimiser launch.
+            full = int(total >= getattr(exp, "max_size", total + 1))
+            if not (self._nb_final is not None and full):
+                nb = torch.tensor([n_batches, full], dtype=torch.int64, device=self._params.device)
+                torch.distributed.all_reduce(nb, op=torch.distributed.ReduceOp.MIN)
+                n_batches = int(nb[0].item())
+                self._nb_final = n_batches if int(nb[1].item()) == 1 else None
+            else:
+                n_batches = self._nb_final
         # One `rng.permutation(total)` per epoch (experience_buffer.py:98), drawn in the reference's order, uploaded into
         # one [epochs, total] device buffer before any device work: the whole call is then a single graph replay.
         if self._perm_dev is None or self._perm_dev.shape[0] != E or self._perm_dev.shape[1] < total:
