@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     uint64_t* x_free = x_full + 1;          // [1]
     uint64_t* a_ready = x_free + 1;         // [4]
     uint64_t* acc_full = a_ready + 4;       // [2]: one per accumulator
-    uint64_t* st_done = acc_full + 2;       // [4]: the TMA store of k-block kb has finished reading shared memory
-    uint64_t* tile_full = st_done + 4;      // [2]: the producer has published the CTA's next tile index
+    uint64_t* st_done = acc_full + 2;       // [1]: the TMA stores of a phase's output have finished reading shared memory
+    uint64_t* tile_full = st_done + 1;      // [2]: the producer has published the CTA's next tile index
     uint64_t* tile_empty = tile_full + 2;   // [2]: every consumer role has read it
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 2);
     volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2]
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], 8);
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
-        for (int i = 0; i < 4; ++i) mbar_init(&st_done[i], 1);
+        mbar_init(st_done, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tile_full[i], 1);
             mbar_init(&tile_empty[i], TRAIN ? 10 : 9);   // MMA thread, (training) store thread, 8 epilogue warps
@@ -493,7 +493,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     const PhaseDesc& d = np.ph[ph];
                     const bool storing = d.out != NO_STORE;
                     const bool skip = p.dbg_nostore != 0;
-                    int pending = -1;
                     for (int kb = 0; kb < d.rel_kb; ++kb) {
                         mbar_wait(&a_ready[kb], (apar >> kb) & 1u);
                         apar ^= 1u << kb;
@@ -501,17 +500,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         RLPPO_TRACE(2, 2 * nst);
                         if (!skip) tma_store_2d(&maps.out[ni][d.out], act + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
                         bulk_commit();
-                        if (pending >= 0) {
-                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                            mbar_arrive(&st_done[pending]);
-                            RLPPO_TRACE(2, 2 * (nst - 1) + 1);
-                        }
-                        pending = kb;
                         ++nst;
                     }
-                    if (pending >= 0) {
+                    if (storing && d.rel_kb > 0) {
+                        // ONE completion signal per phase: the next epilogue that overwrites the tile starts a whole GEMM tail
+                        // (>= 1k cycles) after the last release, by which time these reads (64 KB) are long done
                         bulk_wait_read_all();
-                        mbar_arrive(&st_done[pending]);
+                        mbar_arrive(st_done);
                         RLPPO_TRACE(2, 2 * (nst - 1) + 1);
                     }
                 }
@@ -540,14 +535,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 
         uint32_t g = 0;                  // mirrors the MMA thread's GEMM counter
         uint32_t fpar = 0;               // bit a: parity of acc_full[a] to wait for next
-        uint32_t pend = 0;               // bit kb: a TMA store of k-block kb was issued since this thread last waited for it
-        uint32_t scnt = 0;               // bit kb: parity of st_done[kb] to wait for next
-        // before overwriting k-block kb of the activation tile: its last TMA store must have read it
-        auto wait_store = [&](int kb) {
-            if ((pend >> kb) & 1u) {
-                mbar_wait(&st_done[kb], (scnt >> kb) & 1u);
-                scnt ^= 1u << kb;
-                pend &= ~(1u << kb);
+        uint32_t pend = 0;               // the previous storing phase's TMA stores have not been waited for yet
+        uint32_t scnt = 0;               // parity of st_done to wait for next
+        // before a phase overwrites the activation tile in place: the stores of the tile's previous contents must have read it
+        auto wait_stores = [&]() {
+            if (pend) {
+                mbar_wait(st_done, scnt);
+                scnt ^= 1u;
+                pend = 0;
             }
         };
         int tr1 = 0;
@@ -579,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 fpar ^= 1u << acc;
                 tc_fence_after();
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: accumulator of (tile, ph) complete
+                if (TRAIN && d.smem) wait_stores();     // the tile is overwritten in place: its last stores must have read it
                 const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + acc * 256u;
                 uint8_t* dst = act;      // in place: the GEMM that read this tile has completed
                 const int li = d.layer;
@@ -627,7 +623,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         }
                         EPI_T();
                         if (d.smem) {
-                            if (TRAIN) wait_store(j);
                             EPI_T();
                             sts_chunk_sw128(dst, e.row_in_tile, c, w);
                         }
@@ -635,7 +630,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         if (!tail) {
                             release_kb(e, j);
                             EPI_T();
-                            if (TRAIN && d.out != NO_STORE) pend |= 1u << j;
                         }
                     }
                     if (tail) {
@@ -704,11 +698,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         }
                         if (d.smem) {
                             pack32(v, w);
-                            if (TRAIN) wait_store(j);
                             sts_chunk_sw128(dst, e.row_in_tile, c, w);
                         }
                         release_kb(e, j);
-                        if (d.out != NO_STORE) pend |= 1u << j;
                     }
                 } else if (d.kind == PH_DGRAD) {
                     // dL/dH_l = (dL/dH_{l+1} W_{l+1}) (.) relu'(H_l).  The bias gradients (column sums of this tile) are
@@ -720,19 +712,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     for (int j = 0; j < nkb; ++j) {
                         const int c = 2 * j + e.half;
                         float v[32];
+                        EPI_T();
                         tmem_ld32_wait(rb);
+                        EPI_T();
                         const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = ((bits >> relu_mask_bit(i)) & 1u) ? __uint_as_float(rb[i]) : 0.f;
                         if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);
+                        EPI_T();
                         if (d.smem) {
                             uint32_t w[16];
                             pack32(v, w);
-                            if (TRAIN) wait_store(j);
+                            EPI_T();
                             sts_chunk_sw128(dst, e.row_in_tile, c, w);
                         }
+                        EPI_T();
                         release_kb(e, j);
-                        if (d.out != NO_STORE) pend |= 1u << j;
+                        EPI_T();
                     }
                 } else {
                 // ---- policy head (discrete_policy.py:44-80, ppo_learner.py:153-177) ----
@@ -882,12 +878,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         uint32_t w[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) w[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
-                        wait_store(c >> 1);
                         sts_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, w);
                     }
                     for (int j = 0; j < np.out_kb; ++j) {
                         release_kb(e, j);
-                        if (d.out != NO_STORE) pend |= 1u << j;
                     }
                 } else {
                     // pass 1: row maximum (+ argmax for the deterministic branch)
@@ -1026,6 +1020,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     }
                 }
                 }
+                if (TRAIN && d.out != NO_STORE) pend = 1u;
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (tile, ph) done
           }
         }

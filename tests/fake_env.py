@@ -46,3 +46,22 @@ class FakeEnv:
 
 def make_env():
     return FakeEnv()
+
+
+class SlowFakeEnv(FakeEnv):
+    """FakeEnv whose steps take a random 0-3 ms: the processes answer in a different order on every pass, which is what
+    the manager's asynchronous batching (min_inference_size < n_procs) has to cope with."""
+
+    def __init__(self):
+        super().__init__()
+        import os
+        self._lag = np.random.RandomState(os.getpid())
+
+    def step(self, actions):
+        import time
+        time.sleep(float(self._lag.rand()) * 0.003)
+        return super().step(actions)
+
+
+def make_slow_env():
+    return SlowFakeEnv()

@@ -81,3 +81,34 @@ def test_collect_timesteps_layout(transport):
         assert run_lengths.max() <= FakeEnv.LEN
     finally:
         mgr.cleanup()
+
+
+def test_collect_timesteps_asynchronous_batching():
+    """min_inference_size < n_procs with environments of uneven speed (batched_agent_manager.py:98-123): inference runs on
+    whatever has arrived, fast processes contribute more steps, and the flat layout still holds -- every run ends done or
+    truncated, next_states chain inside a run, rewards follow the environment's rule for the recorded (state, action)."""
+    from tests.fake_env import FakeEnv, make_slow_env
+    from rlgym_ppo_b200.batched_agents import BatchedAgentManager
+    from rlgym_ppo_b200.ppo import DiscreteFF
+    torch.manual_seed(0)
+    mgr = BatchedAgentManager(None, min_inference_size=1, seed=1, standardize_obs=True, device="cuda:0")
+    try:
+        obs_size, n_act, _ = mgr.init_processes(4, make_slow_env)
+        mgr.policy = DiscreteFF(obs_size, n_act, (32,), "cuda:0")
+        total = 0
+        for _ in range(2):                                    # a second call continues the same environments
+            (states, actions, log_probs, rewards, next_states, dones, truncated), _, n, _ = mgr.collect_timesteps(300)
+            total += n
+            assert n >= 300 and states.shape == (n, FakeEnv.OBS)
+            d, tr = dones.cpu().numpy(), truncated.cpu().numpy()
+            s, ns = states.cpu().numpy(), next_states.cpu().numpy()
+            ends = (d + tr) > 0
+            assert ends[-1] and np.all(ns[:-1][~ends[:-1]] == s[1:][~ends[:-1]])
+            assert np.all(log_probs.cpu().numpy() <= 0)
+            run_lengths = np.diff(np.concatenate([[-1], np.flatnonzero(ends)]))
+            assert run_lengths.max() <= FakeEnv.LEN
+            a, r = actions.cpu().numpy(), rewards.cpu().numpy()
+            assert set(np.unique(r)) <= {0.0, 1.0} and 0 <= a.min() and a.max() < FakeEnv.ACT
+        assert mgr.cumulative_timesteps == total
+    finally:
+        mgr.cleanup()
