@@ -46,7 +46,7 @@ constexpr uint32_t KB_BYTES = TILE_M * KBLK * 2;   // 16 KB: one 64-column k-blo
 constexpr uint32_t ACT_BYTES = 4 * KB_BYTES;       // 64 KB
 constexpr uint32_t WST_BYTES = 256 * KBLK * 2;     // 32 KB: one k-block of a weight operand (<= 256 rows)
 constexpr uint32_t MN_CHUNK = 64 * KBLK * 2;       // 8 KB: 64 k-rows x 64 n-columns of an MN-major weight operand
-constexpr int MAX_NWST = 3;
+constexpr int MAX_NWST = 6;                        // ring stages (3 x 32 KB alone, up to 6 x 16 KB in a CTA pair)
 constexpr int kThreads = 352;
 constexpr int kEpiThreads = 256;
 constexpr int MAXPH = 2 * MAXL + 1;
@@ -61,7 +61,7 @@ constexpr uint32_t ROWX_FLOATS = 1280;
 constexpr uint32_t MISC_DB = MISC_ROWX + ROWX_FLOATS * 4;          // 256 floats: column sums of the value head's weight gradient
 constexpr uint32_t MISC_MASK = MISC_DB + 256 * 4;                  // ReLU bit masks: [MAXL][4 k-blocks][256 threads] words
 constexpr uint32_t MISC_BARS = MISC_MASK + MAXL * 4 * kEpiThreads * 4;
-constexpr uint32_t MISC_BYTES = MISC_BARS + 256;
+constexpr uint32_t MISC_BYTES = MISC_BARS + 384;     // 36 mbarriers + the TMEM slot + the item ring
 constexpr uint32_t SMEM_LIMIT = 232448;                            // 227 KB
 static_assert(ACT_BYTES + 2 * KB_BYTES + MISC_BYTES + 1024 + 3 * WST_BYTES <= SMEM_LIMIT,
               "an observation of <= 128 columns must leave room for a 3-stage weight ring (2 stages starve the MMA)");
@@ -122,6 +122,9 @@ struct NetP {
 struct Params {
     int64_t M;
     int num_tiles, in_kb, nwst;
+    int pair;                    // 1: launched as 2-CTA clusters (cta_group::2): see fused_mlp_kernel
+    int n_units;                 // work units per net: tiles, or tile PAIRS when pair
+    uint32_t wst_bytes;          // bytes of one ring stage (a whole weight k-block, or this CTA's half of it)
     int n_nets;                  // work items = n_nets * num_tiles: item q is tile q % num_tiles of net q / num_tiles
     NetP net[MAXNET];
     unsigned int* sched;         // [0] next item to hand out, [1] CTAs that have left (the last one zeroes both)
@@ -260,26 +263,42 @@ struct EpiCtx {
     float* s_rowx;
     uint32_t* s_mask;     // this thread's column of the mask planes: word (layer * 4 + kb) lives at s_mask[(layer*4+kb) * 256]
     uint64_t* a_ready;    // [4], one per k-block of the activation tile, 8 arrivals (epilogue warps)
+    uint64_t* a_mma;      // CTA pair: the LEADER's [4] barriers the MMA thread waits on (16 arrivals: both CTAs' warps)
+    uint32_t rank;        // CTA rank in the pair (0 = leader)
     int lane, quarter, half, row_in_tile;
 };
 
 // This warp's part of output k-block `kb` is written and its TMEM reads for it are done: one arrival per warp; the MMA
 // thread may then read that k-block as the next GEMM's A operand (and TMA-store it).
+template <bool PAIR>
 __device__ __forceinline__ void release_kb(const EpiCtx& e, int kb) {
     tc_fence_before();
     fence_proxy_async();
     __syncwarp();
-    if (e.lane == 0) mbar_arrive(e.a_ready + kb);
+    if (e.lane == 0) {
+        mbar_arrive(e.a_ready + kb);                       // this CTA's store thread (and, alone, its MMA thread)
+        if (PAIR) mbar_arrive_cta(e.a_mma + kb, 0);       // the pair's MMA thread lives in the leader CTA
+    }
 }
 
-template <bool TRAIN>
+// PAIR: the launch consists of 2-CTA clusters.  Both CTAs of a pair run the same item sequence on two different 128-row
+// tiles (tile 2u + rank of unit u); ONE thread of the leader CTA issues tcgen05.mma.cta_group::2 over both tiles (M = 256),
+// and each CTA stages only ITS half of every weight k-block (N/2 rows, or N/2 columns of an MN-major operand): half the
+// L2 -> shared-memory weight traffic and half the operand reads of B per SM -- the fused kernel's epilogues share the
+// shared-memory pipe with exactly that traffic.  Roles per CTA: producer (own x tile, own weight halves), epilogue warps
+// and store thread (own tile, unchanged); warp 1 is the MMA issuer in the leader and a relay in the peer (tells the leader
+// when the peer's operand stages have landed).  Cross-CTA signals: remote mbarrier arrives (epilogue -> a_mma, relay ->
+// pfull / px_full, consumers -> tile_empty), multicast tcgen05.commit (stage free, x free, accumulator full).
+template <bool TRAIN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_constant__ Maps maps, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* act = smem + OFF_ACT;
     uint8_t* xst = smem + OFF_XST;
     uint8_t* wring = xst + p.in_kb * KB_BYTES;
-    uint8_t* misc = wring + p.nwst * WST_BYTES;
+    uint8_t* misc = wring + p.nwst * p.wst_bytes;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     float* s_bias = reinterpret_cast<float*>(misc + MISC_BIAS);
     float* s_rowx = reinterpret_cast<float*>(misc + MISC_ROWX);
     float* s_db = reinterpret_cast<float*>(misc + MISC_DB);
@@ -293,7 +312,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     uint64_t* st_done = acc_full + 2;       // [1]: the TMA stores of a phase's output have finished reading shared memory
     uint64_t* tile_full = st_done + 1;      // [2]: the producer has published the CTA's next tile index
     uint64_t* tile_empty = tile_full + 2;   // [2]: every consumer role has read it
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 2);
+    uint64_t* a_mma = tile_empty + 2;       // [4] (pair, leader's copy is used): k-block ready in BOTH CTAs
+    uint64_t* pfull = a_mma + 4;            // [MAX_NWST] (pair, leader): the peer's half of ring stage i has landed
+    uint64_t* px_full = pfull + MAX_NWST;   // [1] (pair, leader): the peer's x tile has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(px_full + 1);
     volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -315,13 +337,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
         mbar_init(st_done, 1);
+        const int consumers = TRAIN ? 10 : 9;           // warp 1's thread, (training) store thread, 8 epilogue warps
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tile_full[i], 1);
-            mbar_init(&tile_empty[i], TRAIN ? 10 : 9);   // MMA thread, (training) store thread, 8 epilogue warps
+            mbar_init(&tile_empty[i], PAIR ? 2 * consumers + 1 : consumers);   // pair: + the peer's roles and its producer
+        }
+        if (PAIR) {
+            for (int i = 0; i < 4; ++i) mbar_init(&a_mma[i], 16);
+            for (int i = 0; i < MAX_NWST; ++i) mbar_init(&pfull[i], 1);
+            mbar_init(px_full, 1);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     // PDL: everything above ran while the previous kernel of the stream was still draining; its outputs (x, parameters)
     // are read from here on.  All CTAs of this grid are resident, so the next kernel may be scheduled as SMs free up.
     pdl_wait();
@@ -348,9 +379,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     for (int i = threadIdx.x; i < 256; i += kThreads) s_db[i] = 0.f;
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // both CTAs' barriers are initialised before either one signals the other
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) STAMP(501);
+    // a consumer role has read item slot `slot`: the leader's producer may reuse it once every role of BOTH CTAs has
+    auto ring_done = [&](int slot) {
+        if (leader) mbar_arrive(&tile_empty[slot]);
+        else mbar_arrive_cta(&tile_empty[slot], 0);
+    };
     // Work items (net, tile) are handed out dynamically from a global counter, the first net's tiles first (the policy
     // net's: they take longest, so the launch ends on the cheaper value tiles): 2 x 391 items over 148 CTAs instead of two
     // launches of 391 tiles that each end on a third, 64 %-full round.  The producer thread fetches the next item one
@@ -363,14 +400,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             int tr3 = 0;
             for (int it = 0;; ++it) {
                 const int slot = it & 1;
-                mbar_wait(&tile_empty[slot], ((it >> 1) & 1) ^ 1);
-                int q = (int)atomicAdd(p.sched, 1u);
-                if (q >= p.n_nets * p.num_tiles) q = -1;
-                tile_ring[slot] = q;
-                mbar_arrive(&tile_full[slot]);
+                int q;
+                if (leader) {
+                    mbar_wait(&tile_empty[slot], ((it >> 1) & 1) ^ 1);
+                    q = (int)atomicAdd(p.sched, 1u);
+                    if (q >= p.n_nets * p.n_units) q = -1;
+                    tile_ring[slot] = q;
+                    mbar_arrive(&tile_full[slot]);
+                    if (PAIR) {                          // the same item for the peer CTA's roles
+                        st_shared_cta_s32(const_cast<int*>(tile_ring) + slot, 1, q);
+                        mbar_arrive_cta_release(&tile_full[slot], 1);
+                    }
+                } else {
+                    mbar_wait(&tile_full[slot], (it >> 1) & 1);
+                    q = tile_ring[slot];
+                    mbar_arrive_cta(&tile_empty[slot], 0);
+                }
                 if (q < 0) break;
-                const int ni = q >= p.num_tiles ? 1 : 0;
-                const int tile = q - ni * p.num_tiles;
+                const int ni = q >= p.n_units ? 1 : 0;
+                const int unit = q - ni * p.n_units;
+                const int tile = PAIR ? 2 * unit + (int)rank : unit;      // out-of-range tiles load zeros, store nothing
                 const NetP& np = p.net[ni];
                 mbar_wait(x_free, (it & 1) ^ 1);          // GEMM 0 of the previous tile has read the staging buffer
                 mbar_expect_tx(x_full, p.in_kb * KB_BYTES);
@@ -378,15 +427,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                     tma_load_2d(&maps.x, x_full, xst + kb * KB_BYTES, kb * KBLK, tile * TILE_M);
                 for (int ph = 0; ph < np.n_ph; ++ph) {
                     const PhaseDesc& d = np.ph[ph];
+                    const int nh = PAIR ? d.N >> 1 : d.N;           // operand rows (columns if MN-major) this CTA stages
                     for (int kb = 0; kb < d.n_kb; ++kb) {
                         mbar_wait(&wempty[ws], wpar ^ 1);
-                        mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);
+                        mbar_expect_tx(&wfull[ws], (uint32_t)nh * 128u);
                         RLPPO_TRACE(3, tr3++);
+                        uint8_t* dst = wring + ws * p.wst_bytes;
                         if (d.b_mn) {
-                            for (int c = 0; c < (d.N >> 6); ++c)
-                                tma_load_2d(&maps.w[ni][d.wmap], &wfull[ws], wring + ws * WST_BYTES + c * MN_CHUNK, c * 64, kb * KBLK);
+                            for (int c = 0; c < (nh >> 6); ++c)
+                                tma_load_2d(&maps.w[ni][d.wmap], &wfull[ws], dst + c * MN_CHUNK, (int)rank * nh + c * 64, kb * KBLK);
                         } else {
-                            tma_load_2d(&maps.w[ni][d.wmap], &wfull[ws], wring + ws * WST_BYTES, kb * KBLK, 0);
+                            tma_load_2d(&maps.w[ni][d.wmap], &wfull[ws], dst, kb * KBLK, (int)rank * nh);
                         }
                         if (++ws == (uint32_t)p.nwst) {
                             ws = 0;
@@ -397,23 +448,49 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer + TMA stores =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (leader) / operand relay (peer of a pair) =====================
+        if (lane == 0 && !leader) {
+            // Peer CTA of a pair: its operand stages are filled by its own producer; tell the leader's MMA thread when each
+            // one has landed (the MMA reads both CTAs' shared memory).  Runs as far ahead as the loads do.
+            uint32_t ws = 0, wpar = 0;
+            for (int it = 0;; ++it) {
+                mbar_wait(&tile_full[it & 1], (it >> 1) & 1);
+                const int q = tile_ring[it & 1];
+                mbar_arrive_cta(&tile_empty[it & 1], 0);
+                if (q < 0) break;
+                const NetP& np = p.net[q >= p.n_units ? 1 : 0];
+                mbar_wait(x_full, it & 1);
+                mbar_arrive_cta(px_full, 0);
+                for (int ph = 0; ph < np.n_ph; ++ph) {
+                    const int n_kb = np.ph[ph].n_kb;
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        mbar_wait(&wfull[ws], wpar);
+                        mbar_arrive_cta(&pfull[ws], 0);
+                        if (++ws == (uint32_t)p.nwst) {
+                            ws = 0;
+                            wpar ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0 && leader) {
             uint32_t ws = 0, wpar = 0;
             uint32_t g = 0;                        // GEMMs issued so far: GEMM g accumulates into accumulator g & 1
             uint32_t apar = 0;                     // bit kb: parity of a_ready[kb] to wait for next (registers, not a local array)
+            uint64_t* const a_rdy = PAIR ? a_mma : a_ready;     // pair: k-blocks are ready when BOTH CTAs' warps said so
             int tr0 = 0, tr4 = 0;
             for (int it = 0;; ++it) {
                 mbar_wait(&tile_full[it & 1], (it >> 1) & 1);
                 const int q = tile_ring[it & 1];
                 mbar_arrive(&tile_empty[it & 1]);
                 if (q < 0) break;
-                const NetP& np = p.net[q >= p.num_tiles ? 1 : 0];
+                const NetP& np = p.net[q >= p.n_units ? 1 : 0];
 #pragma unroll 1
                 for (int ph = 0; ph < np.n_ph; ++ph) {
                     const PhaseDesc& d = np.ph[ph];
                     if (d.n_kb > 0) {
-                        const uint32_t idesc = umma_idesc_bf16(TILE_M, d.N, 0, d.b_mn);
+                        const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, d.N, 0, d.b_mn);
                         const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
                         RLPPO_TRACE(0, tr0++);   // MMA: start of (tile, ph)
                         for (int kb = 0; kb < d.n_kb; ++kb) {
@@ -421,53 +498,62 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             if (ph == 0) {
                                 if (kb == 0) {
                                     mbar_wait(x_full, it & 1);
+                                    if (PAIR) mbar_wait(px_full, it & 1);
                                     tc_fence_after();
                                     if (it == 0) STAMP(502);
                                 }
                                 a_addr = smem_u32(xst + kb * KB_BYTES);
                             } else {
-                                mbar_wait(&a_ready[kb], (apar >> kb) & 1u);   // k-block kb of the previous epilogue's output
+                                mbar_wait(&a_rdy[kb], (apar >> kb) & 1u);   // k-block kb of the previous epilogue's output
                                 apar ^= 1u << kb;
                                 tc_fence_after();
                                 a_addr = smem_u32(act + kb * KB_BYTES);
                             }
                             mbar_wait(&wfull[ws], wpar);
+                            if (PAIR) mbar_wait(&pfull[ws], wpar);
                             tc_fence_after();
                             RLPPO_TRACE(4, tr4++);
-                            const uint32_t b_addr = smem_u32(wring + ws * WST_BYTES);
+                            const uint32_t b_addr = smem_u32(wring + ws * p.wst_bytes);
 #pragma unroll
                             for (int k = 0; k < KBLK / 16; ++k) {
                                 const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
                                 const uint64_t bd = d.b_mn ? umma_smem_desc(b_addr + k * (16 * 128), MN_CHUNK, 1024)
                                                            : umma_smem_desc(b_addr + k * 32, 16, 1024);
-                                umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                                if (PAIR) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                                else umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
-                            umma_commit(&wempty[ws]);
+                            if (PAIR) umma_commit_pair(&wempty[ws]);
+                            else umma_commit(&wempty[ws]);
                             if (++ws == (uint32_t)p.nwst) {
                                 ws = 0;
                                 wpar ^= 1;
                             }
                         }
-                        if (ph == 0) umma_commit(x_free);      // the staging buffer can take the next tile's x
+                        if (ph == 0) {                         // the staging buffers can take the next tiles' x
+                            if (PAIR) umma_commit_pair(x_free);
+                            else umma_commit(x_free);
+                        }
                         RLPPO_TRACE(0, tr0++);   // MMA: all MMAs of (tile, ph) issued
-                        umma_commit(&acc_full[g & 1u]);
+                        if (PAIR) umma_commit_pair(&acc_full[g & 1u]);
+                        else umma_commit(&acc_full[g & 1u]);
                         ++g;
                     } else {
                         // GEMM-less phase (value net: dL/dH_L from the accumulator of the last forward GEMM, still in
                         // TMEM): consume the previous epilogue's releases, then hand the SAME accumulator back
                         RLPPO_TRACE(0, tr0++);
                         for (int kb = 0; kb < d.wait_kb; ++kb) {
-                            mbar_wait(&a_ready[kb], (apar >> kb) & 1u);
+                            mbar_wait(&a_rdy[kb], (apar >> kb) & 1u);
                             apar ^= 1u << kb;
                         }
                         RLPPO_TRACE(0, tr0++);
                         mbar_arrive(&acc_full[(g - 1u) & 1u]);
+                        if (PAIR) mbar_arrive_cta(&acc_full[(g - 1u) & 1u], 1);
                     }
                 }
                 // tail: the last epilogue's releases (barrier parity; also: every epilogue warp is done with both
                 // accumulators and the activation tile before the next tile's first GEMM / epilogue touch them)
                 for (int kb = 0; kb < np.tail_rel_kb; ++kb) {
-                    mbar_wait(&a_ready[kb], (apar >> kb) & 1u);
+                    mbar_wait(&a_rdy[kb], (apar >> kb) & 1u);
                     apar ^= 1u << kb;
                 }
             }
@@ -483,10 +569,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             for (int it = 0;; ++it) {
                 mbar_wait(&tile_full[it & 1], (it >> 1) & 1);
                 const int q = tile_ring[it & 1];
-                mbar_arrive(&tile_empty[it & 1]);
+                ring_done(it & 1);
                 if (q < 0) break;
-                const int ni = q >= p.num_tiles ? 1 : 0;
-                const int tile = q - ni * p.num_tiles;
+                const int ni = q >= p.n_units ? 1 : 0;
+                const int unit = q - ni * p.n_units;
+                const int tile = PAIR ? 2 * unit + (int)rank : unit;
                 const NetP& np = p.net[ni];
 #pragma unroll 1
                 for (int ph = 0; ph < np.n_ph; ++ph) {
@@ -521,6 +608,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
         e.s_rowx = s_rowx;
         e.s_mask = s_mask + (threadIdx.x - 64);
         e.a_ready = a_ready;
+        e.a_mma = a_mma;
+        e.rank = rank;
         e.lane = lane;
         e.quarter = warp & 3;
         e.half = (warp - 2) >> 2;
@@ -552,10 +641,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
           mbar_wait(&tile_full[it & 1], (it >> 1) & 1);
           const int q = tile_ring[it & 1];
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tile_empty[it & 1]);
+          if (lane == 0) ring_done(it & 1);
           if (q < 0) break;
-          const int ni = q >= p.num_tiles ? 1 : 0;
-          const int tile = q - ni * p.num_tiles;
+          const int ni = q >= p.n_units ? 1 : 0;
+          const int unit = q - ni * p.n_units;
+          const int tile = PAIR ? 2 * unit + (int)rank : unit;
           const NetP& np = p.net[ni];
           const float* s_bias_n = s_bias + ni * (int)BIAS_FLOATS;   // this net's bias table
           const int64_t row = (int64_t)tile * TILE_M + e.row_in_tile;
@@ -628,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         }
                         EPI_T();
                         if (!tail) {
-                            release_kb(e, j);
+                            release_kb<PAIR>(e, j);
                             EPI_T();
                         }
                     }
@@ -655,7 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             // H_L is complete in shared memory: it is TMA-stored by the next, GEMM-less phase, whose
                             // epilogue then overwrites it with dL/dH_L
                         }
-                        for (int j = 0; j < nkb; ++j) release_kb(e, j);
+                        for (int j = 0; j < nkb; ++j) release_kb<PAIR>(e, j);
                     }
                 } else if (d.kind == PH_VALUE_BWD) {
                     // dL/dH_L = dv * w (.) relu'(H_L), dw_head += dv * H_L: re-reads the accumulator of the last forward
@@ -700,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             pack32(v, w);
                             sts_chunk_sw128(dst, e.row_in_tile, c, w);
                         }
-                        release_kb(e, j);
+                        release_kb<PAIR>(e, j);
                     }
                 } else if (d.kind == PH_DGRAD) {
                     // dL/dH_l = (dL/dH_{l+1} W_{l+1}) (.) relu'(H_l).  The bias gradients (column sums of this tile) are
@@ -727,7 +817,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                             sts_chunk_sw128(dst, e.row_in_tile, c, w);
                         }
                         EPI_T();
-                        release_kb(e, j);
+                        release_kb<PAIR>(e, j);
                         EPI_T();
                     }
                 } else {
@@ -881,7 +971,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         sts_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, w);
                     }
                     for (int j = 0; j < np.out_kb; ++j) {
-                        release_kb(e, j);
+                        release_kb<PAIR>(e, j);
                     }
                 } else {
                     // pass 1: row maximum (+ argmax for the deterministic branch)
@@ -1052,10 +1142,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // neither CTA leaves (or frees TMEM) while the other may still signal it / be read by an MMA
     if (threadIdx.x == 0) STAMP(503);
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
     if (threadIdx.x == 0) {
         // every CTA has drawn its last (out-of-range) index by now: the last CTA to leave re-arms the scheduler words
@@ -1093,7 +1185,7 @@ int check_net(const rlppo_fused_net* net) {
 // Fills net slot `ni` of a launch: phase list, tensor maps of its weights and outputs.  `n` already holds the head's
 // arguments (entry points below).
 template <bool TRAIN>
-int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& maps, NetP& p) {
+int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& maps, NetP& p, bool pair) {
     int rc = check_net(net);
     if (rc) return rc;
     const int L = net->n_hidden;
@@ -1110,8 +1202,10 @@ int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& 
 
     int nw = 0, nph = 0;
     for (int i = 0; i < MAXPH; ++i) p.ph[i] = PhaseDesc{};
-    auto add_w = [&](const uint16_t* w, int64_t ld, int rows, int cols, int box_rows) -> int {
+    // K-major operands are boxes of N rows (a CTA pair: each CTA stages its N/2 rows); MN-major ones 64 x 64 chunks
+    auto add_w = [&](const uint16_t* w, int64_t ld, int rows, int cols, int box_rows, bool mn = false) -> int {
         RLPPO_CHECK_ARG(w != nullptr && ld % 8 == 0, "missing weight operand");
+        if (pair && !mn) box_rows /= 2;
         int r = make_tmap_bf16_2d(&maps.w[ni][nw], w, (uint64_t)rows, (uint64_t)cols, (uint64_t)ld, (uint32_t)box_rows);
         if (r) return r;
         ++nw;
@@ -1183,7 +1277,7 @@ int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& 
         if (POLICY) {
             const int wmap = nw;
             // dL/dH_L = dz W_head: W_head [out_pad8, hidden] itself as the MN-major operand (k = its rows)
-            rc = add_w(net->wq[L], net->wq_ld[L], out_pad8, net->hidden[L - 1], 64);
+            rc = add_w(net->wq[L], net->wq_ld[L], out_pad8, net->hidden[L - 1], 64, true);
             if (rc) return rc;
             add_phase(PH_DGRAD, L - 1, p.out_kb, net->hidden[L - 1], wmap, out, 1, 0, kb_of(net->hidden[L - 1]), 1);
         } else {
@@ -1195,7 +1289,7 @@ int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& 
             // produce dH (hidden index l-1) from dH (hidden index l): dH_l W_l with W_l [hidden_l, hidden_{l-1}] read as the
             // MN-major operand (the forward pass reads the same array K-major)
             const int wmap = nw;
-            rc = add_w(net->wq[l], net->wq_ld[l], net->hidden[l], net->hidden[l - 1], 64);
+            rc = add_w(net->wq[l], net->wq_ld[l], net->hidden[l], net->hidden[l - 1], 64, true);
             if (rc) return rc;
             out = add_out(net->dh[l - 1], net->dh_ld[l - 1], net->hidden[l - 1]);
             if (out < 0) return out;
@@ -1207,40 +1301,61 @@ int build_net(bool POLICY, const rlppo_fused_net* net, int64_t M, int ni, Maps& 
     return RLPPO_OK;
 }
 
-template <bool TRAIN>
-int launch_nets(const rlppo_fused_net* const* nets, const bool* is_policy, int n_nets, const uint16_t* x, int64_t M, Params& p,
-                cudaStream_t s) {
-    RLPPO_CHECK_ARG(n_nets >= 1 && n_nets <= MAXNET && nets[0] != nullptr, "1..%d nets per launch", MAXNET);
-    RLPPO_CHECK_ARG(M >= 1 && M < (1ll << 30) - TILE_M, "bad row count");
+// RLPPO_FUSED_PAIR=1: run the training launch as 2-CTA clusters (cta_group::2) when every GEMM splits evenly over the pair:
+// hidden widths 128 or 256 (the MN-major backward operands are staged in 64-column chunks per CTA).  OFF by default:
+// measured on B200 (profiles/README_r02.md) the pair's epilogues are faster (2.5k vs 2.9k cycles per phase: half the
+// weight traffic through each SM's shared memory) but every phase pays ~1.3k cycles more in cross-CTA signalling (remote
+// a_mma arrivals, multicast commits) on a chain that synchronises four times per 5k-cycle phase: 132 vs 123 us per launch.
+bool pair_ok(const rlppo_fused_net* const* nets, int n_nets) {
+    static const bool on = getenv("RLPPO_FUSED_PAIR") != nullptr && getenv("RLPPO_FUSED_PAIR")[0] == '1';
+    if (!on) return false;
+    for (int ni = 0; ni < n_nets; ++ni)
+        for (int l = 0; l < nets[ni]->n_hidden; ++l)
+            if (nets[ni]->hidden[l] != 128 && nets[ni]->hidden[l] != 256) return false;
+    return true;
+}
+
+template <bool TRAIN, bool PAIR>
+int launch_nets_t(const rlppo_fused_net* const* nets, const bool* is_policy, int n_nets, const uint16_t* x, int64_t M,
+                  Params& p, cudaStream_t s) {
     Maps maps;
     p.M = M;
     p.num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+    p.pair = PAIR ? 1 : 0;
+    p.n_units = PAIR ? (p.num_tiles + 1) / 2 : p.num_tiles;
     p.n_nets = n_nets;
     p.in_kb = (nets[0]->in_dim + KBLK - 1) / KBLK;
     for (int ni = 0; ni < n_nets; ++ni) {
         RLPPO_CHECK_ARG(nets[ni]->in_dim == nets[0]->in_dim && nets[ni]->in_ld == nets[0]->in_ld,
                         "nets of one launch read the same x");
-        int rc = build_net<TRAIN>(is_policy[ni], nets[ni], M, ni, maps, p.net[ni]);
+        int rc = build_net<TRAIN>(is_policy[ni], nets[ni], M, ni, maps, p.net[ni], PAIR);
         if (rc) return rc;
     }
     const rlppo_fused_net* net = nets[0];
     int rc = make_tmap_bf16_2d(&maps.x, x, (uint64_t)M, (uint64_t)net->in_dim, (uint64_t)net->in_ld, TILE_M);
     if (rc) return rc;
 
-    // shared memory: activation tile + x staging (in_kb k-blocks) + as deep a weight ring as fits + misc
+    // shared memory: activation tile + x staging (in_kb k-blocks) + as deep an operand ring as fits + misc
+    p.wst_bytes = PAIR ? WST_BYTES / 2 : WST_BYTES;
     const uint32_t fixed = ACT_BYTES + (uint32_t)p.in_kb * KB_BYTES + MISC_BYTES + 1024;
-    p.nwst = (int)((SMEM_LIMIT - fixed) / WST_BYTES);
-    if (p.nwst > MAX_NWST) p.nwst = MAX_NWST;
+    p.nwst = (int)((SMEM_LIMIT - fixed) / p.wst_bytes);
+    if (p.nwst > (PAIR ? MAX_NWST : 3)) p.nwst = PAIR ? MAX_NWST : 3;
     RLPPO_CHECK_ARG(p.nwst >= 2, "fused path: shared memory budget");
-    const uint32_t smem_bytes = fixed + (uint32_t)p.nwst * WST_BYTES;
+    const uint32_t smem_bytes = fixed + (uint32_t)p.nwst * p.wst_bytes;
     static bool configured = false;
-    auto kfn = fused_mlp_kernel<TRAIN>;
+    auto kfn = fused_mlp_kernel<TRAIN, PAIR>;
     if (!configured) {
         RLPPO_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         configured = true;
     }
-    const int items = p.num_tiles * n_nets;
-    const int grid = items < num_sms() ? items : num_sms();
+    const int items = p.n_units * n_nets;
+    int grid;
+    if (PAIR) {
+        const int pairs = num_sms() / 2;
+        grid = 2 * (items < pairs ? items : pairs);
+    } else {
+        grid = items < num_sms() ? items : num_sms();
+    }
     // scheduler words: a pool of self-resetting {next tile, departures} pairs, handed out round-robin so that launches that
     // may overlap (the two nets of a batch on two streams; consecutive launches under PDL) never share a pair
     {
@@ -1264,7 +1379,7 @@ int launch_nets(const rlppo_fused_net* const* nets, const bool* is_policy, int n
         RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 3072 * sizeof(unsigned long long), s));
         p.trace = d_trace;
     }
-    RLPPO_CUDA(launch_pdl(kfn, dim3(grid), dim3(kThreads), smem_bytes, s, maps, p));
+    RLPPO_CUDA(launch_pdl_cluster(kfn, dim3(grid), dim3(kThreads), smem_bytes, s, PAIR ? 2 : 1, maps, p));
     if (tracing) {
         static unsigned long long h[3072];
         RLPPO_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -1288,6 +1403,19 @@ int launch_nets(const rlppo_fused_net* const* nets, const bool* is_policy, int n
             fprintf(stderr, "  fine #%d at=%llu (+%llu)\n", i, h[2560 + i] - t0, i ? h[2560 + i] - h[2560 + i - 1] : 0ull);
     }
     return RLPPO_OK;
+}
+
+template <bool TRAIN>
+int launch_nets(const rlppo_fused_net* const* nets, const bool* is_policy, int n_nets, const uint16_t* x, int64_t M, Params& p,
+                cudaStream_t s) {
+    RLPPO_CHECK_ARG(n_nets >= 1 && n_nets <= MAXNET && nets[0] != nullptr, "1..%d nets per launch", MAXNET);
+    RLPPO_CHECK_ARG(M >= 1 && M < (1ll << 30) - TILE_M, "bad row count");
+    for (int ni = 0; ni < n_nets; ++ni) {
+        int rc = check_net(nets[ni]);
+        if (rc) return rc;
+    }
+    if (TRAIN && pair_ok(nets, n_nets)) return launch_nets_t<TRAIN, TRAIN>(nets, is_policy, n_nets, x, M, p, s);
+    return launch_nets_t<TRAIN, false>(nets, is_policy, n_nets, x, M, p, s);
 }
 
 void fill_policy_train(NetP& n, int n_actions, const float* actions, const float* old_logp, const float* adv,

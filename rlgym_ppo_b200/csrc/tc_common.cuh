@@ -169,6 +169,64 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): one thread of the leader CTA issues an MMA that spans both SMs of a 2-CTA cluster -------
+// (tools/microbench/cta_pair_gemm.cu is the minimal working example these were lifted from.)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory address of THIS CTA) as seen in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(cta));
+    return ra;
+}
+// arrive on the mbarrier at the same offset in CTA `cta` (default semantics, the form CUTLASS's ClusterBarrier::arrive
+// uses).  NOT the cluster-scope release: measured in the fused kernel, `mbarrier.arrive.release.cluster` from the epilogue
+// warps cost ~1k cycles per arrival (forward epilogue 3.0k -> 7.3k cycles).  What the signal guards is shared memory the
+// tensor core reads through the async proxy, which the sender has already fenced with fence.proxy.async.
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(bar, cta)) : "memory");
+}
+// the same with release at cluster scope: publishes this thread's earlier st.shared::cluster to the waiter
+__device__ __forceinline__ void mbar_arrive_cta_release(uint64_t* bar, uint32_t cta) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(bar, cta)) : "memory");
+}
+__device__ __forceinline__ void st_shared_cta_s32(int* p, uint32_t cta, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(mapa_u32(p, cta)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {   // whole warp, in BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {     // whole warp, in BOTH CTAs
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs: 2 x 128 rows] * B[smem of both CTAs: 2 x N/2 rows]; leader CTA only
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
 // ---- host: tensor maps ----------------------------------------------------------------------------------------
 // 2-D bf16 tensor [rows, cols] with row stride ld (elements), box [box_rows, 64 cols] (128 B), 128B swizzle,
 // out-of-bounds elements read as zero.

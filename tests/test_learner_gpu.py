@@ -665,3 +665,18 @@ def test_late_next_states_path_matches_fifo_oracle(pkg):
         finally:
             os.environ.pop("RLPPO_LATE_NEXT_STATES", None)
     assert np.array_equal(results[0][1]["next_states"], results[1][1]["next_states"])
+
+
+def test_cta_pair_mode_matches(pkg):
+    """RLPPO_FUSED_PAIR=1 (the training launch as 2-CTA clusters, tcgen05.mma.cta_group::2, each CTA staging half of every
+    weight k-block) gives the same results as the default single-CTA launch: the fused-vs-layerwise and golden tests re-run
+    in a fresh process with the switch on (it is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, RLPPO_FUSED_PAIR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_learner_gpu.py", "-m", "gpu", "-x", "-q", "-k",
+                        "fused_kernels_match_layerwise or policy_and_value_golden or ppo_learner_golden or row_partition"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
