@@ -67,10 +67,10 @@ TENSOR_BOUND = ("rlppo_policy_value_train_fused", "rlppo_policy_train_fused", "r
                 "rlppo_linear_fwd_split", "rlppo_linear_dgrad_split", "rlppo_linear_wgrad_split",
                 "rlppo_policy_head_train_split", "rlppo_policy_head_sample_split")
 # C-ABI entry point -> kernel name in the ncu reports (profiles/ncu_traffic.json is keyed by kernel name)
-KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_value_train_fused": "fused_mlp_kernel<1>",
-             "rlppo_policy_train_fused": "fused_mlp_kernel<1>",
-             "rlppo_value_train_fused": "fused_mlp_kernel<1>", "rlppo_value_infer_fused": "fused_mlp_kernel<0>",
-             "rlppo_policy_infer_fused": "fused_mlp_kernel<0>",
+KERNEL_OF = {"rlppo_wgrad_multi": "wgrad_multi_kernel", "rlppo_policy_value_train_fused": "fused_duo_kernel",
+             "rlppo_policy_train_fused": "fused_duo_kernel",
+             "rlppo_value_train_fused": "fused_duo_kernel", "rlppo_value_infer_fused": "fused_mlp_kernel<0, 0>",
+             "rlppo_policy_infer_fused": "fused_mlp_kernel<0, 0>",
              "rlppo_gather_batch": "gather_kernel", "rlppo_gae_f32": "gae_scan3_kernel<1, 1>",
              "rlppo_linear_wgrad": "wgrad_kernel<256>", "rlppo_linear_fwd": "rowgemm_kernel<256, 0>",
              "rlppo_linear_dgrad": "rowgemm_kernel<256, 1>", "rlppo_linear_dgrad_db": "rowgemm_kernel<256, 1>",

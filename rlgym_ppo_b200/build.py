@@ -28,7 +28,7 @@ def _nvcc():
 
 def _digest():
     h = hashlib.sha256()
-    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h")))
+    files = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h", ".inc")))
     files = [os.path.join(CSRC, f) for f in files] + [os.path.join(HERE, "..", "include", "rlppo.h")]
     for f in files:
         with open(f, "rb") as fh:

@@ -669,447 +669,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 uint8_t* dst = act;      // in place: the GEMM that read this tile has completed
                 const int li = d.layer;
 
-                if (d.kind == PH_FWD || d.kind == PH_FWD_VALUE) {
-                    const int nkb = d.N >> 6;
-                    const bool tail = (d.kind == PH_FWD_VALUE);
-                    float dq[4] = {0.f, 0.f, 0.f, 0.f};
-                    uint32_t rb[32];
-                    tmem_ld32_issue(trow + e.half * 32, rb);
-#pragma unroll 1
-                    for (int j = 0; j < nkb; ++j) {
-                        const int c = 2 * j + e.half;
-                        float v[32];
-                        EPI_T();
-                        tmem_ld32_wait(rb);
-                        EPI_T();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
-                        if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);   // next chunk in flight during this one
-                        // biases as 8 x 128-bit shared loads (one wavefront each; the MMA's operand fetch owns most of the
-                        // shared-memory bandwidth while this runs); bias add in fp32, ReLU inside the bf16 pack
-                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias_n + li * 256 + c * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b4 = sb4[q];
-                            v[q * 4 + 0] += b4.x;
-                            v[q * 4 + 1] += b4.y;
-                            v[q * 4 + 2] += b4.z;
-                            v[q * 4 + 3] += b4.w;
-                        }
-                        uint32_t w[16];
-                        pack32_relu(v, w);
-                        if (TRAIN) e.s_mask[(li * 4 + j) * kEpiThreads] = relu_mask32(w);
-                        if (tail) {
-                            // value head dot product on the bf16-rounded activations (what a GEMM would read)
-                            const float4* wv4 = reinterpret_cast<const float4*>(s_bias_n + MAXL * 256 + c * 32);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 w4 = wv4[q];
-                                dq[0] = fmaf(__uint_as_float(w[2 * q] << 16), w4.x, dq[0]);
-                                dq[1] = fmaf(__uint_as_float(w[2 * q] & 0xFFFF0000u), w4.y, dq[1]);
-                                dq[2] = fmaf(__uint_as_float(w[2 * q + 1] << 16), w4.z, dq[2]);
-                                dq[3] = fmaf(__uint_as_float(w[2 * q + 1] & 0xFFFF0000u), w4.w, dq[3]);
-                            }
-                        }
-                        EPI_T();
-                        if (d.smem) {
-                            EPI_T();
-                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
-                        }
-                        EPI_T();
-                        if (!tail) {
-                            release_kb<PAIR>(e, j);
-                            EPI_T();
-                        }
-                    }
-                    if (tail) {
-                        // ---- value head: v = H_L . w + b (value_estimator.py:27), MSE loss and its gradient ----
-                        float* rowx = e.s_rowx;
-                        rowx[e.half * 128 + e.row_in_tile] = (dq[0] + dq[1]) + (dq[2] + dq[3]);
-                        epi_bar_sync();
-                        const float bhead = np.bias[MAXL] != nullptr ? __ldg(np.bias[MAXL]) : 0.f;
-                        const float val = rowx[e.row_in_tile] + rowx[128 + e.row_in_tile] + bhead;
-                        if (e.half == 0 && row_ok && np.values_out != nullptr) np.values_out[row] = val;
-                        if (TRAIN) {
-                            float dv = 0.f;
-                            if (row_ok) {
-                                const float err = val - __ldg(np.targets + row);
-                                dv = 2.0f * np.inv_batch * err;                     // d(MSE * mb/B)/dv, ppo_learner.py:176
-                                if (e.half == 0) {
-                                    vm0 += err * err;
-                                    vrows += 1.f;
-                                    vm1 += dv;                                     // head bias gradient
-                                }
-                            }
-                            dv_keep = dv;
-                            // H_L is complete in shared memory: it is TMA-stored by the next, GEMM-less phase, whose
-                            // epilogue then overwrites it with dL/dH_L
-                        }
-                        for (int j = 0; j < nkb; ++j) release_kb<PAIR>(e, j);
-                    }
-                } else if (d.kind == PH_VALUE_BWD) {
-                    // dL/dH_L = dv * w (.) relu'(H_L), dw_head += dv * H_L: re-reads the accumulator of the last forward
-                    // GEMM, which is still in TMEM; the ReLU mask is the one the forward epilogue kept
-                    const int nkb = d.N >> 6;
-                    const float dv = dv_keep;
-#pragma unroll 1
-                    for (int j = 0; j < nkb; ++j) {
-                        const int c = 2 * j + e.half;
-                        float v[32], t[32];
-                        tmem_ld32(trow + c * 32, v);
-                        const float4* sb4 = reinterpret_cast<const float4*>(s_bias_n + li * 256 + c * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b4 = sb4[q];
-                            v[q * 4 + 0] += b4.x;
-                            v[q * 4 + 1] += b4.y;
-                            v[q * 4 + 2] += b4.z;
-                            v[q * 4 + 3] += b4.w;
-                        }
-                        uint32_t w[16];
-                        pack32_relu(v, w);                               // H_L as the forward pass rounded it
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            t[2 * i] = dv * __uint_as_float(w[i] << 16);
-                            t[2 * i + 1] = dv * __uint_as_float(w[i] & 0xFFFF0000u);
-                        }
-                        db_add(c, warp_colsum32(t, e.lane));     // value head weight gradient (slot MAXL)
-                        const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
-                        const float4* wv4 = reinterpret_cast<const float4*>(s_bias_n + MAXL * 256 + c * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 w4 = wv4[q];
-                            const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = q * 4 + u;
-                                v[i] = ((bits >> relu_mask_bit(i)) & 1u) ? dv * ww[u] : 0.f;
-                            }
-                        }
-                        if (d.smem) {
-                            pack32(v, w);
-                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
-                        }
-                        release_kb<PAIR>(e, j);
-                    }
-                } else if (d.kind == PH_DGRAD) {
-                    // dL/dH_l = (dL/dH_{l+1} W_{l+1}) (.) relu'(H_l).  The bias gradients (column sums of this tile) are
-                    // formed by the weight-gradient kernel from the bf16 tile it reads anyway (rlppo_wgrad_multi)
-                    const int nkb = d.N >> 6;
-                    uint32_t rb[32];
-                    tmem_ld32_issue(trow + e.half * 32, rb);
-#pragma unroll 1
-                    for (int j = 0; j < nkb; ++j) {
-                        const int c = 2 * j + e.half;
-                        float v[32];
-                        EPI_T();
-                        tmem_ld32_wait(rb);
-                        EPI_T();
-                        const uint32_t bits = e.s_mask[(li * 4 + j) * kEpiThreads];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = ((bits >> relu_mask_bit(i)) & 1u) ? __uint_as_float(rb[i]) : 0.f;
-                        if (j + 1 < nkb) tmem_ld32_issue(trow + (c + 2) * 32, rb);
-                        EPI_T();
-                        if (d.smem) {
-                            uint32_t w[16];
-                            pack32(v, w);
-                            EPI_T();
-                            sts_chunk_sw128(dst, e.row_in_tile, c, w);
-                        }
-                        EPI_T();
-                        release_kb<PAIR>(e, j);
-                        EPI_T();
-                    }
-                } else {
-                // ---- policy head (discrete_policy.py:44-80, ppo_learner.py:153-177) ----
-                // Two threads per row: the warp pair that owns the row's TMEM lanes splits every 32-column chunk into
-                // its lower / upper 16 columns; the row-wise quantities (max, sum-exp, ...) are combined through shared
-                // memory behind a 64-thread named barrier per warp pair.  Three branch-free passes re-read the logits from
-                // TMEM.  The bias slots of the padding columns hold -1e30, so a padding column's exp() is 0 and its
-                // d(logit) is 0 without a bounds test per element.
-                const int nact = np.n_actions;
-                const int nch = (nact + 31) >> 5;          // <= 4
-                const int hoff = e.half * 16;              // this thread's 16 columns inside each chunk
-                const float* sb = s_bias_n + MAXL * 256;
-                const float kLogMin = -25.328436022934504f;   // ln(1e-11)
-                float* xch = e.s_rowx;                        // exchange planes: [0,256) max, [256,512) argmax, [512,1280) S/T/z_a
-                if (TRAIN) {
-                    const int nch_out = np.out_kb * 2;          // chunks of the d(logits) tile (whole k-blocks)
-                    const int prow = e.half * 128 + e.row_in_tile, orow = (e.half ^ 1) * 128 + e.row_in_tile;
-                    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(2 + e.quarter) : "memory"); };
-                    int a = 0;
-                    float old_lp = 0.f, advv = 0.f;
-                    if (row_ok) {
-                        a = (int)__ldg(np.actions + row);             // acts.long(), discrete_policy.py:71
-                        a = min(max(a, 0), nact - 1);
-                        old_lp = __ldg(np.old_logp + row);
-                        advv = __ldg(np.adv + row);
-                    }
-                    // pass 1: row maximum
-                    float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-                    for (int c = 0; c < nch; ++c) {
-                        float v[16];
-                        tmem_ld16(trow + c * 32 + hoff, v);
-                        const float4* b4p = reinterpret_cast<const float4*>(sb + c * 32 + hoff);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 b4 = b4p[q];
-                            mq[0] = fmaxf(mq[0], v[4 * q + 0] + b4.x);
-                            mq[1] = fmaxf(mq[1], v[4 * q + 1] + b4.y);
-                            mq[2] = fmaxf(mq[2], v[4 * q + 2] + b4.z);
-                            mq[3] = fmaxf(mq[3], v[4 * q + 3] + b4.w);
-                        }
-                    }
-                    float mx = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
-                    xch[prow] = mx;
-                    pair_sync();
-                    mx = fmaxf(mx, xch[orow]);
-                    // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
-                    float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
-                    float zs_a = 0.f;
-#pragma unroll 1
-                    for (int c = 0; c < nch; ++c) {
-                        float v[16];
-                        tmem_ld16(trow + c * 32 + hoff, v);
-                        const float4* b4p = reinterpret_cast<const float4*>(sb + c * 32 + hoff);
-                        const int arel = a - (c * 32 + hoff);             // this row's action column relative to the chunk
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 b4 = b4p[q];
-                            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int i = 4 * q + u;
-                                const float zs = (v[i] + bb[u]) - mx;
-                                const float ej = __expf(zs);              // 0 for the padding (zs ~ -1e30)
-                                Sq[u] += ej;
-                                Tq[u] = fmaf(ej, zs, Tq[u]);
-                                if (i == arel) zs_a = zs;                 // exactly one of the two threads holds column a
-                            }
-                        }
-                    }
-                    float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
-                    float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
-                    {
-                        float* x3 = xch + 512;   // [3][half][row]
-                        x3[prow] = S;
-                        x3[256 + prow] = T;
-                        x3[512 + prow] = zs_a;
-                        pair_sync();
-                        // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
-                        const float So = x3[orow], To = x3[256 + orow];
-                        S = e.half == 0 ? S + So : So + S;
-                        T = e.half == 0 ? T + To : To + T;
-                        zs_a += x3[512 + orow];
-                    }
-                    const float logS = logf(S);
-                    const float mxs = mx + logS;
-                    // Entropy of the CLAMPED probabilities (discrete_policy.py:74-78) from the two sums:
-                    //   -sum s_j log s_j = logS - T/S.  Clamping to [1e-11, 1] changes each term by at most
-                    //   1e-11 * ln(1e11) = 2.5e-10, i.e. below fp32 resolution of the sum.
-                    const float Hent = logS - T / S;
-                    const float Gs = 1.0f - Hent;                       // sum_j s_j (log s_j + 1)
-                    const float ls_a = zs_a - logS;
-                    const float lp_a = fminf(fmaxf(ls_a, kLogMin), 0.f);   // log clamp(s_a, 1e-11, 1), :74-77
-                    const float s_a = __expf(ls_a);
-                    const float p_a = fminf(fmaxf(s_a, 1e-11f), 1.0f);
-                    const float log_ratio = lp_a - old_lp;
-                    const float ratio = expf(log_ratio);                            // ppo_learner.py:153
-                    const float lo = 1.0f - np.clip, hi = 1.0f + np.clip;
-                    const float clipped = fminf(fmaxf(ratio, lo), hi);              // :154-156
-                    const float s1 = ratio * advv, s2 = clipped * advv;
-                    const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-                    const float d1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);      // torch.min backward, ties 0.5/0.5
-                    const float d2 = s1 > s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
-                    const float okf = row_ok ? 1.f : 0.f;
-                    const float d_logp = -np.inv_batch * advv * (d1 + d2 * in_range) * ratio * okf;
-                    const float ga = (ls_a >= kLogMin) ? d_logp / p_a : 0.f;        // through log(clamp(s_a))
-                    const float cw = np.ent_coef * np.inv_batch * okf;
-                    const float G = cw * Gs + ga * s_a;
-                    if (row_ok && e.half == 0) {
-                        m0 += Hent;
-                        m1 += (ratio - 1.0f) - log_ratio;                           // :161
-                        m2 += fabsf(ratio - 1.0f) > np.clip ? 1.f : 0.f;             // :166
-                        m3 += fminf(s1, s2);
-                        mrows += 1.f;
-                        if (np.logp_out) np.logp_out[row] = lp_a;
-                    }
-                    // pass 3: dz_j = s_j (g_j - G), g_j = cw (log s_j + 1) + [j = a] ga  -> bf16 tile (A operand of the
-                    // first dgrad GEMM and of the head's weight-gradient GEMM, which also forms the head's bias gradient).
-                    // The reference's clamp stops the entropy term's gradient where s_j < 1e-11; that term is then below
-                    // 1e-11 * 25 * cw and is kept (|difference| < 2.5e-10 * ent_coef / B per logit).
-                    const float cwG = cw - G;
-#pragma unroll 1
-                    for (int c = 0; c < nch_out; ++c) {
-                        float v[16];
-                        if (c < nch) {
-                            tmem_ld16(trow + c * 32 + hoff, v);
-                            const float4* b4p = reinterpret_cast<const float4*>(sb + c * 32 + hoff);
-                            const int arel = a - (c * 32 + hoff);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float4 b4 = b4p[q];
-                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const int i = 4 * q + u;
-                                    const float ls = (v[i] + bb[u]) - mxs;          // log softmax (<= 0); ~ -1e30 for the padding
-                                    const float sj = __expf(ls);
-                                    float o = sj * fmaf(cw, fmaxf(ls, kLogMin), cwG);
-                                    if (i == arel) o = fmaf(sj, ga, o);
-                                    v[i] = o;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-                        }
-                        uint32_t w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) w[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
-                        sts_chunk16_sw128(dst, e.row_in_tile, c * 2 + e.half, w);
-                    }
-                    for (int j = 0; j < np.out_kb; ++j) {
-                        release_kb<PAIR>(e, j);
-                    }
-                } else {
-                    // pass 1: row maximum (+ argmax for the deterministic branch)
-                    const int a = -1;
-                    float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                    int aq[4] = {0, 0, 0, 0};
-#pragma unroll 1
-                    for (int c = 0; c < nch; ++c) {
-                        float v[16];
-                        tmem_ld16(trow + c * 32 + hoff, v);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int col = c * 32 + hoff + i;
-                            const float zz = col < nact ? v[i] + sb[col] : -INFINITY;
-                            const bool gt = zz > mq[i & 3];
-                            mq[i & 3] = gt ? zz : mq[i & 3];
-                            aq[i & 3] = gt ? col : aq[i & 3];
-                        }
-                    }
-                    float mx = mq[0];
-                    int argmax = aq[0];
-#pragma unroll
-                    for (int q = 1; q < 4; ++q) {
-                        const bool better = mq[q] > mx || (mq[q] == mx && aq[q] < argmax);   // ties: lowest column
-                        mx = better ? mq[q] : mx;
-                        argmax = better ? aq[q] : argmax;
-                    }
-                    xch[e.half * 128 + e.row_in_tile] = mx;
-                    int* xchi = reinterpret_cast<int*>(xch) + 256;   // second plane: argmax (ints)
-                    xchi[e.half * 128 + e.row_in_tile] = argmax;
-                    epi_bar_sync();
-                    {
-                        const float mo = xch[(e.half ^ 1) * 128 + e.row_in_tile];
-                        const int ao = xchi[(e.half ^ 1) * 128 + e.row_in_tile];
-                        const bool better = mo > mx || (mo == mx && ao < argmax);
-                        mx = better ? mo : mx;
-                        argmax = better ? ao : argmax;
-                    }
-                    epi_bar_sync();   // everyone has read the maxima before the plane is reused
-                    // pass 2: S = sum e_j, T = sum e_j (z_j - mx), z_a   (e_j = exp(z_j - mx))
-                    float Sq[4] = {0.f, 0.f, 0.f, 0.f}, Tq[4] = {0.f, 0.f, 0.f, 0.f};
-                    float zs_a = 0.f;
-#pragma unroll 1
-                    for (int c = 0; c < nch; ++c) {
-                        float v[16];
-                        tmem_ld16(trow + c * 32 + hoff, v);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int col = c * 32 + hoff + i;
-                            const float zs = col < nact ? v[i] + sb[col] - mx : -INFINITY;
-                            const float ej = __expf(zs);                      // exp(-inf) = 0 for the padding
-                            Sq[i & 3] += ej;
-                            Tq[i & 3] = fmaf(ej, col < nact ? zs : 0.f, Tq[i & 3]);
-                            zs_a += col == a ? zs : 0.f;                      // exactly one of the two threads holds column a
-                        }
-                    }
-                    float S = (Sq[0] + Sq[1]) + (Sq[2] + Sq[3]);
-                    float T = (Tq[0] + Tq[1]) + (Tq[2] + Tq[3]);
-                    {
-                        float* x3 = xch + 512;   // [3][half][row]
-                        x3[0 * 256 + e.half * 128 + e.row_in_tile] = S;
-                        x3[1 * 256 + e.half * 128 + e.row_in_tile] = T;
-                        x3[2 * 256 + e.half * 128 + e.row_in_tile] = zs_a;
-                        epi_bar_sync();
-                        const int o = (e.half ^ 1) * 128 + e.row_in_tile;
-                        // fixed order (lower half + upper half) so both threads of a row get bit-identical sums
-                        const float S0 = e.half == 0 ? S : x3[o], S1 = e.half == 0 ? x3[o] : S;
-                        const float T0 = e.half == 0 ? T : x3[256 + o], T1 = e.half == 0 ? x3[256 + o] : T;
-                        S = S0 + S1;
-                        T = T0 + T1;
-                        zs_a += x3[512 + o];
-                    }
-                    const float logS = logf(S);
-                    const float mxs = mx + logS;
-                    // ---- sampling (DiscreteFF.get_action, discrete_policy.py:44-62): the inverse-CDF scan is
-                    // sequential over the row, so the lower-half thread does it alone over all columns ----
-                    if (e.half == 0) {
-                        float Pq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                        for (int c = 0; c < nch; ++c) {
-                            float v[32];
-                            tmem_ld32(trow + c * 32, v);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int col = c * 32 + i;
-                                const float pj = fminf(fmaxf(__expf(v[i] + sb[col & 255] - mxs), 1e-11f), 1.0f);
-                                Pq[i & 3] += col < nact ? pj : 0.f;
-                            }
-                        }
-                        const float P = (Pq[0] + Pq[1]) + (Pq[2] + Pq[3]);
-                        int actn = nact - 1;
-                        float pa = 0.f;
-                        if (np.deterministic) {
-                            actn = argmax;
-                            pa = fminf(fmaxf(__expf(-logS), 1e-11f), 1.0f);
-                        } else {
-                            float u = 0.f;
-                            if (row_ok) {
-                                if (np.u_inject != nullptr) {
-                                    u = __ldg(np.u_inject + row);
-                                } else {
-                                    const uint64_t ctr = np.offset + (np.d_offset != nullptr ? (uint64_t)__ldg(np.d_offset) : 0ull) +
-                                                         (uint64_t)row;
-                                    const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u),
-                                                                  make_uint2((uint32_t)np.seed, (uint32_t)(np.seed >> 32)));
-                                    u = (float)(r.x >> 8) * (1.0f / 16777216.0f);
-                                }
-                            }
-                            const float thr = u * P;   // torch.multinomial normalises what it is given
-                            float run = 0.f, plast = 0.f;
-                            int found = 0;
-#pragma unroll 1
-                            for (int c = 0; c < nch; ++c) {
-                                float v[32];
-                                tmem_ld32(trow + c * 32, v);
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const int col = c * 32 + i;
-                                    const bool in = col < nact;
-                                    const float pj = fminf(fmaxf(__expf(v[i] + sb[col & 255] - mxs), 1e-11f), 1.0f);
-                                    run += in ? pj : 0.f;               // the running sum is inherently sequential
-                                    plast = in ? pj : plast;
-                                    const bool hit = in && !found && run > thr;
-                                    actn = hit ? col : actn;
-                                    pa = hit ? pj : pa;
-                                    found |= hit ? 1 : 0;
-                                }
-                            }
-                            pa = found ? pa : plast;
-                        }
-                        if (row_ok) {
-                            if (np.actions_out) np.actions_out[row] = (float)actn;   // batched_agent_manager.py:204
-                            if (np.actions_i64_out) np.actions_i64_out[row] = (int64_t)actn;
-                            if (np.logp_out) np.logp_out[row] = logf(pa);            // :60
-                        }
-                    }
-                }
-                }
+#define RLPPO_RELEASE_KB(j) release_kb<PAIR>(e, j)
+#include "fused_epilogue.inc"
+#undef RLPPO_RELEASE_KB
                 if (TRAIN && d.out != NO_STORE) pend = 1u;
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (tile, ph) done
           }
@@ -1165,6 +727,401 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
             if (np.policy || np.gw_head == nullptr) continue;
             for (int c = threadIdx.x; c < np.H[np.L - 1]; c += kThreads) atomicAdd(np.gw_head + c, s_db[c]);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused_duo_kernel: CTA pairs with TWO tiles in flight per CTA (training).
+//
+// The single-tile kernels above are a chain per tile: GEMM -> epilogue -> GEMM ..., in which the tensor core waits for the
+// epilogue's k-blocks and the epilogue warps wait for the GEMM's tail (and, in a CTA pair, for a cross-SM round trip) at
+// every phase boundary: ~13 k of a tile's 36 k cycles.  Here every CTA keeps two tiles ("slots") resident, each with its
+// own activation buffer (in place, as before) and its own 256-column TMEM accumulator, and all roles walk the same
+// deterministic sequence  step n -> slot n & 1 -> that slot's next phase : while the eight epilogue warps work on one
+// slot, the GEMM of the other slot's next phase runs, so MMA time, weight latency and the pair's signalling latency hide
+// behind an epilogue instead of sitting between two of them.  What makes the second 64 KB buffer fit is the pair: each
+// CTA stages only its N/2 half of a weight k-block (16 KB stages, a 3-deep ring; both CTAs' TMA loads complete on the
+// LEADER's barrier -- cp.async.bulk.tensor.cta_group::2 -- so a stage's round trip is MMA completion -> multicast commit ->
+// TMA from L2, with no relay hop: with a relay the r02ag trace showed 4k cycles per GEMM step for 2k cycles of MMAs), and
+// the x tile of
+// an item is loaded straight into the slot's activation buffer (no staging buffer; its latency hides behind the other
+// slot too).  A GEMM waits for the WHOLE previous epilogue of its slot (one barrier per slot, no k-block hand-over).
+// Roles per CTA: producer (x tiles, weight halves), warp 1 = MMA issuer (leader only), eight epilogue warps, store
+// thread.  Items (net, pair of tiles) come from the same global counter; a slot draws a new item when its
+// current one is finished, in walk order, so every role of both CTAs replays the same assignment.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t DUO_STAGE = WST_BYTES / 2;                      // 16 KB: this CTA's half of a weight k-block
+constexpr int DUO_NST = 3;
+constexpr int DUO_MAXL = 3;                                        // hidden layers (mask planes per slot)
+constexpr uint32_t DUO_MASK_SLOT = DUO_MAXL * 4 * kEpiThreads * 4; // ReLU mask planes of one slot
+constexpr uint32_t DUO_OFF_RING = 2 * ACT_BYTES;
+constexpr uint32_t DUO_OFF_MISC = DUO_OFF_RING + DUO_NST * DUO_STAGE;
+constexpr uint32_t DUO_MISC_MASK = MISC_DB + 256 * 4;              // two slots of mask planes
+constexpr uint32_t DUO_MISC_BARS = DUO_MISC_MASK + 2 * DUO_MASK_SLOT;
+constexpr uint32_t DUO_SMEM = DUO_OFF_MISC + DUO_MISC_BARS + 512 + 1024;
+static_assert(DUO_SMEM <= SMEM_LIMIT, "two activation tiles + a 3 x 16 KB ring + misc must fit in 227 KB");
+
+// the walk every role of both CTAs replays: step n works on slot n & 1, one phase of that slot's current item
+struct DuoWalk {
+    int ph[2], nph[2], ni[2], tile[2], items[2], fetches;
+    bool alive[2];
+    __device__ DuoWalk() {
+        fetches = 0;
+        for (int s = 0; s < 2; ++s) ph[s] = nph[s] = ni[s] = tile[s] = items[s] = 0, alive[s] = true;
+    }
+};
+
+__global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_constant__ Maps maps, const Params p) {
+    constexpr bool TRAIN = true;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ring = smem + DUO_OFF_RING;
+    uint8_t* misc = smem + DUO_OFF_MISC;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    float* s_bias = reinterpret_cast<float*>(misc + MISC_BIAS);
+    float* s_rowx = reinterpret_cast<float*>(misc + MISC_ROWX);
+    float* s_db = reinterpret_cast<float*>(misc + MISC_DB);
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(misc + DUO_MISC_MASK);
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(misc + DUO_MISC_BARS);   // [3] this CTA's half of stage i has landed
+    uint64_t* wempty = wfull + DUO_NST;      // [3] the GEMM has read stage i (multicast commit)
+    uint64_t* pfull = wempty + DUO_NST;      // [3] (leader) the peer's half of stage i has landed
+    uint64_t* x_full = pfull + DUO_NST;      // [2] slot s: this CTA's x tile has landed in act[s]
+    uint64_t* px_full = x_full + 2;          // [2] (leader) the peer's
+    uint64_t* x_free = px_full + 2;          // [2] slot s: the last stores of the finished item have read act[s]
+    uint64_t* a_done = x_free + 2;           // [2] (leader) slot s: both CTAs' epilogue warps finished the phase (16 arrivals)
+    uint64_t* a_loc = a_done + 2;            // [2] slot s: this CTA's eight warps finished the phase (store thread)
+    uint64_t* acc_full = a_loc + 2;          // [2] slot s: the GEMM into accumulator s is complete (multicast commit)
+    uint64_t* st_done = acc_full + 2;        // [2] slot s: the phase's TMA stores have read act[s]
+    uint64_t* tile_full = st_done + 2;       // [2] item ring
+    uint64_t* tile_empty = tile_full + 2;    // [2] (leader)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 2);
+    volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&maps.x);
+        for (int i = 0; i < DUO_NST; ++i) {
+            mbar_init(&wfull[i], 1);
+            mbar_init(&wempty[i], 1);
+            mbar_init(&pfull[i], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&x_full[s], 1);
+            mbar_init(&px_full[s], 1);
+            mbar_init(&x_free[s], 1);
+            mbar_init(&a_done[s], 16);
+            mbar_init(&a_loc[s], 8);
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&st_done[s], 1);
+            mbar_init(&tile_full[s], 1);
+            mbar_init(&tile_empty[s], 10 + 9 + 1);   // leader: MMA thread, store thread, 8 epilogue warps; peer: store thread, 8 warps, producer
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    pdl_wait();
+    pdl_trigger();
+    for (int i = threadIdx.x; i < p.n_nets * (int)BIAS_FLOATS; i += kThreads) {
+        const int ni = i >= (int)BIAS_FLOATS ? 1 : 0;
+        const NetP& np = p.net[ni];
+        const int j = i - ni * (int)BIAS_FLOATS;
+        const int l = j >> 8, c = j & 255;
+        float b = 0.f;
+        if (l < np.L) {
+            if (c < np.H[l]) b = __ldg(np.bias[l] + c);
+        } else if (l == MAXL) {
+            if (np.policy) b = c < np.n_actions ? (np.bias[MAXL] != nullptr ? __ldg(np.bias[MAXL] + c) : 0.f) : -1e30f;
+            else if (c < np.H[np.L - 1]) b = __ldg(np.w_head + c);
+        }
+        s_bias[i] = b;
+    }
+    for (int i = threadIdx.x; i < 256; i += kThreads) s_db[i] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto ring_done = [&](int slot) {
+        if (leader) mbar_arrive(&tile_empty[slot]);
+        else mbar_arrive_cta(&tile_empty[slot], 0);
+    };
+    // next item for slot s (consumer roles): read the ring entry of fetch number w.fetches, acknowledge it
+    // (whole-warp callers -- the epilogue warps -- pass warp_wide: every lane has read the entry before lane 0 acknowledges)
+    auto take_item = [&](DuoWalk& w, int s, bool ack_lane, bool warp_wide) -> bool {
+        const int f = w.fetches++;
+        mbar_wait(&tile_full[f & 1], (f >> 1) & 1);
+        const int q = tile_ring[f & 1];
+        if (warp_wide) __syncwarp();
+        if (ack_lane) ring_done(f & 1);
+        if (q < 0) {
+            w.alive[s] = false;
+            return false;
+        }
+        w.ni[s] = q >= p.n_units ? 1 : 0;
+        w.tile[s] = 2 * (q - w.ni[s] * p.n_units) + (int)rank;
+        w.ph[s] = 0;
+        w.nph[s] = p.net[w.ni[s]].n_ph;
+        ++w.items[s];
+        return true;
+    };
+#define DUO_WALK_BEGIN(w, ack, wide)                                      \
+    for (int n = 0;; ++n) {                                               \
+        const int s = n & 1;                                              \
+        if (!(w).alive[s]) {                                              \
+            if (!(w).alive[s ^ 1]) break;                                 \
+            continue;                                                     \
+        }                                                                 \
+        if ((w).ph[s] == (w).nph[s] && !take_item(w, s, ack, wide)) {     \
+            if (!(w).alive[s ^ 1]) break;                                 \
+            continue;                                                     \
+        }                                                                 \
+        const int ph = (w).ph[s]++;                                       \
+        const int ni = (w).ni[s];                                         \
+        const NetP& np = p.net[ni];                                       \
+        const PhaseDesc& d = np.ph[ph];                                   \
+        (void)d;
+#define DUO_WALK_END }
+
+    if (warp == 0) {
+        // ===================== producer: x tiles and this CTA's weight halves, in walk order =====================
+        if (lane == 0) {
+            DuoWalk w;
+            uint32_t ws = 0, wpar = 0;
+            for (int n = 0;; ++n) {
+                const int s = n & 1;
+                if (!w.alive[s]) {
+                    if (!w.alive[s ^ 1]) break;
+                    continue;
+                }
+                if (w.ph[s] == w.nph[s]) {
+                    const int f = w.fetches++;
+                    int q;
+                    if (leader) {
+                        mbar_wait(&tile_empty[f & 1], ((f >> 1) & 1) ^ 1);
+                        q = (int)atomicAdd(p.sched, 1u);
+                        if (q >= p.n_nets * p.n_units) q = -1;
+                        tile_ring[f & 1] = q;
+                        mbar_arrive(&tile_full[f & 1]);
+                        st_shared_cta_s32(const_cast<int*>(tile_ring) + (f & 1), 1, q);
+                        mbar_arrive_cta_release(&tile_full[f & 1], 1);
+                    } else {
+                        mbar_wait(&tile_full[f & 1], (f >> 1) & 1);
+                        q = tile_ring[f & 1];
+                        mbar_arrive_cta(&tile_empty[f & 1], 0);
+                    }
+                    if (q < 0) {
+                        w.alive[s] = false;
+                        if (!w.alive[s ^ 1]) break;
+                        continue;
+                    }
+                    w.ni[s] = q >= p.n_units ? 1 : 0;
+                    w.tile[s] = 2 * (q - w.ni[s] * p.n_units) + (int)rank;
+                    w.ph[s] = 0;
+                    w.nph[s] = p.net[w.ni[s]].n_ph;
+                    // the item's x tile, straight into the slot's activation buffer once the previous item's stores have read it
+                    const int k_s = w.items[s]++;
+                    mbar_wait(&x_free[s], (k_s & 1) ^ 1);
+                    if (leader) mbar_expect_tx(&x_full[s], 2u * p.in_kb * KB_BYTES);      // both CTAs' tiles, counted in the leader
+                    for (int kb = 0; kb < p.in_kb; ++kb)
+                        tma_load_2d_leaderbar(&maps.x, &x_full[s], smem + s * ACT_BYTES + kb * KB_BYTES, kb * KBLK,
+                                              w.tile[s] * TILE_M);
+                }
+                const int ph = w.ph[s]++;
+                const int ni = w.ni[s];
+                const PhaseDesc& d = p.net[ni].ph[ph];
+                const int nh = d.N >> 1;
+                for (int kb = 0; kb < d.n_kb; ++kb) {
+                    mbar_wait(&wempty[ws], wpar ^ 1);
+                    if (leader) mbar_expect_tx(&wfull[ws], (uint32_t)d.N * 128u);      // both halves complete on the leader's barrier
+                    uint8_t* dst = ring + ws * DUO_STAGE;
+                    if (d.b_mn) {
+                        for (int c = 0; c < (nh >> 6); ++c)
+                            tma_load_2d_leaderbar(&maps.w[ni][d.wmap], &wfull[ws], dst + c * MN_CHUNK, (int)rank * nh + c * 64,
+                                                  kb * KBLK);
+                    } else {
+                        tma_load_2d_leaderbar(&maps.w[ni][d.wmap], &wfull[ws], dst, kb * KBLK, (int)rank * nh);
+                    }
+                    if (++ws == DUO_NST) {
+                        ws = 0;
+                        wpar ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===================== MMA issuer =====================
+            DuoWalk w;
+            uint32_t ws = 0, wpar = 0;
+            uint32_t epi_cnt[2] = {0u, 0u};        // phases of slot s issued so far (every one ends with an epilogue)
+            int tr0 = 0;
+            DUO_WALK_BEGIN(w, true, false)
+                RLPPO_TRACE(0, tr0++);       // step start (before waiting for the slot's previous epilogue)
+                const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
+                uint8_t* act = smem + s * ACT_BYTES;
+                // this slot's previous epilogue, in both CTAs (every completion of a_done[s] is waited for, in order)
+                if (epi_cnt[s] > 0u) mbar_wait(&a_done[s], (epi_cnt[s] - 1u) & 1u);
+                if (ph == 0) mbar_wait(&x_full[s], (w.items[s] - 1) & 1);       // both CTAs' x tiles
+                tc_fence_after();
+                if (d.n_kb > 0) {
+                    const uint32_t idesc = umma_idesc_bf16(2 * TILE_M, d.N, 0, d.b_mn);
+                    for (int kb = 0; kb < d.n_kb; ++kb) {
+                        mbar_wait(&wfull[ws], wpar);                                   // both CTAs' halves
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(act + kb * KB_BYTES);
+                        const uint32_t b_addr = smem_u32(ring + ws * DUO_STAGE);
+#pragma unroll
+                        for (int k = 0; k < KBLK / 16; ++k) {
+                            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+                            const uint64_t bd = d.b_mn ? umma_smem_desc(b_addr + k * (16 * 128), MN_CHUNK, 1024)
+                                                       : umma_smem_desc(b_addr + k * 32, 16, 1024);
+                            umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_pair(&wempty[ws]);
+                        if (++ws == DUO_NST) {
+                            ws = 0;
+                            wpar ^= 1;
+                        }
+                    }
+                    umma_commit_pair(&acc_full[s]);
+                } else {
+                    // GEMM-less phase (value net: dL/dH_L from the accumulator of the last forward GEMM, still in TMEM)
+                    mbar_arrive(&acc_full[s]);
+                    mbar_arrive_cta(&acc_full[s], 1);
+                }
+                ++epi_cnt[s];
+                RLPPO_TRACE(0, tr0++);       // all MMAs of the step issued
+            DUO_WALK_END
+        }
+    } else if (warp == 10) {
+        // ===================== store thread =====================
+        if (lane == 0) {
+            DuoWalk w;
+            uint32_t cnt[2] = {0u, 0u};            // phases of slot s seen so far
+            DUO_WALK_BEGIN(w, true, false)
+                uint8_t* act = smem + s * ACT_BYTES;
+                mbar_wait(&a_loc[s], cnt[s] & 1u);          // this CTA's eight warps have finished the phase's epilogue
+                ++cnt[s];
+                if (d.out != NO_STORE && d.rel_kb > 0) {
+                    for (int kb = 0; kb < d.rel_kb; ++kb) {
+                        if (!p.dbg_nostore) tma_store_2d(&maps.out[ni][d.out], act + kb * KB_BYTES, kb * KBLK, w.tile[s] * TILE_M);
+                        bulk_commit();
+                    }
+                    bulk_wait_read_all();
+                    mbar_arrive(&st_done[s]);
+                }
+                if (ph == np.n_ph - 1) mbar_arrive(&x_free[s]);      // the buffer may take the slot's next x tile
+            DUO_WALK_END
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        EpiCtx e;
+        e.s_bias = s_bias;
+        e.s_rowx = s_rowx;
+        e.a_ready = nullptr;
+        e.a_mma = nullptr;
+        e.rank = rank;
+        e.lane = lane;
+        e.quarter = warp & 3;
+        e.half = (warp - 2) >> 2;
+        e.row_in_tile = e.quarter * 32 + lane;
+        float dv_slot0 = 0.f, dv_slot1 = 0.f;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, mrows = 0.f;
+        float vm0 = 0.f, vm1 = 0.f, vrows = 0.f;
+        auto db_add = [&](int c, float v) { atomicAdd(&s_db[c * 32 + e.lane], v); };
+        uint32_t cnt[2] = {0u, 0u};                // phases of slot s seen so far (parity of acc_full[s])
+        uint32_t pend = 0, scnt = 0;               // bit s: stores of slot s outstanding / parity of st_done[s]
+        int tr1 = 0;
+        DuoWalk w;
+        DUO_WALK_BEGIN(w, lane == 0, true)
+            uint8_t* act = smem + s * ACT_BYTES;
+            e.act = act;
+            e.s_mask = s_mask + s * (DUO_MAXL * 4 * kEpiThreads) + (threadIdx.x - 64);
+            const float* s_bias_n = s_bias + ni * (int)BIAS_FLOATS;
+            const int64_t row = (int64_t)w.tile[s] * TILE_M + e.row_in_tile;
+            const bool row_ok = row < p.M;
+            float dv_keep = s ? dv_slot1 : dv_slot0;
+            if (warp == 2 && lane == 0) RLPPO_TRACE(2, tr1);        // arrived at the step
+            mbar_wait(&acc_full[s], cnt[s] & 1u);
+            ++cnt[s];
+            tc_fence_after();
+            if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);      // accumulator complete
+            if (d.smem && ((pend >> s) & 1u)) {      // the tile is overwritten in place: its last stores must have read it
+                mbar_wait(&st_done[s], (scnt >> s) & 1u);
+                scnt ^= 1u << s;
+                pend &= ~(1u << s);
+            }
+            const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + (uint32_t)s * 256u;
+            uint8_t* dst = act;
+            const int li = d.layer;
+            const int it = 1;      // (fine-trace stamps of the single-tile kernels are off here)
+            int tr5 = 0;
+            (void)it;
+            (void)tr5;
+#define RLPPO_RELEASE_KB(j) do { } while (0)
+#include "fused_epilogue.inc"
+#undef RLPPO_RELEASE_KB
+            if (s) dv_slot1 = dv_keep;
+            else dv_slot0 = dv_keep;
+            if (d.out != NO_STORE) pend |= 1u << s;
+            // the whole phase is done: the tile in act[s] is complete for the slot's next GEMM and for the store thread
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&a_loc[s]);
+                mbar_arrive_cta(&a_done[s], 0);
+            }
+            if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);      // phase done
+        DUO_WALK_END
+        if (e.half == 0) {
+            for (int ni = 0; ni < p.n_nets; ++ni) {
+                const NetP& np = p.net[ni];
+                if (np.metrics == nullptr) continue;
+                if (np.policy) {
+                    const float r0 = warp_sum(m0), r1 = warp_sum(m1), r2 = warp_sum(m2), r3 = warp_sum(m3),
+                                rr = warp_sum(mrows);
+                    if (e.lane == 0 && rr > 0.f) {
+                        atomicAdd(np.metrics + 0, r0);
+                        atomicAdd(np.metrics + 1, r1);
+                        atomicAdd(np.metrics + 2, r2);
+                        atomicAdd(np.metrics + 3, r3);
+                        atomicAdd(np.metrics + 4, rr);
+                    }
+                } else {
+                    const float r0 = warp_sum(vm0), r1 = warp_sum(vm1), rr = warp_sum(vrows);
+                    if (e.lane == 0 && rr > 0.f) {
+                        atomicAdd(np.metrics + 5, r0);
+                        atomicAdd(np.metrics + 6, rr);
+                        if (np.gbias[MAXL] != nullptr) atomicAdd(np.gbias[MAXL], r1);
+                    }
+                }
+            }
+        }
+    }
+#undef DUO_WALK_BEGIN
+#undef DUO_WALK_END
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+    if (threadIdx.x == 0) {
+        if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
+    for (int ni = 0; ni < p.n_nets; ++ni) {
+        const NetP& np = p.net[ni];
+        if (np.policy || np.gw_head == nullptr) continue;
+        for (int c = threadIdx.x; c < np.H[np.L - 1]; c += kThreads) atomicAdd(np.gw_head + c, s_db[c]);
     }
 }
 
@@ -1405,6 +1362,84 @@ int launch_nets_t(const rlppo_fused_net* const* nets, const bool* is_policy, int
     return RLPPO_OK;
 }
 
+// The training launch runs as CTA pairs with two tiles in flight per CTA (fused_duo_kernel) whenever the nets allow it
+// (<= 3 hidden layers of width 128 or 256); RLPPO_FUSED_DUO=0 falls back to the single-tile kernel.
+bool duo_ok(const rlppo_fused_net* const* nets, int n_nets) {
+    static const bool off = getenv("RLPPO_FUSED_DUO") != nullptr && getenv("RLPPO_FUSED_DUO")[0] == '0';
+    if (off) return false;
+    for (int ni = 0; ni < n_nets; ++ni) {
+        if (nets[ni]->n_hidden > DUO_MAXL) return false;
+        for (int l = 0; l < nets[ni]->n_hidden; ++l)
+            if (nets[ni]->hidden[l] != 128 && nets[ni]->hidden[l] != 256) return false;
+    }
+    return true;
+}
+
+int launch_duo(const rlppo_fused_net* const* nets, const bool* is_policy, int n_nets, const uint16_t* x, int64_t M, Params& p,
+               cudaStream_t s) {
+    Maps maps;
+    p.M = M;
+    p.num_tiles = (int)((M + TILE_M - 1) / TILE_M);
+    p.pair = 1;
+    p.n_units = (p.num_tiles + 1) / 2;
+    p.n_nets = n_nets;
+    p.in_kb = (nets[0]->in_dim + KBLK - 1) / KBLK;
+    p.nwst = DUO_NST;
+    p.wst_bytes = DUO_STAGE;
+    for (int ni = 0; ni < n_nets; ++ni) {
+        RLPPO_CHECK_ARG(nets[ni]->in_dim == nets[0]->in_dim && nets[ni]->in_ld == nets[0]->in_ld,
+                        "nets of one launch read the same x");
+        int rc = build_net<true>(is_policy[ni], nets[ni], M, ni, maps, p.net[ni], true);
+        if (rc) return rc;
+    }
+    int rc = make_tmap_bf16_2d(&maps.x, x, (uint64_t)M, (uint64_t)nets[0]->in_dim, (uint64_t)nets[0]->in_ld, TILE_M);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        RLPPO_CUDA(cudaFuncSetAttribute(fused_duo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        configured = true;
+    }
+    const int items = p.n_units * n_nets;                 // one item = one tile per CTA of a pair; two items in flight per pair
+    const int pairs = num_sms() / 2;
+    const int want = (items + 1) / 2;
+    const int grid = 2 * (want < pairs ? want : pairs);
+    {
+        constexpr int kSlots = 64;
+        static unsigned int* d_sched[16] = {};
+        static unsigned int next_slot[16] = {};
+        int dev = 0;
+        RLPPO_CUDA(cudaGetDevice(&dev));
+        RLPPO_CHECK_ARG(dev >= 0 && dev < 16, "device index out of range");
+        if (d_sched[dev] == nullptr) {
+            RLPPO_CUDA(cudaMalloc(&d_sched[dev], kSlots * 2 * sizeof(unsigned int)));
+            RLPPO_CUDA(cudaMemset(d_sched[dev], 0, kSlots * 2 * sizeof(unsigned int)));
+        }
+        p.sched = d_sched[dev] + 2 * (next_slot[dev]++ % kSlots);
+    }
+    p.dbg_nostore = getenv("RLPPO_FUSED_NOSTORE") != nullptr ? 1 : 0;
+    static unsigned long long* d_trace = nullptr;
+    const bool tracing = getenv("RLPPO_FUSED_TRACE") != nullptr;
+    if (tracing) {
+        if (d_trace == nullptr) RLPPO_CUDA(cudaMalloc(&d_trace, 3072 * sizeof(unsigned long long)));
+        RLPPO_CUDA(cudaMemsetAsync(d_trace, 0, 3072 * sizeof(unsigned long long), s));
+        p.trace = d_trace;
+    }
+    RLPPO_CUDA(launch_pdl_cluster(fused_duo_kernel, dim3(grid), dim3(kThreads), (size_t)DUO_SMEM, s, 2, maps, p));
+    if (tracing) {
+        static unsigned long long h[3072];
+        RLPPO_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
+        RLPPO_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long t0 = h[0];
+        fprintf(stderr, "[duo trace] items=%d (steps alternate slots 0/1)\n", items);
+        for (int i = 0; i + 1 < 60 && h[i + 1] != 0; i += 2)
+            fprintf(stderr, "  mma  step %d start=%llu issued=+%llu\n", i / 2, h[i] - t0, h[i + 1] - h[i]);
+        for (int i = 0; i + 1 < 60 && h[512 + i] != 0; i += 2)
+            fprintf(stderr, "  epi  step %d arrive=%llu acc_full=%llu dur=%llu\n", i / 2, h[1024 + i] - t0, h[512 + i] - t0,
+                    h[512 + i + 1] - h[512 + i]);
+    }
+    return RLPPO_OK;
+}
+
 template <bool TRAIN>
 int launch_nets(const rlppo_fused_net* const* nets, const bool* is_policy, int n_nets, const uint16_t* x, int64_t M, Params& p,
                 cudaStream_t s) {
@@ -1414,6 +1449,7 @@ int launch_nets(const rlppo_fused_net* const* nets, const bool* is_policy, int n
         int rc = check_net(nets[ni]);
         if (rc) return rc;
     }
+    if (TRAIN && duo_ok(nets, n_nets)) return launch_duo(nets, is_policy, n_nets, x, M, p, s);
     if (TRAIN && pair_ok(nets, n_nets)) return launch_nets_t<TRAIN, TRAIN>(nets, is_policy, n_nets, x, M, p, s);
     return launch_nets_t<TRAIN, false>(nets, is_policy, n_nets, x, M, p, s);
 }

@@ -37,7 +37,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#ifdef RLPPO_DEBUG_BAR
+        if (clock64() - t0 > 400000000LL) {     // experiments: say which wait timed out (shared-memory offset of the barrier)
+            printf("mbar timeout: block %d thread %d barrier smem 0x%x parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+#else
         if (clock64() - t0 > 4000000000LL) __trap();
+#endif
     }
 }
 __device__ __forceinline__ void fence_barrier_init() {
@@ -199,6 +206,15 @@ __device__ __forceinline__ void mbar_arrive_cta_release(uint64_t* bar, uint32_t 
 }
 __device__ __forceinline__ void st_shared_cta_s32(int* p, uint32_t cta, int v) {
     asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(mapa_u32(p, cta)), "r"(v) : "memory");
+}
+// 2-D tile load into THIS CTA's shared memory whose completion (complete_tx) is counted on the mbarrier at the same offset
+// in the pair's leader CTA: the leader's MMA thread waits on ONE barrier for both CTAs' operand halves (the form
+// CUTLASS's SM100_TMA_2SM_LOAD uses; tools/microbench/cta_pair_gemm.cu tma_mode 1).
+__device__ __forceinline__ void tma_load_2d_leaderbar(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mapa_u32(bar, 0)), "r"(c0), "r"(c1)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {   // whole warp, in BOTH CTAs
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),

@@ -667,16 +667,18 @@ def test_late_next_states_path_matches_fifo_oracle(pkg):
     assert np.array_equal(results[0][1]["next_states"], results[1][1]["next_states"])
 
 
-def test_cta_pair_mode_matches(pkg):
-    """RLPPO_FUSED_PAIR=1 (the training launch as 2-CTA clusters, tcgen05.mma.cta_group::2, each CTA staging half of every
-    weight k-block) gives the same results as the default single-CTA launch: the fused-vs-layerwise and golden tests re-run
-    in a fresh process with the switch on (it is read once per process)."""
+@pytest.mark.parametrize("env", [{"RLPPO_FUSED_DUO": "0"}, {"RLPPO_FUSED_DUO": "0", "RLPPO_FUSED_PAIR": "1"}],
+                         ids=["single_cta", "cta_pair"])
+def test_other_fused_launch_forms_match(pkg, env):
+    """The default training launch is fused_duo_kernel (2-CTA clusters, tcgen05.mma.cta_group::2, two tiles in flight per
+    CTA).  The two other forms -- one tile per CTA (RLPPO_FUSED_DUO=0) and one tile per CTA of a pair (+ RLPPO_FUSED_PAIR=1)
+    -- must give the same results: the fused-vs-layerwise, golden and partition tests re-run in a fresh process with the
+    switches set (they are read once per process)."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, RLPPO_FUSED_PAIR="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_learner_gpu.py", "-m", "gpu", "-x", "-q", "-k",
                         "fused_kernels_match_layerwise or policy_and_value_golden or ppo_learner_golden or row_partition"],
-                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+                       cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

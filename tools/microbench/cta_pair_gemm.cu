@@ -38,6 +38,12 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* b, uint32_t cta) {
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// the same load, but the mbarrier that receives the complete_tx lives in CTA 0 of the pair (what CUTLASS's SM100_TMA_2SM_LOAD does)
+__device__ __forceinline__ void tma_load_2d_leaderbar(const CUtensorMap* m, uint64_t* bar_local_addr, void* dst, int c0, int c1) {
+    uint32_t rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(bar_local_addr)), "r"(0u));
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(rbar), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
@@ -57,7 +63,7 @@ struct Smem {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-pair_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* C, int alloc_mode) {
+pair_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* C, int alloc_mode, int tma_mode) {
     extern __shared__ uint8_t raw[];
     Smem& s = *reinterpret_cast<Smem*>(raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u));
     const uint32_t rank = cluster_rank();
@@ -83,14 +89,22 @@ pair_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s.tmem_base;
     if (threadIdx.x == 0) {
-        mbar_expect(&s.full, 2 * 128 * 128);
-        tma_load_2d(&tmA, &s.full, s.a, 0, rank * 128);
-        tma_load_2d(&tmB, &s.full, s.b, 0, rank * 128);
-        mbar_wait(&s.full, 0);
-        if (rank == 1) {
-            mbar_arrive_remote(&s.peer_ready, 0);       // tell the leader this CTA's operands have landed
+        if (tma_mode == 1) {
+            // all four tiles (two per CTA) complete on the LEADER's barrier; the peer arms nothing
+            if (rank == 0) mbar_expect(&s.full, 4 * 128 * 128);
+            tma_load_2d_leaderbar(&tmA, &s.full, s.a, 0, rank * 128);
+            tma_load_2d_leaderbar(&tmB, &s.full, s.b, 0, rank * 128);
+            if (rank == 0) mbar_wait(&s.full, 0);
         } else {
-            mbar_wait(&s.peer_ready, 0);
+            mbar_expect(&s.full, 2 * 128 * 128);
+            tma_load_2d(&tmA, &s.full, s.a, 0, rank * 128);
+            tma_load_2d(&tmB, &s.full, s.b, 0, rank * 128);
+            mbar_wait(&s.full, 0);
+        }
+        if (rank == 1) {
+            if (tma_mode == 0) mbar_arrive_remote(&s.peer_ready, 0);       // tell the leader this CTA's operands have landed
+        } else {
+            if (tma_mode == 0) mbar_wait(&s.peer_ready, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t idesc = idesc_bf16(256, 256);
 #pragma unroll
@@ -131,6 +145,7 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
 
 int main(int argc, char** argv) {
     const int alloc_mode = argc > 1 ? atoi(argv[1]) : 2;
+    const int tma_mode = argc > 2 ? atoi(argv[2]) : 0;
     const int M = 256, N = 256, K = 64;
     __nv_bfloat16 *hA = new __nv_bfloat16[M * K], *hB = new __nv_bfloat16[N * K];
     float* fa = new float[M * K]; float* fb = new float[N * K];
@@ -151,7 +166,7 @@ int main(int argc, char** argv) {
     if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dB, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("encode B failed\n"); return 1; }
     const size_t smem = sizeof(Smem) + 1024;
     CK(cudaFuncSetAttribute(pair_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_gemm<<<2, 128, smem>>>(tmA, tmB, dC, alloc_mode);
+    pair_gemm<<<2, 128, smem>>>(tmA, tmB, dC, alloc_mode, tma_mode);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     float* hC = new float[M * N];
@@ -161,6 +176,6 @@ int main(int argc, char** argv) {
         double ref = 0; for (int k = 0; k < K; ++k) ref += (double)fa[m * K + k] * fb[n * K + k];
         double e = fabs(ref - hC[m * N + n]); if (e > maxerr) maxerr = e; if (e > 1e-3) ++bad;
     }
-    printf("{\"test\": \"cta_pair_gemm\", \"alloc_mode\": %d, \"max_abs_err\": %.3g, \"bad\": %d, \"C[0]\": %g, \"C[last]\": %g}\n", alloc_mode, maxerr, bad, hC[0], hC[M * N - 1]);
+    printf("{\"test\": \"cta_pair_gemm\", \"tma_mode\": %d, \"alloc_mode\": %d, \"max_abs_err\": %.3g, \"bad\": %d, \"C[0]\": %g, \"C[last]\": %g}\n", tma_mode, alloc_mode, maxerr, bad, hC[0], hC[M * N - 1]);
     return bad != 0;
 }
