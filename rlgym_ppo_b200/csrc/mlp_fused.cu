@@ -795,12 +795,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
     uint64_t* st_done = acc_full + 2;        // [2] slot s: the phase's TMA stores have read act[s]
     uint64_t* tile_full = st_done + 2;       // [2] item ring
     uint64_t* tile_empty = tile_full + 2;    // [2] (leader)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_empty + 2);
+    uint64_t* a_kb = tile_empty + 2;         // [2][4] slot s, k-block kb of the tile is written (this CTA's 8 warps): store thread
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_kb + 8);
     volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&maps.x);
+        for (int i = 0; i < 8; ++i) mbar_init(&a_kb[i], 8);
         for (int i = 0; i < DUO_NST; ++i) {
             mbar_init(&wfull[i], 1);
             mbar_init(&wempty[i], 1);
@@ -1000,15 +1002,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
         if (lane == 0) {
             DuoWalk w;
             uint32_t cnt[2] = {0u, 0u};            // phases of slot s seen so far
+            uint32_t kpar = 0;                      // bit 4s + kb: parity of a_kb[s][kb] to wait for next
             DUO_WALK_BEGIN(w, true, false)
                 uint8_t* act = smem + s * ACT_BYTES;
-                mbar_wait(&a_loc[s], cnt[s] & 1u);          // this CTA's eight warps have finished the phase's epilogue
-                ++cnt[s];
-                if (d.out != NO_STORE && d.rel_kb > 0) {
-                    for (int kb = 0; kb < d.rel_kb; ++kb) {
+                // k-blocks are stored as the epilogue finishes them: a burst of four 16 KB stores at the end of a phase sat in
+                // the TMA queue ahead of the weight loads (r02aj: the launch is 10 % shorter with the stores switched off)
+                for (int kb = 0; kb < d.rel_kb; ++kb) {
+                    const int b = 4 * s + kb;
+                    mbar_wait(&a_kb[b], (kpar >> b) & 1u);
+                    kpar ^= 1u << b;
+                    if (d.out != NO_STORE) {
                         if (!p.dbg_nostore) tma_store_2d(&maps.out[ni][d.out], act + kb * KB_BYTES, kb * KBLK, w.tile[s] * TILE_M);
                         bulk_commit();
                     }
+                }
+                mbar_wait(&a_loc[s], cnt[s] & 1u);          // this CTA's eight warps have finished the phase's epilogue
+                ++cnt[s];
+                if (d.out != NO_STORE && d.rel_kb > 0) {
                     bulk_wait_read_all();
                     mbar_arrive(&st_done[s]);
                 }
@@ -1061,7 +1071,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
             int tr5 = 0;
             (void)it;
             (void)tr5;
-#define RLPPO_RELEASE_KB(j) do { } while (0)
+#define RLPPO_RELEASE_KB(j)                                   \
+    do {                                                       \
+        fence_proxy_async();                                   \
+        __syncwarp();                                          \
+        if (lane == 0) mbar_arrive(&a_kb[4 * s + (j)]);        \
+    } while (0)
 #include "fused_epilogue.inc"
 #undef RLPPO_RELEASE_KB
             if (s) dv_slot1 = dv_keep;

@@ -546,10 +546,11 @@ class PPOLearner(object):
                 n_batches = self._nb_final
         # One `rng.permutation(total)` per epoch (experience_buffer.py:98), drawn in the reference's order, uploaded into
         # one [epochs, total] device buffer before any device work: the whole call is then a single graph replay.
-        if self._perm_dev is None or self._perm_dev.shape[0] != E or self._perm_dev.shape[1] < total:
+        fresh = self._perm_dev is None or self._perm_dev.shape[0] != E or self._perm_dev.shape[1] < total
+        if fresh:
             self._perm_dev = torch.empty((E, max(total, 1)), dtype=torch.int64, device=self._params.device)
         for epoch in range(E):
-            exp.next_permutation_into(self._perm_dev[epoch, :total])
+            exp.next_permutation_into(self._perm_dev[epoch, :total], fresh_alloc=fresh)
         n_iterations = E * n_batches
 
         p2p = R > 1 and self.dp_collective in ("p2p", "p2p2")
