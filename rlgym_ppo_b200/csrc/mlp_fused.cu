@@ -69,7 +69,7 @@ static_assert(ACT_BYTES + 2 * KB_BYTES + MISC_BYTES + 1024 + 3 * WST_BYTES <= SM
 enum { PH_FWD = 0, PH_FWD_VALUE = 1, PH_HEAD = 2, PH_DGRAD = 3, PH_VALUE_BWD = 4 };
 constexpr uint8_t NO_STORE = 0xFF;
 
-struct PhaseDesc {
+struct alignas(16) PhaseDesc {   // one 16-byte word: the duo kernel keeps the table in shared memory and reads a phase with one load
     uint8_t kind;       // PH_*
     uint8_t layer;      // FWD: hidden index (0-based) of the layer produced; DGRAD/VALUE_BWD: hidden index whose ReLU mask applies
     uint8_t n_kb;       // k-blocks of the contraction (0: no GEMM, PH_VALUE_BWD)
@@ -128,7 +128,9 @@ struct Params {
     int n_nets;                  // work items = n_nets * num_tiles: item q is tile q % num_tiles of net q / num_tiles
     NetP net[MAXNET];
     unsigned int* sched;         // [0] next item to hand out, [1] CTAs that have left (the last one zeroes both)
+    uint32_t* mask_scratch;      // duo kernel: gridDim.x x 24 KB of ReLU mask words (L2-resident scratch)
     int dbg_nostore;             // debug (RLPPO_FUSED_NOSTORE=1): timing experiment, outputs are NOT written
+    int dbg;                     // debug (RLPPO_DUO_DBG bits, duo kernel timing experiments, results are WRONG): 1 no MMAs, 2 no weight loads
     unsigned long long* trace;   // debug (RLPPO_FUSED_TRACE=1): clock64 stamps of CTA 0, [role][event]
 };
 
@@ -589,12 +591,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                         bulk_commit();
                         ++nst;
                     }
-                    if (storing && d.rel_kb > 0) {
-                        // ONE completion signal per phase: the next epilogue that overwrites the tile starts a whole GEMM tail
-                        // (>= 1k cycles) after the last release, by which time these reads (64 KB) are long done
-                        bulk_wait_read_all();
+                    if (d.rel_kb > 0) {
+                        // ONE completion signal per phase, storing or not: the epilogue waits for it before its next phase, so
+                        // it is never more than one completion of a_ready ahead of this thread (two would alias the parity).
+                        // The next epilogue starts a whole GEMM (>= 1k cycles) after the last release: the reads are long done
+                        if (storing) bulk_wait_read_all();
                         mbar_arrive(st_done);
-                        RLPPO_TRACE(2, 2 * (nst - 1) + 1);
+                        if (storing) RLPPO_TRACE(2, 2 * (nst - 1) + 1);
                     }
                 }
             }
@@ -664,15 +667,21 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
                 fpar ^= 1u << acc;
                 tc_fence_after();
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: accumulator of (tile, ph) complete
-                if (TRAIN && d.smem) wait_stores();     // the tile is overwritten in place: its last stores must have read it
+                // the tile is overwritten in place: its last stores must have read it (and the store thread has seen every
+                // release of the previous phase)
+                if (TRAIN) wait_stores();
                 const uint32_t trow = tmem_base + ((uint32_t)(e.quarter * 32) << 16) + acc * 256u;
                 uint8_t* dst = act;      // in place: the GEMM that read this tile has completed
                 const int li = d.layer;
 
 #define RLPPO_RELEASE_KB(j) release_kb<PAIR>(e, j)
+#define RLPPO_MASK_ST(l, kb, v) e.s_mask[((l) * 4 + (kb)) * kEpiThreads] = (v)
+#define RLPPO_MASK_LD(l, kb) e.s_mask[((l) * 4 + (kb)) * kEpiThreads]
 #include "fused_epilogue.inc"
+#undef RLPPO_MASK_ST
+#undef RLPPO_MASK_LD
 #undef RLPPO_RELEASE_KB
-                if (TRAIN && d.out != NO_STORE) pend = 1u;
+                if (TRAIN && d.rel_kb > 0) pend = 1u;
                 if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);   // epilogue: (tile, ph) done
           }
         }
@@ -740,10 +749,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 // deterministic sequence  step n -> slot n & 1 -> that slot's next phase : while the eight epilogue warps work on one
 // slot, the GEMM of the other slot's next phase runs, so MMA time, weight latency and the pair's signalling latency hide
 // behind an epilogue instead of sitting between two of them.  What makes the second 64 KB buffer fit is the pair: each
-// CTA stages only its N/2 half of a weight k-block (16 KB stages, a 3-deep ring; both CTAs' TMA loads complete on the
-// LEADER's barrier -- cp.async.bulk.tensor.cta_group::2 -- so a stage's round trip is MMA completion -> multicast commit ->
-// TMA from L2, with no relay hop: with a relay the r02ag trace showed 4k cycles per GEMM step for 2k cycles of MMAs), and
-// the x tile of
+// CTA stages only its N/2 half of a weight k-block (16 KB stages; both CTAs' TMA loads complete on the LEADER's barrier
+// -- cp.async.bulk.tensor.cta_group::2 -- so a stage's round trip is MMA completion -> multicast commit -> TMA from L2, with
+// no relay hop), the ReLU masks (24 KB for two slots) live in a per-CTA global scratch that stays in L2 (written by the
+// forward epilogue, prefetched into registers before a backward epilogue waits for its accumulator; thread-local memory
+// was tried and made the backward epilogues 2x slower), which buys a 5-deep ring: with three stages a GEMM step took 3.8k
+// cycles for 2k cycles of MMAs (~1.7k cycles per TMA round trip, r02ai trace), and the x tile of
 // an item is loaded straight into the slot's activation buffer (no staging buffer; its latency hides behind the other
 // slot too).  A GEMM waits for the WHOLE previous epilogue of its slot (one barrier per slot, no k-block hand-over).
 // Roles per CTA: producer (x tiles, weight halves), warp 1 = MMA issuer (leader only), eight epilogue warps, store
@@ -751,25 +762,30 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 // current one is finished, in walk order, so every role of both CTAs replays the same assignment.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t DUO_STAGE = WST_BYTES / 2;                      // 16 KB: this CTA's half of a weight k-block
-constexpr int DUO_NST = 3;
-constexpr int DUO_MAXL = 3;                                        // hidden layers (mask planes per slot)
-constexpr uint32_t DUO_MASK_SLOT = DUO_MAXL * 4 * kEpiThreads * 4; // ReLU mask planes of one slot
+constexpr int DUO_NST = 5;                                         // 80 KB of weight halves in flight per CTA
+constexpr int DUO_MAXL = 3;                                        // hidden layers (ReLU mask words per thread: 2 slots x 3 x 4)
 constexpr uint32_t DUO_OFF_RING = 2 * ACT_BYTES;
 constexpr uint32_t DUO_OFF_MISC = DUO_OFF_RING + DUO_NST * DUO_STAGE;
-constexpr uint32_t DUO_MISC_MASK = MISC_DB + 256 * 4;              // two slots of mask planes
-constexpr uint32_t DUO_MISC_BARS = DUO_MISC_MASK + 2 * DUO_MASK_SLOT;
-constexpr uint32_t DUO_SMEM = DUO_OFF_MISC + DUO_MISC_BARS + 512 + 1024;
-static_assert(DUO_SMEM <= SMEM_LIMIT, "two activation tiles + a 3 x 16 KB ring + misc must fit in 227 KB");
+constexpr uint32_t DUO_MISC_BARS = MISC_DB + 256 * 4;              // (the ReLU masks live in a global scratch here)
+constexpr uint32_t DUO_SMEM = DUO_OFF_MISC + DUO_MISC_BARS + 256 + 2 * MAXPH * 16 + 1024;   // barriers, phase table, alignment slack
+static_assert(sizeof(PhaseDesc) == 16, "one phase = one 16-byte shared-memory word");
+static_assert(DUO_SMEM <= SMEM_LIMIT, "two activation tiles + a 5 x 16 KB ring + misc must fit in 227 KB");
 
-// the walk every role of both CTAs replays: step n works on slot n & 1, one phase of that slot's current item
+// the walk every role of both CTAs replays: step n works on slot n & 1, one phase of that slot's current item.  The state
+// is kept in scalars selected by the slot bit (arrays indexed by it lived in local memory: ~600 cycles per step).
+// Items are dealt out statically: cluster c takes items c, c + n_clusters, ... (policy items first, they are the longer
+// ones) -- every role derives the same sequence with no shared counter and no hand-over (the dynamic ring cost the producer
+// a global atomic round trip at every item boundary, with the weight ring draining behind it).
 struct DuoWalk {
-    int ph[2], nph[2], ni[2], tile[2], items[2], fetches;
-    bool alive[2];
-    __device__ DuoWalk() {
-        fetches = 0;
-        for (int s = 0; s < 2; ++s) ph[s] = nph[s] = ni[s] = tile[s] = items[s] = 0, alive[s] = true;
-    }
+    int ph0 = 0, ph1 = 0, nph0 = 0, nph1 = 0, ni0 = 0, ni1 = 0, tile0 = 0, tile1 = 0, items0 = 0, items1 = 0, fetches = 0;
+    bool alive0 = true, alive1 = true;
 };
+#define DUO_SEL(w, f, s) ((s) ? (w).f##1 : (w).f##0)
+#define DUO_SET(w, f, s, v)    \
+    do {                       \
+        if (s) (w).f##1 = (v); \
+        else (w).f##0 = (v);   \
+    } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_constant__ Maps maps, const Params p) {
     constexpr bool TRAIN = true;
@@ -782,22 +798,16 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
     float* s_bias = reinterpret_cast<float*>(misc + MISC_BIAS);
     float* s_rowx = reinterpret_cast<float*>(misc + MISC_ROWX);
     float* s_db = reinterpret_cast<float*>(misc + MISC_DB);
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(misc + DUO_MISC_MASK);
-    uint64_t* wfull = reinterpret_cast<uint64_t*>(misc + DUO_MISC_BARS);   // [3] this CTA's half of stage i has landed
-    uint64_t* wempty = wfull + DUO_NST;      // [3] the GEMM has read stage i (multicast commit)
-    uint64_t* pfull = wempty + DUO_NST;      // [3] (leader) the peer's half of stage i has landed
-    uint64_t* x_full = pfull + DUO_NST;      // [2] slot s: this CTA's x tile has landed in act[s]
-    uint64_t* px_full = x_full + 2;          // [2] (leader) the peer's
-    uint64_t* x_free = px_full + 2;          // [2] slot s: the last stores of the finished item have read act[s]
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(misc + DUO_MISC_BARS);   // [5] (leader) both halves of stage i have landed
+    uint64_t* wempty = wfull + DUO_NST;      // [5] the GEMM has read stage i (multicast commit)
+    uint64_t* x_full = wempty + DUO_NST;     // [2] (leader) slot s: both CTAs' x tiles have landed in act[s]
+    uint64_t* x_free = x_full + 2;           // [2] slot s: the last stores of the finished item have read act[s]
     uint64_t* a_done = x_free + 2;           // [2] (leader) slot s: both CTAs' epilogue warps finished the phase (16 arrivals)
-    uint64_t* a_loc = a_done + 2;            // [2] slot s: this CTA's eight warps finished the phase (store thread)
-    uint64_t* acc_full = a_loc + 2;          // [2] slot s: the GEMM into accumulator s is complete (multicast commit)
-    uint64_t* st_done = acc_full + 2;        // [2] slot s: the phase's TMA stores have read act[s]
-    uint64_t* tile_full = st_done + 2;       // [2] item ring
-    uint64_t* tile_empty = tile_full + 2;    // [2] (leader)
-    uint64_t* a_kb = tile_empty + 2;         // [2][4] slot s, k-block kb of the tile is written (this CTA's 8 warps): store thread
+    uint64_t* acc_full = a_done + 2;         // [2] slot s: the GEMM into accumulator s is complete (multicast commit)
+    uint64_t* st_done = acc_full + 2;        // [2] slot s: the store thread is through with the phase (its stores have read act[s])
+    uint64_t* a_kb = st_done + 2;            // [2][4] slot s, k-block kb of the tile is written (this CTA's 8 warps): store thread
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_kb + 8);
-    volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2]
+    const PhaseDesc* s_ph = reinterpret_cast<const PhaseDesc*>(misc + DUO_MISC_BARS + 256);   // [2 nets][MAXPH]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -806,18 +816,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
         for (int i = 0; i < DUO_NST; ++i) {
             mbar_init(&wfull[i], 1);
             mbar_init(&wempty[i], 1);
-            mbar_init(&pfull[i], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&x_full[s], 1);
-            mbar_init(&px_full[s], 1);
             mbar_init(&x_free[s], 1);
             mbar_init(&a_done[s], 16);
-            mbar_init(&a_loc[s], 8);
             mbar_init(&acc_full[s], 1);
             mbar_init(&st_done[s], 1);
-            mbar_init(&tile_full[s], 1);
-            mbar_init(&tile_empty[s], 10 + 9 + 1);   // leader: MMA thread, store thread, 8 epilogue warps; peer: store thread, 8 warps, producer
         }
         fence_barrier_init();
     }
@@ -839,51 +844,53 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
         s_bias[i] = b;
     }
     for (int i = threadIdx.x; i < 256; i += kThreads) s_db[i] = 0.f;
+    for (int i = threadIdx.x; i < p.n_nets * MAXPH; i += kThreads)
+        const_cast<PhaseDesc*>(s_ph)[i] = p.net[i / MAXPH].ph[i % MAXPH];
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    auto ring_done = [&](int slot) {
-        if (leader) mbar_arrive(&tile_empty[slot]);
-        else mbar_arrive_cta(&tile_empty[slot], 0);
-    };
-    // next item for slot s (consumer roles): read the ring entry of fetch number w.fetches, acknowledge it
-    // (whole-warp callers -- the epilogue warps -- pass warp_wide: every lane has read the entry before lane 0 acknowledges)
-    auto take_item = [&](DuoWalk& w, int s, bool ack_lane, bool warp_wide) -> bool {
-        const int f = w.fetches++;
-        mbar_wait(&tile_full[f & 1], (f >> 1) & 1);
-        const int q = tile_ring[f & 1];
-        if (warp_wide) __syncwarp();
-        if (ack_lane) ring_done(f & 1);
-        if (q < 0) {
-            w.alive[s] = false;
+    const int cluster_id = (int)(blockIdx.x >> 1), n_clusters = (int)(gridDim.x >> 1);
+    const int total_items = p.n_nets * p.n_units;
+    const int nph_net0 = p.net[0].n_ph, nph_net1 = p.net[1].n_ph;
+    // next item of this cluster for slot s: the same arithmetic in every role of both CTAs
+    auto next_item = [&](DuoWalk& w, int s) -> bool {
+        const int q = cluster_id + (w.fetches++) * n_clusters;
+        if (q >= total_items) {
+            DUO_SET(w, alive, s, false);
             return false;
         }
-        w.ni[s] = q >= p.n_units ? 1 : 0;
-        w.tile[s] = 2 * (q - w.ni[s] * p.n_units) + (int)rank;
-        w.ph[s] = 0;
-        w.nph[s] = p.net[w.ni[s]].n_ph;
-        ++w.items[s];
+        const int ni = q >= p.n_units ? 1 : 0;
+        DUO_SET(w, ni, s, ni);
+        DUO_SET(w, tile, s, 2 * (q - ni * p.n_units) + (int)rank);
+        DUO_SET(w, ph, s, 0);
+        DUO_SET(w, nph, s, ni ? nph_net1 : nph_net0);
+        DUO_SET(w, items, s, DUO_SEL(w, items, s) + 1);
         return true;
     };
-#define DUO_WALK_BEGIN(w, ack, wide)                                      \
-    for (int n = 0;; ++n) {                                               \
-        const int s = n & 1;                                              \
-        if (!(w).alive[s]) {                                              \
-            if (!(w).alive[s ^ 1]) break;                                 \
-            continue;                                                     \
-        }                                                                 \
-        if ((w).ph[s] == (w).nph[s] && !take_item(w, s, ack, wide)) {     \
-            if (!(w).alive[s ^ 1]) break;                                 \
-            continue;                                                     \
-        }                                                                 \
-        const int ph = (w).ph[s]++;                                       \
-        const int ni = (w).ni[s];                                         \
-        const NetP& np = p.net[ni];                                       \
-        const PhaseDesc& d = np.ph[ph];                                   \
-        (void)d;
+#define DUO_WALK_BEGIN(w, traced)                                             \
+    for (int n = 0;; ++n) {                                                   \
+        const int s = n & 1;                                                  \
+        if ((traced) && warp == 2 && lane == 0) RLPPO_TRACE(3, 4 * n);        \
+        if (!DUO_SEL(w, alive, s)) {                                          \
+            if (!DUO_SEL(w, alive, s ^ 1)) break;                             \
+            continue;                                                         \
+        }                                                                     \
+        if (DUO_SEL(w, ph, s) == DUO_SEL(w, nph, s) && !next_item(w, s)) {    \
+            if (!DUO_SEL(w, alive, s ^ 1)) break;                             \
+            continue;                                                         \
+        }                                                                     \
+        const int ph = DUO_SEL(w, ph, s);                                     \
+        DUO_SET(w, ph, s, ph + 1);                                            \
+        const int ni = DUO_SEL(w, ni, s);                                     \
+        const int tile_s = DUO_SEL(w, tile, s);                               \
+        const int items_s = DUO_SEL(w, items, s);                             \
+        const bool last_ph = ph + 1 == DUO_SEL(w, nph, s);                    \
+        const NetP& np = p.net[ni];                                           \
+        const PhaseDesc d = s_ph[ni * MAXPH + ph];                            \
+        (void)d; (void)np; (void)tile_s; (void)items_s; (void)last_ph;
 #define DUO_WALK_END }
 
     if (warp == 0) {
@@ -891,48 +898,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
         if (lane == 0) {
             DuoWalk w;
             uint32_t ws = 0, wpar = 0;
-            for (int n = 0;; ++n) {
-                const int s = n & 1;
-                if (!w.alive[s]) {
-                    if (!w.alive[s ^ 1]) break;
-                    continue;
-                }
-                if (w.ph[s] == w.nph[s]) {
-                    const int f = w.fetches++;
-                    int q;
-                    if (leader) {
-                        mbar_wait(&tile_empty[f & 1], ((f >> 1) & 1) ^ 1);
-                        q = (int)atomicAdd(p.sched, 1u);
-                        if (q >= p.n_nets * p.n_units) q = -1;
-                        tile_ring[f & 1] = q;
-                        mbar_arrive(&tile_full[f & 1]);
-                        st_shared_cta_s32(const_cast<int*>(tile_ring) + (f & 1), 1, q);
-                        mbar_arrive_cta_release(&tile_full[f & 1], 1);
-                    } else {
-                        mbar_wait(&tile_full[f & 1], (f >> 1) & 1);
-                        q = tile_ring[f & 1];
-                        mbar_arrive_cta(&tile_empty[f & 1], 0);
-                    }
-                    if (q < 0) {
-                        w.alive[s] = false;
-                        if (!w.alive[s ^ 1]) break;
-                        continue;
-                    }
-                    w.ni[s] = q >= p.n_units ? 1 : 0;
-                    w.tile[s] = 2 * (q - w.ni[s] * p.n_units) + (int)rank;
-                    w.ph[s] = 0;
-                    w.nph[s] = p.net[w.ni[s]].n_ph;
-                    // the item's x tile, straight into the slot's activation buffer once the previous item's stores have read it
-                    const int k_s = w.items[s]++;
-                    mbar_wait(&x_free[s], (k_s & 1) ^ 1);
+            DUO_WALK_BEGIN(w, false)
+                if (ph == 0) {
+                    // the item's x tile, straight into the slot's activation buffer once the previous item's stores have read
+                    // it: item k of the slot (k = items_s - 1) waits for completion k - 1 of x_free
+                    mbar_wait(&x_free[s], (uint32_t)(items_s & 1));
                     if (leader) mbar_expect_tx(&x_full[s], 2u * p.in_kb * KB_BYTES);      // both CTAs' tiles, counted in the leader
                     for (int kb = 0; kb < p.in_kb; ++kb)
-                        tma_load_2d_leaderbar(&maps.x, &x_full[s], smem + s * ACT_BYTES + kb * KB_BYTES, kb * KBLK,
-                                              w.tile[s] * TILE_M);
+                        tma_load_2d_leaderbar(&maps.x, &x_full[s], smem + s * ACT_BYTES + kb * KB_BYTES, kb * KBLK, tile_s * TILE_M);
                 }
-                const int ph = w.ph[s]++;
-                const int ni = w.ni[s];
-                const PhaseDesc& d = p.net[ni].ph[ph];
                 const int nh = d.N >> 1;
                 for (int kb = 0; kb < d.n_kb; ++kb) {
                     mbar_wait(&wempty[ws], wpar ^ 1);
@@ -950,7 +924,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
                         wpar ^= 1;
                     }
                 }
-            }
+            DUO_WALK_END
         }
     } else if (warp == 1) {
         if (lane == 0 && leader) {
@@ -959,13 +933,13 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
             uint32_t ws = 0, wpar = 0;
             uint32_t epi_cnt[2] = {0u, 0u};        // phases of slot s issued so far (every one ends with an epilogue)
             int tr0 = 0;
-            DUO_WALK_BEGIN(w, true, false)
+            DUO_WALK_BEGIN(w, false)
                 RLPPO_TRACE(0, tr0++);       // step start (before waiting for the slot's previous epilogue)
                 const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u;
                 uint8_t* act = smem + s * ACT_BYTES;
                 // this slot's previous epilogue, in both CTAs (every completion of a_done[s] is waited for, in order)
                 if (epi_cnt[s] > 0u) mbar_wait(&a_done[s], (epi_cnt[s] - 1u) & 1u);
-                if (ph == 0) mbar_wait(&x_full[s], (w.items[s] - 1) & 1);       // both CTAs' x tiles
+                if (ph == 0) mbar_wait(&x_full[s], (items_s - 1) & 1);       // both CTAs' x tiles
                 tc_fence_after();
                 if (d.n_kb > 0) {
                     const uint32_t idesc = umma_idesc_bf16(2 * TILE_M, d.N, 0, d.b_mn);
@@ -979,7 +953,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
                             const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
                             const uint64_t bd = d.b_mn ? umma_smem_desc(b_addr + k * (16 * 128), MN_CHUNK, 1024)
                                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
-                            umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if (!(p.dbg & 1)) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                         umma_commit_pair(&wempty[ws]);
                         if (++ws == DUO_NST) {
@@ -1001,9 +975,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
         // ===================== store thread =====================
         if (lane == 0) {
             DuoWalk w;
-            uint32_t cnt[2] = {0u, 0u};            // phases of slot s seen so far
             uint32_t kpar = 0;                      // bit 4s + kb: parity of a_kb[s][kb] to wait for next
-            DUO_WALK_BEGIN(w, true, false)
+            DUO_WALK_BEGIN(w, false)
                 uint8_t* act = smem + s * ACT_BYTES;
                 // k-blocks are stored as the epilogue finishes them: a burst of four 16 KB stores at the end of a phase sat in
                 // the TMA queue ahead of the weight loads (r02aj: the launch is 10 % shorter with the stores switched off)
@@ -1012,17 +985,17 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
                     mbar_wait(&a_kb[b], (kpar >> b) & 1u);
                     kpar ^= 1u << b;
                     if (d.out != NO_STORE) {
-                        if (!p.dbg_nostore) tma_store_2d(&maps.out[ni][d.out], act + kb * KB_BYTES, kb * KBLK, w.tile[s] * TILE_M);
+                        if (!p.dbg_nostore) tma_store_2d(&maps.out[ni][d.out], act + kb * KB_BYTES, kb * KBLK, tile_s * TILE_M);
                         bulk_commit();
                     }
                 }
-                mbar_wait(&a_loc[s], cnt[s] & 1u);          // this CTA's eight warps have finished the phase's epilogue
-                ++cnt[s];
-                if (d.out != NO_STORE && d.rel_kb > 0) {
-                    bulk_wait_read_all();
-                    mbar_arrive(&st_done[s]);
-                }
-                if (ph == np.n_ph - 1) mbar_arrive(&x_free[s]);      // the buffer may take the slot's next x tile
+                // (every phase releases at least one k-block and the last release is the epilogue's last write to the tile)
+                // one completion per phase, storing or not: the epilogue waits for it before the slot's next phase, so it is
+                // never two completions of a_kb ahead of this thread (that would alias their parity: the value net's
+                // store-less tail phase did exactly this when the stores of the other slot were slow)
+                if (d.out != NO_STORE && d.rel_kb > 0) bulk_wait_read_all();
+                mbar_arrive(&st_done[s]);
+                if (last_ph) mbar_arrive(&x_free[s]);      // the buffer may take the slot's next x tile
             DUO_WALK_END
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
@@ -1044,22 +1017,33 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
         auto db_add = [&](int c, float v) { atomicAdd(&s_db[c * 32 + e.lane], v); };
         uint32_t cnt[2] = {0u, 0u};                // phases of slot s seen so far (parity of acc_full[s])
         uint32_t pend = 0, scnt = 0;               // bit s: stores of slot s outstanding / parity of st_done[s]
+        // ReLU mask words of this thread's row half, [slot][hidden layer][k-block][thread]: a per-CTA scratch in global memory
+        // (24 KB, lives in L2); a backward phase fetches its four words BEFORE it waits for its accumulator
+        uint32_t* mask_g = p.mask_scratch + (size_t)blockIdx.x * (2 * DUO_MAXL * 4 * kEpiThreads) + (threadIdx.x - 64);
         int tr1 = 0;
         DuoWalk w;
-        DUO_WALK_BEGIN(w, lane == 0, true)
+        DUO_WALK_BEGIN(w, true)
             uint8_t* act = smem + s * ACT_BYTES;
             e.act = act;
-            e.s_mask = s_mask + s * (DUO_MAXL * 4 * kEpiThreads) + (threadIdx.x - 64);
+            e.s_mask = nullptr;
             const float* s_bias_n = s_bias + ni * (int)BIAS_FLOATS;
-            const int64_t row = (int64_t)w.tile[s] * TILE_M + e.row_in_tile;
+            const int64_t row = (int64_t)tile_s * TILE_M + e.row_in_tile;
             const bool row_ok = row < p.M;
             float dv_keep = s ? dv_slot1 : dv_slot0;
             if (warp == 2 && lane == 0) RLPPO_TRACE(2, tr1);        // arrived at the step
+            uint32_t mpre0 = 0u, mpre1 = 0u, mpre2 = 0u, mpre3 = 0u;
+            if (d.kind == PH_DGRAD || d.kind == PH_VALUE_BWD) {
+                const uint32_t* mp = mask_g + (s * DUO_MAXL + d.layer) * 4 * kEpiThreads;
+                mpre0 = __ldcg(mp);
+                mpre1 = __ldcg(mp + kEpiThreads);
+                mpre2 = __ldcg(mp + 2 * kEpiThreads);
+                mpre3 = __ldcg(mp + 3 * kEpiThreads);
+            }
             mbar_wait(&acc_full[s], cnt[s] & 1u);
             ++cnt[s];
             tc_fence_after();
             if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);      // accumulator complete
-            if (d.smem && ((pend >> s) & 1u)) {      // the tile is overwritten in place: its last stores must have read it
+            if ((pend >> s) & 1u) {      // the slot's previous phase: its stores have read the tile, its releases were seen
                 mbar_wait(&st_done[s], (scnt >> s) & 1u);
                 scnt ^= 1u << s;
                 pend &= ~(1u << s);
@@ -1071,24 +1055,37 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
             int tr5 = 0;
             (void)it;
             (void)tr5;
-#define RLPPO_RELEASE_KB(j)                                   \
-    do {                                                       \
-        fence_proxy_async();                                   \
-        __syncwarp();                                          \
-        if (lane == 0) mbar_arrive(&a_kb[4 * s + (j)]);        \
+    // k-blocks are handed to the store thread in pairs: one proxy fence (it waits for the warp's shared-memory writes, a few
+    // hundred cycles with two warps per scheduler) per 128 columns instead of per 64
+#define RLPPO_RELEASE_KB(j)                                                  \
+    do {                                                                      \
+        if (((j) & 1) || (j) + 1 >= (int)d.rel_kb) {                          \
+            fence_proxy_async();                                              \
+            __syncwarp();                                                     \
+            if (lane == 0) {                                                  \
+                if ((j) & 1) mbar_arrive(&a_kb[4 * s + (j) - 1]);             \
+                mbar_arrive(&a_kb[4 * s + (j)]);                              \
+            }                                                                 \
+        }                                                                     \
     } while (0)
+#define RLPPO_MASK_ST(l, kb, v) __stcg(mask_g + ((s * DUO_MAXL + (l)) * 4 + (kb)) * kEpiThreads, (v))
+#define RLPPO_MASK_LD(l, kb) ((kb) == 0 ? mpre0 : (kb) == 1 ? mpre1 : (kb) == 2 ? mpre2 : mpre3)
 #include "fused_epilogue.inc"
+#undef RLPPO_MASK_ST
+#undef RLPPO_MASK_LD
 #undef RLPPO_RELEASE_KB
             if (s) dv_slot1 = dv_keep;
             else dv_slot0 = dv_keep;
-            if (d.out != NO_STORE) pend |= 1u << s;
+            pend |= 1u << s;
+            if (warp == 2 && lane == 0) RLPPO_TRACE(3, 4 * n + 1);  // epilogue body done
             // the whole phase is done: the tile in act[s] is complete for the slot's next GEMM and for the store thread
+            // (every k-block write above was followed by its own proxy fence + release)
             tc_fence_before();
-            fence_proxy_async();
             __syncwarp();
+            if (warp == 2 && lane == 0) RLPPO_TRACE(3, 4 * n + 2);  // fences done
             if (lane == 0) {
-                mbar_arrive(&a_loc[s]);
-                mbar_arrive_cta(&a_done[s], 0);
+                if (leader) mbar_arrive(&a_done[s]);
+                else mbar_arrive_cta(&a_done[s], 0);
             }
             if (warp == 2 && lane == 0) RLPPO_TRACE(1, tr1++);      // phase done
         DUO_WALK_END
@@ -1119,19 +1116,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
     }
 #undef DUO_WALK_BEGIN
 #undef DUO_WALK_END
+#undef DUO_SEL
+#undef DUO_SET
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_pair(tmem_base, 512);
-    }
-    if (threadIdx.x == 0) {
-        if (atomicAdd(p.sched + 1, 1u) == gridDim.x - 1) {
-            p.sched[0] = 0;
-            p.sched[1] = 0;
-            __threadfence();
-        }
     }
     for (int ni = 0; ni < p.n_nets; ++ni) {
         const NetP& np = p.net[ni];
@@ -1418,20 +1410,23 @@ int launch_duo(const rlppo_fused_net* const* nets, const bool* is_policy, int n_
     const int pairs = num_sms() / 2;
     const int want = (items + 1) / 2;
     const int grid = 2 * (want < pairs ? want : pairs);
+    // (items are dealt out statically inside the kernel: cluster c takes items c, c + grid / 2, ...)
+    for (int ni = 0; ni < n_nets; ++ni)
+        for (int i = 0; i < p.net[ni].n_ph; ++i)
+            RLPPO_CHECK_ARG(p.net[ni].ph[i].rel_kb > 0, "duo kernel: every phase must release at least one k-block");
+    p.sched = nullptr;
     {
-        constexpr int kSlots = 64;
-        static unsigned int* d_sched[16] = {};
-        static unsigned int next_slot[16] = {};
+        // four scratch areas handed out round-robin: launches on different streams may overlap (RLPPO_ONE_LAUNCH=0)
+        static uint32_t* d_mask[16] = {};
+        static unsigned int next_area[16] = {};
         int dev = 0;
         RLPPO_CUDA(cudaGetDevice(&dev));
-        RLPPO_CHECK_ARG(dev >= 0 && dev < 16, "device index out of range");
-        if (d_sched[dev] == nullptr) {
-            RLPPO_CUDA(cudaMalloc(&d_sched[dev], kSlots * 2 * sizeof(unsigned int)));
-            RLPPO_CUDA(cudaMemset(d_sched[dev], 0, kSlots * 2 * sizeof(unsigned int)));
-        }
-        p.sched = d_sched[dev] + 2 * (next_slot[dev]++ % kSlots);
+        const size_t area = (size_t)num_sms() * 2 * DUO_MAXL * 4 * kEpiThreads;
+        if (d_mask[dev] == nullptr) RLPPO_CUDA(cudaMalloc(&d_mask[dev], 4 * area * sizeof(uint32_t)));
+        p.mask_scratch = d_mask[dev] + (next_area[dev]++ % 4) * area;
     }
     p.dbg_nostore = getenv("RLPPO_FUSED_NOSTORE") != nullptr ? 1 : 0;
+    p.dbg = getenv("RLPPO_DUO_DBG") != nullptr ? atoi(getenv("RLPPO_DUO_DBG")) : 0;
     static unsigned long long* d_trace = nullptr;
     const bool tracing = getenv("RLPPO_FUSED_TRACE") != nullptr;
     if (tracing) {
@@ -1449,8 +1444,9 @@ int launch_duo(const rlppo_fused_net* const* nets, const bool* is_policy, int n_
         for (int i = 0; i + 1 < 60 && h[i + 1] != 0; i += 2)
             fprintf(stderr, "  mma  step %d start=%llu issued=+%llu\n", i / 2, h[i] - t0, h[i + 1] - h[i]);
         for (int i = 0; i + 1 < 60 && h[512 + i] != 0; i += 2)
-            fprintf(stderr, "  epi  step %d arrive=%llu acc_full=%llu dur=%llu\n", i / 2, h[1024 + i] - t0, h[512 + i] - t0,
-                    h[512 + i + 1] - h[512 + i]);
+            fprintf(stderr, "  epi  step %d top=%llu arrive=%llu acc_full=%llu dur=%llu body_end=+%llu fences=+%llu arrives=+%llu\n", i / 2,
+                    h[1536 + 2 * i] - t0, h[1024 + i] - t0, h[512 + i] - t0, h[512 + i + 1] - h[512 + i],
+                    h[1536 + 2 * i + 1] - h[512 + i], h[1536 + 2 * i + 2] - h[1536 + 2 * i + 1], h[512 + i + 1] - h[1536 + 2 * i + 2]);
     }
     return RLPPO_OK;
 }
