@@ -29,6 +29,7 @@
 // History (profiles/README_r01.md): v1 kept two tiles in flight with one accumulator each and a 2-stage weight ring; its
 // cycle trace showed the MMA thread taking ~4.7k cycles to issue 2k cycles of MMAs per layer (waiting for weight
 // k-blocks: 64 KB in flight per SM cannot cover the L2 latency) and the epilogue warps idle 27 % of the time.
+#include <type_traits>
 #include <math.h>
 #include <stdlib.h>
 
@@ -211,19 +212,38 @@ __device__ __forceinline__ void pack32_relu(const float (&v)[32], uint32_t (&w)[
 #pragma unroll
     for (int i = 0; i < 16; ++i) w[i] = cvt_relu_bf16x2(v[2 * i], v[2 * i + 1]);
 }
-// ReLU mask of 32 post-ReLU bf16 values (16 packed words, all halves >= +0) as ONE word, one instruction per element:
-// the high bytes (sign + exponent[7:1]) of four values are gathered with a byte permute, "+0x7F" carries a non-zero byte
-// into its top bit, and eight such groups are interleaved by shifting group q right by q.  Element 4q+e lands in bit
-// 8e + 7 - q (relu_mask_bit).  A value counts as positive when its exponent field is >= 2, i.e. h >= 2^-125: activations
-// below 2.4e-38 are treated as zero (the reference tests H > 0 on fp32; nothing in between survives bf16 anyway).
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// ReLU mask of 32 post-ReLU bf16 values (16 packed words, all halves >= +0) as ONE word.  The epilogue is bound by the
+// ALU pipe (LOP3 / PRMT / SHF / ISETP issue every other cycle per scheduler), so the compare runs on the other pipe:
+// HSET2.BF16 turns each packed pair into 0xFFFF / 0x0000 halves (h > 0), one byte permute gathers the top bytes of four of
+// them (0xFF / 0x00) and one LOP3 keeps bit 7 - q of each byte for group q.  Element 4q+e lands in bit 8e + 7 - q
+// (relu_mask_bit); the reference tests H > 0 on fp32, which is the same set once H is rounded to bf16.
 __device__ __forceinline__ uint32_t relu_mask32(const uint32_t (&w)[16]) {
     uint32_t m[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const uint32_t t = __byte_perm(w[2 * q], w[2 * q + 1], 0x7531) + 0x7F7F7F7Fu;
-        m[q & 3] |= (t >> q) & (0x80808080u >> q);
+        uint32_t f0, f1;
+        asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(f0) : "r"(w[2 * q]), "r"(0u));
+        asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(f1) : "r"(w[2 * q + 1]), "r"(0u));
+        m[q & 3] |= prmt_b32(f0, f1, 0x7531u) & (0x80808080u >> q);
     }
     return (m[0] | m[1]) | (m[2] | m[3]);
+}
+// w (16 packed bf16x2 words = 32 values) with the values whose ReLU mask bit is clear zeroed: group q's four bits are moved
+// to the top of the four bytes by one shift (IMAD.SHL, the other pipe), a sign-replicating byte permute expands two of them
+// to a 0xFFFF / 0x0000 pair, and one AND applies it -- two ALU instructions per packed word instead of a bit test and a
+// select per value
+__device__ __forceinline__ void apply_relu_mask32(uint32_t (&w)[16], uint32_t bits) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t t = bits << q;
+        w[2 * q] &= prmt_b32(t, 0u, 0x9988u);        // bytes (sign b0, sign b0, sign b1, sign b1): values 4q, 4q+1
+        w[2 * q + 1] &= prmt_b32(t, 0u, 0xBBAAu);    // values 4q+2, 4q+3
+    }
 }
 __device__ __forceinline__ constexpr int relu_mask_bit(int i) { return 8 * (i & 3) + 7 - (i >> 2); }
 // 32 consecutive columns [32*chunk32, +32) of one row into a K-major SWIZZLE_128B activation tile
@@ -829,6 +849,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
     if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
     pdl_wait();
     pdl_trigger();
+    if (p.trace != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[2048 + 2 * blockIdx.x] = t;      // per-CTA start / end (ns), every CTA
+    }
     for (int i = threadIdx.x; i < p.n_nets * (int)BIAS_FLOATS; i += kThreads) {
         const int ni = i >= (int)BIAS_FLOATS ? 1 : 0;
         const NetP& np = p.net[ni];
@@ -1120,6 +1145,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_duo_kernel(const __grid_con
 #undef DUO_SET
     tc_fence_before();
     __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[2048 + 2 * blockIdx.x + 1] = t;
+    }
     cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
@@ -1441,9 +1471,20 @@ int launch_duo(const rlppo_fused_net* const* nets, const bool* is_policy, int n_
         RLPPO_CUDA(cudaStreamSynchronize(s));
         const unsigned long long t0 = h[0];
         fprintf(stderr, "[duo trace] items=%d (steps alternate slots 0/1)\n", items);
-        for (int i = 0; i + 1 < 60 && h[i + 1] != 0; i += 2)
+        for (int i = 0; i + 1 < 100 && h[i + 1] != 0; i += 2)
             fprintf(stderr, "  mma  step %d start=%llu issued=+%llu\n", i / 2, h[i] - t0, h[i + 1] - h[i]);
-        for (int i = 0; i + 1 < 60 && h[512 + i] != 0; i += 2)
+        {
+            unsigned long long g0 = ~0ull, g1 = 0;
+            for (int b = 0; b < grid; ++b) {
+                if (h[2048 + 2 * b] < g0) g0 = h[2048 + 2 * b];
+                if (h[2048 + 2 * b + 1] > g1) g1 = h[2048 + 2 * b + 1];
+            }
+            fprintf(stderr, "  CTA spans (ns from the first start; start..end), kernel body %llu ns:\n", g1 - g0);
+            for (int b = 0; b < grid; b += 2)
+                fprintf(stderr, "   cluster %d: %llu..%llu%s", b / 2, h[2048 + 2 * b] - g0, h[2048 + 2 * b + 1] - g0, (b / 2) % 4 == 3 ? "\n" : "");
+            fprintf(stderr, "\n");
+        }
+        for (int i = 0; i + 1 < 100 && h[512 + i] != 0; i += 2)
             fprintf(stderr, "  epi  step %d top=%llu arrive=%llu acc_full=%llu dur=%llu body_end=+%llu fences=+%llu arrives=+%llu\n", i / 2,
                     h[1536 + 2 * i] - t0, h[1024 + i] - t0, h[512 + i] - t0, h[512 + i + 1] - h[512 + i],
                     h[1536 + 2 * i + 1] - h[512 + i], h[1536 + 2 * i + 2] - h[1536 + 2 * i + 1], h[512 + i + 1] - h[1536 + 2 * i + 2]);

@@ -555,8 +555,12 @@ def test_row_partition_invariance(pkg):
             assert err < 3e-3, (chunk, it, err)
             assert float((upd_p - upd_f).abs().max()) < 2 * lr_, float((upd_p - upd_f).abs().max())
             assert float((part._v - full._v).norm() / full._v.norm()) < 1e-4
-            for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss", "SB3 Clip Fraction"):
+            for k in ("Policy Entropy", "Mean KL Divergence", "Value Function Loss"):
                 assert abs(rep_p[k] - rep_f[k]) < 1e-5 * max(1.0, abs(rep_f[k])), (k, rep_p[k], rep_f[k])
+            # the clip fraction is a COUNT: inside one learn() the two learners' weights drift apart by the Adam sign flips
+            # described above, and a sample whose ratio sits on the clip boundary may then fall on either side of it
+            k = "SB3 Clip Fraction"
+            assert abs(rep_p[k] - rep_f[k]) < 2.5 / B, (k, rep_p[k], rep_f[k])
             for dst, src in ((part._params, full._params), (part._m, full._m), (part._v, full._v)):
                 dst.copy_(src)
         assert rep_p["Cumulative Model Updates"] == rep_f["Cumulative Model Updates"] == 18
