@@ -421,7 +421,9 @@ int rlppo_gather_batch(const float* actions, const float* logp, const float* val
     RLPPO_CHECK_ARG(!out_states || states, "states ring missing");
     RLPPO_CHECK_ARG(!out_states_bf16 || (states_bf16 && bf16_ld % 8 == 0), "bf16 states ring missing / ld %% 8");
     if (B == 0) return RLPPO_OK;
-    const int threads = 256, per_block = threads / 32 * 8;      // eight samples per warp
+    // 128-thread CTAs of <= 48 registers: one fits on an SM BESIDE a persistent fused-MLP CTA (352 threads x 168 registers leave
+    // 6400), so a gather launched on a second stream runs under the previous step's kernels (ppo_learner._learn_body)
+    const int threads = 128, per_block = threads / 32 * 8;      // eight samples per warp
     const unsigned blocks = (unsigned)((B + per_block - 1) / per_block);
     RLPPO_CUDA(rlppo::launch_pdl(gather_kernel, dim3(blocks), dim3(threads), 0, static_cast<cudaStream_t>(stream), actions,
                                  logp, values, adv, states, states_ld, states_bf16, bf16_ld, obs_dim, capacity, start,

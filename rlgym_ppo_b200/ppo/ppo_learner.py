@@ -203,6 +203,14 @@ class PPOLearner(object):
         # RLPPO_ONE_LAUNCH=0: the two nets of a batch as two fused launches (two streams) instead of one (see _train_chunk)
         self.one_launch = os.environ.get("RLPPO_ONE_LAUNCH", "1") == "1"
         self._side_stream = None
+        # RLPPO_GATHER_PREFETCH=1 (experiment, off by default): the gather of batch i + 1 (independent of the weights) runs on
+        # a second stream -- a parallel branch of the captured graph -- beside the weight-gradient and optimiser launches of
+        # batch i, into the other of two minibatch buffer sets (see _learn_body).  Measured on B200 at the example shape
+        # (profiles/r02be_timeline_prefetch.txt): the 24 us gather does run under the weight-gradient kernel, which then
+        # takes 92 instead of 80 us -- both stream the same HBM -- and the step is unchanged (0.935 vs 0.933 ms).
+        self.gather_prefetch = os.environ.get("RLPPO_GATHER_PREFETCH", "0") == "1"
+        self._gather_stream = None
+        self._mb_alt = None
 
     def _setup_peers(self, dev, n):
         """Gradient arena + flag block in symmetric memory (torch.distributed._symmetric_memory: CUDA peer mappings over
@@ -247,22 +255,40 @@ class PPOLearner(object):
             self._gsum = torch.zeros(n, dtype=torch.float32, device=dev)
 
     # ---- workspaces ----------------------------------------------------------------------------------------
-    def _minibatch_buffers(self, rows):
-        if self._mb is None or self._mb["rows"] < rows:
+    def _minibatch_buffers(self, rows, slot=0):
+        """The gathered minibatch (bf16 observation rows + the per-sample scalars).  Two sets exist when the next batch is
+        gathered while the current one trains (slot 1, see _learn_body)."""
+        cur = self._mb if slot == 0 else self._mb_alt
+        if cur is None or cur["rows"] < rows:
             dev = self._params.device
             f = lambda: torch.empty(rows, dtype=torch.float32, device=dev)  # noqa: E731
             self._mb_gen = getattr(self, "_mb_gen", 0) + 1
             ps = self.policy._stack
-            self._mb = {"rows": rows, "actions": f(), "old_logp": f(), "targets": f(), "adv": f()}
+            cur = {"rows": rows, "actions": f(), "old_logp": f(), "targets": f(), "adv": f()}
             if self._act_w > 1:      # action rows (batch_acts.view(batch_size, -1), ppo_learner.py:131)
-                self._mb["actions"] = torch.empty((rows, self._act_w), dtype=torch.float32, device=dev)
+                cur["actions"] = torch.empty((rows, self._act_w), dtype=torch.float32, device=dev)
             if ps.exact:
                 # "fp32" mode: the f32 observation rows are gathered and split into 3 bf16 parts (both nets read them)
-                self._mb["x32"] = torch.empty((rows, ps.in_dim), dtype=torch.float32, device=dev)
-                self._mb["x"] = torch.zeros((rows, 3 * ps.in_ps), dtype=torch.bfloat16, device=dev)
+                cur["x32"] = torch.empty((rows, ps.in_dim), dtype=torch.float32, device=dev)
+                cur["x"] = torch.zeros((rows, 3 * ps.in_ps), dtype=torch.bfloat16, device=dev)
             else:
-                self._mb["x"] = torch.zeros((rows, ps.in_pad), dtype=torch.bfloat16, device=dev)
-        return self._mb
+                cur["x"] = torch.zeros((rows, ps.in_pad), dtype=torch.bfloat16, device=dev)
+            if slot == 0:
+                self._mb = cur
+            else:
+                self._mb_alt = cur
+        return cur
+
+    def _gather(self, exp, idx, M, mb):
+        """Rows idx[0:M] of the experience rings into a minibatch buffer set, on the current stream."""
+        if self.policy._stack.exact:
+            exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
+                       out_adv=mb["adv"], out_states=mb["x32"])
+            self.policy._stack.stage_rows(mb["x32"][:M], mb["x"])
+            self.launches += 1
+        else:
+            exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
+                       out_adv=mb["adv"], out_states_bf16=mb["x"])
 
     def _sync_lr(self):
         lr = (float(self.policy_optimizer.param_groups[0]["lr"]), float(self.value_optimizer.param_groups[0]["lr"]))
@@ -289,17 +315,13 @@ class PPOLearner(object):
         self._views_sig = sig
 
     # ---- one chunk of one batch: gather -> fwd -> fused heads -> bwd (grads accumulate) -------------------------
-    def _train_chunk(self, exp, idx, M):
+    def _train_chunk(self, exp, idx, M, mb=None, after_fused=None):
+        """`mb`: a minibatch buffer set that already holds the gathered rows (gather prefetch); None: gather here.
+        `after_fused`: called once the fused forward/backward launch is enqueued (where the next batch's gather forks off)."""
         self._sync_operand_views()
-        mb = self._minibatch_buffers(M)
-        if self.policy._stack.exact:
-            exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
-                       out_adv=mb["adv"], out_states=mb["x32"])
-            self.policy._stack.stage_rows(mb["x32"][:M], mb["x"])
-            self.launches += 1
-        else:
-            exp.gather(idx, out_actions=mb["actions"], out_logp=mb["old_logp"], out_values=mb["targets"],
-                       out_adv=mb["adv"], out_states_bf16=mb["x"])
+        if mb is None:
+            mb = self._minibatch_buffers(M)
+            self._gather(exp, idx, M, mb)
         x = mb["x"]
         # (1/mb) * (mb/B), ppo_learner.py:172-177; B = the number of samples one optimiser step averages over
         inv_b = 1.0 / float(parallel.samples_per_step(self.batch_size, self.world_size, self.dp_mode))
@@ -316,9 +338,13 @@ class PPOLearner(object):
                                          self.policy.n_actions, mb["actions"], mb["old_logp"], mb["adv"], inv_b,
                                          float(self.clip_range), float(self.ent_coef), vs.w[-1], mb["targets"], vs.gw[-1],
                                          metrics)
+            if after_fused is not None:
+                after_fused()
             ops.wgrad_multi(ps.fused_wgrad_items(x, wp, head_dy=wp["dz"]) + vs.fused_wgrad_items(x, wv), M)
             self.launches += 3
             return
+        if after_fused is not None:
+            after_fused()
         if both_fused and self.two_streams and _lib._TIMING is None:
             # The two nets are independent until the optimiser step: the value net's chain (fused kernel, weight
             # gradients) runs on a second stream -- a parallel branch of the captured graph.  Each kernel is persistent
@@ -498,6 +524,7 @@ class PPOLearner(object):
         """Everything a captured graph bakes in: buffer identity, workspace generations (addresses), scalar arguments."""
         return (exp.uid, local, chunk, float(self.clip_range), float(self.ent_coef), self.batch_size, self.world_size,
                 self.dp_mode, self.dp_collective, self.precision, self.policy_type, self.policy._stack.fused_ok, self.value_net._stack.fused_ok, getattr(self, "_mb_gen", 0),
+                self.gather_prefetch,
                 getattr(self.policy._stack, "ws_gen", 0), getattr(self.value_net._stack, "ws_gen", 0))
 
     def _learn_body(self, exp, n_batches, local, chunk, tail=True):
@@ -507,10 +534,43 @@ class PPOLearner(object):
         B, R = self.batch_size, self.world_size
         self._before.copy_(self._params)          # update-magnitude baseline (:110-116), stays on the device
         self._tail.zero_()
-        for epoch in range(self.n_epochs):
-            for k in range(n_batches):
-                base = parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0]
-                self._batch_body(exp, self._perm_dev[epoch, base:base + local], local, chunk)
+        steps = [(epoch, parallel.rank_rows(k, B, self.rank, R, self.dp_mode)[0])
+                 for epoch in range(self.n_epochs) for k in range(n_batches)]
+        idx_of = lambda i: self._perm_dev[steps[i][0], steps[i][1]:steps[i][1] + local]  # noqa: E731
+        if self.gather_prefetch and chunk == local and len(steps) > 1:
+            # Software pipeline over the optimiser steps: while step i runs its fused / weight-gradient / optimiser launches
+            # (persistent, one CTA per SM, with idle SMs in every tail), the rows of step i + 1 are gathered on a second
+            # stream into the other buffer set.  The gather reads only the rings and the permutation, never the weights.
+            main = torch.cuda.current_stream()
+            if self._gather_stream is None:
+                self._gather_stream = torch.cuda.Stream(device=self._params.device)
+            side = self._gather_stream
+            sets = (self._minibatch_buffers(local, 0), self._minibatch_buffers(local, 1))
+            self._gather(exp, idx_of(0), local, sets[0])
+            for i in range(len(steps)):
+                joins = []
+
+                def prefetch(i=i, joins=joins):
+                    # Forked BEHIND the fused launch of step i (an event waits for everything before it): the gather shares
+                    # the SMs with the weight-gradient and optimiser launches -- its 128-thread CTAs fit beside their CTAs.
+                    # Forked ahead of the fused launch it only runs first: a persistent CTA needs a whole SM's shared memory
+                    # and waits for the gather's CTAs to drain (timeline r02bd).
+                    fork, join = torch.cuda.Event(), torch.cuda.Event()
+                    fork.record(main)
+                    side.wait_event(fork)
+                    with torch.cuda.stream(side):
+                        self._gather(exp, idx_of(i + 1), local, sets[(i + 1) & 1])
+                        join.record(side)
+                    joins.append(join)
+
+                self._grads.zero_()                                     # ppo_learner.py:131-132
+                self._train_chunk(exp, None, local, mb=sets[i & 1], after_fused=prefetch if i + 1 < len(steps) else None)
+                self._optimizer_step()
+                for join in joins:
+                    main.wait_event(join)
+        else:
+            for i in range(len(steps)):
+                self._batch_body(exp, idx_of(i), local, chunk)
         ops.sqdiff(self._before, self._params, self._seg, self._tail[8:8 + len(self._seg) - 1])
         if tail:
             self._tail_host.copy_(self._tail, non_blocking=True)      # metric sums are global already (see __init__)
