@@ -15,6 +15,8 @@
 //                           (get_backprop_data + ppo_learner.py:153-177 + SURVEY A.3), dz -> bf16
 //  (II) wgrad_kernel    dW[N,K] += dY[M,N]^T * X[M,K]: both operands MN-major (the contraction runs over rows),
 //         split over M across all SMs, fp32 accumulation in TMEM, coalesced fp32 atomics into the grad arena.
+#include <mutex>
+#include <unordered_map>
 #include <math.h>
 
 #include <stdlib.h>
@@ -50,6 +52,36 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     RLPPO_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA operand must be 16-byte aligned");
     RLPPO_CHECK_ARG((ld * 2) % 16 == 0 && cols <= ld && cols >= 1 && rows >= 1, "TMA operand: ld must be a multiple of 8");
     RLPPO_CHECK_ARG(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+    // A descriptor is a pure function of these five values, and an eager training step asks for the same ~50 of them at
+    // every launch (the driver call costs ~1 us each: a quarter of the fused kernel's own duration): keep them.
+    struct Key {
+        const void* base;
+        uint64_t rows, cols, ld;
+        uint32_t box_rows;
+        bool operator==(const Key& o) const {
+            return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+        }
+    };
+    struct KeyHash {
+        size_t operator()(const Key& k) const {
+            uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+            h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+            h ^= (k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+            h ^= (k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
+            return (size_t)(h ^ k.box_rows);
+        }
+    };
+    static std::mutex mu;
+    static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+    const Key key{base, rows, cols, ld, box_rows};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *out = it->second;
+            return RLPPO_OK;
+        }
+    }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {ld * 2};
     cuuint32_t box[2] = {64, box_rows};
@@ -61,6 +93,11 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", (int)r,
                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
         return RLPPO_ERR_CUDA;
+    }
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (cache.size() >= 4096) cache.clear();      // (workspaces that were reallocated leave stale keys behind)
+        cache.emplace(key, *out);
     }
     return RLPPO_OK;
 }
