@@ -933,9 +933,9 @@ wgrad_multi_kernel(const __grid_constant__ WMaps maps, const WMultiParams p) {
                     uint8_t* sx = smem + stage * STAGE;
                     const int mrow = (int)(it.m0 + (int64_t)kb * BLOCK_K);
                     for (int c = 0; c < it.n_x; ++c)
-                        tma_load_2d(&maps.x[it.layer], &full[stage], sx + c * CHUNK, it.k0 + c * 64, mrow);
+                        tma_load_2d_hint(&maps.x[it.layer], &full[stage], sx + c * CHUNK, it.k0 + c * 64, mrow, L2_EVICT_FIRST);
                     for (int c = 0; c < it.n_y; ++c)
-                        tma_load_2d(&maps.dy[it.layer], &full[stage], sx + (4 + c) * CHUNK, it.n0 + c * 64, mrow);
+                        tma_load_2d_hint(&maps.dy[it.layer], &full[stage], sx + (4 + c) * CHUNK, it.n0 + c * 64, mrow, L2_EVICT_FIRST);
                     if (++stage == NST) {
                         stage = 0;
                         phase ^= 1;
