@@ -671,6 +671,56 @@ def test_late_next_states_path_matches_fifo_oracle(pkg):
     assert np.array_equal(results[0][1]["next_states"], results[1][1]["next_states"])
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("M", [50000, 49999, 20480])
+def test_fused_training_launch_back_to_back(pkg, M):
+    """Thirty fused training launches of the example shape replayed from one CUDA graph, three times.  Regression test for a
+    hang: the store thread of the two-tiles-per-CTA kernel could fall two barrier completions behind the epilogue warps on
+    the value net's store-less tail phase (slow stores of the other slot) and then wait on a parity that never comes --
+    seen with the bench shape only, never with the small parity shapes.  Also: the per-row outputs (log-probabilities) do not
+    depend on which launch wrote them."""
+    import contextlib
+    import io
+    from rlgym_ppo_b200 import ops
+    from rlgym_ppo_b200.ppo import ExperienceBuffer, PPOLearner
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        lr = PPOLearner(89, 90, 0, (256,) * 3, (256,) * 3, (0.1, 1.0), M, 1, 3e-4, 3e-4, 0.2, 0.01, M, DEV)
+    lr.use_cuda_graph = False
+    rng = np.random.RandomState(0)
+    buf = ExperienceBuffer(M, 1, DEV)
+    buf.submit_experience(rng.randn(M, 89).astype(np.float32), rng.randint(0, 90, M).astype(np.float32),
+                          np.full(M, -4.5, np.float32), np.zeros(M, np.float32), np.zeros((M, 89), np.float32),
+                          np.zeros(M, np.float32), np.zeros(M), rng.randn(M).astype(np.float32),
+                          rng.randn(M).astype(np.float32))
+    lr.learn(buf)
+    mb = lr._minibatch_buffers(M)
+    ps, vs = lr.policy._stack, lr.value_net._stack
+    wp, wv = ps.workspace(M), vs.workspace(M)
+    x, metrics = mb["x"], lr._step_metrics()
+    logp = torch.zeros(M, device=DEV)
+
+    def launch():
+        ops.policy_value_train_fused(ps.fused_net(x.stride(0), wp, policy_head=True), vs.fused_net(x.stride(0), wv), x, M,
+                                     lr.policy.n_actions, mb["actions"], mb["old_logp"], mb["adv"], 1.0 / M, 0.2, 0.01,
+                                     vs.w[-1], mb["targets"], vs.gw[-1], metrics, logp_out=logp)
+
+    launch()
+    torch.cuda.synchronize()
+    first = logp.clone()
+    graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(30):
+                launch()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(logp).all() and torch.equal(logp, first)
+    assert torch.isfinite(lr._grads).all() and torch.isfinite(metrics).all()
+
+
 @pytest.mark.parametrize("env", [{"RLPPO_FUSED_DUO": "0"}, {"RLPPO_FUSED_DUO": "0", "RLPPO_FUSED_PAIR": "1"}],
                          ids=["single_cta", "cta_pair"])
 def test_other_fused_launch_forms_match(pkg, env):
