@@ -351,9 +351,9 @@ int rlppo_u64_add(uint64_t* d_counter, uint64_t inc, void* stream);
 int rlppo_value_train_fused(const rlppo_fused_net* net, const uint16_t* x, int64_t M, const float* w_head,
                             const float* targets, float inv_batch, float* gw_head, float* values_out,
                             float* metrics, void* stream);
-/* Both nets of a PPO batch in ONE persistent launch: the work items are (net, 128-row tile), policy tiles first, handed
- * out dynamically to one CTA per SM -- 2 x ceil(M/128) items instead of two launches that each end on a partly filled
- * round of tiles.  Arguments as rlppo_policy_train_fused + rlppo_value_train_fused (both nets read the same x; `metrics`
+/* Both nets of a PPO batch in ONE persistent launch: the work items are (net, 128-row tile) -- (net, pair of tiles) for
+ * the two-CTA cluster form -- policy tiles first, dealt out over one CTA per SM: 2 x ceil(M/128) items instead of two
+ * launches that each end on a partly filled round of tiles.  Arguments as rlppo_policy_train_fused + rlppo_value_train_fused (both nets read the same x; `metrics`
  * is the shared 8-float block: policy sums in [0,5), value sums in [5,7)).  ppo_learner.py:146-180 for one minibatch. */
 int rlppo_policy_value_train_fused(const rlppo_fused_net* policy_net, const rlppo_fused_net* value_net,
                                    const uint16_t* x, int64_t M, int n_actions, const float* actions,

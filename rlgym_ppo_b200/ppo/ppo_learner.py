@@ -329,7 +329,7 @@ class PPOLearner(object):
         n = 1
         both_fused = self.policy_type == 0 and self.policy._stack.fused_ok and self.value_net._stack.fused_ok
         if both_fused and self.one_launch:
-            # Both nets in ONE persistent launch: 2 x ceil(M/128) work items (policy tiles first) handed out dynamically to
+            # Both nets in ONE persistent launch: 2 x ceil(M/128) work items (policy tiles first) dealt out over
             # one CTA per SM, then every weight (and bias) gradient of both nets in one launch.  Two launches on two
             # streams (RLPPO_ONE_LAUNCH=0) each end on a partly filled round of tiles: 391 tiles over 148 CTAs.
             ps, vs = self.policy._stack, self.value_net._stack
