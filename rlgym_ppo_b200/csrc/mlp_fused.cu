@@ -773,13 +773,16 @@ __global__ void __launch_bounds__(kThreads, 1) fused_mlp_kernel(const __grid_con
 // -- cp.async.bulk.tensor.cta_group::2 -- so a stage's round trip is MMA completion -> multicast commit -> TMA from L2, with
 // no relay hop), the ReLU masks (24 KB for two slots) live in a per-CTA global scratch that stays in L2 (written by the
 // forward epilogue, prefetched into registers before a backward epilogue waits for its accumulator; thread-local memory
-// was tried and made the backward epilogues 2x slower), which buys a 5-deep ring: with three stages a GEMM step took 3.8k
-// cycles for 2k cycles of MMAs (~1.7k cycles per TMA round trip, r02ai trace), and the x tile of
-// an item is loaded straight into the slot's activation buffer (no staging buffer; its latency hides behind the other
-// slot too).  A GEMM waits for the WHOLE previous epilogue of its slot (one barrier per slot, no k-block hand-over).
+// was tried and made the backward epilogues 2x slower), which buys a 5-deep ring (108.3 us per launch with three
+// stages, 104.0 with five: tools/time_fused.py), and the x tile of an item is loaded straight into the slot's activation
+// buffer (no staging buffer; its latency hides behind the other slot too).  A GEMM waits for the WHOLE previous epilogue
+// of its slot (one barrier per slot, no k-block hand-over).
 // Roles per CTA: producer (x tiles, weight halves), warp 1 = MMA issuer (leader only), eight epilogue warps, store
-// thread.  Items (net, pair of tiles) come from the same global counter; a slot draws a new item when its
-// current one is finished, in walk order, so every role of both CTAs replays the same assignment.
+// thread.  Items (net, pair of tiles) are dealt out statically (see DuoWalk); a slot takes its next item when its current
+// one is finished, in walk order, so every role of both CTAs replays the same assignment.
+// The kernel is bound by its epilogue warps (profiles/README_r02.md section 2b): 168 registers per thread is a hard cap
+// with 11 warps, and a destination register of an in-flight tcgen05.ld must never be spilled -- check STACK:0 / 16
+// (cuobjdump -res-usage) after every change to fused_epilogue.inc.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t DUO_STAGE = WST_BYTES / 2;                      // 16 KB: this CTA's half of a weight k-block
 constexpr int DUO_NST = 5;                                         // 80 KB of weight halves in flight per CTA
