@@ -46,6 +46,8 @@ int num_sms();
 // then block in pdl_wait() until the previous grid has completed and its writes are visible.  A kernel launched without
 // the attribute treats both instructions as no-ops.  pdl_trigger() early in a kernel whose CTAs are all resident lets the
 // dependent grid be scheduled as soon as SMs free up instead of when the last CTA exits.
+// NOTE: data written by the PREVIOUS kernel must not be read with __ldg (ld.global.nc) after pdl_wait(): the compiler treats
+// that as an invariant load and may hoist it above the wait (seen in the optimiser kernel); use __ldcg or a plain load.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 int pdl_mode();   // 0 off, 1 on (RLPPO_PDL), cached

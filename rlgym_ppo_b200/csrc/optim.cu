@@ -176,8 +176,13 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     __shared__ double s_t[kMaxSeg];
     const int64_t total = segs.off[segs.n];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    rlppo::pdl_wait();      // gradients come from the previous kernel of the stream
-    rlppo::pdl_trigger();   // every block of this grid is resident (grid barrier below): the next kernel may queue up
+    // Everything up to pdl_wait() below reads only what EARLIER launches wrote (step counts, p, m, v), never the previous
+    // kernel's output (the gradients): these loads and the double-precision bias corrections run under the tail of the
+    // weight-gradient kernel.  Two things make that safe: this kernel never triggers its own dependents early (no
+    // pdl_trigger), so whatever follows an optimiser step in the stream -- another optimiser step included -- starts after
+    // it has completed; and the gradients are read with ld.global.cg, never __ldg: the compiler treats ld.global.nc as an
+    // invariant load and hoisted it ABOVE griddepcontrol.wait (the graph-replayed and the launch-by-launch iteration then
+    // diverged: test_graph_replayed_iteration_equals_eager).
     if (threadIdx.x < segs.n) {
         // step count read BEFORE the barrier (block 0 writes it after); the double-precision bias corrections are formed
         // here too, off the critical path between the barrier and the update
@@ -186,6 +191,24 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
         s_step_size[threadIdx.x] = (float)((double)lr[threadIdx.x] / (1.0 - pow(beta1d, st)));
         s_bc2_sqrt[threadIdx.x] = (float)sqrt(1.0 - pow(beta2d, st));
     }
+
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
+    // The first kPre elements of every thread (all of them at the example nets: 332k parameters over 83k threads) stay in
+    // registers across the grid barrier: the summed gradient is not re-read, and p, m, v are fetched BEFORE the barrier,
+    // so the update phase starts without a DRAM round trip.
+    constexpr int kPre = 4;
+    float g_pre[kPre], p_pre[kPre], m_pre[kPre], v_pre[kPre];
+#pragma unroll
+    for (int e = 0; e < kPre; ++e) {
+        const int64_t i = gtid + e * gthreads;
+        g_pre[e] = 0.f;
+        if (i < total) {
+            p_pre[e] = __ldcs(p + i);
+            m_pre[e] = __ldcs(m + i);
+            v_pre[e] = __ldcs(v + i);
+        }
+    }
+    rlppo::pdl_wait();      // gradients come from the previous kernel of the stream
 
     // ---- phase 0 (PEERS): every rank's gradients are complete ----
     // This launch is stream-ordered behind the local backward kernels; block 0 tells every peer so, and every block
@@ -209,22 +232,6 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     // everywhere, so the replicas stay identical without a broadcast.  Same thread <-> element mapping and accumulation
     // order as the one-rank kernel; the loads of four elements x all peers are issued before anything is summed: a loop of
     // dependent loads paid one NVLink round trip per peer and element (measured on 8 GPUs: no faster than NCCL).
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (int64_t)gridDim.x * blockDim.x;
-    // The first kPre elements of every thread (all of them at the example nets: 332k parameters over 83k threads) stay in
-    // registers across the grid barrier: the summed gradient is not re-read, and p, m, v are fetched BEFORE the barrier,
-    // so the update phase starts without a DRAM round trip.
-    constexpr int kPre = 4;
-    float g_pre[kPre], p_pre[kPre], m_pre[kPre], v_pre[kPre];
-#pragma unroll
-    for (int e = 0; e < kPre; ++e) {
-        const int64_t i = gtid + e * gthreads;
-        g_pre[e] = 0.f;
-        if (i < total) {
-            p_pre[e] = __ldcs(p + i);
-            m_pre[e] = __ldcs(m + i);
-            v_pre[e] = __ldcs(v + i);
-        }
-    }
     if (MODE == kModeTwoShot) {
         // EXPERIMENTAL (not selected by default; see PPOLearner dp_collective="p2p2"): reduce-scatter + all-gather inside
         // the launch.  (a) this rank sums ITS slice of every peer's arena into its own `gsum` (which the peers have
@@ -328,7 +335,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
 #pragma unroll
         for (int e = 0; e < kPre; ++e) {
             const int64_t i = gtid + e * gthreads;
-            if (i < total) g_pre[e] = __ldg(g + i);
+            if (i < total) g_pre[e] = __ldcg(g + i);      // NOT __ldg: an invariant load may be hoisted above pdl_wait
         }
 #pragma unroll
         for (int e = 0; e < kPre; ++e) {                  // same thread-serial order as the plain loop below
@@ -341,7 +348,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
             }
         }
         for (int64_t i = gtid + kPre * gthreads; i < total; i += gthreads) {
-            const float x = __ldg(g + i);
+            const float x = __ldcg(g + i);
             const int k = seg_of(segs, i);
 #pragma unroll
             for (int j = 0; j < kMaxSeg; ++j)
@@ -428,7 +435,7 @@ norm_clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float*
         if (i < total) update(i, g_pre[e], m_pre[e], v_pre[e], p_pre[e]);
     }
     for (int64_t i = gtid + kPre * gthreads; i < total; i += gthreads)
-        update(i, PEERS ? pr.gsum[i] : g[i], m[i], v[i], p[i]);
+        update(i, PEERS ? pr.gsum[i] : __ldcg(g + i), m[i], v[i], p[i]);
     // ---- leave: the last block resets the counters for the next launch ----
     __syncthreads();
     if (threadIdx.x == 0) {
